@@ -1,0 +1,146 @@
+"""Generate tests/golden/*.npz by running the REAL reference (build container only).
+
+    python -m oracle.make_golden
+
+Every fixture stores the seeded inputs' recipe (seed, shapes) and the reference's
+outputs; weights come from ``oracle.weights.make_state_dict`` (numpy PCG64, portable)
+and are loaded into the reference's own ``model.MISO_1`` / ``model.MISO_3`` with
+``load_state_dict`` (strict), which also proves the key/shape table.
+Fixtures are kept small (a few hundred kB each).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_import, weights  # noqa: E402
+from oracle.miso_net_torch import NetConfig, LAYOUTS  # noqa: E402
+from misonet_b200 import synth  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def build_reference_model(kind, cfg_seed):
+    ns = ref_import.load()
+    en, de = LAYOUTS["REF"]
+    if kind == "miso1":
+        cfg = NetConfig.miso1(2, 6, "REF")
+        mod = ns.model.MISO_1(2, 6, len(en), list(en), list(de), "IN")
+    else:
+        cfg = NetConfig.miso3(1, 6, "REF")
+        mod = ns.model.MISO_3(1, 6, len(en), list(en), list(de), "IN")
+    sd = weights.make_state_dict(cfg, cfg_seed)
+    missing = mod.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert list(mod.state_dict().keys()) == list(sd.keys()), "key order differs from the reference"
+    mod.eval()
+    return mod, cfg, sd
+
+
+def golden_stft():
+    cases = []
+    for i, (n, m, nperseg, noverlap) in enumerate([(1000, 3, 256, 192), (1024, 2, 256, 192), (1500, 2, 512, 384)]):
+        host = ref_import.make_stft_host(nperseg, noverlap)
+        rng = np.random.default_rng(100 + i)
+        x = (0.1 * rng.standard_normal((n, m))).astype(np.float32)
+        spec = host.STFT(x)                              # tester.py:992-1012 -> torch [M,F,T]
+        spec = torch.permute(spec / host.scale, [0, 2, 1]).numpy()   # data.py:77-79
+        cases.append((x, spec, nperseg, noverlap))
+    np.savez_compressed(os.path.join(OUT, "stft_ref.npz"),
+                        **{f"x{i}": c[0] for i, c in enumerate(cases)},
+                        **{f"y{i}": c[1] for i, c in enumerate(cases)},
+                        params=np.array([[c[2], c[3]] for c in cases]))
+
+
+def golden_net():
+    for kind, wseed in (("miso1", 0), ("miso3", 1)):
+        mod, cfg, sd = build_reference_model(kind, wseed)
+        taps = {}
+        hooks = []
+        for name, sub in [("enc0", mod.encoders[0]), ("enc4", mod.encoders[4]), ("enc6", mod.encoders[6]), ("tcn", mod.TCN),
+                          ("dec0", mod.decoders[0]), ("dec2", mod.decoders[2])]:
+            hooks.append(sub.register_forward_hook(lambda m, i, o, name=name: taps.__setitem__(name, o.detach().numpy().copy())))
+        out = {}
+        for b, t in ((2, 20), (1, 11)):
+            mix = synth.random_spec(7 + b, (b, 6, t, 129))
+            with torch.no_grad():
+                if kind == "miso1":
+                    y = mod(torch.from_numpy(mix))
+                else:
+                    a2 = synth.random_spec(17 + b, (b, 1, t, 129))
+                    a3 = synth.random_spec(27 + b, (b, 1, t, 129))
+                    y = mod(torch.from_numpy(mix), torch.from_numpy(a2), torch.from_numpy(a3))
+            out[f"y_b{b}"] = y.numpy()
+            # keep only cheap taps: enc0 is large -> store a strided subsample
+            out[f"enc0_sub_b{b}"] = taps["enc0"].reshape((b,) + taps["enc0"].shape[-3:])[:, :, ::3, ::9]
+            out[f"enc4_b{b}"] = taps["enc4"].reshape((b,) + taps["enc4"].shape[-3:])
+            out[f"enc6_b{b}"] = taps["enc6"].reshape((b,) + taps["enc6"].shape[-3:])
+            out[f"tcn_b{b}"] = taps["tcn"].reshape((b,) + taps["tcn"].shape[-2:])
+            out[f"dec0_b{b}"] = taps["dec0"]
+            out[f"dec2_b{b}"] = taps["dec2"]
+        for h in hooks:
+            h.remove()
+        out["weights_digest"] = np.array(weights.state_dict_digest(sd))
+        np.savez_compressed(os.path.join(OUT, f"net_ref_{kind}.npz"), **out)
+
+
+def golden_mvdr():
+    t = ref_import.make_tester()
+    out = {}
+    for i, (b, f, m, tt) in enumerate([(2, 9, 6, 50), (1, 17, 6, 33)]):
+        src, mix = synth.mvdr_case(300 + i, b, f, m, tt)        # [B,F,M,T] complex64
+        y = t.Apply_Beamforming(src.copy(), mix.copy())
+        out[f"src{i}"], out[f"mix{i}"], out[f"y{i}"] = src, mix, y.numpy()
+    np.savez_compressed(os.path.join(OUT, "mvdr_ref.npz"), **out)
+
+
+def golden_inference():
+    """MISO1_Inference (tester.py:1014-1068) at B=1 -- the only batch size at which
+    the reference's own batch handling is well defined."""
+    mod, cfg, sd = build_reference_model("miso1", 0)
+    t = ref_import.make_tester(model_sep=mod)
+    out = {}
+    for i, ref_ch in enumerate((0, 2)):
+        t.ref_ch = ref_ch
+        mix = synth.random_spec(50 + i, (1, 6, 9, 129))
+        res = t.MISO1_Inference(torch.from_numpy(mix), ref_ch=ref_ch)
+        out[f"mix{i}"] = mix
+        out[f"ref_ch{i}"] = np.array(ref_ch)
+        for k in range(2):
+            out[f"spk{k}_{i}"] = res[k].numpy()
+    np.savez_compressed(os.path.join(OUT, "miso1_inference_ref.npz"), **out)
+
+
+def golden_losses():
+    ns = ref_import.load()
+    out = {}
+    for i, (b, tt, f) in enumerate([(3, 14, 33), (1, 7, 129)]):
+        est = synth.random_spec(70 + i, (b, 2, tt, f))
+        ref = synth.random_spec(80 + i, (b, 2, tt, f))
+        # make utterance 0 prefer the swapped permutation
+        ref[0] = est[0, ::-1] + 0.05 * ref[0]
+        refs = [torch.from_numpy(ref[:, k].copy()) for k in range(2)]
+        loss = ns.criterion.loss_uPIT(2, torch.from_numpy(est), refs)
+        e1 = synth.random_spec(90 + i, (b, 1, tt, f))
+        r1 = synth.random_spec(95 + i, (b, 1, tt, f))
+        le = ns.criterion.loss_Enhance(torch.from_numpy(e1), torch.from_numpy(r1))
+        out.update({f"est{i}": est, f"ref{i}": ref, f"upit{i}": loss.numpy(), f"e1_{i}": e1, f"r1_{i}": r1, f"enh{i}": le.numpy()})
+    np.savez_compressed(os.path.join(OUT, "loss_ref.npz"), **out)
+
+
+def main():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    os.makedirs(OUT, exist_ok=True)
+    golden_stft()
+    golden_mvdr()
+    golden_losses()
+    golden_net()
+    golden_inference()
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+if __name__ == "__main__":
+    main()

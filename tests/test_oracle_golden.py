@@ -1,0 +1,106 @@
+"""Pin the CPU oracle (oracle/) against outputs of the real reference
+(tests/golden/*.npz, produced by oracle/make_golden.py in the build container)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from oracle import miso_np, weights
+from oracle import miso_net_torch as mnt
+from misonet_b200 import synth
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def test_stft_matches_reference():
+    g = _load("stft_ref.npz")
+    for i, (nperseg, noverlap) in enumerate(g["params"]):
+        y = miso_np.stft(g[f"x{i}"], int(nperseg), int(noverlap))
+        assert y.shape == g[f"y{i}"].shape
+        assert y.shape[1] == miso_np.stft_num_frames(g[f"x{i}"].shape[0], int(nperseg), int(noverlap))
+        assert rel_err(y, g[f"y{i}"]) < 2e-6
+
+
+def test_mvdr_matches_reference():
+    g = _load("mvdr_ref.npz")
+    for i in range(2):
+        y = miso_np.apply_beamforming(g[f"src{i}"], g[f"mix{i}"])
+        assert y.dtype == np.complex64 and y.shape == g[f"y{i}"].shape
+        assert rel_err(y, g[f"y{i}"]) < 1e-5
+
+
+def test_mvdr_phase_scan_equivalence():
+    """The sequential recurrence (tester.py:1163-1166) equals a prefix product of unit
+    phasors on the uncorrected vectors -- the form the CUDA kernel uses."""
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal((2, 40, 6)) + 1j * rng.standard_normal((2, 40, 6))
+    seq = miso_np.phase_correction(d)
+    c = np.sum(d[:, 1:] * d[:, :-1].conj(), axis=-1)
+    ph = np.concatenate([np.ones((2, 1), complex), np.cumprod(np.exp(-1j * np.angle(c)), axis=1)], axis=1)
+    assert rel_err(d * ph[..., None], seq) < 1e-12
+
+
+def test_losses_match_reference():
+    g = _load("loss_ref.npz")
+    for i in range(2):
+        loss, idx, _ = miso_np.loss_upit(g[f"est{i}"], g[f"ref{i}"])
+        assert abs(loss - g[f"upit{i}"]) <= 2e-6 * abs(g[f"upit{i}"])
+        assert idx[0] == 1          # utterance 0 was built to prefer the swapped order
+        le = miso_np.loss_enhance(g[f"e1_{i}"], g[f"r1_{i}"])
+        assert abs(le - g[f"enh{i}"]) <= 2e-6 * abs(g[f"enh{i}"])
+
+
+@pytest.mark.parametrize("kind", ["miso1", "miso3"])
+def test_net_matches_reference(kind):
+    g = _load(f"net_ref_{kind}.npz")
+    cfg = mnt.NetConfig.miso1() if kind == "miso1" else mnt.NetConfig.miso3()
+    sd = weights.make_state_dict(cfg, 0 if kind == "miso1" else 1)
+    assert weights.state_dict_digest(sd) == str(g["weights_digest"])
+    for b, t in ((2, 20), (1, 11)):
+        mix = torch.from_numpy(synth.random_spec(7 + b, (b, 6, t, 129)))
+        if kind == "miso1":
+            x = torch.cat((mix.real, mix.imag), dim=1)
+        else:
+            a2 = torch.from_numpy(synth.random_spec(17 + b, (b, 1, t, 129)))
+            a3 = torch.from_numpy(synth.random_spec(27 + b, (b, 1, t, 129)))
+            x = torch.cat((mix.real, a2.real, a3.real, mix.imag, a2.imag, a3.imag), dim=1)
+        with torch.no_grad():
+            y, taps = mnt.net_forward(sd, cfg, x, return_taps=True)
+        yc = mnt._to_complex(y).numpy()
+        assert rel_err(yc, g[f"y_b{b}"]) < 5e-6
+        assert rel_err(taps["enc0"].numpy()[:, :, ::3, ::9], g[f"enc0_sub_b{b}"]) < 5e-6
+        for name in ("enc4", "enc6", "dec0", "dec2"):
+            assert rel_err(taps[name].numpy(), g[f"{name}_b{b}"]) < 5e-6, name
+        assert rel_err(taps["tcn"].numpy(), g[f"tcn_b{b}"]) < 5e-6
+
+
+def test_miso1_inference_matches_reference():
+    g = _load("miso1_inference_ref.npz")
+    cfg = mnt.NetConfig.miso1()
+    sd = weights.make_state_dict(cfg, 0)
+    for i in range(2):
+        out, _ = mnt.miso1_inference(sd, cfg, torch.from_numpy(g[f"mix{i}"]), int(g[f"ref_ch{i}"]))
+        for k in range(2):
+            assert rel_err(out[k].numpy(), g[f"spk{k}_{i}"]) < 5e-6
+
+
+def test_paper_layout_shapes():
+    """PAPER layout (8 blocks, 257 bins, TCN width 384) runs and reduces F to 1;
+    parameter count matches SURVEY.md section 8(c) (8,579,704)."""
+    cfg = mnt.NetConfig.miso1(layout="PAPER")
+    shapes = weights.param_shapes(cfg)
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 8579704
+    sd = weights.make_state_dict(cfg, 3)
+    mix = torch.from_numpy(synth.random_spec(1, (1, 6, 6, 257)))
+    y = mnt.miso1_forward(sd, cfg, mix)
+    assert y.shape == (1, 2, 6, 257) and y.dtype == torch.complex64
+    assert torch.isfinite(torch.view_as_real(y)).all()
+
+
+def test_ref_param_count():
+    assert sum(int(np.prod(s)) for s in weights.param_shapes(mnt.NetConfig.miso1()).values()) == 2587384
+    assert sum(int(np.prod(s)) for s in weights.param_shapes(mnt.NetConfig.miso3()).values()) == 2587382
