@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the MISO hot path on B200 (see DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workloads (BASELINE.json configs):
+  miso1_paper   (default, configs[1]) MISO_1 separation forward, per-GPU batch 16 x 6 mics x 257 bins x
+                500 frames, 8-block "paper" layout (model.py:13-14,30 comments)
+  miso1_ref     the same on the shipped 7-block / 129-bin / 501-frame layout
+  pipeline_ref  (configs[2]) STFT -> MISO1 x6 shifts -> align -> MVDR x2 -> MISO3 x2, per-GPU batch 32, REF layout
+
+One "step" = one pass of the workload over one synthetic batch per GPU.  `value` is whole-job
+frames/s with inputs resident in HBM; `e2e` is the same through the public API with pinned host
+buffers (H2D of the inputs and D2H of the result inside the timed region).  Under torchrun every
+rank processes its own batch (weak scaling, no data-path collective); time = max over ranks.
+
+--impl reference times the reference's own CPU algorithm for the same workload on the host cores.
+/root/reference does not exist on the GPU box, so this is the oracle port (oracle/miso_net_torch.py,
+pinned to the real reference by tests/golden); rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYOUTS = {
+    "REF": ([24, 32, 32, 32, 32, 64, 128], [128, 64, 32, 32, 32, 32, 24]),
+    "PAPER": ([24, 32, 32, 32, 32, 64, 128, 384], [384, 128, 64, 32, 32, 32, 32, 24]),
+}
+WORKLOADS = {
+    "miso1_paper": dict(layout="PAPER", B=16, M=6, T=500, F=257, kind="miso1",
+                        desc="MISO1 separation fwd, batch 16 x 6ch x 257bin x 500fr per GPU (BASELINE configs[1])"),
+    "miso1_ref": dict(layout="REF", B=16, M=6, T=501, F=129, kind="miso1",
+                      desc="MISO1 separation fwd, batch 16 x 6ch x 129bin x 501fr per GPU (shipped config shape)"),
+    "pipeline_ref": dict(layout="REF", B=32, M=6, T=501, F=129, kind="pipeline", n_samples=32000,
+                         desc="STFT->MISO1x6->align->MVDRx2->MISO3x2, batch 32 per GPU (BASELINE configs[2], REF shape)"),
+}
+# algorithmic conv-stack work per utterance, SURVEY.md section 8(d) / appendix A
+GFLOP_PER_UTT = {"REF": 75.151, "PAPER": 163.37}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            d = json.load(open(p))
+            return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                        source="measured (MEASURED_PEAKS.json, sustained bf16)")
+        except Exception:
+            pass
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+def rand_spec(seed, shape, device):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(*shape, 2, generator=g, dtype=torch.float32)
+    return torch.view_as_complex(x).contiguous().to(device) if device != "pinned" else torch.view_as_complex(x).contiguous().pin_memory()
+
+
+def oracle_state_dict(kind, layout, seed):
+    from oracle import weights
+    from oracle import miso_net_torch as mnt
+    cfg = mnt.NetConfig.miso1(layout=layout) if kind == "miso1" else mnt.NetConfig.miso3(layout=layout)
+    return cfg, weights.make_state_dict(cfg, seed)
+
+
+def make_state_dict_np(model, seed):
+    """Seeded random weights with PyTorch-default magnitudes, generated without touching oracle/."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        if k.endswith("gamma"):
+            sd[k] = torch.ones_like(v)
+        elif k.endswith("beta"):
+            sd[k] = torch.zeros_like(v)
+        elif v.numel() == 1:
+            sd[k] = torch.full_like(v, 0.25)
+        else:
+            fan = v[0].numel() if v.dim() > 1 else 64
+            sd[k] = (torch.rand(v.shape, generator=g) * 2 - 1) / np.sqrt(fan)
+    return sd
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(", ") for r in open(self.tmp.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower() == "active":
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------ ours
+def run_ours(args, wl, rank, world, local):
+    from misonet_b200 import _lib, distributed as D
+    from misonet_b200.model import MISO_1, MISO_3
+    from misonet_b200 import pipeline
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    en, de = LAYOUTS[wl["layout"]]
+    B, M, T, F = wl["B"], wl["M"], wl["T"], wl["F"]
+    m1 = MISO_1(2, M, len(en), list(en), list(de), "IN")
+    m1.load_state_dict(make_state_dict_np(m1, 0))
+    m1 = m1.cuda(dev).eval()
+    if wl["kind"] == "pipeline":
+        m3 = MISO_3(1, M, len(en), list(en), list(de), "IN")
+        m3.load_state_dict(make_state_dict_np(m3, 1))
+        m3 = m3.cuda(dev).eval()
+        pipe = pipeline.MisoBfMiso(m1, m3)
+        g = torch.Generator().manual_seed(100 + rank)
+        host_in = (0.05 * torch.randn(B, wl["n_samples"], M, generator=g)).pin_memory()
+        dev_in = host_in.to(dev)
+
+        def step(x):
+            return pipe(x)["enhanced"]
+    else:
+        host_in = rand_spec(100 + rank, (B, M, T, F), "pinned")
+        dev_in = host_in.to(dev)
+
+        def step(x):
+            return m1(x)
+
+    frames_per_step = B * T
+    with torch.no_grad():
+        out = step(dev_in)
+        host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        for _ in range(max(args.warmup, 3) - 1):
+            step(dev_in)
+        torch.cuda.synchronize()
+
+        # ---- resident-input throughput (value) with per-launch conv timing (roofline) ----
+        sampler = ClockSampler(local) if rank == 0 else None
+        lib.miso_prof_enable(1)
+        import ctypes
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        torch.cuda.synchronize()
+        launches0 = _lib.launch_count()
+        e0.record()
+        for _ in range(args.steps):
+            step(dev_in)
+        e1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - launches0
+        lib.miso_prof_enable(0)
+        cm, cf, cb, cn = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
+        _lib.check(lib.miso_prof_collect(ctypes.byref(cm), ctypes.byref(cf), ctypes.byref(cb), ctypes.byref(cn)))
+        clocks = sampler.stop() if sampler else None
+
+        # ---- end to end through the public API: pinned host in -> H2D -> step -> D2H ----
+        for _ in range(1):
+            host_out.copy_(step(host_in.to(dev, non_blocking=True)), non_blocking=True)
+        torch.cuda.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            host_out.copy_(step(host_in.to(dev, non_blocking=True)), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        ms_e2e = e0.elapsed_time(e1)
+
+    ms = D.max_over_ranks(ms, dev)
+    ms_e2e = D.max_over_ranks(ms_e2e, dev)
+    if rank != 0:
+        return None
+    pk = peaks()
+    total_frames = frames_per_step * world * args.steps
+    conv_ms, conv_flops, conv_launches = cm.value, cf.value, cn.value
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    line = {
+        "metric": "frames/sec MISO-BF-MISO fwd 6ch/257bin at 1/2/4/8 GPU; SI-SDR vs ref",
+        "value": total_frames / (ms * 1e-3),
+        "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (seeded random spectrograms / waveforms, seeded random weights)",
+        "config": {"workload": wl["desc"], "layout": wl["layout"], "per_gpu_batch": B, "global_batch": B * world,
+                   "frames": T, "bins": F, "mics": M, "parallelism": f"utterance-sharded x{world}, no data-path collective",
+                   "conv_mode": "fp32 FMA (parity mode)",
+                   "l2": "activation working set per step is several GB (>> 126 MB L2), so every step starts cold"},
+        "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s",
+                "h2d_bytes_per_step": int(host_in.numel() * host_in.element_size()),
+                "d2h_bytes_per_step": int(host_out.numel() * host_out.element_size())},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_fp32_kernel (3x3 conv / deconv / pointwise implicit GEMM family)",
+                     "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+                     "launches": int(conv_launches), "kernel_ms_per_step": conv_ms / args.steps,
+                     "share_of_step": conv_ms / ms if ms > 0 else None,
+                     "note": "algorithmic 2*MAC of the conv launches / summed CUDA-event time of those launches, "
+                             "measured inside the timed region; fp32 FMA pipe, tensor cores not yet used"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(wl, steps=1)
+    return line
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_baseline(wl, steps=1, warmup=1, utts=1):
+    """The reference's CPU algorithm (oracle port) for the same workload on a bounded sample."""
+    from oracle import miso_net_torch as mnt
+    from oracle import miso_np
+    torch.set_num_threads(os.cpu_count() or 1)
+    layout, M, T, F = wl["layout"], wl["M"], wl["T"], wl["F"]
+    cfg1, sd1 = oracle_state_dict("miso1", layout, 0)
+    mix = rand_spec(7, (utts, M, T, F), "cpu")
+    if wl["kind"] == "pipeline":
+        cfg3, sd3 = oracle_state_dict("miso3", layout, 1)
+
+        def step():
+            m1, _ = mnt.miso1_inference(sd1, cfg1, mix, 0)
+            for s in range(2):
+                src = m1[s].permute(0, 3, 1, 2).numpy()
+                bf = miso_np.apply_beamforming(src, mix.permute(0, 3, 1, 2).numpy())
+                mnt.miso3_forward(sd3, cfg3, mix, torch.from_numpy(bf).unsqueeze(1), m1[s][:, 0:1])
+    else:
+        def step():
+            mnt.miso1_forward(sd1, cfg1, mix)
+    for _ in range(warmup):
+        step()
+    best = float("inf")
+    t_all0 = time.perf_counter()
+    for _ in range(max(steps, 1)):
+        t0 = time.perf_counter()
+        step()
+        best = min(best, time.perf_counter() - t0)
+    total = time.perf_counter() - t_all0
+    return {"value": utts * T / best, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{utts} utterance(s) of the same workload ({wl['layout']} layout, {T} frames x {F} bins), "
+                      f"fp32 torch CPU ops, best of {max(steps, 1)} after {warmup} warm-up",
+            "seconds_best": best, "seconds_total": total}
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return None
+    steps = max(1, min(args.steps, 5))
+    cb = cpu_baseline(wl, steps=steps, warmup=max(1, min(args.warmup, 2)))
+    return {
+        "impl": "reference",
+        "metric": "frames/sec MISO-BF-MISO fwd 6ch/257bin at 1/2/4/8 GPU; SI-SDR vs ref",
+        "value": cb["value"], "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": cb["seconds_best"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (seeded random spectrograms, seeded random weights)",
+        "config": {"workload": wl["desc"], "layout": wl["layout"], "frames": wl["T"], "bins": wl["F"], "mics": wl["M"],
+                   "note": "reference CPU algorithm (oracle port of model.py/tester.py; /root/reference is absent on the GPU "
+                           "box), all host threads, each step = 1 utterance of the workload"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="miso1_paper", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        line = run_reference(args, wl, rank, world)
+    else:
+        from misonet_b200 import distributed as D
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+        D.init_from_env("nccl")
+        line = run_ours(args, wl, rank, world, local)
+        if world > 1:
+            torch.distributed.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

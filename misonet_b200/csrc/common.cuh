@@ -1,0 +1,80 @@
+// Shared helpers for the misonet_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/misonet_b200.h"
+
+namespace miso {
+
+// ---- error reporting (thread-local message, C ABI returns an int) ---------------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+inline int cuda_fail(cudaError_t e, const char *what) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MISO_E_CUDA;
+}
+
+#define MISO_CUDA(call)                                                      \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) return miso::cuda_fail(_e, #call);            \
+    } while (0)
+
+// call after every kernel launch
+#define MISO_LAUNCHED(name)                                                  \
+    do {                                                                     \
+        miso::g_launch_count.fetch_add(1, std::memory_order_relaxed);        \
+        cudaError_t _e = cudaGetLastError();                                 \
+        if (_e != cudaSuccess) return miso::cuda_fail(_e, name);             \
+    } while (0)
+
+#define MISO_REQUIRE(cond, ...)                                              \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            miso::set_error(__VA_ARGS__);                                    \
+            return MISO_E_ARG;                                               \
+        }                                                                    \
+    } while (0)
+
+// optional per-launch event timing of the dominant kernel family (runtime.cu)
+bool prof_enabled();
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st, double flops, double bytes);
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device helpers -----------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+
+// Statistics convention: every activation channel owns two fp64 accumulators
+// (sum, sum of squares).  A negative sum-of-squares marks a channel that is consumed
+// raw (no normalisation in the reference at that point).
+__device__ __forceinline__ float2 affine_from_sums(double s, double q, double inv_n, double eps) {
+    if (q < 0.0) return make_float2(1.f, 0.f);
+    double mean = s * inv_n;
+    double var = q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double r = rsqrt(var + eps);
+    return make_float2((float)r, (float)(-mean * r));
+}
+
+}  // namespace miso

@@ -1,0 +1,436 @@
+// Per-frequency MVDR beamformer (M1..M7 of SURVEY.md section 8(a); reference
+// tester.py:1071-1167, 1211-1228 and its two verbatim twins).
+//
+// Four kernels, all HBM-bound or trivially small:
+//   scm_kernel    streams source + mixture once (coalesced along f, the contiguous axis of
+//                 [B,M,T,F]) and accumulates both spatial covariance matrices per (b,s,f);
+//                 T is split across CTAs and the partial sums are combined in a fixed order.
+//   eig_kernel    Hermitian Jacobi eigen-decomposition per (b,s,f) -> principal eigenvector
+//                 (np.linalg.eigh + argmax, tester.py:1107-1115) -> reference-mic and
+//                 sqrt(M/||d||) normalisation (tester.py:1119-1123, reproduced as written).
+//   solve_kernel  phase correction as a prefix product of unit phasors (equivalent to the
+//                 sequential recurrence of tester.py:1163-1166), diagonal loading,
+//                 pivoted 6x6 complex solve and w = u / (d^H u) (tester.py:1211-1225).
+//   apply_kernel  y[t] = sum_m conj(w[m]) x[m,t] for all sources in one pass over the mixture.
+#include "common.cuh"
+
+namespace miso {
+namespace {
+
+template <int M>
+struct Tri {
+    static constexpr int N = M * (M + 1) / 2;  // complex entries of the upper triangle
+    static constexpr int NV = 4 * N;           // floats per (b,s,f): re/im x {source, noise}
+};
+
+constexpr int kFx = 32, kTy = 8;
+
+template <int M>
+__global__ void __launch_bounds__(kFx *kTy) scm_kernel(const float2 *__restrict__ src, int64_t src_ss,
+                                                        const float2 *__restrict__ mix, int64_t sb, int64_t sm, int64_t st,
+                                                        int64_t sf, float *__restrict__ partial, int S, int B, int T, int F,
+                                                        int tsplit) {
+    constexpr int N = Tri<M>::N, NV = Tri<M>::NV;
+    __shared__ float red[NV][kFx];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int f = blockIdx.x * kFx + tx;
+    const int split = blockIdx.y;
+    const int b = blockIdx.z;
+    const int tc = (T + tsplit - 1) / tsplit;
+    const int t0 = split * tc, t1 = min(T, t0 + tc);
+    const bool fok = f < F;
+    const float2 *mix_b = mix + b * sb + (int64_t)f * sf;
+
+    for (int s = 0; s < S; ++s) {
+        float acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+        if (fok) {
+            const float2 *src_b = src + s * src_ss + b * sb + (int64_t)f * sf;
+            for (int t = t0 + ty; t < t1; t += kTy) {
+                float2 x[M], y[M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    float2 mx = mix_b[m * sm + t * st];
+                    float2 sx = src_b[m * sm + t * st];
+                    x[m] = sx;
+                    y[m] = make_float2(mx.x - sx.x, mx.y - sx.y);  // noise = mix - source (tester.py:1095)
+                }
+                int k = 0;
+#pragma unroll
+                for (int i = 0; i < M; ++i)
+#pragma unroll
+                    for (int j = i; j < M; ++j) {
+                        // Phi[i][j] += x_i conj(x_j)
+                        acc[4 * k + 0] = fmaf(x[i].x, x[j].x, fmaf(x[i].y, x[j].y, acc[4 * k + 0]));
+                        acc[4 * k + 1] = fmaf(x[i].y, x[j].x, fmaf(-x[i].x, x[j].y, acc[4 * k + 1]));
+                        acc[4 * k + 2] = fmaf(y[i].x, y[j].x, fmaf(y[i].y, y[j].y, acc[4 * k + 2]));
+                        acc[4 * k + 3] = fmaf(y[i].y, y[j].x, fmaf(-y[i].x, y[j].y, acc[4 * k + 3]));
+                        ++k;
+                    }
+            }
+        }
+        // ordered reduction over the 8 time lanes
+        for (int r = 0; r < kTy; ++r) {
+            if (ty == r) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) red[i][tx] = (r == 0 ? 0.f : red[i][tx]) + acc[i];
+            }
+            __syncthreads();
+        }
+        if (fok) {
+            float *dst = partial + (((size_t)(s * B + b) * tsplit + split) * NV) * F + f;  // problem index = s*B + b
+            for (int i = ty; i < NV; i += kTy) dst[(size_t)i * F] = red[i][tx];
+        }
+        __syncthreads();
+    }
+    (void)N;
+}
+
+// sum the T-split partials in a fixed order; which = 0 source, 1 noise.  Returns the full
+// Hermitian matrix scaled by 1/T (the 0.5*(R+R^H) of tester.py:1092,1100 is implicit: only
+// the upper triangle is accumulated and the diagonal is real by construction).
+template <int M>
+__device__ void load_scm(const float *__restrict__ partial, int bs, int f, int F, int tsplit, int which, double inv_t,
+                         double (*Ar)[M], double (*Ai)[M]) {
+    constexpr int NV = Tri<M>::NV;
+    int k = 0;
+    for (int i = 0; i < M; ++i)
+        for (int j = i; j < M; ++j) {
+            double re = 0.0, im = 0.0;
+            for (int sp = 0; sp < tsplit; ++sp) {
+                const float *p = partial + (((size_t)bs * tsplit + sp) * NV) * F + f;
+                re += (double)p[(size_t)(4 * k + 2 * which) * F];
+                im += (double)p[(size_t)(4 * k + 2 * which + 1) * F];
+            }
+            re *= inv_t;
+            im *= inv_t;
+            if (i == j) im = 0.0;
+            Ar[i][j] = re;
+            Ai[i][j] = im;
+            Ar[j][i] = re;
+            Ai[j][i] = -im;
+            ++k;
+        }
+}
+
+template <int M>
+__global__ void __launch_bounds__(64) eig_kernel(const float *__restrict__ partial, double2 *__restrict__ steer, int nprob,
+                                                 int F, int T, int tsplit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nprob) return;
+    const int f = i % F, bs = i / F;
+    double Ar[M][M], Ai[M][M], Vr[M][M], Vi[M][M];
+    load_scm<M>(partial, bs, f, F, tsplit, 0, 1.0 / (double)T, Ar, Ai);
+    for (int p = 0; p < M; ++p)
+        for (int q = 0; q < M; ++q) {
+            Vr[p][q] = p == q ? 1.0 : 0.0;
+            Vi[p][q] = 0.0;
+        }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int p = 0; p < M; ++p) {
+            dg += Ar[p][p] * Ar[p][p];
+            for (int q = p + 1; q < M; ++q) off += Ar[p][q] * Ar[p][q] + Ai[p][q] * Ai[p][q];
+        }
+        if (off <= 1e-30 * dg || off == 0.0) break;
+        for (int p = 0; p < M - 1; ++p)
+            for (int q = p + 1; q < M; ++q) {
+                const double xr = Ar[p][q], xi = Ai[p][q];
+                const double ax = sqrt(xr * xr + xi * xi);
+                if (ax == 0.0) continue;
+                const double tau = (Ar[q][q] - Ar[p][p]) / (2.0 * ax);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+                const double er = xr / ax, ei = -xi / ax;  // e = conj(x)/|x|
+                const double ser = s * er, sei = s * ei, cer = c * er, cei = c * ei;
+                // columns: X[:,p] = c X[:,p] - s e X[:,q];  X[:,q] = s X[:,p] + c e X[:,q]
+                for (int r = 0; r < M; ++r) {
+                    double pr = Ar[r][p], pi = Ai[r][p], qr = Ar[r][q], qi = Ai[r][q];
+                    Ar[r][p] = c * pr - (ser * qr - sei * qi);
+                    Ai[r][p] = c * pi - (ser * qi + sei * qr);
+                    Ar[r][q] = s * pr + (cer * qr - cei * qi);
+                    Ai[r][q] = s * pi + (cer * qi + cei * qr);
+                    pr = Vr[r][p], pi = Vi[r][p], qr = Vr[r][q], qi = Vi[r][q];
+                    Vr[r][p] = c * pr - (ser * qr - sei * qi);
+                    Vi[r][p] = c * pi - (ser * qi + sei * qr);
+                    Vr[r][q] = s * pr + (cer * qr - cei * qi);
+                    Vi[r][q] = s * pi + (cer * qi + cei * qr);
+                }
+                // rows: A[p,:] = c A[p,:] - s conj(e) A[q,:];  A[q,:] = s A[p,:] + c conj(e) A[q,:]
+                for (int r = 0; r < M; ++r) {
+                    double pr = Ar[p][r], pi = Ai[p][r], qr = Ar[q][r], qi = Ai[q][r];
+                    Ar[p][r] = c * pr - (ser * qr + sei * qi);
+                    Ai[p][r] = c * pi - (ser * qi - sei * qr);
+                    Ar[q][r] = s * pr + (cer * qr + cei * qi);
+                    Ai[q][r] = s * pi + (cer * qi - cei * qr);
+                }
+                Ar[p][q] = Ai[p][q] = Ar[q][p] = Ai[q][p] = 0.0;
+                Ai[p][p] = Ai[q][q] = 0.0;
+            }
+    }
+    int kmax = 0;
+    for (int p = 1; p < M; ++p)
+        if (Ar[p][p] > Ar[kmax][kmax]) kmax = p;
+    // d = v / v[0];  d *= sqrt(M / ||d||_2)     (tester.py:1119-1123)
+    const double v0r = Vr[0][kmax], v0i = Vi[0][kmax];
+    const double den = v0r * v0r + v0i * v0i;
+    double dr[M], di[M], nrm = 0.0;
+    for (int m = 0; m < M; ++m) {
+        const double vr = Vr[m][kmax], vi = Vi[m][kmax];
+        dr[m] = (vr * v0r + vi * v0i) / den;
+        di[m] = (vi * v0r - vr * v0i) / den;
+        nrm += dr[m] * dr[m] + di[m] * di[m];
+    }
+    const double g = sqrt((double)M / sqrt(nrm));
+    for (int m = 0; m < M; ++m) steer[((size_t)bs * F + f) * M + m] = make_double2(dr[m] * g, di[m] * g);
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ partial, const double2 *__restrict__ steer,
+                                                    float2 *__restrict__ wout, int F, int T, int tsplit, double epsi) {
+    extern __shared__ double2 ph[];  // [F] phasors, then their prefix products
+    const int bs = blockIdx.x;
+    const double2 *d = steer + (size_t)bs * F * M;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        double2 p = make_double2(1.0, 0.0);
+        if (f > 0) {
+            double cr = 0.0, ci = 0.0;
+            for (int m = 0; m < M; ++m) {
+                double2 a = d[(size_t)f * M + m], bq = d[(size_t)(f - 1) * M + m];
+                cr += a.x * bq.x + a.y * bq.y;  // a * conj(b)
+                ci += a.y * bq.x - a.x * bq.y;
+            }
+            double n = sqrt(cr * cr + ci * ci);
+            if (n > 0.0) p = make_double2(cr / n, -ci / n);  // exp(-j angle(c))
+        }
+        ph[f] = p;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double2 acc = ph[0];
+        for (int f = 1; f < F; ++f) {
+            double2 p = ph[f];
+            acc = make_double2(acc.x * p.x - acc.y * p.y, acc.x * p.y + acc.y * p.x);
+            ph[f] = acc;
+        }
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        double Ar[M][M], Ai[M][M];
+        load_scm<M>(partial, bs, f, F, tsplit, 1, 1.0 / (double)T, Ar, Ai);
+        double dr[M], di[M], ur[M], ui[M];
+        const double2 P = ph[f];
+        for (int m = 0; m < M; ++m) {
+            double2 a = d[(size_t)f * M + m];
+            dr[m] = a.x * P.x - a.y * P.y;
+            di[m] = a.x * P.y + a.y * P.x;
+            ur[m] = dr[m];
+            ui[m] = di[m];
+            Ar[m][m] += epsi;  // tester.py:1221
+        }
+        // Gaussian elimination with partial pivoting on [A | u]
+        for (int k = 0; k < M; ++k) {
+            int piv = k;
+            double best = Ar[k][k] * Ar[k][k] + Ai[k][k] * Ai[k][k];
+            for (int r = k + 1; r < M; ++r) {
+                double v = Ar[r][k] * Ar[r][k] + Ai[r][k] * Ai[r][k];
+                if (v > best) {
+                    best = v;
+                    piv = r;
+                }
+            }
+            if (piv != k) {
+                for (int c = 0; c < M; ++c) {
+                    double t = Ar[k][c]; Ar[k][c] = Ar[piv][c]; Ar[piv][c] = t;
+                    t = Ai[k][c]; Ai[k][c] = Ai[piv][c]; Ai[piv][c] = t;
+                }
+                double t = ur[k]; ur[k] = ur[piv]; ur[piv] = t;
+                t = ui[k]; ui[k] = ui[piv]; ui[piv] = t;
+            }
+            const double pr = Ar[k][k], pi = Ai[k][k];
+            const double pd = pr * pr + pi * pi;
+            for (int r = k + 1; r < M; ++r) {
+                // l = A[r][k] / A[k][k]
+                const double lr = (Ar[r][k] * pr + Ai[r][k] * pi) / pd;
+                const double li = (Ai[r][k] * pr - Ar[r][k] * pi) / pd;
+                for (int c = k; c < M; ++c) {
+                    Ar[r][c] -= lr * Ar[k][c] - li * Ai[k][c];
+                    Ai[r][c] -= lr * Ai[k][c] + li * Ar[k][c];
+                }
+                ur[r] -= lr * ur[k] - li * ui[k];
+                ui[r] -= lr * ui[k] + li * ur[k];
+            }
+        }
+        for (int k = M - 1; k >= 0; --k) {
+            double sr = ur[k], si = ui[k];
+            for (int c = k + 1; c < M; ++c) {
+                sr -= Ar[k][c] * ur[c] - Ai[k][c] * ui[c];
+                si -= Ar[k][c] * ui[c] + Ai[k][c] * ur[c];
+            }
+            const double pr = Ar[k][k], pi = Ai[k][k];
+            const double pd = pr * pr + pi * pi;
+            ur[k] = (sr * pr + si * pi) / pd;
+            ui[k] = (si * pr - sr * pi) / pd;
+        }
+        // w = u / (d^H u)
+        double nr = 0.0, ni = 0.0;
+        for (int m = 0; m < M; ++m) {
+            nr += dr[m] * ur[m] + di[m] * ui[m];
+            ni += dr[m] * ui[m] - di[m] * ur[m];
+        }
+        const double nd = nr * nr + ni * ni;
+        for (int m = 0; m < M; ++m) {
+            const double wr = (ur[m] * nr + ui[m] * ni) / nd;
+            const double wi = (ui[m] * nr - ur[m] * ni) / nd;
+            wout[((size_t)bs * F + f) * M + m] = make_float2((float)wr, (float)wi);
+        }
+    }
+}
+
+constexpr int kMaxS = 4;
+constexpr int kApplyTile = 64;
+
+template <int M>
+__global__ void __launch_bounds__(kFx *kTy) apply_kernel(const float2 *__restrict__ mix, int64_t sb, int64_t sm, int64_t st,
+                                                          int64_t sf, const float2 *__restrict__ w, float2 *__restrict__ out,
+                                                          int S, int B, int T, int F) {
+    const int f = blockIdx.x * kFx + threadIdx.x;
+    const int b = blockIdx.z;
+    if (f >= F) return;
+    float2 wv[kMaxS][M];
+#pragma unroll
+    for (int s = 0; s < kMaxS; ++s)
+        if (s < S) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) wv[s][m] = w[((size_t)(s * B + b) * F + f) * M + m];
+        }
+    const int t0 = blockIdx.y * kApplyTile;
+    const int t1 = min(T, t0 + kApplyTile);
+    const float2 *mix_b = mix + b * sb + (int64_t)f * sf;
+    for (int t = t0 + threadIdx.y; t < t1; t += kTy) {
+        float2 x[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) x[m] = mix_b[m * sm + t * st];
+#pragma unroll
+        for (int s = 0; s < kMaxS; ++s)
+            if (s < S) {
+                float yr = 0.f, yi = 0.f;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    // conj(w) * x
+                    yr = fmaf(wv[s][m].x, x[m].x, fmaf(wv[s][m].y, x[m].y, yr));
+                    yi = fmaf(wv[s][m].x, x[m].y, fmaf(-wv[s][m].y, x[m].x, yi));
+                }
+                out[((size_t)(s * B + b) * T + t) * F + f] = make_float2(yr, yi);
+            }
+    }
+}
+
+int pick_tsplit(int B, int F) {
+    int ctas = ceil_div(F, kFx) * B;
+    int ts = ceil_div(2 * 148, ctas);
+    return ts < 1 ? 1 : (ts > 8 ? 8 : ts);
+}
+
+struct MvdrWs {
+    float *partial;
+    double2 *steer;
+    float2 *w;
+    size_t total;
+};
+
+template <int M>
+MvdrWs carve(char *base, int S, int B, int T, int F, int tsplit) {
+    MvdrWs ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    ws.partial = reinterpret_cast<float *>(take((size_t)B * S * tsplit * Tri<M>::NV * F * sizeof(float)));
+    ws.steer = reinterpret_cast<double2 *>(take((size_t)B * S * F * M * sizeof(double2)));
+    ws.w = reinterpret_cast<float2 *>(take((size_t)B * S * F * M * sizeof(float2)));
+    ws.total = off;
+    return ws;
+}
+
+template <int M>
+int run(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf, void *d_out,
+        void *d_weights, int S, int B, int T, int F, float epsi, void *d_ws, size_t ws_bytes, cudaStream_t stream) {
+    const int tsplit = pick_tsplit(B, F);
+    MvdrWs ws = carve<M>(reinterpret_cast<char *>(d_ws), S, B, T, F, tsplit);
+    if (ws.total > ws_bytes) {
+        set_error("miso_mvdr_fwd: workspace %zu < required %zu bytes", ws_bytes, ws.total);
+        return MISO_E_WORKSPACE;
+    }
+    float2 *w = d_weights ? reinterpret_cast<float2 *>(d_weights) : ws.w;
+    const float2 *src = reinterpret_cast<const float2 *>(d_src);
+    const float2 *mix = reinterpret_cast<const float2 *>(d_mix);
+    dim3 blk(kFx, kTy);
+    scm_kernel<M><<<dim3(ceil_div(F, kFx), tsplit, B), blk, 0, stream>>>(src, src_ss, mix, sb, sm, st, sf, ws.partial, S, B, T,
+                                                                       F, tsplit);
+    MISO_LAUNCHED("scm_kernel");
+    // problems are ordered (s, b, f): bs = s*B + b, matching the [S,B,...] outputs
+    const int nprob = B * S * F;
+    eig_kernel<M><<<ceil_div(nprob, 64), 64, 0, stream>>>(ws.partial, ws.steer, nprob, F, T, tsplit);
+    MISO_LAUNCHED("eig_kernel");
+    solve_kernel<M><<<B * S, 256, (size_t)F * sizeof(double2), stream>>>(ws.partial, ws.steer, w, F, T, tsplit, (double)epsi);
+    MISO_LAUNCHED("solve_kernel");
+    apply_kernel<M><<<dim3(ceil_div(F, kFx), ceil_div(T, kApplyTile), B), blk, 0, stream>>>(
+        mix, sb, sm, st, sf, w, reinterpret_cast<float2 *>(d_out), S, B, T, F);
+    MISO_LAUNCHED("apply_kernel");
+    return MISO_OK;
+}
+
+template <int M>
+size_t ws_bytes_for(int S, int B, int T, int F) {
+    return carve<M>(nullptr, S, B, T, F, pick_tsplit(B, F)).total;
+}
+
+}  // namespace
+}  // namespace miso
+
+using namespace miso;
+
+extern "C" {
+
+size_t miso_mvdr_workspace_bytes(int S, int B, int M, int T, int F) {
+    if (S < 1 || B < 1 || T < 1 || F < 1) return 0;
+    switch (M) {
+        case 2: return ws_bytes_for<2>(S, B, T, F);
+        case 3: return ws_bytes_for<3>(S, B, T, F);
+        case 4: return ws_bytes_for<4>(S, B, T, F);
+        case 5: return ws_bytes_for<5>(S, B, T, F);
+        case 6: return ws_bytes_for<6>(S, B, T, F);
+        case 7: return ws_bytes_for<7>(S, B, T, F);
+        case 8: return ws_bytes_for<8>(S, B, T, F);
+    }
+    return 0;
+}
+
+int miso_mvdr_fwd(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf,
+                  void *d_out, void *d_weights, int S, int B, int M, int T, int F, float epsi, void *d_ws, size_t ws_bytes,
+                  void *stream) {
+    MISO_REQUIRE(d_src && d_mix && d_out && d_ws, "miso_mvdr_fwd: null argument");
+    MISO_REQUIRE(S >= 1 && S <= kMaxS, "miso_mvdr_fwd: S=%d unsupported (1..%d)", S, kMaxS);
+    MISO_REQUIRE(M >= 2 && M <= 8, "miso_mvdr_fwd: M=%d unsupported (2..8)", M);
+    MISO_REQUIRE(B >= 1 && B <= 65535 && T >= 1 && F >= 1 && F <= 2048, "miso_mvdr_fwd: bad shape B=%d T=%d F=%d", B, T, F);
+    cudaStream_t s = as_stream(stream);
+#define MISO_MVDR_CASE(m) \
+    case m: return run<m>(d_src, src_ss, d_mix, sb, sm, st, sf, d_out, d_weights, S, B, T, F, epsi, d_ws, ws_bytes, s)
+    switch (M) {
+        MISO_MVDR_CASE(2);
+        MISO_MVDR_CASE(3);
+        MISO_MVDR_CASE(4);
+        MISO_MVDR_CASE(5);
+        MISO_MVDR_CASE(6);
+        MISO_MVDR_CASE(7);
+        MISO_MVDR_CASE(8);
+    }
+#undef MISO_MVDR_CASE
+    return MISO_E_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,899 @@
+// MISO_1 / MISO_3 network body: packed-weight handle, workspace plan and the forward
+// launch sequence (reference model.py:8-111, 282-395; layers model.py:401-632).
+//
+// Data layout in HBM: every activation is fp32 channels-last [B, T, F, Ctot].  A
+// DenseBlock owns ONE buffer [x | y0 | y1 | y2 | y3] and conv k reads the channel
+// prefix it needs (model.py:470-479 concatenates instead); an encoder's final output is
+// written straight into the skip half of the decoder buffer that will consume it
+// (model.py:99 concatenates instead), and the next encoder reads it from there.
+// Tensors are stored as raw ELU outputs plus fp64 (sum, sumsq) per (sample, channel);
+// InstanceNorm is applied by whoever loads them.
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv.cuh"
+
+namespace miso {
+
+int conv_fp32_tile_n(int cout);
+
+namespace {
+
+constexpr float kInEps = 1e-5f;   // nn.InstanceNorm default (model.py:413,430,445,530)
+constexpr float kGlnEps = 1e-8f;  // model.py:6,631
+
+// ------------------------------------------------------------------ small kernels ----
+__global__ void pack_conv_w_kernel(const float *__restrict__ w, float *__restrict__ packed, int cout, int cin, int taps,
+                                   int cout_pad, int transposed) {
+    int64_t total = (int64_t)taps * cin * cout_pad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int co = (int)(i % cout_pad);
+        int64_t r = i / cout_pad;
+        int ci = (int)(r % cin);
+        int tap = (int)(r / cin);
+        float v = 0.f;
+        if (co < cout) v = transposed ? w[((int64_t)ci * cout + co) * taps + tap] : w[((int64_t)co * cin + ci) * taps + tap];
+        packed[i] = v;
+    }
+}
+
+__global__ void pad_copy_kernel(const float *__restrict__ src, float *__restrict__ dst, int n, int n_pad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) dst[i] = i < n ? src[i] : 0.f;
+}
+
+__global__ void sentinel_kernel(double *sums, int B, int ctot, int coff, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * n) {
+        int b = i / n, c = i - b * n;
+        sums[((size_t)b * ctot + coff + c) * 2 + 1] = -1.0;
+    }
+}
+
+// x0 = InstanceNorm(raw bottleneck output) materialised as the TCN state [B,T,C], plus the
+// per-(b,c) statistics its first TemporalBlock needs (model.py:530).
+constexpr int kTcnTile = 32;
+__global__ void __launch_bounds__(128) tcn_prep_kernel(const float *__restrict__ raw, int raw_ctot, int raw_coff,
+                                                       const double *__restrict__ raw_sums, double inv_n, float eps,
+                                                       float *__restrict__ S, double *__restrict__ s_sums, int T, int C) {
+    const int c = blockIdx.y * 128 + threadIdx.x;
+    const int b = blockIdx.z;
+    if (c >= C) return;
+    const double *rs = raw_sums + ((size_t)b * raw_ctot + raw_coff + c) * 2;
+    const float2 af = affine_from_sums(rs[0], rs[1], inv_n, (double)eps);
+    const int t0 = blockIdx.x * kTcnTile;
+    const int t1 = min(T, t0 + kTcnTile);
+    float s = 0.f, q = 0.f;
+    for (int t = t0; t < t1; ++t) {
+        float x = fmaf(raw[((size_t)b * T + t) * raw_ctot + raw_coff + c], af.x, af.y);
+        S[((size_t)b * T + t) * C + c] = x;
+        s += x;
+        q += x * x;
+    }
+    atomicAdd(s_sums + ((size_t)b * C + c) * 2, (double)s);
+    atomicAdd(s_sums + ((size_t)b * C + c) * 2 + 1, (double)q);
+}
+
+// First half of DepthwiseSeparableConv fused with the block's norm/activation prologue
+// (model.py:530-531 / 538-539 then 556-558): v = ELU(IN1d(u)); y = dwconv_k3_dil(v);
+// p = PReLU(y); accumulates the gLN statistics of p over (C,T) per sample.
+__global__ void __launch_bounds__(128) tcn_dw_kernel(const float *__restrict__ U, const double *__restrict__ u_sums,
+                                                     double inv_n, float eps, const float *__restrict__ wdw,
+                                                     const float *__restrict__ alpha, float *__restrict__ P,
+                                                     double *__restrict__ g_sums, int T, int C, int dil) {
+    const int c = blockIdx.y * 128 + threadIdx.x;
+    const int b = blockIdx.z;
+    float s = 0.f, q = 0.f;
+    if (c < C) {
+        const double *us = u_sums + ((size_t)b * C + c) * 2;
+        const float2 af = affine_from_sums(us[0], us[1], inv_n, (double)eps);
+        const float w0 = wdw[c * 3 + 0], w1 = wdw[c * 3 + 1], w2 = wdw[c * 3 + 2];
+        const float al = alpha[0];
+        const int t0 = blockIdx.x * kTcnTile;
+        const int t1 = min(T, t0 + kTcnTile);
+        const float *ub = U + (size_t)b * T * C + c;
+        for (int t = t0; t < t1; ++t) {
+            float vm = 0.f, vp = 0.f;
+            float v0 = elu1(fmaf(ub[(size_t)t * C], af.x, af.y));
+            if (t - dil >= 0) vm = elu1(fmaf(ub[(size_t)(t - dil) * C], af.x, af.y));
+            if (t + dil < T) vp = elu1(fmaf(ub[(size_t)(t + dil) * C], af.x, af.y));
+            float y = fmaf(w0, vm, fmaf(w1, v0, w2 * vp));
+            y = y > 0.f ? y : al * y;
+            P[((size_t)b * T + t) * C + c] = y;
+            s += y;
+            q += y * y;
+        }
+    }
+    __shared__ float red[2][4];
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s;
+        red[1][threadIdx.x >> 5] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ds = (double)red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        double dq = (double)red[1][0] + red[1][1] + red[1][2] + red[1][3];
+        atomicAdd(g_sums + (size_t)b * 2, ds);
+        atomicAdd(g_sums + (size_t)b * 2 + 1, dq);
+    }
+}
+
+struct ShiftList {
+    int n;
+    int s[16];
+};
+
+__global__ void pack_miso1_kernel(const float2 *__restrict__ mix, float *__restrict__ x, int B, int M, int TF,
+                                  ShiftList sh) {
+    // one thread per (b, pixel): reads M complex values (coalesced along f), writes 2M floats per shift
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * TF) return;
+    int b = (int)(i / TF);
+    int p = (int)(i - (int64_t)b * TF);
+    float2 v[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+        if (m < M) v[m] = mix[((size_t)b * M + m) * TF + p];
+    for (int k = 0; k < sh.n; ++k) {
+        float *o = x + (((size_t)k * B + b) * TF + p) * (2 * M);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < M) {
+                int m = j + sh.s[k];
+                m -= (m >= M) ? M : 0;
+                float2 z = v[0];
+#pragma unroll
+                for (int mm = 1; mm < 8; ++mm)
+                    if (mm == m) z = v[mm];
+                o[j] = z.x;
+                o[M + j] = z.y;
+            }
+        }
+    }
+}
+
+__global__ void pack_miso3_kernel(const float2 *__restrict__ mix, const float2 *__restrict__ second,
+                                  const float2 *__restrict__ third, float *__restrict__ x, int B, int M, int TF) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * TF) return;
+    int b = (int)(i / TF);
+    int p = (int)(i - (int64_t)b * TF);
+    const int C = M + 2;
+    float *o = x + (size_t)i * (2 * C);
+    for (int m = 0; m < M; ++m) {
+        float2 z = mix[((size_t)b * M + m) * TF + p];
+        o[m] = z.x;
+        o[C + m] = z.y;
+    }
+    float2 z2 = second[(size_t)b * TF + p];
+    float2 z3 = third[(size_t)b * TF + p];
+    o[M] = z2.x;
+    o[C + M] = z2.y;
+    o[M + 1] = z3.x;
+    o[C + M + 1] = z3.y;
+}
+
+__global__ void unpack_complex_kernel(const float *__restrict__ y, float2 *__restrict__ out, int B, int S, int TF) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * TF) return;
+    int b = (int)(i / TF);
+    int p = (int)(i - (int64_t)b * TF);
+    const float *src = y + (size_t)i * (2 * S);
+    for (int s = 0; s < S; ++s) out[((size_t)b * S + s) * TF + p] = make_float2(src[s], src[S + s]);
+}
+
+__global__ void tap_kernel(const float *__restrict__ buf, int ctot, int coff, int C, const double *__restrict__ sums,
+                           double inv_n, float eps, float *__restrict__ out, int B, int TF) {
+    int64_t total = (int64_t)B * C * TF;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int p = (int)(i % TF);
+        int64_t r = i / TF;
+        int c = (int)(r % C);
+        int b = (int)(r / C);
+        float2 af = make_float2(1.f, 0.f);
+        if (sums) {
+            const double *s = sums + ((size_t)b * ctot + coff + c) * 2;
+            af = affine_from_sums(s[0], s[1], inv_n, (double)eps);
+        }
+        out[i] = fmaf(buf[((size_t)b * TF + p) * ctot + coff + c], af.x, af.y);
+    }
+}
+
+// ------------------------------------------------------------------ handle -------------
+enum ParamKind { P_CONV_W, P_DECONV_W, P_PW_W, P_BIAS, P_PLAIN };
+
+struct Param {
+    std::string key;
+    ParamKind kind;
+    int64_t numel;
+    int cout, cin, taps, cout_pad;  // conv-like
+    float *d;                       // packed device storage (owned by the arena)
+    size_t packed_elems;
+    bool loaded;
+};
+
+struct ConvDesc {
+    int w = -1, b = -1;  // param indices
+    int cin = 0, cout = 0, cout_pad = 0;
+};
+
+struct TcnHalf {
+    int dw, alpha, gamma, beta, pw;
+};
+
+}  // namespace
+}  // namespace miso
+
+using namespace miso;
+
+struct miso_net {
+    int in_ch, out_ch, nb, R, X, C;
+    std::vector<int> en, de;  // en[0]=in_ch ... en[nb]; de[0..nb-1], de[nb]=out_ch
+    std::vector<Param> params;
+    std::map<std::string, int> index;
+    std::vector<ConvDesc> enc_conv;                 // [nb]
+    std::vector<std::vector<ConvDesc>> enc_dense;   // [nb][5] (empty if no dense block)
+    std::vector<std::vector<ConvDesc>> dec_dense;   // [nb][5]
+    std::vector<ConvDesc> dec_deconv;               // [nb]
+    std::vector<TcnHalf> tcn;                       // [R*X*2]
+    float *arena = nullptr;
+    int mode = 0;
+    int n_loaded = 0;
+};
+
+namespace miso {
+namespace {
+
+bool dense_enc(int i) { return i < 5; }   // model.py:42
+bool dense_dec(int j) { return j >= 2; }  // model.py:60
+
+int add_param(miso_net *n, const std::string &key, ParamKind kind, int64_t numel, int cout, int cin, int taps) {
+    Param p;
+    p.key = key;
+    p.kind = kind;
+    p.numel = numel;
+    p.cout = cout;
+    p.cin = cin;
+    p.taps = taps;
+    p.cout_pad = 0;
+    p.d = nullptr;
+    p.loaded = false;
+    if (kind == P_CONV_W || kind == P_DECONV_W || kind == P_PW_W) {
+        int bn = conv_fp32_tile_n(cout);
+        p.cout_pad = (cout + bn - 1) / bn * bn;
+        p.packed_elems = (size_t)taps * cin * p.cout_pad;
+    } else if (kind == P_BIAS) {
+        int bn = conv_fp32_tile_n(cout);
+        p.cout_pad = (cout + bn - 1) / bn * bn;
+        p.packed_elems = p.cout_pad;
+    } else {
+        p.packed_elems = (size_t)numel;
+    }
+    n->params.push_back(p);
+    n->index[key] = (int)n->params.size() - 1;
+    return (int)n->params.size() - 1;
+}
+
+ConvDesc add_conv(miso_net *n, const std::string &prefix, int cin, int cout, bool transposed) {
+    ConvDesc d;
+    d.cin = cin;
+    d.cout = cout;
+    d.w = add_param(n, prefix + ".weight", transposed ? P_DECONV_W : P_CONV_W, (int64_t)cin * cout * 9, cout, cin, 9);
+    d.b = add_param(n, prefix + ".bias", P_BIAS, cout, cout, 0, 0);
+    d.cout_pad = n->params[d.w].cout_pad;
+    return d;
+}
+
+std::vector<ConvDesc> add_dense(miso_net *n, const std::string &prefix, int c, int g1, int g2) {
+    std::vector<ConvDesc> v;
+    for (int k = 1; k <= 5; ++k)
+        v.push_back(add_conv(n, prefix + ".conv" + std::to_string(k) + ".0", c + (k - 1) * g1, k < 5 ? g1 : g2, false));
+    return v;
+}
+
+// spatial size of xs[i] (encoder outputs); returns false if the bottleneck is not F == 1
+bool encoder_sizes(const miso_net *n, int F, std::vector<int> &Fx) {
+    Fx.assign(n->nb, 0);
+    int f = F;
+    for (int i = 0; i < n->nb; ++i) {
+        int stride = (i == 0 || i == n->nb - 1) ? 1 : 2;
+        if (f < 3) return false;
+        f = (f - 3) / stride + 1;
+        Fx[i] = f;
+    }
+    if (f != 1) return false;
+    // the decoder must reproduce the encoder sizes exactly (skip concatenation, model.py:99)
+    int g = 1;
+    for (int j = 0; j < n->nb; ++j) {
+        if (g != Fx[n->nb - 1 - j]) return false;
+        int stride = (j == 0 || j == n->nb - 1) ? 1 : 2;
+        g = (g - 1) * stride + 3;
+    }
+    return g == F;
+}
+
+struct BufDesc {
+    float *p = nullptr;
+    double *sums = nullptr;
+    int ctot = 0, F = 0;
+};
+
+struct Plan {
+    std::vector<int> Fx;
+    std::vector<BufDesc> E, D, Y;
+    float *S = nullptr, *U = nullptr, *P = nullptr;
+    std::vector<double *> sS, sU, g1, g2;
+    double *stats_base = nullptr;
+    size_t stats_bytes = 0;
+    size_t total = 0;
+};
+
+bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
+    if (!encoder_sizes(n, F, pl.Fx)) return false;
+    const int nb = n->nb;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    pl.E.assign(nb, BufDesc());
+    pl.D.assign(nb, BufDesc());
+    pl.Y.assign(nb, BufDesc());
+    // statistics first (one memset clears them all)
+    size_t stats_doubles = 0;
+    auto stat_take = [&](size_t doubles) {
+        size_t o = stats_doubles;
+        stats_doubles += (doubles + 1) & ~(size_t)1;
+        return o;
+    };
+    std::vector<size_t> oE(nb), oD(nb), oY(nb);
+    for (int i = 0; i < nb; ++i) {
+        if (dense_enc(i)) {
+            pl.E[i].ctot = 5 * n->en[i + 1];
+            pl.E[i].F = pl.Fx[i];
+            oE[i] = stat_take((size_t)B * pl.E[i].ctot * 2);
+        }
+    }
+    for (int j = 0; j < nb; ++j) {
+        pl.D[j].ctot = (dense_dec(j) ? 6 : 2) * n->de[j];
+        pl.D[j].F = pl.Fx[nb - 1 - j];
+        oD[j] = stat_take((size_t)B * pl.D[j].ctot * 2);
+        if (dense_dec(j)) {
+            pl.Y[j].ctot = 2 * n->de[j];
+            pl.Y[j].F = pl.D[j].F;
+            oY[j] = stat_take((size_t)B * pl.Y[j].ctot * 2);
+        }
+    }
+    const int nblk = n->R * n->X;
+    std::vector<size_t> oS(nblk), oU(nblk), o1(nblk), o2(nblk);
+    for (int k = 0; k < nblk; ++k) {
+        oS[k] = stat_take((size_t)B * n->C * 2);
+        oU[k] = stat_take((size_t)B * n->C * 2);
+        o1[k] = stat_take((size_t)B * 2);
+        o2[k] = stat_take((size_t)B * 2);
+    }
+    pl.stats_bytes = stats_doubles * sizeof(double);
+    pl.stats_base = reinterpret_cast<double *>(take(pl.stats_bytes));
+    auto sp = [&](size_t o) { return pl.stats_base ? pl.stats_base + o : nullptr; };
+    for (int i = 0; i < nb; ++i)
+        if (dense_enc(i)) {
+            pl.E[i].sums = sp(oE[i]);
+            pl.E[i].p = reinterpret_cast<float *>(take((size_t)B * T * pl.E[i].F * pl.E[i].ctot * sizeof(float)));
+        }
+    for (int j = 0; j < nb; ++j) {
+        pl.D[j].sums = sp(oD[j]);
+        pl.D[j].p = reinterpret_cast<float *>(take((size_t)B * T * pl.D[j].F * pl.D[j].ctot * sizeof(float)));
+        if (dense_dec(j)) {
+            pl.Y[j].sums = sp(oY[j]);
+            pl.Y[j].p = reinterpret_cast<float *>(take((size_t)B * T * pl.Y[j].F * pl.Y[j].ctot * sizeof(float)));
+        }
+    }
+    size_t tcn_bytes = (size_t)B * T * n->C * sizeof(float);
+    pl.S = reinterpret_cast<float *>(take(tcn_bytes));
+    pl.U = reinterpret_cast<float *>(take(tcn_bytes));
+    pl.P = reinterpret_cast<float *>(take(tcn_bytes));
+    pl.sS.resize(nblk);
+    pl.sU.resize(nblk);
+    pl.g1.resize(nblk);
+    pl.g2.resize(nblk);
+    for (int k = 0; k < nblk; ++k) {
+        pl.sS[k] = sp(oS[k]);
+        pl.sU[k] = sp(oU[k]);
+        pl.g1[k] = sp(o1[k]);
+        pl.g2[k] = sp(o2[k]);
+    }
+    pl.total = off;
+    return true;
+}
+
+// where encoder i's block output xs[i] lives: the skip half of decoder (nb-1-i)'s buffer
+struct ViewRef {
+    const BufDesc *buf;
+    int coff, c;
+};
+ViewRef xs_view(const miso_net *n, const Plan &pl, int i) {
+    int j = n->nb - 1 - i;
+    return ViewRef{&pl.D[j], n->de[j], n->en[i + 1]};
+}
+
+int run_conv(const miso_net *n, const ConvDesc &cd, bool transposed, const float *in, int in_ctot, int in_coff, int Fin,
+             const double *in_sums, float *out, int out_ctot, int out_coff, int Fout, double *out_sums, int B, int T,
+             int stride_f, int pad_f, bool elu, cudaStream_t st) {
+    ConvArgs a{};
+    a.in = in;
+    a.w = n->params[cd.w].d;
+    a.bias = n->params[cd.b].d;
+    a.out = out;
+    a.resid = nullptr;
+    a.in_sums = in_sums;
+    a.out_sums = out_sums;
+    a.B = B;
+    a.T = T;
+    a.Fin = Fin;
+    a.Fout = Fout;
+    a.in_ctot = in_ctot;
+    a.in_coff = in_coff;
+    a.cin = cd.cin;
+    a.out_ctot = out_ctot;
+    a.out_coff = out_coff;
+    a.cout = cd.cout;
+    a.cout_pad = cd.cout_pad;
+    a.KT = 3;
+    a.KF = 3;
+    a.stride_f = stride_f;
+    a.pad_t = 1;
+    a.pad_f = pad_f;
+    a.transposed = transposed ? 1 : 0;
+    a.norm_mode = in_sums ? NORM_IN : NORM_NONE;
+    a.norm_eps = kInEps;
+    a.norm_inv_n = 1.0 / ((double)T * Fin);
+    a.elu = elu ? 1 : 0;
+    return launch_conv_fp32(a, st);
+}
+
+}  // namespace
+}  // namespace miso
+
+// =========================================================================== C ABI =====
+extern "C" {
+
+int miso_net_create(miso_net_t **out, int in_ch, int out_ch, int num_bottleneck, const int *en_channels,
+                    const int *de_channels, int tcn_repeats, int tcn_blocks) {
+    MISO_REQUIRE(out && en_channels && de_channels, "miso_net_create: null argument");
+    MISO_REQUIRE(num_bottleneck >= 6 && num_bottleneck <= 12, "miso_net_create: num_bottleneck %d unsupported (6..12)",
+                 num_bottleneck);
+    MISO_REQUIRE(in_ch > 0 && in_ch % 4 == 0, "miso_net_create: in_ch=%d must be a positive multiple of 4", in_ch);
+    MISO_REQUIRE(out_ch > 0 && out_ch % 2 == 0, "miso_net_create: out_ch=%d must be even", out_ch);
+    MISO_REQUIRE(tcn_repeats > 0 && tcn_blocks > 0 && tcn_blocks <= 12, "miso_net_create: bad TCN shape");
+    miso_net *n = new miso_net();
+    n->in_ch = in_ch;
+    n->out_ch = out_ch;
+    n->nb = num_bottleneck;
+    n->R = tcn_repeats;
+    n->X = tcn_blocks;
+    n->en.push_back(in_ch);
+    for (int i = 0; i < n->nb; ++i) n->en.push_back(en_channels[i]);
+    for (int i = 0; i < n->nb; ++i) n->de.push_back(de_channels[i]);
+    n->de.push_back(out_ch);
+    n->C = n->en[n->nb];
+    for (int i = 1; i <= n->nb; ++i)
+        if (n->en[i] <= 0 || n->en[i] % 4) {
+            set_error("miso_net_create: encoder channels must be positive multiples of 4");
+            delete n;
+            return MISO_E_ARG;
+        }
+    for (int j = 0; j < n->nb; ++j)
+        if (n->de[j] != n->en[n->nb - j]) {
+            // the skip connection concatenates xs[nb-1-j] (en[nb-j] channels) with a de[j]-channel
+            // tensor and the layer is declared with 2*de[j] inputs (model.py:35, 99)
+            set_error("miso_net_create: de_channels[%d]=%d must equal en_channels[%d]=%d", j, n->de[j], n->nb - 1 - j,
+                      n->en[n->nb - j]);
+            delete n;
+            return MISO_E_ARG;
+        }
+    const int nb = n->nb;
+    n->enc_conv.resize(nb);
+    n->enc_dense.resize(nb);
+    n->dec_dense.resize(nb);
+    n->dec_deconv.resize(nb);
+    // key order follows the reference's module registration order: encoders, decoders, TCN
+    for (int i = 0; i < nb; ++i) {
+        std::string p = "encoders." + std::to_string(i);
+        n->enc_conv[i] = add_conv(n, p + (i == 0 ? ".0.conv2d" : ".0.net.0"), n->en[i], n->en[i + 1], false);
+        if (dense_enc(i)) n->enc_dense[i] = add_dense(n, p + ".1", n->en[i + 1], n->en[i + 1], n->en[i + 1]);
+    }
+    for (int j = 0; j < nb; ++j) {
+        std::string p = "decoders." + std::to_string(j);
+        int cin = 2 * n->de[j], cout = n->de[j + 1];
+        if (dense_dec(j)) {
+            n->dec_dense[j] = add_dense(n, p + ".0", cin, cin / 2, cin);
+            n->dec_deconv[j] = add_conv(n, p + (j == nb - 1 ? ".1.deconv2d" : ".1.net.0"), cin, cout, true);
+        } else {
+            n->dec_deconv[j] = add_conv(n, p + ".0.net.0", cin, cout, true);
+        }
+    }
+    const int C = n->C;
+    for (int r = 0; r < n->R; ++r)
+        for (int x = 0; x < n->X; ++x)
+            for (int half : {2, 5}) {
+                std::string p = "TCN.temporal_conv_net." + std::to_string(r) + "." + std::to_string(x) + ".net." +
+                                std::to_string(half) + ".net";
+                TcnHalf h;
+                h.dw = add_param(n, p + ".0.weight", P_PLAIN, (int64_t)C * 3, 0, 0, 0);
+                h.alpha = add_param(n, p + ".1.weight", P_PLAIN, 1, 0, 0, 0);
+                h.gamma = add_param(n, p + ".2.gamma", P_PLAIN, C, 0, 0, 0);
+                h.beta = add_param(n, p + ".2.beta", P_PLAIN, C, 0, 0, 0);
+                h.pw = add_param(n, p + ".3.weight", P_PW_W, (int64_t)C * C, C, C, 1);
+                n->tcn.push_back(h);
+            }
+    size_t total = 0;
+    for (auto &p : n->params) total += align_up(p.packed_elems, 64);
+    cudaError_t e = cudaMalloc(&n->arena, total * sizeof(float));
+    if (e != cudaSuccess) {
+        delete n;
+        return cuda_fail(e, "cudaMalloc(packed weights)");
+    }
+    cudaMemset(n->arena, 0, total * sizeof(float));
+    size_t off = 0;
+    for (auto &p : n->params) {
+        p.d = n->arena + off;
+        off += align_up(p.packed_elems, 64);
+    }
+    *out = n;
+    return MISO_OK;
+}
+
+int miso_net_destroy(miso_net_t *net) {
+    if (!net) return MISO_OK;
+    if (net->arena) cudaFree(net->arena);
+    delete net;
+    return MISO_OK;
+}
+
+int miso_net_num_params(const miso_net_t *net) { return net ? (int)net->params.size() : 0; }
+const char *miso_net_param_key(const miso_net_t *net, int i) {
+    if (!net || i < 0 || i >= (int)net->params.size()) return nullptr;
+    return net->params[i].key.c_str();
+}
+int64_t miso_net_param_numel(const miso_net_t *net, int i) {
+    if (!net || i < 0 || i >= (int)net->params.size()) return -1;
+    return net->params[i].numel;
+}
+
+int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, int64_t numel, void *stream) {
+    MISO_REQUIRE(net && key && d_data, "miso_net_set_param: null argument");
+    auto it = net->index.find(key);
+    MISO_REQUIRE(it != net->index.end(), "miso_net_set_param: unexpected key '%s'", key);
+    Param &p = net->params[it->second];
+    MISO_REQUIRE(p.numel == numel, "miso_net_set_param: '%s' has %lld elements, expected %lld", key, (long long)numel,
+                 (long long)p.numel);
+    cudaStream_t st = as_stream(stream);
+    switch (p.kind) {
+        case P_CONV_W:
+        case P_DECONV_W:
+        case P_PW_W: {
+            int blocks = (int)std::min<size_t>((p.packed_elems + 255) / 256, 4096);
+            pack_conv_w_kernel<<<blocks, 256, 0, st>>>(d_data, p.d, p.cout, p.cin, p.taps, p.cout_pad,
+                                                      p.kind == P_DECONV_W ? 1 : 0);
+            MISO_LAUNCHED("pack_conv_w_kernel");
+            break;
+        }
+        case P_BIAS:
+            pad_copy_kernel<<<ceil_div(p.cout_pad, 128), 128, 0, st>>>(d_data, p.d, p.cout, p.cout_pad);
+            MISO_LAUNCHED("pad_copy_kernel");
+            break;
+        case P_PLAIN:
+            MISO_CUDA(cudaMemcpyAsync(p.d, d_data, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            break;
+    }
+    if (!p.loaded) {
+        p.loaded = true;
+        net->n_loaded++;
+    }
+    return MISO_OK;
+}
+
+int miso_net_set_mode(miso_net_t *net, int mode) {
+    MISO_REQUIRE(net, "miso_net_set_mode: null handle");
+    MISO_REQUIRE(mode == 0, "miso_net_set_mode: mode %d not available in this build (0 = fp32 FMA)", mode);
+    net->mode = mode;
+    return MISO_OK;
+}
+
+int miso_net_check_shape(const miso_net_t *net, int T, int F) {
+    MISO_REQUIRE(net, "miso_net_check_shape: null handle");
+    MISO_REQUIRE(T >= 1, "T=%d must be positive", T);
+    std::vector<int> Fx;
+    if (!encoder_sizes(net, F, Fx)) {
+        // required F: 2^(nb-2)*... easiest to state by search
+        int want = -1;
+        for (int f = 3; f < 100000; ++f)
+            if (encoder_sizes(net, f, Fx)) {
+                want = f;
+                break;
+            }
+        set_error("F=%d does not reduce to 1 at the bottleneck of a %d-block MISO network (needs F=%d)", F, net->nb, want);
+        return MISO_E_ARG;
+    }
+    return MISO_OK;
+}
+
+size_t miso_net_workspace_bytes(const miso_net_t *net, int B, int T, int F) {
+    if (!net || B <= 0 || T <= 0) return 0;
+    Plan pl;
+    if (!make_plan(net, B, T, F, nullptr, pl)) return 0;
+    return pl.total;
+}
+
+int miso_net_forward(miso_net_t *net, const float *d_x, float *d_y, int B, int T, int F, void *d_ws, size_t ws_bytes,
+                     void *stream) {
+    MISO_REQUIRE(net && d_x && d_y && d_ws, "miso_net_forward: null argument");
+    if (net->n_loaded != (int)net->params.size()) {
+        for (auto &p : net->params)
+            if (!p.loaded) {
+                set_error("miso_net_forward: parameter '%s' was never set (%d of %d loaded)", p.key.c_str(), net->n_loaded,
+                          (int)net->params.size());
+                return MISO_E_STATE;
+            }
+    }
+    MISO_REQUIRE(B >= 1 && B <= 65535, "miso_net_forward: batch %d out of range", B);
+    int rc = miso_net_check_shape(net, T, F);
+    if (rc) return rc;
+    Plan pl;
+    make_plan(net, B, T, F, reinterpret_cast<char *>(d_ws), pl);
+    if (pl.total > ws_bytes) {
+        set_error("miso_net_forward: workspace %zu < required %zu bytes", ws_bytes, pl.total);
+        return MISO_E_WORKSPACE;
+    }
+    MISO_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "miso_net_forward: workspace must be 256-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int nb = net->nb, C = net->C;
+    const miso_net *n = net;
+
+    MISO_CUDA(cudaMemsetAsync(pl.stats_base, 0, pl.stats_bytes, st));
+    {
+        // raw (never normalised) channels: enc0's first conv output (model.py:401-406) and the TCN output
+        const BufDesc &e0 = pl.E[0];
+        sentinel_kernel<<<ceil_div(B * n->en[1], 128), 128, 0, st>>>(e0.sums, B, e0.ctot, 0, n->en[1]);
+        MISO_LAUNCHED("sentinel_kernel");
+        sentinel_kernel<<<ceil_div(B * C, 128), 128, 0, st>>>(pl.D[0].sums, B, pl.D[0].ctot, 0, C);
+        MISO_LAUNCHED("sentinel_kernel");
+    }
+
+    // ---------------- encoders (model.py:40-53, 83-86) ----------------
+    for (int i = 0; i < nb; ++i) {
+        const float *in;
+        const double *in_sums;
+        int in_ctot, in_coff, Fin;
+        if (i == 0) {
+            in = d_x;
+            in_sums = nullptr;
+            in_ctot = n->in_ch;
+            in_coff = 0;
+            Fin = F;
+        } else {
+            ViewRef v = xs_view(n, pl, i - 1);
+            in = v.buf->p;
+            in_sums = v.buf->sums;
+            in_ctot = v.buf->ctot;
+            in_coff = v.coff;
+            Fin = v.buf->F;
+        }
+        const int stride = (i == 0 || i == nb - 1) ? 1 : 2;
+        ViewRef xo = xs_view(n, pl, i);
+        if (dense_enc(i)) {
+            const BufDesc &e = pl.E[i];
+            rc = run_conv(n, n->enc_conv[i], false, in, in_ctot, in_coff, Fin, in_sums, e.p, e.ctot, 0, e.F,
+                          i == 0 ? nullptr : e.sums, B, T, stride, 0, i != 0, st);
+            if (rc) return rc;
+            const int c = n->en[i + 1];
+            for (int k = 1; k <= 5; ++k) {
+                const ConvDesc &cd = n->enc_dense[i][k - 1];
+                if (k < 5)
+                    rc = run_conv(n, cd, false, e.p, e.ctot, 0, e.F, e.sums, e.p, e.ctot, c + (k - 1) * c, e.F, e.sums, B, T,
+                                  1, 1, true, st);
+                else
+                    rc = run_conv(n, cd, false, e.p, e.ctot, 0, e.F, e.sums, xo.buf->p, xo.buf->ctot, xo.coff, e.F,
+                                  xo.buf->sums, B, T, 1, 1, true, st);
+                if (rc) return rc;
+            }
+        } else {
+            rc = run_conv(n, n->enc_conv[i], false, in, in_ctot, in_coff, Fin, in_sums, xo.buf->p, xo.buf->ctot, xo.coff,
+                          xo.buf->F, xo.buf->sums, B, T, stride, 0, true, st);
+            if (rc) return rc;
+        }
+    }
+
+    // ---------------- TCN (model.py:486-567) ----------------
+    {
+        const BufDesc &d0 = pl.D[0];
+        const double inv_T = 1.0 / (double)T;
+        dim3 grid(ceil_div(T, kTcnTile), ceil_div(C, 128), B);
+        tcn_prep_kernel<<<grid, 128, 0, st>>>(d0.p, d0.ctot, C, d0.sums, inv_T, kInEps, pl.S, pl.sS[0], T, C);
+        MISO_LAUNCHED("tcn_prep_kernel");
+        const int nblk = n->R * n->X;
+        const int bn = conv_fp32_tile_n(C);
+        const int cpad = (C + bn - 1) / bn * bn;
+        for (int k = 0; k < nblk; ++k) {
+            const int dil = 1 << (k % n->X);
+            for (int half = 0; half < 2; ++half) {
+                const TcnHalf &h = n->tcn[k * 2 + half];
+                const float *u = half == 0 ? pl.S : pl.U;
+                const double *us = half == 0 ? pl.sS[k] : pl.sU[k];
+                double *gs = half == 0 ? pl.g1[k] : pl.g2[k];
+                tcn_dw_kernel<<<grid, 128, 0, st>>>(u, us, inv_T, kInEps, n->params[h.dw].d, n->params[h.alpha].d, pl.P, gs,
+                                                    T, C, dil);
+                MISO_LAUNCHED("tcn_dw_kernel");
+                ConvArgs a{};
+                a.in = pl.P;
+                a.w = n->params[h.pw].d;
+                a.bias = nullptr;
+                a.in_sums = gs;
+                a.gamma = n->params[h.gamma].d;
+                a.beta = n->params[h.beta].d;
+                a.B = B;
+                a.T = T;
+                a.Fin = 1;
+                a.Fout = 1;
+                a.in_ctot = C;
+                a.in_coff = 0;
+                a.cin = C;
+                a.cout = C;
+                a.cout_pad = cpad;
+                a.KT = 1;
+                a.KF = 1;
+                a.stride_f = 1;
+                a.pad_t = 0;
+                a.pad_f = 0;
+                a.transposed = 0;
+                a.norm_mode = NORM_GLN;
+                a.norm_eps = kGlnEps;
+                a.norm_inv_n = 1.0 / ((double)C * T);
+                a.elu = 0;
+                if (half == 0) {
+                    a.out = pl.U;
+                    a.out_ctot = C;
+                    a.out_coff = 0;
+                    a.out_sums = pl.sU[k];
+                    a.resid = nullptr;
+                } else {
+                    a.resid = pl.S;
+                    a.resid_ctot = C;
+                    a.resid_coff = 0;
+                    if (k + 1 < nblk) {
+                        a.out = pl.S;  // in-place residual update: each element is read once by its own writer
+                        a.out_ctot = C;
+                        a.out_coff = 0;
+                        a.out_sums = pl.sS[k + 1];
+                    } else {
+                        a.out = d0.p;
+                        a.out_ctot = d0.ctot;
+                        a.out_coff = 0;
+                        a.out_sums = nullptr;
+                    }
+                }
+                rc = launch_conv_fp32(a, st);
+                if (rc) return rc;
+            }
+        }
+    }
+
+    // ---------------- decoders (model.py:55-73, 97-100) ----------------
+    for (int j = 0; j < nb; ++j) {
+        const BufDesc &d = pl.D[j];
+        const int stride = (j == 0 || j == nb - 1) ? 1 : 2;
+        const bool last = j == nb - 1;
+        float *out = last ? d_y : pl.D[j + 1].p;
+        const int out_ctot = last ? n->out_ch : pl.D[j + 1].ctot;
+        const int Fout = last ? F : pl.D[j + 1].F;
+        double *out_sums = last ? nullptr : pl.D[j + 1].sums;
+        if (dense_dec(j)) {
+            const int c = 2 * n->de[j], g1 = n->de[j];
+            const BufDesc &y = pl.Y[j];
+            for (int k = 1; k <= 5; ++k) {
+                const ConvDesc &cd = n->dec_dense[j][k - 1];
+                if (k < 5)
+                    rc = run_conv(n, cd, false, d.p, d.ctot, 0, d.F, d.sums, d.p, d.ctot, c + (k - 1) * g1, d.F, d.sums, B,
+                                  T, 1, 1, true, st);
+                else
+                    rc = run_conv(n, cd, false, d.p, d.ctot, 0, d.F, d.sums, y.p, y.ctot, 0, y.F, y.sums, B, T, 1, 1, true,
+                                  st);
+                if (rc) return rc;
+            }
+            rc = run_conv(n, n->dec_deconv[j], true, y.p, y.ctot, 0, y.F, y.sums, out, out_ctot, 0, Fout, out_sums, B, T,
+                          stride, 0, !last, st);
+        } else {
+            rc = run_conv(n, n->dec_deconv[j], true, d.p, d.ctot, 0, d.F, d.sums, out, out_ctot, 0, Fout, out_sums, B, T,
+                          stride, 0, true, st);
+        }
+        if (rc) return rc;
+    }
+    return MISO_OK;
+}
+
+int64_t miso_net_tap(miso_net_t *net, const char *name, float *d_out, int64_t capacity, int B, int T, int F, void *d_ws,
+                     void *stream) {
+    MISO_REQUIRE(net && name && d_out && d_ws, "miso_net_tap: null argument");
+    Plan pl;
+    if (!make_plan(net, B, T, F, reinterpret_cast<char *>(d_ws), pl)) {
+        set_error("miso_net_tap: bad shape");
+        return MISO_E_ARG;
+    }
+    const miso_net *n = net;
+    std::string s(name);
+    const BufDesc *buf = nullptr;
+    int coff = 0, c = 0;
+    if (s.rfind("enc", 0) == 0) {
+        int i = atoi(s.c_str() + 3);
+        MISO_REQUIRE(i >= 0 && i < n->nb, "miso_net_tap: no such tap '%s'", name);
+        ViewRef v = xs_view(n, pl, i);
+        buf = v.buf;
+        coff = v.coff;
+        c = v.c;
+    } else if (s == "tcn") {
+        buf = &pl.D[0];
+        coff = 0;
+        c = n->C;
+    } else if (s.rfind("dec", 0) == 0) {
+        int j = atoi(s.c_str() + 3);
+        MISO_REQUIRE(j >= 0 && j < n->nb - 1, "miso_net_tap: no such tap '%s' (the last decoder is the network output)",
+                     name);
+        buf = &pl.D[j + 1];
+        coff = 0;
+        c = n->de[j + 1];
+    } else {
+        set_error("miso_net_tap: no such tap '%s'", name);
+        return MISO_E_ARG;
+    }
+    int64_t total = (int64_t)B * c * T * buf->F;
+    MISO_REQUIRE(total <= capacity, "miso_net_tap: output capacity %lld < %lld", (long long)capacity, (long long)total);
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, 8192);
+    tap_kernel<<<blocks, 256, 0, as_stream(stream)>>>(buf->p, buf->ctot, coff, c, buf->sums, 1.0 / ((double)T * buf->F),
+                                                      kInEps, d_out, B, T * buf->F);
+    MISO_LAUNCHED("tap_kernel");
+    return total;
+}
+
+int miso_pack_miso1(const void *d_mix, float *d_x, int B, int M, int T, int F, const int *shifts, int n_shift,
+                    void *stream) {
+    MISO_REQUIRE(d_mix && d_x && shifts, "miso_pack_miso1: null argument");
+    MISO_REQUIRE(M >= 1 && M <= 8, "miso_pack_miso1: M=%d unsupported (1..8)", M);
+    MISO_REQUIRE(n_shift >= 1 && n_shift <= 16, "miso_pack_miso1: n_shift=%d unsupported (1..16)", n_shift);
+    ShiftList sh;
+    sh.n = n_shift;
+    for (int k = 0; k < n_shift; ++k) sh.s[k] = ((shifts[k] % M) + M) % M;
+    int64_t n = (int64_t)B * T * F;
+    pack_miso1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float2 *>(d_mix), d_x, B, M, T * F, sh);
+    MISO_LAUNCHED("pack_miso1_kernel");
+    return MISO_OK;
+}
+
+int miso_pack_miso3(const void *d_mix, const void *d_second, const void *d_third, float *d_x, int B, int M, int T, int F,
+                    void *stream) {
+    MISO_REQUIRE(d_mix && d_second && d_third && d_x, "miso_pack_miso3: null argument");
+    MISO_REQUIRE(M >= 1, "miso_pack_miso3: bad M");
+    int64_t n = (int64_t)B * T * F;
+    pack_miso3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float2 *>(d_mix), reinterpret_cast<const float2 *>(d_second),
+        reinterpret_cast<const float2 *>(d_third), d_x, B, M, T * F);
+    MISO_LAUNCHED("pack_miso3_kernel");
+    return MISO_OK;
+}
+
+int miso_unpack_complex(const float *d_y, void *d_out, int B, int S, int T, int F, void *stream) {
+    MISO_REQUIRE(d_y && d_out && S >= 1, "miso_unpack_complex: bad argument");
+    int64_t n = (int64_t)B * T * F;
+    unpack_complex_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(d_y, reinterpret_cast<float2 *>(d_out),
+                                                                                  B, S, T * F);
+    MISO_LAUNCHED("unpack_complex_kernel");
+    return MISO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Library-level plumbing of the C ABI: error string, launch counter, device check.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace miso {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+
+// ---- per-launch event profiler ---------------------------------------------------------
+namespace {
+struct ProfRec {
+    cudaEvent_t a, b;
+    double flops, bytes;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_pool;
+std::atomic<bool> g_prof_on{false};
+thread_local cudaEvent_t g_open = nullptr;
+
+cudaEvent_t get_event() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_pool.empty()) {
+        cudaEvent_t e = g_pool.back();
+        g_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void prof_begin(cudaStream_t st) {
+    if (!prof_enabled()) return;
+    g_open = get_event();
+    cudaEventRecord(g_open, st);
+}
+void prof_end(cudaStream_t st, double flops, double bytes) {
+    if (!g_open) return;
+    ProfRec r;
+    r.a = g_open;
+    g_open = nullptr;
+    r.b = get_event();
+    cudaEventRecord(r.b, st);
+    r.flops = flops;
+    r.bytes = bytes;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+}
+
+}  // namespace miso
+
+extern "C" {
+
+int miso_prof_enable(int on) {
+    miso::g_prof_on.store(on != 0);
+    return MISO_OK;
+}
+
+int miso_prof_collect(double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches) {
+    std::vector<miso::ProfRec> recs;
+    {
+        std::lock_guard<std::mutex> lk(miso::g_prof_mu);
+        recs.swap(miso::g_prof);
+    }
+    double ms = 0.0, fl = 0.0, by = 0.0;
+    for (auto &r : recs) {
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e != cudaSuccess) return miso::cuda_fail(e, "cudaEventSynchronize");
+        float t = 0.f;
+        e = cudaEventElapsedTime(&t, r.a, r.b);
+        if (e != cudaSuccess) return miso::cuda_fail(e, "cudaEventElapsedTime");
+        ms += t;
+        fl += r.flops;
+        by += r.bytes;
+    }
+    {
+        std::lock_guard<std::mutex> lk(miso::g_prof_mu);
+        for (auto &r : recs) {
+            miso::g_pool.push_back(r.a);
+            miso::g_pool.push_back(r.b);
+        }
+    }
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = fl;
+    if (total_bytes) *total_bytes = by;
+    if (launches) *launches = recs.size();
+    return MISO_OK;
+}
+
+
+int miso_abi_version(void) { return MISO_ABI_VERSION; }
+const char *miso_last_error(void) { return miso::g_err; }
+uint64_t miso_launch_count(void) { return miso::g_launch_count.load(); }
+
+int miso_check_device(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return miso::cuda_fail(e, "cudaGetDevice");
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return miso::cuda_fail(e, "cudaDeviceGetAttribute");
+    if (major != 10) {
+        miso::set_error("misonet_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
+        return MISO_E_ARCH;
+    }
+    return MISO_OK;
+}
+
+}  // extern "C"

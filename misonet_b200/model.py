@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference's ``model.py`` interface for the hot path.
+
+``MISO_1`` / ``MISO_3`` keep the reference constructor and ``forward`` signatures
+(model.py:9, 76 and model.py:283, 350 of yuhogun0908/MISOnet) and the reference
+``state_dict`` keys/shapes, so ``run.py:66-78``-style construction and
+``load_state_dict(package['model_state_dict'])`` work unchanged.  The torch modules
+below are *parameter containers only* (plumbing: storage, ``.cuda()``, ``state_dict``,
+default initialisation in the reference's construction order); none of their
+``forward`` methods is ever called.  The arithmetic runs in the CUDA library through
+the C ABI (``include/misonet_b200.h``): pack -> ``miso_net_forward`` -> unpack.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------- containers
+class _Holder(nn.Module):
+    """A module that only holds parameters; calling it is a bug."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("misonet_b200 parameter container: the computation runs in the CUDA library")
+
+
+def _conv_unit(conv):
+    # (conv, ELU, InstanceNorm2d) triple of model.py:411-414 / 428-431 / 443-445
+    return nn.Sequential(conv, nn.ELU(), nn.InstanceNorm2d(conv.out_channels))
+
+
+class _InitConv(_Holder):          # model.py:401-406
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv2d = nn.Conv2d(cin, cout, (3, 3), stride=(1, 1), padding=(1, 0))
+
+
+class _Conv(_Holder):              # model.py:408-416
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.net = _conv_unit(nn.Conv2d(cin, cout, (3, 3), stride=stride, padding=(1, 0)))
+
+
+class _LastDeconv(_Holder):        # model.py:418-423
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.deconv2d = nn.ConvTranspose2d(cin, cout, (3, 3), stride=(1, 1), padding=(1, 0))
+
+
+class _Deconv(_Holder):            # model.py:425-433
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.net = _conv_unit(nn.ConvTranspose2d(cin, cout, (3, 3), stride=stride, padding=(1, 0)))
+
+
+class _Dense(_Holder):             # model.py:437-466
+    def __init__(self, c, g1, g2):
+        super().__init__()
+        for k in range(1, 6):
+            setattr(self, f"conv{k}", _conv_unit(nn.Conv2d(c + (k - 1) * g1, g1 if k < 5 else g2, (3, 3), padding=(1, 1))))
+
+
+class _GLN(_Holder):               # model.py:609-619
+    def __init__(self, c):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(1, c, 1))
+        self.beta = nn.Parameter(torch.zeros(1, c, 1))
+
+
+class _DSConv(_Holder):            # model.py:553-561
+    def __init__(self, c, dilation):
+        super().__init__()
+        self.net = nn.Sequential(
+            nn.Conv1d(c, c, 3, stride=1, padding=dilation, dilation=dilation, groups=c, bias=False),
+            nn.PReLU(), _GLN(c), nn.Conv1d(c, c, 1, bias=False))
+
+
+class _TemporalBlock(_Holder):     # model.py:515-540
+    def __init__(self, c, dilation):
+        super().__init__()
+        self.net = nn.Sequential(nn.InstanceNorm1d(c), nn.ELU(), _DSConv(c, dilation),
+                                 nn.InstanceNorm1d(c), nn.ELU(), _DSConv(c, dilation))
+
+
+class _TCN(_Holder):               # model.py:486-508
+    def __init__(self, repeats, blocks, c):
+        super().__init__()
+        self.temporal_conv_net = nn.Sequential(
+            *[nn.Sequential(*[_TemporalBlock(c, 2 ** x) for x in range(blocks)]) for _ in range(repeats)])
+
+
+# --------------------------------------------------------------------------- network
+class _MisoNet(nn.Module):
+    """Shared body of MISO_1 and MISO_3 (model.py:24-73 / 298-347)."""
+
+    TCN_REPEATS, TCN_BLOCKS = 2, 7     # model.py:31
+
+    def __init__(self, in_ch, out_ch, num_bottleneck, en_bottleneck_channels, de_bottleneck_channels, norm_type):
+        super().__init__()
+        if norm_type not in ("IN", None):
+            raise ValueError(f"norm_type={norm_type!r}: only 'IN' (config/NN_BSS.yml:123) is implemented")
+        # the reference mutates the caller's lists (model.py:16-17); we copy instead
+        self._en = [int(c) for c in en_bottleneck_channels][:num_bottleneck]
+        self._de = [int(c) for c in de_bottleneck_channels][:num_bottleneck]
+        if len(self._en) != num_bottleneck or len(self._de) != num_bottleneck:
+            raise ValueError("channel lists must have num_bottleneck entries")
+        self.num_bottleneck = int(num_bottleneck)
+        self._in_ch, self._out_ch = int(in_ch), int(out_ch)
+        nb = self.num_bottleneck
+        en = [self._in_ch] + self._en
+        de = self._de + [self._out_ch]
+        # construction order = the reference's (encoders, TCN, decoders) so that
+        # torch.manual_seed(s) followed by construction gives the reference's weights,
+        # registration order = the reference's (encoders, decoders, TCN) for state_dict.
+        self.encoders = nn.ModuleList()
+        self.decoders = nn.ModuleList()
+        for i in range(nb):
+            layers = []
+            if i < 5:
+                layers.append(_InitConv(en[i], en[i + 1]) if i == 0 else _Conv(en[i], en[i + 1], (1, 2)))
+                layers.append(_Dense(en[i + 1], en[i + 1], en[i + 1]))
+            elif i == nb - 1:
+                layers.append(_Conv(en[i], en[i + 1], (1, 1)))
+            else:
+                layers.append(_Conv(en[i], en[i + 1], (1, 2)))
+            self.encoders.append(nn.Sequential(*layers))
+        # model.py:31 hard-wires 128; the documented 257-bin layout (model.py:30) needs the
+        # bottleneck width, which is 128 for the shipped config.
+        self.TCN = _TCN(self.TCN_REPEATS, self.TCN_BLOCKS, en[nb])
+        for j in range(nb):
+            cin, cout = 2 * de[j], de[j + 1]
+            layers = []
+            if j >= 2:
+                layers.append(_Dense(cin, cin // 2, cin))
+                layers.append(_LastDeconv(cin, cout) if j == nb - 1 else _Deconv(cin, cout, (1, 2)))
+            elif j == 0:
+                layers.append(_Deconv(cin, cout, (1, 1)))
+            else:
+                layers.append(_Deconv(cin, cout, (1, 2)))
+            self.decoders.append(nn.Sequential(*layers))
+        self.sigmoid = nn.Sigmoid()     # model.py:37 (unused there too)
+        self._handle = None
+        self._handle_device = None
+        self._packed = {}
+        self._ws = None
+        self.max_workspace_bytes = 48 << 30   # batches are processed in chunks that fit this
+
+    # ---- handle / weights ------------------------------------------------------------
+    def _release(self):
+        if self._handle is not None:
+            _lib.load().miso_net_destroy(self._handle)
+            self._handle = None
+            self._packed = {}
+            self._ws = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _ensure_handle(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _lib.MisoError("misonet_b200 modules run on CUDA only (call .cuda() first); there is no CPU fallback")
+        if self._handle is not None and self._handle_device == dev:
+            return
+        self._release()
+        _lib.check_device(dev)
+        lib = _lib.load()
+        nb = self.num_bottleneck
+        h = ctypes.c_void_p()
+        en = (ctypes.c_int * nb)(*self._en)
+        de = (ctypes.c_int * nb)(*self._de)
+        with torch.cuda.device(dev):
+            _lib.check(lib.miso_net_create(ctypes.byref(h), self._in_ch, self._out_ch, nb, en, de, self.TCN_REPEATS,
+                                           self.TCN_BLOCKS), "miso_net_create")
+        self._handle, self._handle_device = h, dev
+        keys = [lib.miso_net_param_key(h, i).decode() for i in range(lib.miso_net_num_params(h))]
+        mine = [k for k, _ in self.named_parameters()]
+        if keys != mine:
+            raise _lib.MisoError("parameter key table of the library differs from the module's state_dict")
+
+    def _sync_params(self):
+        """(Re)pack every parameter whose storage or version changed since the last call."""
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        for key, p in self.named_parameters():
+            tag = (p.data_ptr(), p._version)
+            if self._packed.get(key) == tag:
+                continue
+            t = p.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            _lib.check(lib.miso_net_set_param(self._handle, key.encode(), _lib.ptr(t), t.numel(), st),
+                       f"miso_net_set_param({key})")
+            self._packed[key] = tag
+
+    def _workspace(self, nbytes, dev):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def _chunk(self, B, T, F):
+        lib = _lib.load()
+        _lib.check(lib.miso_net_check_shape(self._handle, T, F), "miso_net_check_shape")
+        per = lib.miso_net_workspace_bytes(self._handle, 1, T, F)
+        return max(1, min(B, int(self.max_workspace_bytes // max(per, 1))))
+
+    def _run_body(self, x_cl, B, T, F):
+        """x_cl: float32 [B,T,F,in_ch] channels-last -> float32 [B,T,F,out_ch]."""
+        lib = _lib.load()
+        dev = x_cl.device
+        y_cl = torch.empty(B, T, F, self._out_ch, dtype=torch.float32, device=dev)
+        step = self._chunk(B, T, F)
+        nbytes = lib.miso_net_workspace_bytes(self._handle, step, T, F)
+        ws = self._workspace(nbytes, dev)
+        st = _lib.stream_ptr()
+        for b0 in range(0, B, step):
+            nbat = min(step, B - b0)
+            _lib.check(lib.miso_net_forward(self._handle, _lib.ptr(x_cl[b0]), _lib.ptr(y_cl[b0]), nbat, T, F,
+                                            _lib.ptr(ws), ws.numel(), st), "miso_net_forward")
+        return y_cl
+
+    def _prepare(self, *tensors):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "misonet_b200: the backward pass is not implemented yet (SURVEY.md section 8(f) rank 1); "
+                "call under torch.no_grad()")
+        self._ensure_handle()
+        dev = self._handle_device
+        out = []
+        for t in tensors:
+            _lib.require_cuda(t, "input")
+            if t.device != dev:
+                raise _lib.MisoError(f"input on {t.device}, module on {dev}")
+            if not t.is_complex():
+                raise TypeError("expected a complex spectrogram [B, Ch, T, F] (model.py:77-78 reads .real/.imag)")
+            out.append(t.to(torch.complex64).contiguous())
+        return out
+
+    def _unpack(self, y_cl, B, T, F):
+        S = self._out_ch // 2
+        out = torch.empty(B, S, T, F, dtype=torch.complex64, device=y_cl.device)
+        _lib.check(_lib.load().miso_unpack_complex(_lib.ptr(y_cl), _lib.ptr(out), B, S, T, F, _lib.stream_ptr()),
+                   "miso_unpack_complex")
+        return out
+
+    def tap(self, name, B, T, F):
+        """Parity/debug: an internal activation of the last forward as the reference sees it (NCHW)."""
+        lib = _lib.load()
+        cap = B * T * F * 6 * max(self._en + self._de)
+        buf = torch.empty(cap, dtype=torch.float32, device=self._handle_device)
+        n = lib.miso_net_tap(self._handle, name.encode(), _lib.ptr(buf), cap, B, T, F, _lib.ptr(self._ws), _lib.stream_ptr())
+        _lib.check(n, "miso_net_tap")
+        return buf[:n]
+
+
+class MISO_1(_MisoNet):
+    """Separation network; same constructor and call signature as model.py:8-111."""
+
+    def __init__(self, num_spks, num_ch, num_bottleneck, en_bottleneck_channels, de_bottleneck_channels, norm_type="IN"):
+        super().__init__(2 * num_ch, 2 * num_spks, num_bottleneck, en_bottleneck_channels, de_bottleneck_channels, norm_type)
+        self.num_spks, self.num_ch = int(num_spks), int(num_ch)
+
+    def forward(self, mixture):
+        """mixture: complex [B, Mic, T, F] -> complex64 [B, Spk, T, F] (model.py:76-111)."""
+        return self.forward_shifts(mixture, (0,))
+
+    def forward_shifts(self, mixture, shifts):
+        """All circular microphone shifts of tester.py:1034,1049 as ONE batch:
+        returns complex64 [len(shifts)*B, Spk, T, F]; row k*B+b is model(roll(mix,-shifts[k],1))[b]."""
+        (mix,) = self._prepare(mixture)
+        B, M, T, F = mix.shape
+        if 2 * M != self._in_ch:
+            raise ValueError(f"expected {self._in_ch // 2} microphones, got {M}")
+        self._sync_params()
+        n = len(shifts)
+        x_cl = torch.empty(n * B, T, F, 2 * M, dtype=torch.float32, device=mix.device)
+        arr = (ctypes.c_int * n)(*[int(s) for s in shifts])
+        _lib.check(_lib.load().miso_pack_miso1(_lib.ptr(mix), _lib.ptr(x_cl), B, M, T, F, arr, n, _lib.stream_ptr()),
+                   "miso_pack_miso1")
+        y_cl = self._run_body(x_cl, n * B, T, F)
+        return self._unpack(y_cl, n * B, T, F)
+
+
+class MISO_3(_MisoNet):
+    """Enhancement network; same constructor and call signature as model.py:282-395."""
+
+    def __init__(self, num_spks, num_ch, num_bottleneck, en_bottleneck_channels, de_bottleneck_channels, norm_type="IN"):
+        super().__init__(2 * (num_ch + 2), 2 * num_spks, num_bottleneck, en_bottleneck_channels, de_bottleneck_channels,
+                         norm_type)
+        self.num_spks, self.num_ch = int(num_spks), int(num_ch)
+
+    def forward(self, mixture, MISO1, BF):
+        """Positional order is what matters (model.py:350 names the arguments (mixture, MISO1, BF)
+        but every caller passes (mix, beamformed, MISO1): tester.py:1242, trainer.py:398-414);
+        the weights see channels [mix x M, second, third].
+        mixture [B,M,T,F], second/third [B,1,T,F] complex -> complex64 [B, num_spks, T, F]."""
+        mix, second, third = self._prepare(mixture, MISO1, BF)
+        B, M, T, F = mix.shape
+        if 2 * (M + 2) != self._in_ch:
+            raise ValueError(f"expected {self._in_ch // 2 - 2} microphones, got {M}")
+        if second.shape != (B, 1, T, F) or third.shape != (B, 1, T, F):
+            raise ValueError("second/third inputs must be [B,1,T,F]")
+        self._sync_params()
+        x_cl = torch.empty(B, T, F, self._in_ch, dtype=torch.float32, device=mix.device)
+        _lib.check(_lib.load().miso_pack_miso3(_lib.ptr(mix), _lib.ptr(second), _lib.ptr(third), _lib.ptr(x_cl), B, M, T, F,
+                                               _lib.stream_ptr()), "miso_pack_miso3")
+        y_cl = self._run_body(x_cl, B, T, F)
+        return self._unpack(y_cl, B, T, F)

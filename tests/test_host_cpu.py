@@ -1,0 +1,140 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the header
+declares, host logic (shapes, sharding, key tables, error paths) and the world_size-2 gloo path."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+EN = [24, 32, 32, 32, 32, 64, 128]
+DE = [128, 64, 32, 32, 32, 32, 24]
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "misonet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(miso_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from misonet_b200 import _lib
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/misonet_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes table and header disagree"
+    assert lib.miso_abi_version() == 1
+
+
+def test_stft_frame_count_matches_oracle():
+    from misonet_b200 import audio
+    from oracle import miso_np
+    for n in (1, 63, 64, 65, 1000, 1024, 12345, 32000, 64000):
+        for nperseg, nover in ((256, 192), (512, 384)):
+            assert audio.stft_num_frames(n, nperseg, nover) == miso_np.stft_num_frames(n, nperseg, nover)
+    assert audio.stft_num_frames(32000) == 501
+
+
+def test_shard_range_partitions():
+    from misonet_b200.pipeline import shard_range
+    for n in (0, 1, 7, 16, 33):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_module_keys_shapes_and_reference_init():
+    from misonet_b200.model import MISO_1, MISO_3
+    from oracle import weights, ref_import
+    from oracle import miso_net_torch as mnt
+    en, de = list(EN), list(DE)
+    m1 = MISO_1(2, 6, 7, en, de, "IN")
+    assert en == EN and de == DE, "constructor must not mutate the caller's lists (model.py:16-17 does)"
+    shapes = weights.param_shapes(mnt.NetConfig.miso1())
+    sd = m1.state_dict()
+    assert list(sd.keys()) == list(shapes.keys()) and len(sd) == 268
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    m3 = MISO_3(1, 6, 7, en, de, "IN")
+    assert sum(p.numel() for p in m3.parameters()) == 2587382
+    p8 = MISO_1(2, 6, 8, [24, 32, 32, 32, 32, 64, 128, 384], [384, 128, 64, 32, 32, 32, 32, 24], "IN")
+    assert sum(p.numel() for p in p8.parameters()) == 8579704
+    if ref_import.available():
+        ns = ref_import.load()
+        torch.manual_seed(0)
+        r = ns.model.MISO_1(2, 6, 7, list(EN), list(DE), "IN")
+        torch.manual_seed(0)
+        o = MISO_1(2, 6, 7, list(EN), list(DE), "IN")
+        rs, os_ = r.state_dict(), o.state_dict()
+        assert list(rs.keys()) == list(os_.keys())
+        assert all(torch.equal(rs[k], os_[k]) for k in rs), "same seed must give the reference's initial weights"
+
+
+def test_no_cpu_fallback():
+    from misonet_b200 import _lib, audio, beamforming, criterion
+    from misonet_b200.model import MISO_1
+    m = MISO_1(2, 6, 7, list(EN), list(DE), "IN")
+    x = torch.zeros(1, 6, 4, 129, dtype=torch.complex64)
+    with torch.no_grad():
+        with pytest.raises(_lib.MisoError):
+            m(x)
+    with pytest.raises(_lib.MisoError):
+        audio.stft(torch.zeros(1000, 2))
+    with pytest.raises(_lib.MisoError):
+        criterion.loss_Enhance(x, x)
+    with pytest.raises(_lib.MisoError):
+        beamforming.mvdr(torch.zeros(1, 1, 6, 4, 9, dtype=torch.complex64), torch.zeros(1, 6, 4, 9, dtype=torch.complex64))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under misonet_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "misonet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), fn
+                assert "/root/reference" not in text, fn
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from misonet_b200 import distributed as D
+rank, world, local = D.init_from_env("gloo")
+n_total = 7
+lo, hi = D.shard_range(n_total, rank, world)
+# a per-utterance "loss" and "decision" that only depend on the global utterance index
+loss = sum(float(i + 1) for i in range(lo, hi))
+idx = torch.tensor([i % 2 for i in range(lo, hi)], dtype=torch.long)
+mean, count = D.reduce_metrics(loss, hi - lo)
+allidx = D.gather_perm_indices(idx, n_total)
+mx = D.max_over_ranks(10.0 * (rank + 1))
+D.barrier()
+assert count == n_total and abs(mean - 4.0) < 1e-12, (mean, count)
+assert allidx.tolist() == [i % 2 for i in range(n_total)], allidx
+assert mx == 10.0 * world
+if rank == 0:
+    print("GLOO_OK", world)
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "GLOO_OK 2" in res.stdout
