@@ -134,7 +134,11 @@ __global__ void __launch_bounds__(64) eig_kernel(const float *__restrict__ parti
             for (int q = p + 1; q < M; ++q) off += Ar[p][q] * Ar[p][q] + Ai[p][q] * Ai[p][q];
         }
         if (off <= 1e-30 * dg || off == 0.0) break;
+        // unroll 1: nvcc 12.9 -O3 miscompiles the fully unrolled rotation sweep (verified on B200:
+        // wrong eigenvectors at -O3, correct at -O0 and with rolled loops; tools/eig_test.cu)
+#pragma unroll 1
         for (int p = 0; p < M - 1; ++p)
+#pragma unroll 1
             for (int q = p + 1; q < M; ++q) {
                 const double xr = Ar[p][q], xi = Ai[p][q];
                 const double ax = sqrt(xr * xr + xi * xi);
@@ -230,6 +234,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ pa
             Ar[m][m] += epsi;  // tester.py:1221
         }
         // Gaussian elimination with partial pivoting on [A | u]
+#pragma unroll 1
         for (int k = 0; k < M; ++k) {
             int piv = k;
             double best = Ar[k][k] * Ar[k][k] + Ai[k][k] * Ai[k][k];
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ pa
                 ui[r] -= lr * ui[k] + li * ur[k];
             }
         }
+#pragma unroll 1
         for (int k = M - 1; k >= 0; --k) {
             double sr = ur[k], si = ui[k];
             for (int c = k + 1; c < M; ++c) {
