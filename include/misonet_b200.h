@@ -86,7 +86,10 @@ int64_t miso_net_param_numel(const miso_net_t *net, int i);
 /* (re)pack one parameter from a DEVICE fp32 tensor in the reference's layout
  * (Conv2d [Cout,Cin,3,3], ConvTranspose2d [Cin,Cout,3,3], Conv1d [C,1,3]/[C,C,1], ...). */
 int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, int64_t numel, void *stream);
-/* compute precision of the 3x3 (de)conv stack: 0 = fp32 FMA (parity mode). */
+/* compute path of the stride-1 3x3 (de)convs with <= 64 output channels (the DenseBlocks, 94 % of the
+ * FLOPs): 0 = fp32 FMA everywhere; 1 = tcgen05 bf16x3 split (fp32-grade accuracy, 3 MMAs per product);
+ * 2 = tcgen05 bf16 operands, fp32 accumulate (throughput mode, ~1e-2 relative error).
+ * The remaining layers (strided convs, TCN) always run in fp32. */
 int miso_net_set_mode(miso_net_t *net, int mode);
 /* F must reduce to exactly 1 at the bottleneck (129 for 7 blocks, 257 for 8); returns
  * MISO_E_ARG with a clear message otherwise (the reference raises an opaque conv error). */

@@ -35,8 +35,19 @@ struct ConvArgs {
     float norm_eps;
     double norm_inv_n;  // 1 / (elements per statistic)
     int elu;
+    // tcgen05 path only (conv_tc.cu)
+    const void *w_tc;  // bf16 weight image in shared-memory order, or null
+    int cout_pad16;    // cout rounded up to the UMMA N granularity (16 at M = 128)
+    int tc_G;          // 128-row M tiles per CTA (set by the launcher)
 };
 
 int launch_conv_fp32(const ConvArgs &a, cudaStream_t stream);
+
+// tensor-core path: split = 1 (bf16) or 3 (bf16x3, parity-grade)
+bool conv_tc_eligible(const ConvArgs &a);
+int launch_conv_tc(const ConvArgs &a, int split, cudaStream_t stream);
+size_t conv_tc_weight_elems(int cin, int cout_pad16, int nsp);
+int pack_conv_tc_weights(const float *d_w, void *d_img, int cout, int cin, int cout_pad16, int nsp, int transposed,
+                         cudaStream_t stream);
 
 }  // namespace miso

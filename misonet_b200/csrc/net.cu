@@ -215,12 +215,16 @@ struct Param {
     float *d;                       // packed device storage (owned by the arena)
     size_t packed_elems;
     bool loaded;
+    void *tc1 = nullptr, *tc3 = nullptr;  // bf16 / bf16 hi+lo weight images for the tcgen05 path
+    int cout_pad16 = 0;
 };
 
 struct ConvDesc {
     int w = -1, b = -1;  // param indices
     int cin = 0, cout = 0, cout_pad = 0;
 };
+
+constexpr int kTcMaxN = 64;
 
 struct TcnHalf {
     int dw, alpha, gamma, beta, pw;
@@ -454,6 +458,9 @@ int run_conv(const miso_net *n, const ConvDesc &cd, bool transposed, const float
     a.norm_eps = kInEps;
     a.norm_inv_n = 1.0 / ((double)T * Fin);
     a.elu = elu ? 1 : 0;
+    a.cout_pad16 = n->params[cd.w].cout_pad16;
+    a.w_tc = n->mode == 1 ? n->params[cd.w].tc3 : (n->mode == 2 ? n->params[cd.w].tc1 : nullptr);
+    if (n->mode != 0 && conv_tc_eligible(a)) return launch_conv_tc(a, n->mode == 1 ? 3 : 1, st);
     return launch_conv_fp32(a, st);
 }
 
@@ -544,6 +551,17 @@ int miso_net_create(miso_net_t **out, int in_ch, int out_ch, int num_bottleneck,
     for (auto &p : n->params) {
         p.d = n->arena + off;
         off += align_up(p.packed_elems, 64);
+        if ((p.kind == P_CONV_W || p.kind == P_DECONV_W) && p.taps == 9) {
+            p.cout_pad16 = (p.cout + 15) / 16 * 16;
+            if (p.cout_pad16 <= kTcMaxN) {
+                cudaError_t e1 = cudaMalloc(&p.tc1, conv_tc_weight_elems(p.cin, p.cout_pad16, 1) * 2);
+                cudaError_t e3 = cudaMalloc(&p.tc3, conv_tc_weight_elems(p.cin, p.cout_pad16, 2) * 2);
+                if (e1 != cudaSuccess || e3 != cudaSuccess) {
+                    miso_net_destroy(n);
+                    return cuda_fail(e1 != cudaSuccess ? e1 : e3, "cudaMalloc(tcgen05 weight images)");
+                }
+            }
+        }
     }
     *out = n;
     return MISO_OK;
@@ -552,6 +570,10 @@ int miso_net_create(miso_net_t **out, int in_ch, int out_ch, int num_bottleneck,
 int miso_net_destroy(miso_net_t *net) {
     if (!net) return MISO_OK;
     if (net->arena) cudaFree(net->arena);
+    for (auto &p : net->params) {
+        if (p.tc1) cudaFree(p.tc1);
+        if (p.tc3) cudaFree(p.tc3);
+    }
     delete net;
     return MISO_OK;
 }
@@ -582,6 +604,13 @@ int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, in
             pack_conv_w_kernel<<<blocks, 256, 0, st>>>(d_data, p.d, p.cout, p.cin, p.taps, p.cout_pad,
                                                       p.kind == P_DECONV_W ? 1 : 0);
             MISO_LAUNCHED("pack_conv_w_kernel");
+            if (p.tc1) {
+                const int tr = p.kind == P_DECONV_W ? 1 : 0;
+                int rc = pack_conv_tc_weights(d_data, p.tc1, p.cout, p.cin, p.cout_pad16, 1, tr, st);
+                if (rc) return rc;
+                rc = pack_conv_tc_weights(d_data, p.tc3, p.cout, p.cin, p.cout_pad16, 2, tr, st);
+                if (rc) return rc;
+            }
             break;
         }
         case P_BIAS:
@@ -601,7 +630,8 @@ int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, in
 
 int miso_net_set_mode(miso_net_t *net, int mode) {
     MISO_REQUIRE(net, "miso_net_set_mode: null handle");
-    MISO_REQUIRE(mode == 0, "miso_net_set_mode: mode %d not available in this build (0 = fp32 FMA)", mode);
+    MISO_REQUIRE(mode >= 0 && mode <= 2, "miso_net_set_mode: mode %d unknown (0 fp32 FMA, 1 bf16x3 tcgen05, 2 bf16 tcgen05)",
+                 mode);
     net->mode = mode;
     return MISO_OK;
 }

@@ -145,6 +145,9 @@ class _MisoNet(nn.Module):
         self._packed = {}
         self._ws = None
         self.max_workspace_bytes = 48 << 30   # batches are processed in chunks that fit this
+        # compute path of the stride-1 3x3 convs (include/misonet_b200.h, miso_net_set_mode):
+        # "fp32" FMA | "bf16x3" tcgen05 split (fp32-grade) | "bf16" tcgen05 (throughput)
+        self.conv_mode = "fp32"
 
     # ---- handle / weights ------------------------------------------------------------
     def _release(self):
@@ -189,6 +192,10 @@ class _MisoNet(nn.Module):
         """(Re)pack every parameter whose storage or version changed since the last call."""
         lib = _lib.load()
         st = _lib.stream_ptr()
+        modes = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+        if self.conv_mode not in modes:
+            raise ValueError(f"conv_mode must be one of {sorted(modes)}")
+        _lib.check(lib.miso_net_set_mode(self._handle, modes[self.conv_mode]), "miso_net_set_mode")
         for key, p in self.named_parameters():
             tag = (p.data_ptr(), p._version)
             if self._packed.get(key) == tag:
