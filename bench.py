@@ -44,6 +44,12 @@ WORKLOADS = {
     "pipeline_ref": dict(layout="REF", B=32, M=6, T=501, F=129, kind="pipeline", n_samples=32000,
                          desc="STFT->MISO1x6->align->MVDRx2->MISO3x2, batch 32 per GPU (BASELINE configs[2], REF shape)"),
 }
+PROF_FAMILIES = {0: "conv_fp32_kernel (fp32 FMA implicit-GEMM conv / deconv / pointwise)",
+                 1: "conv_tc_kernel (tcgen05 implicit-GEMM 3x3 conv, TMEM accumulators)",
+                 2: "tcn kernels", 3: "mvdr kernels"}
+CONV_MODES = {"fp32": ("f32", "fp32 FMA everywhere (reference-grade, ~2e-6 rel. error)"),
+              "bf16x3": ("bf16x3", "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (parity-grade, ~2e-5 rel. error)"),
+              "bf16": ("bf16", "tcgen05 bf16 operands, fp32 accumulate (throughput mode, ~1e-2 rel. error: outside north_star's 1e-3)")}
 # algorithmic conv-stack work per utterance, SURVEY.md section 8(d) / appendix A
 GFLOP_PER_UTT = {"REF": 75.151, "PAPER": 163.37}
 
@@ -144,10 +150,12 @@ def run_ours(args, wl, rank, world, local):
     m1 = MISO_1(2, M, len(en), list(en), list(de), "IN")
     m1.load_state_dict(make_state_dict_np(m1, 0))
     m1 = m1.cuda(dev).eval()
+    m1.conv_mode = args.conv_mode
     if wl["kind"] == "pipeline":
         m3 = MISO_3(1, M, len(en), list(en), list(de), "IN")
         m3.load_state_dict(make_state_dict_np(m3, 1))
         m3 = m3.cuda(dev).eval()
+        m3.conv_mode = args.conv_mode
         pipe = pipeline.MisoBfMiso(m1, m3)
         g = torch.Generator().manual_seed(100 + rank)
         host_in = (0.05 * torch.randn(B, wl["n_samples"], M, generator=g)).pin_memory()
@@ -187,8 +195,11 @@ def run_ours(args, wl, rank, world, local):
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count() - launches0
         lib.miso_prof_enable(0)
-        cm, cf, cb, cn = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
-        _lib.check(lib.miso_prof_collect(ctypes.byref(cm), ctypes.byref(cf), ctypes.byref(cb), ctypes.byref(cn)))
+        fams = {}
+        for fid, fname in PROF_FAMILIES.items():
+            cm, cf, cb, cn = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
+            _lib.check(lib.miso_prof_collect(fid, ctypes.byref(cm), ctypes.byref(cf), ctypes.byref(cb), ctypes.byref(cn)))
+            fams[fname] = dict(ms=cm.value, flops=cf.value, bytes=cb.value, launches=int(cn.value))
         clocks = sampler.stop() if sampler else None
 
         # ---- end to end through the public API: pinned host in -> H2D -> step -> D2H ----
@@ -211,8 +222,14 @@ def run_ours(args, wl, rank, world, local):
         return None
     pk = peaks()
     total_frames = frames_per_step * world * args.steps
-    conv_ms, conv_flops, conv_launches = cm.value, cf.value, cn.value
+    dom = max(fams, key=lambda k: fams[k]["ms"])
+    conv_ms, conv_flops, conv_launches = fams[dom]["ms"], fams[dom]["flops"], fams[dom]["launches"]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    fam_report = {k: {"ms_per_step": v["ms"] / args.steps, "share_of_step": v["ms"] / ms if ms > 0 else None,
+                      "launches_per_step": v["launches"] // max(args.steps, 1),
+                      "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0,
+                      "algorithmic_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0}
+                  for k, v in fams.items() if v["launches"]}
     line = {
         "metric": "frames/sec MISO-BF-MISO fwd 6ch/257bin at 1/2/4/8 GPU; SI-SDR vs ref",
         "value": total_frames / (ms * 1e-3),
@@ -220,23 +237,24 @@ def run_ours(args, wl, rank, world, local):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic (seeded random spectrograms / waveforms, seeded random weights)",
+        "dtype": CONV_MODES[args.conv_mode][0], "data": "synthetic (seeded random spectrograms / waveforms, seeded random weights)",
         "config": {"workload": wl["desc"], "layout": wl["layout"], "per_gpu_batch": B, "global_batch": B * world,
                    "frames": T, "bins": F, "mics": M, "parallelism": f"utterance-sharded x{world}, no data-path collective",
-                   "conv_mode": "fp32 FMA (parity mode)",
+                   "conv_mode": f"{args.conv_mode}: {CONV_MODES[args.conv_mode][1]}",
                    "l2": "activation working set per step is several GB (>> 126 MB L2), so every step starts cold"},
         "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s",
                 "h2d_bytes_per_step": int(host_in.numel() * host_in.element_size()),
                 "d2h_bytes_per_step": int(host_out.numel() * host_out.element_size())},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_fp32_kernel (3x3 conv / deconv / pointwise implicit GEMM family)",
+        "roofline": {"bound": "tensor", "kernel": dom,
                      "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
                      "launches": int(conv_launches), "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms if ms > 0 else None,
-                     "note": "algorithmic 2*MAC of the conv launches / summed CUDA-event time of those launches, "
-                             "measured inside the timed region; fp32 FMA pipe, tensor cores not yet used"},
+                     "families": fam_report,
+                     "note": "algorithmic 2*MAC of the launches of the dominant kernel family / summed CUDA-event time of "
+                             "those launches, measured inside the timed region (bf16x3 issues 3 MMAs per algorithmic MAC)"},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, steps=1)
@@ -305,6 +323,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="miso1_paper", choices=sorted(WORKLOADS))
+    ap.add_argument("--conv-mode", default="bf16x3", choices=sorted(CONV_MODES),
+                    help="compute path of the conv stack (default: the parity-grade tensor-core mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (profiling runs only)")
     args = ap.parse_args()

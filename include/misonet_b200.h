@@ -54,8 +54,14 @@ uint64_t miso_launch_count(void);
  * the recorded events, returns the summed device time, the ALGORITHMIC flops and bytes
  * of those launches (2*MAC; each conv reads its logical input
  * once and writes its output once) and their count, and clears the record. */
+#define MISO_PROF_ALL (-1)
+#define MISO_PROF_CONV_FP32 0 /* fp32 FMA implicit-GEMM (de)conv / pointwise kernels */
+#define MISO_PROF_CONV_TC 1   /* tcgen05 implicit-GEMM conv kernels */
+#define MISO_PROF_TCN 2       /* fused TCN kernels */
+#define MISO_PROF_MVDR 3      /* MVDR kernels */
 int miso_prof_enable(int on);
-int miso_prof_collect(double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches);
+/* collects (and clears) the records of one family, or of all with MISO_PROF_ALL */
+int miso_prof_collect(int family, double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches);
 
 /* ---- S1: STFT front end -------------------------------------------------------
  * replaces AudioDataset.STFT + "/scale" + permute, dataloader/data.py:49-66,77-79

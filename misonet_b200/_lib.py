@@ -20,7 +20,7 @@ SIGNATURES = {
     "miso_check_device": (c_int, []),
     "miso_launch_count": (c_uint64, []),
     "miso_prof_enable": (c_int, [c_int]),
-    "miso_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+    "miso_prof_collect": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                   POINTER(c_uint64)]),
     "miso_stft_num_frames": (c_int, [c_int, c_int, c_int]),
     "miso_stft_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

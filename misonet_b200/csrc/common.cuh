@@ -44,7 +44,7 @@ inline int cuda_fail(cudaError_t e, const char *what) {
 // optional per-launch event timing of the dominant kernel family (runtime.cu)
 bool prof_enabled();
 void prof_begin(cudaStream_t st);
-void prof_end(cudaStream_t st, double flops, double bytes);
+void prof_end(cudaStream_t st, double flops, double bytes, int family);
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -251,7 +251,7 @@ int launch(const ConvArgs &a, cudaStream_t stream) {
         const double pix = (double)a.B * a.T * (a.transposed ? a.Fin : a.Fout);
         const double flops = 2.0 * pix * a.cin * a.cout * a.KT * a.KF;
         const double bytes = 4.0 * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
-        prof_end(stream, flops, bytes);
+        prof_end(stream, flops, bytes, MISO_PROF_CONV_FP32);
     }
     MISO_LAUNCHED("conv_fp32_kernel");
     return MISO_OK;

@@ -439,7 +439,7 @@ int launch_conv_tc(const ConvArgs &a_in, int split, cudaStream_t stream) {
     {
         const double flops = 2.0 * a.B * a.T * a.Fout * a.cin * a.cout * 9.0;
         const double bytes = 4.0 * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
-        prof_end(stream, flops, bytes);
+        prof_end(stream, flops, bytes, MISO_PROF_CONV_TC);
     }
     MISO_LAUNCHED("conv_tc_kernel");
     return MISO_OK;

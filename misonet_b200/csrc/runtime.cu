@@ -22,6 +22,7 @@ namespace {
 struct ProfRec {
     cudaEvent_t a, b;
     double flops, bytes;
+    int family;
 };
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
@@ -48,7 +49,7 @@ void prof_begin(cudaStream_t st) {
     g_open = get_event();
     cudaEventRecord(g_open, st);
 }
-void prof_end(cudaStream_t st, double flops, double bytes) {
+void prof_end(cudaStream_t st, double flops, double bytes, int family) {
     if (!g_open) return;
     ProfRec r;
     r.a = g_open;
@@ -57,6 +58,7 @@ void prof_end(cudaStream_t st, double flops, double bytes) {
     cudaEventRecord(r.b, st);
     r.flops = flops;
     r.bytes = bytes;
+    r.family = family;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(r);
 }
@@ -70,11 +72,13 @@ int miso_prof_enable(int on) {
     return MISO_OK;
 }
 
-int miso_prof_collect(double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches) {
+int miso_prof_collect(int family, double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches) {
     std::vector<miso::ProfRec> recs;
     {
         std::lock_guard<std::mutex> lk(miso::g_prof_mu);
-        recs.swap(miso::g_prof);
+        std::vector<miso::ProfRec> keep;
+        for (auto &r : miso::g_prof) (family < 0 || r.family == family ? recs : keep).push_back(r);
+        miso::g_prof.swap(keep);
     }
     double ms = 0.0, fl = 0.0, by = 0.0;
     for (auto &r : recs) {

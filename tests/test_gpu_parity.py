@@ -116,6 +116,45 @@ def test_net_full_size_vs_oracle():
     assert e < 2e-4 and e < REQUIRED_TOL
 
 
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 2e-4), ("bf16", 5e-2)])
+def test_net_tensor_core_modes_vs_oracle(mode, tol):
+    """tcgen05 conv path.  bf16x3 (hi/lo split, 3 MMAs per product) must meet north_star's 1e-3 with a wide
+    margin; plain bf16 operands are a throughput mode whose error is reported, not held to 1e-3
+    (bf16 operands give ~1e-2 vs the fp32 reference)."""
+    from misonet_b200 import synth
+    from oracle import miso_net_torch as mnt
+    m, cfg, sd = _model("miso1", 0)
+    m.conv_mode = mode
+    mix = synth.random_spec(3, (1, 6, 501, 129))
+    ref = mnt.miso1_forward(sd, cfg, torch.from_numpy(mix)).numpy()
+    with torch.no_grad():
+        y = m(torch.from_numpy(mix).cuda()).cpu().numpy()
+    e = rel_err(y, ref)
+    print(f"full-size MISO_1 {mode} rel err", e)
+    assert e < tol
+    if mode == "bf16x3":
+        assert e < REQUIRED_TOL
+    # ragged T / small batch shapes through the same kernels, PAPER layout
+    m2, cfg2, sd2 = _model("miso1", 3, layout="PAPER")
+    m2.conv_mode = mode
+    mix2 = synth.random_spec(1, (2, 6, 13, 257))
+    ref2 = mnt.miso1_forward(sd2, cfg2, torch.from_numpy(mix2)).numpy()
+    with torch.no_grad():
+        y2 = m2(torch.from_numpy(mix2).cuda()).cpu().numpy()
+    assert rel_err(y2, ref2) < tol
+
+
+def test_net_tensor_core_decisions_match_fp32():
+    """The alignment decisions of the shifted MISO1 inference must not change with the conv mode."""
+    from misonet_b200 import separation, synth
+    m, cfg, sd = _model("miso1", 0)
+    mix = torch.from_numpy(synth.random_spec(60, (2, 6, 40, 129))).cuda()
+    _, p0 = separation.miso1_inference(m, mix, ref_ch=1, return_perm=True)
+    m.conv_mode = "bf16x3"
+    _, p1 = separation.miso1_inference(m, mix, ref_ch=1, return_perm=True)
+    assert torch.equal(p0, p1)
+
+
 def test_net_paper_layout_vs_oracle():
     """8-block / 257-bin / 384-wide-TCN layout (model.py:13-14,30 comments) against the oracle."""
     from misonet_b200 import synth
