@@ -92,17 +92,23 @@ int64_t miso_net_param_numel(const miso_net_t *net, int i);
 /* (re)pack one parameter from a DEVICE fp32 tensor in the reference's layout
  * (Conv2d [Cout,Cin,3,3], ConvTranspose2d [Cin,Cout,3,3], Conv1d [C,1,3]/[C,C,1], ...). */
 int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, int64_t numel, void *stream);
-/* compute path of the stride-1 3x3 (de)convs with <= 64 output channels (the DenseBlocks, 94 % of the
- * FLOPs): 0 = fp32 FMA everywhere; 1 = tcgen05 bf16x3 split (fp32-grade accuracy, 3 MMAs per product);
- * 2 = tcgen05 bf16 operands, fp32 accumulate (throughput mode, ~1e-2 relative error).
- * The remaining layers (strided convs, TCN) always run in fp32. */
+/* compute path of the 3x3 (de)convs: 0 = fp32 FMA kernels everywhere; 1 = tcgen05 bf16x3 split
+ * (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 accumulate: parity-grade, 3 MMAs per product); 2 = tcgen05
+ * bf16 operands and hi-only activation planes (throughput mode, ~1e-2 relative error).
+ * The TCN always runs in fp32. */
 int miso_net_set_mode(miso_net_t *net, int mode);
 /* F must reduce to exactly 1 at the bottleneck (129 for 7 blocks, 257 for 8); returns
  * MISO_E_ARG with a clear message otherwise (the reference raises an opaque conv error). */
 int miso_net_check_shape(const miso_net_t *net, int T, int F);
 size_t miso_net_workspace_bytes(const miso_net_t *net, int B, int T, int F);
-/* d_x : fp32 channels-last [B, T, F, in_ch]; d_y : fp32 channels-last [B, T, F, out_ch]. */
-int miso_net_forward(miso_net_t *net, const float *d_x, float *d_y, int B, int T, int F, void *d_ws,
+/* Network input layout ("planes"): bf16 [B][2: hi, lo][in_pad/8][T][F][8] with in_pad = in_ch rounded
+ * up to 8; value = hi + lo (16-17 mantissa bits), padding channels are zero.  Written by
+ * miso_pack_miso1 / miso_pack_miso3; miso_net_input_bytes gives the buffer size (128-byte aligned base).
+ * All internal activations use the same layout: a [T, F] tile of 8 channels is a dense box of
+ * 16-byte pixels, which TMA moves straight into the UMMA operand layout. */
+size_t miso_net_input_bytes(const miso_net_t *net, int B, int T, int F);
+/* d_x : input planes (above); d_y : fp32 channels-last [B, T, F, out_ch]. */
+int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T, int F, void *d_ws,
                      size_t ws_bytes, void *stream);
 /* debugging / parity taps: copy an internal activation of the LAST forward on this
  * workspace into a dense NCHW fp32 tensor (normalised as the reference sees it).
@@ -111,15 +117,15 @@ int64_t miso_net_tap(miso_net_t *net, const char *name, float *d_out, int64_t ca
                      void *d_ws, void *stream);
 
 /* input / output layout adapters (model.py:76-80, 109-111; 358-366):
- * pack_miso1 : mixture complex64 [B,M,T,F] -> [n_shift*B, T, F, 2M] with the mic axis
+ * pack_miso1 : mixture complex64 [B,M,T,F] -> input planes of n_shift*B samples with the mic axis
  *              circularly rolled by -shift[k] (torch.roll(mix,-q,dims=1), tester.py:1034,1049);
  *              batch index of (k, b) is k*B + b;  channels = re(m0..), im(m0..).
- * pack_miso3 : (mix [B,M,T,F], second [B,1,T,F], third [B,1,T,F]) -> [B,T,F,2(M+2)]
+ * pack_miso3 : (mix [B,M,T,F], second [B,1,T,F], third [B,1,T,F]) -> input planes, 2(M+2) channels
  *              in the positional order every caller uses (tester.py:1242).
  * unpack     : channels-last [B,T,F,2S] -> complex64 [B,S,T,F]. */
-int miso_pack_miso1(const void *d_mix, float *d_x, int B, int M, int T, int F, const int *shifts, int n_shift,
+int miso_pack_miso1(const void *d_mix, void *d_x, int B, int M, int T, int F, const int *shifts, int n_shift,
                     void *stream);
-int miso_pack_miso3(const void *d_mix, const void *d_second, const void *d_third, float *d_x, int B, int M, int T,
+int miso_pack_miso3(const void *d_mix, const void *d_second, const void *d_third, void *d_x, int B, int M, int T,
                     int F, void *stream);
 int miso_unpack_complex(const float *d_y, void *d_out, int B, int S, int T, int F, void *stream);
 

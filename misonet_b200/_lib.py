@@ -33,6 +33,7 @@ SIGNATURES = {
     "miso_net_set_mode": (c_int, [c_void_p, c_int]),
     "miso_net_check_shape": (c_int, [c_void_p, c_int, c_int]),
     "miso_net_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "miso_net_input_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "miso_net_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "miso_net_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "miso_pack_miso1": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p]),

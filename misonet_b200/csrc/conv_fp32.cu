@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(const ConvArgs a) {
     }
     const int nchunk = (a.cin + BK - 1) / BK;
     const int nk = a.KT * a.KF * nchunk;
-    const float *in_b = a.in + (size_t)b * a.T * a.Fin * a.in_ctot + a.in_coff;
+    const float *in_b = reinterpret_cast<const float *>(a.in) + (size_t)b * a.T * a.Fin * a.in_ctot + a.in_coff;
+    // plane layout: [B][hi|lo][in_ctot/8][T][Fin][8] bf16
+    const __nv_bfloat16 *in_pl = reinterpret_cast<const __nv_bfloat16 *>(a.in) + (size_t)b * 2 * a.in_ctot * a.T * a.Fin;
+    const bool in_planes = a.in_layout == LAYOUT_PLANES;
 
     float4 ra[4];
     float4 rb[B_PER_THREAD];
@@ -104,7 +107,21 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(const ConvArgs a) {
             ok = ok && ti >= 0 && ti < a.T && fi >= 0 && fi < a.Fin;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok) {
-                v = __ldg(reinterpret_cast<const float4 *>(in_b + ((size_t)ti * a.Fin + fi) * a.in_ctot + c));
+                if (in_planes) {
+                    const int ca = a.in_coff + c;
+                    const __nv_bfloat16 *p = in_pl + (((size_t)(ca >> 3) * a.T + ti) * a.Fin + fi) * 8 + (ca & 7);
+                    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(p));
+                    v = make_float4(bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y));
+                    if (a.use_lo) {
+                        const uint2 l = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(p) + a.in_lo_off));
+                        v.x += bf16_lo(l.x);
+                        v.y += bf16_hi(l.x);
+                        v.z += bf16_lo(l.y);
+                        v.w += bf16_hi(l.y);
+                    }
+                } else {
+                    v = __ldg(reinterpret_cast<const float4 *>(in_b + ((size_t)ti * a.Fin + fi) * a.in_ctot + c));
+                }
                 v.x = fmaf(v.x, f0.x, f0.y);
                 v.y = fmaf(v.y, f1.x, f1.y);
                 v.z = fmaf(v.z, f2.x, f2.y);
@@ -186,7 +203,9 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(const ConvArgs a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) ssum[j] = ssq[j] = 0.f;
 
-    float *out_b = a.out + (size_t)b * npix * a.out_ctot + a.out_coff;
+    float *out_b = reinterpret_cast<float *>(a.out) + (size_t)b * npix * a.out_ctot + a.out_coff;
+    __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
+    const bool out_planes = a.out_layout == LAYOUT_PLANES;
     const float *res_b = a.resid ? a.resid + (size_t)b * npix * a.resid_ctot + a.resid_coff : nullptr;
     const int co0 = n0 + tx * TN;
     const bool vec_ok = (TN % 4 == 0) && ((a.out_ctot & 3) == 0) && ((a.out_coff & 3) == 0) && (co0 + TN <= a.cout);
@@ -203,6 +222,40 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(const ConvArgs a) {
             v[j] = x;
             ssum[j] += x;
             ssq[j] += x * x;
+        }
+        if (out_planes) {
+            // channels co0 .. co0+TN-1 of pixel `pix` in the [C/8][T*F][8] plane layout, hi and lo sets
+#pragma unroll
+            for (int j0 = 0; j0 < TN; j0 += 4) {
+                const int ca = a.out_coff + co0 + j0;
+                __nv_bfloat16 *p = out_pl + ((size_t)(ca >> 3) * npix + pix) * 8 + (ca & 7);
+                if constexpr (TN >= 4) {
+                    if (co0 + j0 + 4 <= a.cout) {
+                        float h[4], l[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            h[q] = bf16_round(v[j0 + q]);
+                            l[q] = v[j0 + q] - h[q];
+                        }
+                        *reinterpret_cast<uint2 *>(p) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+                        if (a.use_lo)
+                            *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(p) + a.out_lo_off) =
+                                make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+                        continue;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < (TN < 4 ? TN : 4); ++q) {
+                    if (co0 + j0 + q < a.cout) {
+                        const float h = bf16_round(v[j0 + q]);
+                        p[q] = __float2bfloat16_rn(h);
+                        if (a.use_lo)
+                            *reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<char *>(p + q) + a.out_lo_off) =
+                                __float2bfloat16_rn(v[j0 + q] - h);
+                    }
+                }
+            }
+            continue;
         }
         float *o = out_b + (size_t)pix * a.out_ctot + co0;
         if (vec_ok) {
@@ -250,7 +303,7 @@ int launch(const ConvArgs &a, cudaStream_t stream) {
         // algorithmic work: a transposed conv does one MAC per input pixel and tap
         const double pix = (double)a.B * a.T * (a.transposed ? a.Fin : a.Fout);
         const double flops = 2.0 * pix * a.cin * a.cout * a.KT * a.KF;
-        const double bytes = 4.0 * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
+        const double bytes = 4.0 * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);  // fp32-equivalent (hi + lo)
         prof_end(stream, flops, bytes, MISO_PROF_CONV_FP32);
     }
     MISO_LAUNCHED("conv_fp32_kernel");
@@ -262,6 +315,9 @@ int launch(const ConvArgs &a, cudaStream_t stream) {
 int conv_fp32_tile_n(int cout) { return cout <= 8 ? 8 : (cout <= 32 ? 32 : 64); }
 
 int launch_conv_fp32(const ConvArgs &a, cudaStream_t stream) {
+    MISO_REQUIRE(a.in_layout != LAYOUT_PLANES || a.in_ctot % 8 == 0, "conv: plane layout needs in_ctot %% 8 == 0");
+    MISO_REQUIRE(a.out_layout != LAYOUT_PLANES || (a.out_ctot % 8 == 0 && a.out_coff % 4 == 0),
+                 "conv: plane layout needs out_ctot %% 8 == 0 and out_coff %% 4 == 0");
     MISO_REQUIRE(a.cin % 4 == 0 && a.in_ctot % 4 == 0 && a.in_coff % 4 == 0,
                  "conv: input channel counts/offsets must be multiples of 4 (cin=%d ctot=%d coff=%d)", a.cin, a.in_ctot,
                  a.in_coff);

@@ -1,46 +1,104 @@
-// tcgen05 implicit-GEMM 3x3 stride-1 convolution over channels-last activations -- the
-// tensor-core path of the MISO conv stack (the DenseBlock convs, model.py:437-482, are 94 %
-// of all FLOPs).
+// tcgen05 implicit-GEMM (de)convolution over bf16 hi/lo activation planes -- the tensor-core
+// path of the MISO conv stack (model.py:401-482: 3x3 convs, stride (1,1)/(1,2), and their
+// transposed forms).
 //
-// Formulation.  One sample's input is viewed as a zero-padded raster of width
-// W = Fin + 2*pad_f with one zero row above and below; the output uses the same raster
-// (columns >= Fout = W-2 are discarded).  For tap (kt,kf) the input needed by output raster
-// position R is raster position R + kt*W + kf: the im2col matrix of a tap is the SAME staged
-// tile shifted by a constant number of rows.  A CTA stages a halo tile
-// [H = 128*G + 2W + 2 raster pixels] x [16 channels] once per channel chunk into shared
-// memory in the canonical no-swizzle K-major UMMA layout (pixel p, 8-channel group j at
-// byte p*16 + j*H*16), and the nine taps are nine shared-memory descriptors whose start
-// addresses differ by (kt*W + kf)*16 bytes.  Global traffic is ~(1 + (2W+2)/(128 G)) x the
-// input instead of 9x.
+// Formulation.  A CTA owns a [TT frames x TF bins] tile of one sample's output.  Per 16-channel
+// chunk it TMA-loads the halo tile [(TT+2) x Wr pixels x 8 channels] of two channel planes
+// straight into the canonical no-swizzle K-major UMMA layout (pixel p of plane j at byte
+// j*PL + p*16).  With the tile flattened as a raster of width Wr, the im2col matrix of tap
+// (kt,kf) is the SAME staged tile shifted by a constant number of rows, so the nine taps are
+// nine shared-memory descriptors that differ only in their start address: global traffic is
+// (1 + halo) x the input instead of 9x.  Stride-2 convs load the even and odd bins as two tiles
+// (TMA element stride 2); stride-2 transposed convs are two output phases over one tile.
 //
-// Pipeline (one CTA = G consecutive 128-row M tiles of one sample, accumulators in TMEM):
-//   warps 0..7  producers: LDG fp32 -> producer's InstanceNorm as an affine -> bf16 (or a
-//               bf16 hi/lo split) -> st.shared, plus the pre-packed weight image of the chunk;
-//               then the epilogue: tcgen05.ld -> bias -> ELU -> store at a channel offset ->
-//               (sum, sumsq) statistics for the consumers.
-//   warp  8     one elected lane issues tcgen05.mma (M=128, N=cout_pad, K=16) per tap / M tile
-//               and commits to the "buffer free" mbarriers.
-// SPLIT = 1: bf16 operands (throughput mode, ~1e-2 relative error).
-// SPLIT = 3: bf16x3 (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 accumulate): parity-grade.
+// InstanceNorm of the producer (an affine per (sample, channel), applied by the consumer with
+// zero padding AFTER it, model.py:411-414) is folded into the operands: a tiny prep kernel
+// scales the weights per sample (W * rstd) and tabulates the border-dependent bias
+// sum_taps-in-bounds W * (-mean * rstd) for the 64 (frame-mask, bin-mask) classes, so raw
+// activations go from HBM to the tensor core untouched and TMA zero fill IS the padding.
+//
+// Pipeline: warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane, M = 128,
+// N = cout tile, K = 16, accumulators in TMEM), warps 2..9 = epilogue (tcgen05.ld -> border bias
+// -> ELU -> (sum, sumsq) statistics for the consumers -> bf16 hi/lo split -> 16-byte plane stores).
+// SPLIT = 1: bf16 operands (throughput mode).  SPLIT = 3: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with
+// fp32 accumulation (parity-grade).
+#include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <algorithm>
 
 #include "conv.cuh"
 
 namespace miso {
 namespace {
 
-constexpr int kProducerWarps = 8;
-constexpr int kThreads = (kProducerWarps + 1) * 32;
-constexpr int CK = 16;  // channels per chunk = one UMMA K step
-constexpr int kMaxItems = 10;
+constexpr int kThreads = 320;       // 10 warps: TMA, MMA, 8 epilogue
+constexpr int kEpiThreads = 256;
+constexpr int kMaxTaps = 9;
+constexpr int kMaxStages = 4;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kFixedSmem = 1024;    // barriers, tmem slot
 
+struct TcGeom {
+    // tap table
+    int ntap;
+    int shift[kMaxTaps];   // row shift of the A descriptor, in pixels
+    int aset[kMaxTaps];    // which input tile (0 = even / only, 1 = odd bins)
+    int acc[kMaxTaps];     // accumulator set (output phase)
+    int tapk[kMaxTaps];    // kt * KF + kf of the weight slot
+    int first_mask;        // bit i set: tap i is the first contribution to its accumulator set
+    int nset, nacc, nsp;
+    // tiling
+    int Wr, TT, TF, rows, G, N, nNt, ncols;
+    int t_tiles, f_tiles;
+    int t_org, f_org, f_mul;   // input tile origin: t0 + t_org ; f = j0 * f_mul + f_org (+1 for the odd set)
+    int ostride;               // fo = j * ostride + acc
+    int nchunk, nplanes;
+    // shared memory
+    int PL, a_stage, w_stage, stage, nstage, box_bytes;
+    int off_btab, off_red, off_stage, smem_total;
+    int tmem_cols;
+    int strided;               // 5-D bf16 tensor map with element stride 2 along bins
+};
+
+struct TcArgs {
+    TcGeom g;
+    const __nv_bfloat16 *wimg;  // [B][nNt][nchunk][ntap][2][nsp*N][8]
+    const float *btab;          // [B][nNt][64][N]
+    void *out;
+    double *out_sums;
+    int B, T, Fin, Fout;
+    int in_coff;                // channel offset of the input view (multiple of 8)
+    int out_ctot, out_coff, cout;
+    int out_layout;
+    size_t out_lo_off;
+    int use_lo;
+    int KT, KF, stride_f, pad_t, pad_f, transposed, elu;
+};
+
+struct PrepArgs {
+    const float *w;        // packed fp32 [ntaps][cin][cout_pad]
+    const float *bias;     // [cout_pad] or null
+    const double *in_sums;
+    int in_ctot, in_coff, cin, cout, cout_pad;
+    int norm_mode;
+    float norm_eps;
+    double norm_inv_n;
+    __nv_bfloat16 *wimg;
+    float *btab;
+    int B, N, nNt, nchunk, nsp, ntap, KT, KF;
+    int tapk[kMaxTaps];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -55,10 +113,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
-// shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor):
-// start address [0,14) >>4, leading byte offset [16,30) >>4 (between the two 8-element K groups),
-// stride byte offset [32,46) >>4 (between 8-row groups), version [46,48) = 1, layout type [61,64) = 0.
+// one lane of a converged warp; the compiler then keeps UTMALDG / UTCHMMA on the uniform datapath
+// (a plain `lane == 0` branch makes it wrap every such instruction in a serialising loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// shared-memory matrix descriptor, SWIZZLE_NONE, K-major: start address [0,14) >>4, leading byte
+// offset [16,30) >>4 (between the two 8-element K groups), stride byte offset [32,46) >>4 (between
+// 8-row groups), version [46,48) = 1 (sm_100), layout type [61,64) = 0.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -67,12 +150,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;
     return d;
 }
-
-// instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D fp32, A/B bf16, K-major both
+// instruction descriptor, kind::f16: D fp32 (bit 4), A/B bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
 __device__ __forceinline__ uint32_t make_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
-
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -87,358 +168,647 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t *>(&v);
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
 }
 
-struct TcGeom {
-    int W, Fout, G, N, H, Hp, nchunk;
-    size_t off_aff, off_a, a_buf_bytes, off_b, b_buf_bytes, total;
-};
-
-__host__ __device__ inline TcGeom tc_geom(const ConvArgs &a, int split) {
-    TcGeom g;
-    g.W = a.Fin + 2 * a.pad_f;
-    g.Fout = g.W - 2;
-    g.G = a.tc_G;
-    g.N = a.cout_pad16;
-    g.H = 128 * g.G + 2 * g.W + 2;
-    g.Hp = (g.H + 15) & ~15;
-    g.nchunk = (a.cin + CK - 1) / CK;
-    const int nsp = split == 3 ? 2 : 1;
-    g.off_aff = 64;
-    g.off_a = (g.off_aff + (size_t)((a.cin + 3) & ~3) * 8 + 127) & ~(size_t)127;
-    g.a_buf_bytes = (size_t)nsp * 2 * g.Hp * 16;
-    g.off_b = g.off_a + 2 * g.a_buf_bytes;
-    g.b_buf_bytes = (size_t)nsp * 9 * 2 * g.N * 16;
-    g.total = g.off_b + 2 * g.b_buf_bytes;
-    return g;
+// 16 per-lane values -> lanes 2k and 2k+1 hold the warp total of value k (16 shuffles)
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int off = 16 >> s, half = 8 >> s;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// ------------------------------------------------------------------------------------------------
 template <int SPLIT>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvArgs a) {
-    constexpr int NSP = SPLIT == 3 ? 2 : 1;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const TcGeom g = tc_geom(a, SPLIT);
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const TcGeom &g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y;
-    const int R0 = blockIdx.x * 128 * g.G;
-    const int W = g.W, N = g.N, Hp = g.Hp;
+    const int b = blockIdx.z, nt = blockIdx.y;
+    const int ft = blockIdx.x % g.f_tiles, ttile = blockIdx.x / g.f_tiles;
+    const int t0 = ttile * g.TT, j0 = ft * g.TF;
+    const int N = g.N;
 
-    // barriers: full[2] (producers -> MMA), empty[2] (MMA commit -> producers), done
-    const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 16), bar_done = smem_u32(smem + 32);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 40);
-    float2 *aff = reinterpret_cast<float2 *>(smem + g.off_aff);
-    const uint32_t sA = smem_u32(smem + g.off_a), sB = smem_u32(smem + g.off_b);
+    const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 64), bar_done = smem_u32(smem + 128);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 136);
+    float *btab_s = reinterpret_cast<float *>(smem + g.off_btab);
+    float *red = reinterpret_cast<float *>(smem + g.off_red);
+    const uint32_t s_stage = smem_u32(smem + g.off_stage);
 
     if (tid == 0) {
-        mbar_init(bar_full, kProducerWarps * 32);
-        mbar_init(bar_full + 8, kProducerWarps * 32);
-        mbar_init(bar_empty, 1);
-        mbar_init(bar_empty + 8, 1);
+        for (int s = 0; s < g.nstage; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kProducerWarps) {
-        // TMEM: G accumulators of N fp32 columns (power of two >= 32)
-        uint32_t cols = 32;
-        while (cols < (uint32_t)(g.G * N)) cols <<= 1;
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols)
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int c = tid; c < a.cin; c += kThreads) {
-        float2 v = make_float2(1.f, 0.f);
-        if (a.norm_mode == NORM_IN) {
-            const double *s = a.in_sums + ((size_t)b * a.in_ctot + a.in_coff + c) * 2;
-            v = affine_from_sums(s[0], s[1], a.norm_inv_n, (double)a.norm_eps);
+    {
+        // border-bias table of this (sample, N tile); statistics scratch; and zero the operand stages so
+        // that a half-filled last chunk (cin % 16 == 8) never multiplies uninitialised shared memory
+        const float *src = a.btab + ((size_t)b * g.nNt + nt) * 64 * N;
+        for (int i = tid; i < 64 * N; i += kThreads) btab_s[i] = src[i];
+        for (int i = tid; i < 2 * N; i += kThreads) red[i] = 0.f;
+        if (g.nplanes & 1) {
+            uint4 *z = reinterpret_cast<uint4 *>(smem + g.off_stage);
+            const int n16 = g.nstage * g.stage / 16;
+            for (int i = tid; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-        aff[c] = v;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < kProducerWarps) {
-        // ------------------------------------------------------------------ producers
-        // item i of this thread: halo pixel h = (warp + 8*i)*16 + (lane & 15), channel half kc = lane >> 4
-        const int kc = lane >> 4;
-        int poff[kMaxItems];
-        const int ngroups = Hp >> 4;
-#pragma unroll
-        for (int i = 0; i < kMaxItems; ++i) {
-            const int grp = warp + kProducerWarps * i;
-            const int h = grp * 16 + (lane & 15);
-            int off = -1;
-            if (grp < ngroups && h < g.H) {
-                const int Q = R0 + h;
-                const int row = Q / W;
-                const int ti = row - 1;
-                const int fi = Q - row * W - a.pad_f;
-                if (ti >= 0 && ti < a.T && fi >= 0 && fi < a.Fin) off = ti * a.Fin + fi;
-            }
-            poff[i] = off;
-        }
-        const float *in_b = a.in + (size_t)b * a.T * a.Fin * a.in_ctot + a.in_coff;
-        const uint4 *wimg = reinterpret_cast<const uint4 *>(a.w_tc);
-        const int b_vec = (int)(g.b_buf_bytes >> 4);
-
-        for (int c = 0; c < g.nchunk; ++c) {
-            const int buf = c & 1;
-            if (c >= 2) mbar_wait(bar_empty + 8 * buf, ((c >> 1) + 1) & 1);
-            const int ch = c * CK + kc * 8;
-            const bool ok0 = ch < a.cin, ok1 = ch + 4 < a.cin;
-            float2 f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = (ch + j < a.cin) ? aff[ch + j] : make_float2(0.f, 0.f);
-            uint8_t *abuf = smem + g.off_a + (size_t)buf * g.a_buf_bytes;
-#pragma unroll
-            for (int i = 0; i < kMaxItems; ++i) {
-                const int grp = warp + kProducerWarps * i;
-                if (grp < ngroups) {
-                    const int h = grp * 16 + (lane & 15);
-                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (poff[i] >= 0) {
-                        const float *p = in_b + (size_t)poff[i] * a.in_ctot + ch;
-                        if (ok0) v0 = __ldg(reinterpret_cast<const float4 *>(p));
-                        if (ok1) v1 = __ldg(reinterpret_cast<const float4 *>(p + 4));
-                        x[0] = fmaf(v0.x, f[0].x, f[0].y);
-                        x[1] = fmaf(v0.y, f[1].x, f[1].y);
-                        x[2] = fmaf(v0.z, f[2].x, f[2].y);
-                        x[3] = fmaf(v0.w, f[3].x, f[3].y);
-                        x[4] = fmaf(v1.x, f[4].x, f[4].y);
-                        x[5] = fmaf(v1.y, f[5].x, f[5].y);
-                        x[6] = fmaf(v1.z, f[6].x, f[6].y);
-                        x[7] = fmaf(v1.w, f[7].x, f[7].y);
-                        if (!ok0) x[0] = x[1] = x[2] = x[3] = 0.f;
-                        if (!ok1) x[4] = x[5] = x[6] = x[7] = 0.f;
-                    }
-                    uint4 hi;
-                    hi.x = pack_bf16(x[0], x[1]);
-                    hi.y = pack_bf16(x[2], x[3]);
-                    hi.z = pack_bf16(x[4], x[5]);
-                    hi.w = pack_bf16(x[6], x[7]);
-                    *reinterpret_cast<uint4 *>(abuf + ((size_t)kc * Hp + h) * 16) = hi;
-                    if constexpr (NSP == 2) {
-                        float r[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) r[j] = x[j] - __bfloat162float(__float2bfloat16_rn(x[j]));
-                        uint4 lo;
-                        lo.x = pack_bf16(r[0], r[1]);
-                        lo.y = pack_bf16(r[2], r[3]);
-                        lo.z = pack_bf16(r[4], r[5]);
-                        lo.w = pack_bf16(r[6], r[7]);
-                        *reinterpret_cast<uint4 *>(abuf + ((size_t)(2 + kc) * Hp + h) * 16) = lo;
-                    }
-                }
-            }
-            // weight image of this chunk: [NSP][9 taps][2 k-groups][N][8] bf16, already in smem order
-            uint4 *bbuf = reinterpret_cast<uint4 *>(smem + g.off_b + (size_t)buf * g.b_buf_bytes);
-            const uint4 *wsrc = wimg + (size_t)c * b_vec;
-            for (int i = tid; i < b_vec; i += kProducerWarps * 32) bbuf[i] = __ldg(wsrc + i);
-            // generic-proxy writes -> visible to the tensor core (async proxy), then signal "full"
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(bar_full + 8 * buf);
-        }
-
-        // ------------------------------------------------------------------ epilogue
-        mbar_wait(bar_done, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quad = warp & 3;
-        const int npix = a.T * W;
-        float *red = reinterpret_cast<float *>(smem + g.off_a);  // [N][2], A buffers are free now
-        if (a.out_sums) {
-            for (int i = tid; i < 2 * N; i += kProducerWarps * 32) red[i] = 0.f;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32));
-        float *out_b = a.out + (size_t)b * a.T * g.Fout * a.out_ctot + a.out_coff;
-        for (int gt = warp >> 2; gt < g.G; gt += 2) {
-            const int R = R0 + gt * 128 + quad * 32 + lane;
-            const int t = R / W;
-            const int wo = R - t * W;
-            const bool valid = R < npix && wo < g.Fout;
-            float *o = out_b + ((size_t)t * g.Fout + wo) * a.out_ctot;
-            for (int j = 0; j < N; j += 16) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(gt * N + j);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float y[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    float x = __uint_as_float(v[q]) + (a.bias ? a.bias[j + q] : 0.f);
-                    if (a.elu) x = elu1(x);
-                    y[q] = valid ? x : 0.f;
-                }
-                if (valid) {
-                    if (((a.out_ctot | a.out_coff) & 3) == 0 && j + 16 <= a.cout) {
-#pragma unroll
-                        for (int q = 0; q < 16; q += 4)
-                            *reinterpret_cast<float4 *>(o + j + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                            if (j + q < a.cout) o[j + q] = y[q];
-                    }
-                }
-                if (a.out_sums) {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        float s = warp_sum(y[q]);
-                        float sq = warp_sum(y[q] * y[q]);
-                        if (lane == 0) {
-                            atomicAdd(&red[(j + q) * 2], s);
-                            atomicAdd(&red[(j + q) * 2 + 1], sq);
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (elect_one()) {
+            const int tin = t0 + g.t_org;
+            const int fin = j0 * g.f_mul + g.f_org;
+            const int plane0 = a.in_coff >> 3;
+            const __nv_bfloat16 *wsrc = a.wimg + ((size_t)b * g.nNt + nt) * g.nchunk * (size_t)(g.w_stage / 2);
+            for (int c = 0; c < g.nchunk; ++c) {
+                const int s = c % g.nstage;
+                if (c >= g.nstage) mbar_wait(bar_empty + 8 * s, ((c / g.nstage) + 1) & 1);
+                const int np = min(2, g.nplanes - 2 * c);
+                const uint32_t full = bar_full + 8 * s;
+                mbar_expect_tx(full, (uint32_t)(g.nset * g.nsp * np * g.box_bytes + g.w_stage));
+                const uint32_t sa = s_stage + (uint32_t)(s * g.stage);
+                for (int set = 0; set < g.nset; ++set)
+                    for (int sp = 0; sp < g.nsp; ++sp)
+                        for (int p = 0; p < np; ++p) {
+                            const uint32_t dst = sa + (uint32_t)(((set * g.nsp + sp) * 2 + p) * g.PL);
+                            const CUtensorMap *tm = sp == 0 ? &tm_hi : &tm_lo;
+                            if (g.strided)
+                                tma_load_5d(dst, tm, full, 0, fin + set, tin, plane0 + 2 * c + p, b);
+                            else
+                                tma_load_4d(dst, tm, full, 2 * fin, tin, plane0 + 2 * c + p, b);
                         }
-                    }
-                }
+                bulk_load(sa + (uint32_t)g.a_stage, wsrc + (size_t)c * (g.w_stage / 2), (uint32_t)g.w_stage, full);
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32));
-        if (a.out_sums && tid < N && tid < a.cout) {
-            double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + tid) * 2;
-            atomicAdd(dst, (double)red[tid * 2]);
-            atomicAdd(dst + 1, (double)red[tid * 2 + 1]);
-        }
-    } else {
-        // ------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = make_idesc(N);
-        const uint32_t a_lbo = (uint32_t)Hp * 16, b_lbo = (uint32_t)N * 16;
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        // SPLIT == 3: the weight image of a tap is [kg][2N rows: w_hi then w_lo][8], so
+        //   D[:, 0:N] , D[:, N:2N] += A_hi * [W_hi | W_lo]   (one MMA of width 2N)
+        //   D[:, 0:N]              += A_lo * W_hi             (one MMA of width N)
+        // and the epilogue adds the two column halves: 2 MMAs instead of 3, A_hi read once.
+        constexpr int WB = SPLIT == 3 ? 2 : 1;              // weight rows per output channel
+        const uint32_t idesc_wide = make_idesc(WB * N), idesc_n = make_idesc(N);
+        const uint32_t a_lbo = (uint32_t)g.PL, b_lbo = (uint32_t)(WB * N) * 16;
+        const uint32_t cw = (uint32_t)(WB * N);              // accumulator columns per (M tile, phase)
+        const uint32_t gstep = cw * (uint32_t)g.nacc;
         for (int c = 0; c < g.nchunk; ++c) {
-            const int buf = c & 1;
-            mbar_wait(bar_full + 8 * buf, (c >> 1) & 1);
+            const int s = c % g.nstage;
+            mbar_wait(bar_full + 8 * s, (c / g.nstage) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t abase = sA + (uint32_t)(buf * g.a_buf_bytes);
-                const uint32_t bbase = sB + (uint32_t)(buf * g.b_buf_bytes);
+            if (elect_one()) {
+                const uint32_t abase = s_stage + (uint32_t)(s * g.stage);
+                const uint32_t bbase = abase + (uint32_t)g.a_stage;
 #pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int kt = tap / 3, kf = tap - kt * 3;
-#pragma unroll 1
-                    for (int sp = 0; sp < SPLIT; ++sp) {
-                        const int asel = sp == 1 ? 1 : 0, bsel = sp == 2 ? 1 : 0;
-                        const uint64_t bdesc = make_desc(bbase + (uint32_t)((bsel * 9 + tap) * 2 * N * 16), b_lbo, 128);
-                        for (int gt = 0; gt < g.G; ++gt) {
-                            const uint32_t aaddr = abase + (uint32_t)(asel * 2 * Hp * 16) + (uint32_t)((gt * 128 + kt * W + kf) * 16);
-                            umma_bf16(tmem_base + (uint32_t)(gt * N), make_desc(aaddr, a_lbo, 128), bdesc, idesc,
-                                      (c | tap | sp) != 0 ? 1u : 0u);
-                        }
+                for (int i = 0; i < g.ntap; ++i) {
+                    const uint32_t a_hi = abase + (uint32_t)(g.aset[i] * g.nsp * 2 * g.PL) + (uint32_t)(g.shift[i] * 16);
+                    const uint64_t bdesc = make_desc(bbase + (uint32_t)(i * 2 * WB * N * 16), b_lbo, 128);
+                    const uint32_t acc_flag = (c == 0 && ((g.first_mask >> i) & 1)) ? 0u : 1u;
+                    const uint32_t d0 = tmem_base + (uint32_t)g.acc[i] * cw;
+                    uint64_t ad = make_desc(a_hi, a_lbo, 128);
+#pragma unroll 4
+                    for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_wide, acc_flag);
+                    if constexpr (SPLIT == 3) {
+                        ad = make_desc(a_hi + (uint32_t)(2 * g.PL), a_lbo, 128);
+#pragma unroll 4
+                        for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_n, 1u);
                     }
                 }
-                umma_commit(bar_empty + 8 * buf);
+                umma_commit(bar_empty + 8 * s);
                 if (c == g.nchunk - 1) umma_commit(bar_done);
             }
             __syncwarp();
         }
+    } else {
+        // ---------------------------------------------------------------- epilogue
+        mbar_wait(bar_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int npix = a.T * a.Fout;
+        const bool planes = a.out_layout == LAYOUT_PLANES;
+        __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
+        float *out_cl = reinterpret_cast<float *>(a.out) + (size_t)b * npix * a.out_ctot + a.out_coff;
+        const int co_base = nt * N;
+        for (int cb = 0; cb < N; cb += 16) {
+            float ssum[16], ssq[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
+            for (int gt = half; gt < g.G; gt += 2) {
+                const int R = gt * 128 + quad * 32 + lane;
+                const int tt = R / g.Wr;
+                const int jl = R - tt * g.Wr;
+                const int t = t0 + tt, j = j0 + jl;
+                const bool rowok = tt < g.TT && t < a.T && jl < g.TF;
+                int tmask = 0;
+#pragma unroll
+                for (int kt = 0; kt < 3; ++kt) {
+                    const int ti = a.transposed ? t + a.pad_t - kt : t + kt - a.pad_t;
+                    if (kt < a.KT && ti >= 0 && ti < a.T) tmask |= 1 << kt;
+                }
+                for (int ph = 0; ph < g.nacc; ++ph) {
+                    const int fo = j * g.ostride + ph;
+                    const bool valid = rowok && fo < a.Fout;
+                    int fmask = 0;
+#pragma unroll
+                    for (int kf = 0; kf < 3; ++kf) {
+                        bool ok;
+                        if (a.transposed) {
+                            const int num = fo + a.pad_f - kf;
+                            const int fi = num / a.stride_f;
+                            ok = num >= 0 && fi * a.stride_f == num && fi < a.Fin;
+                        } else {
+                            const int fi = fo * a.stride_f + kf - a.pad_f;
+                            ok = fi >= 0 && fi < a.Fin;
+                        }
+                        if (kf < a.KF && ok) fmask |= 1 << kf;
+                    }
+                    const float *bt = btab_s + (tmask * 8 + fmask) * N + cb;
+                    constexpr int WB = SPLIT == 3 ? 2 : 1;
+                    uint32_t v[16], v2[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((gt * g.nacc + ph) * WB * N + cb);
+                    tmem_ld16(taddr, v);
+                    if constexpr (SPLIT == 3) tmem_ld16(taddr + (uint32_t)N, v2);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float y[16];
+#pragma unroll
+                    for (int q = 0; q < 16; q += 4) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(bt + q);
+                        y[q] = __uint_as_float(v[q]) + bb.x;
+                        y[q + 1] = __uint_as_float(v[q + 1]) + bb.y;
+                        y[q + 2] = __uint_as_float(v[q + 2]) + bb.z;
+                        y[q + 3] = __uint_as_float(v[q + 3]) + bb.w;
+                    }
+                    if constexpr (SPLIT == 3) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) y[q] += __uint_as_float(v2[q]);
+                    }
+                    if (a.elu) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) y[q] = elu1(y[q]);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            ssum[q] += y[q];
+                            ssq[q] = fmaf(y[q], y[q], ssq[q]);
+                        }
+                        const int pix = t * a.Fout + fo;
+                        if (planes) {
+#pragma unroll
+                            for (int g8 = 0; g8 < 16; g8 += 8) {
+                                const int co = co_base + cb + g8;
+                                if (co < a.cout) {
+                                    const int ca = a.out_coff + co;
+                                    __nv_bfloat16 *p = out_pl + ((size_t)(ca >> 3) * npix + pix) * 8;
+                                    float h[8];
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) h[q] = bf16_round(y[g8 + q]);
+                                    *reinterpret_cast<uint4 *>(p) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
+                                                                               pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+                                    if (a.use_lo) {
+                                        *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(p) + a.out_lo_off) = make_uint4(
+                                            pack_bf16x2(y[g8] - h[0], y[g8 + 1] - h[1]), pack_bf16x2(y[g8 + 2] - h[2], y[g8 + 3] - h[3]),
+                                            pack_bf16x2(y[g8 + 4] - h[4], y[g8 + 5] - h[5]), pack_bf16x2(y[g8 + 6] - h[6], y[g8 + 7] - h[7]));
+                                    }
+                                }
+                            }
+                        } else {
+                            float *o = out_cl + (size_t)pix * a.out_ctot + co_base + cb;
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                if (co_base + cb + q < a.cout) o[q] = y[q];
+                        }
+                    }
+                }
+            }
+            if (a.out_sums) {
+                const float s = warp_reduce16(ssum, lane);
+                const float q2 = warp_reduce16(ssq, lane);
+                if ((lane & 1) == 0) {
+                    atomicAdd(&red[(cb + (lane >> 1)) * 2], s);
+                    atomicAdd(&red[(cb + (lane >> 1)) * 2 + 1], q2);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
+        const int et = tid - 64;
+        if (a.out_sums && et < N && co_base + et < a.cout) {
+            double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + co_base + et) * 2;
+            atomicAdd(dst, (double)red[et * 2]);
+            atomicAdd(dst + 1, (double)red[et * 2 + 1]);
+        }
     }
     __syncthreads();
-    if (warp == kProducerWarps) {
+    if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t cols = 32;
-        while (cols < (uint32_t)(g.G * N)) cols <<= 1;
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
     }
 }
 
-// weight image for the tcgen05 path: [nchunk][NSP (hi, lo)][9 taps][2 k-groups][N][8] bf16.
-// Deconvolutions (stride 1) are convolutions with the kernel flipped in both directions.
-__global__ void pack_tc_w_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ img, int cout, int cin, int N,
-                                 int nchunk, int nsp, int transposed) {
-    const int64_t total = (int64_t)nchunk * nsp * 9 * 2 * N * 8;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int e = (int)(i & 7);
-        int64_t r = i >> 3;
-        int n = (int)(r % N);
-        r /= N;
-        int kg = (int)(r & 1);
-        r >>= 1;
-        int tap = (int)(r % 9);
-        r /= 9;
-        int sp = (int)(r % nsp);
-        int c = (int)(r / nsp);
-        int ci = c * CK + kg * 8 + e;
-        float v = 0.f;
-        if (n < cout && ci < cin) {
-            if (transposed)
-                v = w[((int64_t)ci * cout + n) * 9 + (8 - tap)];
-            else
-                v = w[((int64_t)n * cin + ci) * 9 + tap];
+// ------------------------------------------------------------------------------------------------
+// Per-sample operand preparation: blocks [0, B*nchunk) write the weight images of one (sample, chunk)
+//   wimg[b][nt][chunk][tap][kg][w_hi rows | w_lo rows][8] = bf16 split of W[tap][ci][co] * rstd[b][ci]
+// and blocks [B*nchunk, B*nchunk + B*nNt) write the border-bias tables of one (sample, N tile)
+//   btab[b][nt][tmask*8+fmask][n] = bias[co] + sum_{kt in tmask, kf in fmask} sum_ci W[kt,kf][ci][co] * shift[b][ci]
+// where x_norm = x * rstd + shift is the consumer-side InstanceNorm affine (model.py:413,430,445).
+__global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
+    extern __shared__ float sh[];
+    const int nimg = p.B * p.nchunk;
+    if ((int)blockIdx.x < nimg) {
+        const int b = blockIdx.x / p.nchunk, chunk = blockIdx.x - b * p.nchunk;
+        float *scale = sh;  // [16]
+        if (threadIdx.x < 16) {
+            const int ci = chunk * 16 + threadIdx.x;
+            float sc = 0.f;
+            if (ci < p.cin) {
+                sc = 1.f;
+                if (p.norm_mode == NORM_IN) {
+                    const double *s = p.in_sums + ((size_t)b * p.in_ctot + p.in_coff + ci) * 2;
+                    sc = affine_from_sums(s[0], s[1], p.norm_inv_n, (double)p.norm_eps).x;
+                }
+            }
+            scale[threadIdx.x] = sc;
         }
-        __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        img[i] = sp == 0 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+        __syncthreads();
+        const int per_nt = p.ntap * 2 * p.N;  // (tap, kg, n) triples per N tile
+        const size_t w_stage = (size_t)p.nsp * p.ntap * 2 * p.N * 8;
+        for (int i = threadIdx.x; i < p.nNt * per_nt; i += blockDim.x) {
+            const int nt = i / per_nt;
+            int r = i - nt * per_nt;
+            const int n = r % p.N;
+            r /= p.N;
+            const int kg = r & 1, tap = r >> 1;
+            const int co = nt * p.N + n;
+            float h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ci = chunk * 16 + kg * 8 + e;
+                float v = 0.f;
+                if (ci < p.cin && co < p.cout) v = p.w[((size_t)p.tapk[tap] * p.cin + ci) * p.cout_pad + co] * scale[kg * 8 + e];
+                h[e] = bf16_round(v);
+                l[e] = v - h[e];
+            }
+            // image of one (sample, N tile, chunk): [tap][kg][nsp * N rows: w_hi rows then w_lo rows][8]
+            __nv_bfloat16 *dst = p.wimg + (((size_t)b * p.nNt + nt) * p.nchunk + chunk) * w_stage +
+                                 ((size_t)(tap * 2 + kg) * p.nsp * p.N + n) * 8;
+            *reinterpret_cast<uint4 *>(dst) =
+                make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+            if (p.nsp == 2)
+                *reinterpret_cast<uint4 *>(dst + (size_t)p.N * 8) =
+                    make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+        }
+    } else {
+        const int idx = blockIdx.x - nimg;
+        const int b = idx / p.nNt, nt = idx - b * p.nNt;
+        float *shift = sh;              // [cin]
+        float *wb = sh + p.cin;         // [9][N]
+        for (int ci = threadIdx.x; ci < p.cin; ci += blockDim.x) {
+            float v = 0.f;
+            if (p.norm_mode == NORM_IN) {
+                const double *s = p.in_sums + ((size_t)b * p.in_ctot + p.in_coff + ci) * 2;
+                v = affine_from_sums(s[0], s[1], p.norm_inv_n, (double)p.norm_eps).y;
+            }
+            shift[ci] = v;
+        }
+        __syncthreads();
+        const int ntaps = p.KT * p.KF;
+        for (int i = threadIdx.x; i < ntaps * p.N; i += blockDim.x) {
+            const int k = i / p.N, n = i - k * p.N;
+            const int co = nt * p.N + n;
+            float acc = 0.f;
+            if (co < p.cout) {
+                const float *w = p.w + (size_t)k * p.cin * p.cout_pad + co;
+                for (int ci = 0; ci < p.cin; ++ci) acc = fmaf(w[(size_t)ci * p.cout_pad], shift[ci], acc);
+            }
+            wb[i] = acc;
+        }
+        __syncthreads();
+        float *dst = p.btab + ((size_t)b * p.nNt + nt) * 64 * p.N;
+        for (int i = threadIdx.x; i < 64 * p.N; i += blockDim.x) {
+            const int m = i / p.N, n = i - m * p.N;
+            const int tm = m >> 3, fm = m & 7;
+            const int co = nt * p.N + n;
+            float v = (p.bias && co < p.cout) ? p.bias[co] : 0.f;
+            for (int kt = 0; kt < p.KT; ++kt)
+                for (int kf = 0; kf < p.KF; ++kf)
+                    if (((tm >> kt) & 1) && ((fm >> kf) & 1)) v += wb[(kt * p.KF + kf) * p.N + n];
+            dst[i] = v;
+        }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Tiling and shared-memory plan of one launch.  Returns false when the layer does not fit.
+bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
+    g = TcGeom{};
+    const bool s2 = a.stride_f == 2;
+    g.nsp = split == 3 ? 2 : 1;
+    g.nset = (!a.transposed && s2) ? 2 : 1;
+    g.nacc = (a.transposed && s2) ? 2 : 1;
+    g.ostride = g.nacc;
+    g.strided = g.nset == 2;
+    const int cout16 = round_up(a.cout, 16);
+    g.N = std::min(cout16, 64);
+    if (cout16 % g.N) {  // keep every N tile the same width
+        g.N = 48;
+        if (cout16 % 48) g.N = 32;
+        if (cout16 % g.N) g.N = 16;
+    }
+    g.nNt = cout16 / g.N;
+    g.ncols = (a.transposed && s2) ? a.Fin + 1 : a.Fout;
+    g.nplanes = (a.cin + 7) / 8;
+    g.nchunk = (g.nplanes + 1) / 2;
+    // tap table
+    const int halo_t = a.KT == 3 ? 1 : 0;
+    const int extra_w = a.KF == 1 ? 0 : (s2 ? 1 : 2);
+    g.ntap = 0;
+    g.first_mask = 0;
+    int seen_acc = 0;
+    auto add = [&](int dt, int df, int set, int acc, int kt, int kf, int Wr) {
+        const int i = g.ntap++;
+        g.shift[i] = dt * Wr + df;
+        g.aset[i] = set;
+        g.acc[i] = acc;
+        g.tapk[i] = kt * a.KF + kf;
+        if (!((seen_acc >> acc) & 1)) {
+            seen_acc |= 1 << acc;
+            g.first_mask |= 1 << i;
+        }
+    };
+    // columns per tile
+    int TF = std::min(g.ncols, 64);
+    g.f_tiles = (g.ncols + TF - 1) / TF;
+    TF = (g.ncols + g.f_tiles - 1) / g.f_tiles;
+    g.TF = TF;
+    g.Wr = TF + extra_w;
+    const int Wr = g.Wr;
+    if (a.KT == 1 && a.KF == 1) {
+        add(0, 0, 0, 0, 0, 0, Wr);
+        g.t_org = 0;
+        g.f_org = 0;
+        g.f_mul = 1;
+    } else if (!a.transposed && !s2) {  // conv, stride 1: fi = fo + kf - pad_f, ti = t + kt - 1
+        for (int kt = 0; kt < 3; ++kt)
+            for (int kf = 0; kf < 3; ++kf) add(kt, kf, 0, 0, kt, kf, Wr);
+        g.t_org = -1;
+        g.f_org = -a.pad_f;
+        g.f_mul = 1;
+    } else if (!a.transposed && s2) {  // conv, stride 2, pad_f 0: fi = 2 fo + kf
+        for (int kt = 0; kt < 3; ++kt) {
+            add(kt, 0, 0, 0, kt, 0, Wr);
+            add(kt, 0, 1, 0, kt, 1, Wr);
+            add(kt, 1, 0, 0, kt, 2, Wr);
+        }
+        g.t_org = -1;
+        g.f_org = 0;
+        g.f_mul = 2;
+    } else if (a.transposed && !s2) {  // transposed, stride 1: fi = fo + pad_f - kf, ti = t + 1 - kt
+        for (int kt = 0; kt < 3; ++kt)
+            for (int kf = 0; kf < 3; ++kf) add(2 - kt, 2 - kf, 0, 0, kt, kf, Wr);
+        g.t_org = -1;
+        g.f_org = a.pad_f - 2;
+        g.f_mul = 1;
+    } else {  // transposed, stride 2, pad_f 0: fo = 2 j + ph; even: kf 0 -> fi = j, kf 2 -> fi = j - 1; odd: kf 1 -> fi = j
+        for (int kt = 0; kt < 3; ++kt) {
+            add(2 - kt, 1, 0, 0, kt, 0, Wr);
+            add(2 - kt, 0, 0, 0, kt, 2, Wr);
+            add(2 - kt, 1, 0, 1, kt, 1, Wr);
+        }
+        g.t_org = -1;
+        g.f_org = -1;
+        g.f_mul = 1;
+    }
+    int maxshift = 0;
+    for (int i = 0; i < g.ntap; ++i) maxshift = std::max(maxshift, g.shift[i]);
+    const int cw = g.N * g.nsp;  // accumulator columns per (M tile, phase): bf16x3 keeps the w_hi / w_lo halves apart
+    const int Gmax = std::min(8, 512 / (cw * g.nacc));
+    if (Gmax < 1) return false;
+    g.off_btab = kFixedSmem;
+    g.off_red = g.off_btab + 64 * g.N * 4;
+    g.off_stage = round_up(g.off_red + 2 * g.N * 4, 1024);
+    g.w_stage = g.nsp * g.ntap * 2 * g.N * 16;
+    for (int G = Gmax; G >= 1; --G) {
+        int TT = std::min({a.T, 128 * G / Wr, 254 - 2 * halo_t});
+        if (TT < 1) continue;
+        int t_tiles = (a.T + TT - 1) / TT;
+        // small layers: prefer at least ~2 CTAs per SM over the largest tile
+        while (TT > 4 && (int64_t)t_tiles * g.f_tiles * g.nNt * a.B < 2 * 148) {
+            TT = (TT + 1) / 2;
+            t_tiles = (a.T + TT - 1) / TT;
+        }
+        TT = (a.T + t_tiles - 1) / t_tiles;
+        g.TT = TT;
+        g.t_tiles = t_tiles;
+        g.rows = TT + 2 * halo_t;
+        g.G = (TT * Wr + 127) / 128;
+        g.box_bytes = g.rows * Wr * 16;
+        g.PL = round_up(std::max(g.rows * Wr, 128 * g.G + maxshift) * 16, 128);
+        g.a_stage = g.nset * g.nsp * 2 * g.PL;
+        g.stage = g.a_stage + round_up(g.w_stage, 128);
+        g.nstage = std::min({kMaxStages, (kSmemLimit - g.off_stage) / g.stage, std::max(g.nchunk, 2)});
+        if (g.nstage >= 2) {
+            g.smem_total = g.off_stage + g.nstage * g.stage;
+            int cols = 32;
+            while (cols < g.G * g.nacc * cw) cols <<= 1;
+            g.tmem_cols = cols;
+            return cols <= 512 && g.rows <= 256 && 2 * Wr <= 256;
+        }
+    }
+    return false;
+}
+
+int encode_maps(const ConvArgs &a, const TcGeom &g, CUtensorMap *hi, CUtensorMap *lo) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+        return MISO_E_CUDA;
+    }
+    const uint64_t CG = (uint64_t)a.in_ctot / 8, T = (uint64_t)a.T, F = (uint64_t)a.Fin;
+    char *base = const_cast<char *>(reinterpret_cast<const char *>(a.in));
+    for (int sp = 0; sp < 2; ++sp) {
+        CUtensorMap *tm = sp == 0 ? hi : lo;
+        void *addr = base + (sp ? a.in_lo_off : 0);
+        CUresult r;
+        if (!g.strided) {
+            // [2F (8-byte units)][T][CG][B]: a tile row is one contiguous run of Wr * 16 bytes
+            cuuint64_t dims[4] = {2 * F, T, CG, (cuuint64_t)a.B};
+            cuuint64_t strides[3] = {F * 16, T * F * 16, 2 * CG * T * F * 16};
+            cuuint32_t box[4] = {(cuuint32_t)(2 * g.Wr), (cuuint32_t)g.rows, 1, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, addr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            // [8 ch][F][T][CG][B] with element stride 2 along F: the even / odd bins of a tile
+            cuuint64_t dims[5] = {8, F, T, CG, (cuuint64_t)a.B};
+            cuuint64_t strides[4] = {16, F * 16, T * F * 16, 2 * CG * T * F * 16};
+            cuuint32_t box[5] = {8, (cuuint32_t)(2 * g.Wr), (cuuint32_t)g.rows, 1, 1};
+            cuuint32_t es[5] = {1, 2, 1, 1, 1};
+            r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, addr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (r != CUDA_SUCCESS) {
+            set_error("conv_tc: cuTensorMapEncodeTiled failed (%d) for Fin=%d T=%d ctot=%d Wr=%d rows=%d", (int)r, a.Fin, a.T, a.in_ctot,
+                      g.Wr, g.rows);
+            return MISO_E_CUDA;
+        }
+    }
+    return MISO_OK;
 }
 
 }  // namespace
 
-size_t conv_tc_weight_elems(int cin, int cout_pad16, int nsp) {
-    return (size_t)((cin + CK - 1) / CK) * nsp * 9 * 2 * cout_pad16 * 8;
-}
-
-int pack_conv_tc_weights(const float *d_w, void *d_img, int cout, int cin, int cout_pad16, int nsp, int transposed,
-                         cudaStream_t stream) {
-    const int nchunk = (cin + CK - 1) / CK;
-    const size_t total = conv_tc_weight_elems(cin, cout_pad16, nsp);
-    const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-    pack_tc_w_kernel<<<blocks, 256, 0, stream>>>(d_w, reinterpret_cast<__nv_bfloat16 *>(d_img), cout, cin, cout_pad16, nchunk,
-                                                  nsp, transposed);
-    MISO_LAUNCHED("pack_tc_w_kernel");
-    return MISO_OK;
-}
-
 bool conv_tc_eligible(const ConvArgs &a) {
-    return a.KT == 3 && a.KF == 3 && a.stride_f == 1 && a.pad_t == 1 && a.cout_pad16 <= 64 && a.cin % 4 == 0 &&
-           a.resid == nullptr && a.norm_mode != NORM_GLN && a.w_tc != nullptr;
+    if (!((a.KT == 3 && a.KF == 3) || (a.KT == 1 && a.KF == 1))) return false;
+    if (a.KT == 3 && a.pad_t != 1) return false;
+    if (a.stride_f != 1 && a.stride_f != 2) return false;
+    if (a.stride_f == 2 && a.pad_f != 0) return false;
+    if (a.in_layout != LAYOUT_PLANES || a.in_ctot % 8 || a.in_coff % 8) return false;
+    if (a.out_layout == LAYOUT_PLANES && (a.out_ctot % 8 || a.out_coff % 8 || a.cout % 8)) return false;
+    if (a.resid != nullptr || a.norm_mode == NORM_GLN) return false;
+    TcGeom g;
+    return make_geom(a, 3, g);
 }
 
-int conv_tc_pick_G(const ConvArgs &a) {
-    // enough CTAs to fill the machine twice, otherwise the largest G the TMEM/halo budget allows
-    const int W = a.Fin + 2 * a.pad_f;
-    const int tiles = ceil_div(a.T * W, 128);
-    int G = 4;
-    while (G > 1 && (int64_t)ceil_div(tiles, G) * a.B < 2 * 148) G >>= 1;
-    while (G > 1 && G * a.cout_pad16 > 256) G >>= 1;
-    return G;
+void conv_tc_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size_t *btab_bytes) {
+    TcGeom g;
+    *wimg_bytes = *btab_bytes = 0;
+    if (!make_geom(a, split, g)) return;
+    *wimg_bytes = (size_t)a.B * g.nNt * g.nchunk * g.w_stage;
+    *btab_bytes = (size_t)a.B * g.nNt * 64 * g.N * sizeof(float);
 }
 
-int launch_conv_tc(const ConvArgs &a_in, int split, cudaStream_t stream) {
-    ConvArgs a = a_in;
-    MISO_REQUIRE(conv_tc_eligible(a), "conv_tc: layer not eligible for the tcgen05 path");
+int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream) {
     MISO_REQUIRE(split == 1 || split == 3, "conv_tc: bad split");
-    if (a.transposed) {  // stride-1 ConvTranspose2d == conv with flipped kernel and pad_f -> 2 - pad_f
-        a.pad_f = 2 - a.pad_f;
-        a.transposed = 0;
+    TcGeom g;
+    MISO_REQUIRE(make_geom(a, split, g), "conv_tc: layer does not fit the tcgen05 path (cin=%d cout=%d Fin=%d)", a.cin, a.cout, a.Fin);
+    const size_t need_w = (size_t)a.B * g.nNt * g.nchunk * g.w_stage, need_b = (size_t)a.B * g.nNt * 64 * g.N * sizeof(float);
+    if (need_w > scratch.wimg_bytes || need_b > scratch.btab_bytes) {
+        set_error("conv_tc: scratch too small (%zu/%zu weight bytes, %zu/%zu bias bytes)", scratch.wimg_bytes, need_w,
+                  scratch.btab_bytes, need_b);
+        return MISO_E_WORKSPACE;
     }
-    a.tc_G = conv_tc_pick_G(a);
-    const TcGeom g = tc_geom(a, split);
-    MISO_REQUIRE(g.Fout == a.Fout, "conv_tc: Fout %d inconsistent with Fin %d pad %d", a.Fout, a.Fin, a.pad_f);
-    MISO_REQUIRE(ceil_div(g.Hp >> 4, kProducerWarps) <= kMaxItems, "conv_tc: halo %d too large", g.H);
-    MISO_REQUIRE(g.total <= 227 * 1024, "conv_tc: shared memory %zu exceeds 227 KB", g.total);
+    CUtensorMap tm_hi, tm_lo;
+    int rc = encode_maps(a, g, &tm_hi, &tm_lo);
+    if (rc) return rc;
+
+    PrepArgs p{};
+    p.w = a.w;
+    p.bias = a.bias;
+    p.in_sums = a.in_sums;
+    p.in_ctot = a.in_ctot;
+    p.in_coff = a.in_coff;
+    p.cin = a.cin;
+    p.cout = a.cout;
+    p.cout_pad = a.cout_pad;
+    p.norm_mode = a.norm_mode;
+    p.norm_eps = a.norm_eps;
+    p.norm_inv_n = a.norm_inv_n;
+    p.wimg = reinterpret_cast<__nv_bfloat16 *>(scratch.wimg);
+    p.btab = scratch.btab;
+    p.B = a.B;
+    p.N = g.N;
+    p.nNt = g.nNt;
+    p.nchunk = g.nchunk;
+    p.nsp = g.nsp;
+    p.ntap = g.ntap;
+    p.KT = a.KT;
+    p.KF = a.KF;
+    for (int i = 0; i < g.ntap; ++i) p.tapk[i] = g.tapk[i];
+    const size_t prep_smem = std::max<size_t>(64, (size_t)(a.cin + 9 * g.N) * sizeof(float));
+    prof_begin(stream);
+    conv_tc_prep_kernel<<<a.B * g.nchunk + a.B * g.nNt, 256, prep_smem, stream>>>(p);
+    MISO_LAUNCHED("conv_tc_prep_kernel");
+
+    TcArgs k{};
+    k.g = g;
+    k.wimg = p.wimg;
+    k.btab = p.btab;
+    k.out = a.out;
+    k.out_sums = a.out_sums;
+    k.B = a.B;
+    k.T = a.T;
+    k.Fin = a.Fin;
+    k.Fout = a.Fout;
+    k.in_coff = a.in_coff;
+    k.out_ctot = a.out_ctot;
+    k.out_coff = a.out_coff;
+    k.cout = a.cout;
+    k.out_layout = a.out_layout;
+    k.out_lo_off = a.out_lo_off;
+    k.use_lo = a.use_lo;
+    k.KT = a.KT;
+    k.KF = a.KF;
+    k.stride_f = a.stride_f;
+    k.pad_t = a.pad_t;
+    k.pad_f = a.pad_f;
+    k.transposed = a.transposed;
+    k.elu = a.elu;
+
     static bool attr_set[2] = {false, false};
     const int ai = split == 3 ? 1 : 0;
     if (!attr_set[ai]) {
-        cudaError_t e = split == 3 ? cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                                   : cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = split == 3 ? cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)
+                                   : cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
         attr_set[ai] = true;
     }
-    dim3 grid(ceil_div(a.T * g.W, 128 * g.G), a.B);
-    prof_begin(stream);
+    dim3 grid(g.t_tiles * g.f_tiles, g.nNt, a.B);
     if (split == 3)
-        conv_tc_kernel<3><<<grid, kThreads, g.total, stream>>>(a);
+        conv_tc_kernel<3><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
     else
-        conv_tc_kernel<1><<<grid, kThreads, g.total, stream>>>(a);
+        conv_tc_kernel<1><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
     {
-        const double flops = 2.0 * a.B * a.T * a.Fout * a.cin * a.cout * 9.0;
-        const double bytes = 4.0 * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
+        const double pix = (double)a.B * a.T * (a.transposed ? a.Fin : a.Fout);
+        const double flops = 2.0 * pix * a.cin * a.cout * a.KT * a.KF;
+        const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
         prof_end(stream, flops, bytes, MISO_PROF_CONV_TC);
     }
     MISO_LAUNCHED("conv_tc_kernel");

@@ -1,13 +1,14 @@
 // MISO_1 / MISO_3 network body: packed-weight handle, workspace plan and the forward
 // launch sequence (reference model.py:8-111, 282-395; layers model.py:401-632).
 //
-// Data layout in HBM: every activation is fp32 channels-last [B, T, F, Ctot].  A
-// DenseBlock owns ONE buffer [x | y0 | y1 | y2 | y3] and conv k reads the channel
-// prefix it needs (model.py:470-479 concatenates instead); an encoder's final output is
-// written straight into the skip half of the decoder buffer that will consume it
-// (model.py:99 concatenates instead), and the next encoder reads it from there.
-// Tensors are stored as raw ELU outputs plus fp64 (sum, sumsq) per (sample, channel);
-// InstanceNorm is applied by whoever loads them.
+// Data layout in HBM: every conv-stack activation is a set of bf16 planes
+// [B][hi|lo][Ctot/8][T][F][8] (conv.cuh, LAYOUT_PLANES).  A DenseBlock owns ONE buffer
+// [x | y0 | y1 | y2 | y3] and conv k reads the channel prefix it needs (model.py:470-479
+// concatenates instead); an encoder's final output is written straight into the skip half
+// of the decoder buffer that will consume it (model.py:99 concatenates instead), and the
+// next encoder reads it from there.  Tensors are stored as raw ELU outputs plus fp64
+// (sum, sumsq) per (sample, channel); InstanceNorm is applied by whoever consumes them.
+// The TCN state stays fp32 channels-last [B, T, C].
 #include <algorithm>
 #include <cstdlib>
 #include <map>
@@ -56,8 +57,8 @@ __global__ void sentinel_kernel(double *sums, int B, int ctot, int coff, int n) 
 // x0 = InstanceNorm(raw bottleneck output) materialised as the TCN state [B,T,C], plus the
 // per-(b,c) statistics its first TemporalBlock needs (model.py:530).
 constexpr int kTcnTile = 32;
-__global__ void __launch_bounds__(128) tcn_prep_kernel(const float *__restrict__ raw, int raw_ctot, int raw_coff,
-                                                       const double *__restrict__ raw_sums, double inv_n, float eps,
+__global__ void __launch_bounds__(128) tcn_prep_kernel(const __nv_bfloat16 *__restrict__ raw, int raw_ctot, int raw_coff,
+                                                       int use_lo, const double *__restrict__ raw_sums, double inv_n, float eps,
                                                        float *__restrict__ S, double *__restrict__ s_sums, int T, int C) {
     const int c = blockIdx.y * 128 + threadIdx.x;
     const int b = blockIdx.z;
@@ -68,7 +69,12 @@ __global__ void __launch_bounds__(128) tcn_prep_kernel(const float *__restrict__
     const int t1 = min(T, t0 + kTcnTile);
     float s = 0.f, q = 0.f;
     for (int t = t0; t < t1; ++t) {
-        float x = fmaf(raw[((size_t)b * T + t) * raw_ctot + raw_coff + c], af.x, af.y);
+        // planes [b][hi|lo][raw_ctot/8][T][F=1][8]
+        const int ca = raw_coff + c;
+        const size_t e = (size_t)b * 2 * raw_ctot * T + ((size_t)(ca >> 3) * T + t) * 8 + (ca & 7);
+        float r = __bfloat162float(raw[e]);
+        if (use_lo) r += __bfloat162float(raw[e + (size_t)raw_ctot * T]);
+        float x = fmaf(r, af.x, af.y);
         S[((size_t)b * T + t) * C + c] = x;
         s += x;
         q += x * x;
@@ -128,19 +134,38 @@ struct ShiftList {
     int s[16];
 };
 
-__global__ void pack_miso1_kernel(const float2 *__restrict__ mix, float *__restrict__ x, int B, int M, int TF,
+// Writes one pixel's channel vector (<= 16 channels) into the plane layout [hi|lo][cpad/8][TF][8].
+__device__ __forceinline__ void store_pixel_planes(__nv_bfloat16 *base, int cpad, int TF, int p, const float *v) {
+    for (int g8 = 0; g8 < cpad; g8 += 8) {
+        float h[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h[q] = bf16_round(v[g8 + q]);
+        __nv_bfloat16 *dst = base + ((size_t)(g8 >> 3) * TF + p) * 8;
+        *reinterpret_cast<uint4 *>(dst) =
+            make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+        *reinterpret_cast<uint4 *>(dst + (size_t)cpad * TF) =
+            make_uint4(pack_bf16x2(v[g8] - h[0], v[g8 + 1] - h[1]), pack_bf16x2(v[g8 + 2] - h[2], v[g8 + 3] - h[3]),
+                       pack_bf16x2(v[g8 + 4] - h[4], v[g8 + 5] - h[5]), pack_bf16x2(v[g8 + 6] - h[6], v[g8 + 7] - h[7]));
+    }
+}
+
+__global__ void pack_miso1_kernel(const float2 *__restrict__ mix, __nv_bfloat16 *__restrict__ x, int B, int M, int TF,
                                   ShiftList sh) {
-    // one thread per (b, pixel): reads M complex values (coalesced along f), writes 2M floats per shift
+    // one thread per (b, pixel): reads M complex values (coalesced along f), writes the 2M (padded to a
+    // multiple of 8) channels re(m0..), im(m0..) of every shifted copy as 16-byte plane pixels
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * TF) return;
     int b = (int)(i / TF);
     int p = (int)(i - (int64_t)b * TF);
+    const int cpad = (2 * M + 7) & ~7;
     float2 v[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m)
         if (m < M) v[m] = mix[((size_t)b * M + m) * TF + p];
     for (int k = 0; k < sh.n; ++k) {
-        float *o = x + (((size_t)k * B + b) * TF + p) * (2 * M);
+        float c[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) c[j] = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (j < M) {
@@ -150,32 +175,46 @@ __global__ void pack_miso1_kernel(const float2 *__restrict__ mix, float *__restr
 #pragma unroll
                 for (int mm = 1; mm < 8; ++mm)
                     if (mm == m) z = v[mm];
-                o[j] = z.x;
-                o[M + j] = z.y;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    if (q == j) c[q] = z.x;
+                    if (q == M + j) c[q] = z.y;
+                }
             }
         }
+        store_pixel_planes(x + ((size_t)k * B + b) * 2 * cpad * TF, cpad, TF, p, c);
     }
 }
 
 __global__ void pack_miso3_kernel(const float2 *__restrict__ mix, const float2 *__restrict__ second,
-                                  const float2 *__restrict__ third, float *__restrict__ x, int B, int M, int TF) {
+                                  const float2 *__restrict__ third, __nv_bfloat16 *__restrict__ x, int B, int M, int TF) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * TF) return;
     int b = (int)(i / TF);
     int p = (int)(i - (int64_t)b * TF);
     const int C = M + 2;
-    float *o = x + (size_t)i * (2 * C);
-    for (int m = 0; m < M; ++m) {
-        float2 z = mix[((size_t)b * M + m) * TF + p];
-        o[m] = z.x;
-        o[C + m] = z.y;
+    const int cpad = (2 * C + 7) & ~7;
+    float c[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c[j] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        if (m < C) {
+            float2 z;
+            if (m < M)
+                z = mix[((size_t)b * M + m) * TF + p];
+            else if (m == M)
+                z = second[(size_t)b * TF + p];
+            else
+                z = third[(size_t)b * TF + p];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (q == m) c[q] = z.x;
+                if (q == C + m) c[q] = z.y;
+            }
+        }
     }
-    float2 z2 = second[(size_t)b * TF + p];
-    float2 z3 = third[(size_t)b * TF + p];
-    o[M] = z2.x;
-    o[C + M] = z2.y;
-    o[M + 1] = z3.x;
-    o[C + M + 1] = z3.y;
+    store_pixel_planes(x + (size_t)b * 2 * cpad * TF, cpad, TF, p, c);
 }
 
 __global__ void unpack_complex_kernel(const float *__restrict__ y, float2 *__restrict__ out, int B, int S, int TF) {
@@ -187,8 +226,8 @@ __global__ void unpack_complex_kernel(const float *__restrict__ y, float2 *__res
     for (int s = 0; s < S; ++s) out[((size_t)b * S + s) * TF + p] = make_float2(src[s], src[S + s]);
 }
 
-__global__ void tap_kernel(const float *__restrict__ buf, int ctot, int coff, int C, const double *__restrict__ sums,
-                           double inv_n, float eps, float *__restrict__ out, int B, int TF) {
+__global__ void tap_kernel(const __nv_bfloat16 *__restrict__ buf, int ctot, int coff, int C, int use_lo,
+                           const double *__restrict__ sums, double inv_n, float eps, float *__restrict__ out, int B, int TF) {
     int64_t total = (int64_t)B * C * TF;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int p = (int)(i % TF);
@@ -200,7 +239,11 @@ __global__ void tap_kernel(const float *__restrict__ buf, int ctot, int coff, in
             const double *s = sums + ((size_t)b * ctot + coff + c) * 2;
             af = affine_from_sums(s[0], s[1], inv_n, (double)eps);
         }
-        out[i] = fmaf(buf[((size_t)b * TF + p) * ctot + coff + c], af.x, af.y);
+        const int ca = coff + c;
+        const size_t e = (size_t)b * 2 * ctot * TF + ((size_t)(ca >> 3) * TF + p) * 8 + (ca & 7);
+        float raw = __bfloat162float(buf[e]);
+        if (use_lo) raw += __bfloat162float(buf[e + (size_t)ctot * TF]);
+        out[i] = fmaf(raw, af.x, af.y);
     }
 }
 
@@ -215,16 +258,12 @@ struct Param {
     float *d;                       // packed device storage (owned by the arena)
     size_t packed_elems;
     bool loaded;
-    void *tc1 = nullptr, *tc3 = nullptr;  // bf16 / bf16 hi+lo weight images for the tcgen05 path
-    int cout_pad16 = 0;
 };
 
 struct ConvDesc {
     int w = -1, b = -1;  // param indices
     int cin = 0, cout = 0, cout_pad = 0;
 };
-
-constexpr int kTcMaxN = 64;
 
 struct TcnHalf {
     int dw, alpha, gamma, beta, pw;
@@ -322,9 +361,10 @@ bool encoder_sizes(const miso_net *n, int F, std::vector<int> &Fx) {
 }
 
 struct BufDesc {
-    float *p = nullptr;
+    char *p = nullptr;  // bf16 planes [B][hi|lo][ctot/8][T][F][8]
     double *sums = nullptr;
     int ctot = 0, F = 0;
+    size_t lo_off = 0;  // bytes from a sample's hi plane set to its lo plane set
 };
 
 struct Plan {
@@ -334,8 +374,11 @@ struct Plan {
     std::vector<double *> sS, sU, g1, g2;
     double *stats_base = nullptr;
     size_t stats_bytes = 0;
+    TcScratch scratch{};
     size_t total = 0;
 };
+
+size_t plane_bytes(int B, int ctot, int T, int F) { return (size_t)B * ctot * T * F * 4; }  // hi + lo bf16
 
 bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
     if (!encoder_sizes(n, F, pl.Fx)) return false;
@@ -388,14 +431,17 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
     for (int i = 0; i < nb; ++i)
         if (dense_enc(i)) {
             pl.E[i].sums = sp(oE[i]);
-            pl.E[i].p = reinterpret_cast<float *>(take((size_t)B * T * pl.E[i].F * pl.E[i].ctot * sizeof(float)));
+            pl.E[i].p = take(plane_bytes(B, pl.E[i].ctot, T, pl.E[i].F));
+            pl.E[i].lo_off = (size_t)pl.E[i].ctot * T * pl.E[i].F * 2;
         }
     for (int j = 0; j < nb; ++j) {
         pl.D[j].sums = sp(oD[j]);
-        pl.D[j].p = reinterpret_cast<float *>(take((size_t)B * T * pl.D[j].F * pl.D[j].ctot * sizeof(float)));
+        pl.D[j].p = take(plane_bytes(B, pl.D[j].ctot, T, pl.D[j].F));
+        pl.D[j].lo_off = (size_t)pl.D[j].ctot * T * pl.D[j].F * 2;
         if (dense_dec(j)) {
             pl.Y[j].sums = sp(oY[j]);
-            pl.Y[j].p = reinterpret_cast<float *>(take((size_t)B * T * pl.Y[j].F * pl.Y[j].ctot * sizeof(float)));
+            pl.Y[j].p = take(plane_bytes(B, pl.Y[j].ctot, T, pl.Y[j].F));
+            pl.Y[j].lo_off = (size_t)pl.Y[j].ctot * T * pl.Y[j].F * 2;
         }
     }
     size_t tcn_bytes = (size_t)B * T * n->C * sizeof(float);
@@ -416,6 +462,18 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
     return true;
 }
 
+// tensor-core scratch (per-sample weight images, border-bias tables) goes after the activations
+void plan_scratch(Plan &pl, char *base, size_t need_w, size_t need_b) {
+    size_t off = pl.total;
+    pl.scratch.wimg = base ? base + off : nullptr;
+    pl.scratch.wimg_bytes = need_w;
+    off += align_up(need_w, 256);
+    pl.scratch.btab = base ? reinterpret_cast<float *>(base + off) : nullptr;
+    pl.scratch.btab_bytes = need_b;
+    off += align_up(need_b, 256);
+    pl.total = off;
+}
+
 // where encoder i's block output xs[i] lives: the skip half of decoder (nb-1-i)'s buffer
 struct ViewRef {
     const BufDesc *buf;
@@ -426,42 +484,235 @@ ViewRef xs_view(const miso_net *n, const Plan &pl, int i) {
     return ViewRef{&pl.D[j], n->de[j], n->en[i + 1]};
 }
 
-int run_conv(const miso_net *n, const ConvDesc &cd, bool transposed, const float *in, int in_ctot, int in_coff, int Fin,
-             const double *in_sums, float *out, int out_ctot, int out_coff, int Fout, double *out_sums, int B, int T,
-             int stride_f, int pad_f, bool elu, cudaStream_t st) {
-    ConvArgs a{};
-    a.in = in;
-    a.w = n->params[cd.w].d;
-    a.bias = n->params[cd.b].d;
-    a.out = out;
-    a.resid = nullptr;
-    a.in_sums = in_sums;
-    a.out_sums = out_sums;
-    a.B = B;
-    a.T = T;
-    a.Fin = Fin;
-    a.Fout = Fout;
-    a.in_ctot = in_ctot;
-    a.in_coff = in_coff;
-    a.cin = cd.cin;
-    a.out_ctot = out_ctot;
-    a.out_coff = out_coff;
-    a.cout = cd.cout;
-    a.cout_pad = cd.cout_pad;
-    a.KT = 3;
-    a.KF = 3;
-    a.stride_f = stride_f;
-    a.pad_t = 1;
-    a.pad_f = pad_f;
-    a.transposed = transposed ? 1 : 0;
-    a.norm_mode = in_sums ? NORM_IN : NORM_NONE;
-    a.norm_eps = kInEps;
-    a.norm_inv_n = 1.0 / ((double)T * Fin);
-    a.elu = elu ? 1 : 0;
-    a.cout_pad16 = n->params[cd.w].cout_pad16;
-    a.w_tc = n->mode == 1 ? n->params[cd.w].tc3 : (n->mode == 2 ? n->params[cd.w].tc1 : nullptr);
-    if (n->mode != 0 && conv_tc_eligible(a)) return launch_conv_tc(a, n->mode == 1 ? 3 : 1, st);
-    return launch_conv_fp32(a, st);
+// One pass over the layer list.  dry = true only sizes the tensor-core scratch (no launches).
+struct Walker {
+    const miso_net *n;
+    const Plan &pl;
+    int B, T, F;
+    cudaStream_t st;
+    bool dry;
+    size_t need_w = 0, need_b = 0;
+
+    int conv(const ConvDesc &cd, bool transposed, const BufDesc *inb, const void *in_raw, int in_ctot, int in_coff, int Fin,
+             const double *in_sums, const BufDesc *outb, float *out_raw, int out_ctot, int out_coff, int Fout, double *out_sums,
+             int stride_f, int pad_f, bool elu) {
+        ConvArgs a{};
+        a.in = inb ? inb->p : in_raw;
+        a.in_layout = LAYOUT_PLANES;
+        a.in_lo_off = (size_t)in_ctot * T * Fin * 2;
+        a.w = n->params[cd.w].d;
+        a.bias = n->params[cd.b].d;
+        a.out = outb ? (void *)outb->p : (void *)out_raw;
+        a.out_layout = outb ? LAYOUT_PLANES : LAYOUT_CL_F32;
+        a.out_lo_off = (size_t)out_ctot * T * Fout * 2;
+        a.use_lo = n->mode == 2 ? 0 : 1;
+        a.resid = nullptr;
+        a.in_sums = in_sums;
+        a.out_sums = out_sums;
+        a.B = B;
+        a.T = T;
+        a.Fin = Fin;
+        a.Fout = Fout;
+        a.in_ctot = in_ctot;
+        a.in_coff = in_coff;
+        a.cin = cd.cin;
+        a.out_ctot = out_ctot;
+        a.out_coff = out_coff;
+        a.cout = cd.cout;
+        a.cout_pad = cd.cout_pad;
+        a.KT = 3;
+        a.KF = 3;
+        a.stride_f = stride_f;
+        a.pad_t = 1;
+        a.pad_f = pad_f;
+        a.transposed = transposed ? 1 : 0;
+        a.norm_mode = in_sums ? NORM_IN : NORM_NONE;
+        a.norm_eps = kInEps;
+        a.norm_inv_n = 1.0 / ((double)T * Fin);
+        a.elu = elu ? 1 : 0;
+        const bool tc = conv_tc_eligible(a);
+        if (dry) {
+            if (tc) {
+                size_t w, bt;
+                conv_tc_scratch_need(a, 3, &w, &bt);
+                need_w = std::max(need_w, w);
+                need_b = std::max(need_b, bt);
+            }
+            return MISO_OK;
+        }
+        if (n->mode != 0 && tc) return launch_conv_tc(a, n->mode == 1 ? 3 : 1, pl.scratch, st);
+        return launch_conv_fp32(a, st);
+    }
+
+    int run(const void *d_x, float *d_y);
+};
+
+int Walker::run(const void *d_x, float *d_y) {
+    const int nb = n->nb, C = n->C;
+    int rc;
+    const int in_pad = (n->in_ch + 7) & ~7;
+    // ---------------- encoders (model.py:40-53, 83-86) ----------------
+    for (int i = 0; i < nb; ++i) {
+        const BufDesc *inb = nullptr;
+        const double *in_sums;
+        int in_ctot, in_coff, Fin;
+        if (i == 0) {
+            in_sums = nullptr;
+            in_ctot = in_pad;
+            in_coff = 0;
+            Fin = F;
+        } else {
+            ViewRef v = xs_view(n, pl, i - 1);
+            inb = v.buf;
+            in_sums = v.buf->sums;
+            in_ctot = v.buf->ctot;
+            in_coff = v.coff;
+            Fin = v.buf->F;
+        }
+        const int stride = (i == 0 || i == nb - 1) ? 1 : 2;
+        ViewRef xo = xs_view(n, pl, i);
+        if (dense_enc(i)) {
+            const BufDesc &e = pl.E[i];
+            rc = conv(n->enc_conv[i], false, inb, d_x, in_ctot, in_coff, Fin, in_sums, &e, nullptr, e.ctot, 0, e.F,
+                      i == 0 ? nullptr : e.sums, stride, 0, i != 0);
+            if (rc) return rc;
+            const int c = n->en[i + 1];
+            for (int k = 1; k <= 5; ++k) {
+                const ConvDesc &cd = n->enc_dense[i][k - 1];
+                if (k < 5)
+                    rc = conv(cd, false, &e, nullptr, e.ctot, 0, e.F, e.sums, &e, nullptr, e.ctot, c + (k - 1) * c, e.F, e.sums, 1, 1,
+                              true);
+                else
+                    rc = conv(cd, false, &e, nullptr, e.ctot, 0, e.F, e.sums, xo.buf, nullptr, xo.buf->ctot, xo.coff, e.F,
+                              xo.buf->sums, 1, 1, true);
+                if (rc) return rc;
+            }
+        } else {
+            rc = conv(n->enc_conv[i], false, inb, d_x, in_ctot, in_coff, Fin, in_sums, xo.buf, nullptr, xo.buf->ctot, xo.coff,
+                      xo.buf->F, xo.buf->sums, stride, 0, true);
+            if (rc) return rc;
+        }
+    }
+
+    // ---------------- TCN (model.py:486-567) ----------------
+    if (!dry) {
+        const BufDesc &d0 = pl.D[0];
+        const double inv_T = 1.0 / (double)T;
+        const int use_lo = n->mode == 2 ? 0 : 1;
+        dim3 grid(ceil_div(T, kTcnTile), ceil_div(C, 128), B);
+        tcn_prep_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(d0.p), d0.ctot, C, use_lo, d0.sums, inv_T,
+                                              kInEps, pl.S, pl.sS[0], T, C);
+        MISO_LAUNCHED("tcn_prep_kernel");
+        const int nblk = n->R * n->X;
+        const int bn = conv_fp32_tile_n(C);
+        const int cpad = (C + bn - 1) / bn * bn;
+        for (int k = 0; k < nblk; ++k) {
+            const int dil = 1 << (k % n->X);
+            for (int half = 0; half < 2; ++half) {
+                const TcnHalf &h = n->tcn[k * 2 + half];
+                const float *u = half == 0 ? pl.S : pl.U;
+                const double *us = half == 0 ? pl.sS[k] : pl.sU[k];
+                double *gs = half == 0 ? pl.g1[k] : pl.g2[k];
+                tcn_dw_kernel<<<grid, 128, 0, st>>>(u, us, inv_T, kInEps, n->params[h.dw].d, n->params[h.alpha].d, pl.P, gs, T, C,
+                                                    dil);
+                MISO_LAUNCHED("tcn_dw_kernel");
+                ConvArgs a{};
+                a.in = pl.P;
+                a.in_layout = LAYOUT_CL_F32;
+                a.out_layout = LAYOUT_CL_F32;
+                a.use_lo = use_lo;
+                a.w = n->params[h.pw].d;
+                a.bias = nullptr;
+                a.in_sums = gs;
+                a.gamma = n->params[h.gamma].d;
+                a.beta = n->params[h.beta].d;
+                a.B = B;
+                a.T = T;
+                a.Fin = 1;
+                a.Fout = 1;
+                a.in_ctot = C;
+                a.in_coff = 0;
+                a.cin = C;
+                a.cout = C;
+                a.cout_pad = cpad;
+                a.KT = 1;
+                a.KF = 1;
+                a.stride_f = 1;
+                a.pad_t = 0;
+                a.pad_f = 0;
+                a.transposed = 0;
+                a.norm_mode = NORM_GLN;
+                a.norm_eps = kGlnEps;
+                a.norm_inv_n = 1.0 / ((double)C * T);
+                a.elu = 0;
+                if (half == 0) {
+                    a.out = pl.U;
+                    a.out_ctot = C;
+                    a.out_coff = 0;
+                    a.out_sums = pl.sU[k];
+                    a.resid = nullptr;
+                } else {
+                    a.resid = pl.S;
+                    a.resid_ctot = C;
+                    a.resid_coff = 0;
+                    if (k + 1 < nblk) {
+                        a.out = pl.S;  // in-place residual update: each element is read once by its own writer
+                        a.out_ctot = C;
+                        a.out_coff = 0;
+                        a.out_sums = pl.sS[k + 1];
+                    } else {
+                        a.out = d0.p;  // TCN output = first half of decoder 0's input, consumed raw
+                        a.out_layout = LAYOUT_PLANES;
+                        a.out_lo_off = d0.lo_off;
+                        a.out_ctot = d0.ctot;
+                        a.out_coff = 0;
+                        a.out_sums = nullptr;
+                    }
+                }
+                rc = launch_conv_fp32(a, st);
+                if (rc) return rc;
+            }
+        }
+    }
+
+    // ---------------- decoders (model.py:55-73, 97-100) ----------------
+    for (int j = 0; j < nb; ++j) {
+        const BufDesc &d = pl.D[j];
+        const int stride = (j == 0 || j == nb - 1) ? 1 : 2;
+        const bool last = j == nb - 1;
+        const BufDesc *outb = last ? nullptr : &pl.D[j + 1];
+        const int out_ctot = last ? n->out_ch : pl.D[j + 1].ctot;
+        const int Fout = last ? F : pl.D[j + 1].F;
+        double *out_sums = last ? nullptr : pl.D[j + 1].sums;
+        if (dense_dec(j)) {
+            const int c = 2 * n->de[j], g1 = n->de[j];
+            const BufDesc &y = pl.Y[j];
+            for (int k = 1; k <= 5; ++k) {
+                const ConvDesc &cd = n->dec_dense[j][k - 1];
+                if (k < 5)
+                    rc = conv(cd, false, &d, nullptr, d.ctot, 0, d.F, d.sums, &d, nullptr, d.ctot, c + (k - 1) * g1, d.F, d.sums, 1, 1,
+                              true);
+                else
+                    rc = conv(cd, false, &d, nullptr, d.ctot, 0, d.F, d.sums, &y, nullptr, y.ctot, 0, y.F, y.sums, 1, 1, true);
+                if (rc) return rc;
+            }
+            rc = conv(n->dec_deconv[j], true, &y, nullptr, y.ctot, 0, y.F, y.sums, outb, d_y, out_ctot, 0, Fout, out_sums, stride, 0,
+                      !last);
+        } else {
+            rc = conv(n->dec_deconv[j], true, &d, nullptr, d.ctot, 0, d.F, d.sums, outb, d_y, out_ctot, 0, Fout, out_sums, stride, 0,
+                      true);
+        }
+        if (rc) return rc;
+    }
+    return MISO_OK;
+}
+
+bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
+    if (!make_plan(n, B, T, F, base, pl)) return false;
+    Walker w{n, pl, B, T, F, nullptr, true};
+    w.run(nullptr, nullptr);
+    plan_scratch(pl, base, w.need_w, w.need_b);
+    return true;
 }
 
 }  // namespace
@@ -551,17 +802,6 @@ int miso_net_create(miso_net_t **out, int in_ch, int out_ch, int num_bottleneck,
     for (auto &p : n->params) {
         p.d = n->arena + off;
         off += align_up(p.packed_elems, 64);
-        if ((p.kind == P_CONV_W || p.kind == P_DECONV_W) && p.taps == 9) {
-            p.cout_pad16 = (p.cout + 15) / 16 * 16;
-            if (p.cout_pad16 <= kTcMaxN) {
-                cudaError_t e1 = cudaMalloc(&p.tc1, conv_tc_weight_elems(p.cin, p.cout_pad16, 1) * 2);
-                cudaError_t e3 = cudaMalloc(&p.tc3, conv_tc_weight_elems(p.cin, p.cout_pad16, 2) * 2);
-                if (e1 != cudaSuccess || e3 != cudaSuccess) {
-                    miso_net_destroy(n);
-                    return cuda_fail(e1 != cudaSuccess ? e1 : e3, "cudaMalloc(tcgen05 weight images)");
-                }
-            }
-        }
     }
     *out = n;
     return MISO_OK;
@@ -570,10 +810,6 @@ int miso_net_create(miso_net_t **out, int in_ch, int out_ch, int num_bottleneck,
 int miso_net_destroy(miso_net_t *net) {
     if (!net) return MISO_OK;
     if (net->arena) cudaFree(net->arena);
-    for (auto &p : net->params) {
-        if (p.tc1) cudaFree(p.tc1);
-        if (p.tc3) cudaFree(p.tc3);
-    }
     delete net;
     return MISO_OK;
 }
@@ -604,13 +840,6 @@ int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, in
             pack_conv_w_kernel<<<blocks, 256, 0, st>>>(d_data, p.d, p.cout, p.cin, p.taps, p.cout_pad,
                                                       p.kind == P_DECONV_W ? 1 : 0);
             MISO_LAUNCHED("pack_conv_w_kernel");
-            if (p.tc1) {
-                const int tr = p.kind == P_DECONV_W ? 1 : 0;
-                int rc = pack_conv_tc_weights(d_data, p.tc1, p.cout, p.cin, p.cout_pad16, 1, tr, st);
-                if (rc) return rc;
-                rc = pack_conv_tc_weights(d_data, p.tc3, p.cout, p.cin, p.cout_pad16, 2, tr, st);
-                if (rc) return rc;
-            }
             break;
         }
         case P_BIAS:
@@ -657,11 +886,16 @@ int miso_net_check_shape(const miso_net_t *net, int T, int F) {
 size_t miso_net_workspace_bytes(const miso_net_t *net, int B, int T, int F) {
     if (!net || B <= 0 || T <= 0) return 0;
     Plan pl;
-    if (!make_plan(net, B, T, F, nullptr, pl)) return 0;
+    if (!full_plan(net, B, T, F, nullptr, pl)) return 0;
     return pl.total;
 }
 
-int miso_net_forward(miso_net_t *net, const float *d_x, float *d_y, int B, int T, int F, void *d_ws, size_t ws_bytes,
+size_t miso_net_input_bytes(const miso_net_t *net, int B, int T, int F) {
+    if (!net || B <= 0 || T <= 0 || F <= 0) return 0;
+    return plane_bytes(B, (net->in_ch + 7) & ~7, T, F);
+}
+
+int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T, int F, void *d_ws, size_t ws_bytes,
                      void *stream) {
     MISO_REQUIRE(net && d_x && d_y && d_ws, "miso_net_forward: null argument");
     if (net->n_loaded != (int)net->params.size()) {
@@ -675,183 +909,35 @@ int miso_net_forward(miso_net_t *net, const float *d_x, float *d_y, int B, int T
     MISO_REQUIRE(B >= 1 && B <= 65535, "miso_net_forward: batch %d out of range", B);
     int rc = miso_net_check_shape(net, T, F);
     if (rc) return rc;
+    MISO_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "miso_net_forward: workspace must be 256-byte aligned");
+    MISO_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 127) == 0, "miso_net_forward: input planes must be 128-byte aligned");
     Plan pl;
-    make_plan(net, B, T, F, reinterpret_cast<char *>(d_ws), pl);
+    full_plan(net, B, T, F, reinterpret_cast<char *>(d_ws), pl);
     if (pl.total > ws_bytes) {
         set_error("miso_net_forward: workspace %zu < required %zu bytes", ws_bytes, pl.total);
         return MISO_E_WORKSPACE;
     }
-    MISO_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "miso_net_forward: workspace must be 256-byte aligned");
     cudaStream_t st = as_stream(stream);
-    const int nb = net->nb, C = net->C;
-    const miso_net *n = net;
+    const int C = net->C;
 
     MISO_CUDA(cudaMemsetAsync(pl.stats_base, 0, pl.stats_bytes, st));
     {
         // raw (never normalised) channels: enc0's first conv output (model.py:401-406) and the TCN output
         const BufDesc &e0 = pl.E[0];
-        sentinel_kernel<<<ceil_div(B * n->en[1], 128), 128, 0, st>>>(e0.sums, B, e0.ctot, 0, n->en[1]);
+        sentinel_kernel<<<ceil_div(B * net->en[1], 128), 128, 0, st>>>(e0.sums, B, e0.ctot, 0, net->en[1]);
         MISO_LAUNCHED("sentinel_kernel");
         sentinel_kernel<<<ceil_div(B * C, 128), 128, 0, st>>>(pl.D[0].sums, B, pl.D[0].ctot, 0, C);
         MISO_LAUNCHED("sentinel_kernel");
     }
-
-    // ---------------- encoders (model.py:40-53, 83-86) ----------------
-    for (int i = 0; i < nb; ++i) {
-        const float *in;
-        const double *in_sums;
-        int in_ctot, in_coff, Fin;
-        if (i == 0) {
-            in = d_x;
-            in_sums = nullptr;
-            in_ctot = n->in_ch;
-            in_coff = 0;
-            Fin = F;
-        } else {
-            ViewRef v = xs_view(n, pl, i - 1);
-            in = v.buf->p;
-            in_sums = v.buf->sums;
-            in_ctot = v.buf->ctot;
-            in_coff = v.coff;
-            Fin = v.buf->F;
-        }
-        const int stride = (i == 0 || i == nb - 1) ? 1 : 2;
-        ViewRef xo = xs_view(n, pl, i);
-        if (dense_enc(i)) {
-            const BufDesc &e = pl.E[i];
-            rc = run_conv(n, n->enc_conv[i], false, in, in_ctot, in_coff, Fin, in_sums, e.p, e.ctot, 0, e.F,
-                          i == 0 ? nullptr : e.sums, B, T, stride, 0, i != 0, st);
-            if (rc) return rc;
-            const int c = n->en[i + 1];
-            for (int k = 1; k <= 5; ++k) {
-                const ConvDesc &cd = n->enc_dense[i][k - 1];
-                if (k < 5)
-                    rc = run_conv(n, cd, false, e.p, e.ctot, 0, e.F, e.sums, e.p, e.ctot, c + (k - 1) * c, e.F, e.sums, B, T,
-                                  1, 1, true, st);
-                else
-                    rc = run_conv(n, cd, false, e.p, e.ctot, 0, e.F, e.sums, xo.buf->p, xo.buf->ctot, xo.coff, e.F,
-                                  xo.buf->sums, B, T, 1, 1, true, st);
-                if (rc) return rc;
-            }
-        } else {
-            rc = run_conv(n, n->enc_conv[i], false, in, in_ctot, in_coff, Fin, in_sums, xo.buf->p, xo.buf->ctot, xo.coff,
-                          xo.buf->F, xo.buf->sums, B, T, stride, 0, true, st);
-            if (rc) return rc;
-        }
-    }
-
-    // ---------------- TCN (model.py:486-567) ----------------
-    {
-        const BufDesc &d0 = pl.D[0];
-        const double inv_T = 1.0 / (double)T;
-        dim3 grid(ceil_div(T, kTcnTile), ceil_div(C, 128), B);
-        tcn_prep_kernel<<<grid, 128, 0, st>>>(d0.p, d0.ctot, C, d0.sums, inv_T, kInEps, pl.S, pl.sS[0], T, C);
-        MISO_LAUNCHED("tcn_prep_kernel");
-        const int nblk = n->R * n->X;
-        const int bn = conv_fp32_tile_n(C);
-        const int cpad = (C + bn - 1) / bn * bn;
-        for (int k = 0; k < nblk; ++k) {
-            const int dil = 1 << (k % n->X);
-            for (int half = 0; half < 2; ++half) {
-                const TcnHalf &h = n->tcn[k * 2 + half];
-                const float *u = half == 0 ? pl.S : pl.U;
-                const double *us = half == 0 ? pl.sS[k] : pl.sU[k];
-                double *gs = half == 0 ? pl.g1[k] : pl.g2[k];
-                tcn_dw_kernel<<<grid, 128, 0, st>>>(u, us, inv_T, kInEps, n->params[h.dw].d, n->params[h.alpha].d, pl.P, gs,
-                                                    T, C, dil);
-                MISO_LAUNCHED("tcn_dw_kernel");
-                ConvArgs a{};
-                a.in = pl.P;
-                a.w = n->params[h.pw].d;
-                a.bias = nullptr;
-                a.in_sums = gs;
-                a.gamma = n->params[h.gamma].d;
-                a.beta = n->params[h.beta].d;
-                a.B = B;
-                a.T = T;
-                a.Fin = 1;
-                a.Fout = 1;
-                a.in_ctot = C;
-                a.in_coff = 0;
-                a.cin = C;
-                a.cout = C;
-                a.cout_pad = cpad;
-                a.KT = 1;
-                a.KF = 1;
-                a.stride_f = 1;
-                a.pad_t = 0;
-                a.pad_f = 0;
-                a.transposed = 0;
-                a.norm_mode = NORM_GLN;
-                a.norm_eps = kGlnEps;
-                a.norm_inv_n = 1.0 / ((double)C * T);
-                a.elu = 0;
-                if (half == 0) {
-                    a.out = pl.U;
-                    a.out_ctot = C;
-                    a.out_coff = 0;
-                    a.out_sums = pl.sU[k];
-                    a.resid = nullptr;
-                } else {
-                    a.resid = pl.S;
-                    a.resid_ctot = C;
-                    a.resid_coff = 0;
-                    if (k + 1 < nblk) {
-                        a.out = pl.S;  // in-place residual update: each element is read once by its own writer
-                        a.out_ctot = C;
-                        a.out_coff = 0;
-                        a.out_sums = pl.sS[k + 1];
-                    } else {
-                        a.out = d0.p;
-                        a.out_ctot = d0.ctot;
-                        a.out_coff = 0;
-                        a.out_sums = nullptr;
-                    }
-                }
-                rc = launch_conv_fp32(a, st);
-                if (rc) return rc;
-            }
-        }
-    }
-
-    // ---------------- decoders (model.py:55-73, 97-100) ----------------
-    for (int j = 0; j < nb; ++j) {
-        const BufDesc &d = pl.D[j];
-        const int stride = (j == 0 || j == nb - 1) ? 1 : 2;
-        const bool last = j == nb - 1;
-        float *out = last ? d_y : pl.D[j + 1].p;
-        const int out_ctot = last ? n->out_ch : pl.D[j + 1].ctot;
-        const int Fout = last ? F : pl.D[j + 1].F;
-        double *out_sums = last ? nullptr : pl.D[j + 1].sums;
-        if (dense_dec(j)) {
-            const int c = 2 * n->de[j], g1 = n->de[j];
-            const BufDesc &y = pl.Y[j];
-            for (int k = 1; k <= 5; ++k) {
-                const ConvDesc &cd = n->dec_dense[j][k - 1];
-                if (k < 5)
-                    rc = run_conv(n, cd, false, d.p, d.ctot, 0, d.F, d.sums, d.p, d.ctot, c + (k - 1) * g1, d.F, d.sums, B,
-                                  T, 1, 1, true, st);
-                else
-                    rc = run_conv(n, cd, false, d.p, d.ctot, 0, d.F, d.sums, y.p, y.ctot, 0, y.F, y.sums, B, T, 1, 1, true,
-                                  st);
-                if (rc) return rc;
-            }
-            rc = run_conv(n, n->dec_deconv[j], true, y.p, y.ctot, 0, y.F, y.sums, out, out_ctot, 0, Fout, out_sums, B, T,
-                          stride, 0, !last, st);
-        } else {
-            rc = run_conv(n, n->dec_deconv[j], true, d.p, d.ctot, 0, d.F, d.sums, out, out_ctot, 0, Fout, out_sums, B, T,
-                          stride, 0, true, st);
-        }
-        if (rc) return rc;
-    }
-    return MISO_OK;
+    Walker w{net, pl, B, T, F, st, false};
+    return w.run(d_x, d_y);
 }
 
 int64_t miso_net_tap(miso_net_t *net, const char *name, float *d_out, int64_t capacity, int B, int T, int F, void *d_ws,
                      void *stream) {
     MISO_REQUIRE(net && name && d_out && d_ws, "miso_net_tap: null argument");
     Plan pl;
-    if (!make_plan(net, B, T, F, reinterpret_cast<char *>(d_ws), pl)) {
+    if (!full_plan(net, B, T, F, reinterpret_cast<char *>(d_ws), pl)) {
         set_error("miso_net_tap: bad shape");
         return MISO_E_ARG;
     }
@@ -884,13 +970,14 @@ int64_t miso_net_tap(miso_net_t *net, const char *name, float *d_out, int64_t ca
     int64_t total = (int64_t)B * c * T * buf->F;
     MISO_REQUIRE(total <= capacity, "miso_net_tap: output capacity %lld < %lld", (long long)capacity, (long long)total);
     int blocks = (int)std::min<int64_t>((total + 255) / 256, 8192);
-    tap_kernel<<<blocks, 256, 0, as_stream(stream)>>>(buf->p, buf->ctot, coff, c, buf->sums, 1.0 / ((double)T * buf->F),
-                                                      kInEps, d_out, B, T * buf->F);
+    tap_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16 *>(buf->p), buf->ctot, coff, c,
+                                                      net->mode == 2 ? 0 : 1, buf->sums, 1.0 / ((double)T * buf->F), kInEps,
+                                                      d_out, B, T * buf->F);
     MISO_LAUNCHED("tap_kernel");
     return total;
 }
 
-int miso_pack_miso1(const void *d_mix, float *d_x, int B, int M, int T, int F, const int *shifts, int n_shift,
+int miso_pack_miso1(const void *d_mix, void *d_x, int B, int M, int T, int F, const int *shifts, int n_shift,
                     void *stream) {
     MISO_REQUIRE(d_mix && d_x && shifts, "miso_pack_miso1: null argument");
     MISO_REQUIRE(M >= 1 && M <= 8, "miso_pack_miso1: M=%d unsupported (1..8)", M);
@@ -900,19 +987,19 @@ int miso_pack_miso1(const void *d_mix, float *d_x, int B, int M, int T, int F, c
     for (int k = 0; k < n_shift; ++k) sh.s[k] = ((shifts[k] % M) + M) % M;
     int64_t n = (int64_t)B * T * F;
     pack_miso1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float2 *>(d_mix), d_x, B, M, T * F, sh);
+        reinterpret_cast<const float2 *>(d_mix), reinterpret_cast<__nv_bfloat16 *>(d_x), B, M, T * F, sh);
     MISO_LAUNCHED("pack_miso1_kernel");
     return MISO_OK;
 }
 
-int miso_pack_miso3(const void *d_mix, const void *d_second, const void *d_third, float *d_x, int B, int M, int T, int F,
+int miso_pack_miso3(const void *d_mix, const void *d_second, const void *d_third, void *d_x, int B, int M, int T, int F,
                     void *stream) {
     MISO_REQUIRE(d_mix && d_second && d_third && d_x, "miso_pack_miso3: null argument");
-    MISO_REQUIRE(M >= 1, "miso_pack_miso3: bad M");
+    MISO_REQUIRE(M >= 1 && M <= 6, "miso_pack_miso3: M=%d unsupported (1..6)", M);
     int64_t n = (int64_t)B * T * F;
     pack_miso3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float2 *>(d_mix), reinterpret_cast<const float2 *>(d_second),
-        reinterpret_cast<const float2 *>(d_third), d_x, B, M, T * F);
+        reinterpret_cast<const float2 *>(d_third), reinterpret_cast<__nv_bfloat16 *>(d_x), B, M, T * F);
     MISO_LAUNCHED("pack_miso3_kernel");
     return MISO_OK;
 }

@@ -7,7 +7,8 @@
 below are *parameter containers only* (plumbing: storage, ``.cuda()``, ``state_dict``,
 default initialisation in the reference's construction order); none of their
 ``forward`` methods is ever called.  The arithmetic runs in the CUDA library through
-the C ABI (``include/misonet_b200.h``): pack -> ``miso_net_forward`` -> unpack.
+the C ABI (``include/misonet_b200.h``): pack (complex spectrogram -> bf16 hi/lo input planes) ->
+``miso_net_forward`` -> unpack.
 """
 import ctypes
 
@@ -219,8 +220,13 @@ class _MisoNet(nn.Module):
         per = lib.miso_net_workspace_bytes(self._handle, 1, T, F)
         return max(1, min(B, int(self.max_workspace_bytes // max(per, 1))))
 
+    def _input_planes(self, B, T, F, dev):
+        """Input buffer in the library's plane layout (include/misonet_b200.h): uint8 [B, bytes per sample]."""
+        per = _lib.load().miso_net_input_bytes(self._handle, 1, T, F)
+        return torch.empty(B, per, dtype=torch.uint8, device=dev)
+
     def _run_body(self, x_cl, B, T, F):
-        """x_cl: float32 [B,T,F,in_ch] channels-last -> float32 [B,T,F,out_ch]."""
+        """x_cl: input planes uint8 [B, bytes per sample] -> float32 [B,T,F,out_ch]."""
         lib = _lib.load()
         dev = x_cl.device
         y_cl = torch.empty(B, T, F, self._out_ch, dtype=torch.float32, device=dev)
@@ -288,7 +294,7 @@ class MISO_1(_MisoNet):
             raise ValueError(f"expected {self._in_ch // 2} microphones, got {M}")
         self._sync_params()
         n = len(shifts)
-        x_cl = torch.empty(n * B, T, F, 2 * M, dtype=torch.float32, device=mix.device)
+        x_cl = self._input_planes(n * B, T, F, mix.device)
         arr = (ctypes.c_int * n)(*[int(s) for s in shifts])
         _lib.check(_lib.load().miso_pack_miso1(_lib.ptr(mix), _lib.ptr(x_cl), B, M, T, F, arr, n, _lib.stream_ptr()),
                    "miso_pack_miso1")
@@ -316,7 +322,7 @@ class MISO_3(_MisoNet):
         if second.shape != (B, 1, T, F) or third.shape != (B, 1, T, F):
             raise ValueError("second/third inputs must be [B,1,T,F]")
         self._sync_params()
-        x_cl = torch.empty(B, T, F, self._in_ch, dtype=torch.float32, device=mix.device)
+        x_cl = self._input_planes(B, T, F, mix.device)
         _lib.check(_lib.load().miso_pack_miso3(_lib.ptr(mix), _lib.ptr(second), _lib.ptr(third), _lib.ptr(x_cl), B, M, T, F,
                                                _lib.stream_ptr()), "miso_pack_miso3")
         y_cl = self._run_body(x_cl, B, T, F)
