@@ -62,6 +62,9 @@ uint64_t miso_launch_count(void);
 int miso_prof_enable(int on);
 /* collects (and clears) the records of one family, or of all with MISO_PROF_ALL */
 int miso_prof_collect(int family, double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches);
+/* per-launch view of the queued records, in launch order: fills up to `capacity` entries of each
+ * non-NULL array and returns the count; the records stay queued for miso_prof_collect. */
+int miso_prof_dump(double *ms, double *flops, int *family, int capacity);
 
 /* ---- S1: STFT front end -------------------------------------------------------
  * replaces AudioDataset.STFT + "/scale" + permute, dataloader/data.py:49-66,77-79
@@ -110,6 +113,11 @@ size_t miso_net_input_bytes(const miso_net_t *net, int B, int T, int F);
 /* d_x : input planes (above); d_y : fp32 channels-last [B, T, F, out_ch]. */
 int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T, int F, void *d_ws,
                      size_t ws_bytes, void *stream);
+/* The forward's ~200 launches are captured into a CUDA graph the first time a given (d_x, d_y, d_ws,
+ * B, T, F, mode) is seen and replayed afterwards (weights are read through the handle, so repacking
+ * them needs no re-capture).  on = 0 disables this (every call enqueues the launches one by one);
+ * per-launch profiling (miso_prof_enable) always uses the eager path. */
+int miso_net_set_graph(miso_net_t *net, int on);
 /* debugging / parity taps: copy an internal activation of the LAST forward on this
  * workspace into a dense NCHW fp32 tensor (normalised as the reference sees it).
  * name: "enc<i>", "tcn", "dec<i>".  Returns the element count or a negative error. */

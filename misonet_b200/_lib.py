@@ -22,6 +22,7 @@ SIGNATURES = {
     "miso_prof_enable": (c_int, [c_int]),
     "miso_prof_collect": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                   POINTER(c_uint64)]),
+    "miso_prof_dump": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int), c_int]),
     "miso_stft_num_frames": (c_int, [c_int, c_int, c_int]),
     "miso_stft_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "miso_net_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int]),
@@ -31,6 +32,7 @@ SIGNATURES = {
     "miso_net_param_numel": (c_int64, [c_void_p, c_int]),
     "miso_net_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
     "miso_net_set_mode": (c_int, [c_void_p, c_int]),
+    "miso_net_set_graph": (c_int, [c_void_p, c_int]),
     "miso_net_check_shape": (c_int, [c_void_p, c_int, c_int]),
     "miso_net_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "miso_net_input_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <atomic>
+#include <vector>
 
 #include "../../include/misonet_b200.h"
 
@@ -42,7 +43,15 @@ inline int cuda_fail(cudaError_t e, const char *what) {
     } while (0)
 
 // optional per-launch event timing of the dominant kernel family (runtime.cu)
+struct ProfRec {
+    cudaEvent_t a, b;
+    double flops, bytes;
+    int family;
+    bool persistent;
+};
 bool prof_enabled();
+void prof_capture(std::vector<ProfRec> *sink);
+void prof_replayed(const std::vector<ProfRec> &recs);
 void prof_begin(cudaStream_t st);
 void prof_end(cudaStream_t st, double flops, double bytes, int family);
 

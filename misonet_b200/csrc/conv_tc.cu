@@ -26,6 +26,8 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 #include "conv.cuh"
 
@@ -50,7 +52,7 @@ struct TcGeom {
     int nset, nacc, nsp;
     // tiling
     int Wr, TT, TF, rows, G, N, nNt, ncols;
-    int t_tiles, f_tiles;
+    int t_tiles, f_tiles, ntiles, nbuf;  // nbuf = 2: the epilogue of tile k overlaps the MMAs of tile k+1
     int t_org, f_org, f_mul;   // input tile origin: t0 + t_org ; f = j0 * f_mul + f_org (+1 for the odd set)
     int ostride;               // fo = j * ostride + acc
     int nchunk, nplanes;
@@ -59,6 +61,7 @@ struct TcGeom {
     int off_btab, off_red, off_stage, smem_total;
     int tmem_cols;
     int strided;               // 5-D bf16 tensor map with element stride 2 along bins
+    int ntap_for(const ConvArgs &a) const { return a.KT * a.KF; }
 };
 
 struct TcArgs {
@@ -99,6 +102,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -193,19 +199,45 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// tile id -> (sample, N tile, frame tile, bin tile); bin tiles vary fastest so that consecutive tiles of a CTA
+// share the sample's weight image and bias table in L2
+struct TileRef {
+    int b, nt, t0, j0;
+};
+__device__ __forceinline__ TileRef decode_tile(const TcGeom &g, int tile) {
+    TileRef r;
+    const int ft = tile % g.f_tiles;
+    int q = tile / g.f_tiles;
+    const int tt = q % g.t_tiles;
+    q /= g.t_tiles;
+    r.nt = q % g.nNt;
+    r.b = q / g.nNt;
+    r.t0 = tt * g.TT;
+    r.j0 = ft * g.TF;
+    return r;
+}
+
+__device__ __forceinline__ float elu_fast(float x) {
+    // ELU(alpha = 1).  exp(x) - 1 through ex2.approx: absolute error ~1e-7, far below the bf16 hi+lo
+    // storage step of the activations (the fp32 FMA kernels keep expm1f)
+    return x > 0.f ? x : __expf(x) - 1.f;
+}
+
 template <int SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcGeom &g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.z, nt = blockIdx.y;
-    const int ft = blockIdx.x % g.f_tiles, ttile = blockIdx.x / g.f_tiles;
-    const int t0 = ttile * g.TT, j0 = ft * g.TF;
     const int N = g.N;
+    constexpr int WB = SPLIT == 3 ? 2 : 1;  // weight rows (and accumulator columns) per output channel
+    const int cw = WB * N;                  // accumulator columns per (M tile, phase)
+    const int buf_cols = g.G * g.nacc * cw; // accumulator columns per tile
 
-    const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 64), bar_done = smem_u32(smem + 128);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 136);
+    // barriers: full[s], empty[s] (operand stages); tfull[2], tempty[2] (TMEM accumulator buffers)
+    const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 64);
+    const uint32_t bar_tfull = smem_u32(smem + 128), bar_tempty = smem_u32(smem + 144);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 160);
     float *btab_s = reinterpret_cast<float *>(smem + g.off_btab);
     float *red = reinterpret_cast<float *>(smem + g.off_red);
     const uint32_t s_stage = smem_u32(smem + g.off_stage);
@@ -215,7 +247,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, kEpiThreads / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -224,10 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {
-        // border-bias table of this (sample, N tile); statistics scratch; and zero the operand stages so
-        // that a half-filled last chunk (cin % 16 == 8) never multiplies uninitialised shared memory
-        const float *src = a.btab + ((size_t)b * g.nNt + nt) * 64 * N;
-        for (int i = tid; i < 64 * N; i += kThreads) btab_s[i] = src[i];
+        // statistics scratch; and zero the operand stages once so that a half-filled last chunk
+        // (cin % 16 == 8) never multiplies uninitialised shared memory (later it sees stale finite data)
         for (int i = tid; i < 2 * N; i += kThreads) red[i] = 0.f;
         if (g.nplanes & 1) {
             uint4 *z = reinterpret_cast<uint4 *>(smem + g.off_stage);
@@ -244,28 +277,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (elect_one()) {
-            const int tin = t0 + g.t_org;
-            const int fin = j0 * g.f_mul + g.f_org;
             const int plane0 = a.in_coff >> 3;
-            const __nv_bfloat16 *wsrc = a.wimg + ((size_t)b * g.nNt + nt) * g.nchunk * (size_t)(g.w_stage / 2);
-            for (int c = 0; c < g.nchunk; ++c) {
-                const int s = c % g.nstage;
-                if (c >= g.nstage) mbar_wait(bar_empty + 8 * s, ((c / g.nstage) + 1) & 1);
-                const int np = min(2, g.nplanes - 2 * c);
-                const uint32_t full = bar_full + 8 * s;
-                mbar_expect_tx(full, (uint32_t)(g.nset * g.nsp * np * g.box_bytes + g.w_stage));
-                const uint32_t sa = s_stage + (uint32_t)(s * g.stage);
-                for (int set = 0; set < g.nset; ++set)
-                    for (int sp = 0; sp < g.nsp; ++sp)
-                        for (int p = 0; p < np; ++p) {
-                            const uint32_t dst = sa + (uint32_t)(((set * g.nsp + sp) * 2 + p) * g.PL);
-                            const CUtensorMap *tm = sp == 0 ? &tm_hi : &tm_lo;
-                            if (g.strided)
-                                tma_load_5d(dst, tm, full, 0, fin + set, tin, plane0 + 2 * c + p, b);
-                            else
-                                tma_load_4d(dst, tm, full, 2 * fin, tin, plane0 + 2 * c + p, b);
-                        }
-                bulk_load(sa + (uint32_t)g.a_stage, wsrc + (size_t)c * (g.w_stage / 2), (uint32_t)g.w_stage, full);
+            int q = 0;  // running chunk index over all tiles of this CTA
+            for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+                const TileRef tr = decode_tile(g, tile);
+                const int tin = tr.t0 + g.t_org;
+                const int fin = tr.j0 * g.f_mul + g.f_org;
+                const __nv_bfloat16 *wsrc = a.wimg + ((size_t)tr.b * g.nNt + tr.nt) * g.nchunk * (size_t)(g.w_stage / 2);
+                for (int c = 0; c < g.nchunk; ++c, ++q) {
+                    const int s = q % g.nstage;
+                    if (q >= g.nstage) mbar_wait(bar_empty + 8 * s, ((q / g.nstage) + 1) & 1);
+                    const int np = min(2, g.nplanes - 2 * c);
+                    const uint32_t full = bar_full + 8 * s;
+                    mbar_expect_tx(full, (uint32_t)(g.nset * g.nsp * np * g.box_bytes + g.w_stage));
+                    const uint32_t sa = s_stage + (uint32_t)(s * g.stage);
+                    for (int set = 0; set < g.nset; ++set)
+                        for (int sp = 0; sp < g.nsp; ++sp)
+                            for (int p = 0; p < np; ++p) {
+                                const uint32_t dst = sa + (uint32_t)(((set * g.nsp + sp) * 2 + p) * g.PL);
+                                const CUtensorMap *tm = sp == 0 ? &tm_hi : &tm_lo;
+                                if (g.strided)
+                                    tma_load_5d(dst, tm, full, 0, fin + set, tin, plane0 + 2 * c + p, tr.b);
+                                else
+                                    tma_load_4d(dst, tm, full, 2 * fin, tin, plane0 + 2 * c + p, tr.b);
+                            }
+                    bulk_load(sa + (uint32_t)g.a_stage, wsrc + (size_t)c * (g.w_stage / 2), (uint32_t)g.w_stage, full);
+                }
             }
         }
     } else if (warp == 1) {
@@ -274,158 +311,195 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         //   D[:, 0:N] , D[:, N:2N] += A_hi * [W_hi | W_lo]   (one MMA of width 2N)
         //   D[:, 0:N]              += A_lo * W_hi             (one MMA of width N)
         // and the epilogue adds the two column halves: 2 MMAs instead of 3, A_hi read once.
-        constexpr int WB = SPLIT == 3 ? 2 : 1;              // weight rows per output channel
-        const uint32_t idesc_wide = make_idesc(WB * N), idesc_n = make_idesc(N);
-        const uint32_t a_lbo = (uint32_t)g.PL, b_lbo = (uint32_t)(WB * N) * 16;
-        const uint32_t cw = (uint32_t)(WB * N);              // accumulator columns per (M tile, phase)
-        const uint32_t gstep = cw * (uint32_t)g.nacc;
-        for (int c = 0; c < g.nchunk; ++c) {
-            const int s = c % g.nstage;
-            mbar_wait(bar_full + 8 * s, (c / g.nstage) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint32_t abase = s_stage + (uint32_t)(s * g.stage);
-                const uint32_t bbase = abase + (uint32_t)g.a_stage;
-#pragma unroll 1
-                for (int i = 0; i < g.ntap; ++i) {
-                    const uint32_t a_hi = abase + (uint32_t)(g.aset[i] * g.nsp * 2 * g.PL) + (uint32_t)(g.shift[i] * 16);
-                    const uint64_t bdesc = make_desc(bbase + (uint32_t)(i * 2 * WB * N * 16), b_lbo, 128);
-                    const uint32_t acc_flag = (c == 0 && ((g.first_mask >> i) & 1)) ? 0u : 1u;
-                    const uint32_t d0 = tmem_base + (uint32_t)g.acc[i] * cw;
-                    uint64_t ad = make_desc(a_hi, a_lbo, 128);
-#pragma unroll 4
-                    for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_wide, acc_flag);
-                    if constexpr (SPLIT == 3) {
-                        ad = make_desc(a_hi + (uint32_t)(2 * g.PL), a_lbo, 128);
-#pragma unroll 4
-                        for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_n, 1u);
-                    }
-                }
-                umma_commit(bar_empty + 8 * s);
-                if (c == g.nchunk - 1) umma_commit(bar_done);
+        const uint32_t idesc_wide = make_idesc(cw), idesc_n = make_idesc(N);
+        const uint32_t a_lbo = (uint32_t)g.PL, b_lbo = (uint32_t)cw * 16;
+        const uint32_t gstep = (uint32_t)(cw * g.nacc);
+        int q = 0, k = 0;
+        for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++k) {
+            const int buf = g.nbuf == 2 ? (k & 1) : 0;
+            // the epilogue must have drained this accumulator buffer (use u = k / nbuf of it)
+            {
+                const int u = k / g.nbuf;
+                if (u > 0) mbar_wait(bar_tempty + 8 * buf, (u + 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            __syncwarp();
+            const uint32_t tbuf = tmem_base + (uint32_t)(buf * buf_cols);
+            for (int c = 0; c < g.nchunk; ++c, ++q) {
+                const int s = q % g.nstage;
+                mbar_wait(bar_full + 8 * s, (q / g.nstage) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t abase = s_stage + (uint32_t)(s * g.stage);
+                    const uint32_t bbase = abase + (uint32_t)g.a_stage;
+#pragma unroll 1
+                    for (int i = 0; i < g.ntap; ++i) {
+                        const uint32_t a_hi = abase + (uint32_t)(g.aset[i] * g.nsp * 2 * g.PL) + (uint32_t)(g.shift[i] * 16);
+                        const uint64_t bdesc = make_desc(bbase + (uint32_t)(i * 2 * cw * 16), b_lbo, 128);
+                        const uint32_t acc_flag = (c == 0 && ((g.first_mask >> i) & 1)) ? 0u : 1u;
+                        const uint32_t d0 = tbuf + (uint32_t)g.acc[i] * cw;
+                        uint64_t ad = make_desc(a_hi, a_lbo, 128);
+#pragma unroll 4
+                        for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_wide, acc_flag);
+                        if constexpr (SPLIT == 3) {
+                            ad = make_desc(a_hi + (uint32_t)(2 * g.PL), a_lbo, 128);
+#pragma unroll 4
+                            for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_n, 1u);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * s);
+                    if (c == g.nchunk - 1) umma_commit(bar_tfull + 8 * buf);
+                }
+                __syncwarp();
+            }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue
-        mbar_wait(bar_done, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---------------------------------------------------------------- epilogue (warps 2..9)
         const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int et = tid - 64;
         const int npix = a.T * a.Fout;
         const bool planes = a.out_layout == LAYOUT_PLANES;
-        __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
-        float *out_cl = reinterpret_cast<float *>(a.out) + (size_t)b * npix * a.out_ctot + a.out_coff;
-        const int co_base = nt * N;
-        for (int cb = 0; cb < N; cb += 16) {
-            float ssum[16], ssq[16];
+        int prev_b = -1, prev_nt = -1, k = 0;
+        for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++k) {
+            const TileRef tr = decode_tile(g, tile);
+            const int b = tr.b, t0 = tr.t0, j0 = tr.j0;
+            const int buf = g.nbuf == 2 ? (k & 1) : 0;
+            if (b != prev_b || tr.nt != prev_nt) {
+                // border-bias table of this (sample, N tile)
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
+                const float4 *src = reinterpret_cast<const float4 *>(a.btab + ((size_t)b * g.nNt + tr.nt) * 64 * N);
+                for (int i = et; i < 16 * N; i += kEpiThreads) reinterpret_cast<float4 *>(btab_s)[i] = __ldg(src + i);
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
+                prev_b = b;
+                prev_nt = tr.nt;
+            }
+            mbar_wait(bar_tfull + 8 * buf, (k / g.nbuf) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tbuf = tmem_base + (uint32_t)(buf * buf_cols);
+            __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
+            float *out_cl = reinterpret_cast<float *>(a.out) + (size_t)b * npix * a.out_ctot + a.out_coff;
+            const int co_base = tr.nt * N;
+            for (int cb = 0; cb < N; cb += 16) {
+                float ssum[16], ssq[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
-            for (int gt = half; gt < g.G; gt += 2) {
-                const int R = gt * 128 + quad * 32 + lane;
-                const int tt = R / g.Wr;
-                const int jl = R - tt * g.Wr;
-                const int t = t0 + tt, j = j0 + jl;
-                const bool rowok = tt < g.TT && t < a.T && jl < g.TF;
-                int tmask = 0;
+                for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
+                for (int gt = half; gt < g.G; gt += 2) {
+                    const int R = gt * 128 + quad * 32 + lane;
+                    const int tt = R / g.Wr;
+                    const int jl = R - tt * g.Wr;
+                    const int t = t0 + tt, j = j0 + jl;
+                    const bool rowok = tt < g.TT && t < a.T && jl < g.TF;
+                    int tmask = 0;
 #pragma unroll
-                for (int kt = 0; kt < 3; ++kt) {
-                    const int ti = a.transposed ? t + a.pad_t - kt : t + kt - a.pad_t;
-                    if (kt < a.KT && ti >= 0 && ti < a.T) tmask |= 1 << kt;
-                }
-                for (int ph = 0; ph < g.nacc; ++ph) {
-                    const int fo = j * g.ostride + ph;
-                    const bool valid = rowok && fo < a.Fout;
-                    int fmask = 0;
+                    for (int kt = 0; kt < 3; ++kt) {
+                        const int ti = a.transposed ? t + a.pad_t - kt : t + kt - a.pad_t;
+                        if (kt < a.KT && ti >= 0 && ti < a.T) tmask |= 1 << kt;
+                    }
+                    for (int ph = 0; ph < g.nacc; ++ph) {
+                        const int fo = j * g.ostride + ph;
+                        const bool valid = rowok && fo < a.Fout;
+                        int fmask = 0;
 #pragma unroll
-                    for (int kf = 0; kf < 3; ++kf) {
-                        bool ok;
-                        if (a.transposed) {
-                            const int num = fo + a.pad_f - kf;
-                            const int fi = num / a.stride_f;
-                            ok = num >= 0 && fi * a.stride_f == num && fi < a.Fin;
-                        } else {
-                            const int fi = fo * a.stride_f + kf - a.pad_f;
-                            ok = fi >= 0 && fi < a.Fin;
+                        for (int kf = 0; kf < 3; ++kf) {
+                            bool ok;
+                            if (a.transposed) {
+                                const int num = fo + a.pad_f - kf;
+                                const int fi = num / a.stride_f;
+                                ok = num >= 0 && fi * a.stride_f == num && fi < a.Fin;
+                            } else {
+                                const int fi = fo * a.stride_f + kf - a.pad_f;
+                                ok = fi >= 0 && fi < a.Fin;
+                            }
+                            if (kf < a.KF && ok) fmask |= 1 << kf;
                         }
-                        if (kf < a.KF && ok) fmask |= 1 << kf;
-                    }
-                    const float *bt = btab_s + (tmask * 8 + fmask) * N + cb;
-                    constexpr int WB = SPLIT == 3 ? 2 : 1;
-                    uint32_t v[16], v2[16];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((gt * g.nacc + ph) * WB * N + cb);
-                    tmem_ld16(taddr, v);
-                    if constexpr (SPLIT == 3) tmem_ld16(taddr + (uint32_t)N, v2);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    float y[16];
+                        const float *bt = btab_s + (tmask * 8 + fmask) * N + cb;
+                        uint32_t v[16], v2[16];
+                        const uint32_t taddr = tbuf + ((uint32_t)(quad * 32) << 16) + (uint32_t)((gt * g.nacc + ph) * cw + cb);
+                        tmem_ld16(taddr, v);
+                        if constexpr (SPLIT == 3) tmem_ld16(taddr + (uint32_t)N, v2);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float y[16];
 #pragma unroll
-                    for (int q = 0; q < 16; q += 4) {
-                        const float4 bb = *reinterpret_cast<const float4 *>(bt + q);
-                        y[q] = __uint_as_float(v[q]) + bb.x;
-                        y[q + 1] = __uint_as_float(v[q + 1]) + bb.y;
-                        y[q + 2] = __uint_as_float(v[q + 2]) + bb.z;
-                        y[q + 3] = __uint_as_float(v[q + 3]) + bb.w;
-                    }
-                    if constexpr (SPLIT == 3) {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) y[q] += __uint_as_float(v2[q]);
-                    }
-                    if (a.elu) {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) y[q] = elu1(y[q]);
-                    }
-                    if (valid) {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            ssum[q] += y[q];
-                            ssq[q] = fmaf(y[q], y[q], ssq[q]);
+                        for (int q = 0; q < 16; q += 4) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(bt + q);
+                            y[q] = __uint_as_float(v[q]) + bb.x;
+                            y[q + 1] = __uint_as_float(v[q + 1]) + bb.y;
+                            y[q + 2] = __uint_as_float(v[q + 2]) + bb.z;
+                            y[q + 3] = __uint_as_float(v[q + 3]) + bb.w;
                         }
-                        const int pix = t * a.Fout + fo;
-                        if (planes) {
+                        if constexpr (SPLIT == 3) {
 #pragma unroll
-                            for (int g8 = 0; g8 < 16; g8 += 8) {
-                                const int co = co_base + cb + g8;
-                                if (co < a.cout) {
-                                    const int ca = a.out_coff + co;
-                                    __nv_bfloat16 *p = out_pl + ((size_t)(ca >> 3) * npix + pix) * 8;
-                                    float h[8];
+                            for (int q = 0; q < 16; ++q) y[q] += __uint_as_float(v2[q]);
+                        }
+                        if (a.elu) {
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) h[q] = bf16_round(y[g8 + q]);
-                                    *reinterpret_cast<uint4 *>(p) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
-                                                                               pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-                                    if (a.use_lo) {
-                                        *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(p) + a.out_lo_off) = make_uint4(
-                                            pack_bf16x2(y[g8] - h[0], y[g8 + 1] - h[1]), pack_bf16x2(y[g8 + 2] - h[2], y[g8 + 3] - h[3]),
-                                            pack_bf16x2(y[g8 + 4] - h[4], y[g8 + 5] - h[5]), pack_bf16x2(y[g8 + 6] - h[6], y[g8 + 7] - h[7]));
+                            for (int q = 0; q < 16; ++q) y[q] = elu_fast(y[q]);
+                        }
+                        if (valid) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                ssum[q] += y[q];
+                                ssq[q] = fmaf(y[q], y[q], ssq[q]);
+                            }
+                            const int pix = t * a.Fout + fo;
+                            if (planes) {
+#pragma unroll
+                                for (int g8 = 0; g8 < 16; g8 += 8) {
+                                    const int co = co_base + cb + g8;
+                                    if (co < a.cout) {
+                                        const int ca = a.out_coff + co;
+                                        __nv_bfloat16 *p = out_pl + ((size_t)(ca >> 3) * npix + pix) * 8;
+                                        uint32_t hp[4];
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) hp[q] = pack_bf16x2(y[g8 + 2 * q], y[g8 + 2 * q + 1]);
+                                        *reinterpret_cast<uint4 *>(p) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                                        if (a.use_lo) {
+                                            uint32_t lp[4];
+#pragma unroll
+                                            for (int q = 0; q < 4; ++q)
+                                                lp[q] = pack_bf16x2(y[g8 + 2 * q] - bf16_lo(hp[q]), y[g8 + 2 * q + 1] - bf16_hi(hp[q]));
+                                            *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(p) + a.out_lo_off) =
+                                                make_uint4(lp[0], lp[1], lp[2], lp[3]);
+                                        }
                                     }
                                 }
-                            }
-                        } else {
-                            float *o = out_cl + (size_t)pix * a.out_ctot + co_base + cb;
+                            } else {
+                                float *o = out_cl + (size_t)pix * a.out_ctot + co_base + cb;
 #pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                                if (co_base + cb + q < a.cout) o[q] = y[q];
+                                for (int q = 0; q < 16; ++q)
+                                    if (co_base + cb + q < a.cout) o[q] = y[q];
+                            }
                         }
                     }
                 }
-            }
-            if (a.out_sums) {
-                const float s = warp_reduce16(ssum, lane);
-                const float q2 = warp_reduce16(ssq, lane);
-                if ((lane & 1) == 0) {
-                    atomicAdd(&red[(cb + (lane >> 1)) * 2], s);
-                    atomicAdd(&red[(cb + (lane >> 1)) * 2 + 1], q2);
+                if (a.out_sums) {
+                    const float s = warp_reduce16(ssum, lane);
+                    const float q2 = warp_reduce16(ssq, lane);
+                    if ((lane & 1) == 0) {
+                        atomicAdd(&red[(cb + (lane >> 1)) * 2], s);
+                        atomicAdd(&red[(cb + (lane >> 1)) * 2 + 1], q2);
+                    }
                 }
             }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
-        const int et = tid - 64;
-        if (a.out_sums && et < N && co_base + et < a.cout) {
-            double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + co_base + et) * 2;
-            atomicAdd(dst, (double)red[et * 2]);
-            atomicAdd(dst + 1, (double)red[et * 2 + 1]);
+            // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            if (a.out_sums) {
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
+                if (et < N) {
+                    if (co_base + et < a.cout) {
+                        double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + co_base + et) * 2;
+                        atomicAdd(dst, (double)red[et * 2]);
+                        atomicAdd(dst + 1, (double)red[et * 2 + 1]);
+                    }
+                    red[et * 2] = 0.f;
+                    red[et * 2 + 1] = 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
+            }
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -583,12 +657,71 @@ bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
             g.first_mask |= 1 << i;
         }
     };
-    // columns per tile
-    int TF = std::min(g.ncols, 64);
-    g.f_tiles = (g.ncols + TF - 1) / TF;
-    TF = (g.ncols + g.f_tiles - 1) / g.f_tiles;
-    g.TF = TF;
-    g.Wr = TF + extra_w;
+    // ---- tile search: bins per tile (TF), frames per tile (TT <-> G M-tiles of 128 raster rows) and whether the
+    // TMEM accumulators are double buffered, by a small cost model (cycles per tile, measured MMA issue costs:
+    // 32 + Nw/4 cycles for an MMA of width Nw <= 128 -- the A tile is read from shared memory at 128 B/clk)
+    const int cw = g.N * g.nsp;  // accumulator columns per (M tile, phase): bf16x3 keeps the w_hi / w_lo halves apart
+    g.off_btab = kFixedSmem;
+    g.off_red = g.off_btab + 64 * g.N * 4;
+    g.off_stage = round_up(g.off_red + 2 * g.N * 4, 1024);
+    g.w_stage = g.nsp * g.ntap_for(a) * 2 * g.N * 16;
+    auto mma_cost = [](int nw) { return nw <= 128 ? 32.0 + nw / 4.0 : nw / 2.0; };
+    const double cyc_mma = split == 3 ? mma_cost(2 * g.N) + mma_cost(g.N) : mma_cost(g.N);
+    const int ntap_n = g.ntap_for(a);
+    const int maxshift_k = a.KF == 1 ? 0 : (s2 ? 1 : 2);
+    double best = 1e300;
+    TcGeom bg{};
+    bool found = false;
+    for (int tf_cap : {16, 24, 32, 48, 64, 96, 128}) {
+        if (tf_cap > 16 && tf_cap / 2 >= g.ncols) continue;
+        for (int nbuf = 2; nbuf >= 1; --nbuf) {
+            TcGeom c = g;
+            int TF = std::min(g.ncols, tf_cap);
+            c.f_tiles = (g.ncols + TF - 1) / TF;
+            TF = (g.ncols + c.f_tiles - 1) / c.f_tiles;
+            c.TF = TF;
+            c.Wr = TF + extra_w;
+            if (2 * c.Wr > 256) continue;
+            const int Gmax = std::min(8, 512 / (cw * g.nacc * nbuf));
+            if (Gmax < 1) continue;
+            const int maxshift = a.KT == 1 ? 0 : 2 * c.Wr + maxshift_k;
+            for (int G = Gmax; G >= 1; --G) {
+                int TT = std::min({a.T, 128 * G / c.Wr, 254 - 2 * halo_t});
+                if (TT < 1) break;
+                c.t_tiles = (a.T + TT - 1) / TT;
+                TT = (a.T + c.t_tiles - 1) / c.t_tiles;
+                c.TT = TT;
+                c.rows = TT + 2 * halo_t;
+                c.G = (TT * c.Wr + 127) / 128;
+                c.nbuf = nbuf;
+                c.box_bytes = c.rows * c.Wr * 16;
+                c.PL = round_up(std::max(c.rows * c.Wr, 128 * c.G + maxshift) * 16, 128);
+                c.a_stage = c.nset * c.nsp * 2 * c.PL;
+                c.stage = c.a_stage + round_up(c.w_stage, 128);
+                c.nstage = std::min(kMaxStages, (kSmemLimit - c.off_stage) / c.stage);
+                if (c.nstage < 2) continue;
+                c.ntiles = a.B * c.nNt * c.t_tiles * c.f_tiles;
+                const double main_cyc = (double)c.nchunk * ntap_n * c.G * cyc_mma;
+                const double load_cyc = (double)c.nchunk * (c.nset * c.nsp * 2 * c.box_bytes + c.w_stage) / 24.0;  // ~L2 -> SM bytes/clk
+                const double epi_cyc = 0.35 * c.G * 128.0 * c.N * c.nacc + 1500.0;
+                const double body = std::max(main_cyc, load_cyc);
+                const double tile_cyc = nbuf == 2 ? std::max(body, epi_cyc) + 500.0 : body + epi_cyc + 2500.0;
+                const int ctas = std::min(c.ntiles, 148);
+                const double total = std::ceil((double)c.ntiles / ctas) * tile_cyc + 6000.0;
+                if (total < best) {
+                    best = total;
+                    bg = c;
+                    found = true;
+                }
+            }
+        }
+    }
+    if (!found) return false;
+    {
+        const int keep_ntap = g.ntap;
+        g = bg;
+        g.ntap = keep_ntap;
+    }
     const int Wr = g.Wr;
     if (a.KT == 1 && a.KF == 1) {
         add(0, 0, 0, 0, 0, 0, Wr);
@@ -626,43 +759,11 @@ bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
         g.f_org = -1;
         g.f_mul = 1;
     }
-    int maxshift = 0;
-    for (int i = 0; i < g.ntap; ++i) maxshift = std::max(maxshift, g.shift[i]);
-    const int cw = g.N * g.nsp;  // accumulator columns per (M tile, phase): bf16x3 keeps the w_hi / w_lo halves apart
-    const int Gmax = std::min(8, 512 / (cw * g.nacc));
-    if (Gmax < 1) return false;
-    g.off_btab = kFixedSmem;
-    g.off_red = g.off_btab + 64 * g.N * 4;
-    g.off_stage = round_up(g.off_red + 2 * g.N * 4, 1024);
-    g.w_stage = g.nsp * g.ntap * 2 * g.N * 16;
-    for (int G = Gmax; G >= 1; --G) {
-        int TT = std::min({a.T, 128 * G / Wr, 254 - 2 * halo_t});
-        if (TT < 1) continue;
-        int t_tiles = (a.T + TT - 1) / TT;
-        // small layers: prefer at least ~2 CTAs per SM over the largest tile
-        while (TT > 4 && (int64_t)t_tiles * g.f_tiles * g.nNt * a.B < 2 * 148) {
-            TT = (TT + 1) / 2;
-            t_tiles = (a.T + TT - 1) / TT;
-        }
-        TT = (a.T + t_tiles - 1) / t_tiles;
-        g.TT = TT;
-        g.t_tiles = t_tiles;
-        g.rows = TT + 2 * halo_t;
-        g.G = (TT * Wr + 127) / 128;
-        g.box_bytes = g.rows * Wr * 16;
-        g.PL = round_up(std::max(g.rows * Wr, 128 * g.G + maxshift) * 16, 128);
-        g.a_stage = g.nset * g.nsp * 2 * g.PL;
-        g.stage = g.a_stage + round_up(g.w_stage, 128);
-        g.nstage = std::min({kMaxStages, (kSmemLimit - g.off_stage) / g.stage, std::max(g.nchunk, 2)});
-        if (g.nstage >= 2) {
-            g.smem_total = g.off_stage + g.nstage * g.stage;
-            int cols = 32;
-            while (cols < g.G * g.nacc * cw) cols <<= 1;
-            g.tmem_cols = cols;
-            return cols <= 512 && g.rows <= 256 && 2 * Wr <= 256;
-        }
-    }
-    return false;
+    g.smem_total = g.off_stage + g.nstage * g.stage;
+    int cols = 32;
+    while (cols < g.nbuf * g.G * g.nacc * cw) cols <<= 1;
+    g.tmem_cols = cols;
+    return cols <= 512 && g.rows <= 256;
 }
 
 int encode_maps(const ConvArgs &a, const TcGeom &g, CUtensorMap *hi, CUtensorMap *lo) {
@@ -705,6 +806,21 @@ int encode_maps(const ConvArgs &a, const TcGeom &g, CUtensorMap *hi, CUtensorMap
 
 }  // namespace
 
+// one-time, capture-unsafe setup (function attributes, driver entry point); called before graph capture
+int conv_tc_init() {
+    static bool done = false;
+    if (done) return MISO_OK;
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
+    if (!get_encode()) {
+        set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver");
+        return MISO_E_CUDA;
+    }
+    done = true;
+    return MISO_OK;
+}
+
 bool conv_tc_eligible(const ConvArgs &a) {
     if (!((a.KT == 3 && a.KF == 3) || (a.KT == 1 && a.KF == 1))) return false;
     if (a.KT == 3 && a.pad_t != 1) return false;
@@ -735,6 +851,13 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
                   scratch.btab_bytes, need_b);
         return MISO_E_WORKSPACE;
     }
+    static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr,
+                "conv_tc: cin=%d cout=%d Fin=%d Fout=%d s=%d tr=%d | N=%d nNt=%d TF=%d Wr=%d TT=%d G=%d nbuf=%d nstage=%d stage=%dB "
+                "tiles=%d (t%d x f%d) tmem=%d smem=%d\n",
+                a.cin, a.cout, a.Fin, a.Fout, a.stride_f, a.transposed, g.N, g.nNt, g.TF, g.Wr, g.TT, g.G, g.nbuf, g.nstage, g.stage,
+                g.ntiles, g.t_tiles, g.f_tiles, g.tmem_cols, g.smem_total);
     CUtensorMap tm_hi, tm_lo;
     int rc = encode_maps(a, g, &tm_hi, &tm_lo);
     if (rc) return rc;
@@ -792,15 +915,9 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     k.transposed = a.transposed;
     k.elu = a.elu;
 
-    static bool attr_set[2] = {false, false};
-    const int ai = split == 3 ? 1 : 0;
-    if (!attr_set[ai]) {
-        cudaError_t e = split == 3 ? cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)
-                                   : cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
-        attr_set[ai] = true;
-    }
-    dim3 grid(g.t_tiles * g.f_tiles, g.nNt, a.B);
+    rc = conv_tc_init();
+    if (rc) return rc;
+    dim3 grid(std::min(g.ntiles, 148), 1, 1);  // persistent: one CTA per SM walks the tile list
     if (split == 3)
         conv_tc_kernel<3><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
     else

@@ -287,6 +287,20 @@ struct miso_net {
     float *arena = nullptr;
     int mode = 0;
     int n_loaded = 0;
+    // CUDA-graph cache of the forward launch sequence (about 200 launches, 140 tensor-map encodes):
+    // keyed by everything that is baked into the kernel arguments
+    struct GraphEntry {
+        const void *x;
+        float *y;
+        void *ws;
+        int B, T, F, mode, prof;
+        cudaGraphExec_t exec;
+        uint64_t launches;
+        std::vector<miso::ProfRec> recs;  // per-launch timing events baked into the graph (prof = 1)
+    };
+    std::vector<GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;
+    int use_graph = 1;
 };
 
 namespace miso {
@@ -707,6 +721,8 @@ int Walker::run(const void *d_x, float *d_y) {
     return MISO_OK;
 }
 
+int enqueue_forward(miso_net *net, const Plan &pl, const void *d_x, float *d_y, int B, int T, int F, cudaStream_t st);
+
 bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
     if (!make_plan(n, B, T, F, base, pl)) return false;
     Walker w{n, pl, B, T, F, nullptr, true};
@@ -809,6 +825,8 @@ int miso_net_create(miso_net_t **out, int in_ch, int out_ch, int num_bottleneck,
 
 int miso_net_destroy(miso_net_t *net) {
     if (!net) return MISO_OK;
+    for (auto &g : net->graphs) cudaGraphExecDestroy(g.exec);
+    if (net->cap_stream) cudaStreamDestroy(net->cap_stream);
     if (net->arena) cudaFree(net->arena);
     delete net;
     return MISO_OK;
@@ -918,6 +936,61 @@ int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T,
         return MISO_E_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
+    // Replay a captured graph when nothing baked into the kernel arguments changed.  With per-launch
+    // profiling on (miso_prof_enable) the graph additionally carries event-record nodes around every conv.
+    if (net->use_graph) {
+        const int prof = prof_enabled() ? 1 : 0;
+        for (auto &g : net->graphs)
+            if (g.x == d_x && g.y == d_y && g.ws == d_ws && g.B == B && g.T == T && g.F == F && g.mode == net->mode &&
+                g.prof == prof) {
+                MISO_CUDA(cudaGraphLaunch(g.exec, st));
+                g_launch_count.fetch_add(g.launches, std::memory_order_relaxed);
+                if (prof) prof_replayed(g.recs);
+                return MISO_OK;
+            }
+        rc = conv_tc_init();
+        if (rc) return rc;
+        if (!net->cap_stream) MISO_CUDA(cudaStreamCreateWithFlags(&net->cap_stream, cudaStreamNonBlocking));
+        const uint64_t l0 = g_launch_count.load();
+        std::vector<ProfRec> recs;
+        MISO_CUDA(cudaStreamBeginCapture(net->cap_stream, cudaStreamCaptureModeThreadLocal));
+        prof_capture(&recs);
+        rc = enqueue_forward(net, pl, d_x, d_y, B, T, F, net->cap_stream);
+        prof_capture(nullptr);
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(net->cap_stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        miso_net::GraphEntry e{d_x, d_y, d_ws, B, T, F, net->mode, prof, nullptr, g_launch_count.load() - l0, recs};
+        ce = cudaGraphInstantiate(&e.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+        if (net->graphs.size() >= 8) {
+            cudaGraphExecDestroy(net->graphs.front().exec);
+            net->graphs.erase(net->graphs.begin());
+        }
+        net->graphs.push_back(e);
+        MISO_CUDA(cudaGraphLaunch(e.exec, st));
+        if (prof) prof_replayed(e.recs);
+        return MISO_OK;
+    }
+    return enqueue_forward(net, pl, d_x, d_y, B, T, F, st);
+}
+
+int miso_net_set_graph(miso_net_t *net, int on) {
+    MISO_REQUIRE(net, "miso_net_set_graph: null handle");
+    net->use_graph = on ? 1 : 0;
+    return MISO_OK;
+}
+
+}  // extern "C"
+
+namespace miso {
+namespace {
+int enqueue_forward(miso_net *net, const Plan &pl, const void *d_x, float *d_y, int B, int T, int F, cudaStream_t st) {
     const int C = net->C;
 
     MISO_CUDA(cudaMemsetAsync(pl.stats_base, 0, pl.stats_bytes, st));
@@ -932,6 +1005,10 @@ int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T,
     Walker w{net, pl, B, T, F, st, false};
     return w.run(d_x, d_y);
 }
+}  // namespace
+}  // namespace miso
+
+extern "C" {
 
 int64_t miso_net_tap(miso_net_t *net, const char *name, float *d_out, int64_t capacity, int B, int T, int F, void *d_ws,
                      void *stream) {

@@ -19,16 +19,13 @@ void set_error(const char *fmt, ...) {
 
 // ---- per-launch event profiler ---------------------------------------------------------
 namespace {
-struct ProfRec {
-    cudaEvent_t a, b;
-    double flops, bytes;
-    int family;
-};
+
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_pool;
 std::atomic<bool> g_prof_on{false};
 thread_local cudaEvent_t g_open = nullptr;
+thread_local std::vector<ProfRec> *g_sink = nullptr;  // set while a forward is being captured into a CUDA graph
 
 cudaEvent_t get_event() {
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -44,10 +41,23 @@ cudaEvent_t get_event() {
 }  // namespace
 
 bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+// While capturing, the events become event-record NODES of the graph (cudaEventRecordExternal): every replay
+// re-records them, and prof_replayed() queues them for the next miso_prof_collect.
+void prof_capture(std::vector<ProfRec> *sink) { g_sink = sink; }
+void prof_replayed(const std::vector<ProfRec> &recs) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto r : recs) {
+        r.persistent = true;
+        g_prof.push_back(r);
+    }
+}
 void prof_begin(cudaStream_t st) {
     if (!prof_enabled()) return;
     g_open = get_event();
-    cudaEventRecord(g_open, st);
+    if (g_sink)
+        cudaEventRecordWithFlags(g_open, st, cudaEventRecordExternal);
+    else
+        cudaEventRecord(g_open, st);
 }
 void prof_end(cudaStream_t st, double flops, double bytes, int family) {
     if (!g_open) return;
@@ -55,10 +65,16 @@ void prof_end(cudaStream_t st, double flops, double bytes, int family) {
     r.a = g_open;
     g_open = nullptr;
     r.b = get_event();
-    cudaEventRecord(r.b, st);
     r.flops = flops;
     r.bytes = bytes;
     r.family = family;
+    r.persistent = false;
+    if (g_sink) {
+        cudaEventRecordWithFlags(r.b, st, cudaEventRecordExternal);
+        g_sink->push_back(r);
+        return;
+    }
+    cudaEventRecord(r.b, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(r);
 }
@@ -94,6 +110,7 @@ int miso_prof_collect(int family, double *total_ms, double *total_flops, double 
     {
         std::lock_guard<std::mutex> lk(miso::g_prof_mu);
         for (auto &r : recs) {
+            if (r.persistent) continue;  // owned by a captured graph
             miso::g_pool.push_back(r.a);
             miso::g_pool.push_back(r.b);
         }
@@ -105,6 +122,27 @@ int miso_prof_collect(int family, double *total_ms, double *total_flops, double 
     return MISO_OK;
 }
 
+
+int miso_prof_dump(double *ms, double *flops, int *family, int capacity) {
+    // per-record times of everything queued since the last collect, in launch order (records stay queued)
+    std::vector<miso::ProfRec> recs;
+    {
+        std::lock_guard<std::mutex> lk(miso::g_prof_mu);
+        recs = miso::g_prof;
+    }
+    int n = 0;
+    for (auto &r : recs) {
+        if (n >= capacity) break;
+        if (cudaEventSynchronize(r.b) != cudaSuccess) return MISO_E_CUDA;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return MISO_E_CUDA;
+        if (ms) ms[n] = t;
+        if (flops) flops[n] = r.flops;
+        if (family) family[n] = r.family;
+        ++n;
+    }
+    return n;
+}
 
 int miso_abi_version(void) { return MISO_ABI_VERSION; }
 const char *miso_last_error(void) { return miso::g_err; }
