@@ -118,6 +118,10 @@ int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T,
  * them needs no re-capture).  on = 0 disables this (every call enqueues the launches one by one);
  * per-launch profiling (miso_prof_enable) always uses the eager path. */
 int miso_net_set_graph(miso_net_t *net, int on);
+/* debugging: subsequent tensor-core conv launches whose (cin, Fin) match write a clock64 event log of
+ * their CTA 0 into d_buf (3 x 4096 int64: producer / MMA issuer / epilogue regions of (tag, clock) pairs;
+ * see tools/tc_trace.py).  d_buf = NULL turns it off.  Use with miso_net_set_graph(net, 0). */
+int miso_debug_tc_trace(long long *d_buf, int cin, int fin);
 /* debugging / parity taps: copy an internal activation of the LAST forward on this
  * workspace into a dense NCHW fp32 tensor (normalised as the reference sees it).
  * name: "enc<i>", "tcn", "dec<i>".  Returns the element count or a negative error. */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "miso_net_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
     "miso_net_set_mode": (c_int, [c_void_p, c_int]),
     "miso_net_set_graph": (c_int, [c_void_p, c_int]),
+    "miso_debug_tc_trace": (c_int, [c_void_p, c_int, c_int]),
     "miso_net_check_shape": (c_int, [c_void_p, c_int, c_int]),
     "miso_net_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "miso_net_input_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),

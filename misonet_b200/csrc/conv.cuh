@@ -62,6 +62,7 @@ struct TcScratch {
     size_t wimg_bytes, btab_bytes;
 };
 int conv_tc_init();
+void conv_tc_set_trace(long long *d_buf, int cin, int fin);
 bool conv_tc_eligible(const ConvArgs &a);
 void conv_tc_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size_t *btab_bytes);
 int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream);

@@ -40,6 +40,7 @@ constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 4;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kFixedSmem = 1024;    // barriers, tmem slot
+constexpr int kBiasCi = 64;         // input channels per border-bias partial block (conv_tc_prep_kernel)
 
 struct TcGeom {
     // tap table
@@ -55,19 +56,22 @@ struct TcGeom {
     int t_tiles, f_tiles, ntiles, nbuf;  // nbuf = 2: the epilogue of tile k overlaps the MMAs of tile k+1
     int t_org, f_org, f_mul;   // input tile origin: t0 + t_org ; f = j0 * f_mul + f_org (+1 for the odd set)
     int ostride;               // fo = j * ostride + acc
-    int nchunk, nplanes;
+    int nchunk, nplanes, kper, nunit;  // a stage holds kper 16-channel K units (2 planes each); nunit = total units
     // shared memory
-    int PL, a_stage, w_stage, stage, nstage, box_bytes;
-    int off_btab, off_red, off_stage, smem_total;
+    int PL, GS, a_stage, w_unit, w_stage, stage, nstage, box_bytes;  // PL: plane bytes; GS: bytes of one (set, split) box  // w_unit: weight image bytes of one K unit
+    int off_btab, off_red, off_list, off_stage, smem_total;
     int tmem_cols;
     int strided;               // 5-D bf16 tensor map with element stride 2 along bins
+    int ppb;                   // planes per TMA box: 2*kper (dense planes, one box per stage) or 1 (padded planes)
     int ntap_for(const ConvArgs &a) const { return a.KT * a.KF; }
 };
 
 struct TcArgs {
     TcGeom g;
     const __nv_bfloat16 *wimg;  // [B][nNt][nchunk][ntap][2][nsp*N][8]
-    const float *btab;          // [B][nNt][64][N]
+    const float *btab;          // border-bias partial sums [B][nNt][nsplit][9][N] (conv_tc_prep_kernel)
+    const float *bias;          // [cout_pad] or null
+    int nsplit;
     void *out;
     double *out_sums;
     int B, T, Fin, Fout;
@@ -77,19 +81,38 @@ struct TcArgs {
     size_t out_lo_off;
     int use_lo;
     int KT, KF, stride_f, pad_t, pad_f, transposed, elu;
+    size_t wimg_bstride;        // elements between the weight images of consecutive samples (0: one shared image)
+    const double *gln_sums;     // non-null: multiply the accumulator by the sample's gLN rstd (weights carry gamma only)
+    double gln_inv_n;
+    float gln_eps;
+    const float *resid;         // optional fp32 channels-last residual (TCN, model.py:549), added before the store
+    int resid_ctot, resid_coff;
+    long long *trace;  // debug: clock64 event log of CTA 0 (tools/tc_trace.py), or null
 };
+
+// trace regions: [0,4096) producer, [4096,8192) MMA issuer, [8192,12288) epilogue warp 2; entries are (tag, clock)
+__device__ __forceinline__ void trace_ev(long long *trace, int region, int &n, int tag) {
+    if (trace && blockIdx.x == 0 && n < 2040) {
+        trace[region * 4096 + 2 * n] = tag;
+        trace[region * 4096 + 2 * n + 1] = clock64();
+        ++n;
+    }
+}
 
 struct PrepArgs {
     const float *w;        // packed fp32 [ntaps][cin][cout_pad]
     const float *bias;     // [cout_pad] or null
     const double *in_sums;
+    const float *gamma, *beta;  // NORM_GLN
     int in_ctot, in_coff, cin, cout, cout_pad;
     int norm_mode;
     float norm_eps;
     double norm_inv_n;
     __nv_bfloat16 *wimg;
     float *btab;
-    int B, N, nNt, nchunk, nsp, ntap, KT, KF;
+    int B, N, nNt, nunit, nsp, ntap, KT, KF;
+    int shared_w;  // gLN: one weight image for all samples (scaled by gamma only; rstd is applied in the epilogue)
+    int nsplit;    // channel splits of the border-bias partial sums
     int tapk[kMaxTaps];
 };
 
@@ -223,7 +246,7 @@ __device__ __forceinline__ float elu_fast(float x) {
     return x > 0.f ? x : __expf(x) - 1.f;
 }
 
-template <int SPLIT>
+template <int SPLIT, int VAR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -259,14 +282,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {
-        // statistics scratch; and zero the operand stages once so that a half-filled last chunk
-        // (cin % 16 == 8) never multiplies uninitialised shared memory (later it sees stale finite data)
+        // statistics scratch
         for (int i = tid; i < 2 * N; i += kThreads) red[i] = 0.f;
-        if (g.nplanes & 1) {
-            uint4 *z = reinterpret_cast<uint4 *>(smem + g.off_stage);
-            const int n16 = g.nstage * g.stage / 16;
-            for (int i = tid; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -279,29 +296,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         if (elect_one()) {
             const int plane0 = a.in_coff >> 3;
             int q = 0;  // running chunk index over all tiles of this CTA
+            int ntr = 0;
             for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
                 const TileRef tr = decode_tile(g, tile);
                 const int tin = tr.t0 + g.t_org;
                 const int fin = tr.j0 * g.f_mul + g.f_org;
-                const __nv_bfloat16 *wsrc = a.wimg + ((size_t)tr.b * g.nNt + tr.nt) * g.nchunk * (size_t)(g.w_stage / 2);
+                const __nv_bfloat16 *wsrc = a.wimg + (size_t)tr.b * a.wimg_bstride + (size_t)tr.nt * g.nunit * (size_t)(g.w_unit / 2);
                 for (int c = 0; c < g.nchunk; ++c, ++q) {
                     const int s = q % g.nstage;
+                    trace_ev(a.trace, 0, ntr, 100 + c);
                     if (q >= g.nstage) mbar_wait(bar_empty + 8 * s, ((q / g.nstage) + 1) & 1);
-                    const int np = min(2, g.nplanes - 2 * c);
+                    trace_ev(a.trace, 0, ntr, 200 + c);
+                    const int pbase = 2 * g.kper * c;
+                    const int np = min(2 * g.kper, g.nplanes - pbase);
+                    const int nu = (np + 1) >> 1;
                     const uint32_t full = bar_full + 8 * s;
-                    mbar_expect_tx(full, (uint32_t)(g.nset * g.nsp * np * g.box_bytes + g.w_stage));
+                    const int nbox = g.ppb == 1 ? 2 * nu : 1;  // an odd last plane pairs with an out-of-bounds (zero) plane
+                    mbar_expect_tx(full, (uint32_t)(g.nset * g.nsp * nbox * g.ppb * g.box_bytes + nu * g.w_unit));
                     const uint32_t sa = s_stage + (uint32_t)(s * g.stage);
+                    // one box = all 2*kper planes of the stage (planes past the view's last one are either the next
+                    // channels of the buffer -- finite, multiplied by zero weights -- or out of bounds -> zero fill)
                     for (int set = 0; set < g.nset; ++set)
-                        for (int sp = 0; sp < g.nsp; ++sp)
-                            for (int p = 0; p < np; ++p) {
-                                const uint32_t dst = sa + (uint32_t)(((set * g.nsp + sp) * 2 + p) * g.PL);
-                                const CUtensorMap *tm = sp == 0 ? &tm_hi : &tm_lo;
+                        for (int sp = 0; sp < g.nsp; ++sp) {
+                            const CUtensorMap *tm = sp == 0 ? &tm_hi : &tm_lo;
+                            for (int p = 0; p < nbox; ++p) {
+                                const uint32_t dst = sa + (uint32_t)((set * g.nsp + sp) * g.GS + p * g.PL);
                                 if (g.strided)
-                                    tma_load_5d(dst, tm, full, 0, fin + set, tin, plane0 + 2 * c + p, tr.b);
+                                    tma_load_5d(dst, tm, full, 0, fin + set, tin, plane0 + pbase + p, tr.b);
                                 else
-                                    tma_load_4d(dst, tm, full, 2 * fin, tin, plane0 + 2 * c + p, tr.b);
+                                    tma_load_4d(dst, tm, full, 2 * fin, tin, plane0 + pbase + p, tr.b);
                             }
-                    bulk_load(sa + (uint32_t)g.a_stage, wsrc + (size_t)c * (g.w_stage / 2), (uint32_t)g.w_stage, full);
+                        }
+                    bulk_load(sa + (uint32_t)g.a_stage, wsrc + (size_t)c * g.kper * (g.w_unit / 2), (uint32_t)(nu * g.w_unit), full);
                 }
             }
         }
@@ -312,44 +338,96 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         //   D[:, 0:N]              += A_lo * W_hi             (one MMA of width N)
         // and the epilogue adds the two column halves: 2 MMAs instead of 3, A_hi read once.
         const uint32_t idesc_wide = make_idesc(cw), idesc_n = make_idesc(N);
-        const uint32_t a_lbo = (uint32_t)g.PL, b_lbo = (uint32_t)cw * 16;
         const uint32_t gstep = (uint32_t)(cw * g.nacc);
+        // Descriptor arithmetic is kept to one 32-bit add per operand: the high words (stride offset 128 B,
+        // version) are constants and the low words are (address >> 4) | (leading offset >> 4) << 16, so moving
+        // a descriptor by a multiple of 16 bytes is an add to its low word (addresses stay below 2^18).
+        constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lo0 = (s_stage >> 4) | (((uint32_t)g.PL >> 4) << 16);
+        const uint32_t b_lo0 = ((s_stage + (uint32_t)g.a_stage) >> 4) | ((((uint32_t)cw * 16) >> 4) << 16);
+        uint32_t tapA[kMaxTaps], tapB[kMaxTaps], tapD[kMaxTaps];
+#pragma unroll
+        for (int i = 0; i < kMaxTaps; ++i) {
+            tapA[i] = (uint32_t)(g.aset[i] * g.nsp * g.GS + g.shift[i] * 16) >> 4;
+            tapB[i] = (uint32_t)(i * 2 * cw * 16) >> 4;
+            tapD[i] = (uint32_t)(g.acc[i] * cw);
+        }
+        const uint32_t lo_split = (uint32_t)g.GS >> 4;  // A_lo planes follow the A_hi planes of the same set
+        const uint32_t a_kstep = (uint32_t)(2 * g.PL) >> 4, b_kstep = (uint32_t)g.w_unit >> 4;
         int q = 0, k = 0;
+        int ntr = 0;
         for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++k) {
             const int buf = g.nbuf == 2 ? (k & 1) : 0;
             // the epilogue must have drained this accumulator buffer (use u = k / nbuf of it)
             {
                 const int u = k / g.nbuf;
+                if (lane == 0) trace_ev(a.trace, 1, ntr, 1000);
                 if (u > 0) mbar_wait(bar_tempty + 8 * buf, (u + 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) trace_ev(a.trace, 1, ntr, 1001);
             }
             const uint32_t tbuf = tmem_base + (uint32_t)(buf * buf_cols);
             for (int c = 0; c < g.nchunk; ++c, ++q) {
                 const int s = q % g.nstage;
+                if (lane == 0) trace_ev(a.trace, 1, ntr, 100 + c);
                 mbar_wait(bar_full + 8 * s, (q / g.nstage) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) trace_ev(a.trace, 1, ntr, 200 + c);
                 if (elect_one()) {
-                    const uint32_t abase = s_stage + (uint32_t)(s * g.stage);
-                    const uint32_t bbase = abase + (uint32_t)g.a_stage;
+                    const uint32_t st4 = (uint32_t)(s * g.stage) >> 4;
+                    const int nu = min(g.kper, g.nunit - g.kper * c);
+                    if constexpr (VAR == 0) {
 #pragma unroll 1
-                    for (int i = 0; i < g.ntap; ++i) {
-                        const uint32_t a_hi = abase + (uint32_t)(g.aset[i] * g.nsp * 2 * g.PL) + (uint32_t)(g.shift[i] * 16);
-                        const uint64_t bdesc = make_desc(bbase + (uint32_t)(i * 2 * cw * 16), b_lbo, 128);
-                        const uint32_t acc_flag = (c == 0 && ((g.first_mask >> i) & 1)) ? 0u : 1u;
-                        const uint32_t d0 = tbuf + (uint32_t)g.acc[i] * cw;
-                        uint64_t ad = make_desc(a_hi, a_lbo, 128);
+                        for (int ks = 0; ks < nu; ++ks) {
+                            const uint32_t a_ks = a_lo0 + st4 + (uint32_t)ks * a_kstep;
+                            const uint32_t b_ks = b_lo0 + st4 + (uint32_t)ks * b_kstep;
+                            const bool first_unit = c == 0 && ks == 0;
+#pragma unroll
+                            for (int i = 0; i < kMaxTaps; ++i) {
+                                if (i < g.ntap) {
+                                    const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(b_ks + tapB[i]);
+                                    const uint32_t acc_flag = (first_unit && ((g.first_mask >> i) & 1)) ? 0u : 1u;
+                                    const uint32_t d0 = tbuf + tapD[i];
+                                    const uint32_t alo = a_ks + tapA[i];
 #pragma unroll 4
-                        for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_wide, acc_flag);
-                        if constexpr (SPLIT == 3) {
-                            ad = make_desc(a_hi + (uint32_t)(2 * g.PL), a_lbo, 128);
+                                    for (int gt = 0; gt < g.G; ++gt)
+                                        umma_bf16(d0 + gt * gstep, ((uint64_t)kDescHi << 32) | (uint64_t)(alo + gt * 128), bdesc, idesc_wide, acc_flag);
+                                    if constexpr (SPLIT == 3) {
 #pragma unroll 4
-                            for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_n, 1u);
+                                        for (int gt = 0; gt < g.G; ++gt)
+                                            umma_bf16(d0 + gt * gstep, ((uint64_t)kDescHi << 32) | (uint64_t)(alo + lo_split + gt * 128), bdesc, idesc_n, 1u);
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        const uint32_t abase = s_stage + (uint32_t)(s * g.stage);
+                        const uint32_t bbase = abase + (uint32_t)g.a_stage;
+                        const uint32_t a_lbo = (uint32_t)g.PL, b_lbo = (uint32_t)cw * 16;
+#pragma unroll 1
+                        for (int ks = 0; ks < nu; ++ks) {
+#pragma unroll 1
+                            for (int i = 0; i < g.ntap; ++i) {
+                                const uint32_t a_hi = abase + (uint32_t)(g.aset[i] * g.nsp * g.GS + ks * 2 * g.PL) + (uint32_t)(g.shift[i] * 16);
+                                const uint64_t bdesc = make_desc(bbase + (uint32_t)(ks * g.w_unit) + (uint32_t)(i * 2 * cw * 16), b_lbo, 128);
+                                const uint32_t acc_flag = (c == 0 && ks == 0 && ((g.first_mask >> i) & 1)) ? 0u : 1u;
+                                const uint32_t d0 = tbuf + (uint32_t)g.acc[i] * cw;
+                                uint64_t ad = make_desc(a_hi, a_lbo, 128);
+#pragma unroll 4
+                                for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_wide, acc_flag);
+                                if constexpr (SPLIT == 3) {
+                                    ad = make_desc(a_hi + (uint32_t)g.GS, a_lbo, 128);
+#pragma unroll 4
+                                    for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_n, 1u);
+                                }
+                            }
                         }
                     }
                     umma_commit(bar_empty + 8 * s);
                     if (c == g.nchunk - 1) umma_commit(bar_tfull + 8 * buf);
                 }
                 __syncwarp();
+                if (lane == 0) trace_ev(a.trace, 1, ntr, 300 + c);
             }
         }
     } else {
@@ -359,21 +437,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         const int npix = a.T * a.Fout;
         const bool planes = a.out_layout == LAYOUT_PLANES;
         int prev_b = -1, prev_nt = -1, k = 0;
+        int ntr = 0;
+        const bool tracer = warp == 2 && lane == 0;
         for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++k) {
             const TileRef tr = decode_tile(g, tile);
             const int b = tr.b, t0 = tr.t0, j0 = tr.j0;
+            if (tracer) trace_ev(a.trace, 2, ntr, 1);
             const int buf = g.nbuf == 2 ? (k & 1) : 0;
             if (b != prev_b || tr.nt != prev_nt) {
                 // border-bias table of this (sample, N tile)
+                // border-bias table of this (sample, N tile): add the channel splits of the prep kernel's partial sums,
+                // then expand to the 64 (frame-mask, bin-mask) classes
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
-                const float4 *src = reinterpret_cast<const float4 *>(a.btab + ((size_t)b * g.nNt + tr.nt) * 64 * N);
-                for (int i = et; i < 16 * N; i += kEpiThreads) reinterpret_cast<float4 *>(btab_s)[i] = __ldg(src + i);
+                float *wb = red + 2 * N;  // [9][N] scratch behind the statistics
+                const int ntaps = a.KT * a.KF;
+                const float *src = a.btab + ((size_t)b * g.nNt + tr.nt) * a.nsplit * 9 * N;
+                for (int i = et; i < ntaps * N; i += kEpiThreads) {
+                    float v = 0.f;
+                    for (int sp = 0; sp < a.nsplit; ++sp) v += __ldg(src + (size_t)sp * 9 * N + i);
+                    wb[i] = v;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
+                for (int i = et; i < 64 * N; i += kEpiThreads) {
+                    const int m = i / N, n = i - m * N;
+                    const int tm = m >> 3, fm = m & 7;
+                    const int co = tr.nt * N + n;
+                    float v = (a.bias && co < a.cout) ? __ldg(a.bias + co) : 0.f;
+                    for (int kt = 0; kt < a.KT; ++kt)
+                        for (int kf = 0; kf < a.KF; ++kf)
+                            if (((tm >> kt) & 1) && ((fm >> kf) & 1)) v += wb[(kt * a.KF + kf) * N + n];
+                    btab_s[i] = v;
+                }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
                 prev_b = b;
                 prev_nt = tr.nt;
             }
+            float oscale = 1.f;
+            if (a.gln_sums) {  // gLN rstd of this sample (model.py:628-631); gamma is in the weights, beta / mean in the bias table
+                const double mean = a.gln_sums[(size_t)b * 2] * a.gln_inv_n;
+                double var = a.gln_sums[(size_t)b * 2 + 1] * a.gln_inv_n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                oscale = (float)rsqrt(var + (double)a.gln_eps);
+            }
             mbar_wait(bar_tfull + 8 * buf, (k / g.nbuf) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tracer) trace_ev(a.trace, 2, ntr, 2);
             const uint32_t tbuf = tmem_base + (uint32_t)(buf * buf_cols);
             __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
             float *out_cl = reinterpret_cast<float *>(a.out) + (size_t)b * npix * a.out_ctot + a.out_coff;
@@ -419,16 +527,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         float y[16];
 #pragma unroll
-                        for (int q = 0; q < 16; q += 4) {
-                            const float4 bb = *reinterpret_cast<const float4 *>(bt + q);
-                            y[q] = __uint_as_float(v[q]) + bb.x;
-                            y[q + 1] = __uint_as_float(v[q + 1]) + bb.y;
-                            y[q + 2] = __uint_as_float(v[q + 2]) + bb.z;
-                            y[q + 3] = __uint_as_float(v[q + 3]) + bb.w;
-                        }
+                        for (int q = 0; q < 16; ++q) y[q] = __uint_as_float(v[q]);
                         if constexpr (SPLIT == 3) {
 #pragma unroll
                             for (int q = 0; q < 16; ++q) y[q] += __uint_as_float(v2[q]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 16; q += 4) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(bt + q);
+                            y[q] = fmaf(y[q], oscale, bb.x);
+                            y[q + 1] = fmaf(y[q + 1], oscale, bb.y);
+                            y[q + 2] = fmaf(y[q + 2], oscale, bb.z);
+                            y[q + 3] = fmaf(y[q + 3], oscale, bb.w);
+                        }
+                        if (a.resid && valid) {
+                            const float *rp = a.resid + ((size_t)b * npix + (size_t)t * a.Fout + fo) * a.resid_ctot + a.resid_coff + co_base + cb;
+#pragma unroll
+                            for (int q = 0; q < 16; q += 4) {
+                                if (co_base + cb + q < a.cout) {
+                                    const float4 rr = *reinterpret_cast<const float4 *>(rp + q);
+                                    y[q] += rr.x;
+                                    y[q + 1] += rr.y;
+                                    y[q + 2] += rr.z;
+                                    y[q + 3] += rr.w;
+                                }
+                            }
                         }
                         if (a.elu) {
 #pragma unroll
@@ -465,8 +588,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                             } else {
                                 float *o = out_cl + (size_t)pix * a.out_ctot + co_base + cb;
 #pragma unroll
-                                for (int q = 0; q < 16; ++q)
-                                    if (co_base + cb + q < a.cout) o[q] = y[q];
+                                for (int q = 0; q < 16; q += 4)
+                                    if (co_base + cb + q + 4 <= a.cout) *reinterpret_cast<float4 *>(o + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
                             }
                         }
                     }
@@ -483,6 +606,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
+            if (tracer) trace_ev(a.trace, 2, ntr, 3);
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
             if (a.out_sums) {
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
@@ -497,6 +621,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
             }
+            if (tracer) trace_ev(a.trace, 2, ntr, 4);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -511,25 +636,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 // Per-sample operand preparation: blocks [0, B*nchunk) write the weight images of one (sample, chunk)
 //   wimg[b][nt][chunk][tap][kg][w_hi rows | w_lo rows][8] = bf16 split of W[tap][ci][co] * rstd[b][ci]
 // and blocks [B*nchunk, B*nchunk + B*nNt) write the border-bias tables of one (sample, N tile)
-//   btab[b][nt][tmask*8+fmask][n] = bias[co] + sum_{kt in tmask, kf in fmask} sum_ci W[kt,kf][ci][co] * shift[b][ci]
+//   wbp[b][nt][split][k][n] = sum_{ci in split} W[k][ci][co] * shift[b][ci]   (border-bias partial sums; the conv kernel
+//   expands them to btab[tmask*8+fmask][n] = bias[co] + sum_{kt in tmask, kf in fmask} sum_splits wbp)
 // where x_norm = x * rstd + shift is the consumer-side InstanceNorm affine (model.py:413,430,445).
+// consumer-side normalisation of input channel ci of sample b as an affine (scale, shift)
+__device__ __forceinline__ float2 prep_affine(const PrepArgs &p, int b, int ci) {
+    if (p.norm_mode == NORM_IN) {
+        const double *s = p.in_sums + ((size_t)b * p.in_ctot + p.in_coff + ci) * 2;
+        return affine_from_sums(s[0], s[1], p.norm_inv_n, (double)p.norm_eps);
+    }
+    if (p.norm_mode == NORM_GLN) {
+        // gLN (model.py:609-632): y = gamma (x - mean) rstd + beta with one (mean, rstd) per sample.  rstd is a per-sample
+        // scalar, so the weights carry gamma only (sample independent), the epilogue multiplies the accumulator by rstd,
+        // and the bias term is sum_c W (beta - gamma mean rstd)
+        const double *s = p.in_sums + (size_t)b * 2;
+        const double mean = s[0] * p.norm_inv_n;
+        double var = s[1] * p.norm_inv_n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double r = rsqrt(var + (double)p.norm_eps);
+        const double gm = (double)p.gamma[ci];
+        return make_float2((float)gm, (float)((double)p.beta[ci] - gm * mean * r));
+    }
+    return make_float2(1.f, 0.f);
+}
+
 __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
     extern __shared__ float sh[];
-    const int nimg = p.B * p.nchunk;
+    const int nimg = (p.shared_w ? 1 : p.B) * p.nunit;
     if ((int)blockIdx.x < nimg) {
-        const int b = blockIdx.x / p.nchunk, chunk = blockIdx.x - b * p.nchunk;
+        const int b = blockIdx.x / p.nunit, chunk = blockIdx.x - b * p.nunit;  // chunk = 16-channel K unit
         float *scale = sh;  // [16]
         if (threadIdx.x < 16) {
             const int ci = chunk * 16 + threadIdx.x;
-            float sc = 0.f;
-            if (ci < p.cin) {
-                sc = 1.f;
-                if (p.norm_mode == NORM_IN) {
-                    const double *s = p.in_sums + ((size_t)b * p.in_ctot + p.in_coff + ci) * 2;
-                    sc = affine_from_sums(s[0], s[1], p.norm_inv_n, (double)p.norm_eps).x;
-                }
-            }
-            scale[threadIdx.x] = sc;
+            scale[threadIdx.x] = ci < p.cin ? prep_affine(p, b, ci).x : 0.f;
         }
         __syncthreads();
         const int per_nt = p.ntap * 2 * p.N;  // (tap, kg, n) triples per N tile
@@ -551,7 +690,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
                 l[e] = v - h[e];
             }
             // image of one (sample, N tile, chunk): [tap][kg][nsp * N rows: w_hi rows then w_lo rows][8]
-            __nv_bfloat16 *dst = p.wimg + (((size_t)b * p.nNt + nt) * p.nchunk + chunk) * w_stage +
+            __nv_bfloat16 *dst = p.wimg + (((size_t)b * p.nNt + nt) * p.nunit + chunk) * w_stage +
                                  ((size_t)(tap * 2 + kg) * p.nsp * p.N + n) * 8;
             *reinterpret_cast<uint4 *>(dst) =
                 make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
@@ -560,42 +699,35 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
                     make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
         }
     } else {
-        const int idx = blockIdx.x - nimg;
+        // border-bias partial sums: block (b, nt, split) covers input channels [split*kBiasCi, +kBiasCi) and writes
+        //   wbp[b][nt][split][k][n] = sum_ci W[k][ci][co] * shift[b][ci]
+        // (the conv kernel adds the splits and expands them into the 64 mask classes; many small blocks keep the
+        // weight reads parallel -- a single block per sample is latency bound for the 768-channel bottleneck layers)
+        int idx = blockIdx.x - nimg;
+        const int split = idx % p.nsplit;
+        idx /= p.nsplit;
         const int b = idx / p.nNt, nt = idx - b * p.nNt;
-        float *shift = sh;              // [cin]
-        float *wb = sh + p.cin;         // [9][N]
-        for (int ci = threadIdx.x; ci < p.cin; ci += blockDim.x) {
-            float v = 0.f;
-            if (p.norm_mode == NORM_IN) {
-                const double *s = p.in_sums + ((size_t)b * p.in_ctot + p.in_coff + ci) * 2;
-                v = affine_from_sums(s[0], s[1], p.norm_inv_n, (double)p.norm_eps).y;
-            }
-            shift[ci] = v;
-        }
-        __syncthreads();
+        float *shift = sh;                 // [kBiasCi]
+        float *wb = sh + kBiasCi;          // [ntaps][N]
+        const int ci0 = split * kBiasCi, nci = min(kBiasCi, p.cin - ci0);
         const int ntaps = p.KT * p.KF;
-        for (int i = threadIdx.x; i < ntaps * p.N; i += blockDim.x) {
-            const int k = i / p.N, n = i - k * p.N;
-            const int co = nt * p.N + n;
-            float acc = 0.f;
-            if (co < p.cout) {
-                const float *w = p.w + (size_t)k * p.cin * p.cout_pad + co;
-                for (int ci = 0; ci < p.cin; ++ci) acc = fmaf(w[(size_t)ci * p.cout_pad], shift[ci], acc);
+        for (int i = threadIdx.x; i < nci; i += blockDim.x) shift[i] = prep_affine(p, b, ci0 + i).y;
+        for (int i = threadIdx.x; i < ntaps * p.N; i += blockDim.x) wb[i] = 0.f;
+        __syncthreads();
+        const int n = threadIdx.x % p.N, part = threadIdx.x / p.N, nparts = blockDim.x / p.N;
+        const int co = nt * p.N + n;
+        if (part < nparts && co < p.cout) {
+            for (int k = 0; k < ntaps; ++k) {
+                const float *w = p.w + ((size_t)k * p.cin + ci0) * p.cout_pad + co;
+                float acc = 0.f;
+#pragma unroll 8
+                for (int ci = part; ci < nci; ci += nparts) acc = fmaf(__ldg(w + (size_t)ci * p.cout_pad), shift[ci], acc);
+                atomicAdd(&wb[k * p.N + n], acc);
             }
-            wb[i] = acc;
         }
         __syncthreads();
-        float *dst = p.btab + ((size_t)b * p.nNt + nt) * 64 * p.N;
-        for (int i = threadIdx.x; i < 64 * p.N; i += blockDim.x) {
-            const int m = i / p.N, n = i - m * p.N;
-            const int tm = m >> 3, fm = m & 7;
-            const int co = nt * p.N + n;
-            float v = (p.bias && co < p.cout) ? p.bias[co] : 0.f;
-            for (int kt = 0; kt < p.KT; ++kt)
-                for (int kf = 0; kf < p.KF; ++kf)
-                    if (((tm >> kt) & 1) && ((fm >> kf) & 1)) v += wb[(kt * p.KF + kf) * p.N + n];
-            dst[i] = v;
-        }
+        float *dst = p.btab + (((size_t)b * p.nNt + nt) * p.nsplit + split) * 9 * p.N;
+        for (int i = threadIdx.x; i < ntaps * p.N; i += blockDim.x) dst[i] = wb[i];
     }
 }
 
@@ -620,6 +752,9 @@ EncodeTiledFn get_encode() {
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+long long *g_trace_buf = nullptr;
+int g_trace_cin = 0, g_trace_fin = 0;
+
 // Tiling and shared-memory plan of one launch.  Returns false when the layer does not fit.
 bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
     g = TcGeom{};
@@ -639,7 +774,7 @@ bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
     g.nNt = cout16 / g.N;
     g.ncols = (a.transposed && s2) ? a.Fin + 1 : a.Fout;
     g.nplanes = (a.cin + 7) / 8;
-    g.nchunk = (g.nplanes + 1) / 2;
+    g.nunit = (g.nplanes + 1) / 2;
     // tap table
     const int halo_t = a.KT == 3 ? 1 : 0;
     const int extra_w = a.KF == 1 ? 0 : (s2 ? 1 : 2);
@@ -663,8 +798,9 @@ bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
     const int cw = g.N * g.nsp;  // accumulator columns per (M tile, phase): bf16x3 keeps the w_hi / w_lo halves apart
     g.off_btab = kFixedSmem;
     g.off_red = g.off_btab + 64 * g.N * 4;
-    g.off_stage = round_up(g.off_red + 2 * g.N * 4, 1024);
-    g.w_stage = g.nsp * g.ntap_for(a) * 2 * g.N * 16;
+    g.off_list = round_up(g.off_red + (2 + 9) * g.N * 4, 16);
+    g.off_stage = round_up(g.off_list + kMaxTaps * 8 * 2 * 16, 1024);
+    g.w_unit = g.nsp * g.ntap_for(a) * 2 * g.N * 16;
     auto mma_cost = [](int nw) { return nw <= 128 ? 32.0 + nw / 4.0 : nw / 2.0; };
     const double cyc_mma = split == 3 ? mma_cost(2 * g.N) + mma_cost(g.N) : mma_cost(g.N);
     const int ntap_n = g.ntap_for(a);
@@ -685,29 +821,50 @@ bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
             const int Gmax = std::min(8, 512 / (cw * g.nacc * nbuf));
             if (Gmax < 1) continue;
             const int maxshift = a.KT == 1 ? 0 : 2 * c.Wr + maxshift_k;
-            for (int G = Gmax; G >= 1; --G) {
+            for (int G = Gmax; G >= 1; --G)
+              for (int kper : {1, 2, 4}) {
+                if (kper > 1 && kper > g.nunit) continue;
+                c.kper = kper;
+                c.nchunk = (g.nunit + kper - 1) / kper;
+                c.w_stage = kper * g.w_unit;
                 int TT = std::min({a.T, 128 * G / c.Wr, 254 - 2 * halo_t});
                 if (TT < 1) break;
                 c.t_tiles = (a.T + TT - 1) / TT;
-                TT = (a.T + c.t_tiles - 1) / c.t_tiles;
+                if (c.Wr > 2) TT = (a.T + c.t_tiles - 1) / c.t_tiles;  // balance the tiles (narrow rasters keep full M tiles)
                 c.TT = TT;
                 c.rows = TT + 2 * halo_t;
                 c.G = (TT * c.Wr + 127) / 128;
                 c.nbuf = nbuf;
                 c.box_bytes = c.rows * c.Wr * 16;
-                c.PL = round_up(std::max(c.rows * c.Wr, 128 * c.G + maxshift) * 16, 128);
-                c.a_stage = c.nset * c.nsp * 2 * c.PL;
+                static const int dense_env = getenv("MISO_TC_DENSE") ? atoi(getenv("MISO_TC_DENSE")) : -1;
+                const bool dense = dense_env >= 0 ? dense_env != 0 : kper > 1;
+                if (dense) {  // planes are dense: one TMA box fills all of a stage's planes
+                    c.PL = c.box_bytes;
+                    c.ppb = 2 * kper;
+                } else {      // one box per plane, planes padded so that no descriptor reaches past its plane
+                    c.PL = round_up(std::max(c.rows * c.Wr, 128 * c.G + maxshift) * 16, 128);
+                    c.ppb = 1;
+                }
+                c.GS = round_up(2 * kper * c.PL, 128);
+                c.a_stage = c.nset * c.nsp * c.GS;
                 c.stage = c.a_stage + round_up(c.w_stage, 128);
-                c.nstage = std::min(kMaxStages, (kSmemLimit - c.off_stage) / c.stage);
+                // the last plane's descriptors reach (128 G + maxshift) rows past its start: junk rows only, but mapped memory
+                const int tail = std::max(0, (128 * c.G + maxshift) * 16 - c.PL) + 128;
+                c.nstage = std::min(kMaxStages, (kSmemLimit - c.off_stage - tail) / c.stage);
                 if (c.nstage < 2) continue;
                 c.ntiles = a.B * c.nNt * c.t_tiles * c.f_tiles;
-                const double main_cyc = (double)c.nchunk * ntap_n * c.G * cyc_mma;
-                const double load_cyc = (double)c.nchunk * (c.nset * c.nsp * 2 * c.box_bytes + c.w_stage) / 24.0;  // ~L2 -> SM bytes/clk
+                // a stage costs its MMAs plus a fixed hand-over (barrier round trip, descriptor set-up); loads must keep up
+                const double main_cyc = (double)g.nunit * ntap_n * c.G * cyc_mma + 250.0 * c.nchunk;
+                const double load_cyc = (double)g.nunit * (c.nset * c.nsp * 2 * c.box_bytes + g.w_unit) / 24.0 +
+                                        (c.nstage >= 3 ? 0.0 : 1500.0 * c.nchunk);  // ~L2 -> SM bytes/clk; exposed latency when shallow
                 const double epi_cyc = 0.35 * c.G * 128.0 * c.N * c.nacc + 1500.0;
                 const double body = std::max(main_cyc, load_cyc);
-                const double tile_cyc = nbuf == 2 ? std::max(body, epi_cyc) + 500.0 : body + epi_cyc + 2500.0;
+                const double prod_cyc = 300.0 * c.nchunk * (c.nset * c.nsp + 2);  // one thread issues every TMA of the tile
+                const double body2 = std::max(body, prod_cyc);
+                const double tile_cyc = (nbuf == 2 ? std::max(body2, epi_cyc) + 500.0 : body2 + epi_cyc + 2500.0) + 20.0 * c.nchunk;
                 const int ctas = std::min(c.ntiles, 148);
-                const double total = std::ceil((double)c.ntiles / ctas) * tile_cyc + 6000.0;
+                // fewer than 3 stages exposes the load latency: only when nothing deeper fits
+                const double total = std::ceil((double)c.ntiles / ctas) * tile_cyc + 6000.0 + (c.nstage < 3 ? 1e12 : 0.0);
                 if (total < best) {
                     best = total;
                     bg = c;
@@ -759,7 +916,11 @@ bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
         g.f_org = -1;
         g.f_mul = 1;
     }
-    g.smem_total = g.off_stage + g.nstage * g.stage;
+    {
+        int maxshift = 0;
+        for (int i = 0; i < g.ntap; ++i) maxshift = std::max(maxshift, g.shift[i]);
+        g.smem_total = g.off_stage + g.nstage * g.stage + std::max(0, (128 * g.G + maxshift) * 16 - g.PL) + 128;
+    }
     int cols = 32;
     while (cols < g.nbuf * g.G * g.nacc * cw) cols <<= 1;
     g.tmem_cols = cols;
@@ -772,7 +933,9 @@ int encode_maps(const ConvArgs &a, const TcGeom &g, CUtensorMap *hi, CUtensorMap
         set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver");
         return MISO_E_CUDA;
     }
-    const uint64_t CG = (uint64_t)a.in_ctot / 8, T = (uint64_t)a.T, F = (uint64_t)a.Fin;
+    // the plane dimension ends with the view ([in_coff, in_coff + cin)): planes past it are zero-filled, never read
+    const uint64_t CG = (uint64_t)a.in_ctot / 8, CGv = (uint64_t)(a.in_coff + a.cin + 7) / 8, T = (uint64_t)a.T, F = (uint64_t)a.Fin;
+    const cuuint32_t ppb = (cuuint32_t)g.ppb;
     char *base = const_cast<char *>(reinterpret_cast<const char *>(a.in));
     for (int sp = 0; sp < 2; ++sp) {
         CUtensorMap *tm = sp == 0 ? hi : lo;
@@ -780,17 +943,17 @@ int encode_maps(const ConvArgs &a, const TcGeom &g, CUtensorMap *hi, CUtensorMap
         CUresult r;
         if (!g.strided) {
             // [2F (8-byte units)][T][CG][B]: a tile row is one contiguous run of Wr * 16 bytes
-            cuuint64_t dims[4] = {2 * F, T, CG, (cuuint64_t)a.B};
+            cuuint64_t dims[4] = {2 * F, T, CGv, (cuuint64_t)a.B};
             cuuint64_t strides[3] = {F * 16, T * F * 16, 2 * CG * T * F * 16};
-            cuuint32_t box[4] = {(cuuint32_t)(2 * g.Wr), (cuuint32_t)g.rows, 1, 1};
+            cuuint32_t box[4] = {(cuuint32_t)(2 * g.Wr), (cuuint32_t)g.rows, ppb, 1};
             cuuint32_t es[4] = {1, 1, 1, 1};
             r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, addr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         } else {
             // [8 ch][F][T][CG][B] with element stride 2 along F: the even / odd bins of a tile
-            cuuint64_t dims[5] = {8, F, T, CG, (cuuint64_t)a.B};
+            cuuint64_t dims[5] = {8, F, T, CGv, (cuuint64_t)a.B};
             cuuint64_t strides[4] = {16, F * 16, T * F * 16, 2 * CG * T * F * 16};
-            cuuint32_t box[5] = {8, (cuuint32_t)(2 * g.Wr), (cuuint32_t)g.rows, 1, 1};
+            cuuint32_t box[5] = {8, (cuuint32_t)(2 * g.Wr), (cuuint32_t)g.rows, ppb, 1};
             cuuint32_t es[5] = {1, 2, 1, 1, 1};
             r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, addr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -806,12 +969,20 @@ int encode_maps(const ConvArgs &a, const TcGeom &g, CUtensorMap *hi, CUtensorMap
 
 }  // namespace
 
+void conv_tc_set_trace(long long *d_buf, int cin, int fin) {
+    g_trace_buf = d_buf;
+    g_trace_cin = cin;
+    g_trace_fin = fin;
+}
+
 // one-time, capture-unsafe setup (function attributes, driver entry point); called before graph capture
 int conv_tc_init() {
     static bool done = false;
     if (done) return MISO_OK;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
     if (!get_encode()) {
         set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -828,7 +999,8 @@ bool conv_tc_eligible(const ConvArgs &a) {
     if (a.stride_f == 2 && a.pad_f != 0) return false;
     if (a.in_layout != LAYOUT_PLANES || a.in_ctot % 8 || a.in_coff % 8) return false;
     if (a.out_layout == LAYOUT_PLANES && (a.out_ctot % 8 || a.out_coff % 8 || a.cout % 8)) return false;
-    if (a.resid != nullptr || a.norm_mode == NORM_GLN) return false;
+    if (a.out_layout == LAYOUT_CL_F32 && (a.cout % 4 || a.out_ctot % 4 || a.out_coff % 4)) return false;
+    if (a.resid && (a.resid_ctot % 4 || a.resid_coff % 4)) return false;
     TcGeom g;
     return make_geom(a, 3, g);
 }
@@ -837,15 +1009,16 @@ void conv_tc_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size
     TcGeom g;
     *wimg_bytes = *btab_bytes = 0;
     if (!make_geom(a, split, g)) return;
-    *wimg_bytes = (size_t)a.B * g.nNt * g.nchunk * g.w_stage;
-    *btab_bytes = (size_t)a.B * g.nNt * 64 * g.N * sizeof(float);
+    *wimg_bytes = (size_t)a.B * g.nNt * g.nunit * g.w_unit;
+    *btab_bytes = (size_t)a.B * g.nNt * ((a.cin + kBiasCi - 1) / kBiasCi) * 9 * g.N * sizeof(float);
 }
 
 int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream) {
     MISO_REQUIRE(split == 1 || split == 3, "conv_tc: bad split");
     TcGeom g;
     MISO_REQUIRE(make_geom(a, split, g), "conv_tc: layer does not fit the tcgen05 path (cin=%d cout=%d Fin=%d)", a.cin, a.cout, a.Fin);
-    const size_t need_w = (size_t)a.B * g.nNt * g.nchunk * g.w_stage, need_b = (size_t)a.B * g.nNt * 64 * g.N * sizeof(float);
+    const bool shared_w = a.norm_mode == NORM_GLN;
+    const size_t need_w = (size_t)(shared_w ? 1 : a.B) * g.nNt * g.nunit * g.w_unit, need_b = (size_t)a.B * g.nNt * ((a.cin + kBiasCi - 1) / kBiasCi) * 9 * g.N * sizeof(float);
     if (need_w > scratch.wimg_bytes || need_b > scratch.btab_bytes) {
         set_error("conv_tc: scratch too small (%zu/%zu weight bytes, %zu/%zu bias bytes)", scratch.wimg_bytes, need_w,
                   scratch.btab_bytes, need_b);
@@ -854,9 +1027,9 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
     if (debug)
         fprintf(stderr,
-                "conv_tc: cin=%d cout=%d Fin=%d Fout=%d s=%d tr=%d | N=%d nNt=%d TF=%d Wr=%d TT=%d G=%d nbuf=%d nstage=%d stage=%dB "
+                "conv_tc: cin=%d cout=%d Fin=%d Fout=%d s=%d tr=%d | N=%d nNt=%d TF=%d Wr=%d TT=%d G=%d nbuf=%d kper=%d nstage=%d stage=%dB "
                 "tiles=%d (t%d x f%d) tmem=%d smem=%d\n",
-                a.cin, a.cout, a.Fin, a.Fout, a.stride_f, a.transposed, g.N, g.nNt, g.TF, g.Wr, g.TT, g.G, g.nbuf, g.nstage, g.stage,
+                a.cin, a.cout, a.Fin, a.Fout, a.stride_f, a.transposed, g.N, g.nNt, g.TF, g.Wr, g.TT, g.G, g.nbuf, g.kper, g.nstage, g.stage,
                 g.ntiles, g.t_tiles, g.f_tiles, g.tmem_cols, g.smem_total);
     CUtensorMap tm_hi, tm_lo;
     int rc = encode_maps(a, g, &tm_hi, &tm_lo);
@@ -866,6 +1039,8 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.w = a.w;
     p.bias = a.bias;
     p.in_sums = a.in_sums;
+    p.gamma = a.gamma;
+    p.beta = a.beta;
     p.in_ctot = a.in_ctot;
     p.in_coff = a.in_coff;
     p.cin = a.cin;
@@ -879,21 +1054,25 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.B = a.B;
     p.N = g.N;
     p.nNt = g.nNt;
-    p.nchunk = g.nchunk;
+    p.nunit = g.nunit;
+    p.shared_w = shared_w ? 1 : 0;
+    p.nsplit = (a.cin + kBiasCi - 1) / kBiasCi;
     p.nsp = g.nsp;
     p.ntap = g.ntap;
     p.KT = a.KT;
     p.KF = a.KF;
     for (int i = 0; i < g.ntap; ++i) p.tapk[i] = g.tapk[i];
-    const size_t prep_smem = std::max<size_t>(64, (size_t)(a.cin + 9 * g.N) * sizeof(float));
+    const size_t prep_smem = (size_t)(kBiasCi + 9 * g.N) * sizeof(float);
     prof_begin(stream);
-    conv_tc_prep_kernel<<<a.B * g.nchunk + a.B * g.nNt, 256, prep_smem, stream>>>(p);
+    conv_tc_prep_kernel<<<(shared_w ? 1 : a.B) * g.nunit + a.B * g.nNt * p.nsplit, 256, prep_smem, stream>>>(p);
     MISO_LAUNCHED("conv_tc_prep_kernel");
 
     TcArgs k{};
     k.g = g;
     k.wimg = p.wimg;
     k.btab = p.btab;
+    k.bias = a.bias;
+    k.nsplit = p.nsplit;
     k.out = a.out;
     k.out_sums = a.out_sums;
     k.B = a.B;
@@ -914,14 +1093,30 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     k.pad_f = a.pad_f;
     k.transposed = a.transposed;
     k.elu = a.elu;
+    k.wimg_bstride = shared_w ? 0 : (size_t)g.nNt * g.nunit * (g.w_unit / 2);
+    k.gln_sums = shared_w ? a.in_sums : nullptr;
+    k.gln_inv_n = a.norm_inv_n;
+    k.gln_eps = a.norm_eps;
+    k.resid = a.resid;
+    k.resid_ctot = a.resid_ctot;
+    k.resid_coff = a.resid_coff;
+    k.trace = (g_trace_buf && a.cin == g_trace_cin && a.Fin == g_trace_fin) ? g_trace_buf : nullptr;
 
     rc = conv_tc_init();
     if (rc) return rc;
     dim3 grid(std::min(g.ntiles, 148), 1, 1);  // persistent: one CTA per SM walks the tile list
-    if (split == 3)
-        conv_tc_kernel<3><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
-    else
-        conv_tc_kernel<1><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+    static const int var = getenv("MISO_TC_VAR") ? atoi(getenv("MISO_TC_VAR")) : 0;
+    if (split == 3) {
+        if (var == 0)
+            conv_tc_kernel<3, 0><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+        else
+            conv_tc_kernel<3, 1><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+    } else {
+        if (var == 0)
+            conv_tc_kernel<1, 0><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+        else
+            conv_tc_kernel<1, 1><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+    }
     {
         const double pix = (double)a.B * a.T * (a.transposed ? a.Fin : a.Fout);
         const double flops = 2.0 * pix * a.cin * a.cout * a.KT * a.KF;

@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(128) tcn_prep_kernel(const __nv_bfloat16 *__re
 __global__ void __launch_bounds__(128) tcn_dw_kernel(const float *__restrict__ U, const double *__restrict__ u_sums,
                                                      double inv_n, float eps, const float *__restrict__ wdw,
                                                      const float *__restrict__ alpha, float *__restrict__ P,
-                                                     double *__restrict__ g_sums, int T, int C, int dil) {
+                                                     double *__restrict__ g_sums, int T, int C, int dil, int out_planes,
+                                                     int use_lo) {
     const int c = blockIdx.y * 128 + threadIdx.x;
     const int b = blockIdx.z;
     float s = 0.f, q = 0.f;
@@ -108,7 +109,15 @@ __global__ void __launch_bounds__(128) tcn_dw_kernel(const float *__restrict__ U
             if (t + dil < T) vp = elu1(fmaf(ub[(size_t)(t + dil) * C], af.x, af.y));
             float y = fmaf(w0, vm, fmaf(w1, v0, w2 * vp));
             y = y > 0.f ? y : al * y;
-            P[((size_t)b * T + t) * C + c] = y;
+            if (out_planes) {
+                // bf16 planes [b][hi|lo][C/8][T][8]: the A operand layout of the tensor-core pointwise conv
+                __nv_bfloat16 *pp = reinterpret_cast<__nv_bfloat16 *>(P) + (size_t)b * 2 * C * T + ((size_t)(c >> 3) * T + t) * 8 + (c & 7);
+                const __nv_bfloat16 h = __float2bfloat16_rn(y);
+                *pp = h;
+                if (use_lo) pp[(size_t)C * T] = __float2bfloat16_rn(y - __bfloat162float(h));
+            } else {
+                P[((size_t)b * T + t) * C + c] = y;
+            }
             s += y;
             q += y * y;
         }
@@ -609,14 +618,16 @@ int Walker::run(const void *d_x, float *d_y) {
     }
 
     // ---------------- TCN (model.py:486-567) ----------------
-    if (!dry) {
+    {
         const BufDesc &d0 = pl.D[0];
         const double inv_T = 1.0 / (double)T;
         const int use_lo = n->mode == 2 ? 0 : 1;
         dim3 grid(ceil_div(T, kTcnTile), ceil_div(C, 128), B);
-        tcn_prep_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(d0.p), d0.ctot, C, use_lo, d0.sums, inv_T,
-                                              kInEps, pl.S, pl.sS[0], T, C);
-        MISO_LAUNCHED("tcn_prep_kernel");
+        if (!dry) {
+            tcn_prep_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(d0.p), d0.ctot, C, use_lo, d0.sums,
+                                                  inv_T, kInEps, pl.S, pl.sS[0], T, C);
+            MISO_LAUNCHED("tcn_prep_kernel");
+        }
         const int nblk = n->R * n->X;
         const int bn = conv_fp32_tile_n(C);
         const int cpad = (C + bn - 1) / bn * bn;
@@ -627,12 +638,16 @@ int Walker::run(const void *d_x, float *d_y) {
                 const float *u = half == 0 ? pl.S : pl.U;
                 const double *us = half == 0 ? pl.sS[k] : pl.sU[k];
                 double *gs = half == 0 ? pl.g1[k] : pl.g2[k];
-                tcn_dw_kernel<<<grid, 128, 0, st>>>(u, us, inv_T, kInEps, n->params[h.dw].d, n->params[h.alpha].d, pl.P, gs, T, C,
-                                                    dil);
-                MISO_LAUNCHED("tcn_dw_kernel");
+                const bool tc_pw = (dry || n->mode != 0) && C % 8 == 0;
+                if (!dry) {
+                    tcn_dw_kernel<<<grid, 128, 0, st>>>(u, us, inv_T, kInEps, n->params[h.dw].d, n->params[h.alpha].d, pl.P, gs, T,
+                                                        C, dil, tc_pw ? 1 : 0, use_lo);
+                    MISO_LAUNCHED("tcn_dw_kernel");
+                }
                 ConvArgs a{};
                 a.in = pl.P;
-                a.in_layout = LAYOUT_CL_F32;
+                a.in_layout = tc_pw ? LAYOUT_PLANES : LAYOUT_CL_F32;
+                a.in_lo_off = (size_t)C * T * 2;
                 a.out_layout = LAYOUT_CL_F32;
                 a.use_lo = use_lo;
                 a.w = n->params[h.pw].d;
@@ -683,7 +698,19 @@ int Walker::run(const void *d_x, float *d_y) {
                         a.out_sums = nullptr;
                     }
                 }
-                rc = launch_conv_fp32(a, st);
+                if (dry) {
+                    if (conv_tc_eligible(a)) {
+                        size_t w, bt;
+                        conv_tc_scratch_need(a, 3, &w, &bt);
+                        need_w = std::max(need_w, w);
+                        need_b = std::max(need_b, bt);
+                    }
+                    continue;
+                }
+                if (tc_pw && conv_tc_eligible(a))
+                    rc = launch_conv_tc(a, n->mode == 1 ? 3 : 1, pl.scratch, st);
+                else
+                    rc = launch_conv_fp32(a, st);  // reads either layout
                 if (rc) return rc;
             }
         }
@@ -978,6 +1005,11 @@ int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T,
         return MISO_OK;
     }
     return enqueue_forward(net, pl, d_x, d_y, B, T, F, st);
+}
+
+int miso_debug_tc_trace(long long *d_buf, int cin, int fin) {
+    conv_tc_set_trace(d_buf, cin, fin);
+    return MISO_OK;
 }
 
 int miso_net_set_graph(miso_net_t *net, int on) {

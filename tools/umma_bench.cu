@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(128, 1) bench(Cfg c, long long *out) {
         if (tid < 32) {
             const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + 128 * 1024);
             const uint32_t idesc = make_idesc(c.N);
-            const uint64_t a0 = c.mode == 0 ? make_desc(sA + c.shift, 32768, 128, 0, 0) : make_desc(sA + c.shift, 16, 1024, 2, ((sA + c.shift) >> 7) & 7);
+            const uint64_t a0 = c.mode == 0 ? make_desc(sA + c.shift, c.same_a > 1 ? c.same_a : 32768, 128, 0, 0) : make_desc(sA + c.shift, 16, 1024, 2, ((sA + c.shift) >> 7) & 7);
             const uint64_t b0 = c.mode == 0 ? make_desc(sB, c.N * 16, 128, 0, 0) : make_desc(sB, 16, 1024, 2, 0);
-            const uint32_t astep = c.same_a ? 0u : (c.mode == 0 ? 128u : 1024u);  // (bytes >> 4) per M tile
+            const uint32_t astep = c.same_a == 1 ? 0u : (c.mode == 0 ? 128u : 1024u);  // (bytes >> 4) per M tile
             const uint32_t ncols = c.N;
             for (int rep = 0; rep < 2; ++rep) {
                 long long t0 = clock64();
@@ -142,6 +142,13 @@ int main() {
         const char *name;
         Cfg c;
     } cases[] = {
+        {"N=32  noswz LBO=9216       ", {32, 0, 0, 8, 512, 9216, 0}},
+        {"N=32  noswz LBO=9248       ", {32, 0, 0, 8, 512, 9248, 0}},
+        {"N=32  noswz LBO=9280       ", {32, 0, 0, 8, 512, 9280, 0}},
+        {"N=64  noswz LBO=9248       ", {64, 0, 0, 8, 512, 9248, 0}},
+        {"N=128 noswz LBO=4160       ", {128, 0, 0, 2, 512, 4160, 0}},
+        {"N=128 noswz LBO=4352       ", {128, 0, 0, 2, 512, 4352, 0}},
+        {"N=128 noswz LBO=4160 sh16  ", {128, 0, 16, 2, 512, 4160, 0}},
         {"N=32  noswz aligned        ", {32, 0, 0, 8, 512, 0, 0}},
         {"N=32  noswz shift16        ", {32, 0, 16, 8, 512, 0, 0}},
         {"N=32  noswz shift1056      ", {32, 0, 1056, 8, 512, 0, 0}},
