@@ -290,6 +290,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // contiguous tile range per CTA: consecutive tiles share the sample (weight image, bias table) and their halos in L2
+    const int tiles_per_cta = (g.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile_lo = (int)blockIdx.x * tiles_per_cta, tile_hi = min(tile_lo + tiles_per_cta, g.ntiles);
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
@@ -297,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             const int plane0 = a.in_coff >> 3;
             int q = 0;  // running chunk index over all tiles of this CTA
             int ntr = 0;
-            for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+            for (int tile = tile_lo; tile < tile_hi; ++tile) {
                 const TileRef tr = decode_tile(g, tile);
                 const int tin = tr.t0 + g.t_org;
                 const int fin = tr.j0 * g.f_mul + g.f_org;
@@ -356,7 +359,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         const uint32_t a_kstep = (uint32_t)(2 * g.PL) >> 4, b_kstep = (uint32_t)g.w_unit >> 4;
         int q = 0, k = 0;
         int ntr = 0;
-        for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++k) {
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++k) {
             const int buf = g.nbuf == 2 ? (k & 1) : 0;
             // the epilogue must have drained this accumulator buffer (use u = k / nbuf of it)
             {
@@ -439,7 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         int prev_b = -1, prev_nt = -1, k = 0;
         int ntr = 0;
         const bool tracer = warp == 2 && lane == 0;
-        for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++k) {
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++k) {
             const TileRef tr = decode_tile(g, tile);
             const int b = tr.b, t0 = tr.t0, j0 = tr.j0;
             if (tracer) trace_ev(a.trace, 2, ntr, 1);
