@@ -34,7 +34,9 @@
 namespace miso {
 namespace {
 
-constexpr int kThreads = 320;       // 10 warps: TMA, MMA, 8 epilogue
+constexpr int kMmaWarps = 4;        // MMA issuers: warp w owns the M tiles gt = w, w + 4, ... (disjoint accumulators)
+constexpr int kEpiWarp0 = 1 + kMmaWarps;
+constexpr int kThreads = (1 + kMmaWarps + 8) * 32;  // 13 warps: TMA, 4 x MMA, 8 epilogue
 constexpr int kEpiThreads = 256;
 constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 4;
@@ -268,10 +270,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     if (tid == 0) {
         for (int s = 0; s < g.nstage; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, kMmaWarps);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tfull + 8 * i, kMmaWarps);
             mbar_init(bar_tempty + 8 * i, kEpiThreads / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -334,8 +336,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
+    } else if (warp <= kMmaWarps) {
+        // ---------------------------------------------------------------- MMA issuers
+        // One thread issues an MMA in tens of cycles but pays hundreds per tap for descriptor set-up and the tensor
+        // pipe does not run ahead of its issuer, so the M tiles are split over kMmaWarps issuing warps (disjoint
+        // accumulators: no ordering between them is needed); every warp waits for / commits to the same barriers.
+        const int mw = warp - 1;
         // SPLIT == 3: the weight image of a tap is [kg][2N rows: w_hi then w_lo][8], so
         //   D[:, 0:N] , D[:, N:2N] += A_hi * [W_hi | W_lo]   (one MMA of width 2N)
         //   D[:, 0:N]              += A_lo * W_hi             (one MMA of width N)
@@ -364,18 +370,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             // the epilogue must have drained this accumulator buffer (use u = k / nbuf of it)
             {
                 const int u = k / g.nbuf;
-                if (lane == 0) trace_ev(a.trace, 1, ntr, 1000);
+                if (warp == 1 && lane == 0) trace_ev(a.trace, 1, ntr, 1000);
                 if (u > 0) mbar_wait(bar_tempty + 8 * buf, (u + 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) trace_ev(a.trace, 1, ntr, 1001);
+                if (warp == 1 && lane == 0) trace_ev(a.trace, 1, ntr, 1001);
             }
             const uint32_t tbuf = tmem_base + (uint32_t)(buf * buf_cols);
             for (int c = 0; c < g.nchunk; ++c, ++q) {
                 const int s = q % g.nstage;
-                if (lane == 0) trace_ev(a.trace, 1, ntr, 100 + c);
+                if (warp == 1 && lane == 0) trace_ev(a.trace, 1, ntr, 100 + c);
                 mbar_wait(bar_full + 8 * s, (q / g.nstage) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) trace_ev(a.trace, 1, ntr, 200 + c);
+                if (warp == 1 && lane == 0) trace_ev(a.trace, 1, ntr, 200 + c);
                 if (elect_one()) {
                     const uint32_t st4 = (uint32_t)(s * g.stage) >> 4;
                     const int nu = min(g.kper, g.nunit - g.kper * c);
@@ -392,12 +398,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                     const uint32_t acc_flag = (first_unit && ((g.first_mask >> i) & 1)) ? 0u : 1u;
                                     const uint32_t d0 = tbuf + tapD[i];
                                     const uint32_t alo = a_ks + tapA[i];
-#pragma unroll 4
-                                    for (int gt = 0; gt < g.G; ++gt)
+#pragma unroll 2
+                                    for (int gt = mw; gt < g.G; gt += kMmaWarps)
                                         umma_bf16(d0 + gt * gstep, ((uint64_t)kDescHi << 32) | (uint64_t)(alo + gt * 128), bdesc, idesc_wide, acc_flag);
                                     if constexpr (SPLIT == 3) {
-#pragma unroll 4
-                                        for (int gt = 0; gt < g.G; ++gt)
+#pragma unroll 2
+                                        for (int gt = mw; gt < g.G; gt += kMmaWarps)
                                             umma_bf16(d0 + gt * gstep, ((uint64_t)kDescHi << 32) | (uint64_t)(alo + lo_split + gt * 128), bdesc, idesc_n, 1u);
                                     }
                                 }
@@ -416,12 +422,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                 const uint32_t acc_flag = (c == 0 && ks == 0 && ((g.first_mask >> i) & 1)) ? 0u : 1u;
                                 const uint32_t d0 = tbuf + (uint32_t)g.acc[i] * cw;
                                 uint64_t ad = make_desc(a_hi, a_lbo, 128);
-#pragma unroll 4
-                                for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_wide, acc_flag);
+#pragma unroll 2
+                                for (int gt = mw; gt < g.G; gt += kMmaWarps) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_wide, acc_flag);
                                 if constexpr (SPLIT == 3) {
                                     ad = make_desc(a_hi + (uint32_t)g.GS, a_lbo, 128);
-#pragma unroll 4
-                                    for (int gt = 0; gt < g.G; ++gt) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_n, 1u);
+#pragma unroll 2
+                                    for (int gt = mw; gt < g.G; gt += kMmaWarps) umma_bf16(d0 + gt * gstep, ad + (uint64_t)(gt * 128), bdesc, idesc_n, 1u);
                                 }
                             }
                         }
@@ -430,18 +436,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                     if (c == g.nchunk - 1) umma_commit(bar_tfull + 8 * buf);
                 }
                 __syncwarp();
-                if (lane == 0) trace_ev(a.trace, 1, ntr, 300 + c);
+                if (warp == 1 && lane == 0) trace_ev(a.trace, 1, ntr, 300 + c);
             }
         }
     } else {
         // ---------------------------------------------------------------- epilogue (warps 2..9)
-        const int quad = warp & 3, half = (warp - 2) >> 2;
-        const int et = tid - 64;
+        const int quad = warp & 3, half = (warp - kEpiWarp0) >> 2;
+        const int et = tid - kEpiWarp0 * 32;
         const int npix = a.T * a.Fout;
         const bool planes = a.out_layout == LAYOUT_PLANES;
         int prev_b = -1, prev_nt = -1, k = 0;
         int ntr = 0;
-        const bool tracer = warp == 2 && lane == 0;
+        const bool tracer = warp == kEpiWarp0 && lane == 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++k) {
             const TileRef tr = decode_tile(g, tile);
             const int b = tr.b, t0 = tr.t0, j0 = tr.j0;
