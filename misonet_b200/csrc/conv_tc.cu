@@ -65,6 +65,7 @@ struct TcGeom {
     int tmem_cols;
     int strided;               // 5-D bf16 tensor map with element stride 2 along bins
     int ppb;                   // planes per TMA box: 2*kper (dense planes, one box per stage) or 1 (padded planes)
+    unsigned wr_magic;         // ceil(2^32 / Wr): R / Wr == __umulhi(R, wr_magic) for the raster rows of a tile
     int ntap_for(const ConvArgs &a) const { return a.KT * a.KF; }
 };
 
@@ -501,7 +502,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
                 for (int gt = half; gt < g.G; gt += 2) {
                     const int R = gt * 128 + quad * 32 + lane;
-                    const int tt = R / g.Wr;
+                    const int tt = g.Wr == 1 ? R : (int)__umulhi((unsigned)R, g.wr_magic);
                     const int jl = R - tt * g.Wr;
                     const int t = t0 + tt, j = j0 + jl;
                     const bool rowok = tt < g.TT && t < a.T && jl < g.TF;
@@ -520,8 +521,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                             bool ok;
                             if (a.transposed) {
                                 const int num = fo + a.pad_f - kf;
-                                const int fi = num / a.stride_f;
-                                ok = num >= 0 && fi * a.stride_f == num && fi < a.Fin;
+                                const int fi = num >> (a.stride_f - 1);  // stride_f is 1 or 2
+                                ok = num >= 0 && (fi << (a.stride_f - 1)) == num && fi < a.Fin;
                             } else {
                                 const int fi = fo * a.stride_f + kf - a.pad_f;
                                 ok = fi >= 0 && fi < a.Fin;
@@ -533,7 +534,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                         const uint32_t taddr = tbuf + ((uint32_t)(quad * 32) << 16) + (uint32_t)((gt * g.nacc + ph) * cw + cb);
                         tmem_ld16(taddr, v);
                         if constexpr (SPLIT == 3) tmem_ld16(taddr + (uint32_t)N, v2);
+                        if (tracer) trace_ev(a.trace, 2, ntr, 10);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (tracer) trace_ev(a.trace, 2, ntr, 11);
                         float y[16];
 #pragma unroll
                         for (int q = 0; q < 16; ++q) y[q] = __uint_as_float(v[q]);
@@ -566,6 +569,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 #pragma unroll
                             for (int q = 0; q < 16; ++q) y[q] = elu_fast(y[q]);
                         }
+                        if (tracer) trace_ev(a.trace, 2, ntr, 12);
                         if (valid) {
 #pragma unroll
                             for (int q = 0; q < 16; ++q) {
@@ -603,6 +607,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                         }
                     }
                 }
+                if (tracer) trace_ev(a.trace, 2, ntr, 13);
                 if (a.out_sums) {
                     const float s = warp_reduce16(ssum, lane);
                     const float q2 = warp_reduce16(ssq, lane);
@@ -928,7 +933,8 @@ bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
     {
         int maxshift = 0;
         for (int i = 0; i < g.ntap; ++i) maxshift = std::max(maxshift, g.shift[i]);
-        g.smem_total = g.off_stage + g.nstage * g.stage + std::max(0, (128 * g.G + maxshift) * 16 - g.PL) + 128;
+        g.wr_magic = (unsigned)((0x100000000ull + (unsigned)g.Wr - 1) / (unsigned)g.Wr);
+    g.smem_total = g.off_stage + g.nstage * g.stage + std::max(0, (128 * g.G + maxshift) * 16 - g.PL) + 128;
     }
     int cols = 32;
     while (cols < g.nbuf * g.G * g.nacc * cw) cols <<= 1;

@@ -86,43 +86,75 @@ __global__ void __launch_bounds__(128) tcn_prep_kernel(const __nv_bfloat16 *__re
 // First half of DepthwiseSeparableConv fused with the block's norm/activation prologue
 // (model.py:530-531 / 538-539 then 556-558): v = ELU(IN1d(u)); y = dwconv_k3_dil(v);
 // p = PReLU(y); accumulates the gLN statistics of p over (C,T) per sample.
-__global__ void __launch_bounds__(128) tcn_dw_kernel(const float *__restrict__ U, const double *__restrict__ u_sums,
+// One block = one sample x kDwFrames frames x all channels; a thread handles 4 consecutive channels of a frame
+// with float4 loads of the three taps (coalesced along c) and writes 8-byte bf16 hi / lo plane quads.
+constexpr int kDwFrames = 8;
+__global__ void __launch_bounds__(256) tcn_dw_kernel(const float *__restrict__ U, const double *__restrict__ u_sums,
                                                      double inv_n, float eps, const float *__restrict__ wdw,
                                                      const float *__restrict__ alpha, float *__restrict__ P,
                                                      double *__restrict__ g_sums, int T, int C, int dil, int out_planes,
                                                      int use_lo) {
-    const int c = blockIdx.y * 128 + threadIdx.x;
-    const int b = blockIdx.z;
-    float s = 0.f, q = 0.f;
-    if (c < C) {
+    extern __shared__ float dw_sh[];  // [C] scale, [C] shift, [3][C] taps
+    float *sc = dw_sh, *sf = dw_sh + C, *wt = dw_sh + 2 * C;
+    const int b = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double *us = u_sums + ((size_t)b * C + c) * 2;
         const float2 af = affine_from_sums(us[0], us[1], inv_n, (double)eps);
-        const float w0 = wdw[c * 3 + 0], w1 = wdw[c * 3 + 1], w2 = wdw[c * 3 + 2];
-        const float al = alpha[0];
-        const int t0 = blockIdx.x * kTcnTile;
-        const int t1 = min(T, t0 + kTcnTile);
-        const float *ub = U + (size_t)b * T * C + c;
-        for (int t = t0; t < t1; ++t) {
-            float vm = 0.f, vp = 0.f;
-            float v0 = elu1(fmaf(ub[(size_t)t * C], af.x, af.y));
-            if (t - dil >= 0) vm = elu1(fmaf(ub[(size_t)(t - dil) * C], af.x, af.y));
-            if (t + dil < T) vp = elu1(fmaf(ub[(size_t)(t + dil) * C], af.x, af.y));
-            float y = fmaf(w0, vm, fmaf(w1, v0, w2 * vp));
-            y = y > 0.f ? y : al * y;
-            if (out_planes) {
-                // bf16 planes [b][hi|lo][C/8][T][8]: the A operand layout of the tensor-core pointwise conv
-                __nv_bfloat16 *pp = reinterpret_cast<__nv_bfloat16 *>(P) + (size_t)b * 2 * C * T + ((size_t)(c >> 3) * T + t) * 8 + (c & 7);
-                const __nv_bfloat16 h = __float2bfloat16_rn(y);
-                *pp = h;
-                if (use_lo) pp[(size_t)C * T] = __float2bfloat16_rn(y - __bfloat162float(h));
-            } else {
-                P[((size_t)b * T + t) * C + c] = y;
+        sc[c] = af.x;
+        sf[c] = af.y;
+        wt[c] = wdw[c * 3 + 0];
+        wt[C + c] = wdw[c * 3 + 1];
+        wt[2 * C + c] = wdw[c * 3 + 2];
+    }
+    __syncthreads();
+    const float al = alpha[0];
+    const int t0 = blockIdx.x * kDwFrames;
+    const int c4n = C >> 2;
+    const float *ub = U + (size_t)b * T * C;
+    float s = 0.f, q = 0.f;
+    for (int i = threadIdx.x; i < kDwFrames * c4n; i += blockDim.x) {
+        const int tt = i / c4n, c = (i - tt * c4n) * 4;
+        const int t = t0 + tt;
+        if (t >= T) break;
+        const float4 a4 = *reinterpret_cast<const float4 *>(sc + c), b4 = *reinterpret_cast<const float4 *>(sf + c);
+        auto act = [&](int tq) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tq >= 0 && tq < T) {
+                const float4 u = __ldg(reinterpret_cast<const float4 *>(ub + (size_t)tq * C + c));
+                v.x = elu1(fmaf(u.x, a4.x, b4.x));
+                v.y = elu1(fmaf(u.y, a4.y, b4.y));
+                v.z = elu1(fmaf(u.z, a4.z, b4.z));
+                v.w = elu1(fmaf(u.w, a4.w, b4.w));
             }
-            s += y;
-            q += y * y;
+            return v;
+        };
+        const float4 vm = act(t - dil), v0 = act(t), vp = act(t + dil);
+        const float4 w0 = *reinterpret_cast<const float4 *>(wt + c), w1 = *reinterpret_cast<const float4 *>(wt + C + c),
+                     w2 = *reinterpret_cast<const float4 *>(wt + 2 * C + c);
+        float y[4];
+        y[0] = fmaf(w0.x, vm.x, fmaf(w1.x, v0.x, w2.x * vp.x));
+        y[1] = fmaf(w0.y, vm.y, fmaf(w1.y, v0.y, w2.y * vp.y));
+        y[2] = fmaf(w0.z, vm.z, fmaf(w1.z, v0.z, w2.z * vp.z));
+        y[3] = fmaf(w0.w, vm.w, fmaf(w1.w, v0.w, w2.w * vp.w));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            y[k] = y[k] > 0.f ? y[k] : al * y[k];
+            s += y[k];
+            q = fmaf(y[k], y[k], q);
+        }
+        if (out_planes) {
+            // bf16 planes [b][hi|lo][C/8][T][8]: the A operand layout of the tensor-core pointwise conv
+            __nv_bfloat16 *pp = reinterpret_cast<__nv_bfloat16 *>(P) + (size_t)b * 2 * C * T + ((size_t)(c >> 3) * T + t) * 8 + (c & 7);
+            const uint32_t h0 = pack_bf16x2(y[0], y[1]), h1 = pack_bf16x2(y[2], y[3]);
+            *reinterpret_cast<uint2 *>(pp) = make_uint2(h0, h1);
+            if (use_lo)
+                *reinterpret_cast<uint2 *>(pp + (size_t)C * T) =
+                    make_uint2(pack_bf16x2(y[0] - bf16_lo(h0), y[1] - bf16_hi(h0)), pack_bf16x2(y[2] - bf16_lo(h1), y[3] - bf16_hi(h1)));
+        } else {
+            *reinterpret_cast<float4 *>(P + ((size_t)b * T + t) * C + c) = make_float4(y[0], y[1], y[2], y[3]);
         }
     }
-    __shared__ float red[2][4];
+    __shared__ float red[2][8];
     s = warp_sum(s);
     q = warp_sum(q);
     if ((threadIdx.x & 31) == 0) {
@@ -131,8 +163,11 @@ __global__ void __launch_bounds__(128) tcn_dw_kernel(const float *__restrict__ U
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double ds = (double)red[0][0] + red[0][1] + red[0][2] + red[0][3];
-        double dq = (double)red[1][0] + red[1][1] + red[1][2] + red[1][3];
+        double ds = 0.0, dq = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            ds += (double)red[0][w];
+            dq += (double)red[1][w];
+        }
         atomicAdd(g_sums + (size_t)b * 2, ds);
         atomicAdd(g_sums + (size_t)b * 2 + 1, dq);
     }
@@ -640,8 +675,8 @@ int Walker::run(const void *d_x, float *d_y) {
                 double *gs = half == 0 ? pl.g1[k] : pl.g2[k];
                 const bool tc_pw = (dry || n->mode != 0) && C % 8 == 0;
                 if (!dry) {
-                    tcn_dw_kernel<<<grid, 128, 0, st>>>(u, us, inv_T, kInEps, n->params[h.dw].d, n->params[h.alpha].d, pl.P, gs, T,
-                                                        C, dil, tc_pw ? 1 : 0, use_lo);
+                    tcn_dw_kernel<<<dim3(ceil_div(T, kDwFrames), B), 256, 5 * C * sizeof(float), st>>>(
+                        u, us, inv_T, kInEps, n->params[h.dw].d, n->params[h.alpha].d, pl.P, gs, T, C, dil, tc_pw ? 1 : 0, use_lo);
                     MISO_LAUNCHED("tcn_dw_kernel");
                 }
                 ConvArgs a{};
