@@ -219,19 +219,46 @@ def run_ours(args, wl, rank, world, local):
         torch.cuda.synchronize()
         lib.miso_prof_enable(0)
 
-        # ---- end to end through the public API: pinned host in -> H2D -> step -> D2H ----
-        for _ in range(1):
-            host_out.copy_(step(host_in.to(dev, non_blocking=True)), non_blocking=True)
+        # ---- end to end through the public API: every step copies its input from pinned host memory (H2D) and
+        # its result back (D2H) inside the timed region.  Copies run on a second stream and overlap the previous /
+        # next step's compute through two device input buffers, as a streaming caller would do. ----
+        copy_s = torch.cuda.Stream(device=dev)      # H2D
+        back_s = torch.cuda.Stream(device=dev)      # D2H (its own stream, or it would serialise behind the next H2D)
+        main_s = torch.cuda.current_stream(dev)
+        dev_bufs = [torch.empty_like(dev_in) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_loop(nsteps):
+            for i in range(nsteps):
+                k = i & 1
+                with torch.cuda.stream(copy_s):
+                    if i >= 2:
+                        copy_s.wait_event(ev_free[k])          # step i-2 finished reading this buffer
+                    dev_bufs[k].copy_(host_in, non_blocking=True)
+                    ev_in[k].record(copy_s)
+                main_s.wait_event(ev_in[k])
+                out_i = step(dev_bufs[k])
+                ev_free[k].record(main_s)
+                out_i.record_stream(back_s)
+                with torch.cuda.stream(back_s):
+                    back_s.wait_event(ev_free[k])
+                    host_out.copy_(out_i, non_blocking=True)
+            copy_s.synchronize()
+            back_s.synchronize()
+
+        e2e_loop(2)
         torch.cuda.synchronize()
         D.barrier()
         torch.cuda.synchronize()
+        t0 = time.perf_counter()
         e0.record()
-        for _ in range(args.steps):
-            host_out.copy_(step(host_in.to(dev, non_blocking=True)), non_blocking=True)
+        e2e_loop(args.steps)
         e1.record()
         torch.cuda.synchronize()
+        ms_e2e_wall = (time.perf_counter() - t0) * 1e3
         D.barrier()
-        ms_e2e = e0.elapsed_time(e1)
+        ms_e2e = max(e0.elapsed_time(e1), ms_e2e_wall)   # the D2H tail runs on the copy stream: take the host clock too
 
     ms = D.max_over_ranks(ms, dev)
     ms_e2e = D.max_over_ranks(ms_e2e, dev)
@@ -242,6 +269,14 @@ def run_ours(args, wl, rank, world, local):
     dom = max(fams, key=lambda k: fams[k]["ms"])
     conv_ms, conv_flops, conv_launches = fams[dom]["ms"], fams[dom]["flops"], fams[dom]["launches"]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_b_ncu_traffic_conv_tc_bf16x3.json")
+    if args.workload == "miso1_paper" and args.conv_mode == "bf16x3" and args.batch == 0 and dom.startswith("conv_tc") and os.path.isfile(tp):
+        try:
+            traffic = float(json.load(open(tp))["family_dram_bytes_per_launch"])
+            traffic_src = "profiles/r1_b_ncu_traffic_conv_tc_bf16x3.json (dram__bytes_read.sum + dram__bytes_write.sum of this workload's conv_tc + prep launches, per conv launch)"
+        except Exception:
+            pass
     fam_report = {k: {"ms_per_step": v["ms"] / args.steps, "share_of_step": v["ms"] / ms if ms > 0 else None,
                       "launches_per_step": v["launches"] // max(args.steps, 1),
                       "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0,
@@ -266,7 +301,8 @@ def run_ours(args, wl, rank, world, local):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom,
                      "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+                     "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": fams[dom]["bytes"] / max(conv_launches, 1), "peak_source": pk["source"],
                      "launches": int(conv_launches), "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms if ms > 0 else None,
                      "families": fam_report,

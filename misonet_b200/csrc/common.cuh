@@ -74,9 +74,22 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 
-// Statistics convention: every activation channel owns two fp64 accumulators
-// (sum, sum of squares).  A negative sum-of-squares marks a channel that is consumed
-// raw (no normalisation in the reference at that point).
+// Statistics convention: every activation channel owns two 64-bit accumulators (sum, sum of squares) in
+// FIXED POINT (value * 2^20 as int64): integer atomics make the totals independent of the order in which
+// CTAs arrive, so a forward is bitwise reproducible (fp64 atomics are not: a last-bit difference in a sum
+// occasionally flips the bf16 rounding of an activation downstream).  The buffers are declared double*
+// for historical reasons and only touched through stat_add / stat_get / stat_set.  A negative
+// sum-of-squares marks a channel that is consumed raw (no normalisation in the reference at that point).
+constexpr double kStatScale = 1048576.0;
+__device__ __forceinline__ void stat_add(double *p, double v) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)__double2ll_rn(v * kStatScale));
+}
+__device__ __forceinline__ double stat_get(const double *p) {
+    return (double)(*reinterpret_cast<const long long *>(p)) * (1.0 / kStatScale);
+}
+__device__ __forceinline__ void stat_set(double *p, double v) {
+    *reinterpret_cast<long long *>(p) = __double2ll_rn(v * kStatScale);
+}
 __device__ __forceinline__ float2 affine_from_sums(double s, double q, double inv_n, double eps) {
     if (q < 0.0) return make_float2(1.f, 0.f);
     double mean = s * inv_n;

@@ -39,11 +39,11 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(const ConvArgs a) {
         float2 v = make_float2(1.f, 0.f);
         if (a.norm_mode == NORM_IN) {
             const double *s = a.in_sums + ((size_t)b * a.in_ctot + a.in_coff + c) * 2;
-            v = affine_from_sums(s[0], s[1], a.norm_inv_n, (double)a.norm_eps);
+            v = affine_from_sums(stat_get(s), stat_get(s + 1), a.norm_inv_n, (double)a.norm_eps);
         } else if (a.norm_mode == NORM_GLN) {
             const double *s = a.in_sums + (size_t)b * 2;
-            double mean = s[0] * a.norm_inv_n;
-            double var = s[1] * a.norm_inv_n - mean * mean;
+            double mean = stat_get(s) * a.norm_inv_n;
+            double var = stat_get(s + 1) * a.norm_inv_n - mean * mean;
             if (var < 0.0) var = 0.0;
             double r = rsqrt(var + (double)a.norm_eps);
             double g = (double)a.gamma[c];
@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(const ConvArgs a) {
                 q += (double)red[(r * BN + tid) * 2 + 1];
             }
             double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + n0 + tid) * 2;
-            atomicAdd(dst, s);
-            atomicAdd(dst + 1, q);
+            stat_add(dst, s);
+            stat_add(dst + 1, q);
         }
     }
 }

@@ -286,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
     {
         // statistics scratch
-        for (int i = tid; i < 2 * N; i += kThreads) red[i] = 0.f;
+        for (int i = tid; i < 8 * 2 * N; i += kThreads) red[i] = 0.f;  // one slot per epilogue warp: fixed summation order
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -459,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 // border-bias table of this (sample, N tile): add the channel splits of the prep kernel's partial sums,
                 // then expand to the 64 (frame-mask, bin-mask) classes
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
-                float *wb = red + 2 * N;  // [9][N] scratch behind the statistics
+                float *wb = red + 16 * N;  // [9][N] scratch behind the statistics
                 const int ntaps = a.KT * a.KF;
                 const float *src = a.btab + ((size_t)b * g.nNt + tr.nt) * a.nsplit * 9 * N;
                 for (int i = et; i < ntaps * N; i += kEpiThreads) {
@@ -484,8 +484,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             }
             float oscale = 1.f;
             if (a.gln_sums) {  // gLN rstd of this sample (model.py:628-631); gamma is in the weights, beta / mean in the bias table
-                const double mean = a.gln_sums[(size_t)b * 2] * a.gln_inv_n;
-                double var = a.gln_sums[(size_t)b * 2 + 1] * a.gln_inv_n - mean * mean;
+                const double mean = stat_get(a.gln_sums + (size_t)b * 2) * a.gln_inv_n;
+                double var = stat_get(a.gln_sums + (size_t)b * 2 + 1) * a.gln_inv_n - mean * mean;
                 if (var < 0.0) var = 0.0;
                 oscale = (float)rsqrt(var + (double)a.gln_eps);
             }
@@ -612,8 +612,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                     const float s = warp_reduce16(ssum, lane);
                     const float q2 = warp_reduce16(ssq, lane);
                     if ((lane & 1) == 0) {
-                        atomicAdd(&red[(cb + (lane >> 1)) * 2], s);
-                        atomicAdd(&red[(cb + (lane >> 1)) * 2 + 1], q2);
+                        float *slot = red + (warp - kEpiWarp0) * 2 * N;  // this warp's own slot: no atomics, no ordering
+                        slot[(cb + (lane >> 1)) * 2] = s;
+                        slot[(cb + (lane >> 1)) * 2 + 1] = q2;
                     }
                 }
             }
@@ -627,11 +628,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 if (et < N) {
                     if (co_base + et < a.cout) {
                         double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + co_base + et) * 2;
-                        atomicAdd(dst, (double)red[et * 2]);
-                        atomicAdd(dst + 1, (double)red[et * 2 + 1]);
+                        double s8 = 0.0, q8 = 0.0;
+#pragma unroll
+                        for (int w8 = 0; w8 < 8; ++w8) {
+                            s8 += (double)red[w8 * 2 * N + et * 2];
+                            q8 += (double)red[w8 * 2 * N + et * 2 + 1];
+                        }
+                        stat_add(dst, s8);
+                        stat_add(dst + 1, q8);
                     }
-                    red[et * 2] = 0.f;
-                    red[et * 2 + 1] = 0.f;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
             }
@@ -657,15 +662,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 __device__ __forceinline__ float2 prep_affine(const PrepArgs &p, int b, int ci) {
     if (p.norm_mode == NORM_IN) {
         const double *s = p.in_sums + ((size_t)b * p.in_ctot + p.in_coff + ci) * 2;
-        return affine_from_sums(s[0], s[1], p.norm_inv_n, (double)p.norm_eps);
+        return affine_from_sums(stat_get(s), stat_get(s + 1), p.norm_inv_n, (double)p.norm_eps);
     }
     if (p.norm_mode == NORM_GLN) {
         // gLN (model.py:609-632): y = gamma (x - mean) rstd + beta with one (mean, rstd) per sample.  rstd is a per-sample
         // scalar, so the weights carry gamma only (sample independent), the epilogue multiplies the accumulator by rstd,
         // and the bias term is sum_c W (beta - gamma mean rstd)
         const double *s = p.in_sums + (size_t)b * 2;
-        const double mean = s[0] * p.norm_inv_n;
-        double var = s[1] * p.norm_inv_n - mean * mean;
+        const double mean = stat_get(s) * p.norm_inv_n;
+        double var = stat_get(s + 1) * p.norm_inv_n - mean * mean;
         if (var < 0.0) var = 0.0;
         const double r = rsqrt(var + (double)p.norm_eps);
         const double gm = (double)p.gamma[ci];
@@ -722,13 +727,13 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
         idx /= p.nsplit;
         const int b = idx / p.nNt, nt = idx - b * p.nNt;
         float *shift = sh;                 // [kBiasCi]
-        float *wb = sh + kBiasCi;          // [ntaps][N]
+        float *wb = sh + kBiasCi;          // [nparts <= 8][ntaps][N]: one slot per channel part, summed in a fixed order
         const int ci0 = split * kBiasCi, nci = min(kBiasCi, p.cin - ci0);
         const int ntaps = p.KT * p.KF;
         for (int i = threadIdx.x; i < nci; i += blockDim.x) shift[i] = prep_affine(p, b, ci0 + i).y;
-        for (int i = threadIdx.x; i < ntaps * p.N; i += blockDim.x) wb[i] = 0.f;
+        const int n = threadIdx.x % p.N, part = threadIdx.x / p.N, nparts = min(8, (int)blockDim.x / p.N);
+        for (int i = threadIdx.x; i < nparts * ntaps * p.N; i += blockDim.x) wb[i] = 0.f;
         __syncthreads();
-        const int n = threadIdx.x % p.N, part = threadIdx.x / p.N, nparts = blockDim.x / p.N;
         const int co = nt * p.N + n;
         if (part < nparts && co < p.cout) {
             for (int k = 0; k < ntaps; ++k) {
@@ -736,12 +741,16 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
                 float acc = 0.f;
 #pragma unroll 8
                 for (int ci = part; ci < nci; ci += nparts) acc = fmaf(__ldg(w + (size_t)ci * p.cout_pad), shift[ci], acc);
-                atomicAdd(&wb[k * p.N + n], acc);
+                wb[(part * ntaps + k) * p.N + n] = acc;
             }
         }
         __syncthreads();
         float *dst = p.btab + (((size_t)b * p.nNt + nt) * p.nsplit + split) * 9 * p.N;
-        for (int i = threadIdx.x; i < ntaps * p.N; i += blockDim.x) dst[i] = wb[i];
+        for (int i = threadIdx.x; i < ntaps * p.N; i += blockDim.x) {
+            float v = 0.f;
+            for (int q = 0; q < nparts; ++q) v += wb[q * ntaps * p.N + i];
+            dst[i] = v;
+        }
     }
 }
 
@@ -812,7 +821,7 @@ bool make_geom(const ConvArgs &a, int split, TcGeom &g) {
     const int cw = g.N * g.nsp;  // accumulator columns per (M tile, phase): bf16x3 keeps the w_hi / w_lo halves apart
     g.off_btab = kFixedSmem;
     g.off_red = g.off_btab + 64 * g.N * 4;
-    g.off_list = round_up(g.off_red + (2 + 9) * g.N * 4, 16);
+    g.off_list = round_up(g.off_red + (16 + 9) * g.N * 4, 16);
     g.off_stage = round_up(g.off_list + kMaxTaps * 8 * 2 * 16, 1024);
     g.w_unit = g.nsp * g.ntap_for(a) * 2 * g.N * 16;
     auto mma_cost = [](int nw) { return nw <= 128 ? 32.0 + nw / 4.0 : nw / 2.0; };
@@ -1077,7 +1086,7 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.KT = a.KT;
     p.KF = a.KF;
     for (int i = 0; i < g.ntap; ++i) p.tapk[i] = g.tapk[i];
-    const size_t prep_smem = (size_t)(kBiasCi + 9 * g.N) * sizeof(float);
+    const size_t prep_smem = (size_t)(kBiasCi + 8 * 9 * g.N) * sizeof(float);
     prof_begin(stream);
     conv_tc_prep_kernel<<<(shared_w ? 1 : a.B) * g.nunit + a.B * g.nNt * p.nsplit, 256, prep_smem, stream>>>(p);
     MISO_LAUNCHED("conv_tc_prep_kernel");

@@ -50,7 +50,7 @@ __global__ void sentinel_kernel(double *sums, int B, int ctot, int coff, int n) 
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * n) {
         int b = i / n, c = i - b * n;
-        sums[((size_t)b * ctot + coff + c) * 2 + 1] = -1.0;
+        stat_set(sums + ((size_t)b * ctot + coff + c) * 2 + 1, -1.0);
     }
 }
 
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) tcn_prep_kernel(const __nv_bfloat16 *__re
     const int b = blockIdx.z;
     if (c >= C) return;
     const double *rs = raw_sums + ((size_t)b * raw_ctot + raw_coff + c) * 2;
-    const float2 af = affine_from_sums(rs[0], rs[1], inv_n, (double)eps);
+    const float2 af = affine_from_sums(stat_get(rs), stat_get(rs + 1), inv_n, (double)eps);
     const int t0 = blockIdx.x * kTcnTile;
     const int t1 = min(T, t0 + kTcnTile);
     float s = 0.f, q = 0.f;
@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(128) tcn_prep_kernel(const __nv_bfloat16 *__re
         s += x;
         q += x * x;
     }
-    atomicAdd(s_sums + ((size_t)b * C + c) * 2, (double)s);
-    atomicAdd(s_sums + ((size_t)b * C + c) * 2 + 1, (double)q);
+    stat_add(s_sums + ((size_t)b * C + c) * 2, (double)s);
+    stat_add(s_sums + ((size_t)b * C + c) * 2 + 1, (double)q);
 }
 
 // First half of DepthwiseSeparableConv fused with the block's norm/activation prologue
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) tcn_dw_kernel(const float *__restrict__ U
     const int b = blockIdx.y;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double *us = u_sums + ((size_t)b * C + c) * 2;
-        const float2 af = affine_from_sums(us[0], us[1], inv_n, (double)eps);
+        const float2 af = affine_from_sums(stat_get(us), stat_get(us + 1), inv_n, (double)eps);
         sc[c] = af.x;
         sf[c] = af.y;
         wt[c] = wdw[c * 3 + 0];
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(256) tcn_dw_kernel(const float *__restrict__ U
             ds += (double)red[0][w];
             dq += (double)red[1][w];
         }
-        atomicAdd(g_sums + (size_t)b * 2, ds);
-        atomicAdd(g_sums + (size_t)b * 2 + 1, dq);
+        stat_add(g_sums + (size_t)b * 2, ds);
+        stat_add(g_sums + (size_t)b * 2 + 1, dq);
     }
 }
 
@@ -281,7 +281,7 @@ __global__ void tap_kernel(const __nv_bfloat16 *__restrict__ buf, int ctot, int 
         float2 af = make_float2(1.f, 0.f);
         if (sums) {
             const double *s = sums + ((size_t)b * ctot + coff + c) * 2;
-            af = affine_from_sums(s[0], s[1], inv_n, (double)eps);
+            af = affine_from_sums(stat_get(s), stat_get(s + 1), inv_n, (double)eps);
         }
         const int ca = coff + c;
         const size_t e = (size_t)b * 2 * ctot * TF + ((size_t)(ca >> 3) * TF + p) * 8 + (ca & 7);

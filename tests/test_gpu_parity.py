@@ -155,6 +155,33 @@ def test_net_tensor_core_decisions_match_fp32():
     assert torch.equal(p0, p1)
 
 
+def test_net_graph_replay_and_weight_update():
+    """The forward is replayed as a CUDA graph (include/misonet_b200.h, miso_net_set_graph): replays must be
+    bit-identical to the eager launches, and a parameter update must show up without re-capturing."""
+    from misonet_b200 import synth
+    from oracle import miso_net_torch as mnt
+    m, cfg, sd = _model("miso1", 0)
+    m.conv_mode = "bf16x3"
+    mix = torch.from_numpy(synth.random_spec(21, (2, 6, 24, 129))).cuda()
+    with torch.no_grad():
+        m.use_graph = False
+        y_eager = m(mix).clone()
+        m.use_graph = True
+        y_cap = m(mix).clone()          # captures
+        y_rep = m(mix).clone()          # replays
+        # same kernels, same arguments, order-independent (integer) statistics atomics: bitwise reproducible
+        assert torch.equal(y_eager, y_cap) and torch.equal(y_eager, y_rep)
+        # in-place weight change: same graph, new weights
+        key = "encoders.0.0.conv2d.weight"
+        sd2 = {k: v.clone() for k, v in sd.items()}
+        sd2[key] = sd2[key] * 1.5
+        m.load_state_dict(sd2)
+        y_new = m(mix)
+        ref = mnt.miso1_forward(sd2, cfg, mix.cpu()).numpy()
+        assert rel_err(y_new.cpu().numpy(), ref) < 2e-4
+        assert rel_err(y_new.cpu().numpy(), y_rep.cpu().numpy()) > 1e-3
+
+
 def test_net_paper_layout_vs_oracle():
     """8-block / 257-bin / 384-wide-TCN layout (model.py:13-14,30 comments) against the oracle."""
     from misonet_b200 import synth
@@ -181,6 +208,14 @@ def test_net_batch_invariance_and_chunking():
         y_chunk = m(mix)
     assert rel_err(y_one.cpu().numpy(), y_all.cpu().numpy()) < 1e-6
     assert rel_err(y_chunk.cpu().numpy(), y_all.cpu().numpy()) < 1e-6
+    # the same on the tensor-core path (the tiling, hence the fp32 grouping of the per-CTA statistics partial sums,
+    # may depend on the batch size: equal to rounding, not necessarily bitwise)
+    m.max_workspace_bytes = 48 << 30
+    m.conv_mode = "bf16x3"
+    with torch.no_grad():
+        z_all = m(mix)
+        z_one = torch.cat([m(mix[i:i + 1]) for i in range(3)])
+    assert rel_err(z_one.cpu().numpy(), z_all.cpu().numpy()) < 2e-5
 
 
 def test_net_bad_shape_is_a_clear_error():
