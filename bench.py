@@ -31,6 +31,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...") and debug output go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 LAYOUTS = {
     "REF": ([24, 32, 32, 32, 32, 64, 128], [128, 64, 32, 32, 32, 32, 24]),
