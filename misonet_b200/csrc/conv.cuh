@@ -67,6 +67,12 @@ bool conv_tc_eligible(const ConvArgs &a);
 void conv_tc_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size_t *btab_bytes);
 int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream);
 
+// row-streaming variant with the frame taps merged into N (conv_rs.cu): stride-1 pad-(1,1) 3x3 convs at F+1 = 128 / 256
+int conv_rs_init();
+bool conv_rs_eligible(const ConvArgs &a, int split);
+void conv_rs_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size_t *btab_bytes);
+int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream);
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);

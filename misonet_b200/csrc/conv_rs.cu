@@ -1,0 +1,703 @@
+// Row-streaming tcgen05 3x3 convolution with the three FRAME taps merged into the MMA N dimension -- the
+// DenseBlock convs of the MISO conv stack (model.py:437-482: 3x3, stride 1, pad (1,1); 94 % of the FLOPs of
+// MISO_1/MISO_3) at the two widest stages (F + 1 = 128 or 256 bins).
+//
+// Why.  An SS-mode tcgen05.mma (M = 128, K = 16) costs 32 + N/4 cycles for N <= 128: the 128 x 16 A tile is read
+// from shared memory at 128 B/clk (tools/umma_bench.cu), so with N = cout = 24..32 the tensor pipe idles 60 % of
+// the time (conv_tc.cu).  Here one MMA computes, for one input frame row r and one bin tap kf,
+//     E[r, (kt, co)] = sum_ci X[r, f + kf - 1, ci] * W[kt, kf, ci, co]        N = 3 * cout
+// i.e. the contribution of input row r to the THREE output rows r + 1 - kt at once: the A tile is read once per
+// 3 taps (56 cycles per 96 columns instead of 3 x 40.8), and since out[t] = sum_kt E[t + kt - 1, kt] uses the
+// same TMEM lane (bin) of three different input rows, the sum over kt is free: the accumulator of output row t
+// is one Nc-column TMEM slot, slots of consecutive output rows are adjacent ([kt=2 | kt=1 | kt=0] weight order),
+// and the MMA of input row r simply lands on the slots of rows r-1, r, r+1.  A CTA streams down the frames of
+// its strip: every input row is loaded ONCE (no frame halo re-reads) and multiplied once.
+//
+// TMEM is a ring of L logical slots (+ 2 extension slots so that an MMA never wraps: an MMA that starts in slot
+// L-2 / L-1 spills into slots L, L+1, which the epilogue adds to slots 0, 1).  A slot's first write of a round
+// uses accumulate = 0 (the freshly started output row is issued as its own narrow MMA once per row), so the
+// epilogue never has to clear tensor memory.  Tiles of G input rows: the epilogue of tile k (output rows that
+// became complete) overlaps the MMAs of tile k + 1; 2G + 2 <= L.
+//
+// Layout in shared memory per stage (kper 16-channel K units): A planes [hi|lo][unit][kg][row][pitch px][8 ch]
+// by one TMA box per plane set, then the per-sample weight image of the units (conv_rs_prep_kernel):
+// [unit][kf][hi|lo][kg][3 Nc rows][8 ch].  F + 1 = 128: rows are stored at a pitch of 128 pixels starting at
+// bin -1 (TMA zero fill); the right padding of row r IS the left padding of row r + 1 (shared-pad raster).
+// F + 1 = 256: two column regions of 128 bins, rows at a pitch of 130 pixels (5-D bf16 tensor map).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "conv.cuh"
+#include "umma.cuh"
+
+namespace miso {
+namespace {
+
+constexpr int kRsThreads = 10 * 32;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int kRsEpi0 = 2;
+constexpr int kRsEpiThreads = 256;
+constexpr int kRsMaxG = 8;
+constexpr int kRsMaxStages = 4;
+constexpr int kRsSmemLimit = 227 * 1024;
+constexpr int kRsFixed = 1024;
+constexpr int kRsBiasCi = 64;
+
+struct RsGeom {
+    int Nc, N3, L, G, Mr, pitch, PL, GS, nsp;
+    int nplanes, nunit, kper, nchunk;
+    int w_unit, w_off, stage, nstage, box_bytes;
+    int off_btab, off_red, off_stage, smem_total, tmem_cols;
+    int map5d;
+};
+
+struct RsArgs {
+    RsGeom g;
+    const __nv_bfloat16 *wimg;  // [B][nunit][kf][hi|lo][kg][N3][8]
+    size_t wimg_bstride;        // elements per sample
+    const float *btab;          // border-bias partial sums [B][nsplit][9][Nc]
+    const float *bias;
+    int nsplit;
+    void *out;
+    double *out_sums;
+    int B, T, F;
+    int in_coff;
+    int out_ctot, out_coff, cout;
+    size_t out_lo_off;
+    int use_lo, elu;
+};
+
+struct RsPrepArgs {
+    const float *w;  // packed fp32 [9][cin][cout_pad]
+    const double *in_sums;
+    int in_ctot, in_coff, cin, cout, cout_pad;
+    int norm_mode;
+    float norm_eps;
+    double norm_inv_n;
+    __nv_bfloat16 *wimg;
+    float *btab;
+    int B, Nc, nunit, nsp, nsplit;
+};
+
+// the strips of one CTA: its share [rho, rho_end) of the flattened (sample, column region, frame) row space, cut
+// at (sample, region) boundaries
+struct RsWalk {
+    int rho, rho_end, T, Mr;
+    int b, m, t0, TS, nin;
+    __device__ __forceinline__ bool next() {
+        if (rho >= rho_end) return false;
+        const int unit = rho / T;
+        t0 = rho - unit * T;
+        TS = min(T - t0, rho_end - rho);
+        b = unit / Mr;
+        m = unit - b * Mr;
+        nin = TS + 2;  // input rows j = 0 .. TS+1 <-> frames t0-1 .. t0+TS
+        rho += TS;
+        return true;
+    }
+};
+__device__ __forceinline__ RsWalk rs_walk(const RsArgs &a) {
+    RsWalk w;
+    const long long R = (long long)a.B * a.g.Mr * a.T;
+    w.rho = (int)(R * blockIdx.x / gridDim.x);
+    w.rho_end = (int)(R * (blockIdx.x + 1) / gridDim.x);
+    w.T = a.T;
+    w.Mr = a.g.Mr;
+    return w;
+}
+
+__device__ __forceinline__ float rs_elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+
+template <int SPLIT>
+__global__ void __launch_bounds__(kRsThreads, 1)
+conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const RsArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const RsGeom &g = a.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Nc = g.Nc, L = g.L, G = g.G;
+    constexpr int NPROD = SPLIT == 3 ? 3 : 1;
+
+    const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 64);
+    const uint32_t bar_tfull = smem_u32(smem + 128), bar_tempty = smem_u32(smem + 144);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 160);
+    float *btab_s = reinterpret_cast<float *>(smem + g.off_btab);
+    float *red = reinterpret_cast<float *>(smem + g.off_red);
+    const uint32_t s_stage = smem_u32(smem + g.off_stage);
+
+    if (tid == 0) {
+        for (int s = 0; s < g.nstage; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, kRsEpiThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        for (int i = tid; i < 8 * 2 * Nc; i += kRsThreads) red[i] = 0.f;
+        // zero guard behind the A planes of every stage (shared-pad raster: the pixel after the last row)
+        for (int i = tid; i < g.nstage * 32; i += kRsThreads)
+            reinterpret_cast<uint32_t *>(smem + g.off_stage + (i >> 5) * g.stage + g.w_off - 128)[i & 31] = 0u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (elect_one()) {
+            const int plane0 = a.in_coff >> 3;
+            int q = 0;
+            RsWalk w = rs_walk(a);
+            while (w.next()) {
+                const __nv_bfloat16 *wsrc = a.wimg + (size_t)w.b * a.wimg_bstride;
+                const int f0 = 128 * w.m - 1;
+                for (int j0 = 0; j0 < w.nin; j0 += G) {
+                    const int tin = w.t0 - 1 + j0;
+                    for (int c = 0; c < g.nchunk; ++c, ++q) {
+                        const int s = q % g.nstage;
+                        if (q >= g.nstage) mbar_wait(bar_empty + 8 * s, ((q / g.nstage) + 1) & 1);
+                        const int nu = min(g.kper, g.nunit - g.kper * c);
+                        const uint32_t full = bar_full + 8 * s;
+                        mbar_expect_tx(full, (uint32_t)(g.nsp * g.box_bytes + nu * g.w_unit));
+                        const uint32_t sa = s_stage + (uint32_t)(s * g.stage);
+                        const int pl = plane0 + 2 * g.kper * c;
+                        for (int sp = 0; sp < g.nsp; ++sp) {
+                            const CUtensorMap *tm = sp == 0 ? &tm_hi : &tm_lo;
+                            const uint32_t dst = sa + (uint32_t)(sp * g.GS);
+                            if (g.map5d)
+                                tma_load_5d(dst, tm, full, 0, f0, tin, pl, w.b);
+                            else
+                                tma_load_4d(dst, tm, full, 2 * f0, tin, pl, w.b);
+                        }
+                        bulk_load(sa + (uint32_t)g.w_off, wsrc + (size_t)c * g.kper * (g.w_unit / 2), (uint32_t)(nu * g.w_unit), full);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        const uint32_t idesc0 = make_idesc(0);
+        auto idesc_of = [&](int ngroups) { return idesc0 | ((uint32_t)((ngroups * Nc) >> 3) << 17); };
+        constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // stride offset 128 B between 8-row groups, version 1
+        const uint32_t a_lo0 = (s_stage >> 4) | (((uint32_t)g.PL >> 4) << 16);
+        const uint32_t b_lo0 = ((s_stage + (uint32_t)g.w_off) >> 4) | ((uint32_t)g.N3 << 16);  // leading offset N3 * 16 B
+        const uint32_t lo_split = (uint32_t)g.GS >> 4;
+        const uint32_t a_kstep = (uint32_t)(2 * g.PL) >> 4, b_kstep = (uint32_t)g.w_unit >> 4;
+        const uint32_t b_kfstep = (uint32_t)(g.nsp * 2 * g.N3), b_spstep = (uint32_t)(2 * g.N3);
+        const uint32_t row_step = (uint32_t)g.pitch;
+        int q = 0, k = 0, Jbase = 2;
+        RsWalk w = rs_walk(a);
+        while (w.next()) {
+            for (int j0 = 0; j0 < w.nin; j0 += G, ++k) {
+                const int Gk = min(G, w.nin - j0);
+                if (k >= 2) {  // the epilogue of tile k - 2 has drained the slots this tile reuses
+                    mbar_wait(bar_tempty + 8 * (k & 1), ((k >> 1) + 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int c = 0; c < g.nchunk; ++c, ++q) {
+                    const int s = q % g.nstage;
+                    mbar_wait(bar_full + 8 * s, (q / g.nstage) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint32_t st4 = (uint32_t)(s * g.stage) >> 4;
+                        const int nu = min(g.kper, g.nunit - g.kper * c);
+#pragma unroll 1
+                        for (int ks = 0; ks < nu; ++ks) {
+                            const uint32_t a_ks = a_lo0 + st4 + (uint32_t)ks * a_kstep;
+                            const uint32_t b_ks = b_lo0 + st4 + (uint32_t)ks * b_kstep;
+                            const bool first_unit = c == 0 && ks == 0;
+#pragma unroll 1
+                            for (int i = 0; i < Gk; ++i) {
+                                const int j = j0 + i;
+                                const int glo = max(0, 2 - j), ghi = min(2, w.TS + 1 - j);  // output row o = j - 2 + g in [0, TS)
+                                const int P = (Jbase + j - 2) % L;
+                                const uint32_t d0 = tmem_base + (uint32_t)((P + glo) * Nc);
+                                const uint32_t id = idesc_of(ghi - glo + 1);
+                                const uint32_t a_i = a_ks + (uint32_t)i * row_step;
+                                const uint32_t b_i = b_ks + (uint32_t)(glo * Nc);
+#pragma unroll
+                                for (int kf = 0; kf < 3; ++kf) {
+#pragma unroll
+                                    for (int pr = 0; pr < NPROD; ++pr) {  // a_hi w_hi, a_hi w_lo, a_lo w_hi
+                                        const uint32_t alo = a_i + (uint32_t)kf + (pr == 2 ? lo_split : 0u);
+                                        const uint32_t blo = b_i + (uint32_t)kf * b_kfstep + (pr == 1 ? b_spstep : 0u);
+                                        const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)alo;
+                                        const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)blo;
+                                        if (kf == 0 && pr == 0 && first_unit) {
+                                            // first contribution of this input row: slots that start a new round are
+                                            // overwritten (accumulate = 0), slots that already hold partial sums are not
+                                            if (P == 0) {
+                                                umma_bf16(d0, adesc, bdesc, id, 0u);
+                                            } else if (ghi == 2) {
+                                                if (glo <= 1) umma_bf16(d0, adesc, bdesc, idesc_of(2 - glo), 1u);
+                                                umma_bf16(tmem_base + (uint32_t)((P + 2) * Nc), adesc, bdesc + (uint64_t)((2 - glo) * Nc), idesc_of(1), 0u);
+                                            } else {
+                                                umma_bf16(d0, adesc, bdesc, id, 1u);
+                                            }
+                                        } else {
+                                            umma_bf16(d0, adesc, bdesc, id, 1u);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        umma_commit(bar_empty + 8 * s);
+                        if (c == g.nchunk - 1) umma_commit(bar_tfull + 8 * (k & 1));
+                    }
+                    __syncwarp();
+                }
+            }
+            Jbase += w.nin;
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (warps 2..9)
+        const int quad = warp & 3, half = (warp - kRsEpi0) >> 2;
+        const int et = tid - kRsEpi0 * 32;
+        const int npix = a.T * a.F;
+        float *myred = red + (warp - kRsEpi0) * 2 * Nc;
+        int prev_b = -1, k = 0, Jbase = 2;
+        RsWalk w = rs_walk(a);
+        while (w.next()) {
+            const int b = w.b;
+            if (b != prev_b) {
+                // border-bias table of this sample: add the channel splits of the prep kernel's partial sums, then
+                // expand to the 64 (frame-mask, bin-mask) classes
+                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                float *wb = red + 16 * Nc;  // [9][Nc]
+                const float *src = a.btab + (size_t)b * a.nsplit * 9 * Nc;
+                for (int i = et; i < 9 * Nc; i += kRsEpiThreads) {
+                    float v = 0.f;
+                    for (int sp = 0; sp < a.nsplit; ++sp) v += __ldg(src + (size_t)sp * 9 * Nc + i);
+                    wb[i] = v;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                for (int i = et; i < 64 * Nc; i += kRsEpiThreads) {
+                    const int mk = i / Nc, n = i - mk * Nc;
+                    const int tm = mk >> 3, fm = mk & 7;
+                    float v = (a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.f;
+                    for (int kt = 0; kt < 3; ++kt)
+                        for (int kf = 0; kf < 3; ++kf)
+                            if (((tm >> kt) & 1) && ((fm >> kf) & 1)) v += wb[(kt * 3 + kf) * Nc + n];
+                    btab_s[i] = v;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                prev_b = b;
+            }
+            const int f = 128 * w.m + quad * 32 + lane;
+            const bool valid = f < a.F;
+            const int fmask = 7 & ~(f == 0 ? 1 : 0) & ~(f == a.F - 1 ? 4 : 0);
+            __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
+            for (int j0 = 0; j0 < w.nin; j0 += G, ++k) {
+                const int Gk = min(G, w.nin - j0);
+                const int o_lo = max(0, j0 - 2), o_hi = min(w.TS, j0 + Gk - 2);
+                mbar_wait(bar_tfull + 8 * (k & 1), (k >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int cb = 0; cb < Nc; cb += 16) {
+                    float ssum[16], ssq[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
+                    for (int o = o_lo + half; o < o_hi; o += 2) {
+                        const int t = w.t0 + o;
+                        const int tmask = 7 & ~(t == 0 ? 1 : 0) & ~(t == a.T - 1 ? 4 : 0);
+                        const int x = (Jbase + o) % L;
+                        const float *bt = btab_s + (tmask * 8 + fmask) * Nc + cb;
+                        uint32_t v[16], v2[16];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(x * Nc + cb);
+                        tmem_ld16(taddr, v);
+                        if (x < 2) tmem_ld16(taddr + (uint32_t)(L * Nc), v2);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float y[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) y[q] = __uint_as_float(v[q]);
+                        if (x < 2) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) y[q] += __uint_as_float(v2[q]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 16; q += 4) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(bt + q);
+                            y[q] += bb.x;
+                            y[q + 1] += bb.y;
+                            y[q + 2] += bb.z;
+                            y[q + 3] += bb.w;
+                        }
+                        if (a.elu) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) y[q] = rs_elu(y[q]);
+                        }
+                        if (valid) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                ssum[q] += y[q];
+                                ssq[q] = fmaf(y[q], y[q], ssq[q]);
+                            }
+                            const int pix = t * a.F + f;
+#pragma unroll
+                            for (int g8 = 0; g8 < 16; g8 += 8) {
+                                const int co = cb + g8;
+                                if (co < a.cout) {
+                                    const int ca = a.out_coff + co;
+                                    __nv_bfloat16 *p = out_pl + ((size_t)(ca >> 3) * npix + pix) * 8;
+                                    uint32_t hp[4];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) hp[q] = pack_bf16x2(y[g8 + 2 * q], y[g8 + 2 * q + 1]);
+                                    *reinterpret_cast<uint4 *>(p) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                                    if (a.use_lo) {
+                                        uint32_t lp[4];
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q)
+                                            lp[q] = pack_bf16x2(y[g8 + 2 * q] - bf16_lo(hp[q]), y[g8 + 2 * q + 1] - bf16_hi(hp[q]));
+                                        *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(p) + a.out_lo_off) =
+                                            make_uint4(lp[0], lp[1], lp[2], lp[3]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (a.out_sums) {  // this warp's own slot, accumulated over the strip: no atomics, fixed order
+                        const float s = warp_reduce16(ssum, lane);
+                        const float q2 = warp_reduce16(ssq, lane);
+                        if ((lane & 1) == 0) {
+                            myred[(cb + (lane >> 1)) * 2] += s;
+                            myred[(cb + (lane >> 1)) * 2 + 1] += q2;
+                        }
+                    }
+                }
+                // this warp is done with the tile's slots: hand them back to the MMA issuer
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * (k & 1));
+            }
+            if (a.out_sums) {  // strip statistics -> global fixed-point accumulators
+                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                if (et < Nc && et < a.cout) {
+                    double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + et) * 2;
+                    double s8 = 0.0, q8 = 0.0;
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) {
+                        s8 += (double)red[w8 * 2 * Nc + et * 2];
+                        q8 += (double)red[w8 * 2 * Nc + et * 2 + 1];
+                    }
+                    stat_add(dst, s8);
+                    stat_add(dst + 1, q8);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                for (int i = et; i < 8 * 2 * Nc; i += kRsEpiThreads) red[i] = 0.f;
+            }
+            Jbase += w.nin;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-sample operand preparation.  Blocks [0, B * nunit): weight image of one (sample, 16-channel K unit)
+//   wimg[b][unit][kf][hi|lo][kg][n = (2 - kt) * Nc + co][8] = bf16 split of W[kt][kf][ci][co] * rstd[b][ci]
+// Blocks behind them: border-bias partial sums wbp[b][split][kt*3+kf][co] = sum_{ci in split} W * shift[b][ci]
+// (x_norm = x * rstd + shift is the consumer-side InstanceNorm affine, model.py:445; padding is applied after it).
+__device__ __forceinline__ float2 rs_affine(const RsPrepArgs &p, int b, int ci) {
+    if (p.norm_mode == NORM_IN) {
+        const double *s = p.in_sums + ((size_t)b * p.in_ctot + p.in_coff + ci) * 2;
+        return affine_from_sums(stat_get(s), stat_get(s + 1), p.norm_inv_n, (double)p.norm_eps);
+    }
+    return make_float2(1.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
+    extern __shared__ float sh[];
+    const int nimg = p.B * p.nunit;
+    const int N3 = 3 * p.Nc;
+    if ((int)blockIdx.x < nimg) {
+        const int b = blockIdx.x / p.nunit, unit = blockIdx.x - b * p.nunit;
+        float *scale = sh;
+        if (threadIdx.x < 16) {
+            const int ci = unit * 16 + threadIdx.x;
+            scale[threadIdx.x] = ci < p.cin ? rs_affine(p, b, ci).x : 0.f;
+        }
+        __syncthreads();
+        const size_t unit_elems = (size_t)3 * p.nsp * 2 * N3 * 8;
+        __nv_bfloat16 *img = p.wimg + ((size_t)b * p.nunit + unit) * unit_elems;
+        for (int i = threadIdx.x; i < 3 * 2 * N3; i += blockDim.x) {
+            const int n = i % N3;
+            const int r = i / N3;
+            const int kg = r & 1, kf = r >> 1;
+            const int ktg = n / p.Nc, co = n - ktg * p.Nc;
+            const int kt = 2 - ktg;
+            float h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ci = unit * 16 + kg * 8 + e;
+                float v = 0.f;
+                if (ci < p.cin && co < p.cout) v = p.w[((size_t)(kt * 3 + kf) * p.cin + ci) * p.cout_pad + co] * scale[kg * 8 + e];
+                h[e] = bf16_round(v);
+                l[e] = v - h[e];
+            }
+            __nv_bfloat16 *dst = img + ((size_t)((kf * p.nsp) * 2 + kg) * N3 + n) * 8;
+            *reinterpret_cast<uint4 *>(dst) =
+                make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+            if (p.nsp == 2)
+                *reinterpret_cast<uint4 *>(dst + (size_t)2 * N3 * 8) =
+                    make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+        }
+    } else {
+        int idx = blockIdx.x - nimg;
+        const int split = idx % p.nsplit;
+        const int b = idx / p.nsplit;
+        float *shift = sh;            // [kRsBiasCi]
+        float *wb = sh + kRsBiasCi;   // [nparts <= 8][9][Nc]
+        const int ci0 = split * kRsBiasCi, nci = min(kRsBiasCi, p.cin - ci0);
+        for (int i = threadIdx.x; i < nci; i += blockDim.x) shift[i] = rs_affine(p, b, ci0 + i).y;
+        const int n = threadIdx.x % p.Nc, part = threadIdx.x / p.Nc, nparts = min(8, (int)blockDim.x / p.Nc);
+        for (int i = threadIdx.x; i < nparts * 9 * p.Nc; i += blockDim.x) wb[i] = 0.f;
+        __syncthreads();
+        if (part < nparts && n < p.cout) {
+            for (int k = 0; k < 9; ++k) {
+                const float *w = p.w + ((size_t)k * p.cin + ci0) * p.cout_pad + n;
+                float acc = 0.f;
+#pragma unroll 8
+                for (int ci = part; ci < nci; ci += nparts) acc = fmaf(__ldg(w + (size_t)ci * p.cout_pad), shift[ci], acc);
+                wb[(part * 9 + k) * p.Nc + n] = acc;
+            }
+        }
+        __syncthreads();
+        float *dst = p.btab + ((size_t)b * p.nsplit + split) * 9 * p.Nc;
+        for (int i = threadIdx.x; i < 9 * p.Nc; i += blockDim.x) {
+            float v = 0.f;
+            for (int q = 0; q < nparts; ++q) v += wb[q * 9 * p.Nc + i];
+            dst[i] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*RsEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+RsEncodeFn rs_get_encode() {
+    static RsEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<RsEncodeFn>(p);
+    }
+    return fn;
+}
+
+int rs_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+bool rs_shape_ok(const ConvArgs &a) {
+    if (a.transposed || a.KT != 3 || a.KF != 3 || a.stride_f != 1 || a.pad_t != 1 || a.pad_f != 1) return false;
+    if (a.Fin != a.Fout || (a.Fin != 127 && a.Fin != 255)) return false;
+    if (a.in_layout != LAYOUT_PLANES || a.out_layout != LAYOUT_PLANES) return false;
+    if (a.in_ctot % 8 || a.in_coff % 8 || a.out_ctot % 8 || a.out_coff % 8 || a.cout % 8) return false;
+    if (a.resid || a.norm_mode == NORM_GLN) return false;
+    if (a.T < 2) return false;
+    return true;
+}
+
+bool make_rs_geom(const ConvArgs &a, int split, RsGeom &g) {
+    g = RsGeom{};
+    if (!rs_shape_ok(a)) return false;
+    g.nsp = split == 3 ? 2 : 1;
+    g.Nc = rs_round_up(a.cout, 16);
+    static const int max_nc = getenv("MISO_RS_MAXNC") ? atoi(getenv("MISO_RS_MAXNC")) : 32;
+    if (g.Nc > max_nc) return false;
+    g.N3 = 3 * g.Nc;
+    g.Mr = (a.Fin + 1) / 128;
+    g.map5d = g.Mr == 2;
+    g.pitch = g.map5d ? 130 : 128;
+    g.nplanes = (a.cin + 7) / 8;
+    g.nunit = (g.nplanes + 1) / 2;
+    g.w_unit = 3 * g.nsp * 2 * g.N3 * 16;
+    g.L = std::min(512 / g.Nc - 2, 30);
+    g.off_btab = kRsFixed;
+    g.off_red = g.off_btab + 64 * g.Nc * 4;
+    g.off_stage = rs_round_up(g.off_red + (16 + 9) * g.Nc * 4, 1024);
+    static const int g_env = getenv("MISO_RS_G") ? atoi(getenv("MISO_RS_G")) : 0;
+    for (int G = std::min({(g.L - 2) / 2, kRsMaxG, g_env > 0 ? g_env : kRsMaxG}); G >= 1; --G) {
+        for (int kper : {2, 1}) {
+            if (kper > g.nunit) continue;
+            if (split == 3 && kper == 2) continue;
+            g.G = G;
+            g.kper = kper;
+            g.nchunk = (g.nunit + kper - 1) / kper;
+            g.PL = G * g.pitch * 16;
+            g.box_bytes = 2 * kper * g.PL;
+            g.GS = rs_round_up(g.box_bytes, 128);
+            g.w_off = g.nsp * g.GS + 128;  // 128-byte zero guard behind the planes
+            g.stage = rs_round_up(g.w_off + kper * g.w_unit, 1024);
+            g.nstage = std::min(kRsMaxStages, (kRsSmemLimit - g.off_stage) / g.stage);
+            if (g.nstage >= 3) break;
+        }
+        if (g.nstage >= 3) break;
+    }
+    if (g.nstage < 3) return false;
+    if (!g.map5d && g.GS != g.box_bytes) return false;  // the shared-pad raster needs dense plane sets
+    g.smem_total = g.off_stage + g.nstage * g.stage;
+    int cols = 32;
+    while (cols < (g.L + 2) * g.Nc) cols <<= 1;
+    g.tmem_cols = cols;
+    return cols <= 512;
+}
+
+int rs_encode_maps(const ConvArgs &a, const RsGeom &g, CUtensorMap *hi, CUtensorMap *lo) {
+    RsEncodeFn enc = rs_get_encode();
+    if (!enc) {
+        set_error("conv_rs: cuTensorMapEncodeTiled is not available from the driver");
+        return MISO_E_CUDA;
+    }
+    const uint64_t CG = (uint64_t)a.in_ctot / 8, CGv = (uint64_t)(a.in_coff + a.cin + 7) / 8, T = (uint64_t)a.T, F = (uint64_t)a.Fin;
+    char *base = const_cast<char *>(reinterpret_cast<const char *>(a.in));
+    for (int sp = 0; sp < 2; ++sp) {
+        CUtensorMap *tm = sp == 0 ? hi : lo;
+        void *addr = base + (sp ? a.in_lo_off : 0);
+        CUresult r;
+        if (!g.map5d) {
+            cuuint64_t dims[4] = {2 * F, T, CGv, (cuuint64_t)a.B};
+            cuuint64_t strides[3] = {F * 16, T * F * 16, 2 * CG * T * F * 16};
+            cuuint32_t box[4] = {(cuuint32_t)(2 * g.pitch), (cuuint32_t)g.G, (cuuint32_t)(2 * g.kper), 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, addr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            cuuint64_t dims[5] = {8, F, T, CGv, (cuuint64_t)a.B};
+            cuuint64_t strides[4] = {16, F * 16, T * F * 16, 2 * CG * T * F * 16};
+            cuuint32_t box[5] = {8, (cuuint32_t)g.pitch, (cuuint32_t)g.G, (cuuint32_t)(2 * g.kper), 1};
+            cuuint32_t es[5] = {1, 1, 1, 1, 1};
+            r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, addr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (r != CUDA_SUCCESS) {
+            set_error("conv_rs: cuTensorMapEncodeTiled failed (%d) for F=%d T=%d ctot=%d G=%d", (int)r, a.Fin, a.T, a.in_ctot, g.G);
+            return MISO_E_CUDA;
+        }
+    }
+    return MISO_OK;
+}
+
+}  // namespace
+
+int conv_rs_init() {
+    static bool done = false;
+    if (done) return MISO_OK;
+    cudaError_t e = cudaFuncSetAttribute(conv_rs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_rs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemLimit);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rs_kernel)");
+    done = true;
+    return MISO_OK;
+}
+
+bool conv_rs_eligible(const ConvArgs &a, int split) {
+    static const bool off = getenv("MISO_RS") && atoi(getenv("MISO_RS")) == 0;
+    if (off) return false;
+    RsGeom g;
+    return make_rs_geom(a, split, g);
+}
+
+void conv_rs_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size_t *btab_bytes) {
+    RsGeom g;
+    *wimg_bytes = *btab_bytes = 0;
+    if (!make_rs_geom(a, split, g)) return;
+    *wimg_bytes = (size_t)a.B * g.nunit * g.w_unit;
+    *btab_bytes = (size_t)a.B * ((a.cin + kRsBiasCi - 1) / kRsBiasCi) * 9 * g.Nc * sizeof(float);
+}
+
+int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream) {
+    RsGeom g;
+    MISO_REQUIRE(make_rs_geom(a, split, g), "conv_rs: layer does not fit the row-streaming path (cin=%d cout=%d F=%d)", a.cin, a.cout, a.Fin);
+    const int nsplit = (a.cin + kRsBiasCi - 1) / kRsBiasCi;
+    const size_t need_w = (size_t)a.B * g.nunit * g.w_unit, need_b = (size_t)a.B * nsplit * 9 * g.Nc * sizeof(float);
+    if (need_w > scratch.wimg_bytes || need_b > scratch.btab_bytes) {
+        set_error("conv_rs: scratch too small (%zu/%zu weight bytes, %zu/%zu bias bytes)", scratch.wimg_bytes, need_w, scratch.btab_bytes,
+                  need_b);
+        return MISO_E_WORKSPACE;
+    }
+    static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "conv_rs: cin=%d cout=%d F=%d | Nc=%d L=%d G=%d Mr=%d pitch=%d kper=%d nchunk=%d nstage=%d stage=%dB tmem=%d smem=%d\n", a.cin,
+                a.cout, a.Fin, g.Nc, g.L, g.G, g.Mr, g.pitch, g.kper, g.nchunk, g.nstage, g.stage, g.tmem_cols, g.smem_total);
+    CUtensorMap tm_hi, tm_lo;
+    int rc = rs_encode_maps(a, g, &tm_hi, &tm_lo);
+    if (rc) return rc;
+    rc = conv_rs_init();
+    if (rc) return rc;
+
+    RsPrepArgs p{};
+    p.w = a.w;
+    p.in_sums = a.in_sums;
+    p.in_ctot = a.in_ctot;
+    p.in_coff = a.in_coff;
+    p.cin = a.cin;
+    p.cout = a.cout;
+    p.cout_pad = a.cout_pad;
+    p.norm_mode = a.norm_mode;
+    p.norm_eps = a.norm_eps;
+    p.norm_inv_n = a.norm_inv_n;
+    p.wimg = reinterpret_cast<__nv_bfloat16 *>(scratch.wimg);
+    p.btab = scratch.btab;
+    p.B = a.B;
+    p.Nc = g.Nc;
+    p.nunit = g.nunit;
+    p.nsp = g.nsp;
+    p.nsplit = nsplit;
+    const size_t prep_smem = (size_t)(kRsBiasCi + 8 * 9 * g.Nc) * sizeof(float);
+    prof_begin(stream);
+    conv_rs_prep_kernel<<<a.B * g.nunit + a.B * nsplit, 256, prep_smem, stream>>>(p);
+    MISO_LAUNCHED("conv_rs_prep_kernel");
+
+    RsArgs k{};
+    k.g = g;
+    k.wimg = p.wimg;
+    k.wimg_bstride = (size_t)g.nunit * (g.w_unit / 2);
+    k.btab = p.btab;
+    k.bias = a.bias;
+    k.nsplit = nsplit;
+    k.out = a.out;
+    k.out_sums = a.out_sums;
+    k.B = a.B;
+    k.T = a.T;
+    k.F = a.Fin;
+    k.in_coff = a.in_coff;
+    k.out_ctot = a.out_ctot;
+    k.out_coff = a.out_coff;
+    k.cout = a.cout;
+    k.out_lo_off = a.out_lo_off;
+    k.use_lo = a.use_lo;
+    k.elu = a.elu;
+    const long long rows = (long long)a.B * g.Mr * a.T;
+    dim3 grid((unsigned)std::min<long long>(148, std::max<long long>(1, rows / 2)), 1, 1);
+    if (split == 3)
+        conv_rs_kernel<3><<<grid, kRsThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+    else
+        conv_rs_kernel<1><<<grid, kRsThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+    {
+        const double pix = (double)a.B * a.T * a.Fout;
+        const double flops = 2.0 * pix * a.cin * a.cout * 9;
+        const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
+        prof_end(stream, flops, bytes, MISO_PROF_CONV_TC);
+    }
+    MISO_LAUNCHED("conv_rs_kernel");
+    return MISO_OK;
+}
+
+}  // namespace miso
