@@ -69,6 +69,7 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
 
 // row-streaming variant with the frame taps merged into N (conv_rs.cu): stride-1 pad-(1,1) 3x3 convs at F+1 = 128 / 256
 int conv_rs_init();
+void conv_rs_set_trace(long long *d_buf, int cin, int fin);
 bool conv_rs_eligible(const ConvArgs &a, int split);
 void conv_rs_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size_t *btab_bytes);
 int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream);

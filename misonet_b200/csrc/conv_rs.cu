@@ -14,10 +14,11 @@
 // its strip: every input row is loaded ONCE (no frame halo re-reads) and multiplied once.
 //
 // TMEM is a ring of L logical slots (+ 2 extension slots so that an MMA never wraps: an MMA that starts in slot
-// L-2 / L-1 spills into slots L, L+1, which the epilogue adds to slots 0, 1).  A slot's first write of a round
-// uses accumulate = 0 (the freshly started output row is issued as its own narrow MMA once per row), so the
-// epilogue never has to clear tensor memory.  Tiles of G input rows: the epilogue of tile k (output rows that
-// became complete) overlaps the MMAs of tile k + 1; 2G + 2 <= L.
+// L-2 / L-1 spills into slots L, L+1, which the epilogue adds to slots 0, 1).  The epilogue hands every slot it
+// has drained back cleared (tcgen05.st), so every MMA accumulates and the issuing thread -- whose time between
+// two MMAs is on the critical path, the pipe queues only a couple of MMAs -- has no special cases.  Tiles of G
+// input rows: the epilogue of tile k (output rows that became complete) overlaps the MMAs of tile k + 1;
+// 2G + 2 <= L.
 //
 // Layout in shared memory per stage (kper 16-channel K units): A planes [hi|lo][unit][kg][row][pitch px][8 ch]
 // by one TMA box per plane set, then the per-sample weight image of the units (conv_rs_prep_kernel):
@@ -67,7 +68,17 @@ struct RsArgs {
     int out_ctot, out_coff, cout;
     size_t out_lo_off;
     int use_lo, elu;
+    long long *trace;  // debug: clock64 event log of CTA 0 (tools/tc_trace.py), or null
 };
+
+// trace regions: [0,4096) producer, [4096,8192) MMA issuer, [8192,12288) first epilogue warp; entries are (tag, clock)
+__device__ __forceinline__ void rs_trace(long long *trace, int region, int &n, int tag) {
+    if (trace && blockIdx.x == 0 && n < 2040) {
+        trace[region * 4096 + 2 * n] = tag;
+        trace[region * 4096 + 2 * n + 1] = clock64();
+        ++n;
+    }
+}
 
 struct RsPrepArgs {
     const float *w;  // packed fp32 [9][cin][cout_pad]
@@ -117,6 +128,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const RsGeom &g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Nc = g.Nc, L = g.L, G = g.G;
+    const long long t_start = a.trace ? clock64() : 0;
     constexpr int NPROD = SPLIT == 3 ? 3 : 1;
 
     const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 64);
@@ -153,21 +165,31 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= kRsEpi0) {  // all accumulator slots start cleared
+        const int quad = warp & 3, half = (warp - kRsEpi0) >> 2;
+        for (int col = half * 16; col < g.tmem_cols; col += 32) tmem_zero16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (elect_one()) {
             const int plane0 = a.in_coff >> 3;
-            int q = 0;
+            int s = 0, ph = 0, ntr = 0;  // stage index and the parity of the release of its previous use
+            bool primed = false;         // every stage has been filled once
             RsWalk w = rs_walk(a);
             while (w.next()) {
                 const __nv_bfloat16 *wsrc = a.wimg + (size_t)w.b * a.wimg_bstride;
                 const int f0 = 128 * w.m - 1;
                 for (int j0 = 0; j0 < w.nin; j0 += G) {
                     const int tin = w.t0 - 1 + j0;
-                    for (int c = 0; c < g.nchunk; ++c, ++q) {
-                        const int s = q % g.nstage;
-                        if (q >= g.nstage) mbar_wait(bar_empty + 8 * s, ((q / g.nstage) + 1) & 1);
+                    for (int c = 0; c < g.nchunk; ++c) {
+                        rs_trace(a.trace, 0, ntr, 100 + c);
+                        if (primed) mbar_wait(bar_empty + 8 * s, (uint32_t)ph);
+                        rs_trace(a.trace, 0, ntr, 200 + c);
                         const int nu = min(g.kper, g.nunit - g.kper * c);
                         const uint32_t full = bar_full + 8 * s;
                         mbar_expect_tx(full, (uint32_t)(g.nsp * g.box_bytes + nu * g.w_unit));
@@ -182,72 +204,74 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                 tma_load_4d(dst, tm, full, 2 * f0, tin, pl, w.b);
                         }
                         bulk_load(sa + (uint32_t)g.w_off, wsrc + (size_t)c * g.kper * (g.w_unit / 2), (uint32_t)(nu * g.w_unit), full);
+                        if (++s == g.nstage) {
+                            s = 0;
+                            if (primed) ph ^= 1;
+                            primed = true;
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        const uint32_t idesc0 = make_idesc(0);
-        auto idesc_of = [&](int ngroups) { return idesc0 | ((uint32_t)((ngroups * Nc) >> 3) << 17); };
-        constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // stride offset 128 B between 8-row groups, version 1
-        const uint32_t a_lo0 = (s_stage >> 4) | (((uint32_t)g.PL >> 4) << 16);
-        const uint32_t b_lo0 = ((s_stage + (uint32_t)g.w_off) >> 4) | ((uint32_t)g.N3 << 16);  // leading offset N3 * 16 B
-        const uint32_t lo_split = (uint32_t)g.GS >> 4;
-        const uint32_t a_kstep = (uint32_t)(2 * g.PL) >> 4, b_kstep = (uint32_t)g.w_unit >> 4;
-        const uint32_t b_kfstep = (uint32_t)(g.nsp * 2 * g.N3), b_spstep = (uint32_t)(2 * g.N3);
-        const uint32_t row_step = (uint32_t)g.pitch;
-        int q = 0, k = 0, Jbase = 2;
-        RsWalk w = rs_walk(a);
-        while (w.next()) {
-            for (int j0 = 0; j0 < w.nin; j0 += G, ++k) {
-                const int Gk = min(G, w.nin - j0);
-                if (k >= 2) {  // the epilogue of tile k - 2 has drained the slots this tile reuses
-                    mbar_wait(bar_tempty + 8 * (k & 1), ((k >> 1) + 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                for (int c = 0; c < g.nchunk; ++c, ++q) {
-                    const int s = q % g.nstage;
-                    mbar_wait(bar_full + 8 * s, (q / g.nstage) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (elect_one()) {
+        // ---------------------------------------------------------------- MMA issuer (one elected thread)
+        // The tensor pipe queues only a couple of MMAs behind the running one, so anything on the issuing thread's
+        // critical path between two MMAs (row bookkeeping, barrier polls) idles the pipe.  Hence: the per-row
+        // parameters of a tile are computed once per tile, every MMA accumulates (the epilogue hands the slots it has
+        // drained back ZEROED, so there is no first-write special case), and the row loop is unrolled.
+        if (elect_one()) {
+            const uint32_t idesc0 = make_idesc(0);
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // stride offset 128 B between 8-row groups, version 1
+            const uint32_t a_lo0 = (s_stage >> 4) | (((uint32_t)g.PL >> 4) << 16);
+            const uint32_t b_lo0 = ((s_stage + (uint32_t)g.w_off) >> 4) | ((uint32_t)g.N3 << 16);  // leading offset N3 * 16 B
+            const uint32_t lo_split = (uint32_t)g.GS >> 4;
+            const uint32_t a_kstep = (uint32_t)(2 * g.PL) >> 4, b_kstep = (uint32_t)g.w_unit >> 4;
+            const uint32_t b_kfstep = (uint32_t)(g.nsp * 2 * g.N3), b_spstep = (uint32_t)(2 * g.N3);
+            const uint32_t row_step = (uint32_t)g.pitch;
+            int s = 0, ph = 0, k = 0, Pcur = 0, ntr = 0;  // Pcur: ring position of the slot two rows above the tile's first input row
+            RsWalk w = rs_walk(a);
+            while (w.next()) {
+                for (int j0 = 0; j0 < w.nin; j0 += G, ++k) {
+                    const int Gk = min(G, w.nin - j0);
+                    uint32_t rd[kRsMaxG], rb[kRsMaxG], rid[kRsMaxG];  // per row: accumulator address, weight row offset, idesc
+#pragma unroll
+                    for (int i = 0; i < kRsMaxG; ++i) {
+                        const int j = j0 + i;
+                        const int glo = max(0, 2 - j), ghi = min(2, w.TS + 1 - j);  // output row o = j - 2 + g in [0, TS)
+                        int P = Pcur + i;
+                        if (P >= L) P -= L;
+                        rd[i] = tmem_base + (uint32_t)((P + glo) * Nc);
+                        rb[i] = (uint32_t)(glo * Nc);
+                        rid[i] = idesc0 | ((uint32_t)(((ghi - glo + 1) * Nc) >> 3) << 17);
+                    }
+                    rs_trace(a.trace, 1, ntr, 1000);
+                    if (k >= 2) {  // the epilogue of tile k - 2 has drained the slots this tile reuses
+                        mbar_wait(bar_tempty + 8 * (k & 1), ((k >> 1) + 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    for (int c = 0; c < g.nchunk; ++c) {
+                        rs_trace(a.trace, 1, ntr, 100 + c);
+                        mbar_wait(bar_full + 8 * s, (uint32_t)ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        rs_trace(a.trace, 1, ntr, 200 + c);
                         const uint32_t st4 = (uint32_t)(s * g.stage) >> 4;
                         const int nu = min(g.kper, g.nunit - g.kper * c);
 #pragma unroll 1
                         for (int ks = 0; ks < nu; ++ks) {
                             const uint32_t a_ks = a_lo0 + st4 + (uint32_t)ks * a_kstep;
                             const uint32_t b_ks = b_lo0 + st4 + (uint32_t)ks * b_kstep;
-                            const bool first_unit = c == 0 && ks == 0;
-#pragma unroll 1
-                            for (int i = 0; i < Gk; ++i) {
-                                const int j = j0 + i;
-                                const int glo = max(0, 2 - j), ghi = min(2, w.TS + 1 - j);  // output row o = j - 2 + g in [0, TS)
-                                const int P = (Jbase + j - 2) % L;
-                                const uint32_t d0 = tmem_base + (uint32_t)((P + glo) * Nc);
-                                const uint32_t id = idesc_of(ghi - glo + 1);
-                                const uint32_t a_i = a_ks + (uint32_t)i * row_step;
-                                const uint32_t b_i = b_ks + (uint32_t)(glo * Nc);
 #pragma unroll
-                                for (int kf = 0; kf < 3; ++kf) {
+                            for (int i = 0; i < kRsMaxG; ++i) {
+                                if (i < Gk) {
+                                    const uint32_t a_i = a_ks + (uint32_t)i * row_step;
+                                    const uint32_t b_i = b_ks + rb[i];
 #pragma unroll
-                                    for (int pr = 0; pr < NPROD; ++pr) {  // a_hi w_hi, a_hi w_lo, a_lo w_hi
-                                        const uint32_t alo = a_i + (uint32_t)kf + (pr == 2 ? lo_split : 0u);
-                                        const uint32_t blo = b_i + (uint32_t)kf * b_kfstep + (pr == 1 ? b_spstep : 0u);
-                                        const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)alo;
-                                        const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)blo;
-                                        if (kf == 0 && pr == 0 && first_unit) {
-                                            // first contribution of this input row: slots that start a new round are
-                                            // overwritten (accumulate = 0), slots that already hold partial sums are not
-                                            if (P == 0) {
-                                                umma_bf16(d0, adesc, bdesc, id, 0u);
-                                            } else if (ghi == 2) {
-                                                if (glo <= 1) umma_bf16(d0, adesc, bdesc, idesc_of(2 - glo), 1u);
-                                                umma_bf16(tmem_base + (uint32_t)((P + 2) * Nc), adesc, bdesc + (uint64_t)((2 - glo) * Nc), idesc_of(1), 0u);
-                                            } else {
-                                                umma_bf16(d0, adesc, bdesc, id, 1u);
-                                            }
-                                        } else {
-                                            umma_bf16(d0, adesc, bdesc, id, 1u);
+                                    for (int kf = 0; kf < 3; ++kf) {
+#pragma unroll
+                                        for (int pr = 0; pr < NPROD; ++pr) {  // a_hi w_hi, a_hi w_lo, a_lo w_hi
+                                            const uint32_t alo = a_i + (uint32_t)kf + (pr == 2 ? lo_split : 0u);
+                                            const uint32_t blo = b_i + (uint32_t)kf * b_kfstep + (pr == 1 ? b_spstep : 0u);
+                                            umma_bf16(rd[i], ((uint64_t)kDescHi << 32) | (uint64_t)alo, ((uint64_t)kDescHi << 32) | (uint64_t)blo, rid[i], 1u);
                                         }
                                     }
                                 }
@@ -255,11 +279,16 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                         }
                         umma_commit(bar_empty + 8 * s);
                         if (c == g.nchunk - 1) umma_commit(bar_tfull + 8 * (k & 1));
+                        rs_trace(a.trace, 1, ntr, 300 + c);
+                        if (++s == g.nstage) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
-                    __syncwarp();
+                    Pcur += Gk;
+                    if (Pcur >= L) Pcur -= L;
                 }
             }
-            Jbase += w.nin;
         }
     } else {
         // ---------------------------------------------------------------- epilogue (warps 2..9)
@@ -267,7 +296,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         const int et = tid - kRsEpi0 * 32;
         const int npix = a.T * a.F;
         float *myred = red + (warp - kRsEpi0) * 2 * Nc;
-        int prev_b = -1, k = 0, Jbase = 2;
+        int prev_b = -1, k = 0, xo = 2 % L, ntr = 0;  // xo: ring position of the next output row to drain
+        const bool tracer = warp == kRsEpi0 && lane == 0;
         RsWalk w = rs_walk(a);
         while (w.next()) {
             const int b = w.b;
@@ -302,8 +332,10 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             for (int j0 = 0; j0 < w.nin; j0 += G, ++k) {
                 const int Gk = min(G, w.nin - j0);
                 const int o_lo = max(0, j0 - 2), o_hi = min(w.TS, j0 + Gk - 2);
+                if (tracer) rs_trace(a.trace, 2, ntr, 1);
                 mbar_wait(bar_tfull + 8 * (k & 1), (k >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tracer) rs_trace(a.trace, 2, ntr, 2);
                 for (int cb = 0; cb < Nc; cb += 16) {
                     float ssum[16], ssq[16];
 #pragma unroll
@@ -311,13 +343,16 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                     for (int o = o_lo + half; o < o_hi; o += 2) {
                         const int t = w.t0 + o;
                         const int tmask = 7 & ~(t == 0 ? 1 : 0) & ~(t == a.T - 1 ? 4 : 0);
-                        const int x = (Jbase + o) % L;
+                        int x = xo + o - o_lo;
+                        if (x >= L) x -= L;
                         const float *bt = btab_s + (tmask * 8 + fmask) * Nc + cb;
                         uint32_t v[16], v2[16];
                         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(x * Nc + cb);
                         tmem_ld16(taddr, v);
                         if (x < 2) tmem_ld16(taddr + (uint32_t)(L * Nc), v2);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        tmem_zero16(taddr);  // hand the slot back cleared: every MMA accumulates
+                        if (x < 2) tmem_zero16(taddr + (uint32_t)(L * Nc));
                         float y[16];
 #pragma unroll
                         for (int q = 0; q < 16; ++q) y[q] = __uint_as_float(v[q]);
@@ -376,9 +411,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                     }
                 }
                 // this warp is done with the tile's slots: hand them back to the MMA issuer
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
+                if (tracer) rs_trace(a.trace, 2, ntr, 3);
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * (k & 1));
+                xo += max(0, o_hi - o_lo);
+                if (xo >= L) xo -= L;
             }
             if (a.out_sums) {  // strip statistics -> global fixed-point accumulators
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
@@ -396,11 +435,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
                 for (int i = et; i < 8 * 2 * Nc; i += kRsEpiThreads) red[i] = 0.f;
             }
-            Jbase += w.nin;
+            xo += 2;  // the two slots between strips stay unused
+            if (xo >= L) xo -= L;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (a.trace && tid == 0) a.trace[3 * 4096 + blockIdx.x] = clock64() - t_start;  // per-CTA duration (4th trace region)
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
@@ -520,7 +561,7 @@ bool make_rs_geom(const ConvArgs &a, int split, RsGeom &g) {
     if (!rs_shape_ok(a)) return false;
     g.nsp = split == 3 ? 2 : 1;
     g.Nc = rs_round_up(a.cout, 16);
-    static const int max_nc = getenv("MISO_RS_MAXNC") ? atoi(getenv("MISO_RS_MAXNC")) : 32;
+    static const int max_nc = getenv("MISO_RS_MAXNC") ? atoi(getenv("MISO_RS_MAXNC")) : 64;
     if (g.Nc > max_nc) return false;
     g.N3 = 3 * g.Nc;
     g.Mr = (a.Fin + 1) / 128;
@@ -595,7 +636,16 @@ int rs_encode_maps(const ConvArgs &a, const RsGeom &g, CUtensorMap *hi, CUtensor
     return MISO_OK;
 }
 
+long long *g_rs_trace = nullptr;
+int g_rs_trace_cin = 0, g_rs_trace_fin = 0;
+
 }  // namespace
+
+void conv_rs_set_trace(long long *d_buf, int cin, int fin) {
+    g_rs_trace = d_buf;
+    g_rs_trace_cin = cin;
+    g_rs_trace_fin = fin;
+}
 
 int conv_rs_init() {
     static bool done = false;
@@ -684,6 +734,7 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     k.out_lo_off = a.out_lo_off;
     k.use_lo = a.use_lo;
     k.elu = a.elu;
+    k.trace = (g_rs_trace && a.cin == g_rs_trace_cin && a.Fin == g_rs_trace_fin) ? g_rs_trace : nullptr;
     const long long rows = (long long)a.B * g.Mr * a.T;
     dim3 grid((unsigned)std::min<long long>(148, std::max<long long>(1, rows / 2)), 1, 1);
     if (split == 3)

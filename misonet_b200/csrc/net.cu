@@ -1044,6 +1044,7 @@ int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T,
 
 int miso_debug_tc_trace(long long *d_buf, int cin, int fin) {
     conv_tc_set_trace(d_buf, cin, fin);
+    conv_rs_set_trace(d_buf, cin, fin);
     return MISO_OK;
 }
 

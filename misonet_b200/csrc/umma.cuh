@@ -92,6 +92,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr));
 }
 
+// zero 16 accumulator columns of this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+        : "memory");
+}
+
 // 16 per-lane values -> lanes 2k and 2k+1 hold the warp total of value k (16 shuffles)
 __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 #pragma unroll

@@ -13,13 +13,17 @@ m.load_state_dict(bench.make_state_dict_np(m, 0))
 m = m.cuda().eval(); m.conv_mode = mode; m.use_graph = False
 x = bench.rand_spec(100, (wl["B"], 6, wl["T"], wl["F"]), "cuda")
 lib = _lib.load()
-buf = torch.zeros(3 * 4096, dtype=torch.int64, device="cuda")
+buf = torch.zeros(4 * 4096, dtype=torch.int64, device="cuda")
 with torch.no_grad():
     m(x); torch.cuda.synchronize()
     lib.miso_debug_tc_trace(buf.data_ptr(), cin, fin)
     m(x); torch.cuda.synchronize()
     lib.miso_debug_tc_trace(None, 0, 0)
-h = buf.cpu().view(3, 2048, 2)
+h = buf.cpu()[:3 * 4096].view(3, 2048, 2)
+dur = buf.cpu()[3 * 4096:3 * 4096 + 148].tolist()
+if any(dur):
+    print('per-CTA cycles: min', min(dur), 'max', max(dur), 'mean', sum(dur) / len(dur))
+    print('   ', ' '.join(str(d // 1000) for d in dur))
 t0 = min(int(h[r, 0, 1]) for r in range(3) if int(h[r, 0, 0]) != 0)
 names = ["producer", "mma", "epilogue"]
 for r in range(3):
