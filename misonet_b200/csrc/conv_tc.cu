@@ -30,6 +30,7 @@
 #include <cstdlib>
 
 #include "conv.cuh"
+#include "tcn.cuh"
 #include "umma.cuh"
 
 namespace miso {
@@ -909,6 +910,7 @@ int conv_tc_init() {
         return MISO_E_CUDA;
     }
     if (int rc = conv_rs_init()) return rc;
+    if (int rc = tcn_pw_init()) return rc;
     done = true;
     return MISO_OK;
 }

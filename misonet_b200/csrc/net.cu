@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "conv.cuh"
+#include "tcn.cuh"
 
 namespace miso {
 
@@ -429,6 +430,8 @@ struct Plan {
     std::vector<int> Fx;
     std::vector<BufDesc> E, D, Y;
     float *S = nullptr, *U = nullptr, *P = nullptr;
+    void *tcn_wimg = nullptr;  // tensor-core pointwise convs: weight images and W beta / W gamma vectors (tcn.cu)
+    float *tcn_wvec = nullptr;
     std::vector<double *> sS, sU, g1, g2;
     double *stats_base = nullptr;
     size_t stats_bytes = 0;
@@ -506,6 +509,12 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
     pl.S = reinterpret_cast<float *>(take(tcn_bytes));
     pl.U = reinterpret_cast<float *>(take(tcn_bytes));
     pl.P = reinterpret_cast<float *>(take(tcn_bytes));
+    if (tcn_pw_eligible(n->C)) {
+        size_t wi, wv;
+        tcn_pw_scratch_need(n->C, 2 * nblk, &wi, &wv);
+        pl.tcn_wimg = take(wi);
+        pl.tcn_wvec = reinterpret_cast<float *>(take(wv));
+    }
     pl.sS.resize(nblk);
     pl.sU.resize(nblk);
     pl.g1.resize(nblk);
@@ -666,6 +675,17 @@ int Walker::run(const void *d_x, float *d_y) {
         const int nblk = n->R * n->X;
         const int bn = conv_fp32_tile_n(C);
         const int cpad = (C + bn - 1) / bn * bn;
+        const bool use_pw = n->mode != 0 && tcn_pw_eligible(C) && 2 * nblk <= kTcnMaxPw;
+        if (!dry && use_pw) {
+            TcnPwTable tab{};
+            for (int i = 0; i < 2 * nblk; ++i) {
+                tab.w[i] = n->params[n->tcn[i].pw].d;
+                tab.gamma[i] = n->params[n->tcn[i].gamma].d;
+                tab.beta[i] = n->params[n->tcn[i].beta].d;
+            }
+            rc = launch_tcn_wprep(tab, 2 * nblk, C, cpad, n->mode == 1 ? 3 : 1, pl.tcn_wimg, pl.tcn_wvec, st);
+            if (rc) return rc;
+        }
         for (int k = 0; k < nblk; ++k) {
             const int dil = 1 << (k % n->X);
             for (int half = 0; half < 2; ++half) {
@@ -742,7 +762,24 @@ int Walker::run(const void *d_x, float *d_y) {
                     }
                     continue;
                 }
-                if (tc_pw && conv_tc_eligible(a))
+                if (use_pw && a.out_layout == LAYOUT_CL_F32) {
+                    TcnPwArgs p{};
+                    p.planes = pl.P;
+                    p.lo_off = a.in_lo_off;
+                    p.wimg = pl.tcn_wimg;
+                    p.wvec = pl.tcn_wvec;
+                    p.index = k * 2 + half;
+                    p.gln_sums = gs;
+                    p.gln_inv_n = a.norm_inv_n;
+                    p.gln_eps = a.norm_eps;
+                    p.out = reinterpret_cast<float *>(a.out);
+                    p.resid = a.resid;
+                    p.out_sums = a.out_sums;
+                    p.B = B;
+                    p.T = T;
+                    p.C = C;
+                    rc = launch_tcn_pw(p, n->mode == 1 ? 3 : 1, st);
+                } else if (tc_pw && conv_tc_eligible(a))
                     rc = launch_conv_tc(a, n->mode == 1 ? 3 : 1, pl.scratch, st);
                 else
                     rc = launch_conv_fp32(a, st);  // reads either layout
