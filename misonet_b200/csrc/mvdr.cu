@@ -95,7 +95,9 @@ __device__ void load_scm(const float *__restrict__ partial, int bs, int f, int F
                          double (*Ar)[M], double (*Ai)[M]) {
     constexpr int NV = Tri<M>::NV;
     int k = 0;
+#pragma unroll
     for (int i = 0; i < M; ++i)
+#pragma unroll
         for (int j = i; j < M; ++j) {
             double re = 0.0, im = 0.0;
             for (int sp = 0; sp < tsplit; ++sp) {
@@ -114,8 +116,9 @@ __device__ void load_scm(const float *__restrict__ partial, int bs, int f, int F
         }
 }
 
+// any microphone count: one thread per problem, (p,q)-indexed sweep (dynamically indexed arrays)
 template <int M>
-__global__ void __launch_bounds__(64) eig_kernel(const float *__restrict__ partial, double2 *__restrict__ steer, int nprob,
+__global__ void __launch_bounds__(64) eig_generic_kernel(const float *__restrict__ partial, double2 *__restrict__ steer, int nprob,
                                                  int F, int T, int tsplit) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nprob) return;
@@ -190,6 +193,187 @@ __global__ void __launch_bounds__(64) eig_kernel(const float *__restrict__ parti
     for (int m = 0; m < M; ++m) steer[((size_t)bs * F + f) * M + m] = make_double2(dr[m] * g, di[m] * g);
 }
 
+// Principal eigenvector by cyclic Jacobi in ROUND-ROBIN order: a round rotates the three disjoint index pairs
+// (0,1), (2,3), (4,5) at once (their 2x2 rotations commute), then a fixed permutation of the index positions brings
+// three new pairs into those places; five rounds visit all 15 pairs and return the positions to their original order.
+// The rotated pairs are therefore compile-time constants, so the Hermitian matrix (upper triangle) and the eigenvector
+// rows live in registers (the (p,q)-indexed classic sweep needs dynamically indexed arrays = local memory, 6x slower),
+// and the three rotations of a round give the fp64 pipe independent work.  Two adjacent lanes share a problem: both
+// rotate the matrix, each accumulates three of the six eigenvector rows (V <- V J acts on rows independently).
+template <int M>
+__global__ void __launch_bounds__(64) eig6_kernel(const float *__restrict__ partial, double2 *__restrict__ steer, int nprob,
+                                                  int F, int T, int tsplit) {
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = gi & 1;
+    const bool live = (gi >> 1) < nprob;
+    const int i = live ? (gi >> 1) : nprob - 1;
+    const int f = i % F, bs = i / F;
+    double Ar[M][M], Ai[M][M];  // only [i][j], i <= j is maintained after the load
+    load_scm<M>(partial, bs, f, F, tsplit, 0, 1.0 / (double)T, Ar, Ai);
+    double Vr[3][M], Vi[3][M];  // rows 3h .. 3h+2 of V
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < M; ++q) {
+            Vr[r][q] = (3 * h + r == q) ? 1.0 : 0.0;
+            Vi[r][q] = 0.0;
+        }
+    constexpr int perm[6] = {0, 3, 1, 5, 2, 4};  // new position i holds the old position perm[i]
+#pragma unroll 1
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, dg = 0.0;
+#pragma unroll
+        for (int p = 0; p < M; ++p) {
+            dg += Ar[p][p] * Ar[p][p];
+#pragma unroll
+            for (int q = p + 1; q < M; ++q) off += Ar[p][q] * Ar[p][q] + Ai[p][q] * Ai[p][q];
+        }
+        if (off <= 1e-30 * dg || off == 0.0) break;
+#pragma unroll 1
+        for (int rnd = 0; rnd < 5; ++rnd) {
+            double c[3], s[3], er[3], ei[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int p = 2 * a, q = 2 * a + 1;
+                const double xr = Ar[p][q], xi = Ai[p][q];
+                const double ax = sqrt(xr * xr + xi * xi);
+                if (ax == 0.0) {
+                    c[a] = 1.0;
+                    s[a] = 0.0;
+                    er[a] = 1.0;
+                    ei[a] = 0.0;
+                } else {
+                    const double tau = (Ar[q][q] - Ar[p][p]) / (2.0 * ax);
+                    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    c[a] = 1.0 / sqrt(1.0 + t * t);
+                    s[a] = t * c[a];
+                    er[a] = xr / ax;  // e = conj(x) / |x|
+                    ei[a] = -xi / ax;
+                    Ar[p][p] -= t * ax;
+                    Ar[q][q] += t * ax;
+                    Ar[p][q] = 0.0;
+                    Ai[p][q] = 0.0;
+                }
+            }
+            // off-diagonal 2x2 blocks: B <- Ja^H (B Jb), with J = [[c, s], [-s e, c e]]
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = a + 1; b < 3; ++b) {
+                    const double sber = s[b] * er[b], sbei = s[b] * ei[b], cber = c[b] * er[b], cbei = c[b] * ei[b];
+                    double tr[2][2], ti[2][2];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const double pr = Ar[2 * a + r][2 * b], pi = Ai[2 * a + r][2 * b];
+                        const double qr = Ar[2 * a + r][2 * b + 1], qi = Ai[2 * a + r][2 * b + 1];
+                        tr[r][0] = c[b] * pr - (sber * qr - sbei * qi);
+                        ti[r][0] = c[b] * pi - (sber * qi + sbei * qr);
+                        tr[r][1] = s[b] * pr + (cber * qr - cbei * qi);
+                        ti[r][1] = s[b] * pi + (cber * qi + cbei * qr);
+                    }
+                    const double saer = s[a] * er[a], saei = s[a] * ei[a], caer = c[a] * er[a], caei = c[a] * ei[a];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const double pr = tr[0][k], pi = ti[0][k], qr = tr[1][k], qi = ti[1][k];
+                        // row p = c p - s conj(e) q ; row q = s p + c conj(e) q
+                        Ar[2 * a][2 * b + k] = c[a] * pr - (saer * qr + saei * qi);
+                        Ai[2 * a][2 * b + k] = c[a] * pi - (saer * qi - saei * qr);
+                        Ar[2 * a + 1][2 * b + k] = s[a] * pr + (caer * qr + caei * qi);
+                        Ai[2 * a + 1][2 * b + k] = s[a] * pi + (caer * qi - caei * qr);
+                    }
+                }
+            // V <- V J on this lane's rows
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int p = 2 * a, q = 2 * a + 1;
+                const double ser = s[a] * er[a], sei = s[a] * ei[a], cer = c[a] * er[a], cei = c[a] * ei[a];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double pr = Vr[r][p], pi = Vi[r][p], qr = Vr[r][q], qi = Vi[r][q];
+                    Vr[r][p] = c[a] * pr - (ser * qr - sei * qi);
+                    Vi[r][p] = c[a] * pi - (ser * qi + sei * qr);
+                    Vr[r][q] = s[a] * pr + (cer * qr - cei * qi);
+                    Vi[r][q] = s[a] * pi + (cer * qi + cei * qr);
+                }
+            }
+            // move the index positions: new [i][j] = old [perm i][perm j] (conjugated when that entry is below the diagonal)
+            double Nr[M][M], Ni[M][M];
+#pragma unroll
+            for (int p = 0; p < M; ++p)
+#pragma unroll
+                for (int q = p; q < M; ++q) {
+                    const int pp = perm[p], qq = perm[q];
+                    if (pp <= qq) {
+                        Nr[p][q] = Ar[pp][qq];
+                        Ni[p][q] = Ai[pp][qq];
+                    } else {
+                        Nr[p][q] = Ar[qq][pp];
+                        Ni[p][q] = -Ai[qq][pp];
+                    }
+                }
+#pragma unroll
+            for (int p = 0; p < M; ++p)
+#pragma unroll
+                for (int q = p; q < M; ++q) {
+                    Ar[p][q] = Nr[p][q];
+                    Ai[p][q] = p == q ? 0.0 : Ni[p][q];
+                }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double wr[M], wi[M];
+#pragma unroll
+                for (int q = 0; q < M; ++q) {
+                    wr[q] = Vr[r][perm[q]];
+                    wi[q] = Vi[r][perm[q]];
+                }
+#pragma unroll
+                for (int q = 0; q < M; ++q) {
+                    Vr[r][q] = wr[q];
+                    Vi[r][q] = wi[q];
+                }
+            }
+        }
+    }
+    int kmax = 0;
+    double best = Ar[0][0];
+#pragma unroll
+    for (int p = 1; p < M; ++p)
+        if (Ar[p][p] > best) {
+            best = Ar[p][p];
+            kmax = p;
+        }
+    double vr[3], vi[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        vr[r] = Vr[r][0];
+        vi[r] = Vi[r][0];
+#pragma unroll
+        for (int q = 1; q < M; ++q)
+            if (q == kmax) {
+                vr[r] = Vr[r][q];
+                vi[r] = Vi[r][q];
+            }
+    }
+    // d = v / v[0];  d *= sqrt(M / ||d||_2)     (tester.py:1119-1123); v[0] lives in the even lane
+    const int src_lane = (threadIdx.x & 31) & ~1;
+    const double v0r = __shfl_sync(0xffffffffu, vr[0], src_lane), v0i = __shfl_sync(0xffffffffu, vi[0], src_lane);
+    const double den = v0r * v0r + v0i * v0i;
+    double dr[3], di[3], nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        dr[r] = (vr[r] * v0r + vi[r] * v0i) / den;
+        di[r] = (vi[r] * v0r - vr[r] * v0i) / den;
+        nrm += dr[r] * dr[r] + di[r] * di[r];
+    }
+    const double other = __shfl_xor_sync(0xffffffffu, nrm, 1);
+    nrm = h == 0 ? nrm + other : other + nrm;  // same summation order in both lanes
+    const double g = sqrt((double)M / sqrt(nrm));
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) steer[((size_t)bs * F + f) * M + 3 * h + r] = make_double2(dr[r] * g, di[r] * g);
+    }
+}
+
 template <int M>
 __global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ partial, const double2 *__restrict__ steer,
                                                     float2 *__restrict__ wout, int F, int T, int tsplit, double epsi) {
@@ -200,6 +384,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ pa
         double2 p = make_double2(1.0, 0.0);
         if (f > 0) {
             double cr = 0.0, ci = 0.0;
+#pragma unroll
             for (int m = 0; m < M; ++m) {
                 double2 a = d[(size_t)f * M + m], bq = d[(size_t)(f - 1) * M + m];
                 cr += a.x * bq.x + a.y * bq.y;  // a * conj(b)
@@ -225,6 +410,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ pa
         load_scm<M>(partial, bs, f, F, tsplit, 1, 1.0 / (double)T, Ar, Ai);
         double dr[M], di[M], ur[M], ui[M];
         const double2 P = ph[f];
+#pragma unroll
         for (int m = 0; m < M; ++m) {
             double2 a = d[(size_t)f * M + m];
             dr[m] = a.x * P.x - a.y * P.y;
@@ -233,59 +419,52 @@ __global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ pa
             ui[m] = di[m];
             Ar[m][m] += epsi;  // tester.py:1221
         }
-        // Gaussian elimination with partial pivoting on [A | u]
-#pragma unroll 1
+        // Phi_n + epsi I is Hermitian positive definite, so Gaussian elimination needs no pivoting (the reference's
+        // LAPACK gesv pivots, tester.py:1222; both are exact to rounding, and this one runs in fp64) and preserves the
+        // Hermitian structure of the trailing block: only the upper triangle is touched, every index is a compile-time
+        // constant, and the system stays in registers.
+#pragma unroll
         for (int k = 0; k < M; ++k) {
-            int piv = k;
-            double best = Ar[k][k] * Ar[k][k] + Ai[k][k] * Ai[k][k];
+            const double dk = Ar[k][k];
+            const double inv = 1.0 / (fabs(dk) > 1e-300 ? dk : 1e-300);
+#pragma unroll
             for (int r = k + 1; r < M; ++r) {
-                double v = Ar[r][k] * Ar[r][k] + Ai[r][k] * Ai[r][k];
-                if (v > best) {
-                    best = v;
-                    piv = r;
+                // l = A[r][k] / A[k][k] = conj(A[k][r]) / A[k][k]
+                const double lr = Ar[k][r] * inv, li = -Ai[k][r] * inv;
+#pragma unroll
+                for (int c = r; c < M; ++c) {
+                    const double kr = Ar[k][c], ki = Ai[k][c];
+                    Ar[r][c] -= lr * kr - li * ki;
+                    Ai[r][c] -= lr * ki + li * kr;
                 }
-            }
-            if (piv != k) {
-                for (int c = 0; c < M; ++c) {
-                    double t = Ar[k][c]; Ar[k][c] = Ar[piv][c]; Ar[piv][c] = t;
-                    t = Ai[k][c]; Ai[k][c] = Ai[piv][c]; Ai[piv][c] = t;
-                }
-                double t = ur[k]; ur[k] = ur[piv]; ur[piv] = t;
-                t = ui[k]; ui[k] = ui[piv]; ui[piv] = t;
-            }
-            const double pr = Ar[k][k], pi = Ai[k][k];
-            const double pd = pr * pr + pi * pi;
-            for (int r = k + 1; r < M; ++r) {
-                // l = A[r][k] / A[k][k]
-                const double lr = (Ar[r][k] * pr + Ai[r][k] * pi) / pd;
-                const double li = (Ai[r][k] * pr - Ar[r][k] * pi) / pd;
-                for (int c = k; c < M; ++c) {
-                    Ar[r][c] -= lr * Ar[k][c] - li * Ai[k][c];
-                    Ai[r][c] -= lr * Ai[k][c] + li * Ar[k][c];
-                }
-                ur[r] -= lr * ur[k] - li * ui[k];
-                ui[r] -= lr * ui[k] + li * ur[k];
+                Ai[r][r] = 0.0;
+                const double uk = ur[k], uik = ui[k];
+                ur[r] -= lr * uk - li * uik;
+                ui[r] -= lr * uik + li * uk;
             }
         }
-#pragma unroll 1
+#pragma unroll
         for (int k = M - 1; k >= 0; --k) {
             double sr = ur[k], si = ui[k];
+#pragma unroll
             for (int c = k + 1; c < M; ++c) {
                 sr -= Ar[k][c] * ur[c] - Ai[k][c] * ui[c];
                 si -= Ar[k][c] * ui[c] + Ai[k][c] * ur[c];
             }
-            const double pr = Ar[k][k], pi = Ai[k][k];
-            const double pd = pr * pr + pi * pi;
-            ur[k] = (sr * pr + si * pi) / pd;
-            ui[k] = (si * pr - sr * pi) / pd;
+            const double dk = Ar[k][k];
+            const double inv = 1.0 / (fabs(dk) > 1e-300 ? dk : 1e-300);
+            ur[k] = sr * inv;
+            ui[k] = si * inv;
         }
         // w = u / (d^H u)
         double nr = 0.0, ni = 0.0;
+#pragma unroll
         for (int m = 0; m < M; ++m) {
             nr += dr[m] * ur[m] + di[m] * ui[m];
             ni += dr[m] * ui[m] - di[m] * ur[m];
         }
         const double nd = nr * nr + ni * ni;
+#pragma unroll
         for (int m = 0; m < M; ++m) {
             const double wr = (ur[m] * nr + ui[m] * ni) / nd;
             const double wi = (ui[m] * nr - ur[m] * ni) / nd;
@@ -380,7 +559,10 @@ int run(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, int64_
     MISO_LAUNCHED("scm_kernel");
     // problems are ordered (s, b, f): bs = s*B + b, matching the [S,B,...] outputs
     const int nprob = B * S * F;
-    eig_kernel<M><<<ceil_div(nprob, 64), 64, 0, stream>>>(ws.partial, ws.steer, nprob, F, T, tsplit);
+    if constexpr (M == 6)
+        eig6_kernel<M><<<ceil_div(2 * nprob, 64), 64, 0, stream>>>(ws.partial, ws.steer, nprob, F, T, tsplit);
+    else
+        eig_generic_kernel<M><<<ceil_div(nprob, 64), 64, 0, stream>>>(ws.partial, ws.steer, nprob, F, T, tsplit);
     MISO_LAUNCHED("eig_kernel");
     solve_kernel<M><<<B * S, 256, (size_t)F * sizeof(double2), stream>>>(ws.partial, ws.steer, w, F, T, tsplit, (double)epsi);
     MISO_LAUNCHED("solve_kernel");
