@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(128) tcn_prep_kernel(const __nv_bfloat16 *__re
 // p = PReLU(y); accumulates the gLN statistics of p over (C,T) per sample.
 // One block = one sample x kDwFrames frames x all channels; a thread handles 4 consecutive channels of a frame
 // with float4 loads of the three taps (coalesced along c) and writes 8-byte bf16 hi / lo plane quads.
-constexpr int kDwFrames = 8;
+constexpr int kDwFrames = 16;
+// ELU(alpha = 1): the tensor-core modes store the result as bf16 hi/lo planes (16-17 mantissa bits), so exp through
+// ex2.approx (absolute error ~1e-7) is exact enough there; the fp32 mode keeps expm1f
+__device__ __forceinline__ float dw_elu(float x, bool fast) { return x > 0.f ? x : (fast ? __expf(x) - 1.f : expm1f(x)); }
 __global__ void __launch_bounds__(256) tcn_dw_kernel(const float *__restrict__ U, const double *__restrict__ u_sums,
                                                      double inv_n, float eps, const float *__restrict__ wdw,
                                                      const float *__restrict__ alpha, float *__restrict__ P,
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256) tcn_dw_kernel(const float *__restrict__ U
     }
     __syncthreads();
     const float al = alpha[0];
+    const bool fast = out_planes != 0;
     const int t0 = blockIdx.x * kDwFrames;
     const int c4n = C >> 2;
     const float *ub = U + (size_t)b * T * C;
@@ -122,10 +126,10 @@ __global__ void __launch_bounds__(256) tcn_dw_kernel(const float *__restrict__ U
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tq >= 0 && tq < T) {
                 const float4 u = __ldg(reinterpret_cast<const float4 *>(ub + (size_t)tq * C + c));
-                v.x = elu1(fmaf(u.x, a4.x, b4.x));
-                v.y = elu1(fmaf(u.y, a4.y, b4.y));
-                v.z = elu1(fmaf(u.z, a4.z, b4.z));
-                v.w = elu1(fmaf(u.w, a4.w, b4.w));
+                v.x = dw_elu(fmaf(u.x, a4.x, b4.x), fast);
+                v.y = dw_elu(fmaf(u.y, a4.y, b4.y), fast);
+                v.z = dw_elu(fmaf(u.z, a4.z, b4.z), fast);
+                v.w = dw_elu(fmaf(u.w, a4.w, b4.w), fast);
             }
             return v;
         };
