@@ -52,6 +52,7 @@ struct RsGeom {
     int w_unit, w_off, stage, nstage, box_bytes;
     int off_btab, off_red, off_stage, smem_total, tmem_cols;
     int map5d;
+    int S, TS, Wr;  // packed mode (F + 1 = 64 / 32): an M tile holds the same row of S frame strips of TS = T / S frames
 };
 
 struct RsArgs {
@@ -95,7 +96,7 @@ struct RsPrepArgs {
 // the strips of one CTA: its share [rho, rho_end) of the flattened (sample, column region, frame) row space, cut
 // at (sample, region) boundaries
 struct RsWalk {
-    int rho, rho_end, T, Mr;
+    int rho, rho_end, T, Mr;  // T: rows per unit (frames; packed mode: frames per strip)
     int b, m, t0, TS, nin;
     __device__ __forceinline__ bool next() {
         if (rho >= rho_end) return false;
@@ -111,13 +112,47 @@ struct RsWalk {
 };
 __device__ __forceinline__ RsWalk rs_walk(const RsArgs &a) {
     RsWalk w;
-    const long long R = (long long)a.B * a.g.Mr * a.T;
+    const int TU = a.g.S > 1 ? a.g.TS : a.T;
+    const long long R = (long long)a.B * a.g.Mr * TU;
     w.rho = (int)(R * blockIdx.x / gridDim.x);
     w.rho_end = (int)(R * (blockIdx.x + 1) / gridDim.x);
-    w.T = a.T;
+    w.T = TU;
     w.Mr = a.g.Mr;
     return w;
 }
+
+// The tiles of one strip: up to G consecutive input rows each.  Packed mode: the halo row above the first frame of
+// a strip is the LAST frame of the strip before it (zero for strip 0) and the halo row below the last frame is the
+// FIRST frame of the strip after it (zero for the last strip), i.e. the same TMA box moved by one strip; those two
+// rows are tiles of their own (kind 1 / 2).
+struct RsTiles {
+    int j0, Gk, kind, jcur, nin, G;
+    bool top, bottom;
+    __device__ __forceinline__ void init(const RsArgs &a, const RsWalk &w) {
+        jcur = 0;
+        nin = w.nin;
+        G = a.g.G;
+        top = a.g.S > 1 && w.t0 == 0;
+        bottom = a.g.S > 1 && w.t0 + w.TS == a.g.TS;
+    }
+    __device__ __forceinline__ bool next() {
+        if (jcur >= nin) return false;
+        j0 = jcur;
+        const int lim = bottom ? nin - 1 : nin;
+        if (top && jcur == 0) {
+            Gk = 1;
+            kind = 1;
+        } else if (jcur >= lim) {
+            Gk = 1;
+            kind = 2;
+        } else {
+            Gk = min(G, lim - jcur);
+            kind = 0;
+        }
+        jcur += Gk;
+        return true;
+    }
+};
 
 __device__ __forceinline__ float rs_elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
@@ -184,7 +219,10 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             while (w.next()) {
                 const __nv_bfloat16 *wsrc = a.wimg + (size_t)w.b * a.wimg_bstride;
                 const int f0 = 128 * w.m - 1;
-                for (int j0 = 0; j0 < w.nin; j0 += G) {
+                RsTiles tl;
+                tl.init(a, w);
+                while (tl.next()) {
+                    const int j0 = tl.j0;
                     const int tin = w.t0 - 1 + j0;
                     for (int c = 0; c < g.nchunk; ++c) {
                         rs_trace(a.trace, 0, ntr, 100 + c);
@@ -198,7 +236,10 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                         for (int sp = 0; sp < g.nsp; ++sp) {
                             const CUtensorMap *tm = sp == 0 ? &tm_hi : &tm_lo;
                             const uint32_t dst = sa + (uint32_t)(sp * g.GS);
-                            if (g.map5d)
+                            if (g.S > 1)  // {bins, strip, frame in strip, plane, sample}
+                                tma_load_5d(dst, tm, full, -2, tl.kind == 1 ? -1 : (tl.kind == 2 ? 1 : 0),
+                                            tl.kind == 1 ? g.TS - 1 : (tl.kind == 2 ? 0 : tin), pl, w.b);
+                            else if (g.map5d)
                                 tma_load_5d(dst, tm, full, 0, f0, tin, pl, w.b);
                             else
                                 tma_load_4d(dst, tm, full, 2 * f0, tin, pl, w.b);
@@ -231,8 +272,10 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             int s = 0, ph = 0, k = 0, Pcur = 0, ntr = 0;  // Pcur: ring position of the slot two rows above the tile's first input row
             RsWalk w = rs_walk(a);
             while (w.next()) {
-                for (int j0 = 0; j0 < w.nin; j0 += G, ++k) {
-                    const int Gk = min(G, w.nin - j0);
+                RsTiles tl;
+                tl.init(a, w);
+                for (; tl.next(); ++k) {
+                    const int j0 = tl.j0, Gk = tl.Gk;
                     uint32_t rd[kRsMaxG], rb[kRsMaxG], rid[kRsMaxG];  // per row: accumulator address, weight row offset, idesc
 #pragma unroll
                     for (int i = 0; i < kRsMaxG; ++i) {
@@ -325,12 +368,16 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
                 prev_b = b;
             }
-            const int f = 128 * w.m + quad * 32 + lane;
+            const int seg = g.S > 1 ? (quad * 32 + lane) / g.Wr : 0;  // packed mode: which strip this lane belongs to
+            const int f = g.S > 1 ? (quad * 32 + lane) - seg * g.Wr : 128 * w.m + quad * 32 + lane;
+            const int tseg = seg * g.TS;
             const bool valid = f < a.F;
             const int fmask = 7 & ~(f == 0 ? 1 : 0) & ~(f == a.F - 1 ? 4 : 0);
             __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
-            for (int j0 = 0; j0 < w.nin; j0 += G, ++k) {
-                const int Gk = min(G, w.nin - j0);
+            RsTiles tl;
+            tl.init(a, w);
+            for (; tl.next(); ++k) {
+                const int j0 = tl.j0, Gk = tl.Gk;
                 const int o_lo = max(0, j0 - 2), o_hi = min(w.TS, j0 + Gk - 2);
                 if (tracer) rs_trace(a.trace, 2, ntr, 1);
                 mbar_wait(bar_tfull + 8 * (k & 1), (k >> 1) & 1);
@@ -341,7 +388,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 #pragma unroll
                     for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
                     for (int o = o_lo + half; o < o_hi; o += 2) {
-                        const int t = w.t0 + o;
+                        const int t = tseg + w.t0 + o;
                         const int tmask = 7 & ~(t == 0 ? 1 : 0) & ~(t == a.T - 1 ? 4 : 0);
                         int x = xo + o - o_lo;
                         if (x >= L) x -= L;
@@ -548,7 +595,12 @@ int rs_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 bool rs_shape_ok(const ConvArgs &a) {
     if (a.transposed || a.KT != 3 || a.KF != 3 || a.stride_f != 1 || a.pad_t != 1 || a.pad_f != 1) return false;
-    if (a.Fin != a.Fout || (a.Fin != 127 && a.Fin != 255)) return false;
+    if (a.Fin != a.Fout || (a.Fin != 127 && a.Fin != 255 && a.Fin != 63 && a.Fin != 31)) return false;
+    if (a.Fin < 127) {  // packed strips: T must split into 128 / (F + 1) equal strips
+        static const bool packed_off = getenv("MISO_RS_PACKED") && atoi(getenv("MISO_RS_PACKED")) == 0;
+        const int S = 128 / (a.Fin + 1);
+        if (packed_off || a.T % S || a.T / S < 4) return false;
+    }
     if (a.in_layout != LAYOUT_PLANES || a.out_layout != LAYOUT_PLANES) return false;
     if (a.in_ctot % 8 || a.in_coff % 8 || a.out_ctot % 8 || a.out_coff % 8 || a.cout % 8) return false;
     if (a.resid || a.norm_mode == NORM_GLN) return false;
@@ -564,9 +616,12 @@ bool make_rs_geom(const ConvArgs &a, int split, RsGeom &g) {
     static const int max_nc = getenv("MISO_RS_MAXNC") ? atoi(getenv("MISO_RS_MAXNC")) : 64;
     if (g.Nc > max_nc) return false;
     g.N3 = 3 * g.Nc;
-    g.Mr = (a.Fin + 1) / 128;
+    g.Mr = std::max(1, (a.Fin + 1) / 128);
     g.map5d = g.Mr == 2;
     g.pitch = g.map5d ? 130 : 128;
+    g.Wr = std::min(128, a.Fin + 1);
+    g.S = 128 / g.Wr;
+    g.TS = a.T / g.S;
     g.nplanes = (a.cin + 7) / 8;
     g.nunit = (g.nplanes + 1) / 2;
     g.w_unit = 3 * g.nsp * 2 * g.N3 * 16;
@@ -613,7 +668,16 @@ int rs_encode_maps(const ConvArgs &a, const RsGeom &g, CUtensorMap *hi, CUtensor
         CUtensorMap *tm = sp == 0 ? hi : lo;
         void *addr = base + (sp ? a.in_lo_off : 0);
         CUresult r;
-        if (!g.map5d) {
+        if (g.S > 1) {
+            // packed strips: {bins (8-byte units), strip, frame in strip, plane, sample}; a box holds the same G frames of
+            // S consecutive strips, stored [plane][frame][strip][Wr pixels] = one M tile per frame
+            cuuint64_t dims[5] = {2 * F, (cuuint64_t)g.S, (cuuint64_t)g.TS, CGv, (cuuint64_t)a.B};
+            cuuint64_t strides[4] = {(cuuint64_t)g.TS * F * 16, F * 16, T * F * 16, 2 * CG * T * F * 16};
+            cuuint32_t box[5] = {(cuuint32_t)(2 * g.Wr), (cuuint32_t)g.S, (cuuint32_t)g.G, (cuuint32_t)(2 * g.kper), 1};
+            cuuint32_t es[5] = {1, 1, 1, 1, 1};
+            r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, addr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else if (!g.map5d) {
             cuuint64_t dims[4] = {2 * F, T, CGv, (cuuint64_t)a.B};
             cuuint64_t strides[3] = {F * 16, T * F * 16, 2 * CG * T * F * 16};
             cuuint32_t box[4] = {(cuuint32_t)(2 * g.pitch), (cuuint32_t)g.G, (cuuint32_t)(2 * g.kper), 1};
@@ -684,8 +748,8 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     }
     static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
     if (debug)
-        fprintf(stderr, "conv_rs: cin=%d cout=%d F=%d | Nc=%d L=%d G=%d Mr=%d pitch=%d kper=%d nchunk=%d nstage=%d stage=%dB tmem=%d smem=%d\n", a.cin,
-                a.cout, a.Fin, g.Nc, g.L, g.G, g.Mr, g.pitch, g.kper, g.nchunk, g.nstage, g.stage, g.tmem_cols, g.smem_total);
+        fprintf(stderr, "conv_rs: cin=%d cout=%d F=%d | S=%d Nc=%d L=%d G=%d Mr=%d pitch=%d kper=%d nchunk=%d nstage=%d stage=%dB tmem=%d smem=%d\n", a.cin,
+                a.cout, a.Fin, g.S, g.Nc, g.L, g.G, g.Mr, g.pitch, g.kper, g.nchunk, g.nstage, g.stage, g.tmem_cols, g.smem_total);
     CUtensorMap tm_hi, tm_lo;
     int rc = rs_encode_maps(a, g, &tm_hi, &tm_lo);
     if (rc) return rc;
@@ -735,7 +799,7 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     k.use_lo = a.use_lo;
     k.elu = a.elu;
     k.trace = (g_rs_trace && a.cin == g_rs_trace_cin && a.Fin == g_rs_trace_fin) ? g_rs_trace : nullptr;
-    const long long rows = (long long)a.B * g.Mr * a.T;
+    const long long rows = (long long)a.B * g.Mr * (g.S > 1 ? g.TS : a.T);
     dim3 grid((unsigned)std::min<long long>(148, std::max<long long>(1, rows / 2)), 1, 1);
     if (split == 3)
         conv_rs_kernel<3><<<grid, kRsThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);

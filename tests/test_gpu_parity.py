@@ -195,6 +195,24 @@ def test_net_paper_layout_vs_oracle():
     assert rel_err(y, ref) < 2e-4
 
 
+@pytest.mark.parametrize("B,T", [(2, 40), (3, 100), (1, 36)])
+def test_net_row_streaming_convs_vs_oracle(B, T):
+    """conv_rs.cu (frame taps merged into N): PAPER layout in the tensor-core mode so that the wide stages (255 and 127
+    bins: one or two column regions), the packed stages (63 and 31 bins: 2 / 4 frame strips per M tile, T divisible
+    by 4) and CTA ranges that start / end inside a strip or cross samples are all exercised."""
+    from misonet_b200 import synth
+    from oracle import miso_net_torch as mnt
+    m, cfg, sd = _model("miso1", 5, layout="PAPER")
+    m.conv_mode = "bf16x3"
+    mix = synth.random_spec(7, (B, 6, T, 257))
+    ref = mnt.miso1_forward(sd, cfg, torch.from_numpy(mix)).numpy()
+    with torch.no_grad():
+        y = m(torch.from_numpy(mix).cuda()).cpu().numpy()
+    e = rel_err(y, ref)
+    print(f"PAPER layout B={B} T={T} bf16x3 rel err", e)
+    assert e < 2e-4 and e < REQUIRED_TOL
+
+
 def test_net_batch_invariance_and_chunking():
     """A sample's output must not depend on what else is in the batch (no cross-sample coupling:
     InstanceNorm/gLN only), nor on the workspace-driven batch chunking."""
