@@ -208,6 +208,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    pdl_trigger();
+    pdl_wait();  // everything above overlapped the previous kernel's tail; its results are needed from here on
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
@@ -510,6 +512,8 @@ __device__ __forceinline__ float2 rs_affine(const RsPrepArgs &p, int b, int ci) 
 
 __global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
     extern __shared__ float sh[];
+    pdl_trigger();
+    pdl_wait();  // the statistics come from the previous conv, which also still reads the scratch this kernel rewrites
     const int nimg = p.B * p.nunit;
     const int N3 = 3 * p.Nc;
     if ((int)blockIdx.x < nimg) {
@@ -776,7 +780,7 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.nsplit = nsplit;
     const size_t prep_smem = (size_t)(kRsBiasCi + 8 * 9 * g.Nc) * sizeof(float);
     prof_begin(stream);
-    conv_rs_prep_kernel<<<a.B * g.nunit + a.B * nsplit, 256, prep_smem, stream>>>(p);
+    MISO_CUDA(launch_pdl(conv_rs_prep_kernel, dim3(a.B * g.nunit + a.B * nsplit), dim3(256), prep_smem, stream, p));
     MISO_LAUNCHED("conv_rs_prep_kernel");
 
     RsArgs k{};
@@ -802,9 +806,9 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     const long long rows = (long long)a.B * g.Mr * (g.S > 1 ? g.TS : a.T);
     dim3 grid((unsigned)std::min<long long>(148, std::max<long long>(1, rows / 2)), 1, 1);
     if (split == 3)
-        conv_rs_kernel<3><<<grid, kRsThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+        MISO_CUDA(launch_pdl(conv_rs_kernel<3>, grid, dim3(kRsThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
     else
-        conv_rs_kernel<1><<<grid, kRsThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+        MISO_CUDA(launch_pdl(conv_rs_kernel<1>, grid, dim3(kRsThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
     {
         const double pix = (double)a.B * a.T * a.Fout;
         const double flops = 2.0 * pix * a.cin * a.cout * 9;

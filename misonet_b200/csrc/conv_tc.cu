@@ -190,6 +190,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();  // everything above overlapped the previous kernel's tail; its results are needed from here on
     // contiguous tile range per CTA: consecutive tiles share the sample (weight image, bias table) and their halos in L2
     const int tiles_per_cta = (g.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tile_lo = (int)blockIdx.x * tiles_per_cta, tile_hi = min(tile_lo + tiles_per_cta, g.ntiles);
@@ -578,6 +580,8 @@ __device__ __forceinline__ float2 prep_affine(const PrepArgs &p, int b, int ci) 
 
 __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
     extern __shared__ float sh[];
+    pdl_trigger();
+    pdl_wait();  // the statistics come from the previous conv, which also still reads the scratch this kernel rewrites
     const int nimg = (p.shared_w ? 1 : p.B) * p.nunit;
     if ((int)blockIdx.x < nimg) {
         const int b = blockIdx.x / p.nunit, chunk = blockIdx.x - b * p.nunit;  // chunk = 16-channel K unit
@@ -994,7 +998,7 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     for (int i = 0; i < g.ntap; ++i) p.tapk[i] = g.tapk[i];
     const size_t prep_smem = (size_t)(kBiasCi + 8 * 9 * g.N) * sizeof(float);
     prof_begin(stream);
-    conv_tc_prep_kernel<<<(shared_w ? 1 : a.B) * g.nunit + a.B * g.nNt * p.nsplit, 256, prep_smem, stream>>>(p);
+    MISO_CUDA(launch_pdl(conv_tc_prep_kernel, dim3((shared_w ? 1 : a.B) * g.nunit + a.B * g.nNt * p.nsplit), dim3(256), prep_smem, stream, p));
     MISO_LAUNCHED("conv_tc_prep_kernel");
 
     TcArgs k{};
@@ -1038,14 +1042,14 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     static const int var = getenv("MISO_TC_VAR") ? atoi(getenv("MISO_TC_VAR")) : 0;
     if (split == 3) {
         if (var == 0)
-            conv_tc_kernel<3, 0><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+            MISO_CUDA(launch_pdl(conv_tc_kernel<3, 0>, grid, dim3(kThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
         else
-            conv_tc_kernel<3, 1><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+            MISO_CUDA(launch_pdl(conv_tc_kernel<3, 1>, grid, dim3(kThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
     } else {
         if (var == 0)
-            conv_tc_kernel<1, 0><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+            MISO_CUDA(launch_pdl(conv_tc_kernel<1, 0>, grid, dim3(kThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
         else
-            conv_tc_kernel<1, 1><<<grid, kThreads, g.smem_total, stream>>>(tm_hi, tm_lo, k);
+            MISO_CUDA(launch_pdl(conv_tc_kernel<1, 1>, grid, dim3(kThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
     }
     {
         const double pix = (double)a.B * a.T * (a.transposed ? a.Fin : a.Fout);

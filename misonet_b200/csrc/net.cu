@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(256) tcn_dw_kernel(const float *__restrict__ U
                                                      double *__restrict__ g_sums, int T, int C, int dil, int out_planes,
                                                      int use_lo) {
     extern __shared__ float dw_sh[];  // [C] scale, [C] shift, [3][C] taps
+    pdl_trigger();
+    pdl_wait();  // the state and its statistics come from the previous pointwise conv, which still reads P
     float *sc = dw_sh, *sf = dw_sh + C, *wt = dw_sh + 2 * C;
     const int b = blockIdx.y;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -699,8 +701,9 @@ int Walker::run(const void *d_x, float *d_y) {
                 double *gs = half == 0 ? pl.g1[k] : pl.g2[k];
                 const bool tc_pw = (dry || n->mode != 0) && C % 8 == 0;
                 if (!dry) {
-                    tcn_dw_kernel<<<dim3(ceil_div(T, kDwFrames), B), 256, 5 * C * sizeof(float), st>>>(
-                        u, us, inv_T, kInEps, n->params[h.dw].d, n->params[h.alpha].d, pl.P, gs, T, C, dil, tc_pw ? 1 : 0, use_lo);
+                    MISO_CUDA(launch_pdl(tcn_dw_kernel, dim3(ceil_div(T, kDwFrames), B), dim3(256), 5 * C * sizeof(float), st, u, us, inv_T,
+                                         kInEps, (const float *)n->params[h.dw].d, (const float *)n->params[h.alpha].d, pl.P, gs, T, C, dil,
+                                         tc_pw ? 1 : 0, use_lo));
                     MISO_LAUNCHED("tcn_dw_kernel");
                 }
                 ConvArgs a{};

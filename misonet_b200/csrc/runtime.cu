@@ -2,9 +2,17 @@
 #include <mutex>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace miso {
+
+bool pdl_enabled() {
+    static const bool on = getenv("MISO_PDL") && atoi(getenv("MISO_PDL")) != 0;  // measured on B200: 11.84 ms/step with, 11.54 without -> off by default
+    return on;
+}
+
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launch_count{0};

@@ -79,6 +79,8 @@ tcn_pw_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();  // the set-up above overlapped the depthwise kernel's tail
 
     if (warp == 0) {
         if (elect_one()) {
@@ -388,9 +390,9 @@ int launch_tcn_pw(const TcnPwArgs &p, int split, cudaStream_t stream) {
     dim3 grid(p.B * k.t_tiles, g.NH);
     prof_begin(stream);
     if (split == 3)
-        tcn_pw_kernel<3><<<grid, kPwThreads, g.smem_total, stream>>>(tm[0], tm[1], k);
+        MISO_CUDA(launch_pdl(tcn_pw_kernel<3>, grid, dim3(kPwThreads), (size_t)g.smem_total, stream, tm[0], tm[1], k));
     else
-        tcn_pw_kernel<1><<<grid, kPwThreads, g.smem_total, stream>>>(tm[0], tm[1], k);
+        MISO_CUDA(launch_pdl(tcn_pw_kernel<1>, grid, dim3(kPwThreads), (size_t)g.smem_total, stream, tm[0], tm[1], k));
     prof_end(stream, 2.0 * p.B * p.T * (double)p.C * p.C, (double)p.B * p.T * p.C * ((split == 3 ? 4.0 : 2.0) + 4.0 + (p.resid ? 4.0 : 0.0)),
              MISO_PROF_CONV_TC);
     MISO_LAUNCHED("tcn_pw_kernel");
