@@ -47,8 +47,10 @@ WORKLOADS = {
                          desc="STFT->MISO1x6->align->MVDRx2->MISO3x2, batch 32 per GPU (BASELINE configs[2], REF shape)"),
 }
 PROF_FAMILIES = {0: "conv_fp32_kernel (fp32 FMA implicit-GEMM conv / deconv / pointwise)",
-                 1: "conv_tc_kernel (tcgen05 implicit-GEMM 3x3 conv, TMEM accumulators)",
-                 2: "tcn kernels", 3: "mvdr kernels"}
+                 1: "conv_tc_kernel (tcgen05 implicit-GEMM 3x3 (de)conv, shifted-descriptor im2col: strided / transposed / narrow stages)",
+                 2: "tcn_pw_kernel (tcgen05 pointwise convs of the TCN)", 3: "mvdr kernels",
+                 5: "conv_*_prep_kernel (per-sample weight images and border-bias sums of the tensor-core convs)",
+                 4: "conv_rs_kernel (row-streaming tcgen05 3x3 conv, frame taps merged into N: the DenseBlock convs)"}
 CONV_MODES = {"fp32": ("f32", "fp32 FMA everywhere (reference-grade, ~2e-6 rel. error)"),
               "bf16x3": ("bf16x3", "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (parity-grade, ~2e-5 rel. error)"),
               "bf16": ("bf16", "tcgen05 bf16 operands, fp32 accumulate (throughput mode, ~1e-2 rel. error: outside north_star's 1e-3)")}
@@ -272,13 +274,17 @@ def run_ours(args, wl, rank, world, local):
     conv_ms, conv_flops, conv_launches = fams[dom]["ms"], fams[dom]["flops"], fams[dom]["launches"]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_b_ncu_traffic_conv_tc_bf16x3.json")
-    if args.workload == "miso1_paper" and args.conv_mode == "bf16x3" and args.batch == 0 and dom.startswith("conv_tc") and os.path.isfile(tp):
+    tp = os.path.join(ROOT, "profiles", "r1_c_ncu_traffic_conv_rs_bf16x3.json")
+    if args.workload == "miso1_paper" and args.conv_mode == "bf16x3" and args.batch == 0 and dom.startswith("conv_rs") and os.path.isfile(tp):
         try:
             traffic = float(json.load(open(tp))["family_dram_bytes_per_launch"])
-            traffic_src = "profiles/r1_b_ncu_traffic_conv_tc_bf16x3.json (dram__bytes_read.sum + dram__bytes_write.sum of this workload's conv_tc + prep launches, per conv launch)"
+            traffic_src = "profiles/r1_c_ncu_traffic_conv_rs_bf16x3.json (dram__bytes_read.sum + dram__bytes_write.sum of this workload's conv_rs + prep launches, per conv launch)"
         except Exception:
             pass
+    tc = [v for k, v in fams.items() if k.split()[0] in ("conv_tc_kernel", "conv_rs_kernel", "tcn_pw_kernel")]
+    tc_ms, tc_fl = sum(v["ms"] for v in tc), sum(v["flops"] for v in tc)
+    all_tc = {"ms_per_step": tc_ms / args.steps, "tflops": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
+              "frac": tc_fl / (tc_ms * 1e-3) / 1e12 / pk["bf16_tflops"] if tc_ms > 0 else 0.0, "share_of_step": tc_ms / ms if ms > 0 else None}
     fam_report = {k: {"ms_per_step": v["ms"] / args.steps, "share_of_step": v["ms"] / ms if ms > 0 else None,
                       "launches_per_step": v["launches"] // max(args.steps, 1),
                       "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0,
@@ -308,10 +314,14 @@ def run_ours(args, wl, rank, world, local):
                      "launches": int(conv_launches), "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms if ms > 0 else None,
                      "families": fam_report,
-                     "note": "algorithmic 2*MAC of the launches of the dominant kernel family / summed CUDA-event time of "
-                             "those launches (event-record nodes around every conv launch of the replayed CUDA graph, a second "
-                             "pass of the same steps right after the timed one; bf16x3 issues 2 MMAs of width 2N+N per "
-                             "algorithmic MAC block, so its ceiling is about 0.18 of the bf16 peak at N=32)"},
+                     "all_tensor_core_kernels": all_tc,
+                     "note": "algorithmic 2*MAC of the launches of the dominant kernel / summed "
+                             "CUDA-event time of those launches (event-record nodes around every conv launch of the replayed CUDA "
+                             "graph, a second pass of the same steps right after the timed one; the per-sample operand preparation launches are their "
+                             "own entry under families).  bf16x3 spends 3 MMAs per "
+                             "algorithmic product and an SS-mode MMA is shared-memory-operand bound at (4096 + 32 N) / 128 cycles, "
+                             "so the kernel's own ceiling is 0.29 of the bf16 peak at N = 3 cout = 96 (0.86 in bf16 mode); "
+                             "all_tensor_core_kernels aggregates every tcgen05 kernel of the step"},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, steps=1)

@@ -57,8 +57,10 @@ uint64_t miso_launch_count(void);
 #define MISO_PROF_ALL (-1)
 #define MISO_PROF_CONV_FP32 0 /* fp32 FMA implicit-GEMM (de)conv / pointwise kernels */
 #define MISO_PROF_CONV_TC 1   /* tcgen05 implicit-GEMM conv kernels */
-#define MISO_PROF_TCN 2       /* fused TCN kernels */
+#define MISO_PROF_TCN 2       /* tcgen05 pointwise convs of the TCN */
 #define MISO_PROF_MVDR 3      /* MVDR kernels */
+#define MISO_PROF_PREP 5      /* per-sample operand preparation of the tensor-core convs (weight images, border-bias sums) */
+#define MISO_PROF_CONV_RS 4   /* row-streaming tcgen05 conv (frame taps merged into N): the DenseBlock convs */
 int miso_prof_enable(int on);
 /* collects (and clears) the records of one family, or of all with MISO_PROF_ALL */
 int miso_prof_collect(int family, double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches);

@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
         __syncthreads();
         const size_t unit_elems = (size_t)3 * p.nsp * 2 * N3 * 8;
         __nv_bfloat16 *img = p.wimg + ((size_t)b * p.nunit + unit) * unit_elems;
+#pragma unroll 3
         for (int i = threadIdx.x; i < 3 * 2 * N3; i += blockDim.x) {
             const int n = i % N3;
             const int r = i / N3;
@@ -560,13 +561,18 @@ __global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
         for (int i = threadIdx.x; i < nparts * 9 * p.Nc; i += blockDim.x) wb[i] = 0.f;
         __syncthreads();
         if (part < nparts && n < p.cout) {
-            for (int k = 0; k < 9; ++k) {
-                const float *w = p.w + ((size_t)k * p.cin + ci0) * p.cout_pad + n;
-                float acc = 0.f;
-#pragma unroll 8
-                for (int ci = part; ci < nci; ci += nparts) acc = fmaf(__ldg(w + (size_t)ci * p.cout_pad), shift[ci], acc);
-                wb[(part * 9 + k) * p.Nc + n] = acc;
+            // all taps' loads in flight at once (the weights are cold in L2 behind the previous conv's activation stream)
+            float acc[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+#pragma unroll 2
+            for (int ci = part; ci < nci; ci += nparts) {
+                const float sv = shift[ci];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc[k] = fmaf(__ldg(p.w + ((size_t)k * p.cin + ci0 + ci) * p.cout_pad + n), sv, acc[k]);
             }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) wb[(part * 9 + k) * p.Nc + n] = acc[k];
         }
         __syncthreads();
         float *dst = p.btab + ((size_t)b * p.nsplit + split) * 9 * p.Nc;
@@ -781,7 +787,9 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     const size_t prep_smem = (size_t)(kRsBiasCi + 8 * 9 * g.Nc) * sizeof(float);
     prof_begin(stream);
     MISO_CUDA(launch_pdl(conv_rs_prep_kernel, dim3(a.B * g.nunit + a.B * nsplit), dim3(256), prep_smem, stream, p));
+    prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_rs_prep_kernel");
+    prof_begin(stream);
 
     RsArgs k{};
     k.g = g;
@@ -813,7 +821,7 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
         const double pix = (double)a.B * a.T * a.Fout;
         const double flops = 2.0 * pix * a.cin * a.cout * 9;
         const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
-        prof_end(stream, flops, bytes, MISO_PROF_CONV_TC);
+        prof_end(stream, flops, bytes, MISO_PROF_CONV_RS);
     }
     MISO_LAUNCHED("conv_rs_kernel");
     return MISO_OK;

@@ -593,6 +593,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
         __syncthreads();
         const int per_nt = p.ntap * 2 * p.N;  // (tap, kg, n) triples per N tile
         const size_t w_stage = (size_t)p.nsp * p.ntap * 2 * p.N * 8;
+#pragma unroll 3
         for (int i = threadIdx.x; i < p.nNt * per_nt; i += blockDim.x) {
             const int nt = i / per_nt;
             int r = i - nt * per_nt;
@@ -637,13 +638,20 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
         __syncthreads();
         const int co = nt * p.N + n;
         if (part < nparts && co < p.cout) {
-            for (int k = 0; k < ntaps; ++k) {
-                const float *w = p.w + ((size_t)k * p.cin + ci0) * p.cout_pad + co;
-                float acc = 0.f;
-#pragma unroll 8
-                for (int ci = part; ci < nci; ci += nparts) acc = fmaf(__ldg(w + (size_t)ci * p.cout_pad), shift[ci], acc);
-                wb[(part * ntaps + k) * p.N + n] = acc;
+            // all taps' loads in flight at once (the weights are cold in L2 behind the previous conv's activation stream)
+            float acc[kMaxTaps];
+#pragma unroll
+            for (int k = 0; k < kMaxTaps; ++k) acc[k] = 0.f;
+#pragma unroll 2
+            for (int ci = part; ci < nci; ci += nparts) {
+                const float sv = shift[ci];
+#pragma unroll
+                for (int k = 0; k < kMaxTaps; ++k)
+                    if (k < ntaps) acc[k] = fmaf(__ldg(p.w + ((size_t)k * p.cin + ci0 + ci) * p.cout_pad + co), sv, acc[k]);
             }
+#pragma unroll
+            for (int k = 0; k < kMaxTaps; ++k)
+                if (k < ntaps) wb[(part * ntaps + k) * p.N + n] = acc[k];
         }
         __syncthreads();
         float *dst = p.btab + (((size_t)b * p.nNt + nt) * p.nsplit + split) * 9 * p.N;
@@ -999,7 +1007,9 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     const size_t prep_smem = (size_t)(kBiasCi + 8 * 9 * g.N) * sizeof(float);
     prof_begin(stream);
     MISO_CUDA(launch_pdl(conv_tc_prep_kernel, dim3((shared_w ? 1 : a.B) * g.nunit + a.B * g.nNt * p.nsplit), dim3(256), prep_smem, stream, p));
+    prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_tc_prep_kernel");
+    prof_begin(stream);
 
     TcArgs k{};
     k.g = g;
