@@ -79,6 +79,19 @@ int miso_stft_num_frames(int n_samples, int nperseg, int hop);
 int miso_stft_fwd(const float *d_x, int64_t sb, int64_t sn, int64_t sm, void *d_out, int B, int N, int M,
                   int nperseg, int hop, void *stream);
 
+/* ---- ISTFT back end ----------------------------
+ * replaces Tester_*.ISTFT applied to ``spec * scale`` (tester.py:186-198, 545-556, 979-990; call sites
+ * tester.py:949-957): scipy.signal.istft(window='hann', nperseg, noverlap) with its defaults
+ * (one-sided input, boundary trimmed by nperseg/2 both sides, division by the summed squared window)
+ * of the spectrogram times scale = 1/sum(window), i.e. the exact inverse of miso_stft_fwd.
+ *   d_spec : complex64, bin (s, t, f) of signal s at d_spec[s*ss + t*st + f*sf]  (element strides)
+ *   d_out  : fp32 [S, miso_istft_num_samples(T, nperseg, hop)]
+ *   d_ws   : miso_istft_workspace_bytes(S, T, nperseg) bytes (the windowed frames before overlap-add) */
+int miso_istft_num_samples(int T, int nperseg, int hop);
+size_t miso_istft_workspace_bytes(int S, int T, int nperseg);
+int miso_istft_fwd(const void *d_spec, int64_t ss, int64_t st, int64_t sf, float *d_out, int S, int T, int nperseg,
+                   int hop, void *d_ws, size_t ws_bytes, void *stream);
+
 /* ---- N1/N2: MISO_1 / MISO_3 network body --------------------------------------
  * replaces model.MISO_1 / model.MISO_3 (model.py:8-111, 282-395) and the layers they
  * are built from (model.py:401-632).  The handle is created from the constructor

@@ -4,7 +4,7 @@ alignment / uPIT decisions, MVDR) behind the call signatures of yuhogun0908/MISO
 Importing the package does not load the CUDA library; the first call does, and raises if
 it is missing (there is no CPU or stock-PyTorch fallback)."""
 __all__ = ["MISO_1", "MISO_3", "Apply_Beamforming", "mvdr", "miso1_inference", "align_to_clean", "loss_uPIT",
-           "loss_Enhance", "stft", "MisoBfMiso", "B200HotPath"]
+           "loss_Enhance", "stft", "istft", "MisoBfMiso", "B200HotPath", "separate_recording"]
 
 
 def __getattr__(name):
@@ -23,6 +23,12 @@ def __getattr__(name):
     if name == "stft":
         from . import audio
         return audio.stft
+    if name == "istft":
+        from . import audio
+        return audio.istft
+    if name == "separate_recording":
+        from . import continuous
+        return continuous.separate_recording
     if name == "MisoBfMiso":
         from . import pipeline
         return pipeline.MisoBfMiso

@@ -25,6 +25,10 @@ SIGNATURES = {
     "miso_prof_dump": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int), c_int]),
     "miso_stft_num_frames": (c_int, [c_int, c_int, c_int]),
     "miso_stft_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "miso_istft_num_samples": (c_int, [c_int, c_int, c_int]),
+    "miso_istft_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "miso_istft_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                               c_void_p]),
     "miso_net_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int]),
     "miso_net_destroy": (c_int, [c_void_p]),
     "miso_net_num_params": (c_int, [c_void_p]),

@@ -49,3 +49,10 @@ class B200HotPath:
             x = x.T
         spec = audio.stft(x.to(self._b200_device()), self.nperseg, self.noverlap)     # [M,T,F], unnormalised
         return (spec * float(self.scale)).permute(0, 2, 1).cpu()
+
+    def ISTFT(self, FT_sig):
+        """tester.py:979-990: [F,T] (or [C,F,T]) spectrogram already multiplied by self.scale -> numpy [T_samples]
+        (or [C,T_samples]), i.e. scipy.signal.istft with the tester's window / nperseg / noverlap."""
+        z = torch.as_tensor(np.asarray(FT_sig)) if not torch.is_tensor(FT_sig) else FT_sig
+        z = z.to(self._b200_device()).to(torch.complex64) / float(self.scale)      # back to the unnormalised spectrum
+        return audio.istft(z.transpose(-1, -2), self.nperseg, self.noverlap).cpu().numpy()

@@ -54,6 +54,22 @@ def golden_stft():
                         params=np.array([[c[2], c[3]] for c in cases]))
 
 
+def golden_istft():
+    """Tester_Enhance.ISTFT of ``spec^T * scale`` exactly as called at tester.py:949-957."""
+    out = {}
+    params = []
+    for i, (t_frames, nperseg, noverlap) in enumerate([(20, 256, 192), (33, 256, 192), (12, 512, 384)]):
+        host = ref_import.make_stft_host(nperseg, noverlap)
+        rng = np.random.default_rng(300 + i)
+        f_bins = nperseg // 2 + 1
+        spec = (rng.standard_normal((t_frames, f_bins)) + 1j * rng.standard_normal((t_frames, f_bins))).astype(np.complex64)
+        wav = host.ISTFT(torch.permute(torch.from_numpy(spec), [1, 0]) * host.scale)   # [F,T] in, tester.py:979-990
+        out[f"spec{i}"] = spec
+        out[f"wav{i}"] = np.asarray(wav, dtype=np.float32)
+        params.append([nperseg, noverlap])
+    np.savez_compressed(os.path.join(OUT, "istft_ref.npz"), params=np.array(params), **out)
+
+
 def golden_net():
     for kind, wseed in (("miso1", 0), ("miso3", 1)):
         mod, cfg, sd = build_reference_model(kind, wseed)
@@ -134,6 +150,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(OUT, exist_ok=True)
     golden_stft()
+    golden_istft()
     golden_mvdr()
     golden_losses()
     golden_net()

@@ -58,6 +58,31 @@ def stft(time_sig, nperseg=256, noverlap=192):
     return np.ascontiguousarray(np.transpose(spec, (2, 0, 1))).astype(np.complex64)
 
 
+def istft(spec_tf, nperseg=256, noverlap=192):
+    """Tester_*.ISTFT applied to ``spec * scale`` (tester.py:979-990, call sites 949-957): scipy.signal.istft with its
+    defaults -- per frame irfft(Z * sum(w)) (scaling='spectrum'; times scale = 1/sum(w) that is irfft of the
+    unnormalised spectrum), synthesis window, overlap-add, division by the overlap-added squared window where it
+    exceeds 1e-10, and nperseg//2 samples trimmed at both ends (boundary=True).
+
+    spec_tf : complex [T, F] (one signal; the reference passes the [F, T] transpose)
+    returns : float32 [(T - 1) * hop]"""
+    z = np.asarray(spec_tf)
+    t_frames, f_bins = z.shape
+    assert f_bins == nperseg // 2 + 1
+    hop = nperseg - noverlap
+    w = hann_periodic(nperseg)
+    xs = np.fft.irfft(z.astype(np.complex128), n=nperseg, axis=1) * w[None, :]
+    total = nperseg + (t_frames - 1) * hop
+    x = np.zeros(total)
+    norm = np.zeros(total)
+    for t in range(t_frames):
+        x[t * hop:t * hop + nperseg] += xs[t]
+        norm[t * hop:t * hop + nperseg] += w * w
+    half = nperseg // 2
+    x, norm = x[half:total - half], norm[half:total - half]
+    return (x / np.where(norm > 1e-10, norm, 1.0)).astype(np.float32)
+
+
 def stft_num_frames(n_samples, nperseg=256, noverlap=192):
     hop = nperseg - noverlap
     total = n_samples + 2 * (nperseg // 2)

@@ -57,6 +57,27 @@ def test_stft_golden():
         assert rel_err(y, g[f"y{i}"]) < 5e-6          # fp32 radix-2 FFT vs pocketfft
 
 
+def test_istft_golden_and_round_trip():
+    """ISTFT (tester.py:979-990 applied to spec * scale) against the reference-generated fixture, against the oracle
+    at the full chunk size, and as the inverse of the STFT kernel."""
+    from misonet_b200 import audio
+    from oracle import miso_np
+    g = _g("istft_ref.npz")
+    for i, (nperseg, noverlap) in enumerate(g["params"]):
+        y = audio.istft(torch.from_numpy(g[f"spec{i}"]).cuda(), int(nperseg), int(noverlap)).cpu().numpy()
+        assert y.shape == g[f"wav{i}"].shape
+        assert rel_err(y, g[f"wav{i}"]) < 2e-6
+    rng = np.random.default_rng(9)
+    spec = (rng.standard_normal((3, 2, 501, 129)) + 1j * rng.standard_normal((3, 2, 501, 129))).astype(np.complex64)
+    y = audio.istft(torch.from_numpy(spec).cuda()).cpu().numpy()
+    assert y.shape == (3, 2, 32000)
+    for b, s in [(0, 0), (2, 1)]:
+        assert rel_err(y[b, s], miso_np.istft(spec[b, s])) < 2e-6
+    x = torch.from_numpy((0.1 * rng.standard_normal((2, 32000, 6))).astype(np.float32)).cuda()
+    back = audio.istft(audio.stft(x))                      # [B, M, T, F] -> [B, M, 32000]
+    assert rel_err(back.permute(0, 2, 1).cpu().numpy(), x.cpu().numpy()) < 2e-6
+
+
 def test_stft_oracle_batched_full_size():
     from misonet_b200 import audio, synth
     from oracle import miso_np
@@ -388,6 +409,30 @@ def test_pipeline_full_size_vs_oracle():
         ref_enh = mnt.miso3_forward(sd3, cfg3, torch.from_numpy(mix_stft), out["beamformed"][s].cpu().unsqueeze(1),
                                     torch.from_numpy(got_miso1[s][:, 0:1])).numpy()
         assert rel_err(out["enhanced"][:, s].cpu().numpy(), ref_enh[:, 0]) < 2e-4
+
+
+def test_long_recording_chunks_and_sharding():
+    """continuous.separate_recording (dataloader/data.py:524-597 + tester.py:857-974): equals the per-chunk pipeline
+    followed by ISTFT and the gap trim, and the block-partitioned two-rank run is bit-identical to the one-rank run."""
+    from misonet_b200 import audio, continuous, synth
+    from misonet_b200.pipeline import MisoBfMiso
+    m1, _, _ = _model("miso1", 0)
+    m3, _, _ = _model("miso3", 1)
+    pipe = MisoBfMiso(m1, m3)
+    chunk = 64 * 24                                        # 25 frames per chunk
+    n = 3 * chunk - 500
+    wav = torch.from_numpy(np.ascontiguousarray(synth.make_utterance(21, n_samples=n)[0], dtype=np.float32)).cuda()
+    full = continuous.separate_recording(pipe, wav, chunk)
+    assert full.shape == (2, n)
+    chunks, gap = continuous.chunk_signal(wav, chunk)
+    assert gap == 500
+    ref = torch.cat([audio.istft(pipe(chunks[i:i + 1])["enhanced"])[0] for i in range(3)], dim=-1)[:, :n]
+    assert rel_err(full.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    parts = [continuous.separate_recording(pipe, wav, chunk, rank=r, world=2, gather=False) for r in range(2)]
+    both = torch.cat(parts, dim=0).permute(1, 0, 2).reshape(2, -1)[:, :n]
+    assert torch.equal(both, full)
+    as16 = continuous.separate_recording(pipe, wav, chunk, to_int16=True)
+    assert as16.dtype == torch.int16 and as16.shape == (2, n)
 
 
 def test_dropin_methods():

@@ -119,6 +119,10 @@ idx = torch.tensor([i % 2 for i in range(lo, hi)], dtype=torch.long)
 mean, count = D.reduce_metrics(loss, hi - lo)
 allidx = D.gather_perm_indices(idx, n_total)
 mx = D.max_over_ranks(10.0 * (rank + 1))
+from misonet_b200 import continuous as C
+wave = torch.stack([torch.full((2, 5), float(i)) for i in range(lo, hi)]) if hi > lo else torch.zeros(0, 2, 5)
+allwave = C.gather_chunks(wave, n_total)          # the long-recording path: chunk waveforms gathered in chunk order
+assert allwave.shape == (n_total, 2, 5) and allwave[:, 0, 0].tolist() == [float(i) for i in range(n_total)]
 D.barrier()
 assert count == n_total and abs(mean - 4.0) < 1e-12, (mean, count)
 assert allidx.tolist() == [i % 2 for i in range(n_total)], allidx
@@ -138,3 +142,16 @@ def test_world_size_2_gloo(tmp_path):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "GLOO_OK 2" in res.stdout
+
+
+def test_chunk_signal_follows_the_reference_rule():
+    """dataloader/data.py:538-597: full chunks, then the remainder zero-padded by gap."""
+    from misonet_b200 import continuous as C
+    wav = torch.arange(25, dtype=torch.float32).reshape(25, 1).repeat(1, 2)
+    chunks, gap = C.chunk_signal(wav, 10)
+    assert chunks.shape == (3, 10, 2) and gap == 5
+    assert chunks[2, :5, 0].tolist() == [20., 21., 22., 23., 24.] and float(chunks[2, 5:].abs().sum()) == 0.0
+    chunks, gap = C.chunk_signal(wav[:20], 10)
+    assert chunks.shape == (2, 10, 2) and gap == 0
+    chunks, gap = C.chunk_signal(wav[:7], 10)         # shorter than one chunk (data.py:538-541)
+    assert chunks.shape == (1, 10, 2) and gap == 3

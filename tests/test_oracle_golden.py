@@ -25,6 +25,21 @@ def test_stft_matches_reference():
         assert rel_err(y, g[f"y{i}"]) < 2e-6
 
 
+def test_istft_matches_reference_and_inverts_stft():
+    g = _load("istft_ref.npz")
+    for i, (nperseg, noverlap) in enumerate(g["params"]):
+        y = miso_np.istft(g[f"spec{i}"], int(nperseg), int(noverlap))
+        assert y.shape == g[f"wav{i}"].shape
+        assert rel_err(y, g[f"wav{i}"]) < 2e-6
+    # round trip: istft(stft(x)) == x wherever whole hops fit (scipy pads the tail with zeros)
+    rng = np.random.default_rng(5)
+    x = (0.1 * rng.standard_normal((64 * 30, 2))).astype(np.float32)
+    spec = miso_np.stft(x, 256, 192)                    # [M, T, F]
+    for m in range(2):
+        back = miso_np.istft(spec[m], 256, 192)
+        assert rel_err(back[:x.shape[0]], x[:, m]) < 1e-6
+
+
 def test_mvdr_matches_reference():
     g = _load("mvdr_ref.npz")
     for i in range(2):
