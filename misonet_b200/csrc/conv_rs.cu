@@ -1,6 +1,6 @@
 // Row-streaming tcgen05 3x3 convolution with the three FRAME taps merged into the MMA N dimension -- the
 // DenseBlock convs of the MISO conv stack (model.py:437-482: 3x3, stride 1, pad (1,1); 94 % of the FLOPs of
-// MISO_1/MISO_3) at the two widest stages (F + 1 = 128 or 256 bins).
+// MISO_1/MISO_3) at every stage (F + 1 = 256, 128 bins; 64 ... 8 bins as packed strips).
 //
 // Why.  An SS-mode tcgen05.mma (M = 128, K = 16) costs 32 + N/4 cycles for N <= 128: the 128 x 16 A tile is read
 // from shared memory at 128 B/clk (tools/umma_bench.cu), so with N = cout = 24..32 the tensor pipe idles 60 % of
@@ -25,6 +25,7 @@
 // [unit][kf][hi|lo][kg][3 Nc rows][8 ch].  F + 1 = 128: rows are stored at a pitch of 128 pixels starting at
 // bin -1 (TMA zero fill); the right padding of row r IS the left padding of row r + 1 (shared-pad raster).
 // F + 1 = 256: two column regions of 128 bins, rows at a pitch of 130 pixels (5-D bf16 tensor map).
+// F + 1 <= 64: packed strips -- an M tile is the same frame of 128 / (F + 1) frame strips of one sample (RsGeom::S).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -52,7 +53,9 @@ struct RsGeom {
     int w_unit, w_off, stage, nstage, box_bytes;
     int off_btab, off_red, off_stage, smem_total, tmem_cols;
     int map5d;
-    int S, TS, Wr;  // packed mode (F + 1 = 64 / 32): an M tile holds the same row of S frame strips of TS = T / S frames
+    int S, TS, DS, Wr;  // packed mode (F + 1 <= 64): an M tile holds the same row of S frame strips; strip s covers the TS frames
+                        // from s * DS, DS = T / S, TS = DS + T % S (the strips overlap by T % S frames so that they tile any T
+                        // at a uniform stride; the duplicated frames count for the last strip only)
 };
 
 struct RsArgs {
@@ -240,7 +243,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                             const uint32_t dst = sa + (uint32_t)(sp * g.GS);
                             if (g.S > 1)  // {bins, strip, frame in strip, plane, sample}
                                 tma_load_5d(dst, tm, full, -2, tl.kind == 1 ? -1 : (tl.kind == 2 ? 1 : 0),
-                                            tl.kind == 1 ? g.TS - 1 : (tl.kind == 2 ? 0 : tin), pl, w.b);
+                                            tl.kind == 1 ? g.DS - 1 : (tl.kind == 2 ? g.TS - g.DS : tin), pl, w.b);
                             else if (g.map5d)
                                 tma_load_5d(dst, tm, full, 0, f0, tin, pl, w.b);
                             else
@@ -372,8 +375,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             }
             const int seg = g.S > 1 ? (quad * 32 + lane) / g.Wr : 0;  // packed mode: which strip this lane belongs to
             const int f = g.S > 1 ? (quad * 32 + lane) - seg * g.Wr : 128 * w.m + quad * 32 + lane;
-            const int tseg = seg * g.TS;
-            const bool valid = f < a.F;
+            const int tseg = seg * g.DS;
+            const bool fvalid = f < a.F;
+            const bool last_seg = seg == g.S - 1;
             const int fmask = 7 & ~(f == 0 ? 1 : 0) & ~(f == a.F - 1 ? 4 : 0);
             __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
             RsTiles tl;
@@ -391,6 +395,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                     for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
                     for (int o = o_lo + half; o < o_hi; o += 2) {
                         const int t = tseg + w.t0 + o;
+                        const bool valid = fvalid && (last_seg || w.t0 + o < g.DS);  // frames a strip shares with the next one belong to that one
                         const int tmask = 7 & ~(t == 0 ? 1 : 0) & ~(t == a.T - 1 ? 4 : 0);
                         int x = xo + o - o_lo;
                         if (x >= L) x -= L;
@@ -605,11 +610,11 @@ int rs_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 bool rs_shape_ok(const ConvArgs &a) {
     if (a.transposed || a.KT != 3 || a.KF != 3 || a.stride_f != 1 || a.pad_t != 1 || a.pad_f != 1) return false;
-    if (a.Fin != a.Fout || (a.Fin != 127 && a.Fin != 255 && a.Fin != 63 && a.Fin != 31)) return false;
-    if (a.Fin < 127) {  // packed strips: T must split into 128 / (F + 1) equal strips
-        static const bool packed_off = getenv("MISO_RS_PACKED") && atoi(getenv("MISO_RS_PACKED")) == 0;
+    if (a.Fin != a.Fout || (a.Fin != 127 && a.Fin != 255 && a.Fin != 63 && a.Fin != 31 && a.Fin != 15 && a.Fin != 7)) return false;
+    if (a.Fin < 127) {  // packed strips: 128 / (F + 1) strips of at least 4 frames
+        static const int packed_min = getenv("MISO_RS_PACKED_MINF") ? atoi(getenv("MISO_RS_PACKED_MINF")) : 7;
         const int S = 128 / (a.Fin + 1);
-        if (packed_off || a.T % S || a.T / S < 4) return false;
+        if (a.Fin < packed_min || a.T / S < 4) return false;
     }
     if (a.in_layout != LAYOUT_PLANES || a.out_layout != LAYOUT_PLANES) return false;
     if (a.in_ctot % 8 || a.in_coff % 8 || a.out_ctot % 8 || a.out_coff % 8 || a.cout % 8) return false;
@@ -631,7 +636,8 @@ bool make_rs_geom(const ConvArgs &a, int split, RsGeom &g) {
     g.pitch = g.map5d ? 130 : 128;
     g.Wr = std::min(128, a.Fin + 1);
     g.S = 128 / g.Wr;
-    g.TS = a.T / g.S;
+    g.DS = a.T / g.S;
+    g.TS = g.DS + a.T % g.S;
     g.nplanes = (a.cin + 7) / 8;
     g.nunit = (g.nplanes + 1) / 2;
     g.w_unit = 3 * g.nsp * 2 * g.N3 * 16;
@@ -682,7 +688,7 @@ int rs_encode_maps(const ConvArgs &a, const RsGeom &g, CUtensorMap *hi, CUtensor
             // packed strips: {bins (8-byte units), strip, frame in strip, plane, sample}; a box holds the same G frames of
             // S consecutive strips, stored [plane][frame][strip][Wr pixels] = one M tile per frame
             cuuint64_t dims[5] = {2 * F, (cuuint64_t)g.S, (cuuint64_t)g.TS, CGv, (cuuint64_t)a.B};
-            cuuint64_t strides[4] = {(cuuint64_t)g.TS * F * 16, F * 16, T * F * 16, 2 * CG * T * F * 16};
+            cuuint64_t strides[4] = {(cuuint64_t)g.DS * F * 16, F * 16, T * F * 16, 2 * CG * T * F * 16};
             cuuint32_t box[5] = {(cuuint32_t)(2 * g.Wr), (cuuint32_t)g.S, (cuuint32_t)g.G, (cuuint32_t)(2 * g.kper), 1};
             cuuint32_t es[5] = {1, 1, 1, 1, 1};
             r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, addr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
