@@ -30,11 +30,15 @@ def chunk_signal(wav, chunk_size):
     return wav.reshape(c, chunk_size, m), gap
 
 
-def gather_chunks(local, n_total):
-    """local: [c_local, ...] results of this rank's chunks (block partition) -> [n_total, ...] on every rank."""
-    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+def gather_chunks(local, n_total, world=None):
+    """local: [c_local, ...] results of this rank's chunks (block partition over ``world`` ranks, default: the process
+    group's size) -> [n_total, ...] on every rank."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) or world == 1:
         return local
-    world = dist.get_world_size()
+    if world is None:
+        world = dist.get_world_size()
+    if world != dist.get_world_size():
+        raise ValueError(f"chunks were partitioned over {world} ranks but the process group has {dist.get_world_size()}")
     cap = (n_total + world - 1) // world
     buf = local.new_zeros((cap,) + tuple(local.shape[1:]))
     buf[: local.shape[0]] = local
@@ -66,7 +70,7 @@ def separate_recording(pipe, wav, chunk_size=32000, rank=0, world=1, to_int16=Fa
     local = torch.cat(outs, dim=0) if outs else wav.new_zeros((0, spk, chunk_size))
     if not gather:
         return local
-    full = gather_chunks(local, n_chunks)                                 # [C, Spk, chunk]
+    full = gather_chunks(local, n_chunks, world)                          # [C, Spk, chunk]
     sig = full.permute(1, 0, 2).reshape(spk, n_chunks * chunk_size)
     sig = sig[:, : n_chunks * chunk_size - gap]                           # tester.py:961-963
     if to_int16:
