@@ -197,6 +197,22 @@ int miso_mvdr_fwd(const void *d_src, int64_t src_ss, const void *d_mix, int64_t 
                   void *d_out, void *d_weights, int S, int B, int M, int T, int F, float epsi, void *d_ws,
                   size_t ws_bytes, void *stream);
 
+/* Staged form of the same stage, for covariance statistics that span ranks: the reference's utterance-level
+ * beamforming of a chunked recording (Tester_Beamforming.inference with utterance_flag, tester.py:425-449) takes the
+ * spatial covariances over ALL frames of the recording.  Every rank computes the partial sums of its frames
+ * (miso_mvdr_scm: float [S*B][miso_mvdr_tsplit(B,F)][2 M (M+1)][F]), the ranks' partial sums are concatenated along the
+ * split axis (an all-gather of miso_mvdr_partial_bytes each), miso_mvdr_weights adds them in that fixed order in fp64 and
+ * returns the beamformers ([S,B,F,M] complex64; d_ws: S*B*F*M*16 bytes), and miso_mvdr_apply filters the local frames.
+ * With one rank the three calls equal miso_mvdr_fwd bit for bit. */
+int miso_mvdr_tsplit(int B, int F);
+size_t miso_mvdr_partial_bytes(int S, int B, int M, int F);
+int miso_mvdr_scm(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf,
+                  void *d_partial, int S, int B, int M, int T, int F, void *stream);
+int miso_mvdr_weights(const void *d_partial, int nsplit, int T_total, void *d_weights, int S, int B, int M, int F,
+                      float epsi, void *d_ws, size_t ws_bytes, void *stream);
+int miso_mvdr_apply(const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf, const void *d_weights, void *d_out,
+                    int S, int B, int M, int T, int F, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

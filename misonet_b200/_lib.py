@@ -53,6 +53,14 @@ SIGNATURES = {
                                  c_int, c_void_p]),
     "miso_loss_enhance_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "miso_mvdr_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "miso_mvdr_tsplit": (c_int, [c_int, c_int]),
+    "miso_mvdr_partial_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "miso_mvdr_scm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
+                              c_int, c_int, c_void_p]),
+    "miso_mvdr_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t,
+                                  c_void_p]),
+    "miso_mvdr_apply": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_int, c_void_p]),
     "miso_mvdr_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
 }

@@ -572,6 +572,51 @@ int run(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, int64_
     return MISO_OK;
 }
 
+// Staged form: the covariance sums of one recording may be spread over ranks (utterance-level MVDR of a chunked
+// recording, tester.py:425-449): every rank computes its frames' partial sums (same layout as the fused path:
+// [S*B][split][NV][F]), the partial sums of all ranks are concatenated along the split axis, and the eigenvector /
+// solve kernels add them in that fixed order in fp64.
+template <int M>
+int run_scm(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf, float *d_partial,
+            int S, int B, int T, int F, cudaStream_t stream) {
+    const int tsplit = pick_tsplit(B, F);
+    scm_kernel<M><<<dim3(ceil_div(F, kFx), tsplit, B), dim3(kFx, kTy), 0, stream>>>(
+        reinterpret_cast<const float2 *>(d_src), src_ss, reinterpret_cast<const float2 *>(d_mix), sb, sm, st, sf, d_partial, S, B, T, F, tsplit);
+    MISO_LAUNCHED("scm_kernel");
+    return MISO_OK;
+}
+
+template <int M>
+int run_weights(const float *d_partial, int nsplit, int T_total, void *d_weights, int S, int B, int F, float epsi, void *d_ws,
+                size_t ws_bytes, cudaStream_t stream) {
+    const size_t need = (size_t)B * S * F * M * sizeof(double2);
+    if (ws_bytes < need) {
+        set_error("miso_mvdr_weights: workspace %zu < required %zu bytes", ws_bytes, need);
+        return MISO_E_WORKSPACE;
+    }
+    double2 *steer = reinterpret_cast<double2 *>(d_ws);
+    const int nprob = B * S * F;
+    if constexpr (M == 6)
+        eig6_kernel<M><<<ceil_div(2 * nprob, 64), 64, 0, stream>>>(d_partial, steer, nprob, F, T_total, nsplit);
+    else
+        eig_generic_kernel<M><<<ceil_div(nprob, 64), 64, 0, stream>>>(d_partial, steer, nprob, F, T_total, nsplit);
+    MISO_LAUNCHED("eig_kernel");
+    solve_kernel<M><<<B * S, 256, (size_t)F * sizeof(double2), stream>>>(d_partial, steer, reinterpret_cast<float2 *>(d_weights), F, T_total,
+                                                                      nsplit, (double)epsi);
+    MISO_LAUNCHED("solve_kernel");
+    return MISO_OK;
+}
+
+template <int M>
+int run_apply(const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf, const void *d_weights, void *d_out, int S, int B, int T,
+              int F, cudaStream_t stream) {
+    apply_kernel<M><<<dim3(ceil_div(F, kFx), ceil_div(T, kApplyTile), B), dim3(kFx, kTy), 0, stream>>>(
+        reinterpret_cast<const float2 *>(d_mix), sb, sm, st, sf, reinterpret_cast<const float2 *>(d_weights), reinterpret_cast<float2 *>(d_out), S,
+        B, T, F);
+    MISO_LAUNCHED("apply_kernel");
+    return MISO_OK;
+}
+
 template <int M>
 size_t ws_bytes_for(int S, int B, int T, int F) {
     return carve<M>(nullptr, S, B, T, F, pick_tsplit(B, F)).total;
@@ -619,6 +664,55 @@ int miso_mvdr_fwd(const void *d_src, int64_t src_ss, const void *d_mix, int64_t 
     }
 #undef MISO_MVDR_CASE
     return MISO_E_ARG;
+}
+
+int miso_mvdr_tsplit(int B, int F) { return (B < 1 || F < 1) ? -1 : pick_tsplit(B, F); }
+
+size_t miso_mvdr_partial_bytes(int S, int B, int M, int F) {
+    if (S < 1 || B < 1 || F < 1 || M < 2 || M > 8) return 0;
+    return (size_t)S * B * pick_tsplit(B, F) * (size_t)(2 * M * (M + 1)) * F * sizeof(float);
+}
+
+#define MISO_MVDR_SWITCH(call)                 \
+    switch (M) {                               \
+        case 2: return call(2);                \
+        case 3: return call(3);                \
+        case 4: return call(4);                \
+        case 5: return call(5);                \
+        case 6: return call(6);                \
+        case 7: return call(7);                \
+        case 8: return call(8);                \
+    }                                          \
+    return MISO_E_ARG
+
+int miso_mvdr_scm(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf, void *d_partial,
+                  int S, int B, int M, int T, int F, void *stream) {
+    MISO_REQUIRE(d_src && d_mix && d_partial, "miso_mvdr_scm: null argument");
+    MISO_REQUIRE(S >= 1 && S <= kMaxS && M >= 2 && M <= 8, "miso_mvdr_scm: S=%d M=%d unsupported", S, M);
+    MISO_REQUIRE(B >= 1 && B <= 65535 && T >= 1 && F >= 1 && F <= 2048, "miso_mvdr_scm: bad shape B=%d T=%d F=%d", B, T, F);
+#define MISO_CALL(m) run_scm<m>(d_src, src_ss, d_mix, sb, sm, st, sf, reinterpret_cast<float *>(d_partial), S, B, T, F, as_stream(stream))
+    MISO_MVDR_SWITCH(MISO_CALL);
+#undef MISO_CALL
+}
+
+int miso_mvdr_weights(const void *d_partial, int nsplit, int T_total, void *d_weights, int S, int B, int M, int F, float epsi, void *d_ws,
+                      size_t ws_bytes, void *stream) {
+    MISO_REQUIRE(d_partial && d_weights && d_ws, "miso_mvdr_weights: null argument");
+    MISO_REQUIRE(S >= 1 && S <= kMaxS && M >= 2 && M <= 8, "miso_mvdr_weights: S=%d M=%d unsupported", S, M);
+    MISO_REQUIRE(B >= 1 && nsplit >= 1 && T_total >= 1 && F >= 1 && F <= 2048, "miso_mvdr_weights: bad shape");
+#define MISO_CALL(m) run_weights<m>(reinterpret_cast<const float *>(d_partial), nsplit, T_total, d_weights, S, B, F, epsi, d_ws, ws_bytes, as_stream(stream))
+    MISO_MVDR_SWITCH(MISO_CALL);
+#undef MISO_CALL
+}
+
+int miso_mvdr_apply(const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf, const void *d_weights, void *d_out, int S, int B,
+                    int M, int T, int F, void *stream) {
+    MISO_REQUIRE(d_mix && d_weights && d_out, "miso_mvdr_apply: null argument");
+    MISO_REQUIRE(S >= 1 && S <= kMaxS && M >= 2 && M <= 8, "miso_mvdr_apply: S=%d M=%d unsupported", S, M);
+    MISO_REQUIRE(B >= 1 && B <= 65535 && T >= 1 && F >= 1, "miso_mvdr_apply: bad shape");
+#define MISO_CALL(m) run_apply<m>(d_mix, sb, sm, st, sf, d_weights, d_out, S, B, T, F, as_stream(stream))
+    MISO_MVDR_SWITCH(MISO_CALL);
+#undef MISO_CALL
 }
 
 }  // extern "C"

@@ -383,6 +383,46 @@ def test_mvdr_full_size_vs_oracle_and_distortionless():
 
 
 # ------------------------------------------------------------------------------- pipeline
+def test_mvdr_utterance_level_staged():
+    """Staged MVDR (tester.py:425-449: covariances over all frames of a chunked recording): one rank == the fused call
+    bit for bit; two simulated ranks (frames split in halves, partial sums concatenated along the split axis) agree
+    with the fused call to rounding and with the oracle."""
+    from misonet_b200 import _lib, beamforming, synth
+    from oracle import miso_np
+    src_np, mix_np = synth.mvdr_case(5, 1, 129, 6, 400)                    # [B,F,M,T]
+    src = torch.from_numpy(src_np).permute(0, 2, 3, 1).contiguous().cuda()    # [B,M,T,F]
+    mix = torch.from_numpy(mix_np).permute(0, 2, 3, 1).contiguous().cuda()
+    full, w_full = beamforming.mvdr(src.unsqueeze(0), mix, return_weights=True)
+    one, w_one = beamforming.mvdr_utterance(src.unsqueeze(0), mix)
+    assert torch.equal(one, full) and torch.equal(w_one, w_full)
+    lib = _lib.load()
+    S, B, M, T, F = 1, 1, 6, 400, 129
+    tsplit = lib.miso_mvdr_tsplit(B, F)
+    parts, halves = [], [(0, 170), (170, 400)]
+    for lo, hi in halves:
+        s_h, m_h = src[:, :, lo:hi].contiguous(), mix[:, :, lo:hi].contiguous()
+        p = torch.empty(S * B, tsplit, 84, F, dtype=torch.float32, device="cuda")
+        _lib.check(lib.miso_mvdr_scm(_lib.ptr(s_h), 0, _lib.ptr(m_h), *m_h.stride(), _lib.ptr(p), S, B, M, hi - lo, F,
+                                     _lib.stream_ptr()), "miso_mvdr_scm")
+        parts.append(p)
+    allp = torch.stack(parts, dim=1).reshape(S * B, 2 * tsplit, 84, F).contiguous()
+    w = torch.empty(S, B, F, M, dtype=torch.complex64, device="cuda")
+    ws = torch.empty(S * B * F * M * 16, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.miso_mvdr_weights(_lib.ptr(allp), 2 * tsplit, T, _lib.ptr(w), S, B, M, F, 1e-6, _lib.ptr(ws), ws.numel(),
+                                     _lib.stream_ptr()), "miso_mvdr_weights")
+    outs = []
+    for lo, hi in halves:
+        m_h = mix[:, :, lo:hi].contiguous()
+        o = torch.empty(S, B, hi - lo, F, dtype=torch.complex64, device="cuda")
+        _lib.check(lib.miso_mvdr_apply(_lib.ptr(m_h), *m_h.stride(), _lib.ptr(w), _lib.ptr(o), S, B, M, hi - lo, F,
+                                       _lib.stream_ptr()), "miso_mvdr_apply")
+        outs.append(o)
+    two = torch.cat(outs, dim=2)
+    assert rel_err(two.cpu().numpy(), full.cpu().numpy()) < 1e-5
+    ref = miso_np.apply_beamforming(src_np, mix_np)                            # [B,T,F]
+    assert rel_err(two[0].cpu().numpy(), ref) < REQUIRED_TOL
+
+
 def test_pipeline_full_size_vs_oracle():
     """One synthetic SMS-WSJ-shaped 4 s utterance through STFT -> MISO1 x6 -> align -> MVDR x2 ->
     MISO3 x2 against the oracle pipeline fed stage by stage (MVDR amplifies
