@@ -8,6 +8,11 @@
 
 namespace miso {
 
+int pdl_level() {
+    static const int lvl = getenv("MISO_PDL") ? atoi(getenv("MISO_PDL")) : 0;  // 1: whole chain, 2: operand-preparation kernels only
+    return lvl;
+}
+
 bool pdl_enabled() {
     static const bool on = getenv("MISO_PDL") && atoi(getenv("MISO_PDL")) != 0;  // measured on B200: 11.84 ms/step with, 11.54 without -> off by default
     return on;
