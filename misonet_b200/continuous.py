@@ -76,3 +76,42 @@ def separate_recording(pipe, wav, chunk_size=32000, rank=0, world=1, to_int16=Fa
     if to_int16:
         sig = (sig * MAX_INT16).to(torch.int16)                          # numpy astype truncates toward zero, like .to()
     return sig
+
+
+@torch.no_grad()
+def beamform_recording(model_sep, wav, chunk_size=32000, ref_ch=0, nperseg=256, noverlap=192, epsi=1e-6, clean=None,
+                       rank=0, world=1, batch=4):
+    """Utterance-wise beamforming of a long recording (Tester_Beamforming.inference with ``utterance_flag``,
+    tester.py:340-449): per chunk MISO1 over all mic shifts (and, for evaluation, alignment to the clean references),
+    ISTFT of every speaker image at every mic and concatenation along time (tester.py:395-423); then ONE STFT of the
+    whole recording (tester.py:426-434) and an MVDR whose spatial covariances span all frames (tester.py:442).
+
+    wav: float CUDA [N, Mic]; clean (optional): float CUDA [Spk, N] clean sources at ``ref_ch``.
+    Returns dict(beamformed=[Spk, T_all, F] complex64, wav=[Spk, N'] float32 with N' = (T_all - 1) * hop,
+    miso1_wav=[Spk, Mic, N] the concatenated MISO1 images).  Chunks are block-partitioned over the ranks; every rank
+    then holds the whole recording (one waveform gather) and the final MVDR runs replicated."""
+    from . import beamforming, separation
+    n, n_mic = wav.shape
+    chunks, gap = chunk_signal(wav, chunk_size)
+    cchunks = None
+    if clean is not None:
+        cchunks = torch.stack([chunk_signal(c[:, None], chunk_size)[0][:, :, 0] for c in clean], dim=1)   # [C, Spk, chunk]
+    n_chunks = chunks.shape[0]
+    lo, hi = shard_range(n_chunks, rank, world)
+    outs = []
+    for i in range(lo, hi, batch):
+        j = min(hi, i + batch)
+        mix_stft = audio.stft(chunks[i:j], nperseg, noverlap)                                  # [b, Mic, T, F]
+        miso1 = separation.miso1_inference(model_sep, mix_stft, ref_ch, stacked=True)          # [Spk, b, Mic, T, F]
+        if cchunks is not None:
+            cref = audio.stft(cchunks[i:j].permute(0, 2, 1).contiguous(), nperseg, noverlap)   # [b, Spk, T, F]
+            miso1 = separation.align_to_clean(cref, miso1, ref_ch)
+        outs.append(audio.istft(miso1, nperseg, noverlap).permute(1, 0, 2, 3))                 # [b, Spk, Mic, chunk]
+    spk = model_sep.num_spks
+    local = torch.cat(outs, dim=0) if outs else wav.new_zeros((0, spk, n_mic, chunk_size))
+    full = gather_chunks(local.contiguous(), n_chunks, world)                                  # [C, Spk, Mic, chunk]
+    img = full.permute(1, 2, 0, 3).reshape(spk, n_mic, n_chunks * chunk_size)[:, :, :n]        # gap trimmed (tester.py:405-417)
+    src_stft = audio.stft(img.permute(0, 2, 1).contiguous(), nperseg, noverlap)                # [Spk, Mic, T_all, F]
+    mix_all = audio.stft(wav[None], nperseg, noverlap)                                         # [1, Mic, T_all, F]
+    bf = beamforming.mvdr(src_stft[:, None], mix_all, epsi)[:, 0]                              # [Spk, T_all, F]
+    return dict(beamformed=bf, wav=audio.istft(bf, nperseg, noverlap), miso1_wav=img)

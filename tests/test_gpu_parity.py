@@ -475,6 +475,29 @@ def test_long_recording_chunks_and_sharding():
     assert as16.dtype == torch.int16 and as16.shape == (2, n)
 
 
+def test_utterance_wise_beamforming_of_a_recording():
+    """continuous.beamform_recording (tester.py:340-449 with utterance_flag): equals the same composition done by hand
+    with the oracle's STFT / MVDR on the MISO1 images."""
+    from misonet_b200 import continuous, synth
+    from oracle import miso_np
+    m1, _, _ = _model("miso1", 0)
+    chunk = 64 * 24
+    n = 2 * chunk + 700
+    mix, images = synth.make_utterance(31, n_samples=n)
+    wav = torch.from_numpy(mix).cuda()
+    clean = torch.from_numpy(np.ascontiguousarray(images[:, :, 0])).cuda()          # [Spk, N] at the reference mic
+    res = continuous.beamform_recording(m1, wav, chunk, clean=clean)
+    t_all = miso_np.stft_num_frames(n)
+    assert res["beamformed"].shape == (2, t_all, 129) and res["miso1_wav"].shape == (2, 6, n)
+    img = res["miso1_wav"].cpu().numpy()                                             # [Spk, Mic, N]
+    mix_stft = miso_np.stft(mix)                                                     # [Mic, T, F]
+    for s in range(2):
+        src_stft = miso_np.stft(img[s].T)                                            # [Mic, T, F]
+        ref = miso_np.apply_beamforming(src_stft.transpose(2, 0, 1)[None], mix_stft.transpose(2, 0, 1)[None])[0]   # [T, F]
+        assert rel_err(res["beamformed"][s].cpu().numpy(), ref) < REQUIRED_TOL
+    assert res["wav"].shape == (2, (t_all - 1) * 64)
+
+
 def test_dropin_methods():
     """The reference-named methods of B200HotPath at B = 1."""
     from misonet_b200 import dropin
