@@ -2,6 +2,8 @@
 // dataloader/data.py:49-66,77-79 = tester.py:992-1012): zero-padded framing, periodic
 // hann window, unnormalised real FFT.  One warp transforms one (b, mic, frame) with a
 // shared-memory radix-2 FFT; twiddles and the window are computed once per CTA in fp64.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace miso {
@@ -24,13 +26,14 @@ __global__ void __launch_bounds__(kWarps * 32) stft_kernel(const float *__restri
     for (int i = threadIdx.x; i < N; i += blockDim.x) win[i] = (float)(0.5 - 0.5 * cospi(2.0 * (double)i / (double)N));
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t g = (int64_t)blockIdx.x * kWarps + warp;
-    if (g >= (int64_t)B * M * T) return;
+    float2 *bf = buf[warp];
+    // the fp64 twiddle / window tables above cost more than a frame's transform: a CTA keeps them for many frames
+    for (int64_t g = (int64_t)blockIdx.x * kWarps + warp; g < (int64_t)B * M * T; g += (int64_t)gridDim.x * kWarps) {
     const int t = (int)(g % T);
     const int m = (int)((g / T) % M);
     const int b = (int)(g / ((int64_t)T * M));
-    float2 *bf = buf[warp];
     const float *xb = x + b * sb + m * sm;
+    __syncwarp();
     for (int i = lane; i < N; i += 32) {
         int p = t * hop + i - N / 2;
         float v = (p >= 0 && p < Ns) ? xb[(int64_t)p * sn] * win[i] : 0.f;
@@ -55,6 +58,7 @@ __global__ void __launch_bounds__(kWarps * 32) stft_kernel(const float *__restri
     }
     float2 *o = out + (size_t)g * (N / 2 + 1);
     for (int k = lane; k <= N / 2; k += 32) o[k] = bf[k];
+    }
 }
 
 // Inverse: one warp rebuilds one (signal, frame): Hermitian extension of the one-sided spectrum, the same radix-2
@@ -74,12 +78,12 @@ __global__ void __launch_bounds__(kWarps * 32) istft_frames_kernel(const float2 
     for (int i = threadIdx.x; i < N; i += blockDim.x) win[i] = (float)(0.5 - 0.5 * cospi(2.0 * (double)i / (double)N));
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t g = (int64_t)blockIdx.x * kWarps + warp;
-    if (g >= (int64_t)S * T) return;
+    float2 *bf = buf[warp];
+    for (int64_t g = (int64_t)blockIdx.x * kWarps + warp; g < (int64_t)S * T; g += (int64_t)gridDim.x * kWarps) {
     const int t = (int)(g % T);
     const int sidx = (int)(g / T);
-    float2 *bf = buf[warp];
     const float2 *x = spec + sidx * ss + t * st;
+    __syncwarp();
     for (int k = lane; k <= N / 2; k += 32) {
         const float2 v = x[k * sf];
         bf[(int)(__brev((unsigned)k) >> (32 - LOG2N))] = v;
@@ -103,6 +107,7 @@ __global__ void __launch_bounds__(kWarps * 32) istft_frames_kernel(const float2 
     }
     float *o = frames + (size_t)g * N;
     for (int i = lane; i < N; i += 32) o[i] = bf[i].x * (1.f / (float)N) * win[i];
+    }
 }
 
 // Overlap-add as a gather in a fixed order (deterministic), divided by the summed squared window, with the
@@ -110,8 +115,13 @@ __global__ void __launch_bounds__(kWarps * 32) istft_frames_kernel(const float2 
 template <int N>
 __global__ void __launch_bounds__(256) istft_ola_kernel(const float *__restrict__ frames, float *__restrict__ out, int S, int T, int hop,
                                                         int n_out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)S * n_out) return;
+    __shared__ float w2[N];
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        const float w = (float)(0.5 - 0.5 * cospi(2.0 * (double)k / (double)N));
+        w2[k] = w * w;
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)S * n_out; i += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(i % n_out);
     const int sidx = (int)(i / n_out);
     const int p = n + N / 2;  // position in the untrimmed signal
@@ -123,11 +133,11 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float *__restrict_
     for (int t = t_lo; t <= t_hi; ++t) {
         const int k = p - t * hop;
         if (k < 0 || k >= N) continue;
-        const float w = (float)(0.5 - 0.5 * cospi(2.0 * (double)k / (double)N));
         acc += frames[((size_t)sidx * T + t) * N + k];
-        norm = fmaf(w, w, norm);
+        norm += w2[k];
     }
     out[i] = acc / (norm > 1e-10f ? norm : 1.f);
+    }
 }
 
 }  // namespace
@@ -156,7 +166,7 @@ int miso_stft_fwd(const float *d_x, int64_t sb, int64_t sn, int64_t sm, void *d_
     MISO_REQUIRE(B >= 1 && M >= 1 && N >= 1, "miso_stft_fwd: bad shape");
     const int T = miso_stft_num_frames(N, nperseg, hop);
     const int64_t frames = (int64_t)B * M * T;
-    const unsigned blocks = (unsigned)((frames + kWarps - 1) / kWarps);
+    const unsigned blocks = (unsigned)std::min<int64_t>((frames + kWarps - 1) / kWarps, 148 * 16);
     cudaStream_t st = as_stream(stream);
     if (nperseg == 256)
         stft_kernel<256><<<blocks, kWarps * 32, 0, st>>>(d_x, sb, sn, sm, reinterpret_cast<float2 *>(d_out), B, N, M, T, hop);
@@ -187,8 +197,8 @@ int miso_istft_fwd(const void *d_spec, int64_t ss, int64_t st, int64_t sf, float
     cudaStream_t stq = as_stream(stream);
     float *frames = reinterpret_cast<float *>(d_ws);
     const int64_t nfr = (int64_t)S * T;
-    const unsigned blocks = (unsigned)((nfr + kWarps - 1) / kWarps);
-    const unsigned oblocks = (unsigned)(((int64_t)S * n_out + 255) / 256);
+    const unsigned blocks = (unsigned)std::min<int64_t>((nfr + kWarps - 1) / kWarps, 148 * 16);
+    const unsigned oblocks = (unsigned)std::min<int64_t>(((int64_t)S * n_out + 255) / 256, 148 * 32);
     if (nperseg == 256) {
         istft_frames_kernel<256><<<blocks, kWarps * 32, 0, stq>>>(reinterpret_cast<const float2 *>(d_spec), ss, st, sf, frames, S, T);
         MISO_LAUNCHED("istft_frames_kernel");
