@@ -234,6 +234,24 @@ def test_net_row_streaming_convs_vs_oracle(B, T):
     assert e < 2e-4 and e < REQUIRED_TOL
 
 
+def test_net_bench_workload_vs_oracle():
+    """BASELINE configs[1] itself (B = 16 x 6 mics x 500 frames x 257 bins, PAPER layout, bf16x3): three of the sixteen
+    samples against the oracle (samples are independent, so the oracle only runs those)."""
+    from misonet_b200 import synth
+    from oracle import miso_net_torch as mnt
+    m, cfg, sd = _model("miso1", 0, layout="PAPER")
+    m.conv_mode = "bf16x3"
+    mix = synth.random_spec(41, (16, 6, 500, 257))
+    with torch.no_grad():
+        y = m(torch.from_numpy(mix).cuda()).cpu().numpy()
+    assert y.shape == (16, 2, 500, 257)
+    for b in (0, 7, 15):
+        ref = mnt.miso1_forward(sd, cfg, torch.from_numpy(mix[b:b + 1])).numpy()
+        e = rel_err(y[b:b + 1], ref)
+        print(f"bench workload sample {b}: rel err {e:.2e}")
+        assert e < 2e-4 and e < REQUIRED_TOL
+
+
 def test_net_batch_invariance_and_chunking():
     """A sample's output must not depend on what else is in the batch (no cross-sample coupling:
     InstanceNorm/gLN only), nor on the workspace-driven batch chunking."""
