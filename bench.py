@@ -177,6 +177,7 @@ def run_ours(args, wl, rank, world, local):
     frames_per_step = B * T
     with torch.no_grad():
         out = step(dev_in)
+        out0 = out[0:1].cpu()
         host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
         for _ in range(max(args.warmup, 3) - 1):
             step(dev_in)
@@ -325,7 +326,21 @@ def run_ours(args, wl, rank, world, local):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl, steps=1)
+        if wl["kind"] == "miso1":   # "SI-SDR vs ref" of the metric: utterance 0 of the bench batch against the oracle (checker only)
+            line["parity"] = parity_vs_oracle(wl, m1, host_in, out0)
     return line
+
+
+def parity_vs_oracle(wl, model, host_in, out0):
+    """Part of the cpu_baseline leg: the oracle (reference algorithm, fp32 CPU) on utterance 0 of the bench batch with the
+    bench model's weights, against the CUDA result of the timed configuration."""
+    from oracle import miso_net_torch as mnt
+    cfg = mnt.NetConfig.miso1(layout=wl["layout"])
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref = mnt.miso1_forward(sd, cfg, host_in[0:1].clone())
+    err = float((out0 - ref).norm() / ref.norm())
+    return {"rel_err": err, "si_sdr_vs_ref_db": -20.0 * float(np.log10(max(err, 1e-30))), "tolerance": 1e-3,
+            "sample": "utterance 0 of the bench batch, complex64 [1,2,T,F], oracle = reference algorithm in fp32 on the CPU"}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
