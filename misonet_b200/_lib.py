@@ -42,6 +42,13 @@ SIGNATURES = {
     "miso_net_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "miso_net_input_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "miso_net_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "miso_net_grad_numel": (c_int64, [c_void_p]),
+    "miso_net_train_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "miso_net_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "miso_net_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "miso_grad_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "miso_upit_bwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_void_p]),
     "miso_net_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "miso_pack_miso1": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p]),
     "miso_pack_miso3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

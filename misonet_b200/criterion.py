@@ -72,6 +72,30 @@ def perm_gather(src, idx, out=None, out_view=None):
     return out_view
 
 
+class _UpitFunction(torch.autograd.Function):
+    """loss_uPIT with its gradient w.r.t. the estimate (miso_upit_bwd, include/misonet_b200.h)."""
+
+    @staticmethod
+    def forward(ctx, est, ref):
+        _, idx, loss = pair_decide(est, ref, 1, want_loss=True)
+        ctx.save_for_backward(est, ref, idx)
+        ctx.mark_non_differentiable(idx)
+        return loss, idx
+
+    @staticmethod
+    def backward(ctx, gloss, _gidx):
+        est, ref, idx = ctx.saved_tensors
+        est, e_sb, e_ss = _planes(est.detach())
+        ref, r_sb, r_ss = _planes(ref)
+        B, S, T, F = est.shape
+        grad = torch.empty(B, S, T, F, dtype=torch.complex64, device=est.device)
+        g = gloss.detach().to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(est.device):
+            _lib.check(_lib.load().miso_upit_bwd(_lib.ptr(est), e_sb, e_ss, _lib.ptr(ref), r_sb, r_ss, _lib.ptr(idx), B, S, T, F,
+                                                 _lib.ptr(g), _lib.ptr(grad), _lib.stream_ptr()), "miso_upit_bwd")
+        return grad, None
+
+
 def loss_uPIT(num_spks, estimate_clean, ref_clean, return_perm=False):
     """criterion.py:8-63.  estimate_clean: complex [B,Spks,T,F]; ref_clean: list[Spks] of complex
     [B,T,F] (or a stacked [B,Spks,T,F] tensor).  Returns the scalar loss (float32 CUDA tensor);
@@ -79,7 +103,11 @@ def loss_uPIT(num_spks, estimate_clean, ref_clean, return_perm=False):
     ref = torch.stack(list(ref_clean), dim=1) if isinstance(ref_clean, (list, tuple)) else ref_clean
     if estimate_clean.shape[1] != num_spks:
         raise ValueError("estimate does not have num_spks speakers")
-    _, idx, loss = pair_decide(estimate_clean, ref.to(estimate_clean.device), 1, want_loss=True)
+    ref = ref.to(estimate_clean.device)
+    if torch.is_grad_enabled() and estimate_clean.requires_grad:
+        loss, idx = _UpitFunction.apply(estimate_clean, ref)      # training: trainer.py:170-172, loss.backward()
+    else:
+        _, idx, loss = pair_decide(estimate_clean, ref, 1, want_loss=True)
     return (loss, idx) if return_perm else loss
 
 

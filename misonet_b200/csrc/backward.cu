@@ -1,0 +1,682 @@
+// Backward kernels of the MISO network body (fp32 FMA; first correct training path).
+// reference trainer.py:159-212 calls loss.backward() through
+// model.py:76-111 (conv -> ELU -> InstanceNorm2d units model.py:401-466, TCN model.py:486-567, gLN model.py:609-632).
+//
+// Conventions (net.cu): activations are stored as RAW ELU outputs (bf16 hi/lo planes) plus the fixed-point (sum, sumsq)
+// statistics of every (sample, channel); consumers read z = e * rstd + shift.  The gradient buffer of an activation
+// buffer is fp32 channels-last and accumulates dL/dz from every consumer (data gradients of the layers that read it);
+// the producing layer's backward then turns its channel range in place into dL/dy (InstanceNorm + ELU backward) and
+// feeds the weight-gradient GEMM and the data-gradient conv (conv_fp32.cu with transposed weights).
+#include <algorithm>
+
+#include "bwd.cuh"
+
+namespace miso {
+
+int conv_fp32_tile_n(int cout);
+
+namespace {
+
+constexpr int kEw = 256;
+
+__device__ __forceinline__ void load_e4(const __nv_bfloat16 *p, size_t lo_elems, int use_lo, float *e) {
+    const uint2 h = *reinterpret_cast<const uint2 *>(p);
+    e[0] = bf16_lo(h.x);
+    e[1] = bf16_hi(h.x);
+    e[2] = bf16_lo(h.y);
+    e[3] = bf16_hi(h.y);
+    if (use_lo) {
+        const uint2 l = *reinterpret_cast<const uint2 *>(p + lo_elems);
+        e[0] += bf16_lo(l.x);
+        e[1] += bf16_hi(l.x);
+        e[2] += bf16_lo(l.y);
+        e[3] += bf16_hi(l.y);
+    }
+}
+
+// ---- InstanceNorm2d + ELU backward ------------------------------------------------------------------------------
+// pass 1: per (b, channel) sums of dz and dz * z over the pixels
+__global__ void __launch_bounds__(kEw) in_bwd_reduce_kernel(const InBwdArgs a, int pix_per_cta) {
+    extern __shared__ float sh[];  // [c][2]
+    const int b = blockIdx.y;
+    const int nc4 = a.c >> 2;
+    const int lanes = kEw / nc4;
+    const int c4 = threadIdx.x % nc4, lane = threadIdx.x / nc4;
+    for (int i = threadIdx.x; i < 2 * a.c; i += kEw) sh[i] = 0.f;
+    __syncthreads();
+    if (lane < lanes) {
+        const int ca = a.coff + c4 * 4;
+        float2 af[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double *s = a.sums + ((size_t)b * a.ctot + ca + q) * 2;
+            af[q] = affine_from_sums(stat_get(s), stat_get(s + 1), a.inv_n, (double)a.eps);
+        }
+        const size_t lo = (size_t)a.ctot * a.npix;
+        const __nv_bfloat16 *eb = a.e + (size_t)b * 2 * lo + (size_t)(ca >> 3) * a.npix * 8 + (ca & 7);
+        const float *gb = a.g + (size_t)b * a.npix * a.ctot + ca;
+        const int p0 = blockIdx.x * pix_per_cta, p1 = min(a.npix, p0 + pix_per_cta);
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int p = p0 + lane; p < p1; p += lanes) {
+            const float4 dz = *reinterpret_cast<const float4 *>(gb + (size_t)p * a.ctot);
+            float e[4];
+            load_e4(eb + (size_t)p * 8, lo, a.use_lo, e);
+            const float d[4] = {dz.x, dz.y, dz.z, dz.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float z = fmaf(e[q], af[q].x, af[q].y);
+                s1[q] += d[q];
+                s2[q] = fmaf(d[q], z, s2[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            atomicAdd(&sh[(c4 * 4 + q) * 2], s1[q]);
+            atomicAdd(&sh[(c4 * 4 + q) * 2 + 1], s2[q]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * a.c; i += kEw) atomicAdd(&a.red[(size_t)b * a.c * 2 + i], (double)sh[i]);
+}
+
+// pass 2: dy = rstd * (dz - mean(dz) - z * mean(dz * z)) * ELU'(y), in place; bias gradient = sum dy
+__global__ void __launch_bounds__(kEw) in_bwd_apply_kernel(const InBwdArgs a, int pix_per_cta) {
+    extern __shared__ float sh[];  // [c]
+    const int b = blockIdx.y;
+    const int nc4 = a.c >> 2;
+    const int lanes = kEw / nc4;
+    const int c4 = threadIdx.x % nc4, lane = threadIdx.x / nc4;
+    for (int i = threadIdx.x; i < a.c; i += kEw) sh[i] = 0.f;
+    __syncthreads();
+    if (lane < lanes) {
+        const int ca = a.coff + c4 * 4;
+        float2 af[4];
+        float m1[4], m2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            af[q] = make_float2(1.f, 0.f);
+            m1[q] = m2[q] = 0.f;
+            if (!a.plain) {
+                const double *s = a.sums + ((size_t)b * a.ctot + ca + q) * 2;
+                af[q] = affine_from_sums(stat_get(s), stat_get(s + 1), a.inv_n, (double)a.eps);
+                const double *r = a.red + ((size_t)b * a.c + c4 * 4 + q) * 2;
+                m1[q] = (float)(r[0] * a.inv_n);
+                m2[q] = (float)(r[1] * a.inv_n);
+            }
+        }
+        const size_t lo = (size_t)a.ctot * a.npix;
+        const __nv_bfloat16 *eb = a.plain ? nullptr : a.e + (size_t)b * 2 * lo + (size_t)(ca >> 3) * a.npix * 8 + (ca & 7);
+        float *gb = a.g + (size_t)b * a.npix * a.ctot + ca;
+        const int p0 = blockIdx.x * pix_per_cta, p1 = min(a.npix, p0 + pix_per_cta);
+        float sb[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int p = p0 + lane; p < p1; p += lanes) {
+            const float4 dz = *reinterpret_cast<const float4 *>(gb + (size_t)p * a.ctot);
+            float d[4] = {dz.x, dz.y, dz.z, dz.w};
+            if (!a.plain) {
+                float e[4];
+                load_e4(eb + (size_t)p * 8, lo, a.use_lo, e);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float z = fmaf(e[q], af[q].x, af[q].y);
+                    const float de = af[q].x * (d[q] - m1[q] - z * m2[q]);
+                    d[q] = e[q] > 0.f ? de : de * (e[q] + 1.f);  // ELU'(y) = exp(y) = e + 1 for y <= 0
+                }
+                *reinterpret_cast<float4 *>(gb + (size_t)p * a.ctot) = make_float4(d[0], d[1], d[2], d[3]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sb[q] += d[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) atomicAdd(&sh[c4 * 4 + q], sb[q]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.c; i += kEw) atomicAdd(&a.dbias[i], sh[i]);
+}
+
+// ---- weight gradient ---------------------------------------------------------------------------------------------
+// GEMM per tap: dW_tap [cin x cout] = A_tap^T [cin x K] * dY [K x cout], K = B * T * Fout pixels.  A CTA owns one
+// (tap, 64-channel cin tile, BN-channel cout tile) and one slice of the pixels of EVERY sample; register tile 4 x TN.
+constexpr int kWgBM = 64, kWgBK = 16;
+
+template <int TN>
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int splits) {
+    constexpr int BN = 16 * TN;
+    extern __shared__ __align__(16) float wsm[];
+    float *As = wsm;                                                      // [BK][BM + 4]
+    float *Bs = As + kWgBK * (kWgBM + 4);                                 // [BK][BN + 4]
+    float2 *aff = reinterpret_cast<float2 *>(Bs + kWgBK * (BN + 4));      // [B][BM]
+    const int tid = threadIdx.x;
+    const int ci_tiles = (a.cin + kWgBM - 1) / kWgBM, co_tiles = (a.cout + BN - 1) / BN;
+    int tile = blockIdx.y;
+    const int cot = tile % co_tiles;
+    tile /= co_tiles;
+    const int cit = tile % ci_tiles;
+    const int tap = tile / ci_tiles;
+    const int kt = tap / a.KF, kf = tap - kt * a.KF;
+    const int ci0 = cit * kWgBM, co0 = cot * BN;
+    const int npix = a.T * a.Fout;
+    const int per = (npix + splits - 1) / splits;
+    const int p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+
+    for (int i = tid; i < a.B * kWgBM; i += 256) {
+        const int b = i / kWgBM, c = ci0 + (i - b * kWgBM);
+        float2 v = make_float2(1.f, 0.f);
+        if (a.x_sums && c < a.cin) {
+            const double *s = a.x_sums + ((size_t)b * a.x_ctot + a.x_coff + c) * 2;
+            v = affine_from_sums(stat_get(s), stat_get(s + 1), a.inv_n, (double)a.eps);
+        }
+        aff[i] = v;
+    }
+    __syncthreads();
+
+    const int lp = tid >> 4, l4 = tid & 15;
+    const int nchunk = p1 > p0 ? (p1 - p0 + kWgBK - 1) / kWgBK : 0;
+    const int niter = nchunk * a.B;
+    const bool planes = a.x_layout == LAYOUT_PLANES;
+    const size_t x_lo = (size_t)a.x_ctot * a.T * a.Fin;  // bf16 elements from hi to lo plane set
+
+    float4 ra, rb;
+    auto load = [&](int it) {
+        const int b = it / nchunk;
+        const int p = p0 + (it - b * nchunk) * kWgBK + lp;
+        ra = make_float4(0.f, 0.f, 0.f, 0.f);
+        rb = ra;
+        if (p >= p1) return;
+        const int t = p / a.Fout, f = p - t * a.Fout;
+        const int c = ci0 + l4 * 4;
+        if (c < a.cin) {
+            int ti, fi;
+            bool ok = true;
+            if (!a.transposed) {
+                ti = t + kt - a.pad_t;
+                fi = f * a.stride_f + kf - a.pad_f;
+            } else {
+                ti = t + a.pad_t - kt;
+                const int num = f + a.pad_f - kf;
+                fi = num / a.stride_f;
+                ok = num >= 0 && fi * a.stride_f == num;
+            }
+            ok = ok && ti >= 0 && ti < a.T && fi >= 0 && fi < a.Fin;
+            if (ok) {
+                const int ca = a.x_coff + c;
+                float e[4];
+                if (planes) {
+                    const __nv_bfloat16 *xp = reinterpret_cast<const __nv_bfloat16 *>(a.x) + (size_t)b * 2 * x_lo +
+                                              (((size_t)(ca >> 3) * a.T + ti) * a.Fin + fi) * 8 + (ca & 7);
+                    load_e4(xp, x_lo, a.use_lo, e);
+                } else {
+                    const float4 v = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(a.x) +
+                                                                       (((size_t)b * a.T + ti) * a.Fin + fi) * a.x_ctot + ca);
+                    e[0] = v.x;
+                    e[1] = v.y;
+                    e[2] = v.z;
+                    e[3] = v.w;
+                }
+                const float2 *af = aff + b * kWgBM + l4 * 4;
+                ra = make_float4(fmaf(e[0], af[0].x, af[0].y), fmaf(e[1], af[1].x, af[1].y), fmaf(e[2], af[2].x, af[2].y),
+                                 fmaf(e[3], af[3].x, af[3].y));
+                // channels beyond cin inside the last quad cannot occur: cin % 4 == 0
+            }
+        }
+        if (l4 < BN / 4) {
+            const int co = co0 + l4 * 4;
+            if (co < a.cout)
+                rb = *reinterpret_cast<const float4 *>(a.dy + ((size_t)b * npix + p) * a.dy_ctot + a.dy_coff + co);
+        }
+    };
+
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    if (niter > 0) load(0);
+    for (int it = 0; it < niter; ++it) {
+        *reinterpret_cast<float4 *>(As + lp * (kWgBM + 4) + l4 * 4) = ra;
+        if (l4 < BN / 4) *reinterpret_cast<float4 *>(Bs + lp * (BN + 4) + l4 * 4) = rb;
+        __syncthreads();
+        if (it + 1 < niter) load(it + 1);
+#pragma unroll
+        for (int k = 0; k < kWgBK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(As + k * (kWgBM + 4) + ty * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            float bv[TN];
+            if constexpr (TN == 4) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(Bs + k * (BN + 4) + tx * 4);
+                bv[0] = b4.x;
+                bv[1] = b4.y;
+                bv[2] = b4.z;
+                bv[3] = b4.w;
+            } else {
+                const float2 b2 = *reinterpret_cast<const float2 *>(Bs + k * (BN + 4) + tx * 2);
+                bv[0] = b2.x;
+                bv[1] = b2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    const int taps = a.KT * a.KF;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ci = ci0 + ty * 4 + i;
+        if (ci >= a.cin) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int co = co0 + tx * TN + j;
+            if (co >= a.cout) continue;
+            const size_t idx = a.transposed ? ((size_t)ci * a.cout + co) * taps + tap : ((size_t)co * a.cin + ci) * taps + tap;
+            atomicAdd(a.dw + idx, acc[i][j]);
+        }
+    }
+}
+
+__global__ void dgrad_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, int taps, int cin, int cout,
+                                  int cout_pad, int cin_pad) {
+    const int64_t total = (int64_t)taps * cout * cin_pad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin_pad);
+        const int64_t r = i / cin_pad;
+        const int co = (int)(r % cout);
+        const int tap = (int)(r / cout);
+        dst[i] = ci < cin ? src[((size_t)tap * cin + ci) * cout_pad + co] : 0.f;
+    }
+}
+
+// ---- TCN ---------------------------------------------------------------------------------------------------------
+struct GlnStat {
+    float mean, rstd;
+};
+__device__ __forceinline__ GlnStat gln_stat(const double *s, double inv_n, float eps) {
+    const double mean = stat_get(s) * inv_n;
+    double var = stat_get(s + 1) * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    GlnStat g;
+    g.mean = (float)mean;
+    g.rstd = (float)rsqrt(var + (double)eps);
+    return g;
+}
+
+constexpr int kTcnBwFrames = 16;
+
+// y = dwconv(ELU(IN1d(u))) (pre-PReLU) and q = gLN(PReLU(y)) (the pointwise conv's input), both fp32 [B][T][C]
+__global__ void __launch_bounds__(256) tcn_recompute_kernel(const TcnBwdArgs a, float *__restrict__ Y, float *__restrict__ Q) {
+    extern __shared__ float sh[];  // scale, shift, 3 taps, gamma, beta : 7 C
+    const int C = a.C, T = a.T;
+    float *sc = sh, *sf = sh + C, *wt = sh + 2 * C, *gm = sh + 5 * C, *bt = sh + 6 * C;
+    const int b = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double *us = a.u_sums + ((size_t)b * C + c) * 2;
+        const float2 af = affine_from_sums(stat_get(us), stat_get(us + 1), a.inv_T, (double)a.in_eps);
+        sc[c] = af.x;
+        sf[c] = af.y;
+        wt[c] = a.wdw[c * 3];
+        wt[C + c] = a.wdw[c * 3 + 1];
+        wt[2 * C + c] = a.wdw[c * 3 + 2];
+        gm[c] = a.gamma[c];
+        bt[c] = a.beta[c];
+    }
+    __syncthreads();
+    const GlnStat gs = gln_stat(a.g_sums + (size_t)b * 2, a.gln_inv_n, a.gln_eps);
+    const float al = a.alpha[0];
+    const float *ub = a.u + (size_t)b * T * C;
+    const int t0 = blockIdx.x * kTcnBwFrames;
+    for (int i = threadIdx.x; i < kTcnBwFrames * C; i += blockDim.x) {
+        const int tt = i / C, c = i - tt * C;
+        const int t = t0 + tt;
+        if (t >= T) break;
+        auto act = [&](int tq) {
+            if (tq < 0 || tq >= T) return 0.f;
+            return elu1(fmaf(ub[(size_t)tq * C + c], sc[c], sf[c]));
+        };
+        const float y = fmaf(wt[c], act(t - a.dil), fmaf(wt[C + c], act(t), wt[2 * C + c] * act(t + a.dil)));
+        const float p = y > 0.f ? y : al * y;
+        const size_t o = ((size_t)b * T + t) * C + c;
+        Y[o] = y;
+        Q[o] = fmaf(gm[c] * gs.rstd, p - gs.mean, bt[c]);
+    }
+}
+
+constexpr int kTcnRows = 32;  // frames per CTA of the channel-parallel kernels
+constexpr int kTcnCh = 8;     // channels per thread (128 threads): C <= 1024
+
+// gLN backward, pass 1: per-sample sums of g = gamma * dq and g * phat; per-channel gamma / beta gradients
+__global__ void __launch_bounds__(128) gln_bwd_reduce_kernel(const TcnBwdArgs a, const float *__restrict__ DQ,
+                                                             const float *__restrict__ Y, double *__restrict__ gred,
+                                                             float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    __shared__ double red[2][4];
+    const int C = a.C, T = a.T, b = blockIdx.y;
+    const GlnStat gs = gln_stat(a.g_sums + (size_t)b * 2, a.gln_inv_n, a.gln_eps);
+    const float al = a.alpha[0];
+    const int t0 = blockIdx.x * kTcnRows, t1 = min(T, t0 + kTcnRows);
+    float dg[kTcnCh], db[kTcnCh], gam[kTcnCh];
+#pragma unroll
+    for (int k = 0; k < kTcnCh; ++k) {
+        dg[k] = db[k] = 0.f;
+        const int c = threadIdx.x + k * 128;
+        gam[k] = c < C ? a.gamma[c] : 0.f;
+    }
+    float a1 = 0.f, a2 = 0.f;
+    for (int t = t0; t < t1; ++t) {
+        const size_t row = ((size_t)b * T + t) * C;
+#pragma unroll
+        for (int k = 0; k < kTcnCh; ++k) {
+            const int c = threadIdx.x + k * 128;
+            if (c < C) {
+                const float dq = DQ[row + c], y = Y[row + c];
+                const float p = y > 0.f ? y : al * y;
+                const float ph = (p - gs.mean) * gs.rstd;
+                const float g = gam[k] * dq;
+                a1 += g;
+                a2 = fmaf(g, ph, a2);
+                dg[k] = fmaf(dq, ph, dg[k]);
+                db[k] += dq;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kTcnCh; ++k) {
+        const int c = threadIdx.x + k * 128;
+        if (c < C) {
+            atomicAdd(dgamma + c, dg[k]);
+            atomicAdd(dbeta + c, db[k]);
+        }
+    }
+    double d1 = warp_sum((double)a1), d2 = warp_sum((double)a2);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = d1;
+        red[1][threadIdx.x >> 5] = d2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(gred + (size_t)b * 2, red[0][0] + red[0][1] + red[0][2] + red[0][3]);
+        atomicAdd(gred + (size_t)b * 2 + 1, red[1][0] + red[1][1] + red[1][2] + red[1][3]);
+    }
+}
+
+// gLN backward, pass 2, fused with the PReLU backward: DQ becomes dL/dy in place; alpha gradient
+__global__ void __launch_bounds__(128) gln_bwd_apply_kernel(const TcnBwdArgs a, float *__restrict__ DQ, const float *__restrict__ Y,
+                                                            const double *__restrict__ gred, float *__restrict__ dalpha) {
+    __shared__ float red[4];
+    const int C = a.C, T = a.T, b = blockIdx.y;
+    const GlnStat gs = gln_stat(a.g_sums + (size_t)b * 2, a.gln_inv_n, a.gln_eps);
+    const float al = a.alpha[0];
+    const float m1 = (float)(gred[(size_t)b * 2] * a.gln_inv_n), m2 = (float)(gred[(size_t)b * 2 + 1] * a.gln_inv_n);
+    const int t0 = blockIdx.x * kTcnRows, t1 = min(T, t0 + kTcnRows);
+    float da = 0.f;
+    for (int t = t0; t < t1; ++t) {
+        const size_t row = ((size_t)b * T + t) * C;
+        for (int c = threadIdx.x; c < C; c += 128) {
+            const float dq = DQ[row + c], y = Y[row + c];
+            const float p = y > 0.f ? y : al * y;
+            const float ph = (p - gs.mean) * gs.rstd;
+            const float dp = gs.rstd * (a.gamma[c] * dq - m1 - ph * m2);
+            if (y > 0.f) {
+                DQ[row + c] = dp;
+            } else {
+                DQ[row + c] = dp * al;
+                da = fmaf(dp, y, da);
+            }
+        }
+    }
+    da = warp_sum(da);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = da;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(dalpha, red[0] + red[1] + red[2] + red[3]);
+}
+
+// depthwise conv + ELU backward: DN = dL/dn (n = IN1d(u)), its per-(b,c) sums for the InstanceNorm1d backward, and
+// the depthwise weight gradient
+__global__ void __launch_bounds__(128) dw_bwd_kernel(const TcnBwdArgs a, const float *__restrict__ DY, float *__restrict__ DN,
+                                                     double *__restrict__ ired, float *__restrict__ dwdw) {
+    const int C = a.C, T = a.T, b = blockIdx.y, d = a.dil;
+    const int t0 = blockIdx.x * kTcnRows, t1 = min(T, t0 + kTcnRows);
+    const float *ub = a.u + (size_t)b * T * C;
+    const float *dyb = DY + (size_t)b * T * C;
+    for (int c = threadIdx.x; c < C; c += 128) {
+        const double *us = a.u_sums + ((size_t)b * C + c) * 2;
+        const float2 af = affine_from_sums(stat_get(us), stat_get(us + 1), a.inv_T, (double)a.in_eps);
+        const float w0 = a.wdw[c * 3], w1 = a.wdw[c * 3 + 1], w2 = a.wdw[c * 3 + 2];
+        float s1 = 0.f, s2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        auto nrm = [&](int tq) { return fmaf(ub[(size_t)tq * C + c], af.x, af.y); };
+        auto dyat = [&](int tq) { return (tq >= 0 && tq < T) ? dyb[(size_t)tq * C + c] : 0.f; };
+        auto vat = [&](int tq) { return (tq >= 0 && tq < T) ? elu1(nrm(tq)) : 0.f; };
+        for (int t = t0; t < t1; ++t) {
+            // forward: y[t] = w0 v[t-d] + w1 v[t] + w2 v[t+d]
+            const float dy = dyat(t);
+            const float dv = fmaf(w0, dyat(t + d), fmaf(w1, dy, w2 * dyat(t - d)));
+            const float n = nrm(t);
+            const float dn = n > 0.f ? dv : dv * expf(n);
+            DN[((size_t)b * T + t) * C + c] = dn;
+            s1 += dn;
+            s2 = fmaf(dn, n, s2);
+            g0 = fmaf(dy, vat(t - d), g0);
+            g1 = fmaf(dy, n > 0.f ? n : expm1f(n), g1);
+            g2 = fmaf(dy, vat(t + d), g2);
+        }
+        atomicAdd(ired + ((size_t)b * C + c) * 2, (double)s1);
+        atomicAdd(ired + ((size_t)b * C + c) * 2 + 1, (double)s2);
+        atomicAdd(dwdw + c * 3, g0);
+        atomicAdd(dwdw + c * 3 + 1, g1);
+        atomicAdd(dwdw + c * 3 + 2, g2);
+    }
+}
+
+// InstanceNorm1d backward: du = rstd * (dn - mean(dn) - n * mean(dn * n))
+__global__ void __launch_bounds__(128) in1d_bwd_apply_kernel(const TcnBwdArgs a, const float *__restrict__ DN,
+                                                             const double *__restrict__ ired, float *__restrict__ out,
+                                                             int accumulate) {
+    const int C = a.C, T = a.T, b = blockIdx.y;
+    const int t0 = blockIdx.x * kTcnRows, t1 = min(T, t0 + kTcnRows);
+    for (int c = threadIdx.x; c < C; c += 128) {
+        const double *us = a.u_sums + ((size_t)b * C + c) * 2;
+        const float2 af = affine_from_sums(stat_get(us), stat_get(us + 1), a.inv_T, (double)a.in_eps);
+        const float m1 = (float)(ired[((size_t)b * C + c) * 2] * a.inv_T), m2 = (float)(ired[((size_t)b * C + c) * 2 + 1] * a.inv_T);
+        for (int t = t0; t < t1; ++t) {
+            const size_t o = ((size_t)b * T + t) * C + c;
+            const float n = fmaf(a.u[o], af.x, af.y);
+            const float du = af.x * (DN[o] - m1 - n * m2);
+            out[o] = accumulate ? out[o] + du : du;
+        }
+    }
+}
+
+__global__ void copy_channels_kernel(const float *__restrict__ src, int sctot, int scoff, float *__restrict__ dst, int dctot,
+                                     int dcoff, int C, int64_t rows, int accumulate) {
+    const int64_t total = rows * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        const float v = src[r * sctot + scoff + c];
+        float *d = dst + r * dctot + dcoff + c;
+        *d = accumulate ? *d + v : v;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ launchers ----
+int launch_in_bwd(const InBwdArgs &a, cudaStream_t st) {
+    MISO_REQUIRE(a.c % 4 == 0 && a.coff % 4 == 0 && a.ctot % 4 == 0 && a.c >= 4 && a.c <= 4 * kEw,
+                 "in_bwd: channel range (c=%d coff=%d ctot=%d) must be multiples of 4, c <= %d", a.c, a.coff, a.ctot, 4 * kEw);
+    const int lanes = kEw / (a.c / 4);
+    // enough CTAs to fill the machine, at least 8 pixels per lane
+    int chunks = ceil_div(a.npix, lanes * 8);
+    const int cap = std::max(1, ceil_div(148 * 8, a.B));
+    if (chunks > cap) chunks = cap;
+    const int per = ceil_div(a.npix, chunks);
+    chunks = ceil_div(a.npix, per);
+    dim3 grid(chunks, a.B);
+    if (!a.plain) {
+        MISO_CUDA(cudaMemsetAsync(a.red, 0, (size_t)a.B * a.c * 2 * sizeof(double), st));
+        in_bwd_reduce_kernel<<<grid, kEw, 2 * a.c * sizeof(float), st>>>(a, per);
+        MISO_LAUNCHED("in_bwd_reduce_kernel");
+    }
+    in_bwd_apply_kernel<<<grid, kEw, a.c * sizeof(float), st>>>(a, per);
+    MISO_LAUNCHED("in_bwd_apply_kernel");
+    return MISO_OK;
+}
+
+template <int TN>
+static int launch_wgrad_t(const WgradArgs &a, cudaStream_t st) {
+    constexpr int BN = 16 * TN;
+    const int taps = a.KT * a.KF;
+    const int ntile = taps * ceil_div(a.cin, kWgBM) * ceil_div(a.cout, BN);
+    const int npix = a.T * a.Fout;
+    int splits = ceil_div(4 * 148, ntile);
+    splits = std::max(1, std::min(splits, ceil_div(npix, 4 * kWgBK)));
+    const size_t smem = (size_t)(kWgBK * (kWgBM + 4) + kWgBK * (BN + 4)) * sizeof(float) + (size_t)a.B * kWgBM * sizeof(float2);
+    MISO_REQUIRE(smem <= 200 * 1024, "wgrad: batch %d too large for the per-sample affine table", a.B);
+    static size_t attr_set[2] = {0, 0};
+    size_t &cur = attr_set[TN == 4 ? 1 : 0];
+    if (smem > 48 * 1024 && smem > cur) {
+        MISO_CUDA(cudaFuncSetAttribute(wgrad_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    wgrad_kernel<TN><<<dim3(splits, ntile), 256, smem, st>>>(a, splits);
+    MISO_LAUNCHED("wgrad_kernel");
+    return MISO_OK;
+}
+
+int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
+    MISO_REQUIRE(a.cin % 4 == 0 && a.x_coff % 4 == 0 && a.x_ctot % 4 == 0, "wgrad: input channels must be multiples of 4");
+    MISO_REQUIRE(a.cout % 4 == 0 && a.dy_coff % 4 == 0 && a.dy_ctot % 4 == 0,
+                 "wgrad: output channels must be multiples of 4 (cout=%d)", a.cout);
+    MISO_REQUIRE(a.x_layout != LAYOUT_PLANES || a.x_ctot % 8 == 0, "wgrad: plane layout needs ctot %% 8 == 0");
+    if (a.cout <= 32) return launch_wgrad_t<2>(a, st);
+    return launch_wgrad_t<4>(a, st);
+}
+
+int launch_dgrad_pack(const float *src, float *dst, int taps, int cin, int cout, int cout_pad, int cin_pad, cudaStream_t st) {
+    const int64_t total = (int64_t)taps * cout * cin_pad;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    dgrad_pack_kernel<<<blocks, 256, 0, st>>>(src, dst, taps, cin, cout, cout_pad, cin_pad);
+    MISO_LAUNCHED("dgrad_pack_kernel");
+    return MISO_OK;
+}
+
+int launch_tcn_recompute(const TcnBwdArgs &a, float *Y, float *Q, cudaStream_t st) {
+    tcn_recompute_kernel<<<dim3(ceil_div(a.T, kTcnBwFrames), a.B), 256, 7 * a.C * sizeof(float), st>>>(a, Y, Q);
+    MISO_LAUNCHED("tcn_recompute_kernel");
+    return MISO_OK;
+}
+
+int launch_gln_bwd(const TcnBwdArgs &a, float *DQ, const float *Y, double *gred, float *dgamma, float *dbeta, float *dalpha,
+                   cudaStream_t st) {
+    MISO_REQUIRE(a.C <= 128 * kTcnCh, "gln_bwd: C=%d > %d", a.C, 128 * kTcnCh);
+    MISO_CUDA(cudaMemsetAsync(gred, 0, (size_t)a.B * 2 * sizeof(double), st));
+    dim3 grid(ceil_div(a.T, kTcnRows), a.B);
+    gln_bwd_reduce_kernel<<<grid, 128, 0, st>>>(a, DQ, Y, gred, dgamma, dbeta);
+    MISO_LAUNCHED("gln_bwd_reduce_kernel");
+    gln_bwd_apply_kernel<<<grid, 128, 0, st>>>(a, DQ, Y, gred, dalpha);
+    MISO_LAUNCHED("gln_bwd_apply_kernel");
+    return MISO_OK;
+}
+
+int launch_dw_bwd(const TcnBwdArgs &a, const float *DY, float *DN, double *ired, float *dwdw, float *out, int accumulate,
+                  cudaStream_t st) {
+    MISO_CUDA(cudaMemsetAsync(ired, 0, (size_t)a.B * a.C * 2 * sizeof(double), st));
+    dim3 grid(ceil_div(a.T, kTcnRows), a.B);
+    dw_bwd_kernel<<<grid, 128, 0, st>>>(a, DY, DN, ired, dwdw);
+    MISO_LAUNCHED("dw_bwd_kernel");
+    in1d_bwd_apply_kernel<<<grid, 128, 0, st>>>(a, DN, ired, out, accumulate);
+    MISO_LAUNCHED("in1d_bwd_apply_kernel");
+    return MISO_OK;
+}
+
+int launch_copy_channels(const float *src, int sctot, int scoff, float *dst, int dctot, int dcoff, int C, int64_t rows,
+                         int accumulate, cudaStream_t st) {
+    const int64_t total = rows * C;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    copy_channels_kernel<<<blocks, 256, 0, st>>>(src, sctot, scoff, dst, dctot, dcoff, C, rows, accumulate);
+    MISO_LAUNCHED("copy_channels_kernel");
+    return MISO_OK;
+}
+
+}  // namespace miso
+
+// =========================================================================== C ABI =====
+namespace miso {
+namespace {
+
+struct BwdPerms {
+    signed char p[24][4];
+};
+
+// gradient of criterion.py:8-63 w.r.t. the estimate, for the winning permutation of every utterance:
+// L = (1/B) sum_b sum_i [ |re_i - r.re| + |im_i - r.im| + | sqrt(re^2 + im^2 + 1e-8) - |r| | ],  r = ref[perm_b[i]]
+__global__ void upit_bwd_kernel(const float2 *__restrict__ est, int64_t e_sb, int64_t e_ss, const float2 *__restrict__ ref,
+                                int64_t r_sb, int64_t r_ss, const int64_t *__restrict__ idx, BwdPerms perms, int B, int S, int64_t n,
+                                const float *__restrict__ gout, float2 *__restrict__ grad) {
+    const int64_t total = (int64_t)B * S * n;
+    const float scale = gout[0] / (float)B;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i % n;
+        const int64_t r = i / n;
+        const int s = (int)(r % S), b = (int)(r / S);
+        const int j = perms.p[(int)idx[b]][s];
+        const float2 x = est[b * e_sb + s * e_ss + e];
+        const float2 y = ref[b * r_sb + j * r_ss + e];
+        const float mag = sqrtf(x.x * x.x + x.y * x.y + 1e-8f);
+        const float rm = sqrtf(y.x * y.x + y.y * y.y);
+        auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+        const float sm = sgn(mag - rm) / mag;
+        grad[i] = make_float2(scale * (sgn(x.x - y.x) + sm * x.x), scale * (sgn(x.y - y.y) + sm * x.y));
+    }
+}
+
+// complex gradient [B][S][n] -> the network output layout fp32 [B][n][2S] (re of every speaker, then im)
+__global__ void grad_pack_kernel(const float2 *__restrict__ g, float *__restrict__ gy, int B, int S, int64_t n) {
+    const int64_t total = (int64_t)B * n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / n, e = i - b * n;
+        for (int s = 0; s < S; ++s) {
+            const float2 v = g[(b * S + s) * n + e];
+            gy[i * 2 * S + s] = v.x;
+            gy[i * 2 * S + S + s] = v.y;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace miso
+
+extern "C" {
+
+int miso_upit_bwd(const void *d_est, int64_t e_sb, int64_t e_ss, const void *d_ref, int64_t r_sb, int64_t r_ss,
+                  const int64_t *d_perm_idx, int B, int S, int T, int F, const float *d_gout, void *d_grad, void *stream) {
+    using namespace miso;
+    MISO_REQUIRE(d_est && d_ref && d_perm_idx && d_gout && d_grad, "miso_upit_bwd: null argument");
+    MISO_REQUIRE(S >= 1 && S <= 4 && B >= 1, "miso_upit_bwd: S=%d unsupported (1..4)", S);
+    BwdPerms t;
+    int id[4] = {0, 1, 2, 3}, np = 0;
+    do {  // lexicographic order == itertools.permutations(range(S)) (criterion.py:49), as in align.cu
+        for (int i = 0; i < 4; ++i) t.p[np][i] = (signed char)(i < S ? id[i] : 0);
+        np++;
+    } while (std::next_permutation(id, id + S));
+    const int64_t n = (int64_t)T * F;
+    const int blocks = (int)std::min<int64_t>(((int64_t)B * S * n + 255) / 256, 148 * 16);
+    upit_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2 *>(d_est), e_sb, e_ss,
+                                                          reinterpret_cast<const float2 *>(d_ref), r_sb, r_ss, d_perm_idx, t, B, S, n,
+                                                          d_gout, reinterpret_cast<float2 *>(d_grad));
+    MISO_LAUNCHED("upit_bwd_kernel");
+    return MISO_OK;
+}
+
+int miso_grad_pack(const void *d_grad, float *d_gy, int B, int S, int T, int F, void *stream) {
+    using namespace miso;
+    MISO_REQUIRE(d_grad && d_gy && S >= 1, "miso_grad_pack: bad argument");
+    const int64_t n = (int64_t)T * F;
+    const int blocks = (int)std::min<int64_t>((B * n + 255) / 256, 148 * 16);
+    grad_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2 *>(d_grad), d_gy, B, S, n);
+    MISO_LAUNCHED("grad_pack_kernel");
+    return MISO_OK;
+}
+
+}  // extern "C"

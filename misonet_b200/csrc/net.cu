@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "bwd.cuh"
 #include "conv.cuh"
 #include "tcn.cuh"
 
@@ -430,12 +431,23 @@ struct BufDesc {
     double *sums = nullptr;
     int ctot = 0, F = 0;
     size_t lo_off = 0;  // bytes from a sample's hi plane set to its lo plane set
+    float *grad = nullptr;  // training plan: gradient buffer, fp32 channels-last [B][T][F][ctot]
 };
 
 struct Plan {
     std::vector<int> Fx;
     std::vector<BufDesc> E, D, Y;
     float *S = nullptr, *U = nullptr, *P = nullptr;
+    // TCN state per block: block k reads Sk[k] / Uk[k].  Inference: all alias S / U (in-place residual stream);
+    // training plan: one buffer per block, kept for the backward pass.
+    std::vector<float *> Sk, Uk;
+    // training plan only
+    bool train = false;
+    char *grad_base = nullptr;  // all gradient buffers, contiguous (one memset)
+    size_t grad_bytes = 0;
+    float *gS = nullptr, *gU = nullptr, *tY = nullptr, *tQ = nullptr, *tDQ = nullptr, *tDN = nullptr;
+    double *bred = nullptr;  // reduction scratch of the norm backward kernels
+    float *wT = nullptr;     // data-gradient (transposed) weights of the layer being processed
     void *tcn_wimg = nullptr;  // tensor-core pointwise convs: weight images and W beta / W gamma vectors (tcn.cu)
     float *tcn_wvec = nullptr;
     std::vector<double *> sS, sU, g1, g2;
@@ -447,7 +459,7 @@ struct Plan {
 
 size_t plane_bytes(int B, int ctot, int T, int F) { return (size_t)B * ctot * T * F * 4; }  // hi + lo bf16
 
-bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
+bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, bool train = false) {
     if (!encoder_sizes(n, F, pl.Fx)) return false;
     const int nb = n->nb;
     size_t off = 0;
@@ -515,6 +527,44 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
     pl.S = reinterpret_cast<float *>(take(tcn_bytes));
     pl.U = reinterpret_cast<float *>(take(tcn_bytes));
     pl.P = reinterpret_cast<float *>(take(tcn_bytes));
+    pl.train = train;
+    {
+        const int nblk_ = n->R * n->X;
+        pl.Sk.assign(nblk_, pl.S);
+        pl.Uk.assign(nblk_, pl.U);
+        if (train) {
+            for (int k = 1; k < nblk_; ++k) pl.Sk[k] = reinterpret_cast<float *>(take(tcn_bytes));
+            for (int k = 1; k < nblk_; ++k) pl.Uk[k] = reinterpret_cast<float *>(take(tcn_bytes));
+            // gradient buffers: same element counts as the activation buffers, fp32 channels-last
+            const size_t g0 = off;
+            auto gtake = [&](const BufDesc &d) { return reinterpret_cast<float *>(take((size_t)B * d.ctot * T * d.F * sizeof(float))); };
+            for (int i = 0; i < nb; ++i)
+                if (dense_enc(i)) pl.E[i].grad = gtake(pl.E[i]);
+            for (int j = 0; j < nb; ++j) {
+                pl.D[j].grad = gtake(pl.D[j]);
+                if (dense_dec(j)) pl.Y[j].grad = gtake(pl.Y[j]);
+            }
+            pl.grad_base = base ? base + g0 : nullptr;
+            pl.grad_bytes = off - g0;
+            pl.gS = reinterpret_cast<float *>(take(tcn_bytes));
+            pl.gU = reinterpret_cast<float *>(take(tcn_bytes));
+            pl.tY = reinterpret_cast<float *>(take(tcn_bytes));
+            pl.tQ = reinterpret_cast<float *>(take(tcn_bytes));
+            pl.tDQ = reinterpret_cast<float *>(take(tcn_bytes));
+            pl.tDN = reinterpret_cast<float *>(take(tcn_bytes));
+            int maxc = n->C;
+            size_t maxw = 0;
+            for (auto &p : n->params) {
+                if (p.kind == P_CONV_W || p.kind == P_DECONV_W || p.kind == P_PW_W) {
+                    maxc = std::max(maxc, std::max(p.cin, p.cout));
+                    const int bn = conv_fp32_tile_n(p.cin);
+                    maxw = std::max(maxw, (size_t)p.taps * p.cout * ((p.cin + bn - 1) / bn * bn));
+                }
+            }
+            pl.bred = reinterpret_cast<double *>(take(((size_t)B * maxc * 2 + 2 * (size_t)B) * sizeof(double)));
+            pl.wT = reinterpret_cast<float *>(take(maxw * sizeof(float)));
+        }
+    }
     if (tcn_pw_eligible(n->C)) {
         size_t wi, wv;
         tcn_pw_scratch_need(n->C, 2 * nblk, &wi, &wv);
@@ -557,6 +607,16 @@ ViewRef xs_view(const miso_net *n, const Plan &pl, int i) {
     return ViewRef{&pl.D[j], n->de[j], n->en[i + 1]};
 }
 
+// A conv layer of the forward launch sequence as the backward pass needs it (recorded by the same walker that
+// launches the forward, so the two can never disagree about views, strides or statistics).
+struct ConvRec {
+    int kind;  // 0: conv layer, 1: the TCN sits here
+    ConvArgs a;
+    const ConvDesc *cd;
+    float *in_grad;   // gradient buffer of the input buffer (null: the network input, no data gradient)
+    float *out_grad;  // gradient buffer of the output buffer (null: the network output, gradient supplied by the caller)
+};
+
 // One pass over the layer list.  dry = true only sizes the tensor-core scratch (no launches).
 struct Walker {
     const miso_net *n;
@@ -565,6 +625,7 @@ struct Walker {
     cudaStream_t st;
     bool dry;
     size_t need_w = 0, need_b = 0;
+    std::vector<ConvRec> *record = nullptr;  // non-null: list the layers instead of launching them
 
     int conv(const ConvDesc &cd, bool transposed, const BufDesc *inb, const void *in_raw, int in_ctot, int in_coff, int Fin,
              const double *in_sums, const BufDesc *outb, float *out_raw, int out_ctot, int out_coff, int Fout, double *out_sums,
@@ -603,6 +664,10 @@ struct Walker {
         a.norm_eps = kInEps;
         a.norm_inv_n = 1.0 / ((double)T * Fin);
         a.elu = elu ? 1 : 0;
+        if (record) {
+            record->push_back(ConvRec{0, a, &cd, inb ? inb->grad : nullptr, outb ? outb->grad : nullptr});
+            return MISO_OK;
+        }
         const bool tc = conv_tc_eligible(a);
         if (dry) {
             if (tc) {
@@ -668,14 +733,16 @@ int Walker::run(const void *d_x, float *d_y) {
     }
 
     // ---------------- TCN (model.py:486-567) ----------------
-    {
+    if (record) {
+        record->push_back(ConvRec{1, ConvArgs{}, nullptr, nullptr, nullptr});
+    } else {
         const BufDesc &d0 = pl.D[0];
         const double inv_T = 1.0 / (double)T;
         const int use_lo = n->mode == 2 ? 0 : 1;
         dim3 grid(ceil_div(T, kTcnTile), ceil_div(C, 128), B);
         if (!dry) {
             tcn_prep_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(d0.p), d0.ctot, C, use_lo, d0.sums,
-                                                  inv_T, kInEps, pl.S, pl.sS[0], T, C);
+                                                  inv_T, kInEps, pl.Sk[0], pl.sS[0], T, C);
             MISO_LAUNCHED("tcn_prep_kernel");
         }
         const int nblk = n->R * n->X;
@@ -696,7 +763,7 @@ int Walker::run(const void *d_x, float *d_y) {
             const int dil = 1 << (k % n->X);
             for (int half = 0; half < 2; ++half) {
                 const TcnHalf &h = n->tcn[k * 2 + half];
-                const float *u = half == 0 ? pl.S : pl.U;
+                const float *u = half == 0 ? pl.Sk[k] : pl.Uk[k];
                 const double *us = half == 0 ? pl.sS[k] : pl.sU[k];
                 double *gs = half == 0 ? pl.g1[k] : pl.g2[k];
                 const bool tc_pw = (dry || n->mode != 0) && C % 8 == 0;
@@ -737,17 +804,17 @@ int Walker::run(const void *d_x, float *d_y) {
                 a.norm_inv_n = 1.0 / ((double)C * T);
                 a.elu = 0;
                 if (half == 0) {
-                    a.out = pl.U;
+                    a.out = pl.Uk[k];
                     a.out_ctot = C;
                     a.out_coff = 0;
                     a.out_sums = pl.sU[k];
                     a.resid = nullptr;
                 } else {
-                    a.resid = pl.S;
+                    a.resid = pl.Sk[k];
                     a.resid_ctot = C;
                     a.resid_coff = 0;
                     if (k + 1 < nblk) {
-                        a.out = pl.S;  // in-place residual update: each element is read once by its own writer
+                        a.out = pl.Sk[k + 1];  // inference: in-place residual update (each element is read once by its own writer)
                         a.out_ctot = C;
                         a.out_coff = 0;
                         a.out_sums = pl.sS[k + 1];
@@ -829,8 +896,8 @@ int Walker::run(const void *d_x, float *d_y) {
 
 int enqueue_forward(miso_net *net, const Plan &pl, const void *d_x, float *d_y, int B, int T, int F, cudaStream_t st);
 
-bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl) {
-    if (!make_plan(n, B, T, F, base, pl)) return false;
+bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, bool train = false) {
+    if (!make_plan(n, B, T, F, base, pl, train)) return false;
     Walker w{n, pl, B, T, F, nullptr, true};
     w.run(nullptr, nullptr);
     plan_scratch(pl, base, w.need_w, w.need_b);
@@ -1199,6 +1266,295 @@ int miso_unpack_complex(const float *d_y, void *d_out, int B, int S, int T, int 
     unpack_complex_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(d_y, reinterpret_cast<float2 *>(d_out),
                                                                                   B, S, T * F);
     MISO_LAUNCHED("unpack_complex_kernel");
+    return MISO_OK;
+}
+
+}  // extern "C"
+
+// =========================================================================== training =====
+// Forward that keeps what the backward pass needs (per-block TCN state) and the backward pass itself
+// (reference trainer.py:159-212: model(mix) -> loss_uPIT -> loss.backward()).
+namespace miso {
+namespace {
+
+int param_grad_offsets(const miso_net *n, std::vector<int64_t> &off) {
+    off.assign(n->params.size() + 1, 0);
+    for (size_t i = 0; i < n->params.size(); ++i) off[i + 1] = off[i] + n->params[i].numel;
+    return MISO_OK;
+}
+
+struct Backward {
+    const miso_net *n;
+    const Plan &pl;
+    int B, T, F;
+    cudaStream_t st;
+    float *grads;
+    std::vector<int64_t> goff;
+
+    float *g(int param) const { return grads + goff[param]; }
+
+    // data gradient of one layer through the forward FMA kernel with transposed weights: in' = dL/dy (channels-last),
+    // out' = the input buffer's gradient, accumulated in place (resid == out)
+    int dgrad(const ConvArgs &f, const float *w_packed, int cout_pad_fwd, const float *dy, float *din) {
+        const int bn = conv_fp32_tile_n(f.cin);
+        const int cin_pad = (f.cin + bn - 1) / bn * bn;
+        int rc = launch_dgrad_pack(w_packed, pl.wT, f.KT * f.KF, f.cin, f.cout, cout_pad_fwd, cin_pad, st);
+        if (rc) return rc;
+        ConvArgs a{};
+        a.in = dy;
+        a.in_layout = LAYOUT_CL_F32;
+        a.w = pl.wT;
+        a.bias = nullptr;
+        a.out = din;
+        a.out_layout = LAYOUT_CL_F32;
+        a.resid = din;
+        a.resid_ctot = f.in_ctot;
+        a.resid_coff = f.in_coff;
+        a.in_sums = nullptr;
+        a.out_sums = nullptr;
+        a.B = B;
+        a.T = T;
+        a.Fin = f.Fout;
+        a.Fout = f.Fin;
+        a.in_ctot = f.out_ctot;
+        a.in_coff = f.out_coff;
+        a.cin = f.cout;
+        a.out_ctot = f.in_ctot;
+        a.out_coff = f.in_coff;
+        a.cout = f.cin;
+        a.cout_pad = cin_pad;
+        a.KT = f.KT;
+        a.KF = f.KF;
+        a.stride_f = f.stride_f;
+        a.pad_t = f.pad_t;
+        a.pad_f = f.pad_f;
+        a.transposed = f.transposed ? 0 : 1;
+        a.norm_mode = NORM_NONE;
+        a.elu = 0;
+        a.use_lo = 1;
+        return launch_conv_fp32(a, st);
+    }
+
+    int conv_layer(const ConvRec &r, float *d_gy) {
+        const ConvArgs &f = r.a;
+        float *og = r.out_grad ? r.out_grad : d_gy;
+        int rc;
+        InBwdArgs ib{};
+        ib.e = reinterpret_cast<const __nv_bfloat16 *>(f.out);
+        ib.g = og;
+        ib.sums = f.out_sums;
+        ib.red = pl.bred;
+        ib.dbias = g(r.cd->b);
+        ib.B = B;
+        ib.npix = T * f.Fout;
+        ib.ctot = f.out_ctot;
+        ib.coff = f.out_coff;
+        ib.c = f.cout;
+        ib.use_lo = f.use_lo;
+        ib.inv_n = 1.0 / ((double)T * f.Fout);
+        ib.eps = kInEps;
+        ib.plain = f.elu ? 0 : 1;
+        if (!ib.plain && (!f.out_sums || f.out_layout != LAYOUT_PLANES)) {
+            set_error("backward: normalised layer without statistics");
+            return MISO_E_STATE;
+        }
+        rc = launch_in_bwd(ib, st);
+        if (rc) return rc;
+        WgradArgs w{};
+        w.x = f.in;
+        w.x_layout = f.in_layout;
+        w.use_lo = f.use_lo;
+        w.x_sums = f.in_sums;
+        w.inv_n = f.norm_inv_n;
+        w.eps = f.norm_eps;
+        w.dy = og;
+        w.dw = g(r.cd->w);
+        w.B = B;
+        w.T = T;
+        w.Fin = f.Fin;
+        w.Fout = f.Fout;
+        w.x_ctot = f.in_ctot;
+        w.x_coff = f.in_coff;
+        w.cin = f.cin;
+        w.dy_ctot = f.out_ctot;
+        w.dy_coff = f.out_coff;
+        w.cout = f.cout;
+        w.KT = f.KT;
+        w.KF = f.KF;
+        w.stride_f = f.stride_f;
+        w.pad_t = f.pad_t;
+        w.pad_f = f.pad_f;
+        w.transposed = f.transposed;
+        rc = launch_wgrad(w, st);
+        if (rc) return rc;
+        if (r.in_grad) rc = dgrad(f, n->params[r.cd->w].d, r.cd->cout_pad, og, r.in_grad);
+        return rc;
+    }
+
+    // one half of a TemporalBlock: upstream `dout` (gradient of the pointwise conv's output) -> gradient of the half's
+    // input written / accumulated into `din`
+    int tcn_half(int k, int half, const float *dout, float *din, int accumulate) {
+        const int C = n->C;
+        const TcnHalf &h = n->tcn[k * 2 + half];
+        TcnBwdArgs a{};
+        a.u = half == 0 ? pl.Sk[k] : pl.Uk[k];
+        a.u_sums = half == 0 ? pl.sS[k] : pl.sU[k];
+        a.inv_T = 1.0 / (double)T;
+        a.in_eps = kInEps;
+        a.g_sums = half == 0 ? pl.g1[k] : pl.g2[k];
+        a.gln_inv_n = 1.0 / ((double)C * T);
+        a.gln_eps = kGlnEps;
+        a.wdw = n->params[h.dw].d;
+        a.alpha = n->params[h.alpha].d;
+        a.gamma = n->params[h.gamma].d;
+        a.beta = n->params[h.beta].d;
+        a.B = B;
+        a.T = T;
+        a.C = C;
+        a.dil = 1 << (k % n->X);
+        int rc = launch_tcn_recompute(a, pl.tY, pl.tQ, st);
+        if (rc) return rc;
+        // pointwise conv: weight gradient from q, data gradient into tDQ
+        ConvArgs f{};
+        f.in = pl.tQ;
+        f.in_layout = LAYOUT_CL_F32;
+        f.out_layout = LAYOUT_CL_F32;
+        f.use_lo = 1;
+        f.B = B;
+        f.T = T;
+        f.Fin = 1;
+        f.Fout = 1;
+        f.in_ctot = C;
+        f.in_coff = 0;
+        f.cin = C;
+        f.out_ctot = C;
+        f.out_coff = 0;
+        f.cout = C;
+        f.KT = 1;
+        f.KF = 1;
+        f.stride_f = 1;
+        f.pad_t = 0;
+        f.pad_f = 0;
+        f.transposed = 0;
+        WgradArgs w{};
+        w.x = pl.tQ;
+        w.x_layout = LAYOUT_CL_F32;
+        w.use_lo = 1;
+        w.x_sums = nullptr;
+        w.inv_n = 1.0;
+        w.eps = 0.f;
+        w.dy = dout;
+        w.dw = g(h.pw);
+        w.B = B;
+        w.T = T;
+        w.Fin = 1;
+        w.Fout = 1;
+        w.x_ctot = C;
+        w.x_coff = 0;
+        w.cin = C;
+        w.dy_ctot = C;
+        w.dy_coff = 0;
+        w.cout = C;
+        w.KT = 1;
+        w.KF = 1;
+        w.stride_f = 1;
+        w.pad_t = 0;
+        w.pad_f = 0;
+        w.transposed = 0;
+        rc = launch_wgrad(w, st);
+        if (rc) return rc;
+        MISO_CUDA(cudaMemsetAsync(pl.tDQ, 0, (size_t)B * T * C * sizeof(float), st));
+        rc = dgrad(f, n->params[h.pw].d, n->params[h.pw].cout_pad, dout, pl.tDQ);
+        if (rc) return rc;
+        rc = launch_gln_bwd(a, pl.tDQ, pl.tY, pl.bred, g(h.gamma), g(h.beta), g(h.alpha), st);
+        if (rc) return rc;
+        return launch_dw_bwd(a, pl.tDQ, pl.tDN, pl.bred, g(h.dw), din, accumulate, st);
+    }
+
+    int tcn() {
+        const int C = n->C;
+        const BufDesc &d0 = pl.D[0];
+        const int64_t rows = (int64_t)B * T;
+        // upstream: the TCN output is consumed raw as channels [0, C) of decoder 0's buffer (model.py:97-99)
+        int rc = launch_copy_channels(d0.grad, d0.ctot, 0, pl.gS, C, 0, C, rows, 0, st);
+        if (rc) return rc;
+        for (int k = n->R * n->X - 1; k >= 0; --k) {
+            rc = tcn_half(k, 1, pl.gS, pl.gU, 0);  // y = half1(U_k) + S_k
+            if (rc) return rc;
+            rc = tcn_half(k, 0, pl.gU, pl.gS, 1);  // dS_k = dS_{k+1} + d half0
+            if (rc) return rc;
+        }
+        // S_0 = InstanceNorm(last encoder's output) = the normalised view of channels [C, 2C) of decoder 0's buffer
+        return launch_copy_channels(pl.gS, C, 0, d0.grad, d0.ctot, C, C, rows, 1, st);
+    }
+};
+
+}  // namespace
+}  // namespace miso
+
+extern "C" {
+
+int64_t miso_net_grad_numel(const miso_net_t *net) {
+    if (!net) return -1;
+    int64_t t = 0;
+    for (auto &p : net->params) t += p.numel;
+    return t;
+}
+
+size_t miso_net_train_workspace_bytes(const miso_net_t *net, int B, int T, int F) {
+    if (!net || B <= 0 || T <= 0) return 0;
+    Plan pl;
+    if (!full_plan(net, B, T, F, nullptr, pl, true)) return 0;
+    return pl.total;
+}
+
+int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, int T, int F, void *d_ws, size_t ws_bytes,
+                           void *stream) {
+    MISO_REQUIRE(net && d_x && d_y && d_ws, "miso_net_forward_train: null argument");
+    MISO_REQUIRE(net->n_loaded == (int)net->params.size(), "miso_net_forward_train: %d of %d parameters loaded", net->n_loaded,
+                 (int)net->params.size());
+    MISO_REQUIRE(B >= 1 && B <= 65535, "miso_net_forward_train: batch %d out of range", B);
+    int rc = miso_net_check_shape(net, T, F);
+    if (rc) return rc;
+    MISO_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255) == 0, "miso_net_forward_train: workspace must be 256-byte aligned");
+    MISO_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 127) == 0, "miso_net_forward_train: input planes must be 128-byte aligned");
+    Plan pl;
+    full_plan(net, B, T, F, reinterpret_cast<char *>(d_ws), pl, true);
+    if (pl.total > ws_bytes) {
+        set_error("miso_net_forward_train: workspace %zu < required %zu bytes", ws_bytes, pl.total);
+        return MISO_E_WORKSPACE;
+    }
+    rc = conv_tc_init();
+    if (rc) return rc;
+    return enqueue_forward(net, pl, d_x, d_y, B, T, F, as_stream(stream));
+}
+
+int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int T, int F, void *d_ws, size_t ws_bytes,
+                      float *d_grads, void *stream) {
+    MISO_REQUIRE(net && d_x && d_gy && d_ws && d_grads, "miso_net_backward: null argument");
+    MISO_REQUIRE(net->out_ch % 4 == 0, "miso_net_backward: out_ch=%d must be a multiple of 4 (MISO_1 with 2 speakers)", net->out_ch);
+    int rc = miso_net_check_shape(net, T, F);
+    if (rc) return rc;
+    Plan pl;
+    full_plan(net, B, T, F, reinterpret_cast<char *>(d_ws), pl, true);
+    if (pl.total > ws_bytes) {
+        set_error("miso_net_backward: workspace %zu < required %zu bytes", ws_bytes, pl.total);
+        return MISO_E_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    std::vector<ConvRec> recs;
+    Walker w{net, pl, B, T, F, st, false};
+    w.record = &recs;
+    rc = w.run(d_x, nullptr);
+    if (rc) return rc;
+    Backward bw{net, pl, B, T, F, st, d_grads, {}};
+    param_grad_offsets(net, bw.goff);
+    MISO_CUDA(cudaMemsetAsync(d_grads, 0, (size_t)bw.goff.back() * sizeof(float), st));
+    MISO_CUDA(cudaMemsetAsync(pl.grad_base, 0, pl.grad_bytes, st));
+    for (int i = (int)recs.size() - 1; i >= 0; --i) {
+        rc = recs[i].kind == 1 ? bw.tcn() : bw.conv_layer(recs[i], d_gy);
+        if (rc) return rc;
+    }
     return MISO_OK;
 }
 

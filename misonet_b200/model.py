@@ -91,6 +91,47 @@ class _TCN(_Holder):               # model.py:486-508
             *[nn.Sequential(*[_TemporalBlock(c, 2 ** x) for x in range(blocks)]) for _ in range(repeats)])
 
 
+# --------------------------------------------------------------------------- training
+class _NetFunction(torch.autograd.Function):
+    """Autograd node of the network body for training (trainer.py:159-212: ``estimate = model(mix)``,
+    ``loss.backward()``).  Forward = ``miso_net_forward_train`` (keeps the per-block TCN state in the training
+    workspace), backward = ``miso_net_backward`` (include/misonet_b200.h); the parameter gradients come back as one
+    flat buffer in the library's key order (= ``named_parameters()`` order) and are handed to autograd as views."""
+
+    @staticmethod
+    def forward(ctx, module, x_cl, B, T, F, *params):
+        y_cl = module._run_body_train(x_cl, B, T, F)
+        ctx.module, ctx.x_cl, ctx.shape, ctx.token = module, x_cl, (B, T, F), module._train_token
+        ctx.param_shapes = [p.shape for p in params]
+        return module._unpack(y_cl, B, T, F)
+
+    @staticmethod
+    def backward(ctx, gout):
+        m = ctx.module
+        if ctx.token != m._train_token:
+            raise _lib.MisoError("the training workspace of this forward was overwritten by a later forward of the same "
+                                 "module; call backward() before the next training forward")
+        lib = _lib.load()
+        B, T, F = ctx.shape
+        S = m._out_ch // 2
+        dev = ctx.x_cl.device
+        g = gout.to(torch.complex64).contiguous()
+        st = _lib.stream_ptr()
+        with torch.cuda.device(dev):
+            gy = torch.empty(B, T, F, 2 * S, dtype=torch.float32, device=dev)
+            _lib.check(lib.miso_grad_pack(_lib.ptr(g), _lib.ptr(gy), B, S, T, F, st), "miso_grad_pack")
+            flat = torch.empty(lib.miso_net_grad_numel(m._handle), dtype=torch.float32, device=dev)
+            ws = m._ws_train
+            _lib.check(lib.miso_net_backward(m._handle, _lib.ptr(ctx.x_cl), _lib.ptr(gy), B, T, F, _lib.ptr(ws), ws.numel(),
+                                             _lib.ptr(flat), st), "miso_net_backward")
+        grads, off = [], 0
+        for shp in ctx.param_shapes:
+            n = int(torch.Size(shp).numel())
+            grads.append(flat[off:off + n].view(shp))
+            off += n
+        return (None, None, None, None, None, *grads)
+
+
 # --------------------------------------------------------------------------- network
 class _MisoNet(nn.Module):
     """Shared body of MISO_1 and MISO_3 (model.py:24-73 / 298-347)."""
@@ -145,6 +186,8 @@ class _MisoNet(nn.Module):
         self._handle_device = None
         self._packed = {}
         self._ws = None
+        self._ws_train = None     # training workspace: activations + statistics + gradient buffers of ONE forward
+        self._train_token = 0
         self._bufs = {}           # persistent input-plane / output buffers: stable pointers keep the CUDA graph valid
         self._sync_tag = None
         self.use_graph = True     # replay the forward as a CUDA graph (include/misonet_b200.h, miso_net_set_graph)
@@ -160,6 +203,7 @@ class _MisoNet(nn.Module):
             self._handle = None
             self._packed = {}
             self._ws = None
+            self._ws_train = None
             self._bufs = {}
             self._sync_tag = None
 
@@ -280,11 +324,32 @@ class _MisoNet(nn.Module):
                                             _lib.ptr(ws), ws.numel(), st), "miso_net_forward")
         return y_cl
 
-    def _prepare(self, *tensors):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+    def _training_pass(self):
+        """True when this forward must be differentiable (autograd on and a parameter requires grad)."""
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)):
+            return False
+        if self._out_ch % 4:
             raise NotImplementedError(
-                "misonet_b200: the backward pass is not implemented yet (SURVEY.md section 8(f) rank 1); "
-                "call under torch.no_grad()")
+                "misonet_b200: the backward pass needs out_ch % 4 == 0 (MISO_1 with two speakers); the MISO_3 training "
+                "path (SURVEY.md section 8(f) rank 4) is not implemented yet -- call under torch.no_grad()")
+        return True
+
+    def _run_body_train(self, x_cl, B, T, F):
+        """Training forward: x_cl input planes -> float32 [B,T,F,out_ch]; leaves the workspace for the backward."""
+        lib = _lib.load()
+        dev = x_cl.device
+        _lib.check(lib.miso_net_check_shape(self._handle, T, F), "miso_net_check_shape")
+        nbytes = lib.miso_net_train_workspace_bytes(self._handle, B, T, F)
+        if self._ws_train is None or self._ws_train.numel() < nbytes or self._ws_train.device != dev:
+            self._ws_train = None
+            self._ws_train = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        y_cl = torch.empty(B, T, F, self._out_ch, dtype=torch.float32, device=dev)
+        self._train_token += 1
+        _lib.check(lib.miso_net_forward_train(self._handle, _lib.ptr(x_cl), _lib.ptr(y_cl), B, T, F, _lib.ptr(self._ws_train),
+                                              self._ws_train.numel(), _lib.stream_ptr()), "miso_net_forward_train")
+        return y_cl
+
+    def _prepare(self, *tensors):
         self._ensure_handle()
         dev = self._handle_device
         out = []
@@ -338,6 +403,8 @@ class MISO_1(_MisoNet):
         arr = (ctypes.c_int * n)(*[int(s) for s in shifts])
         _lib.check(_lib.load().miso_pack_miso1(_lib.ptr(mix), _lib.ptr(x_cl), B, M, T, F, arr, n, _lib.stream_ptr()),
                    "miso_pack_miso1")
+        if self._training_pass():
+            return _NetFunction.apply(self, x_cl, n * B, T, F, *self._param_list)
         y_cl = self._run_body(x_cl, n * B, T, F)
         return self._unpack(y_cl, n * B, T, F)
 
@@ -355,6 +422,7 @@ class MISO_3(_MisoNet):
         but every caller passes (mix, beamformed, MISO1): tester.py:1242, trainer.py:398-414);
         the weights see channels [mix x M, second, third].
         mixture [B,M,T,F], second/third [B,1,T,F] complex -> complex64 [B, num_spks, T, F]."""
+        self._training_pass()
         mix, second, third = self._prepare(mixture, MISO1, BF)
         B, M, T, F = mix.shape
         if 2 * (M + 2) != self._in_ch:
