@@ -8,6 +8,7 @@
 // the producing layer's backward then turns its channel range in place into dL/dy (InstanceNorm + ELU backward) and
 // feeds the weight-gradient GEMM and the data-gradient conv (conv_fp32.cu with transposed weights).
 #include <algorithm>
+#include <cstdlib>
 
 #include "bwd.cuh"
 
@@ -277,6 +278,205 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int split
     }
 }
 
+// ---- weight gradient on the tensor cores (bf16 hi/lo split, three MMAs per product, fp32 accumulate) ---------------
+// Same GEMM and the same tile ownership as wgrad_kernel, with the inner product on mma.sync m16n8k16: the loader
+// normalises the input pixels, splits xhat and dy into bf16 hi / lo halves (hi + lo carries 16-17 mantissa bits, as the
+// forward's activation planes do) and stores them [pixel][channel]; ldmatrix.trans turns those K-major rows into the
+// A (cin x pixels) and B (pixels x cout) fragments.  Warps 0-3 own 16 input channels each of the first 16 pixels of
+// a 32-pixel chunk, warps 4-7 the same channels of the second 16 pixels; both halves add into dW with atomics.
+constexpr int kWmBK = 32;
+constexpr int kWmAP = kWgBM + 8;  // bf16 row pitch of the A tiles: 144 bytes, ldmatrix rows fall into distinct banks
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
+    const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]);
+    hi = make_uint2(h0, h1);
+    lo = make_uint2(pack_bf16x2(v[0] - bf16_lo(h0), v[1] - bf16_hi(h0)), pack_bf16x2(v[2] - bf16_lo(h1), v[3] - bf16_hi(h1)));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int splits) {
+    constexpr int BP = BN + 8;          // bf16 row pitch of the B tiles
+    constexpr int NB4 = BN / 32;        // float4 of dy per thread and chunk
+    extern __shared__ __align__(16) unsigned char wsm_raw[];
+    __nv_bfloat16 *Ah = reinterpret_cast<__nv_bfloat16 *>(wsm_raw);   // [BK][AP]
+    __nv_bfloat16 *Al = Ah + kWmBK * kWmAP;
+    __nv_bfloat16 *Bh = Al + kWmBK * kWmAP;                           // [BK][BP]
+    __nv_bfloat16 *Bl = Bh + kWmBK * BP;
+    float2 *aff = reinterpret_cast<float2 *>(Bl + kWmBK * BP);        // [B][BM]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ci_tiles = (a.cin + kWgBM - 1) / kWgBM, co_tiles = (a.cout + BN - 1) / BN;
+    int tile = blockIdx.y;
+    const int cot = tile % co_tiles;
+    tile /= co_tiles;
+    const int cit = tile % ci_tiles;
+    const int tap = tile / ci_tiles;
+    const int kt = tap / a.KF, kf = tap - kt * a.KF;
+    const int ci0 = cit * kWgBM, co0 = cot * BN;
+    const int npix = a.T * a.Fout;
+    const int per = (npix + splits - 1) / splits;
+    const int p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+
+    for (int i = tid; i < a.B * kWgBM; i += 256) {
+        const int b = i / kWgBM, c = ci0 + (i - b * kWgBM);
+        float2 v = make_float2(1.f, 0.f);
+        if (a.x_sums && c < a.cin) {
+            const double *s = a.x_sums + ((size_t)b * a.x_ctot + a.x_coff + c) * 2;
+            v = affine_from_sums(stat_get(s), stat_get(s + 1), a.inv_n, (double)a.eps);
+        }
+        aff[i] = v;
+    }
+    __syncthreads();
+
+    const int ap = tid >> 3, a8 = tid & 7;        // A loader: pixel ap of the chunk, channels 8 a8 .. 8 a8 + 7 (one 16-byte plane pixel)
+    const int bp = tid >> 3, b4 = tid & 7;        // B loader: pixel bp, channels 4 b4 (+ 32 j)
+    const int nchunk = p1 > p0 ? (p1 - p0 + kWmBK - 1) / kWmBK : 0;
+    const int niter = nchunk * a.B;
+    const bool planes = a.x_layout == LAYOUT_PLANES;
+    const size_t x_lo = (size_t)a.x_ctot * a.T * a.Fin;
+
+    float ra[8];
+    float4 rb[NB4];
+    // (frame, bin) of this thread's pixel, advanced incrementally (a chunk is 32 consecutive pixels of the output grid)
+    const int t_first = (p0 + ap) / a.Fout, f_first = (p0 + ap) - t_first * a.Fout;
+    int lt = t_first, lf = f_first, lb = 0, lchunk = 0;
+    auto load = [&]() {   // loads the next (sample, chunk) in order
+        const int b = lb;
+        const int pc = p0 + lchunk * kWmBK;
+        const int c = ci0 + a8 * 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ra[q] = 0.f;
+        const int p = pc + ap;
+        if (p < p1 && c < a.cin) {
+            int ti, fi;
+            bool ok = true;
+            if (!a.transposed) {
+                ti = lt + kt - a.pad_t;
+                fi = lf * a.stride_f + kf - a.pad_f;
+            } else {
+                ti = lt + a.pad_t - kt;
+                const int num = lf + a.pad_f - kf;
+                fi = num / a.stride_f;
+                ok = num >= 0 && fi * a.stride_f == num;
+            }
+            ok = ok && ti >= 0 && ti < a.T && fi >= 0 && fi < a.Fin;
+            if (ok) {
+                const int ca = a.x_coff + c;
+                float e[8];
+                if (planes) {
+                    const __nv_bfloat16 *xp = reinterpret_cast<const __nv_bfloat16 *>(a.x) + (size_t)b * 2 * x_lo +
+                                              (((size_t)(ca >> 3) * a.T + ti) * a.Fin + fi) * 8;
+                    const uint4 h = *reinterpret_cast<const uint4 *>(xp);
+                    e[0] = bf16_lo(h.x); e[1] = bf16_hi(h.x); e[2] = bf16_lo(h.y); e[3] = bf16_hi(h.y);
+                    e[4] = bf16_lo(h.z); e[5] = bf16_hi(h.z); e[6] = bf16_lo(h.w); e[7] = bf16_hi(h.w);
+                    if (a.use_lo) {
+                        const uint4 l = *reinterpret_cast<const uint4 *>(xp + x_lo);
+                        e[0] += bf16_lo(l.x); e[1] += bf16_hi(l.x); e[2] += bf16_lo(l.y); e[3] += bf16_hi(l.y);
+                        e[4] += bf16_lo(l.z); e[5] += bf16_hi(l.z); e[6] += bf16_lo(l.w); e[7] += bf16_hi(l.w);
+                    }
+                } else {
+                    const float *xp = reinterpret_cast<const float *>(a.x) + (((size_t)b * a.T + ti) * a.Fin + fi) * a.x_ctot + ca;
+                    const float4 v0 = *reinterpret_cast<const float4 *>(xp), v1 = *reinterpret_cast<const float4 *>(xp + 4);
+                    e[0] = v0.x; e[1] = v0.y; e[2] = v0.z; e[3] = v0.w;
+                    e[4] = v1.x; e[5] = v1.y; e[6] = v1.z; e[7] = v1.w;
+                }
+                const float2 *af = aff + b * kWgBM + a8 * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ra[q] = fmaf(e[q], af[q].x, af[q].y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NB4; ++j) {
+            rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int co = co0 + b4 * 4 + 32 * j;
+            if (p < p1 && co < a.cout) rb[j] = *reinterpret_cast<const float4 *>(a.dy + ((size_t)b * npix + p) * a.dy_ctot + a.dy_coff + co);
+        }
+        // advance to the next chunk (or to the first chunk of the next sample)
+        if (++lchunk == nchunk) {
+            lchunk = 0;
+            ++lb;
+            lt = t_first;
+            lf = f_first;
+        } else {
+            lf += kWmBK;
+            while (lf >= a.Fout) {
+                lf -= a.Fout;
+                ++lt;
+            }
+        }
+    };
+
+    constexpr int NT = BN / 8;  // n tiles of 8 channels
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    const int wm = warp & 3, wk = warp >> 2;
+    // ldmatrix lane addresses (see the fragment layouts of mma.m16n8k16): A matrices (m 0-7 | m 8-15) x (k 0-7 | k 8-15),
+    // B matrices (k 0-7 | k 8-15) x (n 0-7 | n 8-15)
+    const int lr = lane & 7, lm = lane >> 3;
+    const uint32_t a_off = (uint32_t)(((wk * 16 + (lm >> 1) * 8 + lr) * kWmAP + wm * 16 + (lm & 1) * 8) * 2);
+    const uint32_t b_off = (uint32_t)(((wk * 16 + (lm & 1) * 8 + lr) * BP + (lm >> 1) * 8) * 2);
+    const uint32_t sAh = (uint32_t)__cvta_generic_to_shared(Ah), sAl = (uint32_t)__cvta_generic_to_shared(Al);
+    const uint32_t sBh = (uint32_t)__cvta_generic_to_shared(Bh), sBl = (uint32_t)__cvta_generic_to_shared(Bl);
+
+    if (niter > 0) load();
+    for (int it = 0; it < niter; ++it) {
+        {
+            uint2 h0, l0, h1, l1;
+            split4(ra, h0, l0);
+            split4(ra + 4, h1, l1);
+            *reinterpret_cast<uint4 *>(Ah + ap * kWmAP + a8 * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            *reinterpret_cast<uint4 *>(Al + ap * kWmAP + a8 * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        }
+#pragma unroll
+        for (int j = 0; j < NB4; ++j) {
+            const float v[4] = {rb[j].x, rb[j].y, rb[j].z, rb[j].w};
+            uint2 hi, lo;
+            split4(v, hi, lo);
+            *reinterpret_cast<uint2 *>(Bh + bp * BP + b4 * 4 + 32 * j) = hi;
+            *reinterpret_cast<uint2 *>(Bl + bp * BP + b4 * 4 + 32 * j) = lo;
+        }
+        __syncthreads();
+        if (it + 1 < niter) load();
+        uint32_t ah[4], al[4];
+        ldsm_x4_trans(sAh + a_off, ah[0], ah[1], ah[2], ah[3]);
+        ldsm_x4_trans(sAl + a_off, al[0], al[1], al[2], al[3]);
+#pragma unroll
+        for (int n2 = 0; n2 < NT / 2; ++n2) {
+            uint32_t bh[4], bl[4];
+            ldsm_x4_trans(sBh + b_off + n2 * 32, bh[0], bh[1], bh[2], bh[3]);
+            ldsm_x4_trans(sBl + b_off + n2 * 32, bl[0], bl[1], bl[2], bl[3]);
+            mma_bf16(acc[2 * n2], ah, bh[0], bh[1]);
+            mma_bf16(acc[2 * n2], ah, bl[0], bl[1]);
+            mma_bf16(acc[2 * n2], al, bh[0], bh[1]);
+            mma_bf16(acc[2 * n2 + 1], ah, bh[2], bh[3]);
+            mma_bf16(acc[2 * n2 + 1], ah, bl[2], bl[3]);
+            mma_bf16(acc[2 * n2 + 1], al, bh[2], bh[3]);
+        }
+        __syncthreads();
+    }
+
+    const int taps = a.KT * a.KF;
+    const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ci = ci0 + wm * 16 + g + (q >> 1) * 8;
+            const int co = co0 + nt * 8 + t4 * 2 + (q & 1);
+            if (ci >= a.cin || co >= a.cout) continue;
+            const size_t idx = a.transposed ? ((size_t)ci * a.cout + co) * taps + tap : ((size_t)co * a.cin + ci) * taps + tap;
+            atomicAdd(a.dw + idx, acc[nt][q]);
+        }
+}
+
 __global__ void dgrad_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, int taps, int cin, int cout,
                                   int cout_pad, int cin_pad) {
     const int64_t total = (int64_t)taps * cout * cin_pad;
@@ -544,13 +744,36 @@ static int launch_wgrad_t(const WgradArgs &a, cudaStream_t st) {
     return MISO_OK;
 }
 
+template <int BN>
+static int launch_wgrad_mma(const WgradArgs &a, cudaStream_t st) {
+    const int taps = a.KT * a.KF;
+    const int ntile = taps * ceil_div(a.cin, kWgBM) * ceil_div(a.cout, BN);
+    const int npix = a.T * a.Fout;
+    int splits = ceil_div(4 * 148, ntile);
+    splits = std::max(1, std::min(splits, ceil_div(npix, 4 * kWmBK)));
+    const size_t smem = (size_t)(2 * kWmBK * kWmAP + 2 * kWmBK * (BN + 8)) * 2 + (size_t)a.B * kWgBM * sizeof(float2);
+    MISO_REQUIRE(smem <= 200 * 1024, "wgrad: batch %d too large for the per-sample affine table", a.B);
+    static size_t attr_set[2] = {0, 0};
+    size_t &cur = attr_set[BN == 64 ? 1 : 0];
+    if (smem > 48 * 1024 && smem > cur) {
+        MISO_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    wgrad_mma_kernel<BN><<<dim3(splits, ntile), 256, smem, st>>>(a, splits);
+    MISO_LAUNCHED("wgrad_mma_kernel");
+    return MISO_OK;
+}
+
 int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
     MISO_REQUIRE(a.cin % 4 == 0 && a.x_coff % 4 == 0 && a.x_ctot % 4 == 0, "wgrad: input channels must be multiples of 4");
     MISO_REQUIRE(a.cout % 4 == 0 && a.dy_coff % 4 == 0 && a.dy_ctot % 4 == 0,
                  "wgrad: output channels must be multiples of 4 (cout=%d)", a.cout);
     MISO_REQUIRE(a.x_layout != LAYOUT_PLANES || a.x_ctot % 8 == 0, "wgrad: plane layout needs ctot %% 8 == 0");
-    if (a.cout <= 32) return launch_wgrad_t<2>(a, st);
-    return launch_wgrad_t<4>(a, st);
+    MISO_REQUIRE(a.x_coff % 8 == 0 && (a.cin % 8 == 0 || (a.x_layout == LAYOUT_PLANES && a.x_coff + a.cin <= a.x_ctot && a.x_sums == nullptr)),
+                 "wgrad: input channel range must be 8-aligned (cin=%d coff=%d)", a.cin, a.x_coff);
+    static const bool fma = getenv("MISO_WGRAD_FMA") && atoi(getenv("MISO_WGRAD_FMA")) != 0;  // debugging: the fp32 FMA GEMM
+    if (fma) return a.cout <= 32 ? launch_wgrad_t<2>(a, st) : launch_wgrad_t<4>(a, st);
+    return a.cout <= 32 ? launch_wgrad_mma<32>(a, st) : launch_wgrad_mma<64>(a, st);
 }
 
 int launch_dgrad_pack(const float *src, float *dst, int taps, int cin, int cout, int cout_pad, int cin_pad, cudaStream_t st) {

@@ -68,3 +68,30 @@ def gather_perm_indices(idx, n_total):
 def barrier():
     if _on():
         dist.barrier()
+
+
+def allreduce_gradients(params, n_local=None):
+    """Data-parallel gradient reduction of a training step (one all-reduce of the 2.59 M /
+    8.58 M fp32 gradients per step).  Every rank holds the gradient of the MEAN loss over its own ``n_local``
+    utterances (criterion.py:59 averages over the batch); the result on every rank is the gradient of the mean over
+    all utterances of the step: sum_r n_r * g_r / sum_r n_r (a plain average for equal shards).  The gradients are
+    packed into ONE flat bucket (the backward pass produces them as one flat buffer anyway, so this is a single
+    latency-bound collective on NVLink / NVSwitch) and written back in place.  Returns the global utterance count."""
+    params = [p for p in params if p.grad is not None]
+    if not _on():
+        return n_local
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    w = 1.0 if n_local is None else float(n_local)
+    cnt = torch.tensor([w], dtype=torch.float32, device=flat.device)
+    if n_local is not None:
+        flat.mul_(w)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total = float(cnt.item()) if n_local is not None else float(dist.get_world_size())
+    flat.div_(total)
+    off = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return int(total) if n_local is not None else None

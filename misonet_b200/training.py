@@ -1,0 +1,31 @@
+"""MISO_1 training step (mirror of ``Trainer_Separate._run_one_epoch``'s batch body, trainer.py:146-212):
+roll the reference microphone to the front, ``estimate = model(mix)``, ``loss_uPIT`` against the clean images at the
+reference microphone, ``loss.backward()``, gradient clipping, optimizer step.  The arithmetic (forward, loss, backward)
+runs in the CUDA library; the optimizer is the caller's ``torch.optim`` object over the module's parameters, exactly as
+in run.py, and multi-GPU training adds ONE collective: the gradient all-reduce (distributed.allreduce_gradients)."""
+import torch
+
+from . import criterion, distributed
+
+
+def train_step(model, optimizer, mix_stft, ref_stft, ref_ch=0, max_norm=None, training=True):
+    """mix_stft: complex [B, Mic, T, F] (CUDA); ref_stft: list[num_spks] of complex [B, Mic, T, F] or [B, T, F]
+    (the clean source images; trainer.py:160-166 takes microphone ``ref_ch``).  Returns the loss (float32 CUDA scalar,
+    detached).  With ``training=False`` this is the validation pass of trainer.py:138-144 (no_grad, no update)."""
+    num_spks = model.num_spks
+    mix = torch.roll(mix_stft, -ref_ch, dims=1)                                  # trainer.py:154
+    refs = [r[:, ref_ch] if r.dim() == 4 else r for r in ref_stft]               # trainer.py:162-166
+    if not training:
+        with torch.no_grad():
+            return criterion.loss_uPIT(num_spks, model(mix), refs)
+    optimizer.zero_grad(set_to_none=True)
+    estimate = model(mix)                                                        # trainer.py:158
+    if estimate.shape[1] != num_spks:
+        raise ValueError("[ERROR] please check the number of speakers")          # trainer.py:169
+    loss = criterion.loss_uPIT(num_spks, estimate, refs)                         # trainer.py:172
+    loss.backward()                                                              # trainer.py:207
+    distributed.allreduce_gradients(model.parameters(), n_local=mix.shape[0])
+    if max_norm:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)             # trainer.py:209-211
+    optimizer.step()                                                             # trainer.py:212
+    return loss.detach()

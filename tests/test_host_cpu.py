@@ -123,6 +123,15 @@ from misonet_b200 import continuous as C
 wave = torch.stack([torch.full((2, 5), float(i)) for i in range(lo, hi)]) if hi > lo else torch.zeros(0, 2, 5)
 allwave = C.gather_chunks(wave, n_total)          # the long-recording path: chunk waveforms gathered in chunk order
 assert allwave.shape == (n_total, 2, 5) and allwave[:, 0, 0].tolist() == [float(i) for i in range(n_total)]
+# gradient all-reduce of the training step: rank r holds the mean gradient of its (hi - lo) utterances
+params = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5))]
+per_utt = lambda i, p: torch.full_like(p, float(i + 1))
+for p in params:
+    p.grad = sum(per_utt(i, p) for i in range(lo, hi)) / max(hi - lo, 1)
+tot = D.allreduce_gradients(params, n_local=hi - lo)
+assert tot == n_total
+for p in params:
+    assert torch.allclose(p.grad, torch.full_like(p, 4.0)), p.grad      # mean over all 7 utterances of (i + 1)
 D.barrier()
 assert count == n_total and abs(mean - 4.0) < 1e-12, (mean, count)
 assert allidx.tolist() == [i % 2 for i in range(n_total)], allidx
