@@ -35,6 +35,12 @@ __device__ __forceinline__ void load_e4(const __nv_bfloat16 *p, size_t lo_elems,
     }
 }
 
+__device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
+    const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]);
+    hi = make_uint2(h0, h1);
+    lo = make_uint2(pack_bf16x2(v[0] - bf16_lo(h0), v[1] - bf16_hi(h0)), pack_bf16x2(v[2] - bf16_lo(h1), v[3] - bf16_hi(h1)));
+}
+
 // ---- InstanceNorm2d + ELU backward ------------------------------------------------------------------------------
 // pass 1: per (b, channel) sums of dz and dz * z over the pixels
 __global__ void __launch_bounds__(kEw) in_bwd_reduce_kernel(const InBwdArgs a, int pix_per_cta) {
@@ -123,6 +129,14 @@ __global__ void __launch_bounds__(kEw) in_bwd_apply_kernel(const InBwdArgs a, in
                     d[q] = e[q] > 0.f ? de : de * (e[q] + 1.f);  // ELU'(y) = exp(y) = e + 1 for y <= 0
                 }
                 *reinterpret_cast<float4 *>(gb + (size_t)p * a.ctot) = make_float4(d[0], d[1], d[2], d[3]);
+            }
+            if (a.dyp) {
+                const int cl = c4 * 4;
+                __nv_bfloat16 *dp = a.dyp + (size_t)b * 2 * a.c * a.npix + ((size_t)(cl >> 3) * a.npix + p) * 8 + (cl & 7);
+                uint2 hi, lo2;
+                split4(d, hi, lo2);
+                *reinterpret_cast<uint2 *>(dp) = hi;
+                *reinterpret_cast<uint2 *>(dp + (size_t)a.c * a.npix) = lo2;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) sb[q] += d[q];
@@ -295,11 +309,6 @@ __device__ __forceinline__ void mma_bf16(float *c, const uint32_t *a, uint32_t b
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
-    const uint32_t h0 = pack_bf16x2(v[0], v[1]), h1 = pack_bf16x2(v[2], v[3]);
-    hi = make_uint2(h0, h1);
-    lo = make_uint2(pack_bf16x2(v[0] - bf16_lo(h0), v[1] - bf16_hi(h0)), pack_bf16x2(v[2] - bf16_lo(h1), v[3] - bf16_hi(h1)));
-}
 
 template <int BN>
 __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int splits) {
@@ -313,7 +322,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
     float2 *aff = reinterpret_cast<float2 *>(Bl + kWmBK * BP);        // [B][BM]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ci_tiles = (a.cin + kWgBM - 1) / kWgBM, co_tiles = (a.cout + BN - 1) / BN;
-    int tile = blockIdx.y;
+    int tile = blockIdx.x;  // tiles (tap, cin tile, cout tile) of one pixel slice are neighbours in launch order: they share x and dy in L2
     const int cot = tile % co_tiles;
     tile /= co_tiles;
     const int cit = tile % ci_tiles;
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
     const int ci0 = cit * kWgBM, co0 = cot * BN;
     const int npix = a.T * a.Fout;
     const int per = (npix + splits - 1) / splits;
-    const int p0 = blockIdx.x * per, p1 = min(npix, p0 + per);
+    const int p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
 
     for (int i = tid; i < a.B * kWgBM; i += 256) {
         const int b = i / kWgBM, c = ci0 + (i - b * kWgBM);
@@ -478,14 +487,14 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
 }
 
 __global__ void dgrad_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, int taps, int cin, int cout,
-                                  int cout_pad, int cin_pad) {
+                                  int cout_pad, int cin_pad, int flip) {
     const int64_t total = (int64_t)taps * cout * cin_pad;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int ci = (int)(i % cin_pad);
         const int64_t r = i / cin_pad;
         const int co = (int)(r % cout);
         const int tap = (int)(r / cout);
-        dst[i] = ci < cin ? src[((size_t)tap * cin + ci) * cout_pad + co] : 0.f;
+        dst[i] = ci < cin ? src[((size_t)(flip ? taps - 1 - tap : tap) * cin + ci) * cout_pad + co] : 0.f;
     }
 }
 
@@ -759,7 +768,7 @@ static int launch_wgrad_mma(const WgradArgs &a, cudaStream_t st) {
         MISO_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    wgrad_mma_kernel<BN><<<dim3(splits, ntile), 256, smem, st>>>(a, splits);
+    wgrad_mma_kernel<BN><<<dim3(ntile, splits), 256, smem, st>>>(a, splits);
     MISO_LAUNCHED("wgrad_mma_kernel");
     return MISO_OK;
 }
@@ -776,10 +785,10 @@ int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
     return a.cout <= 32 ? launch_wgrad_mma<32>(a, st) : launch_wgrad_mma<64>(a, st);
 }
 
-int launch_dgrad_pack(const float *src, float *dst, int taps, int cin, int cout, int cout_pad, int cin_pad, cudaStream_t st) {
+int launch_dgrad_pack(const float *src, float *dst, int taps, int cin, int cout, int cout_pad, int cin_pad, int flip, cudaStream_t st) {
     const int64_t total = (int64_t)taps * cout * cin_pad;
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
-    dgrad_pack_kernel<<<blocks, 256, 0, st>>>(src, dst, taps, cin, cout, cout_pad, cin_pad);
+    dgrad_pack_kernel<<<blocks, 256, 0, st>>>(src, dst, taps, cin, cout, cout_pad, cin_pad, flip);
     MISO_LAUNCHED("dgrad_pack_kernel");
     return MISO_OK;
 }

@@ -19,6 +19,9 @@ struct InBwdArgs {
     double inv_n;
     float eps;
     int plain;  // layer without ELU / IN (model.py:401-406, 418-423): dy = dz, only the bias gradient is taken
+    // optional copy of dy as bf16 hi/lo planes [B][hi|lo][c/8][npix][8] (c % 8 == 0): the input of the tensor-core
+    // data-gradient conv
+    __nv_bfloat16 *dyp;
 };
 int launch_in_bwd(const InBwdArgs &a, cudaStream_t st);
 
@@ -40,7 +43,8 @@ struct WgradArgs {
 int launch_wgrad(const WgradArgs &a, cudaStream_t st);
 
 // packed forward weights [taps][cin][cout_pad] -> data-gradient weights [taps][cout][cin_pad]
-int launch_dgrad_pack(const float *src, float *dst, int taps, int cin, int cout, int cout_pad, int cin_pad, cudaStream_t st);
+// flip = 1 reverses the tap order (a stride-1 transposed conv as a plain conv)
+int launch_dgrad_pack(const float *src, float *dst, int taps, int cin, int cout, int cout_pad, int cin_pad, int flip, cudaStream_t st);
 
 // One half of a TemporalBlock (model.py:530-531 / 538-539 + DepthwiseSeparableConv model.py:553-567)
 struct TcnBwdArgs {

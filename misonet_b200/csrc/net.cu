@@ -448,6 +448,8 @@ struct Plan {
     float *gS = nullptr, *gU = nullptr, *tY = nullptr, *tQ = nullptr, *tDQ = nullptr, *tDN = nullptr;
     double *bred = nullptr;  // reduction scratch of the norm backward kernels
     float *wT = nullptr;     // data-gradient (transposed) weights of the layer being processed
+    char *dyP = nullptr;     // dL/dy of the layer being processed as bf16 hi/lo planes (tensor-core data gradient)
+    size_t dyP_bytes = 0;
     void *tcn_wimg = nullptr;  // tensor-core pointwise convs: weight images and W beta / W gamma vectors (tcn.cu)
     float *tcn_wvec = nullptr;
     std::vector<double *> sS, sU, g1, g2;
@@ -563,6 +565,13 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
             }
             pl.bred = reinterpret_cast<double *>(take(((size_t)B * maxc * 2 + 2 * (size_t)B) * sizeof(double)));
             pl.wT = reinterpret_cast<float *>(take(maxw * sizeof(float)));
+            // largest layer output (channels x bins): the first dense conv block's buffers bound it
+            size_t maxo = 0;
+            for (int i = 0; i < nb; ++i) maxo = std::max(maxo, (size_t)n->en[i + 1] * pl.Fx[i]);
+            for (int j = 0; j < nb; ++j) maxo = std::max(maxo, (size_t)2 * n->de[j] * pl.D[j].F);
+            for (int j = 0; j + 1 < nb; ++j) maxo = std::max(maxo, (size_t)n->de[j + 1] * pl.D[j + 1].F);
+            pl.dyP_bytes = (size_t)B * maxo * T * 4;
+            pl.dyP = take(pl.dyP_bytes);
         }
     }
     if (tcn_pw_eligible(n->C)) {
@@ -615,6 +624,7 @@ struct ConvRec {
     const ConvDesc *cd;
     float *in_grad;   // gradient buffer of the input buffer (null: the network input, no data gradient)
     float *out_grad;  // gradient buffer of the output buffer (null: the network output, gradient supplied by the caller)
+    bool in_grad_needed;  // false only for the first layer (pointer-independent: plans are also built without a base)
 };
 
 // One pass over the layer list.  dry = true only sizes the tensor-core scratch (no launches).
@@ -665,7 +675,7 @@ struct Walker {
         a.norm_inv_n = 1.0 / ((double)T * Fin);
         a.elu = elu ? 1 : 0;
         if (record) {
-            record->push_back(ConvRec{0, a, &cd, inb ? inb->grad : nullptr, outb ? outb->grad : nullptr});
+            record->push_back(ConvRec{0, a, &cd, inb ? inb->grad : nullptr, outb ? outb->grad : nullptr, inb != nullptr});
             return MISO_OK;
         }
         const bool tc = conv_tc_eligible(a);
@@ -734,7 +744,7 @@ int Walker::run(const void *d_x, float *d_y) {
 
     // ---------------- TCN (model.py:486-567) ----------------
     if (record) {
-        record->push_back(ConvRec{1, ConvArgs{}, nullptr, nullptr, nullptr});
+        record->push_back(ConvRec{1, ConvArgs{}, nullptr, nullptr, nullptr, false});
     } else {
         const BufDesc &d0 = pl.D[0];
         const double inv_T = 1.0 / (double)T;
@@ -896,10 +906,72 @@ int Walker::run(const void *d_x, float *d_y) {
 
 int enqueue_forward(miso_net *net, const Plan &pl, const void *d_x, float *d_y, int B, int T, int F, cudaStream_t st);
 
+// Data gradient of a recorded layer as a forward conv over dL/dy (bf16 hi/lo planes in pl.dyP) with the transposed
+// weights in pl.wT, accumulated into the input buffer's gradient (resid == out).  Every case maps onto a configuration
+// the forward itself uses: a stride-1 pad-(1,1) conv's gradient is the same conv with the taps reversed (*flip = 1),
+// a strided conv's gradient is the transposed conv of the same stride and vice versa.
+ConvArgs dgrad_tc_args(const ConvArgs &f, const Plan &pl, int B, int T, float *din, int *flip) {
+    const int bn = conv_fp32_tile_n(f.cin);
+    ConvArgs a{};
+    a.in = pl.dyP;
+    a.in_layout = LAYOUT_PLANES;
+    a.in_lo_off = (size_t)f.cout * T * f.Fout * 2;
+    a.w = pl.wT;
+    a.bias = nullptr;
+    a.out = din;
+    a.out_layout = LAYOUT_CL_F32;
+    a.resid = din;
+    a.resid_ctot = f.in_ctot;
+    a.resid_coff = f.in_coff;
+    a.B = B;
+    a.T = T;
+    a.Fin = f.Fout;
+    a.Fout = f.Fin;
+    a.in_ctot = f.cout;
+    a.in_coff = 0;
+    a.cin = f.cout;
+    a.out_ctot = f.in_ctot;
+    a.out_coff = f.in_coff;
+    a.cout = f.cin;
+    a.cout_pad = (f.cin + bn - 1) / bn * bn;
+    a.KT = f.KT;
+    a.KF = f.KF;
+    a.stride_f = f.stride_f;
+    a.pad_t = f.pad_t;
+    a.pad_f = f.pad_f;
+    *flip = (!f.transposed && f.stride_f == 1 && f.pad_f == 1) ? 1 : 0;
+    a.transposed = *flip ? 0 : (f.transposed ? 0 : 1);
+    a.norm_mode = NORM_NONE;
+    a.norm_eps = kInEps;
+    a.norm_inv_n = 1.0;
+    a.elu = 0;
+    a.use_lo = 1;
+    return a;
+}
+bool dgrad_tc_ok(const ConvArgs &f, const ConvArgs &d, const Plan &pl, int B, int T) {
+    return f.cout % 8 == 0 && f.KT == 3 && (size_t)B * f.cout * T * f.Fout * 4 <= pl.dyP_bytes && conv_tc_eligible(d);
+}
+
 bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, bool train = false) {
     if (!make_plan(n, B, T, F, base, pl, train)) return false;
     Walker w{n, pl, B, T, F, nullptr, true};
     w.run(nullptr, nullptr);
+    if (train) {  // the tensor-core data-gradient convs share the per-sample operand scratch
+        std::vector<ConvRec> recs;
+        Walker r{n, pl, B, T, F, nullptr, false};
+        r.record = &recs;
+        r.run(nullptr, nullptr);
+        for (auto &rc : recs) {
+            if (rc.kind != 0 || !rc.in_grad_needed) continue;
+            int flip;
+            ConvArgs d = dgrad_tc_args(rc.a, pl, B, T, nullptr, &flip);
+            if (!dgrad_tc_ok(rc.a, d, pl, B, T)) continue;
+            size_t ww, bb;
+            conv_tc_scratch_need(d, 3, &ww, &bb);
+            w.need_w = std::max(w.need_w, ww);
+            w.need_b = std::max(w.need_b, bb);
+        }
+    }
     plan_scratch(pl, base, w.need_w, w.need_b);
     return true;
 }
@@ -1295,10 +1367,24 @@ struct Backward {
 
     // data gradient of one layer through the forward FMA kernel with transposed weights: in' = dL/dy (channels-last),
     // out' = the input buffer's gradient, accumulated in place (resid == out)
-    int dgrad(const ConvArgs &f, const float *w_packed, int cout_pad_fwd, const float *dy, float *din) {
+    bool use_tc(const ConvArgs &f) const {
+        if (n->mode == 0) return false;  // fp32 mode: FMA kernels throughout
+        int flip;
+        ConvArgs d = dgrad_tc_args(f, pl, B, T, nullptr, &flip);
+        return dgrad_tc_ok(f, d, pl, B, T);
+    }
+
+    int dgrad(const ConvArgs &f, const float *w_packed, int cout_pad_fwd, const float *dy, float *din, bool tc = false) {
         const int bn = conv_fp32_tile_n(f.cin);
         const int cin_pad = (f.cin + bn - 1) / bn * bn;
-        int rc = launch_dgrad_pack(w_packed, pl.wT, f.KT * f.KF, f.cin, f.cout, cout_pad_fwd, cin_pad, st);
+        if (tc) {
+            int flip;
+            ConvArgs d = dgrad_tc_args(f, pl, B, T, din, &flip);
+            int rc = launch_dgrad_pack(w_packed, pl.wT, f.KT * f.KF, f.cin, f.cout, cout_pad_fwd, cin_pad, flip, st);
+            if (rc) return rc;
+            return launch_conv_tc(d, 3, pl.scratch, st);
+        }
+        int rc = launch_dgrad_pack(w_packed, pl.wT, f.KT * f.KF, f.cin, f.cout, cout_pad_fwd, cin_pad, 0, st);
         if (rc) return rc;
         ConvArgs a{};
         a.in = dy;
@@ -1354,6 +1440,8 @@ struct Backward {
         ib.inv_n = 1.0 / ((double)T * f.Fout);
         ib.eps = kInEps;
         ib.plain = f.elu ? 0 : 1;
+        const bool tc = r.in_grad != nullptr && use_tc(f);
+        ib.dyp = tc ? reinterpret_cast<__nv_bfloat16 *>(pl.dyP) : nullptr;
         if (!ib.plain && (!f.out_sums || f.out_layout != LAYOUT_PLANES)) {
             set_error("backward: normalised layer without statistics");
             return MISO_E_STATE;
@@ -1387,7 +1475,7 @@ struct Backward {
         w.transposed = f.transposed;
         rc = launch_wgrad(w, st);
         if (rc) return rc;
-        if (r.in_grad) rc = dgrad(f, n->params[r.cd->w].d, r.cd->cout_pad, og, r.in_grad);
+        if (r.in_grad) rc = dgrad(f, n->params[r.cd->w].d, r.cd->cout_pad, og, r.in_grad, tc);
         return rc;
     }
 
