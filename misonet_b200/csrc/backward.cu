@@ -486,6 +486,194 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
         }
 }
 
+// ---- weight gradient of the stride-1 3x3 convs: all nine taps from one staged halo tile ----------------------------
+// The per-tap kernel above re-reads (and re-normalises, re-splits) every input pixel once per tap and dy once per
+// (tap, cin tile).  For the stride-1 convs (the DenseBlocks: 90 % of the FLOPs) a chunk of <= 32 output pixels -- a
+// 32-bin segment of one frame, or R whole frames when the layer has fewer than 32 bins -- needs the input halo tile
+// [(R + 2) frames x (W + 2) bins], and the im2col row of output pixel k for tap (kt, kf) is halo row
+// base_k + kt (W + 2) + kf: the nine A operands are the same staged tile at nine row offsets (ldmatrix takes a row
+// address per lane).  Warps 0-3 / 4-7 own 16 input channels each for taps 0-4 / 5-8; dy is staged once per chunk.
+constexpr int kWtHP = 104;  // halo rows held in shared memory (>= every base_k + 2 (W + 2) + 2, see the launcher)
+constexpr int kWtSlots = 4;  // halo items (pixel, 8-channel group) per thread: 102 * 8 / 256 rounded up
+
+struct WtapsGeom {
+    int W, R, nseg, nrc;  // bins per segment, frames per chunk, segments per frame, chunk rows per sample
+};
+
+__global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, const WtapsGeom g, int splits) {
+    constexpr int BN = 32, BP = BN + 8;
+    extern __shared__ __align__(16) unsigned char wsm_raw[];
+    __nv_bfloat16 *Ah = reinterpret_cast<__nv_bfloat16 *>(wsm_raw);  // [HP][AP]
+    __nv_bfloat16 *Al = Ah + kWtHP * kWmAP;
+    __nv_bfloat16 *Bh = Al + kWtHP * kWmAP;  // [32][BP]
+    __nv_bfloat16 *Bl = Bh + 32 * BP;
+    float2 *aff = reinterpret_cast<float2 *>(Bl + 32 * BP);  // [B][BM]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int co_tiles = (a.cout + BN - 1) / BN;
+    const int cot = blockIdx.x % co_tiles, cit = blockIdx.x / co_tiles;
+    const int ci0 = cit * kWgBM, co0 = cot * BN;
+    const int npix = a.T * a.Fout;
+    const int W2 = g.W + 2;
+    const int nhalo = (g.R + 2) * W2;
+    const int per_sample = g.nrc * g.nseg;
+    const int total = a.B * per_sample;
+    const int per = (total + splits - 1) / splits;
+    const int c_lo = blockIdx.y * per, c_hi = min(total, c_lo + per);
+
+    for (int i = tid; i < kWtHP * kWmAP / 2; i += 256) {
+        reinterpret_cast<uint32_t *>(Ah)[i] = 0u;
+        reinterpret_cast<uint32_t *>(Al)[i] = 0u;
+    }
+    for (int i = tid; i < a.B * kWgBM; i += 256) {
+        const int b = i / kWgBM, c = ci0 + (i - b * kWgBM);
+        float2 v = make_float2(1.f, 0.f);
+        if (a.x_sums && c < a.cin) {
+            const double *s = a.x_sums + ((size_t)b * a.x_ctot + a.x_coff + c) * 2;
+            v = affine_from_sums(stat_get(s), stat_get(s + 1), a.inv_n, (double)a.eps);
+        }
+        aff[i] = v;
+    }
+    __syncthreads();
+
+    // loader constants: halo items of this thread, and its dy pixel
+    int h_row[kWtSlots], h_col[kWtSlots];
+#pragma unroll
+    for (int sl = 0; sl < kWtSlots; ++sl) {
+        const int h = (tid + 256 * sl) >> 3;
+        h_row[sl] = h < nhalo ? h / W2 : -1;
+        h_col[sl] = h - (h / W2) * W2;
+    }
+    const int g8 = tid & 7;
+    const int bp = tid >> 3, b4 = tid & 7;
+    const int b_r = bp / g.W, b_j = bp - b_r * g.W;
+    const size_t x_lo = (size_t)a.x_ctot * a.T * a.Fin;
+    const int cg = ci0 + g8 * 8;
+    const bool c_ok = cg < a.cin;
+
+    float ra[kWtSlots][8];
+    float4 rb;
+    auto load = [&](int chunk) {
+        const int b = chunk / per_sample;
+        const int rem = chunk - b * per_sample;
+        const int rc = rem / g.nseg, seg = rem - rc * g.nseg;
+        const int t0 = rc * g.R, f0 = seg * g.W;
+        const float2 *af = aff + b * kWgBM + g8 * 8;
+        const __nv_bfloat16 *xb = reinterpret_cast<const __nv_bfloat16 *>(a.x) + (size_t)b * 2 * x_lo + (size_t)((a.x_coff + cg) >> 3) * a.T * a.Fin * 8;
+#pragma unroll
+        for (int sl = 0; sl < kWtSlots; ++sl) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ra[sl][q] = 0.f;
+            if (h_row[sl] < 0 || !c_ok) continue;
+            const int ti = t0 - 1 + h_row[sl], fi = f0 - a.pad_f + h_col[sl];
+            if (ti < 0 || ti >= a.T || fi < 0 || fi >= a.Fin) continue;
+            const __nv_bfloat16 *xp = xb + ((size_t)ti * a.Fin + fi) * 8;
+            const uint4 h = *reinterpret_cast<const uint4 *>(xp);
+            float e[8];
+            e[0] = bf16_lo(h.x); e[1] = bf16_hi(h.x); e[2] = bf16_lo(h.y); e[3] = bf16_hi(h.y);
+            e[4] = bf16_lo(h.z); e[5] = bf16_hi(h.z); e[6] = bf16_lo(h.w); e[7] = bf16_hi(h.w);
+            if (a.use_lo) {
+                const uint4 l = *reinterpret_cast<const uint4 *>(xp + x_lo);
+                e[0] += bf16_lo(l.x); e[1] += bf16_hi(l.x); e[2] += bf16_lo(l.y); e[3] += bf16_hi(l.y);
+                e[4] += bf16_lo(l.z); e[5] += bf16_hi(l.z); e[6] += bf16_lo(l.w); e[7] += bf16_hi(l.w);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ra[sl][q] = fmaf(e[q], af[q].x, af[q].y);
+        }
+        rb = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int t = t0 + b_r, f = f0 + b_j, co = co0 + b4 * 4;
+        if (b_r < g.R && t < a.T && f < a.Fout && co < a.cout)
+            rb = *reinterpret_cast<const float4 *>(a.dy + ((size_t)b * npix + (size_t)t * a.Fout + f) * a.dy_ctot + a.dy_coff + co);
+    };
+
+    float acc[5][4][4];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+    const int wm = warp & 3, wt = warp >> 2;
+    const int lr = lane & 7, lm = lane >> 3;
+    // per-lane halo base row of the im2col rows this lane addresses (k = kh * 16 + (lm >> 1) * 8 + lr)
+    uint32_t a_base[2];
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh) {
+        const int k = kh * 16 + (lm >> 1) * 8 + lr;
+        const int r = k / g.W, j = k - r * g.W;
+        a_base[kh] = (uint32_t)(((r * W2 + j) * kWmAP + wm * 16 + (lm & 1) * 8) * 2);
+    }
+    const uint32_t b_off = (uint32_t)((((lm & 1) * 8 + lr) * BP + (lm >> 1) * 8) * 2);
+    const uint32_t sAh = (uint32_t)__cvta_generic_to_shared(Ah), sAl = (uint32_t)__cvta_generic_to_shared(Al);
+    const uint32_t sBh = (uint32_t)__cvta_generic_to_shared(Bh), sBl = (uint32_t)__cvta_generic_to_shared(Bl);
+
+    if (c_lo < c_hi) load(c_lo);
+    for (int chunk = c_lo; chunk < c_hi; ++chunk) {
+#pragma unroll
+        for (int sl = 0; sl < kWtSlots; ++sl) {
+            if (h_row[sl] < 0) continue;
+            const int h = (tid + 256 * sl) >> 3;
+            uint2 h0, l0, h1, l1;
+            split4(ra[sl], h0, l0);
+            split4(ra[sl] + 4, h1, l1);
+            *reinterpret_cast<uint4 *>(Ah + h * kWmAP + g8 * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            *reinterpret_cast<uint4 *>(Al + h * kWmAP + g8 * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        }
+        {
+            const float v[4] = {rb.x, rb.y, rb.z, rb.w};
+            uint2 hi, lo;
+            split4(v, hi, lo);
+            *reinterpret_cast<uint2 *>(Bh + bp * BP + b4 * 4) = hi;
+            *reinterpret_cast<uint2 *>(Bl + bp * BP + b4 * 4) = lo;
+        }
+        __syncthreads();
+        if (chunk + 1 < c_hi) load(chunk + 1);
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+            uint32_t bh[2][4], bl[2][4];
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+                ldsm_x4_trans(sBh + b_off + kh * 16 * BP * 2 + n2 * 32, bh[n2][0], bh[n2][1], bh[n2][2], bh[n2][3]);
+                ldsm_x4_trans(sBl + b_off + kh * 16 * BP * 2 + n2 * 32, bl[n2][0], bl[n2][1], bl[n2][2], bl[n2][3]);
+            }
+#pragma unroll
+            for (int ti = 0; ti < 5; ++ti) {
+                const int tap = wt * 5 + ti;
+                if (tap < 9) {
+                    const int kt = tap / 3, kf = tap - kt * 3;
+                    const uint32_t toff = (uint32_t)((kt * W2 + kf) * kWmAP * 2);
+                    uint32_t ah[4], al[4];
+                    ldsm_x4_trans(sAh + a_base[kh] + toff, ah[0], ah[1], ah[2], ah[3]);
+                    ldsm_x4_trans(sAl + a_base[kh] + toff, al[0], al[1], al[2], al[3]);
+#pragma unroll
+                    for (int n2 = 0; n2 < 2; ++n2) {
+                        mma_bf16(acc[ti][2 * n2], ah, bh[n2][0], bh[n2][1]);
+                        mma_bf16(acc[ti][2 * n2], ah, bl[n2][0], bl[n2][1]);
+                        mma_bf16(acc[ti][2 * n2], al, bh[n2][0], bh[n2][1]);
+                        mma_bf16(acc[ti][2 * n2 + 1], ah, bh[n2][2], bh[n2][3]);
+                        mma_bf16(acc[ti][2 * n2 + 1], ah, bl[n2][2], bl[n2][3]);
+                        mma_bf16(acc[ti][2 * n2 + 1], al, bh[n2][2], bh[n2][3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    const int gq = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int ti = 0; ti < 5; ++ti) {
+        const int tap = wt * 5 + ti;
+        if (tap >= 9) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ci = ci0 + wm * 16 + gq + (q >> 1) * 8;
+                const int co = co0 + nt * 8 + t4 * 2 + (q & 1);
+                if (ci >= a.cin || co >= a.cout) continue;
+                atomicAdd(a.dw + ((size_t)co * a.cin + ci) * 9 + tap, acc[ti][nt][q]);
+            }
+    }
+}
+
 __global__ void dgrad_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, int taps, int cin, int cout,
                                   int cout_pad, int cin_pad, int flip) {
     const int64_t total = (int64_t)taps * cout * cin_pad;
@@ -773,6 +961,37 @@ static int launch_wgrad_mma(const WgradArgs &a, cudaStream_t st) {
     return MISO_OK;
 }
 
+static bool wgrad_taps_ok(const WgradArgs &a) {
+    return !a.transposed && a.stride_f == 1 && a.KT == 3 && a.KF == 3 && a.pad_t == 1 && (a.pad_f == 0 || a.pad_f == 1) &&
+           a.x_layout == LAYOUT_PLANES && a.Fin == a.Fout + 2 - 2 * a.pad_f;
+}
+
+static int launch_wgrad_taps(const WgradArgs &a, cudaStream_t st) {
+    WtapsGeom g;
+    g.W = std::min(a.Fout, 32);
+    g.R = std::max(1, 32 / a.Fout);
+    g.nseg = ceil_div(a.Fout, g.W);
+    g.nrc = ceil_div(a.T, g.R);
+    // every im2col row stays inside the zero-initialised halo buffer: base_31 + 2 (W + 2) + 2 < kWtHP
+    const int r31 = 31 / g.W, j31 = 31 - r31 * g.W;
+    MISO_REQUIRE((g.R + 2) * (g.W + 2) <= kWtHP && (g.R + 2) * (g.W + 2) <= 256 * kWtSlots / 8 && r31 * (g.W + 2) + j31 + 2 * (g.W + 2) + 2 < kWtHP,
+                 "wgrad_taps: halo geometry out of range (Fout=%d)", a.Fout);
+    const int ntile = ceil_div(a.cin, kWgBM) * ceil_div(a.cout, 32);
+    const int total = a.B * g.nrc * g.nseg;
+    int splits = ceil_div(2 * 148, ntile);
+    splits = std::max(1, std::min(splits, ceil_div(total, 8)));
+    const size_t smem = (size_t)(2 * kWtHP * kWmAP + 2 * 32 * 40) * 2 + (size_t)a.B * kWgBM * sizeof(float2);
+    MISO_REQUIRE(smem <= 200 * 1024, "wgrad: batch %d too large for the per-sample affine table", a.B);
+    static size_t cur = 0;
+    if (smem > 48 * 1024 && smem > cur) {
+        MISO_CUDA(cudaFuncSetAttribute(wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    wgrad_taps_kernel<<<dim3(ntile, splits), 256, smem, st>>>(a, g, splits);
+    MISO_LAUNCHED("wgrad_taps_kernel");
+    return MISO_OK;
+}
+
 int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
     MISO_REQUIRE(a.cin % 4 == 0 && a.x_coff % 4 == 0 && a.x_ctot % 4 == 0, "wgrad: input channels must be multiples of 4");
     MISO_REQUIRE(a.cout % 4 == 0 && a.dy_coff % 4 == 0 && a.dy_ctot % 4 == 0,
@@ -782,6 +1001,8 @@ int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
                  "wgrad: input channel range must be 8-aligned (cin=%d coff=%d)", a.cin, a.x_coff);
     static const bool fma = getenv("MISO_WGRAD_FMA") && atoi(getenv("MISO_WGRAD_FMA")) != 0;  // debugging: the fp32 FMA GEMM
     if (fma) return a.cout <= 32 ? launch_wgrad_t<2>(a, st) : launch_wgrad_t<4>(a, st);
+    static const bool no_taps = getenv("MISO_WGRAD_TAPS") && atoi(getenv("MISO_WGRAD_TAPS")) == 0;  // debugging: per-tap kernel only
+    if (!no_taps && wgrad_taps_ok(a)) return launch_wgrad_taps(a, st);
     return a.cout <= 32 ? launch_wgrad_mma<32>(a, st) : launch_wgrad_mma<64>(a, st);
 }
 
