@@ -550,34 +550,33 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
     const int cg = ci0 + g8 * 8;
     const bool c_ok = cg < a.cin;
 
-    float ra[kWtSlots][8];
+    // The loader only ISSUES the global loads (raw plane pixels stay in registers across the MMA phase); normalising and
+    // splitting happen when the tile is stored, one iteration later -- an arithmetic use right behind a load would stall
+    // the warp for the full memory latency before it reaches its MMAs.
+    uint4 rh[kWtSlots], rl[kWtSlots];
+    unsigned rvalid = 0;
+    int rb_sample = 0;
     float4 rb;
     auto load = [&](int chunk) {
         const int b = chunk / per_sample;
         const int rem = chunk - b * per_sample;
         const int rc = rem / g.nseg, seg = rem - rc * g.nseg;
         const int t0 = rc * g.R, f0 = seg * g.W;
-        const float2 *af = aff + b * kWgBM + g8 * 8;
         const __nv_bfloat16 *xb = reinterpret_cast<const __nv_bfloat16 *>(a.x) + (size_t)b * 2 * x_lo + (size_t)((a.x_coff + cg) >> 3) * a.T * a.Fin * 8;
+        rvalid = 0;
+        rb_sample = b;
 #pragma unroll
         for (int sl = 0; sl < kWtSlots; ++sl) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) ra[sl][q] = 0.f;
-            if (h_row[sl] < 0 || !c_ok) continue;
             const int ti = t0 - 1 + h_row[sl], fi = f0 - a.pad_f + h_col[sl];
-            if (ti < 0 || ti >= a.T || fi < 0 || fi >= a.Fin) continue;
-            const __nv_bfloat16 *xp = xb + ((size_t)ti * a.Fin + fi) * 8;
-            const uint4 h = *reinterpret_cast<const uint4 *>(xp);
-            float e[8];
-            e[0] = bf16_lo(h.x); e[1] = bf16_hi(h.x); e[2] = bf16_lo(h.y); e[3] = bf16_hi(h.y);
-            e[4] = bf16_lo(h.z); e[5] = bf16_hi(h.z); e[6] = bf16_lo(h.w); e[7] = bf16_hi(h.w);
-            if (a.use_lo) {
-                const uint4 l = *reinterpret_cast<const uint4 *>(xp + x_lo);
-                e[0] += bf16_lo(l.x); e[1] += bf16_hi(l.x); e[2] += bf16_lo(l.y); e[3] += bf16_hi(l.y);
-                e[4] += bf16_lo(l.z); e[5] += bf16_hi(l.z); e[6] += bf16_lo(l.w); e[7] += bf16_hi(l.w);
+            const bool ok = h_row[sl] >= 0 && c_ok && ti >= 0 && ti < a.T && fi >= 0 && fi < a.Fin;
+            const __nv_bfloat16 *xp = xb + ((size_t)(ok ? ti : 0) * a.Fin + (ok ? fi : 0)) * 8;
+            rh[sl] = make_uint4(0u, 0u, 0u, 0u);
+            rl[sl] = rh[sl];
+            if (ok) {
+                rh[sl] = *reinterpret_cast<const uint4 *>(xp);
+                if (a.use_lo) rl[sl] = *reinterpret_cast<const uint4 *>(xp + x_lo);
+                rvalid |= 1u << sl;
             }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) ra[sl][q] = fmaf(e[q], af[q].x, af[q].y);
         }
         rb = make_float4(0.f, 0.f, 0.f, 0.f);
         const int t = t0 + b_r, f = f0 + b_j, co = co0 + b4 * 4;
@@ -606,15 +605,27 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
 
     if (c_lo < c_hi) load(c_lo);
     for (int chunk = c_lo; chunk < c_hi; ++chunk) {
+        {
+            const float2 *af = aff + rb_sample * kWgBM + g8 * 8;
 #pragma unroll
-        for (int sl = 0; sl < kWtSlots; ++sl) {
-            if (h_row[sl] < 0) continue;
-            const int h = (tid + 256 * sl) >> 3;
-            uint2 h0, l0, h1, l1;
-            split4(ra[sl], h0, l0);
-            split4(ra[sl] + 4, h1, l1);
-            *reinterpret_cast<uint4 *>(Ah + h * kWmAP + g8 * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-            *reinterpret_cast<uint4 *>(Al + h * kWmAP + g8 * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            for (int sl = 0; sl < kWtSlots; ++sl) {
+                if (h_row[sl] < 0) continue;
+                const int h = (tid + 256 * sl) >> 3;
+                float v[8];
+                const uint4 hh = rh[sl], ll = rl[sl];
+                v[0] = bf16_lo(hh.x) + bf16_lo(ll.x); v[1] = bf16_hi(hh.x) + bf16_hi(ll.x);
+                v[2] = bf16_lo(hh.y) + bf16_lo(ll.y); v[3] = bf16_hi(hh.y) + bf16_hi(ll.y);
+                v[4] = bf16_lo(hh.z) + bf16_lo(ll.z); v[5] = bf16_hi(hh.z) + bf16_hi(ll.z);
+                v[6] = bf16_lo(hh.w) + bf16_lo(ll.w); v[7] = bf16_hi(hh.w) + bf16_hi(ll.w);
+                const bool ok = (rvalid >> sl) & 1u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = ok ? fmaf(v[q], af[q].x, af[q].y) : 0.f;
+                uint2 h0, l0, h1, l1;
+                split4(v, h0, l0);
+                split4(v + 4, h1, l1);
+                *reinterpret_cast<uint4 *>(Ah + h * kWmAP + g8 * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<uint4 *>(Al + h * kWmAP + g8 * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
         }
         {
             const float v[4] = {rb.x, rb.y, rb.z, rb.w};
@@ -740,7 +751,7 @@ __global__ void __launch_bounds__(256) tcn_recompute_kernel(const TcnBwdArgs a, 
     }
 }
 
-constexpr int kTcnRows = 32;  // frames per CTA of the channel-parallel kernels
+constexpr int kTcnRows = 8;   // frames per CTA of the channel-parallel kernels
 constexpr int kTcnCh = 8;     // channels per thread (128 threads): C <= 1024
 
 // gLN backward, pass 1: per-sample sums of g = gamma * dq and g * phat; per-channel gamma / beta gradients
