@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
 // base_k + kt (W + 2) + kf: the nine A operands are the same staged tile at nine row offsets (ldmatrix takes a row
 // address per lane).  Warps 0-3 / 4-7 own 16 input channels each for taps 0-4 / 5-8; dy is staged once per chunk.
 constexpr int kWtHP = 104;  // halo rows held in shared memory (>= every base_k + 2 (W + 2) + 2, see the launcher)
+constexpr int kWtAff = 80;   // float2 per sample in the affine table: 8 groups of 8 channels at a pitch of 10
 constexpr int kWtSlots = 4;  // halo items (pixel, 8-channel group) per thread: 102 * 8 / 256 rounded up
 
 struct WtapsGeom {
@@ -525,13 +526,13 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
         reinterpret_cast<uint32_t *>(Al)[i] = 0u;
     }
     for (int i = tid; i < a.B * kWgBM; i += 256) {
-        const int b = i / kWgBM, c = ci0 + (i - b * kWgBM);
+        const int b = i / kWgBM, cl = i - b * kWgBM, c = ci0 + cl;
         float2 v = make_float2(1.f, 0.f);
         if (a.x_sums && c < a.cin) {
             const double *s = a.x_sums + ((size_t)b * a.x_ctot + a.x_coff + c) * 2;
             v = affine_from_sums(stat_get(s), stat_get(s + 1), a.inv_n, (double)a.eps);
         }
-        aff[i] = v;
+        aff[b * kWtAff + (cl >> 3) * 10 + (cl & 7)] = v;  // 80-byte rows per 8-channel group: conflict-free 16-byte reads
     }
     __syncthreads();
 
@@ -606,7 +607,16 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
     if (c_lo < c_hi) load(c_lo);
     for (int chunk = c_lo; chunk < c_hi; ++chunk) {
         {
-            const float2 *af = aff + rb_sample * kWgBM + g8 * 8;
+            float2 af[8];
+            {
+                const float4 *ap4 = reinterpret_cast<const float4 *>(aff + rb_sample * kWtAff + g8 * 10);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v4 = ap4[q];
+                    af[2 * q] = make_float2(v4.x, v4.y);
+                    af[2 * q + 1] = make_float2(v4.z, v4.w);
+                }
+            }
 #pragma unroll
             for (int sl = 0; sl < kWtSlots; ++sl) {
                 if (h_row[sl] < 0) continue;
@@ -654,12 +664,18 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
                     ldsm_x4_trans(sAh + a_base[kh] + toff, ah[0], ah[1], ah[2], ah[3]);
                     ldsm_x4_trans(sAl + a_base[kh] + toff, al[0], al[1], al[2], al[3]);
 #pragma unroll
-                    for (int n2 = 0; n2 < 2; ++n2) {
+                    for (int n2 = 0; n2 < 2; ++n2) {  // four independent accumulators between dependent MMAs
                         mma_bf16(acc[ti][2 * n2], ah, bh[n2][0], bh[n2][1]);
-                        mma_bf16(acc[ti][2 * n2], ah, bl[n2][0], bl[n2][1]);
-                        mma_bf16(acc[ti][2 * n2], al, bh[n2][0], bh[n2][1]);
                         mma_bf16(acc[ti][2 * n2 + 1], ah, bh[n2][2], bh[n2][3]);
+                    }
+#pragma unroll
+                    for (int n2 = 0; n2 < 2; ++n2) {
+                        mma_bf16(acc[ti][2 * n2], ah, bl[n2][0], bl[n2][1]);
                         mma_bf16(acc[ti][2 * n2 + 1], ah, bl[n2][2], bl[n2][3]);
+                    }
+#pragma unroll
+                    for (int n2 = 0; n2 < 2; ++n2) {
+                        mma_bf16(acc[ti][2 * n2], al, bh[n2][0], bh[n2][1]);
                         mma_bf16(acc[ti][2 * n2 + 1], al, bh[n2][2], bh[n2][3]);
                     }
                 }
@@ -989,9 +1005,9 @@ static int launch_wgrad_taps(const WgradArgs &a, cudaStream_t st) {
                  "wgrad_taps: halo geometry out of range (Fout=%d)", a.Fout);
     const int ntile = ceil_div(a.cin, kWgBM) * ceil_div(a.cout, 32);
     const int total = a.B * g.nrc * g.nseg;
-    int splits = ceil_div(2 * 148, ntile);
+    int splits = std::max(1, 148 / ntile);  // one CTA per SM (register-limited), one wave: half the atomics of two waves
     splits = std::max(1, std::min(splits, ceil_div(total, 8)));
-    const size_t smem = (size_t)(2 * kWtHP * kWmAP + 2 * 32 * 40) * 2 + (size_t)a.B * kWgBM * sizeof(float2);
+    const size_t smem = (size_t)(2 * kWtHP * kWmAP + 2 * 32 * 40) * 2 + (size_t)a.B * kWtAff * sizeof(float2);
     MISO_REQUIRE(smem <= 200 * 1024, "wgrad: batch %d too large for the per-sample affine table", a.B);
     static size_t cur = 0;
     if (smem > 48 * 1024 && smem > cur) {
