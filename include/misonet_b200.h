@@ -147,22 +147,26 @@ int64_t miso_net_tap(miso_net_t *net, const char *name, float *d_out, int64_t ca
  * miso_net_forward_train is miso_net_forward on the TRAINING workspace plan: every TemporalBlock keeps its input and
  * mid state (the inference plan updates the residual stream in place), no CUDA graph.  miso_net_backward then consumes
  * the activations and statistics the forward left in the SAME workspace:
- *   d_gy    : dL/d(output), fp32 channels-last [B, T, F, out_ch] (the layout of d_y; see miso_grad_pack); clobbered
+ *   d_gy    : dL/d(output), fp32 channels-last [B, T, F, out_ch rounded up to a multiple of 4] (the layout of d_y with
+ *             zero padding channels; written by miso_grad_pack); clobbered
  *   d_grads : gradient of every parameter, flat fp32 in miso_net_param_key order, each in its torch layout
  *             (miso_net_grad_numel elements in total); overwritten.
  * Both run in the conv mode of miso_net_set_mode for the forward; all backward arithmetic is fp32 FMA
  * (InstanceNorm2d / ELU / gLN / PReLU / depthwise / InstanceNorm1d backward kernels, the weight-gradient GEMM, and
- * the data gradients through the forward FMA conv kernel with transposed weights).  out_ch must be a multiple of 4. */
+ * the data gradients through the forward conv kernels with transposed weights). */
 int64_t miso_net_grad_numel(const miso_net_t *net);
 size_t miso_net_train_workspace_bytes(const miso_net_t *net, int B, int T, int F);
 int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, int T, int F, void *d_ws,
                            size_t ws_bytes, void *stream);
 int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int T, int F, void *d_ws, size_t ws_bytes,
                       float *d_grads, void *stream);
-/* complex64 gradient [B, S, T, F] (PyTorch convention dL/dre + i dL/dim) -> d_gy layout [B, T, F, 2S] */
+/* complex64 gradient [B, S, T, F] (PyTorch convention dL/dre + i dL/dim) -> d_gy layout [B, T, F, round_up(2S, 4)] */
 int miso_grad_pack(const void *d_grad, float *d_gy, int B, int S, int T, int F, void *stream);
 /* gradient of loss_uPIT (criterion.py:8-63) w.r.t. the estimate for the winning permutation d_perm_idx[b]
  * (int64, from miso_pair_fwd mode 1), scaled by the upstream scalar *d_gout: complex64 [B, S, T, F] dense. */
+/* gradient of loss_Enhance (criterion.py:121-141) w.r.t. the estimate, scaled by *d_gout: complex64, same shape */
+int miso_loss_enhance_bwd(const void *d_est, const void *d_ref, int B, int64_t n_per_batch, const float *d_gout,
+                          void *d_grad, void *stream);
 int miso_upit_bwd(const void *d_est, int64_t e_sb, int64_t e_ss, const void *d_ref, int64_t r_sb, int64_t r_ss,
                   const int64_t *d_perm_idx, int B, int S, int T, int F, const float *d_gout, void *d_grad,
                   void *stream);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "miso_net_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "miso_net_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "miso_grad_pack": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "miso_loss_enhance_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "miso_upit_bwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p]),
     "miso_net_tap": (c_int64, [c_void_p, c_char_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -111,6 +111,32 @@ def loss_uPIT(num_spks, estimate_clean, ref_clean, return_perm=False):
     return (loss, idx) if return_perm else loss
 
 
+class _EnhanceFunction(torch.autograd.Function):
+    """loss_Enhance with its gradient w.r.t. the estimate (miso_loss_enhance_bwd)."""
+
+    @staticmethod
+    def forward(ctx, est, rf):
+        B = est.shape[0]
+        loss = torch.empty((), dtype=torch.float32, device=est.device)
+        ws = _workspace(1024 * 8, est.device)
+        with torch.cuda.device(est.device):
+            _lib.check(_lib.load().miso_loss_enhance_fwd(_lib.ptr(est), _lib.ptr(rf), B, est.numel() // B, _lib.ptr(loss), _lib.ptr(ws),
+                                                         ws.numel(), _lib.stream_ptr()), "miso_loss_enhance_fwd")
+        ctx.save_for_backward(est, rf)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        est, rf = ctx.saved_tensors
+        B = est.shape[0]
+        grad = torch.empty_like(est)
+        g = gloss.detach().to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(est.device):
+            _lib.check(_lib.load().miso_loss_enhance_bwd(_lib.ptr(est), _lib.ptr(rf), B, est.numel() // B, _lib.ptr(g), _lib.ptr(grad),
+                                                         _lib.stream_ptr()), "miso_loss_enhance_bwd")
+        return grad, None
+
+
 def loss_Enhance(estimate, ref):
     """criterion.py:121-141.  estimate, ref: complex [B,Ch,T,F] -> float32 scalar."""
     _lib.require_cuda(estimate, "estimate")
@@ -119,6 +145,8 @@ def loss_Enhance(estimate, ref):
     rf = ref.to(device=est.device, dtype=torch.complex64).contiguous()
     if est.shape != rf.shape:
         raise ValueError("shape mismatch")
+    if torch.is_grad_enabled() and estimate.requires_grad:
+        return _EnhanceFunction.apply(est, rf)               # training: trainer.py:398-443
     B = est.shape[0]
     n = est.numel() // B
     loss = torch.empty((), dtype=torch.float32, device=est.device)

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kEw) in_bwd_apply_kernel(const InBwdArgs a, in
         for (int q = 0; q < 4; ++q) atomicAdd(&sh[c4 * 4 + q], sb[q]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < a.c; i += kEw) atomicAdd(&a.dbias[i], sh[i]);
+    for (int i = threadIdx.x; i < a.c_real; i += kEw) atomicAdd(&a.dbias[i], sh[i]);
 }
 
 // ---- weight gradient ---------------------------------------------------------------------------------------------
@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int split
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const int co = co0 + tx * TN + j;
-            if (co >= a.cout) continue;
-            const size_t idx = a.transposed ? ((size_t)ci * a.cout + co) * taps + tap : ((size_t)co * a.cin + ci) * taps + tap;
+            if (co >= a.cout_real) continue;
+            const size_t idx = a.transposed ? ((size_t)ci * a.cout_real + co) * taps + tap : ((size_t)co * a.cin + ci) * taps + tap;
             atomicAdd(a.dw + idx, acc[i][j]);
         }
     }
@@ -480,8 +480,8 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
         for (int q = 0; q < 4; ++q) {
             const int ci = ci0 + wm * 16 + g + (q >> 1) * 8;
             const int co = co0 + nt * 8 + t4 * 2 + (q & 1);
-            if (ci >= a.cin || co >= a.cout) continue;
-            const size_t idx = a.transposed ? ((size_t)ci * a.cout + co) * taps + tap : ((size_t)co * a.cin + ci) * taps + tap;
+            if (ci >= a.cin || co >= a.cout_real) continue;
+            const size_t idx = a.transposed ? ((size_t)ci * a.cout_real + co) * taps + tap : ((size_t)co * a.cin + ci) * taps + tap;
             atomicAdd(a.dw + idx, acc[nt][q]);
         }
 }
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
             for (int q = 0; q < 4; ++q) {
                 const int ci = ci0 + wm * 16 + gq + (q >> 1) * 8;
                 const int co = co0 + nt * 8 + t4 * 2 + (q & 1);
-                if (ci >= a.cin || co >= a.cout) continue;
+                if (ci >= a.cin || co >= a.cout_real) continue;
                 atomicAdd(a.dw + ((size_t)co * a.cin + ci) * 9 + tap, acc[ti][nt][q]);
             }
     }
@@ -1111,16 +1111,32 @@ __global__ void upit_bwd_kernel(const float2 *__restrict__ est, int64_t e_sb, in
     }
 }
 
-// complex gradient [B][S][n] -> the network output layout fp32 [B][n][2S] (re of every speaker, then im)
-__global__ void grad_pack_kernel(const float2 *__restrict__ g, float *__restrict__ gy, int B, int S, int64_t n) {
+// complex gradient [B][S][n] -> the network output layout fp32 [B][n][pitch] (re of every speaker, then im; pitch = 2S
+// rounded up to a multiple of 4, padding zero)
+__global__ void grad_pack_kernel(const float2 *__restrict__ g, float *__restrict__ gy, int B, int S, int64_t n, int pitch) {
     const int64_t total = (int64_t)B * n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = i / n, e = i - b * n;
         for (int s = 0; s < S; ++s) {
             const float2 v = g[(b * S + s) * n + e];
-            gy[i * 2 * S + s] = v.x;
-            gy[i * 2 * S + S + s] = v.y;
+            gy[i * pitch + s] = v.x;
+            gy[i * pitch + S + s] = v.y;
         }
+        for (int c = 2 * S; c < pitch; ++c) gy[i * pitch + c] = 0.f;
+    }
+}
+
+// gradient of criterion.py:121-141 (loss_Enhance): the same three L1 terms without a permutation
+__global__ void enhance_bwd_kernel(const float2 *__restrict__ est, const float2 *__restrict__ ref, int64_t total, float scale_div,
+                                   const float *__restrict__ gout, float2 *__restrict__ grad) {
+    const float scale = gout[0] / scale_div;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 x = est[i], y = ref[i];
+        const float mag = sqrtf(x.x * x.x + x.y * x.y + 1e-8f);
+        const float rm = sqrtf(y.x * y.x + y.y * y.y);
+        auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+        const float sm = sgn(mag - rm) / mag;
+        grad[i] = make_float2(scale * (sgn(x.x - y.x) + sm * x.x), scale * (sgn(x.y - y.y) + sm * x.y));
     }
 }
 
@@ -1154,8 +1170,20 @@ int miso_grad_pack(const void *d_grad, float *d_gy, int B, int S, int T, int F, 
     MISO_REQUIRE(d_grad && d_gy && S >= 1, "miso_grad_pack: bad argument");
     const int64_t n = (int64_t)T * F;
     const int blocks = (int)std::min<int64_t>((B * n + 255) / 256, 148 * 16);
-    grad_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2 *>(d_grad), d_gy, B, S, n);
+    grad_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2 *>(d_grad), d_gy, B, S, n, (2 * S + 3) & ~3);
     MISO_LAUNCHED("grad_pack_kernel");
+    return MISO_OK;
+}
+
+int miso_loss_enhance_bwd(const void *d_est, const void *d_ref, int B, int64_t n_per_batch, const float *d_gout, void *d_grad,
+                          void *stream) {
+    using namespace miso;
+    MISO_REQUIRE(d_est && d_ref && d_gout && d_grad && B >= 1 && n_per_batch >= 1, "miso_loss_enhance_bwd: bad argument");
+    const int64_t total = (int64_t)B * n_per_batch;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    enhance_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2 *>(d_est), reinterpret_cast<const float2 *>(d_ref),
+                                                             total, (float)B, d_gout, reinterpret_cast<float2 *>(d_grad));
+    MISO_LAUNCHED("enhance_bwd_kernel");
     return MISO_OK;
 }
 

@@ -15,6 +15,7 @@ struct InBwdArgs {
     double *red;             // [B][c][2] fp64 scratch: sum dz, sum dz * z
     float *dbias;            // [c] (torch layout), accumulated
     int B, npix, ctot, coff, c;
+    int c_real;  // channels that own a bias (c_real < c only for a network output padded to a multiple of 4 channels)
     int use_lo;
     double inv_n;
     float eps;
@@ -38,6 +39,7 @@ struct WgradArgs {
     int B, T, Fin, Fout;
     int x_ctot, x_coff, cin;
     int dy_ctot, dy_coff, cout;
+    int cout_real;  // output channels of the parameter tensor (cout_real < cout only for a padded network output)
     int KT, KF, stride_f, pad_t, pad_f, transposed;
 };
 int launch_wgrad(const WgradArgs &a, cudaStream_t st);

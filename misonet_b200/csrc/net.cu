@@ -1422,8 +1422,15 @@ struct Backward {
     }
 
     int conv_layer(const ConvRec &r, float *d_gy) {
-        const ConvArgs &f = r.a;
+        ConvArgs f = r.a;
+        const int cout_real = f.cout;
         float *og = r.out_grad ? r.out_grad : d_gy;
+        if (!r.out_grad) {
+            // the network output: the caller's gradient is padded to a multiple of 4 channels (miso_grad_pack); the pad
+            // channels carry zero gradient and meet zero-padded packed weights in the data gradient
+            f.cout = (f.cout + 3) & ~3;
+            f.out_ctot = f.cout;
+        }
         int rc;
         InBwdArgs ib{};
         ib.e = reinterpret_cast<const __nv_bfloat16 *>(f.out);
@@ -1436,6 +1443,7 @@ struct Backward {
         ib.ctot = f.out_ctot;
         ib.coff = f.out_coff;
         ib.c = f.cout;
+        ib.c_real = cout_real;
         ib.use_lo = f.use_lo;
         ib.inv_n = 1.0 / ((double)T * f.Fout);
         ib.eps = kInEps;
@@ -1467,6 +1475,7 @@ struct Backward {
         w.dy_ctot = f.out_ctot;
         w.dy_coff = f.out_coff;
         w.cout = f.cout;
+        w.cout_real = cout_real;
         w.KT = f.KT;
         w.KF = f.KF;
         w.stride_f = f.stride_f;
@@ -1543,6 +1552,7 @@ struct Backward {
         w.dy_ctot = C;
         w.dy_coff = 0;
         w.cout = C;
+        w.cout_real = C;
         w.KT = 1;
         w.KF = 1;
         w.stride_f = 1;
@@ -1620,7 +1630,6 @@ int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, 
 int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int T, int F, void *d_ws, size_t ws_bytes,
                       float *d_grads, void *stream) {
     MISO_REQUIRE(net && d_x && d_gy && d_ws && d_grads, "miso_net_backward: null argument");
-    MISO_REQUIRE(net->out_ch % 4 == 0, "miso_net_backward: out_ch=%d must be a multiple of 4 (MISO_1 with 2 speakers)", net->out_ch);
     int rc = miso_net_check_shape(net, T, F);
     if (rc) return rc;
     Plan pl;

@@ -118,7 +118,7 @@ class _NetFunction(torch.autograd.Function):
         g = gout.to(torch.complex64).contiguous()
         st = _lib.stream_ptr()
         with torch.cuda.device(dev):
-            gy = torch.empty(B, T, F, 2 * S, dtype=torch.float32, device=dev)
+            gy = torch.empty(B, T, F, (2 * S + 3) // 4 * 4, dtype=torch.float32, device=dev)
             _lib.check(lib.miso_grad_pack(_lib.ptr(g), _lib.ptr(gy), B, S, T, F, st), "miso_grad_pack")
             flat = torch.empty(lib.miso_net_grad_numel(m._handle), dtype=torch.float32, device=dev)
             ws = m._ws_train
@@ -326,13 +326,7 @@ class _MisoNet(nn.Module):
 
     def _training_pass(self):
         """True when this forward must be differentiable (autograd on and a parameter requires grad)."""
-        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)):
-            return False
-        if self._out_ch % 4:
-            raise NotImplementedError(
-                "misonet_b200: the backward pass needs out_ch % 4 == 0 (MISO_1 with two speakers); the MISO_3 training "
-                "path (SURVEY.md section 8(f) rank 4) is not implemented yet -- call under torch.no_grad()")
-        return True
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
 
     def _run_body_train(self, x_cl, B, T, F):
         """Training forward: x_cl input planes -> float32 [B,T,F,out_ch]; leaves the workspace for the backward."""
@@ -422,7 +416,6 @@ class MISO_3(_MisoNet):
         but every caller passes (mix, beamformed, MISO1): tester.py:1242, trainer.py:398-414);
         the weights see channels [mix x M, second, third].
         mixture [B,M,T,F], second/third [B,1,T,F] complex -> complex64 [B, num_spks, T, F]."""
-        self._training_pass()
         mix, second, third = self._prepare(mixture, MISO1, BF)
         B, M, T, F = mix.shape
         if 2 * (M + 2) != self._in_ch:
@@ -433,5 +426,9 @@ class MISO_3(_MisoNet):
         x_cl = self._input_planes(B, T, F, mix.device)
         _lib.check(_lib.load().miso_pack_miso3(_lib.ptr(mix), _lib.ptr(second), _lib.ptr(third), _lib.ptr(x_cl), B, M, T, F,
                                                _lib.stream_ptr()), "miso_pack_miso3")
+        if self._training_pass():
+            # trainer.py:398-414: the beamformed / MISO1 inputs are data (computed under no_grad or loaded from
+            # disk, data.py:133-207), so only the parameters receive gradients
+            return _NetFunction.apply(self, x_cl, B, T, F, *self._param_list)
         y_cl = self._run_body(x_cl, B, T, F)
         return self._unpack(y_cl, B, T, F)

@@ -282,10 +282,6 @@ def test_net_bad_shape_is_a_clear_error():
     with pytest.raises(_lib.MisoError, match="needs F=129"):
         with torch.no_grad():
             m(mix)
-    m3, _, _ = _model("miso3", 1)
-    x = torch.from_numpy(synth.random_spec(1, (1, 6, 8, 129))).cuda()
-    with pytest.raises(NotImplementedError):
-        m3(x, x[:, :1], x[:, :1])                  # grad mode: the MISO_3 backward (section 8(f) rank 4) is not built
 
 
 # ------------------------------------------------------------------------------- A1 / L1 / L2

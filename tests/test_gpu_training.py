@@ -48,7 +48,7 @@ def _oracle_grads(sd, cfg, mix, upstream=None, refs=None, dtype=torch.float32, p
     """torch autograd over the oracle network; returns (output complex [B,S,T,F], {key: grad}, loss or None)."""
     from oracle import miso_net_torch as mnt
     sdr = {k: v.clone().to(dtype).requires_grad_(True) for k, v in sd.items()}
-    x = torch.cat((mix.real, mix.imag), dim=1).to(dtype)
+    x = (torch.cat((mix.real, mix.imag), dim=1) if mix.is_complex() else mix).to(dtype)   # a real tensor is the network input itself
     if perturb:
         x = x * (1.0 + perturb * torch.randn(x.shape, dtype=dtype, generator=torch.Generator().manual_seed(99)))
     if upstream is not None:
@@ -157,6 +157,60 @@ def test_backward_reference_prelu_slope():
     a = torch.cat([p.grad.flatten() for p in m.parameters()]).cpu().double()
     b = torch.cat([g_ref[k].flatten() for k, _ in m.named_parameters()])
     assert float((a @ b) / (a.norm() * b.norm())) > 0.99995
+
+
+def test_miso3_backward_and_loss_enhance():
+    """MISO_3 training step (trainer.py:398-443): 16 input / 2 output channels, loss_Enhance; PReLU slopes 1 for the
+    per-parameter check (module docstring)."""
+    from misonet_b200 import criterion, synth
+    from misonet_b200.model import MISO_3
+    from oracle import weights
+    from oracle import miso_net_torch as mnt
+    en, de = mnt.LAYOUTS["REF"]
+    cfg = mnt.NetConfig.miso3(layout="REF")
+    sd = weights.make_state_dict(cfg, 6)
+    for k in sd:
+        if k.startswith("TCN.") and k.endswith(".net.1.weight"):
+            sd[k] = torch.ones_like(sd[k])
+    m = MISO_3(1, 6, len(en), list(en), list(de), "IN")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    m.conv_mode = "bf16x3"
+    B, T, F = 2, 24, 129
+    mix = torch.from_numpy(synth.random_spec(51, (B, 6, T, F)))
+    bf = torch.from_numpy(synth.random_spec(52, (B, 1, T, F)))
+    m1 = torch.from_numpy(synth.random_spec(53, (B, 1, T, F)))
+    up = torch.from_numpy(synth.random_spec(54, (B, 1, T, F)))
+    x = torch.cat((mix.real, bf.real, m1.real, mix.imag, bf.imag, m1.imag), dim=1)          # model.py:358-366
+    out_ref, g_ref, _ = _oracle_grads(sd, cfg, x, upstream=up, dtype=torch.float64)
+    out = m(mix.cuda(), bf.cuda(), m1.cuda())
+    assert rel_err(out.detach().cpu().numpy(), out_ref.numpy()) < 2 * FORWARD_AGREEMENT
+    out.backward(up.cuda())
+    _check_grads(m, g_ref, "MISO_3 REF bf16x3")
+    # loss_Enhance and its gradient on identical inputs (criterion.py:121-141)
+    est = torch.from_numpy(synth.random_spec(55, (B, 1, T, F)))
+    ref = torch.from_numpy(synth.random_spec(56, (B, 1, T, F)))
+    e = est.clone().requires_grad_(True)
+    L = ((e.real - ref.real).abs().sum() + (e.imag - ref.imag).abs().sum() +
+         (torch.sqrt(e.real ** 2 + e.imag ** 2 + 1e-8) - ref.abs()).abs().sum()) / B
+    (2.0 * L).backward()
+    ec = est.cuda().requires_grad_(True)
+    loss = criterion.loss_Enhance(ec, ref.cuda())
+    assert abs(loss.item() - L.item()) <= 2e-6 * abs(L.item())
+    (2.0 * loss).backward()
+    assert rel_err(ec.grad.cpu().numpy(), e.grad.numpy()) < 1e-6
+    # one full step: the loss decreases along the negative gradient
+    m.zero_grad(set_to_none=True)
+    tgt = torch.from_numpy(synth.random_spec(57, (B, 1, T, F))).cuda()
+    l0 = criterion.loss_Enhance(m(mix.cuda(), bf.cuda(), m1.cuda()), tgt)
+    l0.backward()
+    gn2 = sum(float((p.grad ** 2).sum()) for p in m.parameters())
+    step = 1e-3 * l0.item() / gn2
+    with torch.no_grad():
+        for p in m.parameters():
+            p -= step * p.grad
+        l1 = criterion.loss_Enhance(m(mix.cuda(), bf.cuda(), m1.cuda()), tgt)
+    assert l1.item() < l0.item(), (l0.item(), l1.item())
 
 
 def test_upit_loss_gradient_kernel():
