@@ -29,3 +29,32 @@ def train_step(model, optimizer, mix_stft, ref_stft, ref_ch=0, max_norm=None, tr
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)             # trainer.py:209-211
     optimizer.step()                                                             # trainer.py:212
     return loss.detach()
+
+
+def train_step_enhance(model, optimizer, mix_stft, beamform_stft, miso1_stft, ref_stft, max_norm=None, training=True):
+    """MISO_3 enhancement step (mirror of ``Trainer_Enhance``'s batch body, trainer.py:388-416): one optimizer update per
+    speaker, ``model(mix, s_bf, MISO1_spk)`` against ``loss_Enhance``.  ``beamform_stft`` / ``miso1_stft`` / ``ref_stft``:
+    list[num_spks] of complex [B, 1, T, F] (beamformed, MISO1 at the reference microphone, clean reference; they are
+    data -- trainer.py reads them from the pickles of data.py:133-207 -- so only the parameters receive gradients).
+    Returns the mean of the per-speaker losses (trainer.py:410,423 accumulate ``loss.item() / 2``).
+
+    trainer.py:416 feeds speaker 1's beamformed signal to speaker 2's training forward (SURVEY.md appendix B lists it as
+    a defect; the inference path tester.py:936-939 and the validation branch trainer.py:413 use speaker 2's); this
+    mirror pairs each speaker with its own beamformed signal."""
+    total = 0.0
+    n = len(ref_stft)
+    for s in range(n):
+        if not training:
+            with torch.no_grad():
+                total = total + criterion.loss_Enhance(model(mix_stft, beamform_stft[s], miso1_stft[s]), ref_stft[s]) / n
+            continue
+        estimate = model(mix_stft, beamform_stft[s], miso1_stft[s])              # trainer.py:400,416
+        loss = criterion.loss_Enhance(estimate, ref_stft[s])                     # trainer.py:402,418
+        optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        distributed.allreduce_gradients(model.parameters(), n_local=mix_stft.shape[0])
+        if max_norm:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+        optimizer.step()
+        total = total + loss.detach() / n
+    return total
