@@ -911,6 +911,23 @@ __global__ void __launch_bounds__(128) in1d_bwd_apply_kernel(const TcnBwdArgs a,
     }
 }
 
+__global__ void cl_to_planes_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int B, int npix, int C) {
+    const int64_t total = (int64_t)B * npix * (C >> 2);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % (C >> 2));
+        const int64_t r = i / (C >> 2);
+        const int p = (int)(r % npix), b = (int)(r / npix);
+        const float4 v = *reinterpret_cast<const float4 *>(src + r * C + c4 * 4);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        uint2 hi, lo;
+        split4(f, hi, lo);
+        const int c = c4 * 4;
+        __nv_bfloat16 *d = dst + (size_t)b * 2 * C * npix + ((size_t)(c >> 3) * npix + p) * 8 + (c & 7);
+        *reinterpret_cast<uint2 *>(d) = hi;
+        *reinterpret_cast<uint2 *>(d + (size_t)C * npix) = lo;
+    }
+}
+
 __global__ void copy_channels_kernel(const float *__restrict__ src, int sctot, int scoff, float *__restrict__ dst, int dctot,
                                      int dcoff, int C, int64_t rows, int accumulate) {
     const int64_t total = rows * C;
@@ -1067,6 +1084,15 @@ int launch_dw_bwd(const TcnBwdArgs &a, const float *DY, float *DN, double *ired,
     MISO_LAUNCHED("dw_bwd_kernel");
     in1d_bwd_apply_kernel<<<grid, 128, 0, st>>>(a, DN, ired, out, accumulate);
     MISO_LAUNCHED("in1d_bwd_apply_kernel");
+    return MISO_OK;
+}
+
+int launch_cl_to_planes(const float *src, __nv_bfloat16 *dst, int B, int npix, int C, cudaStream_t st) {
+    MISO_REQUIRE(C % 8 == 0, "cl_to_planes: C=%d must be a multiple of 8", C);
+    const int64_t total = (int64_t)B * npix * (C >> 2);
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
+    cl_to_planes_kernel<<<blocks, 256, 0, st>>>(src, dst, B, npix, C);
+    MISO_LAUNCHED("cl_to_planes_kernel");
     return MISO_OK;
 }
 

@@ -940,7 +940,7 @@ ConvArgs dgrad_tc_args(const ConvArgs &f, const Plan &pl, int B, int T, float *d
     a.pad_t = f.pad_t;
     a.pad_f = f.pad_f;
     *flip = (!f.transposed && f.stride_f == 1 && f.pad_f == 1) ? 1 : 0;
-    a.transposed = *flip ? 0 : (f.transposed ? 0 : 1);
+    a.transposed = (*flip || f.KT == 1) ? 0 : (f.transposed ? 0 : 1);  // a 1x1 conv's gradient is a plain 1x1 conv
     a.norm_mode = NORM_NONE;
     a.norm_eps = kInEps;
     a.norm_inv_n = 1.0;
@@ -948,8 +948,32 @@ ConvArgs dgrad_tc_args(const ConvArgs &f, const Plan &pl, int B, int T, float *d
     a.use_lo = 1;
     return a;
 }
+// forward geometry of a TCN pointwise conv (model.py:560), as far as the gradient kernels need it
+ConvArgs tcn_pw_fwd_args(int C, int B, int T) {
+    ConvArgs f{};
+    f.in_layout = LAYOUT_CL_F32;
+    f.out_layout = LAYOUT_CL_F32;
+    f.use_lo = 1;
+    f.B = B;
+    f.T = T;
+    f.Fin = 1;
+    f.Fout = 1;
+    f.in_ctot = C;
+    f.in_coff = 0;
+    f.cin = C;
+    f.out_ctot = C;
+    f.out_coff = 0;
+    f.cout = C;
+    f.KT = 1;
+    f.KF = 1;
+    f.stride_f = 1;
+    f.pad_t = 0;
+    f.pad_f = 0;
+    f.transposed = 0;
+    return f;
+}
 bool dgrad_tc_ok(const ConvArgs &f, const ConvArgs &d, const Plan &pl, int B, int T) {
-    return f.cout % 8 == 0 && f.KT == 3 && (size_t)B * f.cout * T * f.Fout * 4 <= pl.dyP_bytes && conv_tc_eligible(d);
+    return f.cout % 8 == 0 && (size_t)B * f.cout * T * f.Fout * 4 <= pl.dyP_bytes && conv_tc_eligible(d);
 }
 
 bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, bool train = false) {
@@ -970,6 +994,17 @@ bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
             conv_tc_scratch_need(d, 3, &ww, &bb);
             w.need_w = std::max(w.need_w, ww);
             w.need_b = std::max(w.need_b, bb);
+        }
+        {
+            int flip;
+            ConvArgs f = tcn_pw_fwd_args(n->C, B, T);
+            ConvArgs d = dgrad_tc_args(f, pl, B, T, nullptr, &flip);
+            if (dgrad_tc_ok(f, d, pl, B, T)) {
+                size_t ww, bb;
+                conv_tc_scratch_need(d, 3, &ww, &bb);
+                w.need_w = std::max(w.need_w, ww);
+                w.need_b = std::max(w.need_b, bb);
+            }
         }
     }
     plan_scratch(pl, base, w.need_w, w.need_b);
@@ -1512,27 +1547,8 @@ struct Backward {
         int rc = launch_tcn_recompute(a, pl.tY, pl.tQ, st);
         if (rc) return rc;
         // pointwise conv: weight gradient from q, data gradient into tDQ
-        ConvArgs f{};
+        ConvArgs f = tcn_pw_fwd_args(C, B, T);
         f.in = pl.tQ;
-        f.in_layout = LAYOUT_CL_F32;
-        f.out_layout = LAYOUT_CL_F32;
-        f.use_lo = 1;
-        f.B = B;
-        f.T = T;
-        f.Fin = 1;
-        f.Fout = 1;
-        f.in_ctot = C;
-        f.in_coff = 0;
-        f.cin = C;
-        f.out_ctot = C;
-        f.out_coff = 0;
-        f.cout = C;
-        f.KT = 1;
-        f.KF = 1;
-        f.stride_f = 1;
-        f.pad_t = 0;
-        f.pad_f = 0;
-        f.transposed = 0;
         WgradArgs w{};
         w.x = pl.tQ;
         w.x_layout = LAYOUT_CL_F32;
@@ -1562,7 +1578,12 @@ struct Backward {
         rc = launch_wgrad(w, st);
         if (rc) return rc;
         MISO_CUDA(cudaMemsetAsync(pl.tDQ, 0, (size_t)B * T * C * sizeof(float), st));
-        rc = dgrad(f, n->params[h.pw].d, n->params[h.pw].cout_pad, dout, pl.tDQ);
+        const bool tc = use_tc(f);
+        if (tc) {
+            rc = launch_cl_to_planes(dout, reinterpret_cast<__nv_bfloat16 *>(pl.dyP), B, T, C, st);
+            if (rc) return rc;
+        }
+        rc = dgrad(f, n->params[h.pw].d, n->params[h.pw].cout_pad, dout, pl.tDQ, tc);
         if (rc) return rc;
         rc = launch_gln_bwd(a, pl.tDQ, pl.tY, pl.bred, g(h.gamma), g(h.beta), g(h.alpha), st);
         if (rc) return rc;
