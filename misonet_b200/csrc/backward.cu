@@ -492,16 +492,19 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
 // 32-bin segment of one frame, or R whole frames when the layer has fewer than 32 bins -- needs the input halo tile
 // [(R + 2) frames x (W + 2) bins], and the im2col row of output pixel k for tap (kt, kf) is halo row
 // base_k + kt (W + 2) + kf: the nine A operands are the same staged tile at nine row offsets (ldmatrix takes a row
-// address per lane).  Warps 0-3 / 4-7 own 16 input channels each for taps 0-4 / 5-8; dy is staged once per chunk.
+// address per lane).  Twelve warps: warp w owns input channels 16 (w & 3) .. + 15 for taps 3 (w >> 2) .. + 2; dy is staged
+// once per chunk.
 constexpr int kWtHP = 104;  // halo rows held in shared memory (>= every base_k + 2 (W + 2) + 2, see the launcher)
 constexpr int kWtAff = 80;   // float2 per sample in the affine table: 8 groups of 8 channels at a pitch of 10
-constexpr int kWtSlots = 4;  // halo items (pixel, 8-channel group) per thread: 102 * 8 / 256 rounded up
+constexpr int kWtThreads = 384;  // 12 warps: 4 input-channel groups x 3 tap groups
+constexpr int kWtTaps = 3;       // taps per warp
+constexpr int kWtSlots = 3;      // halo items (pixel, 8-channel group) per thread: 102 * 8 / 384 rounded up
 
 struct WtapsGeom {
     int W, R, nseg, nrc;  // bins per segment, frames per chunk, segments per frame, chunk rows per sample
 };
 
-__global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, const WtapsGeom g, int splits) {
+__global__ void __launch_bounds__(kWtThreads, 1) wgrad_taps_kernel(const WgradArgs a, const WtapsGeom g, int splits) {
     constexpr int BN = 32, BP = BN + 8;
     extern __shared__ __align__(16) unsigned char wsm_raw[];
     __nv_bfloat16 *Ah = reinterpret_cast<__nv_bfloat16 *>(wsm_raw);  // [HP][AP]
@@ -521,11 +524,11 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
     const int per = (total + splits - 1) / splits;
     const int c_lo = blockIdx.y * per, c_hi = min(total, c_lo + per);
 
-    for (int i = tid; i < kWtHP * kWmAP / 2; i += 256) {
+    for (int i = tid; i < kWtHP * kWmAP / 2; i += kWtThreads) {
         reinterpret_cast<uint32_t *>(Ah)[i] = 0u;
         reinterpret_cast<uint32_t *>(Al)[i] = 0u;
     }
-    for (int i = tid; i < a.B * kWgBM; i += 256) {
+    for (int i = tid; i < a.B * kWgBM; i += kWtThreads) {
         const int b = i / kWgBM, cl = i - b * kWgBM, c = ci0 + cl;
         float2 v = make_float2(1.f, 0.f);
         if (a.x_sums && c < a.cin) {
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
     int h_row[kWtSlots], h_col[kWtSlots];
 #pragma unroll
     for (int sl = 0; sl < kWtSlots; ++sl) {
-        const int h = (tid + 256 * sl) >> 3;
+        const int h = (tid + kWtThreads * sl) >> 3;
         h_row[sl] = h < nhalo ? h / W2 : -1;
         h_col[sl] = h - (h / W2) * W2;
     }
@@ -581,13 +584,13 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
         }
         rb = make_float4(0.f, 0.f, 0.f, 0.f);
         const int t = t0 + b_r, f = f0 + b_j, co = co0 + b4 * 4;
-        if (b_r < g.R && t < a.T && f < a.Fout && co < a.cout)
+        if (tid < 256 && b_r < g.R && t < a.T && f < a.Fout && co < a.cout)
             rb = *reinterpret_cast<const float4 *>(a.dy + ((size_t)b * npix + (size_t)t * a.Fout + f) * a.dy_ctot + a.dy_coff + co);
     };
 
-    float acc[5][4][4];
+    float acc[kWtTaps][4][4];
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < kWtTaps; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
     const int wm = warp & 3, wt = warp >> 2;
@@ -620,7 +623,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
 #pragma unroll
             for (int sl = 0; sl < kWtSlots; ++sl) {
                 if (h_row[sl] < 0) continue;
-                const int h = (tid + 256 * sl) >> 3;
+                const int h = (tid + kWtThreads * sl) >> 3;
                 float v[8];
                 const uint4 hh = rh[sl], ll = rl[sl];
                 v[0] = bf16_lo(hh.x) + bf16_lo(ll.x); v[1] = bf16_hi(hh.x) + bf16_hi(ll.x);
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
                 *reinterpret_cast<uint4 *>(Al + h * kWmAP + g8 * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
             }
         }
-        {
+        if (tid < 256) {
             const float v[4] = {rb.x, rb.y, rb.z, rb.w};
             uint2 hi, lo;
             split4(v, hi, lo);
@@ -655,9 +658,9 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
                 ldsm_x4_trans(sBl + b_off + kh * 16 * BP * 2 + n2 * 32, bl[n2][0], bl[n2][1], bl[n2][2], bl[n2][3]);
             }
 #pragma unroll
-            for (int ti = 0; ti < 5; ++ti) {
-                const int tap = wt * 5 + ti;
-                if (tap < 9) {
+            for (int ti = 0; ti < kWtTaps; ++ti) {
+                const int tap = wt * kWtTaps + ti;
+                {
                     const int kt = tap / 3, kf = tap - kt * 3;
                     const uint32_t toff = (uint32_t)((kt * W2 + kf) * kWmAP * 2);
                     uint32_t ah[4], al[4];
@@ -686,9 +689,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_taps_kernel(const WgradArgs a, c
 
     const int gq = lane >> 2, t4 = lane & 3;
 #pragma unroll
-    for (int ti = 0; ti < 5; ++ti) {
-        const int tap = wt * 5 + ti;
-        if (tap >= 9) continue;
+    for (int ti = 0; ti < kWtTaps; ++ti) {
+        const int tap = wt * kWtTaps + ti;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -1018,7 +1020,7 @@ static int launch_wgrad_taps(const WgradArgs &a, cudaStream_t st) {
     g.nrc = ceil_div(a.T, g.R);
     // every im2col row stays inside the zero-initialised halo buffer: base_31 + 2 (W + 2) + 2 < kWtHP
     const int r31 = 31 / g.W, j31 = 31 - r31 * g.W;
-    MISO_REQUIRE((g.R + 2) * (g.W + 2) <= kWtHP && (g.R + 2) * (g.W + 2) <= 256 * kWtSlots / 8 && r31 * (g.W + 2) + j31 + 2 * (g.W + 2) + 2 < kWtHP,
+    MISO_REQUIRE((g.R + 2) * (g.W + 2) <= kWtHP && (g.R + 2) * (g.W + 2) <= kWtThreads * kWtSlots / 8 && r31 * (g.W + 2) + j31 + 2 * (g.W + 2) + 2 < kWtHP,
                  "wgrad_taps: halo geometry out of range (Fout=%d)", a.Fout);
     const int ntile = ceil_div(a.cin, kWgBM) * ceil_div(a.cout, 32);
     const int total = a.B * g.nrc * g.nseg;
@@ -1031,7 +1033,7 @@ static int launch_wgrad_taps(const WgradArgs &a, cudaStream_t st) {
         MISO_CUDA(cudaFuncSetAttribute(wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    wgrad_taps_kernel<<<dim3(ntile, splits), 256, smem, st>>>(a, g, splits);
+    wgrad_taps_kernel<<<dim3(ntile, splits), kWtThreads, smem, st>>>(a, g, splits);
     MISO_LAUNCHED("wgrad_taps_kernel");
     return MISO_OK;
 }
