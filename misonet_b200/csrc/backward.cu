@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int split
 // forward's activation planes do) and stores them [pixel][channel]; ldmatrix.trans turns those K-major rows into the
 // A (cin x pixels) and B (pixels x cout) fragments.  Warps 0-3 own 16 input channels each of the first 16 pixels of
 // a 32-pixel chunk, warps 4-7 the same channels of the second 16 pixels; both halves add into dW with atomics.
-constexpr int kWmBK = 32;
+constexpr int kWtAff = 80;   // float2 per sample in the affine tables: 8 groups of 8 channels at a pitch of 10 (conflict-free 16-byte reads)
 constexpr int kWmAP = kWgBM + 8;  // bf16 row pitch of the A tiles: 144 bytes, ldmatrix rows fall into distinct banks
 
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
@@ -310,16 +310,17 @@ __device__ __forceinline__ void mma_bf16(float *c, const uint32_t *a, uint32_t b
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int BN>
+template <int BN, int SL>
 __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int splits) {
+    constexpr int BK = 32 * SL;         // pixels per chunk: SL independent loads per thread in flight
     constexpr int BP = BN + 8;          // bf16 row pitch of the B tiles
-    constexpr int NB4 = BN / 32;        // float4 of dy per thread and chunk
+    constexpr int NB4 = BN / 32;        // float4 of dy per thread and pixel
     extern __shared__ __align__(16) unsigned char wsm_raw[];
     __nv_bfloat16 *Ah = reinterpret_cast<__nv_bfloat16 *>(wsm_raw);   // [BK][AP]
-    __nv_bfloat16 *Al = Ah + kWmBK * kWmAP;
-    __nv_bfloat16 *Bh = Al + kWmBK * kWmAP;                           // [BK][BP]
-    __nv_bfloat16 *Bl = Bh + kWmBK * BP;
-    float2 *aff = reinterpret_cast<float2 *>(Bl + kWmBK * BP);        // [B][BM]
+    __nv_bfloat16 *Al = Ah + BK * kWmAP;
+    __nv_bfloat16 *Bh = Al + BK * kWmAP;                              // [BK][BP]
+    __nv_bfloat16 *Bl = Bh + BK * BP;
+    float2 *aff = reinterpret_cast<float2 *>(Bl + BK * BP);           // [B][kWtAff] (8-channel groups at a pitch of 10)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ci_tiles = (a.cin + kWgBM - 1) / kWgBM, co_tiles = (a.cout + BN - 1) / BN;
     int tile = blockIdx.x;  // tiles (tap, cin tile, cout tile) of one pixel slice are neighbours in launch order: they share x and dy in L2
@@ -334,90 +335,74 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
     const int p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
 
     for (int i = tid; i < a.B * kWgBM; i += 256) {
-        const int b = i / kWgBM, c = ci0 + (i - b * kWgBM);
+        const int b = i / kWgBM, cl = i - b * kWgBM, c = ci0 + cl;
         float2 v = make_float2(1.f, 0.f);
         if (a.x_sums && c < a.cin) {
             const double *s = a.x_sums + ((size_t)b * a.x_ctot + a.x_coff + c) * 2;
             v = affine_from_sums(stat_get(s), stat_get(s + 1), a.inv_n, (double)a.eps);
         }
-        aff[i] = v;
+        aff[b * kWtAff + (cl >> 3) * 10 + (cl & 7)] = v;
     }
     __syncthreads();
 
-    const int ap = tid >> 3, a8 = tid & 7;        // A loader: pixel ap of the chunk, channels 8 a8 .. 8 a8 + 7 (one 16-byte plane pixel)
-    const int bp = tid >> 3, b4 = tid & 7;        // B loader: pixel bp, channels 4 b4 (+ 32 j)
-    const int nchunk = p1 > p0 ? (p1 - p0 + kWmBK - 1) / kWmBK : 0;
+    const int ap = tid >> 3, a8 = tid & 7;        // loaders: pixels ap + 32 sl of the chunk; A: channels 8 a8 .. + 7 (one 16-byte
+    const int b4 = tid & 7;                       // plane pixel), B: channels 4 b4 (+ 32 j)
+    const int nchunk = p1 > p0 ? (p1 - p0 + BK - 1) / BK : 0;
     const int niter = nchunk * a.B;
     const bool planes = a.x_layout == LAYOUT_PLANES;
     const size_t x_lo = (size_t)a.x_ctot * a.T * a.Fin;
+    const int cg = ci0 + a8 * 8;
 
-    float ra[8];
-    float4 rb[NB4];
-    // (frame, bin) of this thread's pixel, advanced incrementally (a chunk is 32 consecutive pixels of the output grid)
-    const int t_first = (p0 + ap) / a.Fout, f_first = (p0 + ap) - t_first * a.Fout;
-    int lt = t_first, lf = f_first, lb = 0, lchunk = 0;
-    auto load = [&]() {   // loads the next (sample, chunk) in order
-        const int b = lb;
-        const int pc = p0 + lchunk * kWmBK;
-        const int c = ci0 + a8 * 8;
+    // The loader only ISSUES the loads; normalising and splitting happen at store time one iteration later (an arithmetic
+    // use right behind a load would stall the warp for the memory latency before it reaches its MMAs).
+    uint4 rh[SL], rl[SL];
+    float4 rb[SL][NB4];
+    unsigned rvalid = 0;
+    int r_sample = 0;
+    auto load = [&](int it) {
+        const int b = it / nchunk;
+        const int pc = p0 + (it - b * nchunk) * BK;
+        rvalid = 0;
+        r_sample = b;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) ra[q] = 0.f;
-        const int p = pc + ap;
-        if (p < p1 && c < a.cin) {
+        for (int sl = 0; sl < SL; ++sl) {
+            const int p = pc + ap + 32 * sl;
+            rh[sl] = make_uint4(0u, 0u, 0u, 0u);
+            rl[sl] = rh[sl];
+#pragma unroll
+            for (int j = 0; j < NB4; ++j) rb[sl][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p >= p1) continue;
+            const int t = p / a.Fout, f = p - t * a.Fout;
             int ti, fi;
-            bool ok = true;
+            bool ok = cg < a.cin;
             if (!a.transposed) {
-                ti = lt + kt - a.pad_t;
-                fi = lf * a.stride_f + kf - a.pad_f;
+                ti = t + kt - a.pad_t;
+                fi = f * a.stride_f + kf - a.pad_f;
             } else {
-                ti = lt + a.pad_t - kt;
-                const int num = lf + a.pad_f - kf;
+                ti = t + a.pad_t - kt;
+                const int num = f + a.pad_f - kf;
                 fi = num / a.stride_f;
-                ok = num >= 0 && fi * a.stride_f == num;
+                ok = ok && num >= 0 && fi * a.stride_f == num;
             }
             ok = ok && ti >= 0 && ti < a.T && fi >= 0 && fi < a.Fin;
             if (ok) {
-                const int ca = a.x_coff + c;
-                float e[8];
+                const int ca = a.x_coff + cg;
                 if (planes) {
                     const __nv_bfloat16 *xp = reinterpret_cast<const __nv_bfloat16 *>(a.x) + (size_t)b * 2 * x_lo +
                                               (((size_t)(ca >> 3) * a.T + ti) * a.Fin + fi) * 8;
-                    const uint4 h = *reinterpret_cast<const uint4 *>(xp);
-                    e[0] = bf16_lo(h.x); e[1] = bf16_hi(h.x); e[2] = bf16_lo(h.y); e[3] = bf16_hi(h.y);
-                    e[4] = bf16_lo(h.z); e[5] = bf16_hi(h.z); e[6] = bf16_lo(h.w); e[7] = bf16_hi(h.w);
-                    if (a.use_lo) {
-                        const uint4 l = *reinterpret_cast<const uint4 *>(xp + x_lo);
-                        e[0] += bf16_lo(l.x); e[1] += bf16_hi(l.x); e[2] += bf16_lo(l.y); e[3] += bf16_hi(l.y);
-                        e[4] += bf16_lo(l.z); e[5] += bf16_hi(l.z); e[6] += bf16_lo(l.w); e[7] += bf16_hi(l.w);
-                    }
+                    rh[sl] = *reinterpret_cast<const uint4 *>(xp);
+                    if (a.use_lo) rl[sl] = *reinterpret_cast<const uint4 *>(xp + x_lo);
                 } else {
                     const float *xp = reinterpret_cast<const float *>(a.x) + (((size_t)b * a.T + ti) * a.Fin + fi) * a.x_ctot + ca;
-                    const float4 v0 = *reinterpret_cast<const float4 *>(xp), v1 = *reinterpret_cast<const float4 *>(xp + 4);
-                    e[0] = v0.x; e[1] = v0.y; e[2] = v0.z; e[3] = v0.w;
-                    e[4] = v1.x; e[5] = v1.y; e[6] = v1.z; e[7] = v1.w;
+                    rh[sl] = *reinterpret_cast<const uint4 *>(xp);       // fp32 channels 0-3 (raw bits)
+                    rl[sl] = *reinterpret_cast<const uint4 *>(xp + 4);   // fp32 channels 4-7
                 }
-                const float2 *af = aff + b * kWgBM + a8 * 8;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) ra[q] = fmaf(e[q], af[q].x, af[q].y);
+                rvalid |= 1u << sl;
             }
-        }
 #pragma unroll
-        for (int j = 0; j < NB4; ++j) {
-            rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int co = co0 + b4 * 4 + 32 * j;
-            if (p < p1 && co < a.cout) rb[j] = *reinterpret_cast<const float4 *>(a.dy + ((size_t)b * npix + p) * a.dy_ctot + a.dy_coff + co);
-        }
-        // advance to the next chunk (or to the first chunk of the next sample)
-        if (++lchunk == nchunk) {
-            lchunk = 0;
-            ++lb;
-            lt = t_first;
-            lf = f_first;
-        } else {
-            lf += kWmBK;
-            while (lf >= a.Fout) {
-                lf -= a.Fout;
-                ++lt;
+            for (int j = 0; j < NB4; ++j) {
+                const int co = co0 + b4 * 4 + 32 * j;
+                if (co < a.cout) rb[sl][j] = *reinterpret_cast<const float4 *>(a.dy + ((size_t)b * npix + p) * a.dy_ctot + a.dy_coff + co);
             }
         }
     };
@@ -428,46 +413,85 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     const int wm = warp & 3, wk = warp >> 2;
     // ldmatrix lane addresses (see the fragment layouts of mma.m16n8k16): A matrices (m 0-7 | m 8-15) x (k 0-7 | k 8-15),
-    // B matrices (k 0-7 | k 8-15) x (n 0-7 | n 8-15)
+    // B matrices (k 0-7 | k 8-15) x (n 0-7 | n 8-15); warps 0-3 take the even 16-pixel steps of a chunk, warps 4-7 the odd ones
     const int lr = lane & 7, lm = lane >> 3;
     const uint32_t a_off = (uint32_t)(((wk * 16 + (lm >> 1) * 8 + lr) * kWmAP + wm * 16 + (lm & 1) * 8) * 2);
     const uint32_t b_off = (uint32_t)(((wk * 16 + (lm & 1) * 8 + lr) * BP + (lm >> 1) * 8) * 2);
     const uint32_t sAh = (uint32_t)__cvta_generic_to_shared(Ah), sAl = (uint32_t)__cvta_generic_to_shared(Al);
     const uint32_t sBh = (uint32_t)__cvta_generic_to_shared(Bh), sBl = (uint32_t)__cvta_generic_to_shared(Bl);
 
-    if (niter > 0) load();
+    if (niter > 0) load(0);
     for (int it = 0; it < niter; ++it) {
         {
-            uint2 h0, l0, h1, l1;
-            split4(ra, h0, l0);
-            split4(ra + 4, h1, l1);
-            *reinterpret_cast<uint4 *>(Ah + ap * kWmAP + a8 * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-            *reinterpret_cast<uint4 *>(Al + ap * kWmAP + a8 * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-        }
+            float2 af[8];
+            const float4 *ap4 = reinterpret_cast<const float4 *>(aff + r_sample * kWtAff + a8 * 10);
 #pragma unroll
-        for (int j = 0; j < NB4; ++j) {
-            const float v[4] = {rb[j].x, rb[j].y, rb[j].z, rb[j].w};
-            uint2 hi, lo;
-            split4(v, hi, lo);
-            *reinterpret_cast<uint2 *>(Bh + bp * BP + b4 * 4 + 32 * j) = hi;
-            *reinterpret_cast<uint2 *>(Bl + bp * BP + b4 * 4 + 32 * j) = lo;
+            for (int q = 0; q < 4; ++q) {
+                const float4 v4 = ap4[q];
+                af[2 * q] = make_float2(v4.x, v4.y);
+                af[2 * q + 1] = make_float2(v4.z, v4.w);
+            }
+#pragma unroll
+            for (int sl = 0; sl < SL; ++sl) {
+                float v[8];
+                const uint4 hh = rh[sl], ll = rl[sl];
+                if (planes) {
+                    v[0] = bf16_lo(hh.x) + bf16_lo(ll.x); v[1] = bf16_hi(hh.x) + bf16_hi(ll.x);
+                    v[2] = bf16_lo(hh.y) + bf16_lo(ll.y); v[3] = bf16_hi(hh.y) + bf16_hi(ll.y);
+                    v[4] = bf16_lo(hh.z) + bf16_lo(ll.z); v[5] = bf16_hi(hh.z) + bf16_hi(ll.z);
+                    v[6] = bf16_lo(hh.w) + bf16_lo(ll.w); v[7] = bf16_hi(hh.w) + bf16_hi(ll.w);
+                } else {
+                    v[0] = __uint_as_float(hh.x); v[1] = __uint_as_float(hh.y); v[2] = __uint_as_float(hh.z); v[3] = __uint_as_float(hh.w);
+                    v[4] = __uint_as_float(ll.x); v[5] = __uint_as_float(ll.y); v[6] = __uint_as_float(ll.z); v[7] = __uint_as_float(ll.w);
+                }
+                const bool ok = (rvalid >> sl) & 1u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = ok ? fmaf(v[q], af[q].x, af[q].y) : 0.f;
+                uint2 h0, l0, h1, l1;
+                split4(v, h0, l0);
+                split4(v + 4, h1, l1);
+                const int row = ap + 32 * sl;
+                *reinterpret_cast<uint4 *>(Ah + row * kWmAP + a8 * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<uint4 *>(Al + row * kWmAP + a8 * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+#pragma unroll
+                for (int j = 0; j < NB4; ++j) {
+                    const float w[4] = {rb[sl][j].x, rb[sl][j].y, rb[sl][j].z, rb[sl][j].w};
+                    uint2 hi, lo;
+                    split4(w, hi, lo);
+                    *reinterpret_cast<uint2 *>(Bh + row * BP + b4 * 4 + 32 * j) = hi;
+                    *reinterpret_cast<uint2 *>(Bl + row * BP + b4 * 4 + 32 * j) = lo;
+                }
+            }
         }
         __syncthreads();
-        if (it + 1 < niter) load();
-        uint32_t ah[4], al[4];
-        ldsm_x4_trans(sAh + a_off, ah[0], ah[1], ah[2], ah[3]);
-        ldsm_x4_trans(sAl + a_off, al[0], al[1], al[2], al[3]);
+        if (it + 1 < niter) load(it + 1);
 #pragma unroll
-        for (int n2 = 0; n2 < NT / 2; ++n2) {
-            uint32_t bh[4], bl[4];
-            ldsm_x4_trans(sBh + b_off + n2 * 32, bh[0], bh[1], bh[2], bh[3]);
-            ldsm_x4_trans(sBl + b_off + n2 * 32, bl[0], bl[1], bl[2], bl[3]);
-            mma_bf16(acc[2 * n2], ah, bh[0], bh[1]);
-            mma_bf16(acc[2 * n2], ah, bl[0], bl[1]);
-            mma_bf16(acc[2 * n2], al, bh[0], bh[1]);
-            mma_bf16(acc[2 * n2 + 1], ah, bh[2], bh[3]);
-            mma_bf16(acc[2 * n2 + 1], ah, bl[2], bl[3]);
-            mma_bf16(acc[2 * n2 + 1], al, bh[2], bh[3]);
+        for (int s2 = 0; s2 < SL; ++s2) {
+            const uint32_t ka = (uint32_t)(s2 * 32 * kWmAP * 2), kb = (uint32_t)(s2 * 32 * BP * 2);
+            uint32_t ah[4], al[4];
+            ldsm_x4_trans(sAh + a_off + ka, ah[0], ah[1], ah[2], ah[3]);
+            ldsm_x4_trans(sAl + a_off + ka, al[0], al[1], al[2], al[3]);
+            uint32_t bh[NT / 2][4], bl[NT / 2][4];
+#pragma unroll
+            for (int n2 = 0; n2 < NT / 2; ++n2) {
+                ldsm_x4_trans(sBh + b_off + kb + n2 * 32, bh[n2][0], bh[n2][1], bh[n2][2], bh[n2][3]);
+                ldsm_x4_trans(sBl + b_off + kb + n2 * 32, bl[n2][0], bl[n2][1], bl[n2][2], bl[n2][3]);
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < NT / 2; ++n2) {  // independent accumulators between dependent MMAs
+                mma_bf16(acc[2 * n2], ah, bh[n2][0], bh[n2][1]);
+                mma_bf16(acc[2 * n2 + 1], ah, bh[n2][2], bh[n2][3]);
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < NT / 2; ++n2) {
+                mma_bf16(acc[2 * n2], ah, bl[n2][0], bl[n2][1]);
+                mma_bf16(acc[2 * n2 + 1], ah, bl[n2][2], bl[n2][3]);
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < NT / 2; ++n2) {
+                mma_bf16(acc[2 * n2], al, bh[n2][0], bh[n2][1]);
+                mma_bf16(acc[2 * n2 + 1], al, bh[n2][2], bh[n2][3]);
+            }
         }
         __syncthreads();
     }
@@ -495,7 +519,6 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(const WgradArgs a, int s
 // address per lane).  Twelve warps: warp w owns input channels 16 (w & 3) .. + 15 for taps 3 (w >> 2) .. + 2; dy is staged
 // once per chunk.
 constexpr int kWtHP = 104;  // halo rows held in shared memory (>= every base_k + 2 (W + 2) + 2, see the launcher)
-constexpr int kWtAff = 80;   // float2 per sample in the affine table: 8 groups of 8 channels at a pitch of 10
 constexpr int kWtThreads = 384;  // 12 warps: 4 input-channel groups x 3 tap groups
 constexpr int kWtTaps = 3;       // taps per warp
 constexpr int kWtSlots = 3;      // halo items (pixel, 8-channel group) per thread: 102 * 8 / 384 rounded up
@@ -987,22 +1010,22 @@ static int launch_wgrad_t(const WgradArgs &a, cudaStream_t st) {
     return MISO_OK;
 }
 
-template <int BN>
+template <int BN, int SL>
 static int launch_wgrad_mma(const WgradArgs &a, cudaStream_t st) {
+    constexpr int BK = 32 * SL;
     const int taps = a.KT * a.KF;
     const int ntile = taps * ceil_div(a.cin, kWgBM) * ceil_div(a.cout, BN);
     const int npix = a.T * a.Fout;
     int splits = ceil_div(4 * 148, ntile);
-    splits = std::max(1, std::min(splits, ceil_div(npix, 4 * kWmBK)));
-    const size_t smem = (size_t)(2 * kWmBK * kWmAP + 2 * kWmBK * (BN + 8)) * 2 + (size_t)a.B * kWgBM * sizeof(float2);
+    splits = std::max(1, std::min(splits, ceil_div(npix, 2 * BK)));
+    const size_t smem = (size_t)(2 * BK * kWmAP + 2 * BK * (BN + 8)) * 2 + (size_t)a.B * kWtAff * sizeof(float2);
     MISO_REQUIRE(smem <= 200 * 1024, "wgrad: batch %d too large for the per-sample affine table", a.B);
-    static size_t attr_set[2] = {0, 0};
-    size_t &cur = attr_set[BN == 64 ? 1 : 0];
+    static size_t cur = 0;
     if (smem > 48 * 1024 && smem > cur) {
-        MISO_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MISO_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<BN, SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    wgrad_mma_kernel<BN><<<dim3(ntile, splits), 256, smem, st>>>(a, splits);
+    wgrad_mma_kernel<BN, SL><<<dim3(ntile, splits), 256, smem, st>>>(a, splits);
     MISO_LAUNCHED("wgrad_mma_kernel");
     return MISO_OK;
 }
@@ -1049,7 +1072,7 @@ int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
     if (fma) return a.cout <= 32 ? launch_wgrad_t<2>(a, st) : launch_wgrad_t<4>(a, st);
     static const bool no_taps = getenv("MISO_WGRAD_TAPS") && atoi(getenv("MISO_WGRAD_TAPS")) == 0;  // debugging: per-tap kernel only
     if (!no_taps && wgrad_taps_ok(a)) return launch_wgrad_taps(a, st);
-    return a.cout <= 32 ? launch_wgrad_mma<32>(a, st) : launch_wgrad_mma<64>(a, st);
+    return a.cout <= 32 ? launch_wgrad_mma<32, 4>(a, st) : launch_wgrad_mma<64, 2>(a, st);
 }
 
 int launch_dgrad_pack(const float *src, float *dst, int taps, int cin, int cout, int cout_pad, int cin_pad, int flip, cudaStream_t st) {
