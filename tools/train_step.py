@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--conv-mode", default="bf16x3")
+    ap.add_argument("--cpu-baseline", action="store_true",
+                    help="also time the reference algorithm's training step (oracle network + torch autograd, fp32, all host "
+                         "cores) on ONE utterance of the same shape")
     args = ap.parse_args()
     rank, world, local = distributed.init_from_env()
     dev = torch.device("cuda", local)
@@ -66,7 +69,41 @@ def main():
             total_ms += ev[0].elapsed_time(ev[4])
     distributed.barrier()
     ms = distributed.max_over_ranks(total_ms / args.steps, device=dev)
+    # algorithmic work of a training step: forward + data gradient + weight gradient = 3 x the forward's 2*MAC
+    # (75.151 / 163.37 GFLOP per utterance at 501 / 500 frames)
+    gflop_fwd = {"REF": 75.151 / 501, "PAPER": 163.37 / 500}[args.layout] * T
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    cpu = None
+    if args.cpu_baseline and rank == 0:
+        import time
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle import miso_net_torch as mnt      # the CPU leg is the checker's arithmetic, timed (bench.py's cpu_baseline rule)
+        cfg = mnt.NetConfig.miso1(layout=args.layout)
+        sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        x = torch.cat((mix[:1].real, mix[:1].imag), dim=1).cpu()
+        r0 = torch.stack([r[:1].cpu() for r in refs], dim=1)
+        torch.set_num_threads(os.cpu_count())
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            y = mnt.net_forward(sd, cfg, x)
+            est = torch.complex(y[:, :2], y[:, 2:])
+            e, r = est.unsqueeze(2), r0.unsqueeze(1)
+            pair = ((e.real - r.real).abs().sum((3, 4)) + (e.imag - r.imag).abs().sum((3, 4)) +
+                    (torch.sqrt(e.real ** 2 + e.imag ** 2 + 1e-8) - r.abs()).abs().sum((3, 4)))
+            per = torch.stack([pair[:, 0, 0] + pair[:, 1, 1], pair[:, 0, 1] + pair[:, 1, 0]], dim=1)
+            per.min(dim=1).values.mean().backward()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        cpu = {"value": T / best, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "1 utterance of the same shape: oracle network forward + loss_uPIT + torch autograd backward, fp32, "
+                         "best of 2", "seconds_best": best}
     if rank == 0:
+        tfl = 3.0 * gflop_fwd * 1e9 * B / (ms * 1e-3) / 1e12
         print(json.dumps({
             "metric": "frames/sec MISO1 training step (fwd + loss_uPIT + bwd + grad all-reduce + Adam)", "value": world * B * T / (ms * 1e-3),
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -74,7 +111,11 @@ def main():
                        "layout": args.layout, "conv_mode": args.conv_mode, "global_batch": world * B},
             "phases_ms_rank0": {"forward+loss": phases[0] / args.steps, "backward": phases[1] / args.steps,
                                 "grad_allreduce": phases[2] / args.steps, "clip+adam": phases[3] / args.steps},
-            "loss": float(loss), "train_workspace_gb": model._ws_train.numel() / 2 ** 30,
+            "roofline": {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s per GPU, algorithmic (3 x forward 2*MAC) / step time",
+                         "peak": peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"), "note": "whole step, not one kernel: "
+                         "the backward GEMMs run bf16 hi/lo split (3 MMAs per product) on mma.sync and the tcgen05 conv kernel"},
+            "cpu_baseline": cpu,
+            "loss": float(loss.detach()), "train_workspace_gb": model._ws_train.numel() / 2 ** 30,
             "data": "synthetic (seeded random spectrograms, default PyTorch initialisation)"}))
 
 
