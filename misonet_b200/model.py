@@ -120,10 +120,20 @@ class _NetFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             gy = torch.empty(B, T, F, (2 * S + 3) // 4 * 4, dtype=torch.float32, device=dev)
             _lib.check(lib.miso_grad_pack(_lib.ptr(g), _lib.ptr(gy), B, S, T, F, st), "miso_grad_pack")
-            flat = torch.empty(lib.miso_net_grad_numel(m._handle), dtype=torch.float32, device=dev)
+            numel = lib.miso_net_grad_numel(m._handle)
+            flat = torch.empty(numel + 1, dtype=torch.float32, device=dev)     # + 1: the utterance count rides along
             ws = m._ws_train
             _lib.check(lib.miso_net_backward(m._handle, _lib.ptr(ctx.x_cl), _lib.ptr(gy), B, T, F, _lib.ptr(ws), ws.numel(),
                                              _lib.ptr(flat), st), "miso_net_backward")
+            if m.data_parallel:
+                # the flat buffer IS the gradient bucket: one in-place all-reduce, weighted by this rank's utterance count
+                # (each rank's loss is a mean over its own utterances), no packing copies
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    flat[numel] = 1.0
+                    flat.mul_(float(B))
+                    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                    flat.div_(flat[numel:].clone())
         grads, off = [], 0
         for shp in ctx.param_shapes:
             n = int(torch.Size(shp).numel())
@@ -188,6 +198,7 @@ class _MisoNet(nn.Module):
         self._ws = None
         self._ws_train = None     # training workspace: activations + statistics + gradient buffers of ONE forward
         self._train_token = 0
+        self.data_parallel = False   # True: backward() all-reduces the parameter gradients across the ranks (training.py)
         self._bufs = {}           # persistent input-plane / output buffers: stable pointers keep the CUDA graph valid
         self._sync_tag = None
         self.use_graph = True     # replay the forward as a CUDA graph (include/misonet_b200.h, miso_net_set_graph)

@@ -8,6 +8,18 @@ import torch
 from . import criterion, distributed
 
 
+def _backward(model, loss, n_local):
+    """loss.backward() plus the data-parallel gradient reduction.  The library's modules reduce their flat gradient
+    buffer in place inside backward (``data_parallel``, model._NetFunction); any other module gets the generic bucketed
+    all-reduce."""
+    if hasattr(model, "data_parallel"):
+        model.data_parallel = True
+        loss.backward()
+    else:
+        loss.backward()
+        distributed.allreduce_gradients(model.parameters(), n_local=n_local)
+
+
 def train_step(model, optimizer, mix_stft, ref_stft, ref_ch=0, max_norm=None, training=True):
     """mix_stft: complex [B, Mic, T, F] (CUDA); ref_stft: list[num_spks] of complex [B, Mic, T, F] or [B, T, F]
     (the clean source images; trainer.py:160-166 takes microphone ``ref_ch``).  Returns the loss (float32 CUDA scalar,
@@ -23,8 +35,7 @@ def train_step(model, optimizer, mix_stft, ref_stft, ref_ch=0, max_norm=None, tr
     if estimate.shape[1] != num_spks:
         raise ValueError("[ERROR] please check the number of speakers")          # trainer.py:169
     loss = criterion.loss_uPIT(num_spks, estimate, refs)                         # trainer.py:172
-    loss.backward()                                                              # trainer.py:207
-    distributed.allreduce_gradients(model.parameters(), n_local=mix.shape[0])
+    _backward(model, loss, mix.shape[0])                                         # trainer.py:207
     if max_norm:
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)             # trainer.py:209-211
     optimizer.step()                                                             # trainer.py:212
@@ -51,8 +62,7 @@ def train_step_enhance(model, optimizer, mix_stft, beamform_stft, miso1_stft, re
         estimate = model(mix_stft, beamform_stft[s], miso1_stft[s])              # trainer.py:400,416
         loss = criterion.loss_Enhance(estimate, ref_stft[s])                     # trainer.py:402,418
         optimizer.zero_grad(set_to_none=True)
-        loss.backward()
-        distributed.allreduce_gradients(model.parameters(), n_local=mix_stft.shape[0])
+        _backward(model, loss, mix_stft.shape[0])
         if max_norm:
             torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
         optimizer.step()
