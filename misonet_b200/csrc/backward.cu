@@ -953,6 +953,27 @@ __global__ void cl_to_planes_kernel(const float *__restrict__ src, __nv_bfloat16
     }
 }
 
+__global__ void planes_accumulate_kernel(const __nv_bfloat16 *__restrict__ src, int sctot, float *__restrict__ dst, int dctot,
+                                         int dcoff, int C, int B, int npix) {
+    const int nc4 = C >> 2;
+    const int64_t total = (int64_t)B * npix * nc4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % nc4);
+        const int64_t r = i / nc4;
+        const int p = (int)(r % npix), b = (int)(r / npix);
+        const int c = c4 * 4;
+        float e[4];
+        load_e4(src + (size_t)b * 2 * sctot * npix + ((size_t)(c >> 3) * npix + p) * 8 + (c & 7), (size_t)sctot * npix, 1, e);
+        float4 *d = reinterpret_cast<float4 *>(dst + r * dctot + dcoff + c);
+        float4 v = *d;
+        v.x += e[0];
+        v.y += e[1];
+        v.z += e[2];
+        v.w += e[3];
+        *d = v;
+    }
+}
+
 __global__ void copy_channels_kernel(const float *__restrict__ src, int sctot, int scoff, float *__restrict__ dst, int dctot,
                                      int dcoff, int C, int64_t rows, int accumulate) {
     const int64_t total = rows * C;
@@ -1118,6 +1139,16 @@ int launch_cl_to_planes(const float *src, __nv_bfloat16 *dst, int B, int npix, i
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 4096);
     cl_to_planes_kernel<<<blocks, 256, 0, st>>>(src, dst, B, npix, C);
     MISO_LAUNCHED("cl_to_planes_kernel");
+    return MISO_OK;
+}
+
+int launch_planes_accumulate(const __nv_bfloat16 *src, int sctot, float *dst, int dctot, int dcoff, int C, int B, int npix,
+                             cudaStream_t st) {
+    MISO_REQUIRE(C % 4 == 0 && sctot % 8 == 0 && dctot % 4 == 0 && dcoff % 4 == 0, "planes_accumulate: bad channel layout");
+    const int64_t total = (int64_t)B * npix * (C >> 2);
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+    planes_accumulate_kernel<<<blocks, 256, 0, st>>>(src, sctot, dst, dctot, dcoff, C, B, npix);
+    MISO_LAUNCHED("planes_accumulate_kernel");
     return MISO_OK;
 }
 

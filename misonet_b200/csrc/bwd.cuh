@@ -67,6 +67,9 @@ int launch_dw_bwd(const TcnBwdArgs &a, const float *DY, float *DN, double *ired,
                   cudaStream_t st);
 // fp32 channels-last [B][npix][C] -> bf16 hi/lo planes [B][hi|lo][C/8][npix][8] (C % 8 == 0)
 int launch_cl_to_planes(const float *src, __nv_bfloat16 *dst, int B, int npix, int C, cudaStream_t st);
+// dst[b][p][dcoff + c] += (hi + lo)[b][c][p] for bf16 hi/lo planes src [B][hi|lo][sctot/8][npix][8], c < C (C % 4 == 0)
+int launch_planes_accumulate(const __nv_bfloat16 *src, int sctot, float *dst, int dctot, int dcoff, int C, int B, int npix,
+                             cudaStream_t st);
 // dst[b][p][dcoff + c] (+)= src[b][p][scoff + c]
 int launch_copy_channels(const float *src, int sctot, int scoff, float *dst, int dctot, int dcoff, int C, int64_t rows,
                          int accumulate, cudaStream_t st);

@@ -450,6 +450,8 @@ struct Plan {
     float *wT = nullptr;     // data-gradient (transposed) weights of the layer being processed
     char *dyP = nullptr;     // dL/dy of the layer being processed as bf16 hi/lo planes (tensor-core data gradient)
     size_t dyP_bytes = 0;
+    char *dgP = nullptr;     // data gradient of a DenseBlock conv as planes (row-streaming kernel), added into the fp32 buffer
+    size_t dgP_bytes = 0;
     void *tcn_wimg = nullptr;  // tensor-core pointwise convs: weight images and W beta / W gamma vectors (tcn.cu)
     float *tcn_wvec = nullptr;
     std::vector<double *> sS, sU, g1, g2;
@@ -572,6 +574,14 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
             for (int j = 0; j + 1 < nb; ++j) maxo = std::max(maxo, (size_t)n->de[j + 1] * pl.D[j + 1].F);
             pl.dyP_bytes = (size_t)B * maxo * T * 4;
             pl.dyP = take(pl.dyP_bytes);
+            // largest DenseBlock conv input (channels x bins): the fourth / fifth conv of a block reads 4 of its 5 (6) groups
+            size_t maxi = 0;
+            for (int i = 0; i < nb; ++i)
+                if (dense_enc(i)) maxi = std::max(maxi, (size_t)pl.E[i].ctot * pl.E[i].F);
+            for (int j = 0; j < nb; ++j)
+                if (dense_dec(j)) maxi = std::max(maxi, (size_t)pl.D[j].ctot * pl.D[j].F);
+            pl.dgP_bytes = (size_t)B * maxi * T * 4;
+            pl.dgP = take(pl.dgP_bytes);
         }
     }
     if (tcn_pw_eligible(n->C)) {
@@ -976,6 +986,31 @@ bool dgrad_tc_ok(const ConvArgs &f, const ConvArgs &d, const Plan &pl, int B, in
     return f.cout % 8 == 0 && (size_t)B * f.cout * T * f.Fout * 4 <= pl.dyP_bytes && conv_tc_eligible(d);
 }
 
+// DenseBlock convs (stride 1, pad (1,1)): the tap-reversed gradient conv is exactly the forward's row-streaming
+// configuration if it writes planes, so it runs on conv_rs in chunks of <= 64 output channels into pl.dgP (the kernel's
+// N limit; the small dL/dy is re-read per chunk) and planes_accumulate_kernel adds the result into the fp32 gradient.
+constexpr int kRsChunk = 64;
+ConvArgs dgrad_rs_chunk(const ConvArgs &d, const Plan &pl, int T, int c0) {
+    ConvArgs a = d;
+    const int ctot8 = (d.cout + 7) & ~7;
+    a.out = pl.dgP;
+    a.out_layout = LAYOUT_PLANES;
+    a.out_ctot = ctot8;
+    a.out_coff = c0;
+    a.out_lo_off = (size_t)ctot8 * T * d.Fout * 2;
+    a.cout = std::min(kRsChunk, d.cout - c0);
+    a.w = d.w ? d.w + c0 : nullptr;
+    a.resid = nullptr;
+    return a;
+}
+bool dgrad_rs_ok(const ConvArgs &d, int flip, const Plan &pl, int B, int T) {
+    if (!flip || d.cout % 8) return false;
+    if ((size_t)B * ((d.cout + 7) & ~7) * T * d.Fout * 4 > pl.dgP_bytes) return false;
+    for (int c0 = 0; c0 < d.cout; c0 += kRsChunk)
+        if (!conv_rs_eligible(dgrad_rs_chunk(d, pl, T, c0), 3)) return false;
+    return true;
+}
+
 bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, bool train = false) {
     if (!make_plan(n, B, T, F, base, pl, train)) return false;
     Walker w{n, pl, B, T, F, nullptr, true};
@@ -994,6 +1029,12 @@ bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
             conv_tc_scratch_need(d, 3, &ww, &bb);
             w.need_w = std::max(w.need_w, ww);
             w.need_b = std::max(w.need_b, bb);
+            if (dgrad_rs_ok(d, flip, pl, B, T))
+                for (int c0 = 0; c0 < d.cout; c0 += kRsChunk) {
+                    conv_tc_scratch_need(dgrad_rs_chunk(d, pl, T, c0), 3, &ww, &bb);
+                    w.need_w = std::max(w.need_w, ww);
+                    w.need_b = std::max(w.need_b, bb);
+                }
         }
         {
             int flip;
@@ -1417,6 +1458,15 @@ struct Backward {
             ConvArgs d = dgrad_tc_args(f, pl, B, T, din, &flip);
             int rc = launch_dgrad_pack(w_packed, pl.wT, f.KT * f.KF, f.cin, f.cout, cout_pad_fwd, cin_pad, flip, st);
             if (rc) return rc;
+            static const bool no_rs = getenv("MISO_DGRAD_RS") && atoi(getenv("MISO_DGRAD_RS")) == 0;  // debugging: general kernel only
+            if (!no_rs && dgrad_rs_ok(d, flip, pl, B, T)) {
+                for (int c0 = 0; c0 < d.cout; c0 += kRsChunk) {
+                    rc = launch_conv_tc(dgrad_rs_chunk(d, pl, T, c0), 3, pl.scratch, st);
+                    if (rc) return rc;
+                }
+                return launch_planes_accumulate(reinterpret_cast<const __nv_bfloat16 *>(pl.dgP), (d.cout + 7) & ~7, din, d.out_ctot,
+                                                d.out_coff, d.cout, B, T * d.Fout, st);
+            }
             return launch_conv_tc(d, 3, pl.scratch, st);
         }
         int rc = launch_dgrad_pack(w_packed, pl.wT, f.KT * f.KF, f.cin, f.cout, cout_pad_fwd, cin_pad, 0, st);
