@@ -143,6 +143,10 @@ int miso_debug_tc_trace(long long *d_buf, int cin, int fin);
 int64_t miso_net_tap(miso_net_t *net, const char *name, float *d_out, int64_t capacity, int B, int T, int F,
                      void *d_ws, void *stream);
 
+/* Output sample format of the reference's wav writer (tester.py:155-157, 444-446, 950-952): (int16) trunc(x * scale)
+ * with the product in double, scale = 32767 (np.iinfo(np.int16).max), saturated. */
+int miso_wave_to_int16(const float *d_x, int16_t *d_out, int64_t n, float scale, void *stream);
+
 /* ---- training (reference trainer.py:159-212: estimate = model(mix); loss = loss_uPIT(...); loss.backward()) ----
  * miso_net_forward_train is miso_net_forward on the TRAINING workspace plan: every TemporalBlock keeps its input and
  * mid state (the inference plan updates the residual stream in place), no CUDA graph.  miso_net_backward then consumes

@@ -29,6 +29,7 @@ SIGNATURES = {
     "miso_istft_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "miso_istft_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                                c_void_p]),
+    "miso_wave_to_int16": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "miso_net_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, c_int]),
     "miso_net_destroy": (c_int, [c_void_p]),
     "miso_net_num_params": (c_int, [c_void_p]),

@@ -70,3 +70,87 @@ def istft(spec, nperseg=256, noverlap=192):
         _lib.check(lib.miso_istft_fwd(_lib.ptr(x), T * F, F, 1, _lib.ptr(out), S, T, nperseg, hop, _lib.ptr(ws), ws.numel(),
                                       _lib.stream_ptr()), "miso_istft_fwd")
     return out.reshape(*lead, n_out)
+
+
+MAX_INT16 = 32767     # np.iinfo(np.int16).max (tester.py:36,280)
+
+
+def to_int16(wave):
+    """float CUDA waveform -> int16, the reference's output sample format (``wave * MaxINT16`` then ``astype(np.int16)``,
+    tester.py:155-157, 444-446, 950-952)."""
+    _lib.require_cuda(wave, "wave")
+    _lib.check_device(wave.device)
+    x = wave.to(torch.float32).contiguous()
+    out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().miso_wave_to_int16(_lib.ptr(x), _lib.ptr(out), x.numel(), float(MAX_INT16), _lib.stream_ptr()),
+                   "miso_wave_to_int16")
+    return out
+
+
+def write_wav(path, pcm, fs, subtype="PCM_24"):
+    """Write int16 samples [N] or [N, channels] (a CPU tensor / array; the reference passes ``x.T``) as a RIFF/WAVE file
+    the way ``sf.write(path, int16_data, fs, 'PCM_24')`` does (tester.py:447, 971-972): libsndfile widens int16 to 24 bits
+    by a left shift of 8.  ``subtype="PCM_16"`` writes the samples as they are.  File I/O only -- no arithmetic."""
+    import struct
+    import numpy as np
+    a = np.asarray(pcm.cpu() if hasattr(pcm, "cpu") else pcm)
+    if a.dtype != np.int16:
+        raise TypeError("write_wav expects int16 samples (audio.to_int16)")
+    if a.ndim == 1:
+        a = a[:, None]
+    n, ch = a.shape
+    if subtype == "PCM_24":
+        width = 3
+        v = a.astype(np.int32) << 8
+        raw = np.empty((n, ch, 3), dtype=np.uint8)
+        raw[..., 0] = v & 0xFF
+        raw[..., 1] = (v >> 8) & 0xFF
+        raw[..., 2] = (v >> 16) & 0xFF
+        data = raw.tobytes()
+    elif subtype == "PCM_16":
+        width = 2
+        data = a.astype("<i2").tobytes()
+    else:
+        raise ValueError("subtype must be PCM_24 or PCM_16")
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE")
+        f.write(b"fmt " + struct.pack("<IHHIIHH", 16, 1, ch, int(fs), int(fs) * ch * width, ch * width, 8 * width))
+        f.write(b"data" + struct.pack("<I", len(data)))
+        f.write(data)
+
+
+def read_wav(path):
+    """Read a PCM (16 / 24 / 32 bit) or float32 RIFF/WAVE file as ``sf.read`` does (data.py:516, tester.py: the samples as
+    floats in [-1, 1), [N, channels]); returns (float32 numpy array, fs)."""
+    import struct
+    import numpy as np
+    raw = open(path, "rb").read()
+    if raw[:4] != b"RIFF" or raw[8:12] != b"WAVE":
+        raise ValueError(f"{path}: not a RIFF/WAVE file")
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= len(raw):
+        cid, size = raw[pos:pos + 4], struct.unpack("<I", raw[pos + 4:pos + 8])[0]
+        body = raw[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", body[:16])
+        elif cid == b"data":
+            data = body
+        pos += 8 + size + (size & 1)
+    if fmt is None or data is None:
+        raise ValueError(f"{path}: missing fmt / data chunk")
+    tag, ch, fs, _, _, bits = fmt
+    if tag == 3 and bits == 32:
+        x = np.frombuffer(data, dtype="<f4").astype(np.float32)
+    elif tag in (1, 0xFFFE) and bits == 16:
+        x = np.frombuffer(data, dtype="<i2").astype(np.float32) / 32768.0
+    elif tag in (1, 0xFFFE) and bits == 24:
+        b = np.frombuffer(data, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        v = np.where(v >= 1 << 23, v - (1 << 24), v)
+        x = v.astype(np.float32) / float(1 << 23)
+    elif tag in (1, 0xFFFE) and bits == 32:
+        x = np.frombuffer(data, dtype="<i4").astype(np.float32) / float(1 << 31)
+    else:
+        raise ValueError(f"{path}: unsupported wav format tag {tag}, {bits} bits")
+    return x.reshape(-1, ch), fs

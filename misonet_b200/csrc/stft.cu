@@ -145,6 +145,16 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float *__restrict_
 
 using namespace miso;
 
+// Output sample format of the reference's wav writer (tester.py:155-157, 444-446, 950-952): wave * MaxINT16 in double,
+// then numpy's astype(np.int16) = truncation toward zero (saturated here; numpy's overflow is undefined).
+__global__ void wave_to_int16_kernel(const float *__restrict__ x, int16_t *__restrict__ out, int64_t n, double scale) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = trunc((double)x[i] * scale);
+        v = fmin(fmax(v, -32768.0), 32767.0);
+        out[i] = (int16_t)v;
+    }
+}
+
 extern "C" {
 
 int miso_stft_num_frames(int n_samples, int nperseg, int hop) {
@@ -209,6 +219,15 @@ int miso_istft_fwd(const void *d_spec, int64_t ss, int64_t st, int64_t sf, float
         if (n_out > 0) istft_ola_kernel<512><<<oblocks, 256, 0, stq>>>(frames, d_out, S, T, hop, n_out);
     }
     MISO_LAUNCHED("istft_ola_kernel");
+    return MISO_OK;
+}
+
+int miso_wave_to_int16(const float *d_x, int16_t *d_out, int64_t n, float scale, void *stream) {
+    MISO_REQUIRE(d_x && d_out && n >= 0, "miso_wave_to_int16: bad argument");
+    if (n == 0) return MISO_OK;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    wave_to_int16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d_x, d_out, n, (double)scale);
+    MISO_LAUNCHED("wave_to_int16_kernel");
     return MISO_OK;
 }
 

@@ -78,6 +78,17 @@ def test_istft_golden_and_round_trip():
     assert rel_err(back.permute(0, 2, 1).cpu().numpy(), x.cpu().numpy()) < 2e-6
 
 
+def test_wave_to_int16_matches_numpy_astype():
+    """tester.py:155-157: wave * MaxINT16 then astype(np.int16) (truncation toward zero) -- bit-exact."""
+    from misonet_b200 import audio
+    rng = np.random.default_rng(4)
+    x = np.clip(0.3 * rng.standard_normal(100003), -0.9999, 0.9999).astype(np.float32)     # in range: numpy's overflow is undefined
+    x[:6] = [0.0, 1.0 / 32767, -1.0 / 32767, 0.99999, -0.99999, 0.5]
+    want = (x.astype(np.float64) * np.iinfo(np.int16).max).astype(np.int16)
+    got = audio.to_int16(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert got.dtype == np.int16 and np.array_equal(got, want)
+
+
 def test_stft_oracle_batched_full_size():
     from misonet_b200 import audio, synth
     from oracle import miso_np

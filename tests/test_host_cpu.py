@@ -164,3 +164,27 @@ def test_chunk_signal_follows_the_reference_rule():
     assert chunks.shape == (2, 10, 2) and gap == 0
     chunks, gap = C.chunk_signal(wav[:7], 10)         # shorter than one chunk (data.py:538-541)
     assert chunks.shape == (1, 10, 2) and gap == 3
+
+
+def test_wav_container_pcm24_round_trip(tmp_path):
+    """The reference writes int16 samples with sf.write(..., 'PCM_24') (tester.py:447, 971-972): a 24-bit container holding
+    the int16 value shifted left by 8.  Checked with the standard library's wave reader."""
+    import wave
+    import numpy as np
+    from misonet_b200 import audio
+    rng = np.random.default_rng(0)
+    pcm = rng.integers(-32768, 32767, size=(1000, 2), dtype=np.int16)
+    path = str(tmp_path / "x.wav")
+    audio.write_wav(path, pcm, 8000)
+    with wave.open(path, "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (2, 3, 8000, 1000)
+        raw = np.frombuffer(w.readframes(1000), dtype=np.uint8).reshape(1000, 2, 3).astype(np.int32)
+    v = raw[..., 0] | (raw[..., 1] << 8) | (raw[..., 2] << 16)
+    v = np.where(v >= 1 << 23, v - (1 << 24), v)
+    assert np.array_equal(v, pcm.astype(np.int32) << 8)
+    x, fs = audio.read_wav(path)
+    assert fs == 8000 and x.shape == (1000, 2)
+    assert np.array_equal(x, (pcm.astype(np.float32) / 32768.0))          # sf.read's normalisation
+    audio.write_wav(path, pcm[:, 0], 16000, subtype="PCM_16")
+    x, fs = audio.read_wav(path)
+    assert fs == 16000 and np.array_equal(x[:, 0], pcm[:, 0].astype(np.float32) / 32768.0)
