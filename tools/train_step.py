@@ -11,7 +11,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from misonet_b200 import criterion, distributed, synth  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (the bench's nvidia-smi clock / throttle sampler)
+from misonet_b200 import _lib, criterion, distributed, synth  # noqa: E402
 from misonet_b200.model import MISO_1  # noqa: E402
 
 LAYOUTS = {"REF": ([24, 32, 32, 32, 32, 64, 128], [128, 64, 32, 32, 32, 32, 24], 129, 501),
@@ -43,14 +44,19 @@ def main():
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     mix = torch.from_numpy(synth.random_spec(100 + rank, (B, 6, T, F))).to(dev)
     refs = [torch.from_numpy(synth.random_spec(200 + 10 * rank + s, (B, T, F))).to(dev) for s in range(2)]
+    host_mix = mix.cpu().pin_memory()
+    host_refs = [r.cpu().pin_memory() for r in refs]
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     phases = [0.0, 0.0, 0.0, 0.0]
     total_ms = 0.0
     loss = None
+    sampler, launches0 = None, 0
     for it in range(args.warmup + args.steps):
         if it == args.warmup:
             distributed.barrier()
             torch.cuda.synchronize()
+            sampler = ClockSampler(local) if rank == 0 else None
+            launches0 = _lib.launch_count()
         opt.zero_grad(set_to_none=True)
         ev[0].record()
         est = model(mix)
@@ -67,6 +73,27 @@ def main():
             for k in range(4):
                 phases[k] += ev[k].elapsed_time(ev[k + 1])
             total_ms += ev[0].elapsed_time(ev[4])
+    launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
+    # end to end: the same step fed from pinned host memory (H2D of the mixture and the references inside the timed
+    # region) with the loss read back to the host every step
+    distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(args.steps):
+        dmix = host_mix.to(dev, non_blocking=True)
+        drefs = [r.to(dev, non_blocking=True) for r in host_refs]
+        opt.zero_grad(set_to_none=True)
+        l = criterion.loss_uPIT(2, model(dmix), drefs)
+        l.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+        opt.step()
+        host_loss = float(l.detach().cpu())
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler is not None else None
+    e2e_ms = distributed.max_over_ranks(e0.elapsed_time(e1) / args.steps, device=dev)
+    h2d = host_mix.numel() * 8 + sum(r.numel() * 8 for r in host_refs)
     distributed.barrier()
     ms = distributed.max_over_ranks(total_ms / args.steps, device=dev)
     # algorithmic work of a training step: forward + data gradient + weight gradient = 3 x the forward's 2*MAC
@@ -111,6 +138,9 @@ def main():
                        "layout": args.layout, "conv_mode": args.conv_mode, "global_batch": world * B},
             "phases_ms_rank0": {"forward+loss": phases[0] / args.steps, "backward+grad_allreduce": phases[1] / args.steps,
                                 "clip+adam": (phases[2] + phases[3]) / args.steps},
+            "higher_is_better": True, "scaling": "weak", "dtype": "bf16x3 forward / bf16x3 + fp32 backward",
+            "e2e": {"value": world * B * T / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s per GPU, algorithmic (3 x forward 2*MAC) / step time",
                          "peak": peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"), "note": "whole step, not one kernel: "
                          "the backward GEMMs run bf16 hi/lo split (3 MMAs per product) on mma.sync and the tcgen05 conv kernel"},
