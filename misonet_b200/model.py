@@ -315,10 +315,12 @@ class _MisoNet(nn.Module):
         per = self._ws_bytes(1, T, F)
         return max(1, min(B, int(self.max_workspace_bytes // max(per, 1))))
 
-    def _input_planes(self, B, T, F, dev):
-        """Input buffer in the library's plane layout (include/misonet_b200.h): uint8 [B, bytes per sample]."""
+    def _input_planes(self, B, T, F, dev, train=False):
+        """Input buffer in the library's plane layout (include/misonet_b200.h): uint8 [B, bytes per sample].
+        A training forward gets its own buffer: the backward reads it (first layer's weight gradient), and an inference
+        forward in between (validation) must not overwrite it."""
         per = _lib.load().miso_net_input_bytes(self._handle, 1, T, F)
-        return self._buffer("x", (B, per), torch.uint8, dev)
+        return self._buffer("x_train" if train else "x", (B, per), torch.uint8, dev)
 
     def _run_body(self, x_cl, B, T, F):
         """x_cl: input planes uint8 [B, bytes per sample] -> float32 [B,T,F,out_ch]."""
@@ -404,11 +406,12 @@ class MISO_1(_MisoNet):
             raise ValueError(f"expected {self._in_ch // 2} microphones, got {M}")
         self._sync_params()
         n = len(shifts)
-        x_cl = self._input_planes(n * B, T, F, mix.device)
+        train = self._training_pass()
+        x_cl = self._input_planes(n * B, T, F, mix.device, train)
         arr = (ctypes.c_int * n)(*[int(s) for s in shifts])
         _lib.check(_lib.load().miso_pack_miso1(_lib.ptr(mix), _lib.ptr(x_cl), B, M, T, F, arr, n, _lib.stream_ptr()),
                    "miso_pack_miso1")
-        if self._training_pass():
+        if train:
             return _NetFunction.apply(self, x_cl, n * B, T, F, *self._param_list)
         y_cl = self._run_body(x_cl, n * B, T, F)
         return self._unpack(y_cl, n * B, T, F)
@@ -434,10 +437,11 @@ class MISO_3(_MisoNet):
         if second.shape != (B, 1, T, F) or third.shape != (B, 1, T, F):
             raise ValueError("second/third inputs must be [B,1,T,F]")
         self._sync_params()
-        x_cl = self._input_planes(B, T, F, mix.device)
+        train = self._training_pass()
+        x_cl = self._input_planes(B, T, F, mix.device, train)
         _lib.check(_lib.load().miso_pack_miso3(_lib.ptr(mix), _lib.ptr(second), _lib.ptr(third), _lib.ptr(x_cl), B, M, T, F,
                                                _lib.stream_ptr()), "miso_pack_miso3")
-        if self._training_pass():
+        if train:
             # trainer.py:398-414: the beamformed / MISO1 inputs are data (computed under no_grad or loaded from
             # disk, data.py:133-207), so only the parameters receive gradients
             return _NetFunction.apply(self, x_cl, B, T, F, *self._param_list)

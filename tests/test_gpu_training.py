@@ -256,6 +256,15 @@ def test_training_step_upit_end_to_end():
     cos = float((a @ b) / (a.norm() * b.norm()))
     assert cos > 0.9995, f"gradient direction cosine {cos}"
     assert abs(float(a.norm() / b.norm()) - 1.0) < 1e-2
+    # an inference forward (validation) between a training forward and its backward leaves the gradients untouched
+    g_first = torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+    m.zero_grad(set_to_none=True)
+    est = m(mix.cuda())
+    with torch.no_grad():
+        m(torch.from_numpy(synth.random_spec(43, (B, 6, T, 129))).cuda())
+    criterion.loss_uPIT(2, est, [refs[:, 0].cuda(), refs[:, 1].cuda()]).backward()
+    g_again = torch.cat([p.grad.flatten() for p in m.parameters()])
+    assert float((g_again - g_first).norm() / g_first.norm()) < 1e-4
     torch.nn.utils.clip_grad_norm_(m.parameters(), 10.0)          # trainer.py:210
     opt.step()
     with torch.no_grad():                                         # repacked weights are picked up by the next forward
