@@ -146,6 +146,52 @@ def golden_losses():
     np.savez_compressed(os.path.join(OUT, "loss_ref.npz"), **out)
 
 
+TRAIN_KEYS = {
+    "miso1": ["encoders.0.0.conv2d.weight", "encoders.1.1.conv3.0.bias", "encoders.6.0.net.0.weight",
+              "TCN.temporal_conv_net.0.3.net.2.net.0.weight", "TCN.temporal_conv_net.1.2.net.5.net.1.weight",
+              "TCN.temporal_conv_net.1.6.net.2.net.2.gamma", "TCN.temporal_conv_net.1.6.net.5.net.3.weight",
+              "decoders.3.0.conv1.0.weight", "decoders.6.1.deconv2d.weight", "decoders.6.1.deconv2d.bias"],
+    "miso3": ["encoders.0.0.conv2d.weight", "TCN.temporal_conv_net.1.6.net.5.net.3.weight", "decoders.6.1.deconv2d.weight",
+              "decoders.6.1.deconv2d.bias"],
+}
+
+
+def golden_training():
+    """The reference's training-step body (trainer.py:158-172, 207 / 400-404): model(mix) -> loss_uPIT / loss_Enhance ->
+    loss.backward() through the REAL model.py and criterion.py; stores the loss, the norm of every parameter gradient
+    and a handful of full gradient tensors.  PReLU slopes are set to 1 for the gradient fixture (the kink of the default
+    slope makes gradients of two fp32 implementations differ at the 1e-3 level; see tests/test_gpu_training.py)."""
+    ns = ref_import.load()
+    out = {}
+    for kind, seed in (("miso1", 0), ("miso3", 1)):
+        mod, cfg, sd = build_reference_model(kind, seed)
+        with torch.no_grad():
+            for k, p in mod.named_parameters():
+                if k.startswith("TCN.") and k.endswith(".net.1.weight"):
+                    p.fill_(1.0)
+        mod.train()
+        b, t = 2, 12
+        mix = torch.from_numpy(synth.random_spec(61, (b, 6, t, 129)))
+        if kind == "miso1":
+            refs = synth.random_spec(62, (b, 2, t, 129))
+            est = mod(mix)
+            loss = ns.criterion.loss_uPIT(2, est, [torch.from_numpy(refs[:, k].copy()) for k in range(2)])
+        else:
+            a2 = torch.from_numpy(synth.random_spec(63, (b, 1, t, 129)))
+            a3 = torch.from_numpy(synth.random_spec(64, (b, 1, t, 129)))
+            refs = synth.random_spec(65, (b, 1, t, 129))
+            est = mod(mix, a2, a3)
+            loss = ns.criterion.loss_Enhance(est, torch.from_numpy(refs))
+        loss.backward()
+        out[f"{kind}_loss"] = loss.detach().numpy()
+        out[f"{kind}_est"] = est.detach().numpy()
+        out[f"{kind}_grad_norms"] = np.array([float(p.grad.norm()) for _, p in mod.named_parameters()], dtype=np.float64)
+        for k, p in mod.named_parameters():
+            if k in TRAIN_KEYS[kind]:
+                out[f"{kind}_grad::{k}"] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "train_ref.npz"), **out)
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     os.makedirs(OUT, exist_ok=True)
@@ -155,6 +201,7 @@ def main():
     golden_losses()
     golden_net()
     golden_inference()
+    golden_training()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

@@ -271,3 +271,54 @@ def test_training_step_upit_end_to_end():
         est2 = m(mix.cuda())
     loss2 = criterion.loss_uPIT(2, est2, [refs[:, 0].cuda(), refs[:, 1].cuda()])
     assert torch.isfinite(loss2) and loss2.item() != loss.item()
+
+
+@pytest.mark.parametrize("kind", ["miso1", "miso3"])
+def test_training_step_against_reference_fixture(kind):
+    """The CUDA training step against the REAL reference's model(mix) -> loss -> loss.backward() (tests/golden/train_ref.npz,
+    generated by oracle/make_golden.py:golden_training from model.py + criterion.py; PReLU slopes 1).  The L1 losses'
+    sign() makes a single estimate/reference crossing worth ~1e-2 of the gradient at this size (12 k output values), so the
+    bounds here are loose by design; the tight gradient checks are the smooth-upstream tests above."""
+    import os
+    from conftest import GOLDEN
+    from misonet_b200 import criterion, synth
+    from misonet_b200.model import MISO_1, MISO_3
+    from oracle import weights
+    from oracle import miso_net_torch as mnt
+    g = np.load(os.path.join(GOLDEN, "train_ref.npz"))
+    en, de = mnt.LAYOUTS["REF"]
+    cfg = mnt.NetConfig.miso1() if kind == "miso1" else mnt.NetConfig.miso3()
+    sd = weights.make_state_dict(cfg, 0 if kind == "miso1" else 1)
+    for k in sd:
+        if k.startswith("TCN.") and k.endswith(".net.1.weight"):
+            sd[k] = torch.ones_like(sd[k])
+    m = (MISO_1(2, 6, 7, list(en), list(de), "IN") if kind == "miso1" else MISO_3(1, 6, 7, list(en), list(de), "IN"))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    m.conv_mode = "bf16x3"
+    b, t = 2, 12
+    mix = torch.from_numpy(synth.random_spec(61, (b, 6, t, 129))).cuda()
+    if kind == "miso1":
+        refs = torch.from_numpy(synth.random_spec(62, (b, 2, t, 129))).cuda()
+        est = m(mix)
+        loss = criterion.loss_uPIT(2, est, [refs[:, 0], refs[:, 1]])
+    else:
+        a2 = torch.from_numpy(synth.random_spec(63, (b, 1, t, 129))).cuda()
+        a3 = torch.from_numpy(synth.random_spec(64, (b, 1, t, 129))).cuda()
+        refs = torch.from_numpy(synth.random_spec(65, (b, 1, t, 129))).cuda()
+        est = m(mix, a2, a3)
+        loss = criterion.loss_Enhance(est, refs)
+    loss.backward()
+    assert rel_err(est.detach().cpu().numpy(), g[f"{kind}_est"]) < 2 * FORWARD_AGREEMENT
+    assert abs(loss.item() - float(g[f"{kind}_loss"])) <= 1e-4 * abs(float(g[f"{kind}_loss"]))
+    ref_norms = g[f"{kind}_grad_norms"]
+    norms = np.array([float(p.grad.norm()) for p in m.parameters()])
+    big = ref_norms > 1e-6 * ref_norms.max()
+    assert np.all(np.abs(norms[big] - ref_norms[big]) <= 3e-2 * ref_norms[big])
+    worst = 0.0
+    for key in g.files:
+        if key.startswith(f"{kind}_grad::"):
+            k = key.split("::", 1)[1]
+            worst = max(worst, rel_err(dict(m.named_parameters())[k].grad.cpu().numpy(), g[key]))
+    assert worst < 3e-2, worst
+    print(f"{kind}: worst stored gradient tensor vs the reference {worst:.2e}")

@@ -119,3 +119,57 @@ def test_paper_layout_shapes():
 def test_ref_param_count():
     assert sum(int(np.prod(s)) for s in weights.param_shapes(mnt.NetConfig.miso1()).values()) == 2587384
     assert sum(int(np.prod(s)) for s in weights.param_shapes(mnt.NetConfig.miso3()).values()) == 2587382
+
+
+def _training_case(kind, g):
+    """Inputs of oracle/make_golden.py:golden_training and the oracle's loss + autograd gradients for them."""
+    cfg = mnt.NetConfig.miso1() if kind == "miso1" else mnt.NetConfig.miso3()
+    sd = weights.make_state_dict(cfg, 0 if kind == "miso1" else 1)
+    for k in sd:
+        if k.startswith("TCN.") and k.endswith(".net.1.weight"):
+            sd[k] = torch.ones_like(sd[k])
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    b, t = 2, 12
+    mix = torch.from_numpy(synth.random_spec(61, (b, 6, t, 129)))
+    if kind == "miso1":
+        refs = torch.from_numpy(synth.random_spec(62, (b, 2, t, 129)))
+        y = mnt.net_forward(sdr, cfg, torch.cat((mix.real, mix.imag), dim=1))
+        est = torch.complex(y[:, :2], y[:, 2:])
+        e, r = est.unsqueeze(2), refs.unsqueeze(1)
+        pair = ((e.real - r.real).abs().sum((3, 4)) + (e.imag - r.imag).abs().sum((3, 4)) +
+                (torch.sqrt(e.real ** 2 + e.imag ** 2 + 1e-8) - r.abs()).abs().sum((3, 4)))            # criterion.py:27-33
+        per = torch.stack([pair[:, 0, 0] + pair[:, 1, 1], pair[:, 0, 1] + pair[:, 1, 0]], dim=1)
+        loss = per.min(dim=1).values.mean()
+    else:
+        a2 = torch.from_numpy(synth.random_spec(63, (b, 1, t, 129)))
+        a3 = torch.from_numpy(synth.random_spec(64, (b, 1, t, 129)))
+        refs = torch.from_numpy(synth.random_spec(65, (b, 1, t, 129)))
+        y = mnt.net_forward(sdr, cfg, torch.cat((mix.real, a2.real, a3.real, mix.imag, a2.imag, a3.imag), dim=1))
+        est = torch.complex(y[:, :1], y[:, 1:])
+        loss = ((est.real - refs.real).abs().sum() + (est.imag - refs.imag).abs().sum() +
+                (torch.sqrt(est.real ** 2 + est.imag ** 2 + 1e-8) - refs.abs()).abs().sum()) / b       # criterion.py:131-139
+    loss.backward()
+    return est.detach(), loss.detach(), {k: v.grad for k, v in sdr.items()}
+
+
+@pytest.mark.parametrize("kind", ["miso1", "miso3"])
+def test_training_step_matches_reference(kind):
+    """The oracle's training step (network + loss + autograd) against the REAL reference's model(mix) -> loss ->
+    loss.backward() (tests/golden/train_ref.npz): this is what pins the gradient parity tests of the CUDA path."""
+    g = _load("train_ref.npz")
+    est, loss, grads = _training_case(kind, g)
+    assert rel_err(est.numpy(), g[f"{kind}_est"]) < 5e-6
+    assert abs(float(loss) - float(g[f"{kind}_loss"])) <= 2e-6 * abs(float(g[f"{kind}_loss"]))
+    norms = np.array([float(v.norm()) for v in grads.values()])
+    ref_norms = g[f"{kind}_grad_norms"]
+    scale = ref_norms.max()
+    big = ref_norms > 1e-6 * scale                      # the gLN betas ahead of an InstanceNorm1d have zero gradient
+    assert np.all(np.abs(norms[big] - ref_norms[big]) <= 2e-4 * ref_norms[big])          # measured 2.5e-5
+    assert np.all(norms[~big] <= 1e-5 * scale)
+    n = 0
+    for key in g.files:
+        if key.startswith(f"{kind}_grad::"):
+            k = key.split("::", 1)[1]
+            assert rel_err(grads[k].numpy(), g[key]) < 5e-5, k                # measured 2e-6
+            n += 1
+    assert n >= 4
