@@ -8,6 +8,8 @@ Workloads (BASELINE.json configs):
                 500 frames, 8-block "paper" layout (model.py:13-14,30 comments)
   miso1_ref     the same on the shipped 7-block / 129-bin / 501-frame layout
   pipeline_ref  (configs[2]) STFT -> MISO1 x6 shifts -> align -> MVDR x2 -> MISO3 x2, per-GPU batch 32, REF layout
+  train_paper   (configs[3] per-GPU shape) MISO_1 training step: forward + loss_uPIT + backward + gradient all-reduce +
+                Adam, 8 utterances per GPU, PAPER layout (tools/train_step.py prints the line)
 
 One "step" = one pass of the workload over one synthetic batch per GPU.  `value` is whole-job
 frames/s with inputs resident in HBM; `e2e` is the same through the public API with pinned host
@@ -404,12 +406,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="miso1_paper", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="miso1_paper", choices=sorted(WORKLOADS) + ["train_paper"])
     ap.add_argument("--conv-mode", default="bf16x3", choices=sorted(CONV_MODES),
                     help="compute path of the conv stack (default: the parity-grade tensor-core mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (profiling runs only)")
     args = ap.parse_args()
+    if args.workload == "train_paper":
+        if args.impl == "reference":
+            raise SystemExit("--workload train_paper: the CPU leg is the line's cpu_baseline (tools/train_step.py --cpu-baseline)")
+        import runpy
+        sys.argv = [sys.argv[0], "--layout", "PAPER", "--batch", str(args.batch or 8), "--steps", str(args.steps), "--warmup",
+                    str(args.warmup), "--conv-mode", args.conv_mode] + ([] if args.no_cpu_baseline else ["--cpu-baseline"])
+        runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "train_step.py"), run_name="__main__")
+        return
     wl = dict(WORKLOADS[args.workload])
     if args.batch > 0:
         wl["B"] = args.batch
