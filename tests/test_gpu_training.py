@@ -326,3 +326,44 @@ def test_training_step_against_reference_fixture(kind):
             worst = max(worst, rel_err(dict(m.named_parameters())[k].grad.cpu().numpy(), g[key]))
     assert worst < 3e-2, worst
     print(f"{kind}: worst stored gradient tensor vs the reference {worst:.2e}")
+
+
+def test_training_full_size_properties():
+    """BASELINE configs[3] utterance shape (PAPER layout, 500 frames x 257 bins) where the oracle's autograd is too slow
+    to be the checker: size-independent properties of the backward pass.
+    (1) The last deconv has no ELU / norm behind it (model.py:418-423), so its bias gradient is exactly the sum of the
+        upstream gradient per output channel.
+    (2) Directional derivative: for the smooth functional L(theta) = Re <g, model(mix; theta)> the central difference
+        along the normalised gradient direction d equals |grad| (grad . d)."""
+    from misonet_b200 import synth
+    m, cfg, sd = _model(9, "PAPER", "bf16x3", prelu_alpha=1.0)
+    B, T, F = 2, 500, 257
+    mix = torch.from_numpy(synth.random_spec(71, (B, 6, T, F))).cuda()
+    up = torch.from_numpy(synth.random_spec(72, (B, 2, T, F))).cuda()
+    out = m(mix)
+    out.backward(up)
+    params = dict(m.named_parameters())
+    gb = params["decoders.7.1.deconv2d.bias"].grad.cpu().double().numpy()
+    want = torch.cat((up.real.sum(dim=(0, 2, 3)), up.imag.sum(dim=(0, 2, 3)))).cpu().double().numpy()      # channels re(s0, s1), im(s0, s1)
+    assert rel_err(gb, want) < 1e-4
+    grads = [p.grad.clone() for p in m.parameters()]
+    assert all(torch.isfinite(g).all() for g in grads)
+    gnorm = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads)))
+
+    def functional():
+        with torch.no_grad():
+            o = m(mix)
+        return float((o.real.double() * up.real.double() + o.imag.double() * up.imag.double()).sum())
+
+    eps = 2e-3
+    with torch.no_grad():
+        for p, g in zip(m.parameters(), grads):
+            p.add_(g, alpha=eps / gnorm)
+        lp = functional()
+        for p, g in zip(m.parameters(), grads):
+            p.add_(g, alpha=-2 * eps / gnorm)
+        lm = functional()
+        for p, g in zip(m.parameters(), grads):
+            p.add_(g, alpha=eps / gnorm)
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd - gnorm) < 2e-2 * gnorm, (fd, gnorm)
