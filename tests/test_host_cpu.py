@@ -132,6 +132,17 @@ tot = D.allreduce_gradients(params, n_local=hi - lo)
 assert tot == n_total
 for p in params:
     assert torch.allclose(p.grad, torch.full_like(p, 4.0)), p.grad      # mean over all 7 utterances of (i + 1)
+# training._backward on a module without the library's in-backward reduction: mean-loss gradients of unequal shards
+# must come out as the gradient of the mean over ALL utterances
+from misonet_b200 import training as TR
+torch.manual_seed(0)
+lin = torch.nn.Linear(4, 1)
+xs = torch.arange(n_total * 4, dtype=torch.float32).reshape(n_total, 4) / 10.0
+full = lin(xs).pow(2).mean()
+gfull = torch.autograd.grad(full, list(lin.parameters()))
+TR._backward(lin, lin(xs[lo:hi]).pow(2).mean(), hi - lo)
+for p, gexp in zip(lin.parameters(), gfull):
+    assert torch.allclose(p.grad, gexp, rtol=1e-5, atol=1e-6), (p.grad, gexp)
 D.barrier()
 assert count == n_total and abs(mean - 4.0) < 1e-12, (mean, count)
 assert allidx.tolist() == [i % 2 for i in range(n_total)], allidx
