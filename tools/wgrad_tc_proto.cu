@@ -1,6 +1,6 @@
 // Prototype of the inner loop of the planned tcgen05 weight-gradient GEMM, self-checking.
-// STATUS: compiles for sm_100a; NOT YET RUN ON HARDWARE (written after the round-1 GPU budget was spent).  It extends
-// tools/umma_mn_test.cu -- whose MN-major operand recipe IS verified on B200 -- from one MMA to the real loop shape:
+// STATUS: verified on B200 (profiles/r1_d_wgrad_tc_proto.log: relative error 1.4e-5 against a float64 sum).  It extends
+// tools/umma_mn_test.cu (one MMA, MN-major operand recipe) to the real loop shape:
 //   dW[ci][co] = sum_p E[ci][p] * dY[co][p],   M = 128 input channels, N = 32 output channels, K = P pixels,
 // operands read from "planes" exactly as the library stores activations / dL/dy: for every 8-channel group, pixel p is
 // the 16-byte row p (bf16 hi plane set and bf16 lo plane set), three MMAs per product (hi*hi + hi*lo + lo*hi, fp32
