@@ -1,8 +1,10 @@
 // Correctness probe for the planned tcgen05 weight-gradient GEMM: one tcgen05.mma (M = 128, N = 32,
 // K = 16, bf16, fp32 accumulate) with BOTH operands MN-major, no swizzle, laid out the way a staged activation-plane tile
 // is: for every group of 8 M (or N) elements, consecutive K rows are consecutive 16-byte rows (8 K rows = one 128-byte core
-// matrix), groups 256 bytes apart.  Tries both assignments of (leading, stride) byte offsets and prints which one
-// reproduces A * B.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_mn_test umma_mn_test.cu && ./umma_mn_test
+// matrix).  Tries both assignments of (leading, stride) byte offsets and prints which one reproduces A * B [verified on
+// B200: LBO = 8-row step, SBO = group step], and -- the open point of the planned weight-gradient kernel, NOT YET RUN -- an
+// A start address shifted by one 16-byte K row (A is stored with 24 K rows per group so that rows 1..16 exist).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_mn_test umma_mn_test.cu && ./umma_mn_test
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -28,17 +30,19 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-constexpr int M = 128, N = 32, K = 16;
+constexpr int M = 128, N = 32, K = 16, KA = 24;  // KA: K rows stored per A group (rows beyond 16 are only used by the shifted probe)
 
-__global__ void __launch_bounds__(128, 1) probe(const __nv_bfloat16 *A, const __nv_bfloat16 *B, float *D, int lbo, int sbo) {
-    __shared__ __align__(1024) uint8_t sA[M / 8 * 256];
+// A is [M][KA]; the MMA reads K rows shift .. shift + 15
+__global__ void __launch_bounds__(128, 1) probe(const __nv_bfloat16 *A, const __nv_bfloat16 *B, float *D, int lbo, int sbo_a, int sbo_b,
+                                                int swap, int shift) {
+    __shared__ __align__(1024) uint8_t sA[M / 8 * KA * 16];
     __shared__ __align__(1024) uint8_t sB[N / 8 * 256];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
     const int tid = threadIdx.x;
-    for (int i = tid; i < M * K; i += 128) {  // A[m][k] -> group m / 8, K row k, element m % 8
-        const int m = i / K, k = i % K;
-        *reinterpret_cast<__nv_bfloat16 *>(sA + (m / 8) * 256 + k * 16 + (m % 8) * 2) = A[i];
+    for (int i = tid; i < M * KA; i += 128) {  // A[m][k] -> group m / 8, K row k, element m % 8
+        const int m = i / KA, k = i % KA;
+        *reinterpret_cast<__nv_bfloat16 *>(sA + (m / 8) * KA * 16 + k * 16 + (m % 8) * 2) = A[i];
     }
     for (int i = tid; i < K * N; i += 128) {  // B[k][n] -> group n / 8, K row k, element n % 8
         const int k = i / N, n = i % N;
@@ -58,7 +62,8 @@ __global__ void __launch_bounds__(128, 1) probe(const __nv_bfloat16 *A, const __
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = slot;
     if (tid == 0) {
-        const uint64_t da = make_desc(smem_u32(sA), lbo, sbo), db = make_desc(smem_u32(sB), lbo, sbo);
+        const uint64_t da = swap ? make_desc(smem_u32(sA) + 16 * shift, sbo_a, lbo) : make_desc(smem_u32(sA) + 16 * shift, lbo, sbo_a);
+        const uint64_t db = swap ? make_desc(smem_u32(sB), sbo_b, lbo) : make_desc(smem_u32(sB), lbo, sbo_b);
         asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem), "l"(da),
                      "l"(db), "r"(make_idesc_mn(N))
                      : "memory");  // predicate false = overwrite the accumulator
@@ -83,17 +88,11 @@ __global__ void __launch_bounds__(128, 1) probe(const __nv_bfloat16 *A, const __
 }
 
 int main() {
-    static __nv_bfloat16 hA[M * K], hB[K * N];
+    static __nv_bfloat16 hA[M * KA], hB[K * N];
     static float ref[M * N], hD[M * N];
     srand(1);
-    for (int i = 0; i < M * K; ++i) hA[i] = __float2bfloat16((float)(rand() % 17 - 8) / 8.f);
+    for (int i = 0; i < M * KA; ++i) hA[i] = __float2bfloat16((float)(rand() % 17 - 8) / 8.f);
     for (int i = 0; i < K * N; ++i) hB[i] = __float2bfloat16((float)(rand() % 13 - 6) / 4.f);
-    for (int m = 0; m < M; ++m)
-        for (int n = 0; n < N; ++n) {
-            float s = 0.f;
-            for (int k = 0; k < K; ++k) s += __bfloat162float(hA[m * K + k]) * __bfloat162float(hB[k * N + n]);
-            ref[m * N + n] = s;
-        }
     __nv_bfloat16 *dA, *dB;
     float *dD;
     cudaMalloc(&dA, sizeof(hA));
@@ -101,16 +100,27 @@ int main() {
     cudaMalloc(&dD, sizeof(hD));
     cudaMemcpy(dA, hA, sizeof(hA), cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB, sizeof(hB), cudaMemcpyHostToDevice);
-    const int variants[2][2] = {{128, 256}, {256, 128}};  // (leading byte offset, stride byte offset)
+    struct {
+        const char *name;
+        int swap, shift;
+    } variants[] = {{"LBO = 8-row step (128), SBO = group step", 0, 0},
+                    {"LBO and SBO swapped", 1, 0},
+                    {"LBO = 128, SBO = group step, A start + 16 bytes (K rows 1..16)", 0, 1},
+                    {"LBO = 128, SBO = group step, A start + 48 bytes (K rows 3..18)", 0, 3}};
     for (auto &v : variants) {
+        for (int m = 0; m < M; ++m)
+            for (int n = 0; n < N; ++n) {
+                float s = 0.f;
+                for (int k = 0; k < K; ++k) s += __bfloat162float(hA[m * KA + k + v.shift]) * __bfloat162float(hB[k * N + n]);
+                ref[m * N + n] = s;
+            }
         cudaMemset(dD, 0xff, sizeof(hD));
-        probe<<<1, 128>>>(dA, dB, dD, v[0], v[1]);
+        probe<<<1, 128>>>(dA, dB, dD, 128, KA * 16, 256, v.swap, v.shift);
         cudaError_t e = cudaDeviceSynchronize();
         cudaMemcpy(hD, dD, sizeof(hD), cudaMemcpyDeviceToHost);
         double mx = 0.0;
         for (int i = 0; i < M * N; ++i) mx = fmax(mx, fabs((double)hD[i] - ref[i]));
-        printf("MN-major A and B, no swizzle, LBO=%d SBO=%d: %s, max |D - A*B| = %g %s\n", v[0], v[1], cudaGetErrorString(e), mx,
-               mx < 1e-3 ? "<-- matches" : "");
+        printf("MN-major A and B, no swizzle, %s: %s, max |D - A*B| = %g %s\n", v.name, cudaGetErrorString(e), mx, mx < 1e-3 ? "<-- matches" : "");
         if (e != cudaSuccess) break;
     }
     return 0;
