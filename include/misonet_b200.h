@@ -113,7 +113,8 @@ int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, in
 /* compute path of the 3x3 (de)convs: 0 = fp32 FMA kernels everywhere; 1 = tcgen05 bf16x3 split
  * (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 accumulate: parity-grade, 3 MMAs per product); 2 = tcgen05
  * bf16 operands and hi-only activation planes (throughput mode, ~1e-2 relative error).
- * The TCN always runs in fp32. */
+ * In modes 1 / 2 the TCN's pointwise convs run on tcgen05 too (tcn_pw_kernel, same split); its depthwise convs,
+ * norms and the residual stream stay fp32. */
 int miso_net_set_mode(miso_net_t *net, int mode);
 /* F must reduce to exactly 1 at the bottleneck (129 for 7 blocks, 257 for 8); returns
  * MISO_E_ARG with a clear message otherwise (the reference raises an opaque conv error). */
@@ -155,9 +156,10 @@ int miso_wave_to_int16(const float *d_x, int16_t *d_out, int64_t n, float scale,
  *             zero padding channels; written by miso_grad_pack); clobbered
  *   d_grads : gradient of every parameter, flat fp32 in miso_net_param_key order, each in its torch layout
  *             (miso_net_grad_numel elements in total); overwritten.
- * Both run in the conv mode of miso_net_set_mode for the forward; all backward arithmetic is fp32 FMA
- * (InstanceNorm2d / ELU / gLN / PReLU / depthwise / InstanceNorm1d backward kernels, the weight-gradient GEMM, and
- * the data gradients through the forward conv kernels with transposed weights). */
+ * Both run in the conv mode of miso_net_set_mode.  Mode 0: all backward arithmetic is fp32 FMA.  Modes 1 / 2: the data
+ * gradients run on the forward's tcgen05 conv kernels (dL/dy as bf16 hi/lo planes x transposed weights) and the weight
+ * gradients on tensor cores with the same bf16 hi/lo split and fp32 accumulation; the InstanceNorm2d / ELU / gLN /
+ * PReLU / depthwise / InstanceNorm1d backward kernels are fp32 elementwise / reduction kernels in every mode. */
 int64_t miso_net_grad_numel(const miso_net_t *net);
 size_t miso_net_train_workspace_bytes(const miso_net_t *net, int B, int T, int F);
 int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, int T, int F, void *d_ws,

@@ -12,7 +12,7 @@ import torch.distributed as dist
 from . import audio
 from .pipeline import shard_range
 
-MAX_INT16 = 32767  # tester.py: self.MaxInt16
+MAX_INT16 = audio.MAX_INT16  # tester.py: self.MaxInt16
 
 
 def chunk_signal(wav, chunk_size):
@@ -74,7 +74,7 @@ def separate_recording(pipe, wav, chunk_size=32000, rank=0, world=1, to_int16=Fa
     sig = full.permute(1, 0, 2).reshape(spk, n_chunks * chunk_size)
     sig = sig[:, : n_chunks * chunk_size - gap]                           # tester.py:961-963
     if to_int16:
-        sig = (sig * MAX_INT16).to(torch.int16)                          # numpy astype truncates toward zero, like .to()
+        sig = audio.to_int16(sig.contiguous())                           # wave_to_int16_kernel: x * MaxINT16 in double, truncation (tester.py:155-157)
     return sig
 
 

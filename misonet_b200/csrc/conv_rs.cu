@@ -46,16 +46,47 @@ constexpr int kRsMaxStages = 4;
 constexpr int kRsSmemLimit = 227 * 1024;
 constexpr int kRsFixed = 1024;
 constexpr int kRsBiasCi = 64;
+constexpr int kRsAffCh = 144;  // channels of the late units in fused mode: a group of <= 128 channels + 8 + padding to a unit
 
 struct RsGeom {
     int Nc, N3, L, G, Mr, pitch, PL, GS, nsp;
     int nplanes, nunit, kper, nchunk;
     int w_unit, w_off, stage, nstage, box_bytes;
-    int off_btab, off_red, off_stage, smem_total, tmem_cols;
+    int off_btab, off_red, off_aff, off_stage, smem_total, tmem_cols;
     int map5d;
     int S, TS, DS, Wr;  // packed mode (F + 1 <= 64): an M tile holds the same row of S frame strips; strip s covers the TS frames
                         // from s * DS, DS = T / S, TS = DS + T % S (the strips overlap by T % S frames so that they tile any T
                         // at a uniform stride; the duplicated frames count for the last strip only)
+};
+
+// In-kernel operand preparation ("fused" mode, the forward DenseBlock convs).  The input channels of conv k of a block
+// are [x | y0 | ... | y_{k-2}]; only the statistics of the LAST group (produced by the kernel right before this one) are
+// new, so the slices of the weight image / border-bias sums of the older groups were written by the earlier convs of
+// the block (their "jobs"), and this kernel's idle epilogue warps build, at kernel start,
+//   (i)  privately (per CTA, for the samples of its own row range): the image of the units that hold the late group
+//        and the late group's border-bias partial sums -- the producer warp streams those units from the private copy;
+//   (ii) shared: the same group's slices for the LATER convs of the block (distributed over the CTAs).
+// No separate preparation launch sits between two convs of a block any more.
+constexpr int kRsMaxSlots = 8;   // samples a CTA's row range may touch in fused mode
+struct RsJob {
+    const float *w;        // consumer's packed fp32 weights [9][cin][cout_pad]
+    __nv_bfloat16 *wimg;   // consumer's image [B][nunit][w_unit / 2]
+    float *btab;           // consumer's border-bias partial sums [B][ngroup][9][Nc]
+    int cin, cout, cout_pad, Nc, nunit, ngroup, gidx;
+};
+struct RsFuse {
+    int on;
+    int c0, u0, nlate;     // late group = channels [c0, cin); units [u0, nunit) are built in the kernel
+    int nslot;             // sample slots per CTA of the private scratch
+    __nv_bfloat16 *priv;   // [grid][nslot][nlate][w_unit / 2]
+    float *priv_bias;      // [grid][nslot][9][Nc]
+    const float *w;        // this layer's packed fp32 weights [9][cin][cout_pad]
+    const double *in_sums; // statistics of the input buffer [B][in_ctot][2]
+    int in_ctot, cin, cout_pad;
+    double inv_n;
+    float eps;
+    int njob;
+    RsJob job[kRsMaxJobs];
 };
 
 struct RsArgs {
@@ -73,6 +104,7 @@ struct RsArgs {
     size_t out_lo_off;
     int use_lo, elu;
     long long *trace;  // debug: clock64 event log of CTA 0 (tools/tc_trace.py), or null
+    RsFuse fuse;
 };
 
 // trace regions: [0,4096) producer, [4096,8192) MMA issuer, [8192,12288) first epilogue warp; entries are (tag, clock)
@@ -157,6 +189,81 @@ struct RsTiles {
     }
 };
 
+// ---- fused-mode operand preparation (executed by the 256 epilogue threads; et = thread index among them) ----
+// One 8-channel half (kg) of a 16-channel K unit of a weight image: rows [kf][hi|lo][kg][n = (2 - kt) * Nc + co][8 ci]
+//   = bf16 split of W[kt][kf][ch0 + e][co] * scale8[e]      (same layout as conv_rs_prep_kernel writes)
+__device__ __forceinline__ void rs_build_half(const float *__restrict__ w, int cin, int cout, int cout_pad, int Nc, int nsp, int ch0,
+                                              const float *scale8, __nv_bfloat16 *dst_unit, int et) {
+    const int N3 = 3 * Nc, kg = (ch0 >> 3) & 1;
+    for (int i = et; i < 3 * N3; i += kRsEpiThreads) {
+        const int kf = i / N3, n = i - kf * N3;
+        const int ktg = n / Nc, co = n - ktg * Nc;
+        const int kt = 2 - ktg;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = ch0 + e;
+            v[e] = (ci < cin && co < cout) ? __ldg(w + ((size_t)(kt * 3 + kf) * cin + ci) * cout_pad + co) : 0.f;
+        }
+        float h[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float x = v[e] * scale8[e];
+            h[e] = bf16_round(x);
+            l[e] = x - h[e];
+        }
+        __nv_bfloat16 *dst = dst_unit + ((size_t)((kf * nsp) * 2 + kg) * N3 + n) * 8;
+        *reinterpret_cast<uint4 *>(dst) =
+            make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+        if (nsp == 2)
+            *reinterpret_cast<uint4 *>(dst + (size_t)2 * N3 * 8) =
+                make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    }
+}
+// Border-bias partial sums of one channel group: dst[kt * 3 + kf][n] = sum_{ci < nch} W[k][ch0 + ci][n] * shift[ci]
+// (fixed summation order: nparts channel parts, then the parts).  scratch: shared memory, cap floats.
+__device__ __forceinline__ void rs_build_bias(const float *__restrict__ w, int cin, int cout, int cout_pad, int Nc, int ch0, int nch,
+                                              const float *shift, float *scratch, int cap, float *dst, int et) {
+    const int nparts = min(min(7, kRsEpiThreads / Nc), cap / (9 * Nc));
+    const int n = et % Nc, part = et / Nc;
+    if (part < nparts) {
+        float acc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+        if (n < cout) {
+#pragma unroll 2
+            for (int ci = part; ci < nch; ci += nparts) {
+                const float sv = shift[ci];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc[k] = fmaf(__ldg(w + ((size_t)k * cin + ch0 + ci) * cout_pad + n), sv, acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) scratch[(part * 9 + k) * Nc + n] = acc[k];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+    for (int i = et; i < 9 * Nc; i += kRsEpiThreads) {
+        float v = 0.f;
+        for (int q = 0; q < nparts; ++q) v += scratch[q * 9 * Nc + i];
+        dst[i] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+}
+// consumer-side InstanceNorm affine of channel ci of the input view (in_coff = 0 inside a DenseBlock)
+__device__ __forceinline__ float2 rs_fuse_affine(const RsFuse &fz, int b, int ci) {
+    const double *sp = fz.in_sums + ((size_t)b * fz.in_ctot + ci) * 2;
+    // the statistics were accumulated with atomics by the previous kernel: plain loads through L2
+    return affine_from_sums(stat_get(sp), stat_get(sp + 1), fz.inv_n, (double)fz.eps);
+}
+// first / last sample of this CTA's row range
+__device__ __forceinline__ void rs_sample_range(const RsArgs &a, int &b_first, int &b_last) {
+    const int TU = a.g.S > 1 ? a.g.TS : a.T;
+    const long long R = (long long)a.B * a.g.Mr * TU;
+    const int rho = (int)(R * blockIdx.x / gridDim.x), rho_end = (int)(R * (blockIdx.x + 1) / gridDim.x);
+    b_first = (rho / TU) / a.g.Mr;
+    b_last = rho_end > rho ? ((rho_end - 1) / TU) / a.g.Mr : b_first - 1;
+}
+
 __device__ __forceinline__ float rs_elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
 template <int SPLIT>
@@ -171,6 +278,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
     const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 64);
     const uint32_t bar_tfull = smem_u32(smem + 128), bar_tempty = smem_u32(smem + 144);
+    const uint32_t bar_late = smem_u32(smem + 192);  // fused mode: the private late units of sample slot i are in place
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 160);
     float *btab_s = reinterpret_cast<float *>(smem + g.off_btab);
     float *red = reinterpret_cast<float *>(smem + g.off_red);
@@ -185,6 +293,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, kRsEpiThreads / 32);
         }
+        for (int i = 0; i < kRsMaxSlots; ++i) mbar_init(bar_late + 8 * i, kRsEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -221,8 +330,14 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             int s = 0, ph = 0, ntr = 0;  // stage index and the parity of the release of its previous use
             bool primed = false;         // every stage has been filled once
             RsWalk w = rs_walk(a);
+            int b_first = 0, b_last = 0;
+            if (a.fuse.on) rs_sample_range(a, b_first, b_last);
+            int late_seen = -1;  // last sample slot whose late-unit barrier has been passed
             while (w.next()) {
                 const __nv_bfloat16 *wsrc = a.wimg + (size_t)w.b * a.wimg_bstride;
+                const int slot = w.b - b_first;
+                const __nv_bfloat16 *wlate =
+                    a.fuse.on ? a.fuse.priv + ((size_t)blockIdx.x * a.fuse.nslot + slot) * a.fuse.nlate * (size_t)(g.w_unit / 2) : nullptr;
                 const int f0 = 128 * w.m - 1;
                 RsTiles tl;
                 tl.init(a, w);
@@ -249,7 +364,24 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                             else
                                 tma_load_4d(dst, tm, full, 2 * f0, tin, pl, w.b);
                         }
-                        bulk_load(sa + (uint32_t)g.w_off, wsrc + (size_t)c * g.kper * (g.w_unit / 2), (uint32_t)(nu * g.w_unit), full);
+                        if (!a.fuse.on) {
+                            bulk_load(sa + (uint32_t)g.w_off, wsrc + (size_t)c * g.kper * (g.w_unit / 2), (uint32_t)(nu * g.w_unit), full);
+                        } else {
+                            for (int q = 0; q < nu; ++q) {  // units below u0 from the layer's image, the late ones from the private copy
+                                const int u = g.kper * c + q;
+                                const __nv_bfloat16 *src;
+                                if (u < a.fuse.u0) {
+                                    src = wsrc + (size_t)u * (g.w_unit / 2);
+                                } else {
+                                    if (late_seen != slot) {
+                                        mbar_wait(bar_late + 8 * slot, 0u);
+                                        late_seen = slot;
+                                    }
+                                    src = wlate + (size_t)(u - a.fuse.u0) * (g.w_unit / 2);
+                                }
+                                bulk_load(sa + (uint32_t)(g.w_off + q * g.w_unit), src, (uint32_t)g.w_unit, full);
+                            }
+                        }
                         if (++s == g.nstage) {
                             s = 0;
                             if (primed) ph ^= 1;
@@ -346,6 +478,59 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         float *myred = red + (warp - kRsEpi0) * 2 * Nc;
         int prev_b = -1, k = 0, xo = 2 % L, ntr = 0;  // xo: ring position of the next output row to drain
         const bool tracer = warp == kRsEpi0 && lane == 0;
+        int b_first = 0, b_last = -1;
+        if (a.fuse.on) {
+            // ------------------------------------------------ fused operand preparation (see RsFuse)
+            const RsFuse &fz = a.fuse;
+            float *aff = reinterpret_cast<float *>(smem + g.off_aff);  // scale[kRsAffCh], shift[kRsAffCh]
+            rs_sample_range(a, b_first, b_last);
+            const int chA = fz.u0 * 16, nA = fz.nlate * 16;  // channels of the private units (the last ones may lie past cin: zero)
+            const int scratch_cap = 64 * Nc;
+            if (tracer) rs_trace(a.trace, 2, ntr, 50);
+            for (int bb = b_first; bb <= b_last; ++bb) {
+                const int slot = bb - b_first;
+                for (int i = et; i < nA; i += kRsEpiThreads) {
+                    float2 af = make_float2(0.f, 0.f);
+                    if (chA + i < fz.cin) af = rs_fuse_affine(fz, bb, chA + i);
+                    aff[i] = af.x;
+                    aff[kRsAffCh + i] = af.y;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                __nv_bfloat16 *dstp = fz.priv + ((size_t)blockIdx.x * fz.nslot + slot) * fz.nlate * (size_t)(g.w_unit / 2);
+                for (int h = 0; h < 2 * fz.nlate; ++h)
+                    rs_build_half(fz.w, fz.cin, a.cout, fz.cout_pad, Nc, g.nsp, chA + 8 * h, aff + 8 * h, dstp + (size_t)(h >> 1) * (g.w_unit / 2), et);
+                rs_build_bias(fz.w, fz.cin, a.cout, fz.cout_pad, Nc, fz.c0, fz.cin - fz.c0, aff + kRsAffCh + (fz.c0 - chA), btab_s, scratch_cap,
+                              fz.priv_bias + ((size_t)blockIdx.x * fz.nslot + slot) * 9 * Nc, et);
+                // the producer's bulk copies (async proxy) read what these generic-proxy stores wrote
+                asm volatile("fence.proxy.async;" ::: "memory");
+                mbar_arrive(bar_late + 8 * slot);
+            }
+            if (tracer) rs_trace(a.trace, 2, ntr, 51);
+            // (ii) the late group's slices for the later convs of the block
+            const int nh = (fz.cin - fz.c0 + 7) >> 3, pieces = nh + 1;
+            const int total = fz.njob * a.B * pieces;
+            for (int it = blockIdx.x; it < total; it += gridDim.x) {
+                const int piece = it % pieces;
+                const int r = it / pieces;
+                const int bb = r % a.B;
+                const RsJob &J = fz.job[r / a.B];
+                if (piece < nh) {
+                    const int ch0 = fz.c0 + 8 * piece;
+                    if (et < 8) aff[et] = ch0 + et < fz.cin ? rs_fuse_affine(fz, bb, ch0 + et).x : 0.f;
+                    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                    const size_t junit = (size_t)3 * g.nsp * 2 * 3 * J.Nc * 8;  // elements of one unit of the consumer's image
+                    rs_build_half(J.w, J.cin, J.cout, J.cout_pad, J.Nc, g.nsp, ch0, aff, J.wimg + ((size_t)bb * J.nunit + (ch0 >> 4)) * junit, et);
+                    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                } else {
+                    const int nch = fz.cin - fz.c0;
+                    for (int i = et; i < nch; i += kRsEpiThreads) aff[kRsAffCh + i] = rs_fuse_affine(fz, bb, fz.c0 + i).y;
+                    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                    rs_build_bias(J.w, J.cin, J.cout, J.cout_pad, J.Nc, fz.c0, nch, aff + kRsAffCh, btab_s, scratch_cap,
+                                  J.btab + ((size_t)bb * J.ngroup + J.gidx) * 9 * J.Nc, et);
+                }
+            }
+            if (tracer) rs_trace(a.trace, 2, ntr, 52);
+        }
         RsWalk w = rs_walk(a);
         while (w.next()) {
             const int b = w.b;
@@ -355,9 +540,11 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
                 float *wb = red + 16 * Nc;  // [9][Nc]
                 const float *src = a.btab + (size_t)b * a.nsplit * 9 * Nc;
+                const float *late = a.fuse.on ? a.fuse.priv_bias + ((size_t)blockIdx.x * a.fuse.nslot + (b - b_first)) * 9 * Nc : nullptr;
                 for (int i = et; i < 9 * Nc; i += kRsEpiThreads) {
                     float v = 0.f;
                     for (int sp = 0; sp < a.nsplit; ++sp) v += __ldg(src + (size_t)sp * 9 * Nc + i);
+                    if (late) v += late[i];  // written by this CTA a moment ago: plain load
                     wb[i] = v;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
@@ -644,7 +831,8 @@ bool make_rs_geom(const ConvArgs &a, int split, RsGeom &g) {
     g.L = std::min(512 / g.Nc - 2, 30);
     g.off_btab = kRsFixed;
     g.off_red = g.off_btab + 64 * g.Nc * 4;
-    g.off_stage = rs_round_up(g.off_red + (16 + 9) * g.Nc * 4, 1024);
+    g.off_aff = g.off_red + (16 + 9) * g.Nc * 4;                     // fused mode: (scale, shift) of up to kRsAffCh channels
+    g.off_stage = rs_round_up(g.off_aff + 2 * kRsAffCh * 4, 1024);
     static const int g_env = getenv("MISO_RS_G") ? atoi(getenv("MISO_RS_G")) : 0;
     for (int G = std::min({(g.L - 2) / 2, kRsMaxG, g_env > 0 ? g_env : kRsMaxG}); G >= 1; --G) {
         for (int kper : {2, 1}) {
@@ -728,9 +916,13 @@ void conv_rs_set_trace(long long *d_buf, int cin, int fin) {
 }
 
 int conv_rs_init() {
-    static bool done = false;
+    static bool done_dev[64] = {};  // per device ordinal: function attributes live in the device's context
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    bool &done = done_dev[dev & 63];
     if (done) return MISO_OK;
-    cudaError_t e = cudaFuncSetAttribute(conv_rs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemLimit);
+    e = cudaFuncSetAttribute(conv_rs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_rs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemLimit);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rs_kernel)");
     done = true;
@@ -752,6 +944,61 @@ void conv_rs_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size
     *btab_bytes = (size_t)a.B * ((a.cin + kRsBiasCi - 1) / kRsBiasCi) * 9 * g.Nc * sizeof(float);
 }
 
+namespace {
+long long rs_rows(const ConvArgs &a, const RsGeom &g) { return (long long)a.B * g.Mr * (g.S > 1 ? g.TS : a.T); }
+unsigned rs_grid(const ConvArgs &a, const RsGeom &g) { return (unsigned)std::min<long long>(148, std::max<long long>(1, rs_rows(a, g) / 2)); }
+// samples the row range of one CTA can touch
+int rs_slots(const ConvArgs &a, const RsGeom &g) {
+    const long long R = rs_rows(a, g), per = g.Mr * (long long)(g.S > 1 ? g.TS : a.T);
+    const long long len = (R + rs_grid(a, g) - 1) / rs_grid(a, g);
+    return (int)((len + per - 2) / per + 1);
+}
+
+int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16 *wimg, const float *btab, int nsplit, const RsFuse &fuse,
+              cudaStream_t stream) {
+    CUtensorMap tm_hi, tm_lo;
+    int rc = rs_encode_maps(a, g, &tm_hi, &tm_lo);
+    if (rc) return rc;
+    rc = conv_rs_init();
+    if (rc) return rc;
+    RsArgs k{};
+    k.g = g;
+    k.wimg = wimg;
+    k.wimg_bstride = (size_t)g.nunit * (g.w_unit / 2);
+    k.btab = btab;
+    k.bias = a.bias;
+    k.nsplit = nsplit;
+    k.out = a.out;
+    k.out_sums = a.out_sums;
+    k.B = a.B;
+    k.T = a.T;
+    k.F = a.Fin;
+    k.in_coff = a.in_coff;
+    k.out_ctot = a.out_ctot;
+    k.out_coff = a.out_coff;
+    k.cout = a.cout;
+    k.out_lo_off = a.out_lo_off;
+    k.use_lo = a.use_lo;
+    k.elu = a.elu;
+    k.trace = (g_rs_trace && a.cin == g_rs_trace_cin && a.Fin == g_rs_trace_fin) ? g_rs_trace : nullptr;
+    k.fuse = fuse;
+    dim3 grid(rs_grid(a, g), 1, 1);
+    prof_begin(stream);
+    if (split == 3)
+        MISO_CUDA(launch_pdl(conv_rs_kernel<3>, grid, dim3(kRsThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
+    else
+        MISO_CUDA(launch_pdl(conv_rs_kernel<1>, grid, dim3(kRsThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
+    {
+        const double pix = (double)a.B * a.T * a.Fout;
+        const double flops = 2.0 * pix * a.cin * a.cout * 9;
+        const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
+        prof_end(stream, flops, bytes, MISO_PROF_CONV_RS);
+    }
+    MISO_LAUNCHED("conv_rs_kernel");
+    return MISO_OK;
+}
+}  // namespace
+
 int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream) {
     RsGeom g;
     MISO_REQUIRE(make_rs_geom(a, split, g), "conv_rs: layer does not fit the row-streaming path (cin=%d cout=%d F=%d)", a.cin, a.cout, a.Fin);
@@ -766,10 +1013,7 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     if (debug)
         fprintf(stderr, "conv_rs: cin=%d cout=%d F=%d | S=%d Nc=%d L=%d G=%d Mr=%d pitch=%d kper=%d nchunk=%d nstage=%d stage=%dB tmem=%d smem=%d\n", a.cin,
                 a.cout, a.Fin, g.S, g.Nc, g.L, g.G, g.Mr, g.pitch, g.kper, g.nchunk, g.nstage, g.stage, g.tmem_cols, g.smem_total);
-    CUtensorMap tm_hi, tm_lo;
-    int rc = rs_encode_maps(a, g, &tm_hi, &tm_lo);
-    if (rc) return rc;
-    rc = conv_rs_init();
+    int rc = conv_rs_init();
     if (rc) return rc;
 
     RsPrepArgs p{};
@@ -795,42 +1039,70 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_rs_prep_kernel, dim3(a.B * g.nunit + a.B * nsplit), dim3(256), prep_smem, stream, p));
     prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_rs_prep_kernel");
-    prof_begin(stream);
+    RsFuse none{};
+    return rs_launch(a, split, g, p.wimg, p.btab, nsplit, none, stream);
+}
 
-    RsArgs k{};
-    k.g = g;
-    k.wimg = p.wimg;
-    k.wimg_bstride = (size_t)g.nunit * (g.w_unit / 2);
-    k.btab = p.btab;
-    k.bias = a.bias;
-    k.nsplit = nsplit;
-    k.out = a.out;
-    k.out_sums = a.out_sums;
-    k.B = a.B;
-    k.T = a.T;
-    k.F = a.Fin;
-    k.in_coff = a.in_coff;
-    k.out_ctot = a.out_ctot;
-    k.out_coff = a.out_coff;
-    k.cout = a.cout;
-    k.out_lo_off = a.out_lo_off;
-    k.use_lo = a.use_lo;
-    k.elu = a.elu;
-    k.trace = (g_rs_trace && a.cin == g_rs_trace_cin && a.Fin == g_rs_trace_fin) ? g_rs_trace : nullptr;
-    const long long rows = (long long)a.B * g.Mr * (g.S > 1 ? g.TS : a.T);
-    dim3 grid((unsigned)std::min<long long>(148, std::max<long long>(1, rows / 2)), 1, 1);
-    if (split == 3)
-        MISO_CUDA(launch_pdl(conv_rs_kernel<3>, grid, dim3(kRsThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
-    else
-        MISO_CUDA(launch_pdl(conv_rs_kernel<1>, grid, dim3(kRsThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
-    {
-        const double pix = (double)a.B * a.T * a.Fout;
-        const double flops = 2.0 * pix * a.cin * a.cout * 9;
-        const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
-        prof_end(stream, flops, bytes, MISO_PROF_CONV_RS);
+// ---- fused mode (forward DenseBlock convs): sizes of the per-layer persistent buffers and the launch
+bool conv_rs_dense_need(const ConvArgs &a, int split, int c0, RsDenseNeed *need) {
+    static const bool off = getenv("MISO_RS_FUSE") && atoi(getenv("MISO_RS_FUSE")) == 0;
+    RsGeom g;
+    if (off || !conv_rs_eligible(a, split) || !make_rs_geom(a, split, g)) return false;
+    if (a.norm_mode != NORM_IN || c0 % 8 || c0 < 0 || c0 >= a.cin) return false;
+    const int u0 = c0 / 16, nlate = g.nunit - u0;
+    if (nlate * 16 > kRsAffCh || a.cin - c0 > kRsAffCh) return false;
+    const int nslot = rs_slots(a, g);
+    if (nslot > kRsMaxSlots) return false;
+    if (need) {
+        need->wimg = align_up((size_t)a.B * g.nunit * g.w_unit, 256);
+        need->btab_per_group = (size_t)a.B * 9 * g.Nc * sizeof(float);
+        need->priv = align_up((size_t)rs_grid(a, g) * nslot * nlate * g.w_unit, 256) + align_up((size_t)rs_grid(a, g) * nslot * 9 * g.Nc * sizeof(float), 256);
     }
-    MISO_LAUNCHED("conv_rs_kernel");
-    return MISO_OK;
+    return true;
+}
+
+int launch_conv_rs_dense(const ConvArgs &a, int split, const RsDense &d, cudaStream_t stream) {
+    RsGeom g;
+    RsDenseNeed need;
+    MISO_REQUIRE(make_rs_geom(a, split, g) && conv_rs_dense_need(a, split, d.c0, &need), "conv_rs: layer does not fit the fused row-streaming path (cin=%d cout=%d F=%d c0=%d)",
+                 a.cin, a.cout, a.Fin, d.c0);
+    MISO_REQUIRE(d.njob <= kRsMaxJobs, "conv_rs: too many jobs");
+    RsFuse f{};
+    f.on = 1;
+    f.c0 = d.c0;
+    f.u0 = d.c0 / 16;
+    f.nlate = g.nunit - f.u0;
+    f.nslot = rs_slots(a, g);
+    const unsigned grid = rs_grid(a, g);
+    f.priv = reinterpret_cast<__nv_bfloat16 *>(d.priv);
+    f.priv_bias = reinterpret_cast<float *>(reinterpret_cast<char *>(d.priv) + align_up((size_t)grid * f.nslot * f.nlate * g.w_unit, 256));
+    f.w = a.w;
+    f.in_sums = a.in_sums + (size_t)a.in_coff * 2;
+    f.in_ctot = a.in_ctot;
+    f.cin = a.cin;
+    f.cout_pad = a.cout_pad;
+    f.inv_n = a.norm_inv_n;
+    f.eps = a.norm_eps;
+    f.njob = d.njob;
+    for (int j = 0; j < d.njob; ++j) {
+        const RsDenseJob &s = d.job[j];
+        RsJob &t = f.job[j];
+        t.w = s.w;
+        t.wimg = reinterpret_cast<__nv_bfloat16 *>(s.wimg);
+        t.btab = s.btab;
+        t.cin = s.cin;
+        t.cout = s.cout;
+        t.cout_pad = s.cout_pad;
+        t.Nc = rs_round_up(s.cout, 16);
+        t.nunit = ((s.cin + 7) / 8 + 1) / 2;
+        t.ngroup = s.ngroup;
+        t.gidx = s.gidx;
+    }
+    static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "conv_rs fused: cin=%d cout=%d F=%d c0=%d | u0=%d nlate=%d nslot=%d njob=%d early groups=%d G=%d nstage=%d smem=%d\n", a.cin, a.cout,
+                a.Fin, d.c0, f.u0, f.nlate, f.nslot, f.njob, d.ngroup_early, g.G, g.nstage, g.smem_total);
+    return rs_launch(a, split, g, reinterpret_cast<const __nv_bfloat16 *>(d.wimg), d.btab, d.ngroup_early, f, stream);
 }
 
 }  // namespace miso

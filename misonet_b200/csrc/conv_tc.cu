@@ -499,9 +499,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                 }
                             } else {
                                 float *o = out_cl + (size_t)pix * a.out_ctot + co_base + cb;
+                                if (((a.out_ctot | a.out_coff | a.cout) & 3) == 0) {
 #pragma unroll
-                                for (int q = 0; q < 16; q += 4)
-                                    if (co_base + cb + q + 4 <= a.cout) *reinterpret_cast<float4 *>(o + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+                                    for (int q = 0; q < 16; q += 4)
+                                        if (co_base + cb + q + 4 <= a.cout) *reinterpret_cast<float4 *>(o + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+                                } else {  // 2-channel outputs (MISO_3's last deconv, model.py:347): 8-byte stores
+#pragma unroll
+                                    for (int q = 0; q < 16; q += 2)
+                                        if (co_base + cb + q + 2 <= a.cout) *reinterpret_cast<float2 *>(o + q) = make_float2(y[q], y[q + 1]);
+                                }
                             }
                         }
                     }
@@ -910,9 +916,14 @@ void conv_tc_set_trace(long long *d_buf, int cin, int fin) {
 
 // one-time, capture-unsafe setup (function attributes, driver entry point); called before graph capture
 int conv_tc_init() {
-    static bool done = false;
+    // function attributes live in the device's context: track the opt-in per device ordinal
+    static bool done_dev[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    bool &done = done_dev[dev & 63];
     if (done) return MISO_OK;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    e = cudaFuncSetAttribute(conv_tc_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -934,7 +945,7 @@ bool conv_tc_eligible(const ConvArgs &a) {
     if (a.stride_f == 2 && a.pad_f != 0) return false;
     if (a.in_layout != LAYOUT_PLANES || a.in_ctot % 8 || a.in_coff % 8) return false;
     if (a.out_layout == LAYOUT_PLANES && (a.out_ctot % 8 || a.out_coff % 8 || a.cout % 8)) return false;
-    if (a.out_layout == LAYOUT_CL_F32 && (a.cout % 4 || a.out_ctot % 4 || a.out_coff % 4)) return false;
+    if (a.out_layout == LAYOUT_CL_F32 && (a.cout % 2 || a.out_ctot % 2 || a.out_coff % 2)) return false;  // float4 / float2 stores
     if (a.resid && (a.resid_ctot % 4 || a.resid_coff % 4)) return false;
     TcGeom g;
     return make_geom(a, 3, g);

@@ -458,6 +458,8 @@ struct Plan {
     double *stats_base = nullptr;
     size_t stats_bytes = 0;
     TcScratch scratch{};
+    char *dense = nullptr;  // fused DenseBlock convs: per-layer persistent weight images / border-bias sums, then the private scratch
+    size_t dense_bytes = 0, dense_priv = 0;
     size_t total = 0;
 };
 
@@ -605,7 +607,7 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
 }
 
 // tensor-core scratch (per-sample weight images, border-bias tables) goes after the activations
-void plan_scratch(Plan &pl, char *base, size_t need_w, size_t need_b) {
+void plan_scratch(Plan &pl, char *base, size_t need_w, size_t need_b, size_t need_d, size_t need_p) {
     size_t off = pl.total;
     pl.scratch.wimg = base ? base + off : nullptr;
     pl.scratch.wimg_bytes = need_w;
@@ -613,6 +615,10 @@ void plan_scratch(Plan &pl, char *base, size_t need_w, size_t need_b) {
     pl.scratch.btab = base ? reinterpret_cast<float *>(base + off) : nullptr;
     pl.scratch.btab_bytes = need_b;
     off += align_up(need_b, 256);
+    pl.dense = base ? base + off : nullptr;
+    pl.dense_bytes = align_up(need_d, 256);
+    pl.dense_priv = align_up(need_p, 256);
+    off += pl.dense_bytes + pl.dense_priv;
     pl.total = off;
 }
 
@@ -647,9 +653,11 @@ struct Walker {
     size_t need_w = 0, need_b = 0;
     std::vector<ConvRec> *record = nullptr;  // non-null: list the layers instead of launching them
 
-    int conv(const ConvDesc &cd, bool transposed, const BufDesc *inb, const void *in_raw, int in_ctot, int in_coff, int Fin,
-             const double *in_sums, const BufDesc *outb, float *out_raw, int out_ctot, int out_coff, int Fout, double *out_sums,
-             int stride_f, int pad_f, bool elu) {
+    size_t need_d = 0, need_p = 0, dense_off = 0;  // fused DenseBlock convs: persistent bytes (running offset) and private scratch (max)
+
+    ConvArgs make_args(const ConvDesc &cd, bool transposed, const BufDesc *inb, const void *in_raw, int in_ctot, int in_coff, int Fin,
+                       const double *in_sums, const BufDesc *outb, float *out_raw, int out_ctot, int out_coff, int Fout, double *out_sums,
+                       int stride_f, int pad_f, bool elu) const {
         ConvArgs a{};
         a.in = inb ? inb->p : in_raw;
         a.in_layout = LAYOUT_PLANES;
@@ -684,6 +692,10 @@ struct Walker {
         a.norm_eps = kInEps;
         a.norm_inv_n = 1.0 / ((double)T * Fin);
         a.elu = elu ? 1 : 0;
+        return a;
+    }
+
+    int dispatch(const ConvArgs &a, const ConvDesc &cd, const BufDesc *inb, const BufDesc *outb) {
         if (record) {
             record->push_back(ConvRec{0, a, &cd, inb ? inb->grad : nullptr, outb ? outb->grad : nullptr, inb != nullptr});
             return MISO_OK;
@@ -700,6 +712,91 @@ struct Walker {
         }
         if (n->mode != 0 && tc) return launch_conv_tc(a, n->mode == 1 ? 3 : 1, pl.scratch, st);
         return launch_conv_fp32(a, st);
+    }
+
+    int conv(const ConvDesc &cd, bool transposed, const BufDesc *inb, const void *in_raw, int in_ctot, int in_coff, int Fin,
+             const double *in_sums, const BufDesc *outb, float *out_raw, int out_ctot, int out_coff, int Fout, double *out_sums,
+             int stride_f, int pad_f, bool elu) {
+        return dispatch(make_args(cd, transposed, inb, in_raw, in_ctot, in_coff, Fin, in_sums, outb, out_raw, out_ctot, out_coff, Fout,
+                                  out_sums, stride_f, pad_f, elu),
+                        cd, inb, outb);
+    }
+
+    // The five convs of a DenseBlock (model.py:437-482) over the block buffer [x | y0 | y1 | y2 | y3]: conv k reads the first
+    // c + (k - 1) g1 channels and writes g1 channels behind them; conv 5 writes its g2 channels to out5 at out5_coff.
+    // Tensor-core modes run them with the operand preparation fused into the kernels (conv_rs.cu, RsFuse) when the first
+    // four convs fit the row-streaming path: conv k then owns a persistent weight image / border-bias buffer in pl.dense.
+    int dense(const std::vector<ConvDesc> &cds, const BufDesc &buf, int c, int g1, const BufDesc &out5, int out5_coff) {
+        ConvArgs a[5];
+        for (int k = 1; k <= 5; ++k) {
+            if (k < 5)
+                a[k - 1] = make_args(cds[k - 1], false, &buf, nullptr, buf.ctot, 0, buf.F, buf.sums, &buf, nullptr, buf.ctot, c + (k - 1) * g1, buf.F,
+                                     buf.sums, 1, 1, true);
+            else
+                a[k - 1] = make_args(cds[k - 1], false, &buf, nullptr, buf.ctot, 0, buf.F, buf.sums, &out5, nullptr, out5.ctot, out5_coff, buf.F,
+                                     out5.sums, 1, 1, true);
+        }
+        const int split = n->mode == 2 ? 1 : 3;
+        bool fused[5];
+        RsDenseNeed need[5];
+        int c0[5];
+        bool all4 = !record;
+        for (int k = 1; k <= 5; ++k) {
+            c0[k - 1] = k == 1 ? 0 : c + (k - 2) * g1;
+            // sized for the bf16x3 images (the plan does not depend on the mode); the launch re-checks the actual split
+            fused[k - 1] = !record && conv_rs_dense_need(a[k - 1], 3, c0[k - 1], &need[k - 1]) &&
+                           (split == 3 || conv_rs_dense_need(a[k - 1], split, c0[k - 1], nullptr));
+            if (k < 5 && !fused[k - 1]) all4 = false;
+        }
+        if (!all4)
+            for (int k = 0; k < 5; ++k) fused[k] = false;
+        char *wimg[5] = {};
+        float *btab[5] = {};
+        for (int k = 1; k <= 5; ++k) {
+            if (!fused[k - 1]) continue;
+            const size_t bt = align_up(need[k - 1].btab_per_group * (size_t)(k - 1), 256);
+            if (!dry) {
+                wimg[k - 1] = pl.dense + dense_off;
+                btab[k - 1] = reinterpret_cast<float *>(pl.dense + dense_off + need[k - 1].wimg);
+            }
+            dense_off += need[k - 1].wimg + bt;
+            need_d = std::max(need_d, dense_off);
+            need_p = std::max(need_p, need[k - 1].priv);
+        }
+        for (int k = 1; k <= 5; ++k) {
+            const BufDesc *outb = k < 5 ? &buf : &out5;
+            int rc;
+            if (fused[k - 1] && !dry && n->mode != 0) {
+                if (dense_off > pl.dense_bytes || need[k - 1].priv > pl.dense_priv) {
+                    set_error("dense block: fused-preparation buffers exceed the plan (%zu > %zu)", dense_off, pl.dense_bytes);
+                    return MISO_E_WORKSPACE;
+                }
+                RsDense d{};
+                d.c0 = c0[k - 1];
+                d.wimg = wimg[k - 1];
+                d.btab = btab[k - 1];
+                d.ngroup_early = k - 1;
+                d.priv = pl.dense + pl.dense_bytes;
+                d.njob = 0;
+                for (int j = k + 1; j <= 5; ++j) {
+                    if (!fused[j - 1]) continue;
+                    RsDenseJob &jb = d.job[d.njob++];
+                    jb.w = a[j - 1].w;
+                    jb.wimg = wimg[j - 1];
+                    jb.btab = btab[j - 1];
+                    jb.cin = a[j - 1].cin;
+                    jb.cout = a[j - 1].cout;
+                    jb.cout_pad = a[j - 1].cout_pad;
+                    jb.ngroup = j - 1;
+                    jb.gidx = k - 1;
+                }
+                rc = launch_conv_rs_dense(a[k - 1], split, d, st);
+            } else {
+                rc = dispatch(a[k - 1], cds[k - 1], &buf, outb);
+            }
+            if (rc) return rc;
+        }
+        return MISO_OK;
     }
 
     int run(const void *d_x, float *d_y);
@@ -735,16 +832,8 @@ int Walker::run(const void *d_x, float *d_y) {
                       i == 0 ? nullptr : e.sums, stride, 0, i != 0);
             if (rc) return rc;
             const int c = n->en[i + 1];
-            for (int k = 1; k <= 5; ++k) {
-                const ConvDesc &cd = n->enc_dense[i][k - 1];
-                if (k < 5)
-                    rc = conv(cd, false, &e, nullptr, e.ctot, 0, e.F, e.sums, &e, nullptr, e.ctot, c + (k - 1) * c, e.F, e.sums, 1, 1,
-                              true);
-                else
-                    rc = conv(cd, false, &e, nullptr, e.ctot, 0, e.F, e.sums, xo.buf, nullptr, xo.buf->ctot, xo.coff, e.F,
-                              xo.buf->sums, 1, 1, true);
-                if (rc) return rc;
-            }
+            rc = dense(n->enc_dense[i], e, c, c, *xo.buf, xo.coff);
+            if (rc) return rc;
         } else {
             rc = conv(n->enc_conv[i], false, inb, d_x, in_ctot, in_coff, Fin, in_sums, xo.buf, nullptr, xo.buf->ctot, xo.coff,
                       xo.buf->F, xo.buf->sums, stride, 0, true);
@@ -894,15 +983,8 @@ int Walker::run(const void *d_x, float *d_y) {
         if (dense_dec(j)) {
             const int c = 2 * n->de[j], g1 = n->de[j];
             const BufDesc &y = pl.Y[j];
-            for (int k = 1; k <= 5; ++k) {
-                const ConvDesc &cd = n->dec_dense[j][k - 1];
-                if (k < 5)
-                    rc = conv(cd, false, &d, nullptr, d.ctot, 0, d.F, d.sums, &d, nullptr, d.ctot, c + (k - 1) * g1, d.F, d.sums, 1, 1,
-                              true);
-                else
-                    rc = conv(cd, false, &d, nullptr, d.ctot, 0, d.F, d.sums, &y, nullptr, y.ctot, 0, y.F, y.sums, 1, 1, true);
-                if (rc) return rc;
-            }
+            rc = dense(n->dec_dense[j], d, c, g1, y, 0);
+            if (rc) return rc;
             rc = conv(n->dec_deconv[j], true, &y, nullptr, y.ctot, 0, y.F, y.sums, outb, d_y, out_ctot, 0, Fout, out_sums, stride, 0,
                       !last);
         } else {
@@ -1048,7 +1130,7 @@ bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
             }
         }
     }
-    plan_scratch(pl, base, w.need_w, w.need_b);
+    plan_scratch(pl, base, w.need_w, w.need_b, w.need_d, w.need_p);
     return true;
 }
 

@@ -328,9 +328,13 @@ void tcn_pw_scratch_need(int C, int nconv, size_t *wimg_bytes, size_t *wvec_byte
 }
 
 int tcn_pw_init() {
-    static bool done = false;
+    static bool done_dev[64] = {};  // per device ordinal: function attributes live in the device's context
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    bool &done = done_dev[dev & 63];
     if (done) return MISO_OK;
-    cudaError_t e = cudaFuncSetAttribute(tcn_pw_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwSmemLimit);
+    e = cudaFuncSetAttribute(tcn_pw_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tcn_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPwSmemLimit);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tcn_pw_kernel)");
     done = true;

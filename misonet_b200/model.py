@@ -205,7 +205,11 @@ class _MisoNet(nn.Module):
         self.max_workspace_bytes = 48 << 30   # batches are processed in chunks that fit this
         # compute path of the stride-1 3x3 convs (include/misonet_b200.h, miso_net_set_mode):
         # "fp32" FMA | "bf16x3" tcgen05 split (fp32-grade) | "bf16" tcgen05 (throughput)
-        self.conv_mode = "fp32"
+        # Default = the parity-grade tensor-core path bench.py measures; "fp32" is the 10x slower FMA reference path.
+        self.conv_mode = "bf16x3"
+        # eval-mode forwards never take the (activation-retaining, un-graphed) training path, even outside
+        # torch.no_grad(); set True to differentiate through a module in eval() mode
+        self.autograd_in_eval = False
 
     # ---- handle / weights ------------------------------------------------------------
     def _release(self):
@@ -226,6 +230,22 @@ class _MisoNet(nn.Module):
 
     def _device(self):
         return next(self.parameters()).device
+
+    def invalidate(self):
+        """Forget what has been packed: the next forward re-uploads every parameter.  Needed after writes the change
+        detection cannot see (``p.data.copy_()`` / ``.data.fill_()`` do not bump ``p._version``); ``load_state_dict`` and
+        ``.to()`` / ``.cuda()`` call it themselves, and a replaced Parameter object is detected by identity."""
+        self._packed = {}
+        self._sync_tag = None
+        self.__dict__.pop("_plist", None)
+
+    def load_state_dict(self, *a, **k):
+        self.invalidate()
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
 
     def _ensure_handle(self):
         dev = self._device()
@@ -260,11 +280,15 @@ class _MisoNet(nn.Module):
         _lib.check(lib.miso_net_set_graph(self._handle, 1 if self.use_graph else 0), "miso_net_set_graph")
         # cheap change detection first: in-place updates bump _version, .cuda()/.to()/load_state_dict(assign) change storage
         params = self._param_list
-        tag = (sum(p._version for p in params), params[0].data_ptr(), params[-1].data_ptr())
+        tag = (sum(p._version for p in params), sum(p.data_ptr() for p in params))
         if tag == self._sync_tag:
             return
+        named = list(self.named_parameters())
+        if len(named) != len(params) or any(a is not b for (_, a), b in zip(named, params)):   # a Parameter was replaced
+            self.__dict__["_plist"] = params = [p for _, p in named]
+            tag = (sum(p._version for p in params), sum(p.data_ptr() for p in params))
         self._sync_tag = tag
-        for key, p in self.named_parameters():
+        for key, p in named:
             tag = (p.data_ptr(), p._version)
             if self._packed.get(key) == tag:
                 continue
@@ -313,7 +337,12 @@ class _MisoNet(nn.Module):
             _lib.check(lib.miso_net_check_shape(self._handle, T, F), "miso_net_check_shape")
             self._bufs[("shape_ok", T, F)] = True
         per = self._ws_bytes(1, T, F)
-        return max(1, min(B, int(self.max_workspace_bytes // max(per, 1))))
+        step = max(1, min(B, int(self.max_workspace_bytes // max(per, 1))))
+        if 1 < step < B:
+            # a sample's input planes are 64 * T * F bytes: an odd T * F makes every odd sample start 64-byte aligned
+            # only, and miso_net_forward wants 128
+            step -= step % 2
+        return step
 
     def _input_planes(self, B, T, F, dev, train=False):
         """Input buffer in the library's plane layout (include/misonet_b200.h): uint8 [B, bytes per sample].
@@ -338,8 +367,11 @@ class _MisoNet(nn.Module):
         return y_cl
 
     def _training_pass(self):
-        """True when this forward must be differentiable (autograd on and a parameter requires grad)."""
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list)
+        """True when this forward must be differentiable: autograd on, a parameter requires grad, and the module is in
+        training mode (or ``autograd_in_eval``).  ``model.eval(); model(x)`` outside ``no_grad`` therefore stays on the
+        graph-replayed inference path instead of silently allocating the training workspace."""
+        return (torch.is_grad_enabled() and (self.training or self.autograd_in_eval)
+                and any(p.requires_grad for p in self._param_list))
 
     def _run_body_train(self, x_cl, B, T, F):
         """Training forward: x_cl input planes -> float32 [B,T,F,out_ch]; leaves the workspace for the backward."""
@@ -380,8 +412,9 @@ class _MisoNet(nn.Module):
         """Parity/debug: an internal activation of the last forward as the reference sees it (NCHW)."""
         lib = _lib.load()
         cap = B * T * F * 6 * max(self._en + self._de)
-        buf = torch.empty(cap, dtype=torch.float32, device=self._handle_device)
-        n = lib.miso_net_tap(self._handle, name.encode(), _lib.ptr(buf), cap, B, T, F, _lib.ptr(self._ws), _lib.stream_ptr())
+        with torch.cuda.device(self._handle_device):
+            buf = torch.empty(cap, dtype=torch.float32, device=self._handle_device)
+            n = lib.miso_net_tap(self._handle, name.encode(), _lib.ptr(buf), cap, B, T, F, _lib.ptr(self._ws), _lib.stream_ptr())
         _lib.check(n, "miso_net_tap")
         return buf[:n]
 
@@ -404,17 +437,20 @@ class MISO_1(_MisoNet):
         B, M, T, F = mix.shape
         if 2 * M != self._in_ch:
             raise ValueError(f"expected {self._in_ch // 2} microphones, got {M}")
-        self._sync_params()
-        n = len(shifts)
-        train = self._training_pass()
-        x_cl = self._input_planes(n * B, T, F, mix.device, train)
-        arr = (ctypes.c_int * n)(*[int(s) for s in shifts])
-        _lib.check(_lib.load().miso_pack_miso1(_lib.ptr(mix), _lib.ptr(x_cl), B, M, T, F, arr, n, _lib.stream_ptr()),
-                   "miso_pack_miso1")
-        if train:
-            return _NetFunction.apply(self, x_cl, n * B, T, F, *self._param_list)
-        y_cl = self._run_body(x_cl, n * B, T, F)
-        return self._unpack(y_cl, n * B, T, F)
+        # every launch below goes to the MODULE's device and that device's current stream, whatever the caller's
+        # current device is (the reference does model.cuda(gpu_num) without torch.cuda.set_device, run.py:68)
+        with torch.cuda.device(self._handle_device):
+            self._sync_params()
+            n = len(shifts)
+            train = self._training_pass()
+            x_cl = self._input_planes(n * B, T, F, mix.device, train)
+            arr = (ctypes.c_int * n)(*[int(s) for s in shifts])
+            _lib.check(_lib.load().miso_pack_miso1(_lib.ptr(mix), _lib.ptr(x_cl), B, M, T, F, arr, n, _lib.stream_ptr()),
+                       "miso_pack_miso1")
+            if train:
+                return _NetFunction.apply(self, x_cl, n * B, T, F, *self._param_list)
+            y_cl = self._run_body(x_cl, n * B, T, F)
+            return self._unpack(y_cl, n * B, T, F)
 
 
 class MISO_3(_MisoNet):
@@ -436,14 +472,15 @@ class MISO_3(_MisoNet):
             raise ValueError(f"expected {self._in_ch // 2 - 2} microphones, got {M}")
         if second.shape != (B, 1, T, F) or third.shape != (B, 1, T, F):
             raise ValueError("second/third inputs must be [B,1,T,F]")
-        self._sync_params()
-        train = self._training_pass()
-        x_cl = self._input_planes(B, T, F, mix.device, train)
-        _lib.check(_lib.load().miso_pack_miso3(_lib.ptr(mix), _lib.ptr(second), _lib.ptr(third), _lib.ptr(x_cl), B, M, T, F,
-                                               _lib.stream_ptr()), "miso_pack_miso3")
-        if train:
-            # trainer.py:398-414: the beamformed / MISO1 inputs are data (computed under no_grad or loaded from
-            # disk, data.py:133-207), so only the parameters receive gradients
-            return _NetFunction.apply(self, x_cl, B, T, F, *self._param_list)
-        y_cl = self._run_body(x_cl, B, T, F)
-        return self._unpack(y_cl, B, T, F)
+        with torch.cuda.device(self._handle_device):     # see MISO_1.forward_shifts
+            self._sync_params()
+            train = self._training_pass()
+            x_cl = self._input_planes(B, T, F, mix.device, train)
+            _lib.check(_lib.load().miso_pack_miso3(_lib.ptr(mix), _lib.ptr(second), _lib.ptr(third), _lib.ptr(x_cl), B, M, T, F,
+                                                   _lib.stream_ptr()), "miso_pack_miso3")
+            if train:
+                # trainer.py:398-414: the beamformed / MISO1 inputs are data (computed under no_grad or loaded from
+                # disk, data.py:133-207), so only the parameters receive gradients
+                return _NetFunction.apply(self, x_cl, B, T, F, *self._param_list)
+            y_cl = self._run_body(x_cl, B, T, F)
+            return self._unpack(y_cl, B, T, F)

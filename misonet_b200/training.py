@@ -25,13 +25,18 @@ def train_step(model, optimizer, mix_stft, ref_stft, ref_ch=0, max_norm=None, tr
     (the clean source images; trainer.py:160-166 takes microphone ``ref_ch``).  Returns the loss (float32 CUDA scalar,
     detached).  With ``training=False`` this is the validation pass of trainer.py:138-144 (no_grad, no update)."""
     num_spks = model.num_spks
-    mix = torch.roll(mix_stft, -ref_ch, dims=1)                                  # trainer.py:154
+    if hasattr(model, "forward_shifts"):
+        # trainer.py:154 rolls the reference microphone to the front; the library's pack kernel applies the circular
+        # shift while it writes the input planes, so no rolled copy of the mixture is made
+        mix, net = mix_stft, (lambda x: model.forward_shifts(x, (ref_ch,)))
+    else:
+        mix, net = torch.roll(mix_stft, -ref_ch, dims=1), model
     refs = [r[:, ref_ch] if r.dim() == 4 else r for r in ref_stft]               # trainer.py:162-166
     if not training:
         with torch.no_grad():
-            return criterion.loss_uPIT(num_spks, model(mix), refs)
+            return criterion.loss_uPIT(num_spks, net(mix), refs)
     optimizer.zero_grad(set_to_none=True)
-    estimate = model(mix)                                                        # trainer.py:158
+    estimate = net(mix)                                                          # trainer.py:158
     if estimate.shape[1] != num_spks:
         raise ValueError("[ERROR] please check the number of speakers")          # trainer.py:169
     loss = criterion.loss_uPIT(num_spks, estimate, refs)                         # trainer.py:172

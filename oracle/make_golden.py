@@ -102,6 +102,74 @@ def golden_net():
         np.savez_compressed(os.path.join(OUT, f"net_ref_{kind}.npz"), **out)
 
 
+def load_paper_reference_model():
+    """The PAPER-layout oracle of SURVEY.md section 8(c): a TEMPORARY patched copy of the reference's model.py (never
+    written into this repository) in which the three hard-codes that pin the shipped file to 7 blocks are generalised --
+    the TCN width 128 (model.py:31 / :305) -> 384 and the two ``block_idx == 6`` tests (model.py:49,62 / :323,336) ->
+    ``== 7``.  Everything else is the reference's own code."""
+    import importlib.util
+    import tempfile
+    src = open(os.path.join(ref_import.REFERENCE_ROOT, "model.py")).read()
+    n_tcn = src.count("TemporalConvNet(2,7,128,128,128,norm_type)")
+    n_blk = src.count("block_idx == 6")
+    assert n_tcn == 3 and n_blk == 6, "reference model.py is not the surveyed revision"
+    src = src.replace("TemporalConvNet(2,7,128,128,128,norm_type)", "TemporalConvNet(2,7,384,384,384,norm_type)")
+    src = src.replace("block_idx == 6", "block_idx == 7")
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "model_paper.py")
+        with open(path, "w") as f:
+            f.write(src)
+        spec = importlib.util.spec_from_file_location("_miso_reference_model_paper", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    return mod
+
+
+def golden_net_paper():
+    """MISO_1 and MISO_3 in the PAPER layout (8 blocks, 257 bins, TCN width 384) from the patched reference copy."""
+    ref_model = load_paper_reference_model()
+    en, de = LAYOUTS["PAPER"]
+    out = {}
+    for kind, wseed in (("miso1", 3), ("miso3", 4)):
+        if kind == "miso1":
+            cfg = NetConfig.miso1(2, 6, "PAPER")
+            mod = ref_model.MISO_1(2, 6, len(en), list(en), list(de), "IN")
+        else:
+            cfg = NetConfig.miso3(1, 6, "PAPER")
+            mod = ref_model.MISO_3(1, 6, len(en), list(en), list(de), "IN")
+        sd = weights.make_state_dict(cfg, wseed)
+        res = mod.load_state_dict(sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        assert list(mod.state_dict().keys()) == list(sd.keys()), "key order differs from the reference"
+        mod.eval()
+        taps = {}
+        hooks = []
+        for name, sub in [("enc0", mod.encoders[0]), ("enc4", mod.encoders[4]), ("enc7", mod.encoders[7]), ("tcn", mod.TCN),
+                          ("dec0", mod.decoders[0]), ("dec2", mod.decoders[2])]:
+            hooks.append(sub.register_forward_hook(lambda m, i, o, name=name: taps.__setitem__(name, o.detach().numpy().copy())))
+        b, t = 2, 9
+        mix = synth.random_spec(31, (b, 6, t, 257))
+        with torch.no_grad():
+            if kind == "miso1":
+                y = mod(torch.from_numpy(mix))
+            else:
+                a2 = synth.random_spec(32, (b, 1, t, 257))
+                a3 = synth.random_spec(33, (b, 1, t, 257))
+                y = mod(torch.from_numpy(mix), torch.from_numpy(a2), torch.from_numpy(a3))
+        for h in hooks:
+            h.remove()
+        out[f"{kind}_y"] = y.numpy()
+        out[f"{kind}_enc0_sub"] = taps["enc0"].reshape((b,) + taps["enc0"].shape[-3:])[:, :, ::3, ::17]
+        out[f"{kind}_enc4"] = taps["enc4"].reshape((b,) + taps["enc4"].shape[-3:])
+        out[f"{kind}_enc7"] = taps["enc7"].reshape((b,) + taps["enc7"].shape[-3:])
+        out[f"{kind}_tcn"] = taps["tcn"].reshape((b,) + taps["tcn"].shape[-2:])
+        out[f"{kind}_dec0"] = taps["dec0"]
+        out[f"{kind}_dec2"] = taps["dec2"]
+        out[f"{kind}_weights_digest"] = np.array(weights.state_dict_digest(sd))
+        out[f"{kind}_n_params"] = np.array(sum(p.numel() for p in mod.parameters()))
+    np.savez_compressed(os.path.join(OUT, "net_ref_paper.npz"), **out)
+
+
 def golden_mvdr():
     t = ref_import.make_tester()
     out = {}
@@ -200,6 +268,7 @@ def main():
     golden_mvdr()
     golden_losses()
     golden_net()
+    golden_net_paper()
     golden_inference()
     golden_training()
     for fn in sorted(os.listdir(OUT)):

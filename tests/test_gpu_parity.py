@@ -105,11 +105,15 @@ def test_stft_oracle_batched_full_size():
 
 
 # ------------------------------------------------------------------------------- N1/N2 nets
+@pytest.mark.parametrize("mode", ["bf16x3", "fp32"])
 @pytest.mark.parametrize("kind", ["miso1", "miso3"])
-def test_net_golden(kind):
+def test_net_golden(kind, mode):
+    """MISO_1 / MISO_3 inference against the reference-generated fixture, in the benched tensor-core mode and on the fp32
+    FMA path (MISO_3's 2-channel last deconv runs on the tcgen05 kernel too: no FMA fallback inside bf16x3)."""
     from misonet_b200 import synth
     g = _g(f"net_ref_{kind}.npz")
     m, cfg, sd = _model(kind, 0 if kind == "miso1" else 1)
+    m.conv_mode = mode
     for b, t in ((2, 20), (1, 11)):
         mix = torch.from_numpy(synth.random_spec(7 + b, (b, 6, t, 129))).cuda()
         with torch.no_grad():
@@ -129,9 +133,38 @@ def test_net_golden(kind):
         tcn = m.tap("tcn", b, t, 129).cpu().numpy().reshape(g[f"tcn_b{b}"].shape)
         errs["tcn"] = rel_err(tcn, g[f"tcn_b{b}"])
         errs["y"] = rel_err(y.cpu().numpy(), g[f"y_b{b}"])
-        print(kind, b, t, {k: f"{v:.2e}" for k, v in errs.items()})
-        assert max(errs.values()) < 2e-4, errs         # fp32 FMA path; required: REQUIRED_TOL
+        print(kind, mode, b, t, {k: f"{v:.2e}" for k, v in errs.items()})
+        assert max(errs.values()) < 2e-4, errs         # required: REQUIRED_TOL
         assert errs["y"] < REQUIRED_TOL
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("kind", ["miso1", "miso3"])
+def test_net_paper_golden(kind, mode):
+    """PAPER layout (8 blocks, 257 bins, TCN width 384 -- the bench's layout) against the fixture generated from the
+    patched copy of the reference's model.py (oracle/make_golden.py:golden_net_paper)."""
+    from misonet_b200 import synth
+    g = _g("net_ref_paper.npz")
+    m, cfg, sd = _model(kind, 3 if kind == "miso1" else 4, layout="PAPER")
+    m.conv_mode = mode
+    b, t = 2, 9
+    mix = torch.from_numpy(synth.random_spec(31, (b, 6, t, 257))).cuda()
+    with torch.no_grad():
+        if kind == "miso1":
+            y = m(mix)
+        else:
+            a2 = torch.from_numpy(synth.random_spec(32, (b, 1, t, 257))).cuda()
+            a3 = torch.from_numpy(synth.random_spec(33, (b, 1, t, 257))).cuda()
+            y = m(mix, a2, a3)
+    errs = {"y": rel_err(y.cpu().numpy(), g[f"{kind}_y"])}
+    for name in ("enc4", "enc7", "dec0", "dec2", "tcn"):
+        want = g[f"{kind}_{name}"]
+        errs[name] = rel_err(m.tap(name, b, t, 257).cpu().numpy().reshape(want.shape), want)
+    enc0 = m.tap("enc0", b, t, 257).cpu().numpy().reshape(b, 24, t, 255)[:, :, ::3, ::17]
+    errs["enc0"] = rel_err(enc0, g[f"{kind}_enc0_sub"])
+    print(kind, mode, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < 2e-4, errs
+    assert errs["y"] < REQUIRED_TOL
 
 
 def test_net_full_size_vs_oracle():
@@ -409,6 +442,29 @@ def test_mvdr_full_size_vs_oracle_and_distortionless():
     assert rel_err(y4, miso_np.apply_beamforming(a, mx)) < 3e-4
 
 
+def test_mvdr_paper_size_vs_oracle():
+    """MVDR at the bench's PAPER shape: 257 bins x 500 frames, 6 mics, two sources (tester.py:1071-1136)."""
+    from misonet_b200 import beamforming, synth
+    from oracle import miso_np
+    B, F, M, T, S = 1, 257, 6, 500, 2
+    srcs, mix = [], None
+    for s in range(S):
+        a, mx = synth.mvdr_case(500 + s, B, F, M, T)
+        srcs.append(a)
+        mix = mx if mix is None else mix + a
+    src_t = torch.stack([torch.from_numpy(a).permute(0, 2, 3, 1) for a in srcs]).contiguous().cuda()   # [S,B,M,T,F]
+    mix_t = torch.from_numpy(mix).permute(0, 2, 3, 1).contiguous().cuda()
+    y, w = beamforming.mvdr(src_t, mix_t, return_weights=True)
+    for s in range(S):
+        ref, parts = miso_np.apply_beamforming(srcs[s], mix, return_parts=True)
+        e = rel_err(y[s].cpu().numpy(), ref)
+        print("mvdr 257 x 500 source", s, e)
+        assert e < 3e-4 and e < REQUIRED_TOL
+        d = torch.from_numpy(parts["steering"]).cuda()
+        resp = (w[s].conj() * d).sum(-1)
+        assert torch.allclose(resp, torch.ones_like(resp), atol=2e-3)      # distortionless response
+
+
 # ------------------------------------------------------------------------------- pipeline
 def test_mvdr_utterance_level_staged():
     """Staged MVDR (tester.py:425-449: covariances over all frames of a chunked recording): one rank == the fused call
@@ -478,6 +534,70 @@ def test_pipeline_full_size_vs_oracle():
         assert rel_err(out["enhanced"][:, s].cpu().numpy(), ref_enh[:, 0]) < 2e-4
 
 
+def test_pipeline_paper_shape_bf16x3_vs_oracle():
+    """BASELINE configs[2] at the PAPER shape, one utterance, in the benched mode: 512-point STFT (257 bins) x 500 frames
+    -> MISO1 x 6 shifts -> MVDR x 2 -> MISO3 x 2, stage by stage against the oracle fed with our upstream outputs."""
+    from misonet_b200 import synth, pipeline
+    from oracle import miso_np
+    from oracle import miso_net_torch as mnt
+    m1, cfg1, sd1 = _model("miso1", 0, layout="PAPER")
+    m3, cfg3, sd3 = _model("miso3", 1, layout="PAPER")
+    assert m1.conv_mode == "bf16x3" and m3.conv_mode == "bf16x3"      # the default IS the benched mode
+    mix_t, _ = synth.make_utterance(9, n_samples=499 * 128)
+    pipe = pipeline.MisoBfMiso(m1, m3, nperseg=512, noverlap=384)
+    out = pipe(torch.from_numpy(mix_t[None]).cuda())
+    mix_stft = miso_np.stft(mix_t, 512, 384)[None]
+    assert mix_stft.shape == (1, 6, 500, 257)
+    assert rel_err(out["mix_stft"].cpu().numpy(), mix_stft) < 5e-6
+    o_miso1, o_perm = mnt.miso1_inference(sd1, cfg1, torch.from_numpy(mix_stft), 0)
+    got_miso1 = out["miso1"].cpu().numpy()
+    for s in range(2):
+        assert rel_err(got_miso1[s], o_miso1[s].numpy()) < 2e-4
+    for s in range(2):
+        src = np.transpose(got_miso1[s], (0, 3, 1, 2))
+        ref_bf = miso_np.apply_beamforming(src, np.transpose(mix_stft, (0, 3, 1, 2)))
+        assert rel_err(out["beamformed"][s].cpu().numpy(), ref_bf) < 1e-3
+        ref_enh = mnt.miso3_forward(sd3, cfg3, torch.from_numpy(mix_stft), out["beamformed"][s].cpu().unsqueeze(1),
+                                    torch.from_numpy(got_miso1[s][:, 0:1])).numpy()
+        e = rel_err(out["enhanced"][:, s].cpu().numpy(), ref_enh[:, 0])
+        print("pipeline PAPER bf16x3 enhanced", s, e)
+        assert e < 2e-4
+
+
+def test_module_on_a_non_current_device():
+    """model.cuda(1) with cuda:0 current (the reference does model.cuda(gpu_num) without set_device, run.py:68): every
+    launch, the graph capture and the workspace must go to the module's device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from misonet_b200 import synth
+    from oracle import miso_net_torch as mnt
+    m, cfg, sd = _model("miso1", 0)
+    m = m.cuda(1)
+    torch.cuda.set_device(0)
+    mix = synth.random_spec(21, (2, 6, 24, 129))
+    ref = mnt.miso1_forward(sd, cfg, torch.from_numpy(mix)).numpy()
+    with torch.no_grad():
+        for _ in range(2):                                       # capture, then replay
+            y = m(torch.from_numpy(mix).to("cuda:1"))
+    assert y.device == torch.device("cuda", 1) and torch.cuda.current_device() == 0
+    assert rel_err(y.cpu().numpy(), ref) < 2e-4
+
+
+def test_chunked_batches_keep_the_input_alignment():
+    """REF shape (501 x 129: an odd T * F makes every odd sample of the input planes 64-byte aligned only): a workspace
+    cap that forces chunking must still give the unchunked result."""
+    from misonet_b200 import synth
+    m, cfg, sd = _model("miso1", 0)
+    mix = torch.from_numpy(synth.random_spec(12, (5, 6, 21, 129))).cuda()
+    with torch.no_grad():
+        y_all = m(mix).clone()
+        per = m._ws_bytes(1, 21, 129)
+        m.max_workspace_bytes = 3 * per + per // 2            # would chunk by 3 -> must round to 2
+        assert m._chunk(5, 21, 129) == 2
+        y_chunk = m(mix)
+    assert rel_err(y_chunk.cpu().numpy(), y_all.cpu().numpy()) < 2e-5
+
+
 def test_long_recording_chunks_and_sharding():
     """continuous.separate_recording (dataloader/data.py:524-597 + tester.py:857-974): equals the per-chunk pipeline
     followed by ISTFT and the gap trim, and the block-partitioned two-rank run is bit-identical to the one-rank run."""
@@ -485,6 +605,9 @@ def test_long_recording_chunks_and_sharding():
     from misonet_b200.pipeline import MisoBfMiso
     m1, _, _ = _model("miso1", 0)
     m3, _, _ = _model("miso3", 1)
+    # this test is about the chunk / shard bookkeeping and compares runs with DIFFERENT batch compositions bit for bit:
+    # the fp32 path is batch-invariant bitwise, the tensor-core path only to rounding (test_net_batch_invariance_and_chunking)
+    m1.conv_mode = m3.conv_mode = "fp32"
     pipe = MisoBfMiso(m1, m3)
     chunk = 64 * 24                                        # 25 frames per chunk
     n = 3 * chunk - 500
