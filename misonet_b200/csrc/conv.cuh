@@ -99,6 +99,8 @@ struct RsDenseNeed {
 };
 bool conv_rs_dense_need(const ConvArgs &a, int split, int c0, RsDenseNeed *need);  // false: not eligible for the fused path
 int launch_conv_rs_dense(const ConvArgs &a, int split, const RsDense &d, cudaStream_t stream);
+bool conv_rs_jobs_in_kernel();  // default: the later convs' slices are built inside the conv kernel
+int launch_rs_group_prep(const ConvArgs &a, int split, const RsDense &d, cudaStream_t stream);  // ... or by a launch of their own
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

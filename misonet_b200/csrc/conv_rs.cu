@@ -65,8 +65,10 @@ struct RsGeom {
 // the block (their "jobs"), and this kernel's idle epilogue warps build, at kernel start,
 //   (i)  privately (per CTA, for the samples of its own row range): the image of the units that hold the late group
 //        and the late group's border-bias partial sums -- the producer warp streams those units from the private copy;
-//   (ii) shared: the same group's slices for the LATER convs of the block (distributed over the CTAs).
-// No separate preparation launch sits between two convs of a block any more.
+//   (ii) shared: the same group's slices for the LATER convs of the block (distributed over the CTAs; needed one conv later).
+// The packed fp32 weights are cold in L2 behind the previous conv's activation stream, so every line this CTA will read is
+// prefetched first; the producer is released as soon as the private units are in place, the border-bias sums and (ii)
+// follow while the first tiles' MMAs run.  No preparation launch sits between two convs of a block any more.
 constexpr int kRsMaxSlots = 8;   // samples a CTA's row range may touch in fused mode
 struct RsJob {
     const float *w;        // consumer's packed fp32 weights [9][cin][cout_pad]
@@ -83,6 +85,15 @@ struct RsFuse {
     const float *w;        // this layer's packed fp32 weights [9][cin][cout_pad]
     const double *in_sums; // statistics of the input buffer [B][in_ctot][2]
     int in_ctot, cin, cout_pad;
+    double inv_n;
+    float eps;
+    int njob;              // (ii) in the kernel: slices of the late group for the later convs of the block
+    RsJob job[kRsMaxJobs];
+};
+// the same slices as a separate launch (rs_group_prep_kernel; A/B switch MISO_RS_GROUPKERNEL=1)
+struct RsGroupPrep {
+    const double *in_sums;
+    int in_ctot, c0, nch, B, nsp;
     double inv_n;
     float eps;
     int njob;
@@ -190,34 +201,81 @@ struct RsTiles {
 };
 
 // ---- fused-mode operand preparation (executed by the 256 epilogue threads; et = thread index among them) ----
-// One 8-channel half (kg) of a 16-channel K unit of a weight image: rows [kf][hi|lo][kg][n = (2 - kt) * Nc + co][8 ci]
-//   = bf16 split of W[kt][kf][ch0 + e][co] * scale8[e]      (same layout as conv_rs_prep_kernel writes)
-__device__ __forceinline__ void rs_build_half(const float *__restrict__ w, int cin, int cout, int cout_pad, int Nc, int nsp, int ch0,
-                                              const float *scale8, __nv_bfloat16 *dst_unit, int et) {
-    const int N3 = 3 * Nc, kg = (ch0 >> 3) & 1;
-    for (int i = et; i < 3 * N3; i += kRsEpiThreads) {
-        const int kf = i / N3, n = i - kf * N3;
-        const int ktg = n / Nc, co = n - ktg * Nc;
-        const int kt = 2 - ktg;
-        float v[8];
+// nhalf consecutive 8-channel halves (kg) of 16-channel K units of a weight image, starting at channel ch0 (multiple of 8):
+// rows [kf][hi|lo][kg][n = (2 - kt) * Nc + co][8 ci] = bf16 split of W[kt][kf][ci][co] * scale[ci - ch0]  (the layout
+// conv_rs_prep_kernel writes).  dst_unit0: image of the unit that holds ch0.  This runs on the critical path of the
+// kernel's start with only a few warps to hide latency, so every thread first issues the loads of kRsBatch outputs
+// (8 weights each) and only then converts and stores them: one L2 round trip per batch instead of one per output.
+constexpr int kRsBatch = 4;
+__device__ __forceinline__ void rs_build_halves(const float *__restrict__ w, int cin, int cout, int cout_pad, int Nc, int nsp, int ch0,
+                                                int nhalf, const float *scale, __nv_bfloat16 *dst_unit0, int tidx, int nthreads) {
+    const int N3 = 3 * Nc, per = 3 * N3;
+    const size_t unit_elems = (size_t)3 * nsp * 2 * N3 * 8;
+    const int total = nhalf * per;
+    for (int i0 = tidx; i0 < total; i0 += kRsBatch * nthreads) {
+        float v[kRsBatch][8];
+        int hh[kRsBatch];
+        size_t doff[kRsBatch];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int ci = ch0 + e;
-            v[e] = (ci < cin && co < cout) ? __ldg(w + ((size_t)(kt * 3 + kf) * cin + ci) * cout_pad + co) : 0.f;
-        }
-        float h[8], l[8];
+        for (int q = 0; q < kRsBatch; ++q) {
+            const int i = i0 + q * nthreads;
+            hh[q] = -1;
+            if (i < total) {
+                const int h = i / per;
+                const int r = i - h * per;
+                const int kf = r / N3, n = r - kf * N3;
+                const int ktg = n / Nc, co = n - ktg * Nc;
+                const int kt = 2 - ktg;
+                const int ch = ch0 + 8 * h, kg = (ch >> 3) & 1;
+                hh[q] = h;
+                doff[q] = (size_t)((ch >> 4) - (ch0 >> 4)) * unit_elems + ((size_t)((kf * nsp) * 2 + kg) * N3 + n) * 8;
+                const float *wp = w + ((size_t)(kt * 3 + kf) * cin + ch) * cout_pad + co;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float x = v[e] * scale8[e];
-            h[e] = bf16_round(x);
-            l[e] = x - h[e];
+                for (int e = 0; e < 8; ++e) v[q][e] = (ch + e < cin && co < cout) ? __ldg(wp + (size_t)e * cout_pad) : 0.f;
+            }
         }
-        __nv_bfloat16 *dst = dst_unit + ((size_t)((kf * nsp) * 2 + kg) * N3 + n) * 8;
-        *reinterpret_cast<uint4 *>(dst) =
-            make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-        if (nsp == 2)
-            *reinterpret_cast<uint4 *>(dst + (size_t)2 * N3 * 8) =
-                make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+#pragma unroll
+        for (int q = 0; q < kRsBatch; ++q) {
+            if (hh[q] < 0) continue;
+            float hv[8], lv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float x = v[q][e] * scale[8 * hh[q] + e];
+                hv[e] = bf16_round(x);
+                lv[e] = x - hv[e];
+            }
+            __nv_bfloat16 *dst = dst_unit0 + doff[q];
+            *reinterpret_cast<uint4 *>(dst) =
+                make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]), pack_bf16x2(hv[6], hv[7]));
+            if (nsp == 2)
+                *reinterpret_cast<uint4 *>(dst + (size_t)2 * N3 * 8) =
+                    make_uint4(pack_bf16x2(lv[0], lv[1]), pack_bf16x2(lv[2], lv[3]), pack_bf16x2(lv[4], lv[5]), pack_bf16x2(lv[6], lv[7]));
+        }
+    }
+}
+// one tap of a group's border-bias partial sums by ONE warp: dst[n] = sum_{ci < nch} W[k][ch0 + ci][n] * shift(ci), where
+// lane l holds shift of channels l, l + 32, ... in sh[] (fixed summation order)
+__device__ __forceinline__ void rs_warp_bias_tap(const float *__restrict__ w, int cin, int cout, int cout_pad, int Nc, int ch0, int nch, int k,
+                                                 const float (&sh)[5], float *dst, int lane) {
+    for (int n0 = 0; n0 < Nc; n0 += 32) {
+        const int n = n0 + lane;
+        const float *wp = w + ((size_t)k * cin + ch0) * cout_pad + n;
+        float acc = 0.f;
+        for (int c8 = 0; c8 < nch; c8 += 8) {
+            float wv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) wv[e] = (c8 + e < nch && n < cout) ? __ldg(wp + (size_t)(c8 + e) * cout_pad) : 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ci = c8 + e;
+                float sv = 0.f;
+#pragma unroll
+                for (int r = 0; r < 5; ++r)
+                    if ((ci >> 5) == r) sv = __shfl_sync(0xffffffffu, sh[r], ci & 31);
+                acc = fmaf(wv[e], sv, acc);
+            }
+        }
+        if (n < Nc) dst[n] = acc;
     }
 }
 // Border-bias partial sums of one channel group: dst[kt * 3 + kf][n] = sum_{ci < nch} W[k][ch0 + ci][n] * shift[ci]
@@ -248,6 +306,15 @@ __device__ __forceinline__ void rs_build_bias(const float *__restrict__ w, int c
         dst[i] = v;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+}
+// L2 prefetch of the packed weights of channels [ch0, ch0 + nch) of all nine taps ([9][cin][cout_pad] fp32)
+__device__ __forceinline__ void rs_prefetch_w(const float *w, int cin, int cout_pad, int ch0, int nch, int tidx, int nthreads) {
+    const int per_tap = (nch * cout_pad * 4 + 127) >> 7;  // 128-byte lines per tap (a tap's channel range is contiguous)
+    for (int l = tidx; l < 9 * per_tap; l += nthreads) {
+        const int k = l / per_tap, q = l - k * per_tap;
+        const char *p = reinterpret_cast<const char *>(w + ((size_t)k * cin + ch0) * cout_pad) + (size_t)q * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
 }
 // consumer-side InstanceNorm affine of channel ci of the input view (in_coff = 0 inside a DenseBlock)
 __device__ __forceinline__ float2 rs_fuse_affine(const RsFuse &fz, int b, int ci) {
@@ -487,6 +554,9 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             const int chA = fz.u0 * 16, nA = fz.nlate * 16;  // channels of the private units (the last ones may lie past cin: zero)
             const int scratch_cap = 64 * Nc;
             if (tracer) rs_trace(a.trace, 2, ntr, 50);
+            rs_prefetch_w(fz.w, fz.cin, fz.cout_pad, chA, fz.cin - chA, et, kRsEpiThreads);
+            const int nchl = fz.cin - fz.c0;  // channels of the late group
+            for (int j = 0; j < fz.njob; ++j) rs_prefetch_w(fz.job[j].w, fz.job[j].cin, fz.job[j].cout_pad, fz.c0, nchl, et, kRsEpiThreads);
             for (int bb = b_first; bb <= b_last; ++bb) {
                 const int slot = bb - b_first;
                 for (int i = et; i < nA; i += kRsEpiThreads) {
@@ -496,38 +566,54 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                     aff[kRsAffCh + i] = af.y;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+                if (tracer) rs_trace(a.trace, 2, ntr, 60);
                 __nv_bfloat16 *dstp = fz.priv + ((size_t)blockIdx.x * fz.nslot + slot) * fz.nlate * (size_t)(g.w_unit / 2);
-                for (int h = 0; h < 2 * fz.nlate; ++h)
-                    rs_build_half(fz.w, fz.cin, a.cout, fz.cout_pad, Nc, g.nsp, chA + 8 * h, aff + 8 * h, dstp + (size_t)(h >> 1) * (g.w_unit / 2), et);
-                rs_build_bias(fz.w, fz.cin, a.cout, fz.cout_pad, Nc, fz.c0, fz.cin - fz.c0, aff + kRsAffCh + (fz.c0 - chA), btab_s, scratch_cap,
-                              fz.priv_bias + ((size_t)blockIdx.x * fz.nslot + slot) * 9 * Nc, et);
+                rs_build_halves(fz.w, fz.cin, a.cout, fz.cout_pad, Nc, g.nsp, chA, 2 * fz.nlate, aff, dstp, et, kRsEpiThreads);
+                if (tracer) rs_trace(a.trace, 2, ntr, 61);
                 // the producer's bulk copies (async proxy) read what these generic-proxy stores wrote
                 asm volatile("fence.proxy.async;" ::: "memory");
                 mbar_arrive(bar_late + 8 * slot);
+                if (tracer) rs_trace(a.trace, 2, ntr, 63);
+                // the MMAs of this sample can start; its border-bias sums are needed by the first epilogue only
+                rs_build_bias(fz.w, fz.cin, a.cout, fz.cout_pad, Nc, fz.c0, nchl, aff + kRsAffCh + (fz.c0 - chA), btab_s, scratch_cap,
+                              fz.priv_bias + ((size_t)blockIdx.x * fz.nslot + slot) * 9 * Nc, et);
+                if (tracer) rs_trace(a.trace, 2, ntr, 62);
             }
             if (tracer) rs_trace(a.trace, 2, ntr, 51);
-            // (ii) the late group's slices for the later convs of the block
-            const int nh = (fz.cin - fz.c0 + 7) >> 3, pieces = nh + 1;
-            const int total = fz.njob * a.B * pieces;
-            for (int it = blockIdx.x; it < total; it += gridDim.x) {
-                const int piece = it % pieces;
-                const int r = it / pieces;
-                const int bb = r % a.B;
-                const RsJob &J = fz.job[r / a.B];
-                if (piece < nh) {
-                    const int ch0 = fz.c0 + 8 * piece;
-                    if (et < 8) aff[et] = ch0 + et < fz.cin ? rs_fuse_affine(fz, bb, ch0 + et).x : 0.f;
-                    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-                    const size_t junit = (size_t)3 * g.nsp * 2 * 3 * J.Nc * 8;  // elements of one unit of the consumer's image
-                    rs_build_half(J.w, J.cin, J.cout, J.cout_pad, J.Nc, g.nsp, ch0, aff, J.wimg + ((size_t)bb * J.nunit + (ch0 >> 4)) * junit, et);
-                    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-                } else {
-                    const int nch = fz.cin - fz.c0;
-                    for (int i = et; i < nch; i += kRsEpiThreads) aff[kRsAffCh + i] = rs_fuse_affine(fz, bb, fz.c0 + i).y;
-                    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-                    rs_build_bias(J.w, J.cin, J.cout, J.cout_pad, J.Nc, fz.c0, nch, aff + kRsAffCh, btab_s, scratch_cap,
-                                  J.btab + ((size_t)bb * J.ngroup + J.gidx) * 9 * J.Nc, et);
+            // (ii) the late group's slices for the later convs of the block: one item per WARP (no CTA barriers): an
+            // 8-channel half of a consumer's image, or one tap of its border-bias partial sums
+            {
+                const int nh = (nchl + 7) >> 3, pieces = nh + 9;
+                const int total = fz.njob * a.B * pieces;
+                const int ew = warp - kRsEpi0;
+                for (int it = blockIdx.x * 8 + ew; it < total; it += gridDim.x * 8) {
+                    const int piece = it % pieces;
+                    const int r = it / pieces;
+                    const int bb = r % a.B;
+                    const RsJob &J = fz.job[r / a.B];
+                    if (piece < nh) {
+                        const int ch0 = fz.c0 + 8 * piece;
+                        float mine = 0.f;
+                        if (lane < 8 && ch0 + lane < fz.cin) mine = rs_fuse_affine(fz, bb, ch0 + lane).x;
+                        float sc8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) sc8[e] = __shfl_sync(0xffffffffu, mine, e);
+                        const size_t junit = (size_t)3 * g.nsp * 2 * 3 * J.Nc * 8;  // elements of one unit of the consumer's image
+                        rs_build_halves(J.w, J.cin, J.cout, J.cout_pad, J.Nc, g.nsp, ch0, 1, sc8, J.wimg + ((size_t)bb * J.nunit + (ch0 >> 4)) * junit, lane,
+                                        32);
+                    } else {
+                        float sh[5];
+#pragma unroll
+                        for (int q = 0; q < 5; ++q) {
+                            const int ci = q * 32 + lane;
+                            sh[q] = ci < nchl ? rs_fuse_affine(fz, bb, fz.c0 + ci).y : 0.f;
+                        }
+                        const int k = piece - nh;
+                        rs_warp_bias_tap(J.w, J.cin, J.cout, J.cout_pad, J.Nc, fz.c0, nchl, k, sh,
+                                         J.btab + (((size_t)bb * J.ngroup + J.gidx) * 9 + k) * J.Nc, lane);
+                    }
                 }
+                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
             }
             if (tracer) rs_trace(a.trace, 2, ntr, 52);
         }
@@ -772,6 +858,52 @@ __global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
             float v = 0.f;
             for (int q = 0; q < nparts; ++q) v += wb[q * 9 * p.Nc + i];
             dst[i] = v;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Slices of one channel group (channels [c0, c0 + nch) of the block buffer, just produced) for the later convs of the
+// DenseBlock.  Block = (job, sample, piece): piece < nh builds one 8-channel half of the consumer's weight image, piece ==
+// nh the group's border-bias partial sums (one output per thread, fixed order).  Tiny shared-memory footprint and 256
+// threads so that the blocks fit on the SMs next to the resident conv_rs CTA.
+__global__ void __launch_bounds__(256) rs_group_prep_kernel(const RsGroupPrep p) {
+    __shared__ float sc[kRsAffCh];
+    const int nh = (p.nch + 7) >> 3, pieces = nh + 1;
+    const int piece = blockIdx.x % pieces;
+    const int r = blockIdx.x / pieces;
+    const int b = r % p.B;
+    const RsJob &J = p.job[r / p.B];
+    if (piece < nh) {
+        const int ch0 = p.c0 + 8 * piece;
+        if (threadIdx.x < 8) {
+            float v = 0.f;
+            if (8 * piece + (int)threadIdx.x < p.nch) {
+                const double *sp = p.in_sums + ((size_t)b * p.in_ctot + ch0 + threadIdx.x) * 2;
+                v = affine_from_sums(stat_get(sp), stat_get(sp + 1), p.inv_n, (double)p.eps).x;
+            }
+            sc[threadIdx.x] = v;
+        }
+        __syncthreads();
+        const size_t junit = (size_t)3 * p.nsp * 2 * 3 * J.Nc * 8;
+        rs_build_halves(J.w, J.cin, J.cout, J.cout_pad, J.Nc, p.nsp, ch0, 1, sc, J.wimg + ((size_t)b * J.nunit + (ch0 >> 4)) * junit, threadIdx.x, 256);
+    } else {
+        for (int i = threadIdx.x; i < p.nch; i += 256) {
+            const double *sp = p.in_sums + ((size_t)b * p.in_ctot + p.c0 + i) * 2;
+            sc[i] = affine_from_sums(stat_get(sp), stat_get(sp + 1), p.inv_n, (double)p.eps).y;
+        }
+        __syncthreads();
+        float *dst = J.btab + ((size_t)b * J.ngroup + J.gidx) * 9 * J.Nc;
+        for (int o = threadIdx.x; o < 9 * J.Nc; o += 256) {
+            const int k = o / J.Nc, n = o - k * J.Nc;
+            float acc = 0.f;
+            if (n < J.cout) {
+                const float *wp = J.w + ((size_t)k * J.cin + p.c0) * J.cout_pad + n;
+#pragma unroll 8
+                for (int ci = 0; ci < p.nch; ++ci) acc = fmaf(__ldg(wp + (size_t)ci * J.cout_pad), sc[ci], acc);
+            }
+            dst[o] = acc;
         }
     }
 }
@@ -1045,9 +1177,12 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
 
 // ---- fused mode (forward DenseBlock convs): sizes of the per-layer persistent buffers and the launch
 bool conv_rs_dense_need(const ConvArgs &a, int split, int c0, RsDenseNeed *need) {
-    static const bool off = getenv("MISO_RS_FUSE") && atoi(getenv("MISO_RS_FUSE")) == 0;
+    // Off by default: measured on B200 (profiles/r2_fused_prep_*.log) the in-kernel preparation costs more than the
+    // launch it removes -- 148 CTAs re-read the same cold weight lines (9x the L2 traffic of the per-sample prep kernel)
+    // and run once-per-launch code at instruction-cache-miss speed: 11.3-11.7 ms per bench step against 10.9-11.1.
+    static const bool on = getenv("MISO_RS_FUSE") && atoi(getenv("MISO_RS_FUSE")) != 0;
     RsGeom g;
-    if (off || !conv_rs_eligible(a, split) || !make_rs_geom(a, split, g)) return false;
+    if (!on || !conv_rs_eligible(a, split) || !make_rs_geom(a, split, g)) return false;
     if (a.norm_mode != NORM_IN || c0 % 8 || c0 < 0 || c0 >= a.cin) return false;
     const int u0 = c0 / 16, nlate = g.nunit - u0;
     if (nlate * 16 > kRsAffCh || a.cin - c0 > kRsAffCh) return false;
@@ -1066,7 +1201,6 @@ int launch_conv_rs_dense(const ConvArgs &a, int split, const RsDense &d, cudaStr
     RsDenseNeed need;
     MISO_REQUIRE(make_rs_geom(a, split, g) && conv_rs_dense_need(a, split, d.c0, &need), "conv_rs: layer does not fit the fused row-streaming path (cin=%d cout=%d F=%d c0=%d)",
                  a.cin, a.cout, a.Fin, d.c0);
-    MISO_REQUIRE(d.njob <= kRsMaxJobs, "conv_rs: too many jobs");
     RsFuse f{};
     f.on = 1;
     f.c0 = d.c0;
@@ -1083,10 +1217,53 @@ int launch_conv_rs_dense(const ConvArgs &a, int split, const RsDense &d, cudaStr
     f.cout_pad = a.cout_pad;
     f.inv_n = a.norm_inv_n;
     f.eps = a.norm_eps;
-    f.njob = d.njob;
+    MISO_REQUIRE(d.njob <= kRsMaxJobs, "conv_rs: too many jobs");
+    f.njob = conv_rs_jobs_in_kernel() ? d.njob : 0;
+    for (int j = 0; j < f.njob; ++j) {
+        const RsDenseJob &sj = d.job[j];
+        RsJob &t = f.job[j];
+        t.w = sj.w;
+        t.wimg = reinterpret_cast<__nv_bfloat16 *>(sj.wimg);
+        t.btab = sj.btab;
+        t.cin = sj.cin;
+        t.cout = sj.cout;
+        t.cout_pad = sj.cout_pad;
+        t.Nc = rs_round_up(sj.cout, 16);
+        t.nunit = ((sj.cin + 7) / 8 + 1) / 2;
+        t.ngroup = sj.ngroup;
+        t.gidx = sj.gidx;
+    }
+    static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "conv_rs fused: cin=%d cout=%d F=%d c0=%d | u0=%d nlate=%d nslot=%d njob=%d early groups=%d G=%d nstage=%d smem=%d\n", a.cin, a.cout,
+                a.Fin, d.c0, f.u0, f.nlate, f.nslot, d.njob, d.ngroup_early, g.G, g.nstage, g.smem_total);
+    return rs_launch(a, split, g, reinterpret_cast<const __nv_bfloat16 *>(d.wimg), d.btab, d.ngroup_early, f, stream);
+}
+
+bool conv_rs_jobs_in_kernel() {
+    static const bool sep = getenv("MISO_RS_GROUPKERNEL") && atoi(getenv("MISO_RS_GROUPKERNEL")) != 0;
+    return !sep;
+}
+
+// the late group's slices for the later convs of the block (d.job) as a launch of their own (MISO_RS_GROUPKERNEL=1)
+int launch_rs_group_prep(const ConvArgs &a, int split, const RsDense &d, cudaStream_t stream) {
+    if (d.njob == 0 || conv_rs_jobs_in_kernel()) return MISO_OK;
+    MISO_REQUIRE(d.njob <= kRsMaxJobs, "conv_rs: too many jobs");
+    RsGroupPrep p{};
+    p.in_sums = a.in_sums + (size_t)a.in_coff * 2;
+    p.in_ctot = a.in_ctot;
+    p.c0 = d.c0;
+    p.nch = a.cin - d.c0;
+    MISO_REQUIRE(p.nch > 0 && p.nch <= kRsAffCh, "conv_rs: group of %d channels", p.nch);
+    p.B = a.B;
+    p.nsp = split == 3 ? 2 : 1;
+    p.inv_n = a.norm_inv_n;
+    p.eps = a.norm_eps;
+    p.njob = d.njob;
+    double bytes = 0.0;
     for (int j = 0; j < d.njob; ++j) {
         const RsDenseJob &s = d.job[j];
-        RsJob &t = f.job[j];
+        RsJob &t = p.job[j];
         t.w = s.w;
         t.wimg = reinterpret_cast<__nv_bfloat16 *>(s.wimg);
         t.btab = s.btab;
@@ -1097,12 +1274,13 @@ int launch_conv_rs_dense(const ConvArgs &a, int split, const RsDense &d, cudaStr
         t.nunit = ((s.cin + 7) / 8 + 1) / 2;
         t.ngroup = s.ngroup;
         t.gidx = s.gidx;
+        bytes += (double)a.B * ((double)p.nch * 9 * 3 * t.Nc * 2 * p.nsp + 9.0 * t.Nc * 4);
     }
-    static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
-    if (debug)
-        fprintf(stderr, "conv_rs fused: cin=%d cout=%d F=%d c0=%d | u0=%d nlate=%d nslot=%d njob=%d early groups=%d G=%d nstage=%d smem=%d\n", a.cin, a.cout,
-                a.Fin, d.c0, f.u0, f.nlate, f.nslot, f.njob, d.ngroup_early, g.G, g.nstage, g.smem_total);
-    return rs_launch(a, split, g, reinterpret_cast<const __nv_bfloat16 *>(d.wimg), d.btab, d.ngroup_early, f, stream);
+    const int pieces = (p.nch + 7) / 8 + 1;
+    rs_group_prep_kernel<<<d.njob * a.B * pieces, 256, 0, stream>>>(p);
+    (void)bytes;
+    MISO_LAUNCHED("rs_group_prep_kernel");
+    return MISO_OK;
 }
 
 }  // namespace miso

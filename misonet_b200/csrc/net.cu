@@ -353,6 +353,9 @@ struct miso_net {
     std::vector<GraphEntry> graphs;
     cudaStream_t cap_stream = nullptr;
     int use_graph = 1;
+    // forked branch of the forward: the DenseBlock group-preparation launches run next to the conv kernels (Walker::dense)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace miso {
@@ -654,6 +657,8 @@ struct Walker {
     std::vector<ConvRec> *record = nullptr;  // non-null: list the layers instead of launching them
 
     size_t need_d = 0, need_p = 0, dense_off = 0;  // fused DenseBlock convs: persistent bytes (running offset) and private scratch (max)
+    cudaStream_t side = nullptr;                    // forked stream for the group-preparation launches (null: run them in line)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     ConvArgs make_args(const ConvDesc &cd, bool transposed, const BufDesc *inb, const void *in_raw, int in_ctot, int in_coff, int Fin,
                        const double *in_sums, const BufDesc *outb, float *out_raw, int out_ctot, int out_coff, int Fout, double *out_sums,
@@ -736,6 +741,9 @@ struct Walker {
                 a[k - 1] = make_args(cds[k - 1], false, &buf, nullptr, buf.ctot, 0, buf.F, buf.sums, &out5, nullptr, out5.ctot, out5_coff, buf.F,
                                      out5.sums, 1, 1, true);
         }
+        // block buffers are always consumed through their producer's InstanceNorm; a plan built without a base address
+        // (size queries) has null statistics pointers and must still take the same decisions
+        for (int k = 0; k < 5; ++k) a[k].norm_mode = NORM_IN;
         const int split = n->mode == 2 ? 1 : 3;
         bool fused[5];
         RsDenseNeed need[5];
@@ -790,7 +798,21 @@ struct Walker {
                     jb.ngroup = j - 1;
                     jb.gidx = k - 1;
                 }
+                // the group's slices for the later convs are needed one conv later: fork them off the conv's predecessor so
+                // that they run next to this conv, and join before the next one
+                const bool fork = d.njob > 0 && side != nullptr && !conv_rs_jobs_in_kernel();
+                if (fork) {
+                    MISO_CUDA(cudaEventRecord(ev_fork, st));
+                    MISO_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+                    rc = launch_rs_group_prep(a[k - 1], split, d, side);
+                    if (rc) return rc;
+                    MISO_CUDA(cudaEventRecord(ev_join, side));
+                } else if (d.njob > 0) {
+                    rc = launch_rs_group_prep(a[k - 1], split, d, st);
+                    if (rc) return rc;
+                }
                 rc = launch_conv_rs_dense(a[k - 1], split, d, st);
+                if (fork) MISO_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
             } else {
                 rc = dispatch(a[k - 1], cds[k - 1], &buf, outb);
             }
@@ -997,6 +1019,13 @@ int Walker::run(const void *d_x, float *d_y) {
 }
 
 int enqueue_forward(miso_net *net, const Plan &pl, const void *d_x, float *d_y, int B, int T, int F, cudaStream_t st);
+int ensure_side(miso_net *net) {
+    if (net->side_stream) return MISO_OK;
+    MISO_CUDA(cudaStreamCreateWithFlags(&net->side_stream, cudaStreamNonBlocking));
+    MISO_CUDA(cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
+    MISO_CUDA(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
+    return MISO_OK;
+}
 
 // Data gradient of a recorded layer as a forward conv over dL/dy (bf16 hi/lo planes in pl.dyP) with the transposed
 // weights in pl.wT, accumulated into the input buffer's gradient (resid == out).  Every case maps onto a configuration
@@ -1230,6 +1259,9 @@ int miso_net_destroy(miso_net_t *net) {
     if (!net) return MISO_OK;
     for (auto &g : net->graphs) cudaGraphExecDestroy(g.exec);
     if (net->cap_stream) cudaStreamDestroy(net->cap_stream);
+    if (net->side_stream) cudaStreamDestroy(net->side_stream);
+    if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+    if (net->ev_join) cudaEventDestroy(net->ev_join);
     if (net->arena) cudaFree(net->arena);
     delete net;
     return MISO_OK;
@@ -1339,6 +1371,8 @@ int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T,
         return MISO_E_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
+    rc = ensure_side(net);
+    if (rc) return rc;
     // Replay a captured graph when nothing baked into the kernel arguments changed.  With per-launch
     // profiling on (miso_prof_enable) the graph additionally carries event-record nodes around every conv.
     if (net->use_graph) {
@@ -1384,8 +1418,12 @@ int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T,
 }
 
 int miso_debug_tc_trace(long long *d_buf, int cin, int fin) {
-    conv_tc_set_trace(d_buf, cin, fin);
-    conv_rs_set_trace(d_buf, cin, fin);
+    // both kernels log into the same buffer; MISO_TRACE_KERNEL=rs|tc restricts the trace to one of them (a strided conv
+    // and a DenseBlock conv can share (cin, Fin), and the later launch would overwrite the earlier one's log)
+    const char *which = getenv("MISO_TRACE_KERNEL");
+    const bool tc = !which || which[0] == 't', rs = !which || which[0] == 'r';
+    conv_tc_set_trace(tc ? d_buf : nullptr, cin, fin);
+    conv_rs_set_trace(rs ? d_buf : nullptr, cin, fin);
     return MISO_OK;
 }
 
@@ -1412,6 +1450,12 @@ int enqueue_forward(miso_net *net, const Plan &pl, const void *d_x, float *d_y, 
         MISO_LAUNCHED("sentinel_kernel");
     }
     Walker w{net, pl, B, T, F, st, false};
+    static const bool no_fork = getenv("MISO_RS_FORK") && atoi(getenv("MISO_RS_FORK")) == 0;
+    if (!no_fork && net->side_stream) {  // created by ensure_side() outside any stream capture
+        w.side = net->side_stream;
+        w.ev_fork = net->ev_fork;
+        w.ev_join = net->ev_join;
+    }
     return w.run(d_x, d_y);
 }
 }  // namespace
@@ -1776,6 +1820,8 @@ int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, 
         return MISO_E_WORKSPACE;
     }
     rc = conv_tc_init();
+    if (rc) return rc;
+    rc = ensure_side(net);
     if (rc) return rc;
     return enqueue_forward(net, pl, d_x, d_y, B, T, F, as_stream(stream));
 }
