@@ -12,6 +12,9 @@
 //                 sequential recurrence of tester.py:1163-1166), diagonal loading,
 //                 pivoted 6x6 complex solve and w = u / (d^H u) (tester.py:1211-1225).
 //   apply_kernel  y[t] = sum_m conj(w[m]) x[m,t] for all sources in one pass over the mixture.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace miso {
@@ -25,34 +28,61 @@ struct Tri {
 
 constexpr int kFx = 32, kTy = 8;
 
+// L2 eviction-priority hints: the mixture is read by the covariance pass and again by the filter-and-sum pass of the
+// same utterance chunk (evict_last keeps it resident in the 126 MB L2 in between), the sources are streamed once
+// (evict_first keeps them from pushing the mixture out).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float2 ld_hint(const float2 *p, uint64_t policy) {
+    float2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(policy));
+    return v;
+}
+
+// Both spatial covariances (source, noise = mixture - source) of up to two sources in ONE pass over the mixture: the
+// block's eight time lanes are split between the sources (ty = sl * lanes + tl), the lanes of both sources walk the
+// frames in lockstep, so the second reader of a mixture element hits L1 / L2 and DRAM sees the mixture once.
 template <int M>
 __global__ void __launch_bounds__(kFx *kTy) scm_kernel(const float2 *__restrict__ src, int64_t src_ss,
                                                         const float2 *__restrict__ mix, int64_t sb, int64_t sm, int64_t st,
                                                         int64_t sf, float *__restrict__ partial, int S, int B, int T, int F,
-                                                        int tsplit) {
-    constexpr int N = Tri<M>::N, NV = Tri<M>::NV;
-    __shared__ float red[NV][kFx];
+                                                        int tsplit, int b0) {
+    constexpr int NV = Tri<M>::NV;
+    __shared__ float red[2][NV][kFx];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int f = blockIdx.x * kFx + tx;
     const int split = blockIdx.y;
-    const int b = blockIdx.z;
+    const int b = blockIdx.z + b0;  // utterance chunk [b0, b0 + gridDim.z)
     const int tc = (T + tsplit - 1) / tsplit;
     const int t0 = split * tc, t1 = min(T, t0 + tc);
     const bool fok = f < F;
     const float2 *mix_b = mix + b * sb + (int64_t)f * sf;
+    const uint64_t pol_mix = l2_policy_evict_last(), pol_src = l2_policy_evict_first();
 
-    for (int s = 0; s < S; ++s) {
+    for (int s0 = 0; s0 < S; s0 += 2) {
+        const int ns = min(2, S - s0);           // sources of this pass
+        const int lanes = kTy / ns;              // time lanes per source
+        const int sl = ty / lanes, tl = ty - sl * lanes;
+        const int s = s0 + sl;
         float acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i] = 0.f;
         if (fok) {
             const float2 *src_b = src + s * src_ss + b * sb + (int64_t)f * sf;
-            for (int t = t0 + ty; t < t1; t += kTy) {
+            for (int t = t0 + tl; t < t1; t += lanes) {
                 float2 x[M], y[M];
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
-                    float2 mx = mix_b[m * sm + t * st];
-                    float2 sx = src_b[m * sm + t * st];
+                    const float2 mx = ld_hint(mix_b + m * sm + t * st, pol_mix);
+                    const float2 sx = ld_hint(src_b + m * sm + t * st, pol_src);
                     x[m] = sx;
                     y[m] = make_float2(mx.x - sx.x, mx.y - sx.y);  // noise = mix - source (tester.py:1095)
                 }
@@ -70,21 +100,22 @@ __global__ void __launch_bounds__(kFx *kTy) scm_kernel(const float2 *__restrict_
                     }
             }
         }
-        // ordered reduction over the 8 time lanes
-        for (int r = 0; r < kTy; ++r) {
-            if (ty == r) {
+        // ordered reduction over the time lanes of each source
+        for (int r = 0; r < lanes; ++r) {
+            if (tl == r) {
 #pragma unroll
-                for (int i = 0; i < NV; ++i) red[i][tx] = (r == 0 ? 0.f : red[i][tx]) + acc[i];
+                for (int i = 0; i < NV; ++i) red[sl][i][tx] = (r == 0 ? 0.f : red[sl][i][tx]) + acc[i];
             }
             __syncthreads();
         }
         if (fok) {
-            float *dst = partial + (((size_t)(s * B + b) * tsplit + split) * NV) * F + f;  // problem index = s*B + b
-            for (int i = ty; i < NV; i += kTy) dst[(size_t)i * F] = red[i][tx];
+            for (int q = 0; q < ns; ++q) {
+                float *dst = partial + (((size_t)((s0 + q) * B + b) * tsplit + split) * NV) * F + f;  // problem index = s*B + b
+                for (int i = ty; i < NV; i += kTy) dst[(size_t)i * F] = red[q][i][tx];
+            }
         }
         __syncthreads();
     }
-    (void)N;
 }
 
 // sum the T-split partials in a fixed order; which = 0 source, 1 noise.  Returns the full
@@ -119,10 +150,11 @@ __device__ void load_scm(const float *__restrict__ partial, int bs, int f, int F
 // any microphone count: one thread per problem, (p,q)-indexed sweep (dynamically indexed arrays)
 template <int M>
 __global__ void __launch_bounds__(64) eig_generic_kernel(const float *__restrict__ partial, double2 *__restrict__ steer, int nprob,
-                                                 int F, int T, int tsplit) {
+                                                 int F, int T, int tsplit, int B, int b0, int Bc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nprob) return;
-    const int f = i % F, bs = i / F;
+    const int f = i % F, bl = i / F;
+    const int bs = (bl / Bc) * B + b0 + bl % Bc;  // problems of the utterance chunk [b0, b0 + Bc): (s, b) -> s * B + b
     double Ar[M][M], Ai[M][M], Vr[M][M], Vi[M][M];
     load_scm<M>(partial, bs, f, F, tsplit, 0, 1.0 / (double)T, Ar, Ai);
     for (int p = 0; p < M; ++p)
@@ -202,12 +234,13 @@ __global__ void __launch_bounds__(64) eig_generic_kernel(const float *__restrict
 // rotate the matrix, each accumulates three of the six eigenvector rows (V <- V J acts on rows independently).
 template <int M>
 __global__ void __launch_bounds__(64) eig6_kernel(const float *__restrict__ partial, double2 *__restrict__ steer, int nprob,
-                                                  int F, int T, int tsplit) {
+                                                  int F, int T, int tsplit, int B, int b0, int Bc) {
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = gi & 1;
     const bool live = (gi >> 1) < nprob;
     const int i = live ? (gi >> 1) : nprob - 1;
-    const int f = i % F, bs = i / F;
+    const int f = i % F, bl = i / F;
+    const int bs = (bl / Bc) * B + b0 + bl % Bc;  // problems of the utterance chunk [b0, b0 + Bc): (s, b) -> s * B + b
     double Ar[M][M], Ai[M][M];  // only [i][j], i <= j is maintained after the load
     load_scm<M>(partial, bs, f, F, tsplit, 0, 1.0 / (double)T, Ar, Ai);
     double Vr[3][M], Vi[3][M];  // rows 3h .. 3h+2 of V
@@ -228,7 +261,10 @@ __global__ void __launch_bounds__(64) eig6_kernel(const float *__restrict__ part
 #pragma unroll
             for (int q = p + 1; q < M; ++q) off += Ar[p][q] * Ar[p][q] + Ai[p][q] * Ai[p][q];
         }
-        if (off <= 1e-30 * dg || off == 0.0) break;
+        // the principal eigenvector feeds a complex64 beamformer (and the reference's np.linalg.eigh runs in single
+        // precision, tester.py:1107): an off-diagonal mass of 1e-18 of the diagonal's bounds the eigenvector error near
+        // 1e-9, far below both -- two sweeps fewer than the 1e-30 of the generic kernel (Jacobi converges quadratically)
+        if (off <= 1e-18 * dg || off == 0.0) break;
 #pragma unroll 1
         for (int rnd = 0; rnd < 5; ++rnd) {
             double c[3], s[3], er[3], ei[3];
@@ -376,9 +412,10 @@ __global__ void __launch_bounds__(64) eig6_kernel(const float *__restrict__ part
 
 template <int M>
 __global__ void __launch_bounds__(256) solve_kernel(const float *__restrict__ partial, const double2 *__restrict__ steer,
-                                                    float2 *__restrict__ wout, int F, int T, int tsplit, double epsi) {
+                                                    float2 *__restrict__ wout, int F, int T, int tsplit, double epsi, int B, int b0,
+                                                    int Bc) {
     extern __shared__ double2 ph[];  // [F] phasors, then their prefix products
-    const int bs = blockIdx.x;
+    const int bs = ((int)blockIdx.x / Bc) * B + b0 + (int)blockIdx.x % Bc;
     const double2 *d = steer + (size_t)bs * F * M;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
         double2 p = make_double2(1.0, 0.0);
@@ -479,9 +516,9 @@ constexpr int kApplyTile = 64;
 template <int M>
 __global__ void __launch_bounds__(kFx *kTy) apply_kernel(const float2 *__restrict__ mix, int64_t sb, int64_t sm, int64_t st,
                                                           int64_t sf, const float2 *__restrict__ w, float2 *__restrict__ out,
-                                                          int S, int B, int T, int F) {
+                                                          int S, int B, int T, int F, int b0) {
     const int f = blockIdx.x * kFx + threadIdx.x;
-    const int b = blockIdx.z;
+    const int b = blockIdx.z + b0;
     if (f >= F) return;
     float2 wv[kMaxS][M];
 #pragma unroll
@@ -493,10 +530,11 @@ __global__ void __launch_bounds__(kFx *kTy) apply_kernel(const float2 *__restric
     const int t0 = blockIdx.y * kApplyTile;
     const int t1 = min(T, t0 + kApplyTile);
     const float2 *mix_b = mix + b * sb + (int64_t)f * sf;
+    const uint64_t pol = l2_policy_evict_first();  // last use of the mixture
     for (int t = t0 + threadIdx.y; t < t1; t += kTy) {
         float2 x[M];
 #pragma unroll
-        for (int m = 0; m < M; ++m) x[m] = mix_b[m * sm + t * st];
+        for (int m = 0; m < M; ++m) x[m] = ld_hint(mix_b + m * sm + t * st, pol);
 #pragma unroll
         for (int s = 0; s < kMaxS; ++s)
             if (s < S) {
@@ -554,21 +592,35 @@ int run(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, int64_
     const float2 *src = reinterpret_cast<const float2 *>(d_src);
     const float2 *mix = reinterpret_cast<const float2 *>(d_mix);
     dim3 blk(kFx, kTy);
-    scm_kernel<M><<<dim3(ceil_div(F, kFx), tsplit, B), blk, 0, stream>>>(src, src_ss, mix, sb, sm, st, sf, ws.partial, S, B, T,
-                                                                       F, tsplit);
-    MISO_LAUNCHED("scm_kernel");
-    // problems are ordered (s, b, f): bs = s*B + b, matching the [S,B,...] outputs
-    const int nprob = B * S * F;
-    if constexpr (M == 6)
-        eig6_kernel<M><<<ceil_div(2 * nprob, 64), 64, 0, stream>>>(ws.partial, ws.steer, nprob, F, T, tsplit);
-    else
-        eig_generic_kernel<M><<<ceil_div(nprob, 64), 64, 0, stream>>>(ws.partial, ws.steer, nprob, F, T, tsplit);
-    MISO_LAUNCHED("eig_kernel");
-    solve_kernel<M><<<B * S, 256, (size_t)F * sizeof(double2), stream>>>(ws.partial, ws.steer, w, F, T, tsplit, (double)epsi);
-    MISO_LAUNCHED("solve_kernel");
-    apply_kernel<M><<<dim3(ceil_div(F, kFx), ceil_div(T, kApplyTile), B), blk, 0, stream>>>(
-        mix, sb, sm, st, sf, w, reinterpret_cast<float2 *>(d_out), S, B, T, F);
-    MISO_LAUNCHED("apply_kernel");
+    // Optional utterance chunks (MISO_MVDR_L2_MB) sized so that a chunk's mixture, read by the covariance pass and again by
+    // filter-and-sum, could stay in L2 between the two passes.  Measured on B200 (profiles/r2_mvdr_*.json): the eigenvector
+    // and solve kernels are latency bound (75 / 46 us whatever the problem count), so every extra chunk costs more than
+    // the 197 MB of DRAM reads it saves -- 1.08 ms with 40 MB chunks against 0.36 ms unchunked.  Default: one chunk.
+    // tsplit and the problem indexing are those of the whole batch, so the result does not depend on the chunking.
+    const size_t mix_bytes = (size_t)M * T * F * sizeof(float2);
+    static const size_t l2_budget = getenv("MISO_MVDR_L2_MB") ? (size_t)atoi(getenv("MISO_MVDR_L2_MB")) << 20 : ~(size_t)0;
+    const int Bc_max = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, l2_budget / std::max<size_t>(mix_bytes, 1)));
+    for (int b0 = 0; b0 < B; b0 += Bc_max) {
+        const int Bc = std::min(Bc_max, B - b0);
+        prof_begin(stream);
+        scm_kernel<M><<<dim3(ceil_div(F, kFx), tsplit, Bc), blk, 0, stream>>>(src, src_ss, mix, sb, sm, st, sf, ws.partial, S, B, T, F, tsplit,
+                                                                           b0);
+        MISO_LAUNCHED("scm_kernel");
+        // problems are ordered (s, b, f): bs = s*B + b, matching the [S,B,...] outputs
+        const int nprob = Bc * S * F;
+        if constexpr (M == 6)
+            eig6_kernel<M><<<ceil_div(2 * nprob, 64), 64, 0, stream>>>(ws.partial, ws.steer, nprob, F, T, tsplit, B, b0, Bc);
+        else
+            eig_generic_kernel<M><<<ceil_div(nprob, 64), 64, 0, stream>>>(ws.partial, ws.steer, nprob, F, T, tsplit, B, b0, Bc);
+        MISO_LAUNCHED("eig_kernel");
+        solve_kernel<M><<<Bc * S, 256, (size_t)F * sizeof(double2), stream>>>(ws.partial, ws.steer, w, F, T, tsplit, (double)epsi, B, b0, Bc);
+        MISO_LAUNCHED("solve_kernel");
+        apply_kernel<M><<<dim3(ceil_div(F, kFx), ceil_div(T, kApplyTile), Bc), blk, 0, stream>>>(
+            mix, sb, sm, st, sf, w, reinterpret_cast<float2 *>(d_out), S, B, T, F, b0);
+        MISO_LAUNCHED("apply_kernel");
+        // algorithmic bytes: mixture + S sources in, S outputs out (160 T F per utterance for S = 2, M = 6)
+        prof_end(stream, 0.0, (double)Bc * T * F * sizeof(float2) * ((double)M * (1 + S) + S), MISO_PROF_MVDR);
+    }
     return MISO_OK;
 }
 
@@ -581,7 +633,7 @@ int run_scm(const void *d_src, int64_t src_ss, const void *d_mix, int64_t sb, in
             int S, int B, int T, int F, cudaStream_t stream) {
     const int tsplit = pick_tsplit(B, F);
     scm_kernel<M><<<dim3(ceil_div(F, kFx), tsplit, B), dim3(kFx, kTy), 0, stream>>>(
-        reinterpret_cast<const float2 *>(d_src), src_ss, reinterpret_cast<const float2 *>(d_mix), sb, sm, st, sf, d_partial, S, B, T, F, tsplit);
+        reinterpret_cast<const float2 *>(d_src), src_ss, reinterpret_cast<const float2 *>(d_mix), sb, sm, st, sf, d_partial, S, B, T, F, tsplit, 0);
     MISO_LAUNCHED("scm_kernel");
     return MISO_OK;
 }
@@ -597,12 +649,12 @@ int run_weights(const float *d_partial, int nsplit, int T_total, void *d_weights
     double2 *steer = reinterpret_cast<double2 *>(d_ws);
     const int nprob = B * S * F;
     if constexpr (M == 6)
-        eig6_kernel<M><<<ceil_div(2 * nprob, 64), 64, 0, stream>>>(d_partial, steer, nprob, F, T_total, nsplit);
+        eig6_kernel<M><<<ceil_div(2 * nprob, 64), 64, 0, stream>>>(d_partial, steer, nprob, F, T_total, nsplit, B, 0, B);
     else
-        eig_generic_kernel<M><<<ceil_div(nprob, 64), 64, 0, stream>>>(d_partial, steer, nprob, F, T_total, nsplit);
+        eig_generic_kernel<M><<<ceil_div(nprob, 64), 64, 0, stream>>>(d_partial, steer, nprob, F, T_total, nsplit, B, 0, B);
     MISO_LAUNCHED("eig_kernel");
     solve_kernel<M><<<B * S, 256, (size_t)F * sizeof(double2), stream>>>(d_partial, steer, reinterpret_cast<float2 *>(d_weights), F, T_total,
-                                                                      nsplit, (double)epsi);
+                                                                      nsplit, (double)epsi, B, 0, B);
     MISO_LAUNCHED("solve_kernel");
     return MISO_OK;
 }
@@ -612,7 +664,7 @@ int run_apply(const void *d_mix, int64_t sb, int64_t sm, int64_t st, int64_t sf,
               int F, cudaStream_t stream) {
     apply_kernel<M><<<dim3(ceil_div(F, kFx), ceil_div(T, kApplyTile), B), dim3(kFx, kTy), 0, stream>>>(
         reinterpret_cast<const float2 *>(d_mix), sb, sm, st, sf, reinterpret_cast<const float2 *>(d_weights), reinterpret_cast<float2 *>(d_out), S,
-        B, T, F);
+        B, T, F, 0);
     MISO_LAUNCHED("apply_kernel");
     return MISO_OK;
 }
