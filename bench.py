@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- frames/sec of the MISO hot path on B200 (see DESIGN.md section "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch_gpu] [--workload NAME]
 
 Workloads (BASELINE.json configs):
   miso1_paper   (default, configs[1]) MISO_1 separation forward, per-GPU batch 16 x 6 mics x 257 bins x
                 500 frames, 8-block "paper" layout (model.py:13-14,30 comments)
   miso1_ref     the same on the shipped 7-block / 129-bin / 501-frame layout
   pipeline_ref  (configs[2]) STFT -> MISO1 x6 shifts -> align -> MVDR x2 -> MISO3 x2, per-GPU batch 32, REF layout
+  pipeline_paper  the same at the PAPER shape (8 blocks, 512-point STFT: 257 bins x 500 frames), per-GPU batch 32
   train_paper   (configs[3] per-GPU shape) MISO_1 training step: forward + loss_uPIT + backward + gradient all-reduce +
                 Adam, 8 utterances per GPU, PAPER layout (tools/train_step.py prints the line)
 
@@ -16,9 +17,12 @@ frames/s with inputs resident in HBM; `e2e` is the same through the public API w
 buffers (H2D of the inputs and D2H of the result inside the timed region).  Under torchrun every
 rank processes its own batch (weak scaling, no data-path collective); time = max over ranks.
 
---impl reference times the reference's own CPU algorithm for the same workload on the host cores.
-/root/reference does not exist on the GPU box, so this is the oracle port (oracle/miso_net_torch.py,
-pinned to the real reference by tests/golden); rank 0 only.
+--impl reference times the reference's own CPU algorithm for the same workload (the full per-GPU batch per step)
+on the host cores.  /root/reference does not exist on the GPU box, so this is the oracle port
+(oracle/miso_net_torch.py, pinned to the real reference by tests/golden); rank 0 only.
+--impl torch_gpu is a CONTEXT line, not the reference arm: the same port run unchanged on the B200 through
+stock PyTorch / cuDNN (fp32 with TF32 off and on) -- the library incumbent on the same chip; the default line
+carries it as `gpu_library_baseline`.
 """
 import argparse
 import json
@@ -45,12 +49,15 @@ WORKLOADS = {
                         desc="MISO1 separation fwd, batch 16 x 6ch x 257bin x 500fr per GPU (BASELINE configs[1])"),
     "miso1_ref": dict(layout="REF", B=16, M=6, T=501, F=129, kind="miso1",
                       desc="MISO1 separation fwd, batch 16 x 6ch x 129bin x 501fr per GPU (shipped config shape)"),
-    "pipeline_ref": dict(layout="REF", B=32, M=6, T=501, F=129, kind="pipeline", n_samples=32000,
+    "pipeline_ref": dict(layout="REF", B=32, M=6, T=501, F=129, kind="pipeline", n_samples=32000, nperseg=256, noverlap=192,
                          desc="STFT->MISO1x6->align->MVDRx2->MISO3x2, batch 32 per GPU (BASELINE configs[2], REF shape)"),
+    "pipeline_paper": dict(layout="PAPER", B=32, M=6, T=500, F=257, kind="pipeline", n_samples=499 * 128, nperseg=512, noverlap=384,
+                           desc="STFT->MISO1x6->align->MVDRx2->MISO3x2, batch 32 x 6ch x 257bin x 500fr per GPU (BASELINE configs[2], PAPER shape)"),
 }
 PROF_FAMILIES = {0: "conv_fp32_kernel (fp32 FMA implicit-GEMM conv / deconv / pointwise)",
                  1: "conv_tc_kernel (tcgen05 implicit-GEMM 3x3 (de)conv, shifted-descriptor im2col: strided / transposed / narrow stages)",
-                 2: "tcn_pw_kernel (tcgen05 pointwise convs of the TCN)", 3: "mvdr kernels",
+                 2: "tcn_pw_kernel (tcgen05 pointwise convs of the TCN)",
+                 3: "mvdr kernels (scm -> eig6 -> solve -> apply per call: HBM-bound streaming + latency-bound 6x6 eigen/solve)",
                  5: "conv_*_prep_kernel (per-sample weight images and border-bias sums of the tensor-core convs)",
                  4: "conv_rs_kernel (row-streaming tcgen05 3x3 conv, frame taps merged into N: the DenseBlock convs)"}
 CONV_MODES = {"fp32": ("f32", "fp32 FMA everywhere (reference-grade, ~2e-6 rel. error)"),
@@ -162,7 +169,7 @@ def run_ours(args, wl, rank, world, local):
         m3.load_state_dict(make_state_dict_np(m3, 1))
         m3 = m3.cuda(dev).eval()
         m3.conv_mode = args.conv_mode
-        pipe = pipeline.MisoBfMiso(m1, m3)
+        pipe = pipeline.MisoBfMiso(m1, m3, nperseg=wl["nperseg"], noverlap=wl["noverlap"])
         g = torch.Generator().manual_seed(100 + rank)
         host_in = (0.05 * torch.randn(B, wl["n_samples"], M, generator=g)).pin_memory()
         dev_in = host_in.to(dev)
@@ -326,10 +333,18 @@ def run_ours(args, wl, rank, world, local):
                              "so the kernel's own ceiling is 0.29 of the bf16 peak at N = 3 cout = 96 (0.86 in bf16 mode); "
                              "all_tensor_core_kernels aggregates every tcgen05 kernel of the step"},
     }
+    mv = fams.get(PROF_FAMILIES[3])
+    if mv and mv["launches"]:
+        gbs = mv["bytes"] / (mv["ms"] * 1e-3) / 1e9
+        line["roofline"]["mvdr"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                                    "ms_per_step": mv["ms"] / args.steps, "calls_per_step": mv["launches"] // max(args.steps, 1),
+                                    "note": "algorithmic bytes (mixture + sources in, outputs out: 160 T F per utterance) / CUDA-event time of "
+                                            "the four kernels of each miso_mvdr_fwd call; the 6x6 eigenvector and solve kernels are latency bound"}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl, steps=1)
+        line["cpu_baseline"] = cpu_baseline(wl, steps=3)
         if wl["kind"] == "miso1":   # "SI-SDR vs ref" of the metric: utterance 0 of the bench batch against the oracle (checker only)
             line["parity"] = parity_vs_oracle(wl, m1, host_in, out0)
+            line["gpu_library_baseline"] = torch_gpu_baseline(wl, dev, steps=3, value_ours=line["value"])
     return line
 
 
@@ -343,6 +358,65 @@ def parity_vs_oracle(wl, model, host_in, out0):
     err = float((out0 - ref).norm() / ref.norm())
     return {"rel_err": err, "si_sdr_vs_ref_db": -20.0 * float(np.log10(max(err, 1e-30))), "tolerance": 1e-3,
             "sample": "utterance 0 of the bench batch, complex64 [1,2,T,F], oracle = reference algorithm in fp32 on the CPU"}
+
+
+# ------------------------------------------------------------------------------------ library incumbent on the GPU
+def torch_gpu_baseline(wl, dev, steps=3, value_ours=None, batch=None):
+    """Context for the headline ratio: the reference algorithm (oracle port = the same ATen ops as
+    model.py) run UNCHANGED on the same B200 through stock PyTorch / cuDNN, fp32 with TF32 off and on, same shape and batch.
+    A baseline leg like cpu_baseline: the only place the bench runs oracle/ on the GPU."""
+    from oracle import miso_net_torch as mnt
+    layout, M, T, F = wl["layout"], wl["M"], wl["T"], wl["F"]
+    B = batch or wl["B"]
+    cfg, sd = oracle_state_dict("miso1", layout, 0)
+    sd_cpu = sd
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    mix = rand_spec(100, (B, M, T, F), "cpu")
+    mix_d = mix.to(dev)
+    ref1 = mnt.miso1_forward(sd_cpu, cfg, mix[0:1])                    # fp32 CPU = the parity yardstick
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            y = None
+            for _ in range(2):
+                y = mnt.miso1_forward(sd, cfg, mix_d)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                y = mnt.miso1_forward(sd, cfg, mix_d)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            err = float((y[0:1].cpu() - ref1).norm() / ref1.norm())
+            out[name] = {"value": B * T / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "rel_err_vs_fp32_cpu": err}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    out["what"] = (f"oracle/miso_net_torch.miso1_forward on cuda through stock PyTorch {torch.__version__} / cuDNN, batch {B}, "
+                   f"{layout} layout, {T} frames x {F} bins, inputs resident, cudnn.benchmark on, {steps} steps after 2 warm-ups")
+    if value_ours:
+        out["ours_over_fp32"] = value_ours / out["fp32"]["value"]
+        out["ours_over_tf32"] = value_ours / out["tf32"]["value"]
+    return out
+
+
+def run_torch_gpu(args, wl, rank, world, local):
+    if rank != 0:
+        return None
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    g = torch_gpu_baseline(wl, dev, steps=max(1, args.steps))
+    return {"impl": "torch_gpu", "metric": "frames/sec MISO-BF-MISO fwd 6ch/257bin at 1/2/4/8 GPU; SI-SDR vs ref",
+            "value": g["fp32"]["value"], "unit": "frames/s", "n_gpus": 1, "steps": max(1, args.steps), "warmup": 2,
+            "ms_per_step": g["fp32"]["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded random spectrograms, seeded random weights)",
+            "config": {"workload": wl["desc"], "layout": wl["layout"], "per_gpu_batch": wl["B"], "frames": wl["T"], "bins": wl["F"],
+                       "mics": wl["M"], "note": "context line (library incumbent on the same GPU), not the reference arm"},
+            "gpu_library_baseline": g}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -385,7 +459,10 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return None
     steps = max(1, min(args.steps, 5))
-    cb = cpu_baseline(wl, steps=steps, warmup=max(1, min(args.warmup, 2)))
+    # the arm's config is the ours-arm's: one step = the whole per-GPU batch (16 utterances take ~4 s on 16 cores); the
+    # pipeline workloads (6 + 2 network forwards and two MVDRs per utterance) are bounded to 2 utterances per step
+    utts = wl["B"] if wl["kind"] == "miso1" else 2
+    cb = cpu_baseline(wl, steps=steps, warmup=max(1, min(args.warmup, 2)), utts=utts)
     return {
         "impl": "reference",
         "metric": "frames/sec MISO-BF-MISO fwd 6ch/257bin at 1/2/4/8 GPU; SI-SDR vs ref",
@@ -393,8 +470,9 @@ def run_reference(args, wl, rank, world):
         "ms_per_step": cb["seconds_best"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (seeded random spectrograms, seeded random weights)",
         "config": {"workload": wl["desc"], "layout": wl["layout"], "frames": wl["T"], "bins": wl["F"], "mics": wl["M"],
+                   "per_gpu_batch": wl["B"], "utterances_per_step": utts,
                    "note": "reference CPU algorithm (oracle port of model.py/tester.py; /root/reference is absent on the GPU "
-                           "box), all host threads, each step = 1 utterance of the workload"},
+                           f"box), all host threads, each step = {utts} utterance(s) of the workload in one batch"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -405,7 +483,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--workload", default="miso1_paper", choices=sorted(WORKLOADS) + ["train_paper"])
     ap.add_argument("--conv-mode", default="bf16x3", choices=sorted(CONV_MODES),
                     help="compute path of the conv stack (default: the parity-grade tensor-core mode)")
@@ -429,6 +507,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         line = run_reference(args, wl, rank, world)
+    elif args.impl == "torch_gpu":
+        if wl["kind"] != "miso1":
+            raise SystemExit("--impl torch_gpu covers the MISO1 forward workloads")
+        line = run_torch_gpu(args, wl, rank, world, local)
     else:
         from misonet_b200 import distributed as D
         if not torch.cuda.is_available():

@@ -161,6 +161,13 @@ int miso_wave_to_int16(const float *d_x, int16_t *d_out, int64_t n, float scale,
  * gradients on tensor cores with the same bf16 hi/lo split and fp32 accumulation; the InstanceNorm2d / ELU / gLN /
  * PReLU / depthwise / InstanceNorm1d backward kernels are fp32 elementwise / reduction kernels in every mode. */
 int64_t miso_net_grad_numel(const miso_net_t *net);
+/* Gradient buckets for a data-parallel step (trainer.py:205-212 is the step; the reference itself is single-GPU): the flat
+ * gradient buffer as contiguous element ranges [begin[k], end[k]) in the ORDER IN WHICH miso_net_backward COMPLETES THEM
+ * (upper decoders, lower decoders, TCN, upper encoders, lower encoders).  miso_net_backward records an event after the last
+ * kernel of every bucket; miso_net_wait_grad_bucket makes `stream` wait for bucket k of the most recent backward, so a
+ * communication stream can all-reduce bucket k while the rest of the backward is still running.  Returns the bucket count. */
+int miso_net_grad_buckets(const miso_net_t *net, int64_t *begin, int64_t *end, int capacity);
+int miso_net_wait_grad_bucket(miso_net_t *net, int bucket, void *stream);
 size_t miso_net_train_workspace_bytes(const miso_net_t *net, int B, int T, int F);
 int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, int T, int F, void *d_ws,
                            size_t ws_bytes, void *stream);

@@ -44,6 +44,8 @@ SIGNATURES = {
     "miso_net_input_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "miso_net_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "miso_net_grad_numel": (c_int64, [c_void_p]),
+    "miso_net_grad_buckets": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), c_int]),
+    "miso_net_wait_grad_bucket": (c_int, [c_void_p, c_int, c_void_p]),
     "miso_net_train_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
     "miso_net_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "miso_net_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -356,6 +356,9 @@ struct miso_net {
     // forked branch of the forward: the DenseBlock group-preparation launches run next to the conv kernels (Walker::dense)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // gradient buckets of the backward pass, in the order in which they complete (decoders top-down, TCN, encoders): an
+    // event per bucket lets the caller start that bucket's all-reduce while the rest of the backward is still running
+    cudaEvent_t bucket_ev[8] = {};
 };
 
 namespace miso {
@@ -1262,6 +1265,8 @@ int miso_net_destroy(miso_net_t *net) {
     if (net->side_stream) cudaStreamDestroy(net->side_stream);
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
     if (net->ev_join) cudaEventDestroy(net->ev_join);
+    for (auto &e : net->bucket_ev)
+        if (e) cudaEventDestroy(e);
     if (net->arena) cudaFree(net->arena);
     delete net;
     return MISO_OK;
@@ -1789,6 +1794,65 @@ struct Backward {
 
 extern "C" {
 
+}  // extern "C"
+
+namespace miso {
+namespace {
+// Bucket k covers the parameters [first[k], first[k + 1]) of one completion group; groups in completion order:
+// decoders nb/2..nb-1, decoders 0..nb/2-1, TCN, encoders nb/2..nb-1, encoders 0..nb/2-1 (the backward walks the layers
+// from the output to the input, model.py:97-106 reversed).  Parameters are in key order (encoders, decoders, TCN), so each
+// group is one contiguous range of the flat gradient buffer.
+constexpr int kGradBuckets = 5;
+struct BucketTable {
+    int lo[kGradBuckets], hi[kGradBuckets];  // parameter index ranges, completion order
+};
+BucketTable grad_buckets(const miso_net *n) {
+    auto first_with = [&](const std::string &prefix) {
+        for (size_t i = 0; i < n->params.size(); ++i)
+            if (n->params[i].key.compare(0, prefix.size(), prefix) == 0) return (int)i;
+        return (int)n->params.size();
+    };
+    const int h = n->nb / 2;
+    const int e0 = 0, e1 = first_with("encoders." + std::to_string(h) + "."), d0 = first_with("decoders.0."),
+              d1 = first_with("decoders." + std::to_string(h) + "."), t0 = first_with("TCN."), end = (int)n->params.size();
+    BucketTable b;
+    b.lo[0] = d1, b.hi[0] = t0;   // upper decoders (run first)
+    b.lo[1] = d0, b.hi[1] = d1;   // lower decoders
+    b.lo[2] = t0, b.hi[2] = end;  // TCN
+    b.lo[3] = e1, b.hi[3] = d0;   // upper encoders
+    b.lo[4] = e0, b.hi[4] = e1;   // lower encoders (run last)
+    return b;
+}
+int bucket_of_param(const BucketTable &b, int p) {
+    for (int k = 0; k < kGradBuckets; ++k)
+        if (p >= b.lo[k] && p < b.hi[k]) return k;
+    return kGradBuckets - 1;
+}
+}  // namespace
+}  // namespace miso
+
+extern "C" {
+
+int miso_net_grad_buckets(const miso_net_t *net, int64_t *begin, int64_t *end, int capacity) {
+    MISO_REQUIRE(net && begin && end, "miso_net_grad_buckets: null argument");
+    MISO_REQUIRE(capacity >= kGradBuckets, "miso_net_grad_buckets: capacity %d < %d", capacity, kGradBuckets);
+    std::vector<int64_t> off;
+    param_grad_offsets(net, off);
+    const BucketTable b = grad_buckets(net);
+    for (int k = 0; k < kGradBuckets; ++k) {
+        begin[k] = off[b.lo[k]];
+        end[k] = off[b.hi[k]];
+    }
+    return kGradBuckets;
+}
+
+int miso_net_wait_grad_bucket(miso_net_t *net, int bucket, void *stream) {
+    MISO_REQUIRE(net && bucket >= 0 && bucket < kGradBuckets, "miso_net_wait_grad_bucket: bad bucket %d", bucket);
+    MISO_REQUIRE(net->bucket_ev[bucket], "miso_net_wait_grad_bucket: no backward pass has run on this handle");
+    MISO_CUDA(cudaStreamWaitEvent(as_stream(stream), net->bucket_ev[bucket], 0));
+    return MISO_OK;
+}
+
 int64_t miso_net_grad_numel(const miso_net_t *net) {
     if (!net) return -1;
     int64_t t = 0;
@@ -1847,9 +1911,15 @@ int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int 
     param_grad_offsets(net, bw.goff);
     MISO_CUDA(cudaMemsetAsync(d_grads, 0, (size_t)bw.goff.back() * sizeof(float), st));
     MISO_CUDA(cudaMemsetAsync(pl.grad_base, 0, pl.grad_bytes, st));
+    const BucketTable bt = grad_buckets(net);
+    for (int k = 0; k < kGradBuckets; ++k)
+        if (!net->bucket_ev[k]) MISO_CUDA(cudaEventCreateWithFlags(&net->bucket_ev[k], cudaEventDisableTiming));
+    auto bucket_of = [&](const ConvRec &r) { return r.kind == 1 ? 2 : bucket_of_param(bt, r.cd->w); };
     for (int i = (int)recs.size() - 1; i >= 0; --i) {
         rc = recs[i].kind == 1 ? bw.tcn() : bw.conv_layer(recs[i], d_gy);
         if (rc) return rc;
+        // the last layer of a completion group: every gradient of the bucket has been written
+        if (i == 0 || bucket_of(recs[i - 1]) != bucket_of(recs[i])) MISO_CUDA(cudaEventRecord(net->bucket_ev[bucket_of(recs[i])], st));
     }
     return MISO_OK;
 }

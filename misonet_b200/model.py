@@ -126,14 +126,9 @@ class _NetFunction(torch.autograd.Function):
             _lib.check(lib.miso_net_backward(m._handle, _lib.ptr(ctx.x_cl), _lib.ptr(gy), B, T, F, _lib.ptr(ws), ws.numel(),
                                              _lib.ptr(flat), st), "miso_net_backward")
             if m.data_parallel:
-                # the flat buffer IS the gradient bucket: one in-place all-reduce, weighted by this rank's utterance count
-                # (each rank's loss is a mean over its own utterances), no packing copies
                 import torch.distributed as dist
                 if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                    flat[numel] = 1.0
-                    flat.mul_(float(B))
-                    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-                    flat.div_(flat[numel:].clone())
+                    m._allreduce_buckets(flat, numel, B, dev)
         grads, off = [], 0
         for shp in ctx.param_shapes:
             n = int(torch.Size(shp).numel())
@@ -387,6 +382,39 @@ class _MisoNet(nn.Module):
         _lib.check(lib.miso_net_forward_train(self._handle, _lib.ptr(x_cl), _lib.ptr(y_cl), B, T, F, _lib.ptr(self._ws_train),
                                               self._ws_train.numel(), _lib.stream_ptr()), "miso_net_forward_train")
         return y_cl
+
+    def _allreduce_buckets(self, flat, numel, n_local, dev):
+        """Data-parallel gradient reduction overlapped with the backward pass.  The flat gradient
+        buffer is cut into the library's completion-ordered buckets (miso_net_grad_buckets: upper decoders, lower decoders,
+        TCN, upper encoders, lower encoders); ``miso_net_backward`` -- already enqueued, still running -- records an event
+        per bucket, and a communication stream all-reduces each bucket in place as soon as its event fires, so only the last
+        (smallest) bucket's collective is exposed.  Every rank's gradient is that of the mean loss over ITS utterances
+        (criterion.py:59), so buckets are weighted by n_local / sum(n_local): the result is the gradient of the mean over
+        all utterances of the step.  Collective: NCCL all-reduce (SUM) of fp32, one call per bucket + one for the count."""
+        import torch.distributed as dist
+        lib = _lib.load()
+        if self.__dict__.get("_comm_stream") is None or self._comm_stream.device != dev:
+            self.__dict__["_comm_stream"] = torch.cuda.Stream(device=dev)
+            cap = 8
+            b0, b1 = (ctypes.c_int64 * cap)(), (ctypes.c_int64 * cap)()
+            nb = lib.miso_net_grad_buckets(self._handle, b0, b1, cap)
+            _lib.check(nb, "miso_net_grad_buckets")
+            self.__dict__["_grad_buckets"] = [(int(b0[k]), int(b1[k])) for k in range(nb)]
+        cs = self._comm_stream
+        main = torch.cuda.current_stream(dev)
+        flat.record_stream(cs)
+        with torch.cuda.stream(cs):
+            cnt = torch.full((1,), float(n_local), dtype=torch.float32, device=dev)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            w = float(n_local) / cnt                                   # device scalar: no host synchronisation
+            for k, (lo, hi) in enumerate(self._grad_buckets):
+                if hi <= lo:
+                    continue
+                _lib.check(lib.miso_net_wait_grad_bucket(self._handle, k, ctypes.c_void_p(cs.cuda_stream)), "miso_net_wait_grad_bucket")
+                seg = flat[lo:hi]
+                seg.mul_(w)
+                dist.all_reduce(seg, op=dist.ReduceOp.SUM)
+        main.wait_stream(cs)
 
     def _prepare(self, *tensors):
         self._ensure_handle()

@@ -40,7 +40,8 @@ def main():
     torch.manual_seed(0)
     model = MISO_1(2, 6, len(en), list(en), list(de), "IN").to(dev).train()
     model.conv_mode = args.conv_mode
-    model.data_parallel = True      # gradients are all-reduced in place inside backward (one flat NCCL bucket)
+    model.data_parallel = True      # gradients are all-reduced in place inside backward: completion-ordered buckets on a
+                                    # communication stream, overlapped with the rest of the backward (model._allreduce_buckets)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     mix = torch.from_numpy(synth.random_spec(100 + rank, (B, 6, T, F))).to(dev)
     refs = [torch.from_numpy(synth.random_spec(200 + 10 * rank + s, (B, T, F))).to(dev) for s in range(2)]
@@ -74,6 +75,25 @@ def main():
                 phases[k] += ev[k].elapsed_time(ev[k + 1])
             total_ms += ev[0].elapsed_time(ev[4])
     launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
+    # the same steps without the gradient all-reduce: the difference is the collective's EXPOSED time (what the overlap
+    # with the backward does not hide)
+    nodp_ms = None
+    if world > 1:
+        model.data_parallel = False
+        distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(args.steps + 1):
+            if it == 1:
+                e0.record()
+            opt.zero_grad(set_to_none=True)
+            criterion.loss_uPIT(2, model(mix), refs).backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+            opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        nodp_ms = distributed.max_over_ranks(e0.elapsed_time(e1) / args.steps, device=dev)
+        model.data_parallel = True
     # end to end: the same step fed from pinned host memory (H2D of the mixture and the references inside the timed
     # region) with the loss read back to the host every step
     distributed.barrier()
@@ -138,6 +158,11 @@ def main():
                        "layout": args.layout, "conv_mode": args.conv_mode, "global_batch": world * B},
             "phases_ms_rank0": {"forward+loss": phases[0] / args.steps, "backward+grad_allreduce": phases[1] / args.steps,
                                 "clip+adam": (phases[2] + phases[3]) / args.steps},
+            "collective": {"op": "NCCL all-reduce (SUM, fp32) of the flat parameter-gradient buffer in 5 completion-ordered buckets "
+                                 "(+ one 4-byte count), launched per bucket on a communication stream behind an event the backward records",
+                           "gradient_bytes": int(sum(p.numel() for p in model.parameters()) * 4),
+                           "ms_per_step_without_allreduce": nodp_ms,
+                           "exposed_ms": (ms - nodp_ms) if nodp_ms is not None else None},
             "higher_is_better": True, "scaling": "weak", "dtype": "bf16x3 forward / bf16x3 + fp32 backward",
             "e2e": {"value": world * B * T / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks,
