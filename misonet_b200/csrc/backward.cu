@@ -1091,6 +1091,7 @@ int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
                  "wgrad: input channel range must be 8-aligned (cin=%d coff=%d)", a.cin, a.x_coff);
     static const bool fma = getenv("MISO_WGRAD_FMA") && atoi(getenv("MISO_WGRAD_FMA")) != 0;  // debugging: the fp32 FMA GEMM
     if (fma) return a.cout <= 32 ? launch_wgrad_t<2>(a, st) : launch_wgrad_t<4>(a, st);
+    if (wgrad_tc_eligible(a)) return launch_wgrad_tc(a, st);  // tcgen05 GEMM over the raw planes (the DenseBlock convs)
     static const bool no_taps = getenv("MISO_WGRAD_TAPS") && atoi(getenv("MISO_WGRAD_TAPS")) == 0;  // debugging: per-tap kernel only
     if (!no_taps && wgrad_taps_ok(a)) return launch_wgrad_taps(a, st);
     return a.cout <= 32 ? launch_wgrad_mma<32, 4>(a, st) : launch_wgrad_mma<64, 2>(a, st);

@@ -41,8 +41,18 @@ struct WgradArgs {
     int dy_ctot, dy_coff, cout;
     int cout_real;  // output channels of the parameter tensor (cout_real < cout only for a padded network output)
     int KT, KF, stride_f, pad_t, pad_f, transposed;
+    // tcgen05 path (wgrad_tc.cu; the stride-1 pad-(1,1) 3x3 convs): dy as bf16 hi/lo planes [B][hi|lo][cout/8][T*Fout][8]
+    // (in_bwd_apply writes them for the data-gradient conv), a partial-accumulator scratch, and the constant-one pixels
+    __nv_bfloat16 *dyp = nullptr;
+    float *partial = nullptr;
+    size_t partial_bytes = 0;
+    __nv_bfloat16 *ones = nullptr;
 };
 int launch_wgrad(const WgradArgs &a, cudaStream_t st);
+bool wgrad_tc_eligible(const WgradArgs &a);
+size_t wgrad_tc_partial_bytes(int B);
+int wgrad_tc_fill_ones(__nv_bfloat16 *ones, size_t npix, cudaStream_t st);
+int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st);
 
 // packed forward weights [taps][cin][cout_pad] -> data-gradient weights [taps][cout][cin_pad]
 // flip = 1 reverses the tap order (a stride-1 transposed conv as a plain conv)

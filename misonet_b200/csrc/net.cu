@@ -458,6 +458,10 @@ struct Plan {
     size_t dyP_bytes = 0;
     char *dgP = nullptr;     // data gradient of a DenseBlock conv as planes (row-streaming kernel), added into the fp32 buffer
     size_t dgP_bytes = 0;
+    float *wgP = nullptr;    // tcgen05 weight gradient: per-CTA raw accumulators (wgrad_tc.cu)
+    size_t wgP_bytes = 0;
+    __nv_bfloat16 *wg_ones = nullptr;  // ... and its constant-one pixels [T * max F][8]
+    size_t wg_ones_pix = 0;
     void *tcn_wimg = nullptr;  // tensor-core pointwise convs: weight images and W beta / W gamma vectors (tcn.cu)
     float *tcn_wvec = nullptr;
     std::vector<double *> sS, sU, g1, g2;
@@ -590,6 +594,10 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
                 if (dense_dec(j)) maxi = std::max(maxi, (size_t)pl.D[j].ctot * pl.D[j].F);
             pl.dgP_bytes = (size_t)B * maxi * T * 4;
             pl.dgP = take(pl.dgP_bytes);
+            pl.wgP_bytes = wgrad_tc_partial_bytes(B);
+            pl.wgP = reinterpret_cast<float *>(take(pl.wgP_bytes));
+            pl.wg_ones_pix = (size_t)T * F;
+            pl.wg_ones = reinterpret_cast<__nv_bfloat16 *>(take(pl.wg_ones_pix * 16));
         }
     }
     if (tcn_pw_eligible(n->C)) {
@@ -1698,6 +1706,12 @@ struct Backward {
         w.pad_t = f.pad_t;
         w.pad_f = f.pad_f;
         w.transposed = f.transposed;
+        if (n->mode != 0 && ib.dyp) {  // tensor-core modes: the DenseBlock convs take the tcgen05 GEMM over the raw planes
+            w.dyp = ib.dyp;
+            w.partial = pl.wgP;
+            w.partial_bytes = pl.wgP_bytes;
+            w.ones = pl.wg_ones;
+        }
         rc = launch_wgrad(w, st);
         if (rc) return rc;
         if (r.in_grad) rc = dgrad(f, n->params[r.cd->w].d, r.cd->cout_pad, og, r.in_grad, tc);
@@ -1911,6 +1925,8 @@ int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int 
     param_grad_offsets(net, bw.goff);
     MISO_CUDA(cudaMemsetAsync(d_grads, 0, (size_t)bw.goff.back() * sizeof(float), st));
     MISO_CUDA(cudaMemsetAsync(pl.grad_base, 0, pl.grad_bytes, st));
+    rc = wgrad_tc_fill_ones(pl.wg_ones, pl.wg_ones_pix, st);
+    if (rc) return rc;
     const BucketTable bt = grad_buckets(net);
     for (int k = 0; k < kGradBuckets; ++k)
         if (!net->bucket_ev[k]) MISO_CUDA(cudaEventCreateWithFlags(&net->bucket_ev[k], cudaEventDisableTiming));
