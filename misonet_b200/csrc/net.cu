@@ -351,6 +351,19 @@ struct miso_net {
         std::vector<miso::ProfRec> recs;  // per-launch timing events baked into the graph (prof = 1)
     };
     std::vector<GraphEntry> graphs;
+    // the training step's launch sequences (forward on the training plan: ~250 launches; backward: ~900) as graphs too:
+    // kind 1 = miso_net_forward_train (p = x, q = y), kind 2 = miso_net_backward (p = dL/dy, q = flat gradients).  The
+    // first call with a given key runs eagerly (one-time set-up such as function attributes must not happen inside a
+    // capture), the second captures, later ones replay.
+    struct TrainGraph {
+        int kind;
+        const void *x, *p, *q;
+        void *ws;
+        int B, T, F, mode;
+        cudaGraphExec_t exec;  // null: seen once, not captured yet
+        uint64_t launches;
+    };
+    std::vector<TrainGraph> tgraphs;
     cudaStream_t cap_stream = nullptr;
     int use_graph = 1;
     // forked branch of the forward: the DenseBlock group-preparation launches run next to the conv kernels (Walker::dense)
@@ -1030,6 +1043,10 @@ int Walker::run(const void *d_x, float *d_y) {
 }
 
 int enqueue_forward(miso_net *net, const Plan &pl, const void *d_x, float *d_y, int B, int T, int F, cudaStream_t st);
+bool capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+}
 int ensure_side(miso_net *net) {
     if (net->side_stream) return MISO_OK;
     MISO_CUDA(cudaStreamCreateWithFlags(&net->side_stream, cudaStreamNonBlocking));
@@ -1269,6 +1286,8 @@ int miso_net_create(miso_net_t **out, int in_ch, int out_ch, int num_bottleneck,
 int miso_net_destroy(miso_net_t *net) {
     if (!net) return MISO_OK;
     for (auto &g : net->graphs) cudaGraphExecDestroy(g.exec);
+    for (auto &g : net->tgraphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (net->cap_stream) cudaStreamDestroy(net->cap_stream);
     if (net->side_stream) cudaStreamDestroy(net->side_stream);
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
@@ -1881,6 +1900,62 @@ size_t miso_net_train_workspace_bytes(const miso_net_t *net, int B, int T, int F
     return pl.total;
 }
 
+}  // extern "C"
+
+namespace miso {
+namespace {
+// Runs `enqueue(stream)` eagerly the first time a key is seen, captures it into a CUDA graph the second time and replays
+// the graph afterwards (miso_net::TrainGraph).
+template <class Fn>
+int train_graphed(miso_net *net, int kind, const void *x, const void *p, const void *q, void *ws, int B, int T, int F, cudaStream_t st,
+                  Fn enqueue) {
+    static const bool off = getenv("MISO_TRAIN_GRAPH") && atoi(getenv("MISO_TRAIN_GRAPH")) == 0;
+    if (!net->use_graph || off || prof_enabled()) return enqueue(st);
+    miso_net::TrainGraph *hit = nullptr;
+    for (auto &g : net->tgraphs)
+        if (g.kind == kind && g.x == x && g.p == p && g.q == q && g.ws == ws && g.B == B && g.T == T && g.F == F && g.mode == net->mode) {
+            hit = &g;
+            break;
+        }
+    if (hit && hit->exec) {
+        MISO_CUDA(cudaGraphLaunch(hit->exec, st));
+        g_launch_count.fetch_add(hit->launches, std::memory_order_relaxed);
+        return MISO_OK;
+    }
+    if (!hit) {
+        if (net->tgraphs.size() >= 8) {
+            if (net->tgraphs.front().exec) cudaGraphExecDestroy(net->tgraphs.front().exec);
+            net->tgraphs.erase(net->tgraphs.begin());
+        }
+        net->tgraphs.push_back(miso_net::TrainGraph{kind, x, p, q, ws, B, T, F, net->mode, nullptr, 0});
+        return enqueue(st);
+    }
+    if (!net->cap_stream) MISO_CUDA(cudaStreamCreateWithFlags(&net->cap_stream, cudaStreamNonBlocking));
+    const uint64_t l0 = g_launch_count.load();
+    MISO_CUDA(cudaStreamBeginCapture(net->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue(net->cap_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(net->cap_stream, &graph);
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture(training)");
+    ce = cudaGraphInstantiate(&hit->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        hit->exec = nullptr;
+        return cuda_fail(ce, "cudaGraphInstantiate(training)");
+    }
+    hit->launches = g_launch_count.load() - l0;
+    MISO_CUDA(cudaGraphLaunch(hit->exec, st));
+    return MISO_OK;
+}
+}  // namespace
+}  // namespace miso
+
+extern "C" {
+
 int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, int T, int F, void *d_ws, size_t ws_bytes,
                            void *stream) {
     MISO_REQUIRE(net && d_x && d_y && d_ws, "miso_net_forward_train: null argument");
@@ -1901,7 +1976,8 @@ int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, 
     if (rc) return rc;
     rc = ensure_side(net);
     if (rc) return rc;
-    return enqueue_forward(net, pl, d_x, d_y, B, T, F, as_stream(stream));
+    return train_graphed(net, 1, d_x, d_x, d_y, d_ws, B, T, F, as_stream(stream),
+                         [&](cudaStream_t s) { return enqueue_forward(net, pl, d_x, d_y, B, T, F, s); });
 }
 
 int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int T, int F, void *d_ws, size_t ws_bytes,
@@ -1915,29 +1991,32 @@ int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int 
         set_error("miso_net_backward: workspace %zu < required %zu bytes", ws_bytes, pl.total);
         return MISO_E_WORKSPACE;
     }
-    cudaStream_t st = as_stream(stream);
     std::vector<ConvRec> recs;
-    Walker w{net, pl, B, T, F, st, false};
+    Walker w{net, pl, B, T, F, nullptr, false};
     w.record = &recs;
     rc = w.run(d_x, nullptr);
     if (rc) return rc;
+    const BucketTable bt = grad_buckets(net);
+    for (int k = 0; k < kGradBuckets; ++k)
+        if (!net->bucket_ev[k]) MISO_CUDA(cudaEventCreateWithFlags(&net->bucket_ev[k], cudaEventDisableTiming));
+    return train_graphed(net, 2, d_x, d_gy, d_grads, d_ws, B, T, F, as_stream(stream), [&](cudaStream_t st) -> int {
     Backward bw{net, pl, B, T, F, st, d_grads, {}};
     param_grad_offsets(net, bw.goff);
     MISO_CUDA(cudaMemsetAsync(d_grads, 0, (size_t)bw.goff.back() * sizeof(float), st));
     MISO_CUDA(cudaMemsetAsync(pl.grad_base, 0, pl.grad_bytes, st));
     rc = wgrad_tc_fill_ones(pl.wg_ones, pl.wg_ones_pix, st);
     if (rc) return rc;
-    const BucketTable bt = grad_buckets(net);
-    for (int k = 0; k < kGradBuckets; ++k)
-        if (!net->bucket_ev[k]) MISO_CUDA(cudaEventCreateWithFlags(&net->bucket_ev[k], cudaEventDisableTiming));
     auto bucket_of = [&](const ConvRec &r) { return r.kind == 1 ? 2 : bucket_of_param(bt, r.cd->w); };
     for (int i = (int)recs.size() - 1; i >= 0; --i) {
         rc = recs[i].kind == 1 ? bw.tcn() : bw.conv_layer(recs[i], d_gy);
         if (rc) return rc;
         // the last layer of a completion group: every gradient of the bucket has been written
-        if (i == 0 || bucket_of(recs[i - 1]) != bucket_of(recs[i])) MISO_CUDA(cudaEventRecord(net->bucket_ev[bucket_of(recs[i])], st));
+        // (an EXTERNAL record: inside a captured graph it becomes an event-record node that fires on every replay)
+        if (i == 0 || bucket_of(recs[i - 1]) != bucket_of(recs[i]))
+            MISO_CUDA(cudaEventRecordWithFlags(net->bucket_ev[bucket_of(recs[i])], st, capturing(st) ? cudaEventRecordExternal : cudaEventRecordDefault));
     }
     return MISO_OK;
+    });
 }
 
 }  // extern "C"

@@ -56,7 +56,7 @@ struct WtcGeom {
 
 struct WtcArgs {
     WtcGeom g;
-    float *partial;   // [slice][cta][3 kf][128][N] fp32
+    float *partial;   // [cta][3 kf][128][N] fp32
     int B, T, F;
     int nper, fper;   // CTAs per sample, frames per CTA
     int pe0, pa0;     // first x / dy plane group of the slice
@@ -231,17 +231,34 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const WtcReduceArg
     __syncthreads();
     const int total = 9 * a.co_n * a.ci_n;
     const float *P = a.partial + (size_t)a.slice * a.ncta * 3 * 128 * a.N;
+    const size_t cstride = (size_t)3 * 128 * a.N;
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < total; o += gridDim.x * blockDim.x) {
-        const int ci = o % a.ci_n;
+        const int ci = o % a.ci_n;  // consecutive threads = consecutive input channels: coalesced partial reads
         int r = o / a.ci_n;
         const int co = r % a.co_n;
         r /= a.co_n;
         const int kf = r % 3, kt = r / 3;
         if (a.co0 + co >= a.cout_real) continue;
         const int row = (2 - kt) * a.co_n + co;
+        const float *p0 = P + ((size_t)kf * 128 + row) * a.N;
         float acc = 0.f;
-        for (int c = 0; c < a.ncta; ++c) {
-            const float *p = P + (((size_t)c * 3 + kf) * 128 + row) * a.N;
+        int c = 0;
+        for (; c + 8 <= a.ncta; c += 8) {  // eight CTAs' loads in flight; the additions keep the CTA order
+            float g[8], s1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float *p = p0 + (size_t)(c + u) * cstride;
+                g[u] = p[ci];
+                s1[u] = p[a.ci_n];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float2 af = aff[((c + u) / a.nper) * a.ci_n + ci];
+                acc = fmaf(af.x, g[u], fmaf(af.y, s1[u], acc));
+            }
+        }
+        for (; c < a.ncta; ++c) {
+            const float *p = p0 + (size_t)c * cstride;
             const float2 af = aff[(c / a.nper) * a.ci_n + ci];
             acc = fmaf(af.x, p[ci], fmaf(af.y, p[a.ci_n], acc));
         }
@@ -335,7 +352,8 @@ int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
     int nci, ci_n, nco, co_n;
     wtc_chunks(a, nci, ci_n, nco, co_n);
     const int nslice = nci * nco;
-    const int nper = std::max(1, std::min(a.T / 2, std::max(1, 148 / (a.B * nslice))));
+    // slices are launches of their own (one after the other), so every launch gets the whole machine: one wave of CTAs
+    const int nper = std::max(1, std::min(a.T / 2, std::max(1, 148 / a.B)));
     const int fper = (a.T + nper - 1) / nper;
     const int ncta = a.B * nper;
     // a.ones: bf16 pixels [npix][8] with channel 0 = 1 (wgrad_tc_fill_ones); uniform, so any [T][F] view of it works
@@ -356,7 +374,8 @@ int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
             WtcGeom g;
             MISO_REQUIRE(make_wtc_geom(a.Fin, cin_c, con_c, split, g), "wgrad_tc: geometry (cin %d cout %d F %d)", cin_c, con_c, a.Fin);
             const int slice = ic * nco + oc;
-            MISO_REQUIRE((size_t)(slice + 1) * ncta * 3 * 128 * g.N * sizeof(float) <= a.partial_bytes, "wgrad_tc: partial buffer too small");
+            // a slice's GEMM and its reduction are consecutive launches of one stream: every slice reuses the same region
+            MISO_REQUIRE((size_t)ncta * 3 * 128 * g.N * sizeof(float) <= a.partial_bytes, "wgrad_tc: partial buffer too small");
             CUtensorMap tm[5];
             for (int sp = 0; sp < 2; ++sp) {
                 // x planes [B][hi|lo][x_ctot/8][T][F][8]: {8 ch, bins, frames, groups, samples}
@@ -404,7 +423,7 @@ int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
             }
             WtcArgs k{};
             k.g = g;
-            k.partial = a.partial + (size_t)slice * ncta * 3 * 128 * g.N;
+            k.partial = a.partial;
             k.B = a.B;
             k.T = a.T;
             k.F = a.Fin;
@@ -441,7 +460,7 @@ int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
             r.co0 = co0;
             r.co_n = con_c;
             r.N = g.N;
-            r.slice = slice;
+            r.slice = 0;
             const int total = 9 * con_c * cin_c;
             wgrad_tc_reduce_kernel<<<std::min(2 * 148, (total + 255) / 256), 256, (size_t)a.B * cin_c * sizeof(float2), st>>>(r);
             MISO_LAUNCHED("wgrad_tc_reduce_kernel");

@@ -118,10 +118,11 @@ class _NetFunction(torch.autograd.Function):
         g = gout.to(torch.complex64).contiguous()
         st = _lib.stream_ptr()
         with torch.cuda.device(dev):
-            gy = torch.empty(B, T, F, (2 * S + 3) // 4 * 4, dtype=torch.float32, device=dev)
+            # persistent buffers: the backward's ~900 launches are replayed as a CUDA graph keyed by these pointers
+            gy = m._buffer("gy_train", (B, T, F, (2 * S + 3) // 4 * 4), torch.float32, dev)
             _lib.check(lib.miso_grad_pack(_lib.ptr(g), _lib.ptr(gy), B, S, T, F, st), "miso_grad_pack")
             numel = lib.miso_net_grad_numel(m._handle)
-            flat = torch.empty(numel + 1, dtype=torch.float32, device=dev)     # + 1: the utterance count rides along
+            flat = m._buffer("flat_grads", (numel,), torch.float32, dev)
             ws = m._ws_train
             _lib.check(lib.miso_net_backward(m._handle, _lib.ptr(ctx.x_cl), _lib.ptr(gy), B, T, F, _lib.ptr(ws), ws.numel(),
                                              _lib.ptr(flat), st), "miso_net_backward")
@@ -129,6 +130,9 @@ class _NetFunction(torch.autograd.Function):
                 import torch.distributed as dist
                 if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                     m._allreduce_buckets(flat, numel, B, dev)
+            # autograd may alias what it is handed as .grad (and accumulate into it): give it a copy, not the buffer the
+            # next backward overwrites
+            flat = flat.clone()
         grads, off = [], 0
         for shp in ctx.param_shapes:
             n = int(torch.Size(shp).numel())
@@ -306,7 +310,7 @@ class _MisoNet(nn.Module):
         key = (name, tuple(shape), dtype, dev)
         t = self._bufs.get(key)
         if t is None:
-            if len(self._bufs) > 16:
+            if len(self._bufs) > 64:
                 self._bufs.clear()
             t = torch.empty(shape, dtype=dtype, device=dev)
             self._bufs[key] = t
@@ -377,7 +381,9 @@ class _MisoNet(nn.Module):
         if self._ws_train is None or self._ws_train.numel() < nbytes or self._ws_train.device != dev:
             self._ws_train = None
             self._ws_train = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        y_cl = torch.empty(B, T, F, self._out_ch, dtype=torch.float32, device=dev)
+        # persistent buffers (input planes, output, workspace): stable pointers let the library replay the training
+        # forward as a CUDA graph from the third step on (miso_net_forward_train)
+        y_cl = self._buffer("y_train", (B, T, F, self._out_ch), torch.float32, dev)
         self._train_token += 1
         _lib.check(lib.miso_net_forward_train(self._handle, _lib.ptr(x_cl), _lib.ptr(y_cl), B, T, F, _lib.ptr(self._ws_train),
                                               self._ws_train.numel(), _lib.stream_ptr()), "miso_net_forward_train")
