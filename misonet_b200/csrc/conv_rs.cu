@@ -114,6 +114,7 @@ struct RsArgs {
     int out_ctot, out_coff, cout;
     size_t out_lo_off;
     int use_lo, elu;
+    int out_cl;  // 1: the output is fp32 channels-last [B][T*F][out_ctot] and the result is ADDED to it (data gradients)
     long long *trace;  // debug: clock64 event log of CTA 0 (tools/tc_trace.py), or null
     RsFuse fuse;
 };
@@ -706,6 +707,21 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                 ssq[q] = fmaf(y[q], y[q], ssq[q]);
                             }
                             const int pix = t * a.F + f;
+                            if (a.out_cl) {
+                                // data gradient: accumulate into the fp32 channels-last gradient of the conv's input
+                                float *o = reinterpret_cast<float *>(a.out) + ((size_t)b * npix + pix) * a.out_ctot + a.out_coff + cb;
+#pragma unroll
+                                for (int q = 0; q < 16; q += 4) {
+                                    if (cb + q < a.cout) {
+                                        float4 old = *reinterpret_cast<float4 *>(o + q);
+                                        old.x += y[q];
+                                        old.y += y[q + 1];
+                                        old.z += y[q + 2];
+                                        old.w += y[q + 3];
+                                        *reinterpret_cast<float4 *>(o + q) = old;
+                                    }
+                                }
+                            } else
 #pragma unroll
                             for (int g8 = 0; g8 < 16; g8 += 8) {
                                 const int co = cb + g8;
@@ -935,9 +951,16 @@ bool rs_shape_ok(const ConvArgs &a) {
         const int S = 128 / (a.Fin + 1);
         if (a.Fin < packed_min || a.T / S < 4) return false;
     }
-    if (a.in_layout != LAYOUT_PLANES || a.out_layout != LAYOUT_PLANES) return false;
-    if (a.in_ctot % 8 || a.in_coff % 8 || a.out_ctot % 8 || a.out_coff % 8 || a.cout % 8) return false;
-    if (a.resid || a.norm_mode == NORM_GLN) return false;
+    if (a.in_layout != LAYOUT_PLANES) return false;
+    if (a.in_ctot % 8 || a.in_coff % 8 || a.cout % 8) return false;
+    if (a.out_layout == LAYOUT_PLANES) {
+        if (a.out_ctot % 8 || a.out_coff % 8 || a.resid) return false;
+    } else {
+        // fp32 channels-last output: only as an in-place accumulation (resid == out), no ELU / statistics
+        if (a.resid != reinterpret_cast<const float *>(a.out) || a.resid_ctot != a.out_ctot || a.resid_coff != a.out_coff) return false;
+        if (a.out_ctot % 4 || a.out_coff % 4 || a.elu || a.out_sums) return false;
+    }
+    if (a.norm_mode == NORM_GLN) return false;
     if (a.T < 2) return false;
     return true;
 }
@@ -1112,6 +1135,7 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
     k.out_lo_off = a.out_lo_off;
     k.use_lo = a.use_lo;
     k.elu = a.elu;
+    k.out_cl = a.out_layout == LAYOUT_CL_F32 ? 1 : 0;
     k.trace = (g_rs_trace && a.cin == g_rs_trace_cin && a.Fin == g_rs_trace_fin) ? g_rs_trace : nullptr;
     k.fuse = fuse;
     dim3 grid(rs_grid(a, g), 1, 1);

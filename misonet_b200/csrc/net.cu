@@ -1129,22 +1129,35 @@ bool dgrad_tc_ok(const ConvArgs &f, const ConvArgs &d, const Plan &pl, int B, in
 // configuration if it writes planes, so it runs on conv_rs in chunks of <= 64 output channels into pl.dgP (the kernel's
 // N limit; the small dL/dy is re-read per chunk) and planes_accumulate_kernel adds the result into the fp32 gradient.
 constexpr int kRsChunk = 64;
+// DenseBlock data gradients on the row-streaming kernel in chunks of <= 64 output channels (its N limit) into a planes
+// scratch that planes_accumulate_kernel adds to the fp32 gradient.  MISO_DGRAD_RS_CL=1: the kernel's epilogue adds into
+// the fp32 gradient buffer itself (no scratch, no second kernel) -- measured SLOWER on B200 (52.1 against 50.1 ms per
+// training step, 8 utterances PAPER): the read-modify-write stalls the epilogue warps that drain tensor memory.
+bool dgrad_rs_cl() {
+    static const bool on = getenv("MISO_DGRAD_RS_CL") && atoi(getenv("MISO_DGRAD_RS_CL")) != 0;
+    return on;
+}
 ConvArgs dgrad_rs_chunk(const ConvArgs &d, const Plan &pl, int T, int c0) {
     ConvArgs a = d;
-    const int ctot8 = (d.cout + 7) & ~7;
-    a.out = pl.dgP;
-    a.out_layout = LAYOUT_PLANES;
-    a.out_ctot = ctot8;
-    a.out_coff = c0;
-    a.out_lo_off = (size_t)ctot8 * T * d.Fout * 2;
     a.cout = std::min(kRsChunk, d.cout - c0);
     a.w = d.w ? d.w + c0 : nullptr;
-    a.resid = nullptr;
+    if (dgrad_rs_cl()) {
+        a.out_coff = d.out_coff + c0;
+        a.resid_coff = d.resid_coff + c0;
+    } else {
+        const int ctot8 = (d.cout + 7) & ~7;
+        a.out = pl.dgP;
+        a.out_layout = LAYOUT_PLANES;
+        a.out_ctot = ctot8;
+        a.out_coff = c0;
+        a.out_lo_off = (size_t)ctot8 * T * d.Fout * 2;
+        a.resid = nullptr;
+    }
     return a;
 }
 bool dgrad_rs_ok(const ConvArgs &d, int flip, const Plan &pl, int B, int T) {
     if (!flip || d.cout % 8) return false;
-    if ((size_t)B * ((d.cout + 7) & ~7) * T * d.Fout * 4 > pl.dgP_bytes) return false;
+    if (!dgrad_rs_cl() && (size_t)B * ((d.cout + 7) & ~7) * T * d.Fout * 4 > pl.dgP_bytes) return false;
     for (int c0 = 0; c0 < d.cout; c0 += kRsChunk)
         if (!conv_rs_eligible(dgrad_rs_chunk(d, pl, T, c0), 3)) return false;
     return true;
@@ -1622,6 +1635,7 @@ struct Backward {
                     rc = launch_conv_tc(dgrad_rs_chunk(d, pl, T, c0), 3, pl.scratch, st);
                     if (rc) return rc;
                 }
+                if (dgrad_rs_cl()) return MISO_OK;
                 return launch_planes_accumulate(reinterpret_cast<const __nv_bfloat16 *>(pl.dgP), (d.cout + 7) & ~7, din, d.out_ctot,
                                                 d.out_coff, d.cout, B, T * d.Fout, st);
             }
