@@ -1706,7 +1706,10 @@ struct Backward {
         ib.eps = kInEps;
         ib.plain = f.elu ? 0 : 1;
         const bool tc = r.in_grad != nullptr && use_tc(f);
-        ib.dyp = tc ? reinterpret_cast<__nv_bfloat16 *>(pl.dyP) : nullptr;
+        // dy as bf16 hi/lo planes: the input of the tensor-core data gradient AND of the tcgen05 weight gradient (which
+        // also serves layers without a data gradient, i.e. the first conv)
+        const bool planes_fit = n->mode != 0 && f.cout % 8 == 0 && (size_t)B * f.cout * T * f.Fout * 4 <= pl.dyP_bytes;
+        ib.dyp = (tc || planes_fit) ? reinterpret_cast<__nv_bfloat16 *>(pl.dyP) : nullptr;
         if (!ib.plain && (!f.out_sums || f.out_layout != LAYOUT_PLANES)) {
             set_error("backward: normalised layer without statistics");
             return MISO_E_STATE;

@@ -20,6 +20,15 @@
 // bf16x3: a_hi b_hi + a_hi b_lo + a_lo b_hi.  An MMA of width N >= 128 costs N / 2 cycles (tensor bound), so one input
 // frame of 128 pixels and 152 channels is 3 kf x 8 K-steps x 3 products x 80 cycles against ~2 k cycles of TMA traffic.
 //
+// The same kernel covers the other 3x3 layers of the stack through a per-tap table (WtcTaps): with K running over the
+// pixels of the COARSER of the two tensors,
+//   conv stride 1, pad p (p = 1: DenseBlocks, p = 0: the first layer)   dy bin = x bin - kf + p     A shifted by 2 - kf pixels
+//   transposed conv stride 1 (the last layer)                           dy bin = x bin + kf - p     A shifted by kf pixels
+//   conv stride (1,2), pad 0 (encoder down-sampling)                    x bin = 2 dy bin + kf       B = even / odd / even + 1
+//   transposed conv stride (1,2), pad 0 (decoder up-sampling)           dy bin = 2 x bin + kf       A = even / odd / even + 1
+// where even / odd are two tiles loaded with a TMA element stride of 2 along the bins.  For the transposed layers the
+// three stacked dy frames r-1, r, r+1 of input frame r are the taps kt = 0, 1, 2 (kt = 2, 1, 0 for the convs).
+//
 // A CTA owns a frame range of ONE sample (the affine is per sample) and an (input-channel chunk, output-channel chunk)
 // slice; it writes its raw accumulators to a partial buffer, and wgrad_tc_reduce_kernel applies rstd / shift and sums
 // the CTAs in a fixed order into the torch-layout gradient (deterministic: no atomics).
@@ -28,6 +37,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "bwd.cuh"
 #include "conv.cuh"
@@ -41,26 +51,40 @@ constexpr int kWtcSmemLimit = 227 * 1024;
 constexpr int kWtcMaxStages = 4;
 constexpr int kWtcMaxN = 160;
 
+struct WtcTaps {      // per bin tap kf: which tile (even / odd set) and how many pixels its start address is shifted
+    int aset[3], ashift[3], bset[3], bshift[3];
+    int nAset, nBset;             // tiles per operand (2: even and odd bins, TMA element stride 2)
+    int a_mul, a_org[2];          // first dy bin of a stage's tile = a_mul * h * Kpx + a_org[set]
+    int b_mul, b_org[2];          // first x bin ...
+};
+
 struct WtcGeom {
-    int Kpx;      // pixels per stage (64 / 32 / 16)
+    int Kpx;      // K pixels per stage (64 / 32 / 16)
     int nhalf;    // stages per frame
     int ngA;      // 8-channel groups of the output-channel chunk
     int ngE;      // 8-channel groups of the input-channel chunk
     int N;        // MMA N: 8 * (ngE + 1 ones group) rounded up to 16
-    int pitchA;   // pixels per dy row in shared memory (Kpx + 2: the kf shifts)
-    int a_box;    // bytes of one (hi | lo) dy tile: 3 frames x ngA groups x pitchA x 16
-    int a_set;    // ... rounded up to 128 (TMA destination alignment): distance between the hi and the lo tile
-    int b_set;    // bytes of one (hi | lo) x tile: N / 8 groups x Kpx x 16
+    int pitchA;   // pixels per dy row in shared memory (Kpx + the largest A shift)
+    int pitchB;   // pixels per x row (Kpx + the largest B shift)
+    int a_box;    // bytes of one dy tile: 3 frames x ngA groups x pitchA x 16
+    int a_set;    // ... rounded up to 128 (TMA destination alignment)
+    int b_set;    // bytes of one x tile: N / 8 groups x pitchB x 16
+    int a_sp, b_sp;  // distance between the hi and the lo tiles of an operand (all its sets)
     int off_b, stage, nstage, smem_total;
+    WtcTaps tp;
 };
 
 struct WtcArgs {
     WtcGeom g;
     float *partial;   // [cta][3 kf][128][N] fp32
-    int B, T, F;
+    int B, T;
     int nper, fper;   // CTAs per sample, frames per CTA
     int pe0, pa0;     // first x / dy plane group of the slice
     int rows;         // valid accumulator lanes (3 * output channels of the chunk)
+};
+
+struct WtcMaps {      // [hi | lo][set]
+    CUtensorMap y[2][2], e[2][2], ones[2];
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2) {
@@ -74,12 +98,10 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int n) {
 }
 
 template <int SPLIT>
-__global__ void __launch_bounds__(kWtcThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_constant__ CUtensorMap tm_e_lo,
-                const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
-                const __grid_constant__ CUtensorMap tm_ones, const WtcArgs a) {
+__global__ void __launch_bounds__(kWtcThreads, 1) wgrad_tc_kernel(const __grid_constant__ WtcMaps tm, const WtcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const WtcGeom &g = a.g;
+    const WtcTaps &tp = g.tp;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NSP = SPLIT == 3 ? 2 : 1;
     const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 64), bar_done = smem_u32(smem + 128);
@@ -98,7 +120,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // the x tiles' groups behind the real ones (the ones group of the lo set, the padding group up to N) are never loaded:
+    // the x tiles' groups behind the real ones (the ones group of the lo tiles, the padding group up to N) are never loaded:
     // zero the whole stage area once
     for (int i = tid; i < g.nstage * g.stage / 16; i += kWtcThreads) reinterpret_cast<uint4 *>(smem + 1024)[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -111,6 +133,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_consta
     const int b = cta / a.nper, q = cta - b * a.nper;
     const int r0 = q * a.fper, r1 = min(a.T, r0 + a.fper);
     const int nst = max(0, r1 - r0) * g.nhalf;  // stages of this CTA
+    const int eb = g.ngE * g.pitchB * 16;        // bytes of the x box of one tile
 
     if (warp == 0) {
         if (elect_one()) {
@@ -121,16 +144,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_consta
                 if (primed) mbar_wait(bar_empty + 8 * s, (uint32_t)ph);
                 const uint32_t full = bar_full + 8 * s;
                 const uint32_t sa = s_stage + (uint32_t)(s * g.stage);
-                const int eb = g.ngE * g.Kpx * 16;  // bytes of the x box of one plane set
-                mbar_expect_tx(full, (uint32_t)(NSP * (g.a_box + eb) + g.Kpx * 16));
+                mbar_expect_tx(full, (uint32_t)(NSP * (tp.nAset * g.a_box + tp.nBset * eb) + tp.nBset * g.pitchB * 16));
                 for (int sp = 0; sp < NSP; ++sp) {
-                    // dy: {8 ch, bins, groups, frames, sample} -> [frame][group][pixel]; bins start one left of the stage
-                    tma_load_5d(sa + (uint32_t)(sp * g.a_set), sp == 0 ? &tm_y_hi : &tm_y_lo, full, 0, h * g.Kpx - 1, a.pa0, r - 1, b);
+                    // dy: {8 ch, bins, groups, frames, sample} -> [frame][group][pixel]: frames r-1, r, r+1
+                    for (int st = 0; st < tp.nAset; ++st)
+                        tma_load_5d(sa + (uint32_t)(sp * g.a_sp + st * g.a_set), &tm.y[sp][st], full, 0, tp.a_mul * h * g.Kpx + tp.a_org[st], a.pa0, r - 1,
+                                    b);
                     // x: {8 ch, bins, frames, groups, sample} -> [group][pixel]
-                    tma_load_5d(sa + (uint32_t)(g.off_b + sp * g.b_set), sp == 0 ? &tm_e_hi : &tm_e_lo, full, 0, h * g.Kpx, r, a.pe0, b);
+                    for (int st = 0; st < tp.nBset; ++st)
+                        tma_load_5d(sa + (uint32_t)(g.off_b + sp * g.b_sp + st * g.b_set), &tm.e[sp][st], full, 0, tp.b_mul * h * g.Kpx + tp.b_org[st], r,
+                                    a.pe0, b);
                 }
-                // ones: {8 ch, bins, frames} -> the group behind the x groups of the hi set
-                tma_load_3d(sa + (uint32_t)(g.off_b + eb), &tm_ones, full, 0, h * g.Kpx, r);
+                // ones: {8 ch, bins, frames} -> the group behind the x groups of the hi tiles
+                for (int st = 0; st < tp.nBset; ++st)
+                    tma_load_3d(sa + (uint32_t)(g.off_b + st * g.b_set + eb), &tm.ones[st], full, 0, tp.b_mul * h * g.Kpx + tp.b_org[st], r);
                 if (++s == g.nstage) {
                     s = 0;
                     if (primed) ph ^= 1;
@@ -141,7 +168,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_consta
     } else if (warp == 1) {
         if (elect_one()) {
             const uint32_t idesc = make_idesc_mn(g.N);
-            const uint32_t sboA = (uint32_t)(g.pitchA * 16), sboB = (uint32_t)(g.Kpx * 16);
+            const uint32_t sboA = (uint32_t)(g.pitchA * 16), sboB = (uint32_t)(g.pitchB * 16);
             int s = 0, ph = 0;
             for (int it = 0; it < nst; ++it) {
                 mbar_wait(bar_full + 8 * s, (uint32_t)ph);
@@ -149,12 +176,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_consta
                 const uint32_t sa = s_stage + (uint32_t)(s * g.stage);
 #pragma unroll
                 for (int kf = 0; kf < 3; ++kf) {
+                    const uint32_t a0 = sa + (uint32_t)(tp.aset[kf] * g.a_set + tp.ashift[kf] * 16);
+                    const uint32_t b0 = sa + (uint32_t)(g.off_b + tp.bset[kf] * g.b_set + tp.bshift[kf] * 16);
                     for (int ks = 0; ks < g.Kpx / 16; ++ks) {
 #pragma unroll
                         for (int pr = 0; pr < (SPLIT == 3 ? 3 : 1); ++pr) {  // a_hi b_hi, a_hi b_lo, a_lo b_hi
-                            // x pixel p of the stage pairs with dy pixel p - kf + 1, i.e. row p - kf + 2 of the dy tile
-                            const uint32_t aaddr = sa + (uint32_t)((pr == 2 ? g.a_set : 0) + (2 - kf) * 16 + ks * 256);
-                            const uint32_t baddr = sa + (uint32_t)(g.off_b + (pr == 1 ? g.b_set : 0) + ks * 256);
+                            const uint32_t aaddr = a0 + (uint32_t)((pr == 2 ? g.a_sp : 0) + ks * 256);
+                            const uint32_t baddr = b0 + (uint32_t)((pr == 1 ? g.b_sp : 0) + ks * 256);
                             umma_bf16(tmem + (uint32_t)(kf * g.N), make_desc(aaddr, 128, sboA), make_desc(baddr, 128, sboB), idesc,
                                       (it == 0 && ks == 0 && pr == 0) ? 0u : 1u);
                         }
@@ -172,7 +200,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_e_hi, const __grid_consta
         // epilogue: raw accumulators -> partial[cta][kf][lane][N]
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        float *dst = a.partial + ((size_t)blockIdx.y * gridDim.x + cta) * 3 * 128 * g.N;
+        float *dst = a.partial + (size_t)cta * 3 * 128 * g.N;
         if (nst > 0) {
             mbar_wait(bar_done, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -216,13 +244,15 @@ struct WtcReduceArgs {
     int B, nper, ncta;     // CTAs per slice = B * nper
     int cin, cout_real;    // layer sizes (torch layout strides)
     int ci0, ci_n, co0, co_n, N, slice;
+    int rev;               // 0: frame block j of the accumulator rows is the tap kt = 2 - j (convs); 1: kt = j (transposed convs)
+    int transposed;        // gradient layout: Conv2d [cout][cin][3][3] or ConvTranspose2d [cin][cout][3][3]
 };
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const WtcReduceArgs a) {
     extern __shared__ float2 aff[];  // [B][ci_n]
     for (int i = threadIdx.x; i < a.B * a.ci_n; i += blockDim.x) {
         const int b = i / a.ci_n, ci = i - b * a.ci_n;
         float2 af = make_float2(1.f, 0.f);
-        if (a.x_sums) {
+        if (a.x_sums && a.ci0 + ci < a.cin) {
             const double *sp = a.x_sums + ((size_t)b * a.x_ctot + a.x_coff + a.ci0 + ci) * 2;
             af = affine_from_sums(stat_get(sp), stat_get(sp + 1), a.inv_n, (double)a.eps);
         }
@@ -238,8 +268,8 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const WtcReduceArg
         const int co = r % a.co_n;
         r /= a.co_n;
         const int kf = r % 3, kt = r / 3;
-        if (a.co0 + co >= a.cout_real) continue;
-        const int row = (2 - kt) * a.co_n + co;
+        if (a.co0 + co >= a.cout_real || a.ci0 + ci >= a.cin) continue;
+        const int row = (a.rev ? kt : 2 - kt) * a.co_n + co;
         const float *p0 = P + ((size_t)kf * 128 + row) * a.N;
         float acc = 0.f;
         int c = 0;
@@ -262,7 +292,8 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const WtcReduceArg
             const float2 af = aff[(c / a.nper) * a.ci_n + ci];
             acc = fmaf(af.x, p[ci], fmaf(af.y, p[a.ci_n], acc));
         }
-        a.dw[(((size_t)(a.co0 + co) * a.cin + a.ci0 + ci) * 3 + kt) * 3 + kf] += acc;
+        const size_t idx = a.transposed ? ((size_t)(a.ci0 + ci) * a.cout_real + a.co0 + co) : ((size_t)(a.co0 + co) * a.cin + a.ci0 + ci);
+        a.dw[(idx * 3 + kt) * 3 + kf] += acc;
     }
 }
 
@@ -289,23 +320,72 @@ WtcEncodeFn wtc_get_encode() {
 
 int wtc_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-bool make_wtc_geom(int F, int ci_n, int co_n, int split, WtcGeom &g) {
+enum WtcCase { WTC_NONE = 0, WTC_CONV_S1, WTC_CONVT_S1, WTC_CONV_S2, WTC_CONVT_S2 };
+
+int wtc_case(const WgradArgs &a) {
+    if (a.KT != 3 || a.KF != 3 || a.pad_t != 1) return WTC_NONE;
+    if (!a.transposed && a.stride_f == 1 && (a.pad_f == 0 || a.pad_f == 1) && a.Fout == a.Fin + 2 * a.pad_f - 2) return WTC_CONV_S1;
+    if (a.transposed && a.stride_f == 1 && (a.pad_f == 0 || a.pad_f == 1) && a.Fout == a.Fin + 2 - 2 * a.pad_f) return WTC_CONVT_S1;
+    if (!a.transposed && a.stride_f == 2 && a.pad_f == 0 && a.Fin >= 3 && a.Fout == (a.Fin - 3) / 2 + 1) return WTC_CONV_S2;
+    if (a.transposed && a.stride_f == 2 && a.pad_f == 0 && a.Fout == (a.Fin - 1) * 2 + 3) return WTC_CONVT_S2;
+    return WTC_NONE;
+}
+
+// Fk: extent of the K (pixel) grid = bins of the coarser tensor
+bool make_wtc_geom(int kase, int pad_f, int Fk, int ci_n, int co_n, int split, WtcGeom &g) {
     g = WtcGeom{};
     const int nsp = split == 3 ? 2 : 1;
-    g.Kpx = F + 1 >= 64 ? 64 : (F + 1 >= 32 ? 32 : 16);
-    g.nhalf = (F + g.Kpx - 1) / g.Kpx;
+    g.Kpx = Fk + 1 >= 64 ? 64 : (Fk + 1 >= 32 ? 32 : 16);
+    g.nhalf = (Fk + g.Kpx - 1) / g.Kpx;
     g.ngA = co_n / 8;
-    g.ngE = ci_n / 8;
+    g.ngE = (ci_n + 7) / 8;
     g.N = wtc_round_up(8 * (g.ngE + 1), 16);
     if (g.N > kWtcMaxN || 3 * co_n > 128) return false;
-    g.pitchA = g.Kpx + 2;
+    WtcTaps &tp = g.tp;
+    tp.nAset = tp.nBset = 1;
+    tp.a_mul = tp.b_mul = 1;
+    g.pitchA = g.pitchB = g.Kpx;
+    switch (kase) {
+        case WTC_CONV_S1:  // dy bin = x bin - kf + pad: the tile starts pad - 2 bins left of the stage
+            tp.a_org[0] = pad_f - 2;
+            for (int kf = 0; kf < 3; ++kf) tp.ashift[kf] = 2 - kf;
+            g.pitchA = g.Kpx + 2;
+            break;
+        case WTC_CONVT_S1:  // dy bin = x bin + kf - pad
+            tp.a_org[0] = -pad_f;
+            for (int kf = 0; kf < 3; ++kf) tp.ashift[kf] = kf;
+            g.pitchA = g.Kpx + 2;
+            break;
+        case WTC_CONV_S2:  // x bin = 2 dy bin + kf: even, odd, even + 1
+            tp.nBset = 2;
+            tp.b_mul = 2;
+            tp.b_org[0] = 0;
+            tp.b_org[1] = 1;
+            tp.bset[1] = 1;
+            tp.bshift[2] = 1;
+            g.pitchB = g.Kpx + 8;  // a multiple of 8 pixels keeps every group 128-byte aligned (the ones group is a TMA target)
+            break;
+        case WTC_CONVT_S2:  // dy bin = 2 x bin + kf
+            tp.nAset = 2;
+            tp.a_mul = 2;
+            tp.a_org[0] = 0;
+            tp.a_org[1] = 1;
+            tp.aset[1] = 1;
+            tp.ashift[2] = 1;
+            g.pitchA = g.Kpx + 1;
+            break;
+        default:
+            return false;
+    }
     g.a_box = 3 * g.ngA * g.pitchA * 16;
     g.a_set = wtc_round_up(g.a_box, 128);
-    g.b_set = g.N / 8 * g.Kpx * 16;
-    g.off_b = wtc_round_up(nsp * g.a_set, 128);
-    // the A descriptor reads 16 groups of pitchA pixels whatever 3 * ngA is: keep that inside the stage
-    const int a_reach = 16 * g.pitchA * 16 + 3 * 16 + (g.Kpx / 16) * 256;
-    g.stage = wtc_round_up(std::max(g.off_b + nsp * g.b_set, (nsp - 1) * g.a_set + a_reach), 1024);
+    g.a_sp = tp.nAset * g.a_set;
+    g.b_set = g.N / 8 * g.pitchB * 16;
+    g.b_sp = tp.nBset * g.b_set;
+    g.off_b = wtc_round_up(nsp * g.a_sp, 128);
+    // an A descriptor reads 16 groups of pitchA pixels whatever 3 * ngA is: keep that inside the stage
+    const int a_reach = (nsp * g.a_sp - g.a_set) + 16 * g.pitchA * 16 + 3 * 16 + (g.Kpx / 16) * 256;
+    g.stage = wtc_round_up(std::max(g.off_b + nsp * g.b_sp, a_reach), 1024);
     g.nstage = std::min(kWtcMaxStages, (kWtcSmemLimit - 1024) / g.stage);
     if (g.nstage < 2) return false;
     g.smem_total = 1024 + g.nstage * g.stage;
@@ -316,17 +396,23 @@ bool make_wtc_geom(int F, int ci_n, int co_n, int split, WtcGeom &g) {
 
 bool wgrad_tc_eligible(const WgradArgs &a) {
     static const bool off = getenv("MISO_WGRAD_TC") && atoi(getenv("MISO_WGRAD_TC")) == 0;
+    static const bool dense_only = getenv("MISO_WGRAD_TC") && atoi(getenv("MISO_WGRAD_TC")) == 2;  // A/B: DenseBlock convs only
     if (off || !a.dyp || !a.partial || !a.ones) return false;
-    if (a.transposed || a.stride_f != 1 || a.KT != 3 || a.KF != 3 || a.pad_t != 1 || a.pad_f != 1 || a.Fin != a.Fout) return false;
-    if (a.x_layout != LAYOUT_PLANES || a.x_ctot % 8 || a.x_coff % 8 || a.cin % 8 || a.cout % 8 || a.cout != a.cout_real) return false;
-    if (a.Fin < 15 || a.T < 2) return false;
+    const int kase = wtc_case(a);
+    if (kase == WTC_NONE) return false;
+    if (dense_only && !(kase == WTC_CONV_S1 && a.pad_f == 1)) return false;
+    if (a.x_layout != LAYOUT_PLANES || a.x_ctot % 8 || a.x_coff % 8 || a.cout % 8 || a.cout != a.cout_real) return false;
+    if (a.cin % 8 && a.x_coff + ((a.cin + 7) & ~7) > a.x_ctot) return false;  // a ragged channel count needs zero planes behind it
+    const int Fk = kase == WTC_CONV_S2 ? a.Fout : a.Fin;
+    if (Fk < 15 || a.T < 2) return false;
     return true;
 }
 
 // chunking of a layer: input-channel chunks of <= 152 channels (N <= 160 with the ones group), output-channel chunks of <= 40
 static void wtc_chunks(const WgradArgs &a, int &nci, int &ci_n, int &nco, int &co_n) {
-    nci = (a.cin + 151) / 152;
-    ci_n = wtc_round_up((a.cin + nci - 1) / nci, 8);
+    const int cin8 = (a.cin + 7) & ~7;
+    nci = (cin8 + 151) / 152;
+    ci_n = wtc_round_up((cin8 + nci - 1) / nci, 8);
     nco = (a.cout + 39) / 40;
     co_n = wtc_round_up((a.cout + nco - 1) / nco, 8);
 }
@@ -366,67 +452,65 @@ int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
         MISO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWtcSmemLimit));
         attr_done[dev & 63] = true;
     }
-    const uint64_t T = (uint64_t)a.T, F = (uint64_t)a.Fin;
+    const int kase = wtc_case(a);
+    const int Fk = kase == WTC_CONV_S2 ? a.Fout : a.Fin;
+    const int cin8 = (a.cin + 7) & ~7;
+    const uint64_t T = (uint64_t)a.T, Fx = (uint64_t)a.Fin, Fy = (uint64_t)a.Fout;
     for (int ic = 0; ic < nci; ++ic)
         for (int oc = 0; oc < nco; ++oc) {
-            const int ci0 = ic * ci_n, cin_c = std::min(ci_n, a.cin - ci0);
+            const int ci0 = ic * ci_n, cin_c = std::min(ci_n, cin8 - ci0);
             const int co0 = oc * co_n, con_c = std::min(co_n, a.cout - co0);
             WtcGeom g;
-            MISO_REQUIRE(make_wtc_geom(a.Fin, cin_c, con_c, split, g), "wgrad_tc: geometry (cin %d cout %d F %d)", cin_c, con_c, a.Fin);
+            MISO_REQUIRE(make_wtc_geom(kase, a.pad_f, Fk, cin_c, con_c, split, g), "wgrad_tc: geometry (cin %d cout %d F %d)", cin_c, con_c, Fk);
             const int slice = ic * nco + oc;
             // a slice's GEMM and its reduction are consecutive launches of one stream: every slice reuses the same region
             MISO_REQUIRE((size_t)ncta * 3 * 128 * g.N * sizeof(float) <= a.partial_bytes, "wgrad_tc: partial buffer too small");
-            CUtensorMap tm[5];
+            WtcMaps tm;
+            memset(&tm, 0, sizeof(tm));
+            auto fail = [&](const char *what, CUresult r) {
+                set_error("wgrad_tc: cuTensorMapEncodeTiled(%s) failed (%d)", what, (int)r);
+                return MISO_E_CUDA;
+            };
             for (int sp = 0; sp < 2; ++sp) {
-                // x planes [B][hi|lo][x_ctot/8][T][F][8]: {8 ch, bins, frames, groups, samples}
-                {
+                // x planes [B][hi|lo][x_ctot/8][T][Fx][8]: {8 ch, bins, frames, groups, samples}
+                for (int st = 0; st < g.tp.nBset; ++st) {
                     const uint64_t CG = (uint64_t)a.x_ctot / 8;
-                    char *base = const_cast<char *>(reinterpret_cast<const char *>(a.x)) + (sp ? CG * T * F * 16 : 0);
-                    cuuint64_t dims[5] = {8, F, T, CG, (cuuint64_t)a.B};
-                    cuuint64_t strides[4] = {16, F * 16, T * F * 16, 2 * CG * T * F * 16};
-                    cuuint32_t box[5] = {8, (cuuint32_t)g.Kpx, 1, (cuuint32_t)g.ngE, 1};
-                    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-                    CUresult r = enc(&tm[sp], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    char *base = const_cast<char *>(reinterpret_cast<const char *>(a.x)) + (sp ? CG * T * Fx * 16 : 0);
+                    cuuint64_t dims[5] = {8, Fx, T, CG, (cuuint64_t)a.B};
+                    cuuint64_t strides[4] = {16, Fx * 16, T * Fx * 16, 2 * CG * T * Fx * 16};
+                    cuuint32_t box[5] = {8, (cuuint32_t)(g.tp.b_mul * g.pitchB), 1, (cuuint32_t)g.ngE, 1};
+                    cuuint32_t es[5] = {1, (cuuint32_t)g.tp.b_mul, 1, 1, 1};
+                    CUresult r = enc(&tm.e[sp][st], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                    if (r != CUDA_SUCCESS) {
-                        set_error("wgrad_tc: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
-                        return MISO_E_CUDA;
-                    }
+                    if (r != CUDA_SUCCESS) return fail("x", r);
                 }
-                // dy planes [B][hi|lo][cout/8][T][F][8] as {8 ch, bins, groups, frames, samples}: the box lands [frame][group][pixel]
-                {
+                // dy planes [B][hi|lo][cout/8][T][Fy][8] as {8 ch, bins, groups, frames, samples}: the box lands [frame][group][pixel]
+                for (int st = 0; st < g.tp.nAset; ++st) {
                     const uint64_t CG = (uint64_t)a.cout / 8;
-                    char *base = reinterpret_cast<char *>(a.dyp) + (sp ? CG * T * F * 16 : 0);
-                    cuuint64_t dims[5] = {8, F, CG, T, (cuuint64_t)a.B};
-                    cuuint64_t strides[4] = {16, T * F * 16, F * 16, 2 * CG * T * F * 16};
-                    cuuint32_t box[5] = {8, (cuuint32_t)g.pitchA, (cuuint32_t)g.ngA, 3, 1};
-                    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-                    CUresult r = enc(&tm[2 + sp], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    char *base = reinterpret_cast<char *>(a.dyp) + (sp ? CG * T * Fy * 16 : 0);
+                    cuuint64_t dims[5] = {8, Fy, CG, T, (cuuint64_t)a.B};
+                    cuuint64_t strides[4] = {16, T * Fy * 16, Fy * 16, 2 * CG * T * Fy * 16};
+                    cuuint32_t box[5] = {8, (cuuint32_t)(g.tp.a_mul * g.pitchA), (cuuint32_t)g.ngA, 3, 1};
+                    cuuint32_t es[5] = {1, (cuuint32_t)g.tp.a_mul, 1, 1, 1};
+                    CUresult r = enc(&tm.y[sp][st], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                    if (r != CUDA_SUCCESS) {
-                        set_error("wgrad_tc: cuTensorMapEncodeTiled(dy) failed (%d)", (int)r);
-                        return MISO_E_CUDA;
-                    }
+                    if (r != CUDA_SUCCESS) return fail("dy", r);
                 }
             }
-            {
-                cuuint64_t dims[3] = {8, F, T};
-                cuuint64_t strides[2] = {16, F * 16};
-                cuuint32_t box[3] = {8, (cuuint32_t)g.Kpx, 1};
-                cuuint32_t es[3] = {1, 1, 1};
-                CUresult r = enc(&tm[4], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ones, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            for (int st = 0; st < g.tp.nBset; ++st) {
+                cuuint64_t dims[3] = {8, Fx, T};
+                cuuint64_t strides[2] = {16, Fx * 16};
+                cuuint32_t box[3] = {8, (cuuint32_t)(g.tp.b_mul * g.pitchB), 1};
+                cuuint32_t es[3] = {1, (cuuint32_t)g.tp.b_mul, 1};
+                CUresult r = enc(&tm.ones[st], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ones, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS) {
-                    set_error("wgrad_tc: cuTensorMapEncodeTiled(ones) failed (%d)", (int)r);
-                    return MISO_E_CUDA;
-                }
+                if (r != CUDA_SUCCESS) return fail("ones", r);
             }
             WtcArgs k{};
             k.g = g;
             k.partial = a.partial;
             k.B = a.B;
             k.T = a.T;
-            k.F = a.Fin;
             k.nper = nper;
             k.fper = fper;
             k.pe0 = (a.x_coff + ci0) / 8;
@@ -434,13 +518,12 @@ int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
             k.rows = 3 * con_c;
             static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
             if (debug)
-                fprintf(stderr, "wgrad_tc: cin=%d cout=%d F=%d | slice %d/%d ci [%d,+%d) co [%d,+%d) N=%d Kpx=%d nhalf=%d nper=%d fper=%d nstage=%d stage=%dB\n", a.cin,
-                        a.cout, a.Fin, slice, nslice, ci0, cin_c, co0, con_c, g.N, g.Kpx, g.nhalf, nper, fper, g.nstage, g.stage);
-            // the slice index is baked into k.partial, so blockIdx.y stays 0
+                fprintf(stderr, "wgrad_tc: case %d cin=%d cout=%d Fx=%d Fy=%d | slice %d/%d ci [%d,+%d) co [%d,+%d) N=%d Kpx=%d nhalf=%d nper=%d fper=%d nstage=%d stage=%dB\n",
+                        kase, a.cin, a.cout, a.Fin, a.Fout, slice, nslice, ci0, cin_c, co0, con_c, g.N, g.Kpx, g.nhalf, nper, fper, g.nstage, g.stage);
             if (split == 3)
-                wgrad_tc_kernel<3><<<dim3(ncta, 1), kWtcThreads, g.smem_total, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], k);
+                wgrad_tc_kernel<3><<<dim3(ncta, 1), kWtcThreads, g.smem_total, st>>>(tm, k);
             else
-                wgrad_tc_kernel<1><<<dim3(ncta, 1), kWtcThreads, g.smem_total, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], k);
+                wgrad_tc_kernel<1><<<dim3(ncta, 1), kWtcThreads, g.smem_total, st>>>(tm, k);
             MISO_LAUNCHED("wgrad_tc_kernel");
             WtcReduceArgs r{};
             r.partial = a.partial;
@@ -456,13 +539,15 @@ int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
             r.cin = a.cin;
             r.cout_real = a.cout_real;
             r.ci0 = ci0;
-            r.ci_n = cin_c;
+            r.ci_n = g.ngE * 8;
             r.co0 = co0;
             r.co_n = con_c;
             r.N = g.N;
             r.slice = 0;
-            const int total = 9 * con_c * cin_c;
-            wgrad_tc_reduce_kernel<<<std::min(2 * 148, (total + 255) / 256), 256, (size_t)a.B * cin_c * sizeof(float2), st>>>(r);
+            r.rev = (kase == WTC_CONVT_S1 || kase == WTC_CONVT_S2) ? 1 : 0;
+            r.transposed = a.transposed;
+            const int total = 9 * con_c * r.ci_n;
+            wgrad_tc_reduce_kernel<<<std::min(2 * 148, (total + 255) / 256), 256, (size_t)a.B * r.ci_n * sizeof(float2), st>>>(r);
             MISO_LAUNCHED("wgrad_tc_reduce_kernel");
         }
     return MISO_OK;
