@@ -152,7 +152,7 @@ int miso_wave_to_int16(const float *d_x, int16_t *d_out, int64_t n, float scale,
  * miso_net_forward_train is miso_net_forward on the TRAINING workspace plan: every TemporalBlock keeps its input and
  * mid state (the inference plan updates the residual stream in place), no CUDA graph.  miso_net_backward then consumes
  * the activations and statistics the forward left in the SAME workspace:
- *   d_gy    : dL/d(output), fp32 channels-last [B, T, F, out_ch rounded up to a multiple of 4] (the layout of d_y with
+ *   d_gy    : dL/d(output), fp32 channels-last [B, T, F, out_ch rounded up to a multiple of 8] (the layout of d_y with
  *             zero padding channels; written by miso_grad_pack); clobbered
  *   d_grads : gradient of every parameter, flat fp32 in miso_net_param_key order, each in its torch layout
  *             (miso_net_grad_numel elements in total); overwritten.
@@ -173,7 +173,7 @@ int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, 
                            size_t ws_bytes, void *stream);
 int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int T, int F, void *d_ws, size_t ws_bytes,
                       float *d_grads, void *stream);
-/* complex64 gradient [B, S, T, F] (PyTorch convention dL/dre + i dL/dim) -> d_gy layout [B, T, F, round_up(2S, 4)] */
+/* complex64 gradient [B, S, T, F] (PyTorch convention dL/dre + i dL/dim) -> d_gy layout [B, T, F, round_up(2S, 8)] */
 int miso_grad_pack(const void *d_grad, float *d_gy, int B, int S, int T, int F, void *stream);
 /* gradient of loss_uPIT (criterion.py:8-63) w.r.t. the estimate for the winning permutation d_perm_idx[b]
  * (int64, from miso_pair_fwd mode 1), scaled by the upstream scalar *d_gout: complex64 [B, S, T, F] dense. */

@@ -1253,7 +1253,7 @@ int miso_grad_pack(const void *d_grad, float *d_gy, int B, int S, int T, int F, 
     MISO_REQUIRE(d_grad && d_gy && S >= 1, "miso_grad_pack: bad argument");
     const int64_t n = (int64_t)T * F;
     const int blocks = (int)std::min<int64_t>((B * n + 255) / 256, 148 * 16);
-    grad_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2 *>(d_grad), d_gy, B, S, n, (2 * S + 3) & ~3);
+    grad_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float2 *>(d_grad), d_gy, B, S, n, (2 * S + 7) & ~7);
     MISO_LAUNCHED("grad_pack_kernel");
     return MISO_OK;
 }

@@ -1683,9 +1683,9 @@ struct Backward {
         const int cout_real = f.cout;
         float *og = r.out_grad ? r.out_grad : d_gy;
         if (!r.out_grad) {
-            // the network output: the caller's gradient is padded to a multiple of 4 channels (miso_grad_pack); the pad
+            // the network output: the caller's gradient is padded to a multiple of 8 channels (miso_grad_pack); the pad
             // channels carry zero gradient and meet zero-padded packed weights in the data gradient
-            f.cout = (f.cout + 3) & ~3;
+            f.cout = (f.cout + 7) & ~7;  // a whole 8-channel plane group: the tensor-core gradient paths take the layer too
             f.out_ctot = f.cout;
         }
         int rc;

@@ -401,7 +401,7 @@ bool wgrad_tc_eligible(const WgradArgs &a) {
     const int kase = wtc_case(a);
     if (kase == WTC_NONE) return false;
     if (dense_only && !(kase == WTC_CONV_S1 && a.pad_f == 1)) return false;
-    if (a.x_layout != LAYOUT_PLANES || a.x_ctot % 8 || a.x_coff % 8 || a.cout % 8 || a.cout != a.cout_real) return false;
+    if (a.x_layout != LAYOUT_PLANES || a.x_ctot % 8 || a.x_coff % 8 || a.cout % 8 || a.cout_real > a.cout) return false;  // cout_real < cout: zero pad channels (the network output)
     if (a.cin % 8 && a.x_coff + ((a.cin + 7) & ~7) > a.x_ctot) return false;  // a ragged channel count needs zero planes behind it
     const int Fk = kase == WTC_CONV_S2 ? a.Fout : a.Fin;
     if (Fk < 15 || a.T < 2) return false;

@@ -119,7 +119,7 @@ class _NetFunction(torch.autograd.Function):
         st = _lib.stream_ptr()
         with torch.cuda.device(dev):
             # persistent buffers: the backward's ~900 launches are replayed as a CUDA graph keyed by these pointers
-            gy = m._buffer("gy_train", (B, T, F, (2 * S + 3) // 4 * 4), torch.float32, dev)
+            gy = m._buffer("gy_train", (B, T, F, (2 * S + 7) // 8 * 8), torch.float32, dev)
             _lib.check(lib.miso_grad_pack(_lib.ptr(g), _lib.ptr(gy), B, S, T, F, st), "miso_grad_pack")
             numel = lib.miso_net_grad_numel(m._handle)
             flat = m._buffer("flat_grads", (numel,), torch.float32, dev)
