@@ -211,7 +211,7 @@ def run_ours(args, wl, rank, world, local):
 
         # ---- roofline pass: the same steps with CUDA-event nodes around every conv launch (baked into the
         # replayed graph), collected after each step ----
-        fams = {fname: dict(ms=0.0, flops=0.0, bytes=0.0, launches=0) for fname in PROF_FAMILIES.values()}
+        fams = {fname: dict(ms=0.0, flops=0.0, bytes=0.0, exec=0.0, launches=0) for fname in PROF_FAMILIES.values()}
         lib.miso_prof_enable(1)
         step(dev_in)                       # captures the instrumented graph
         torch.cuda.synchronize()
@@ -222,12 +222,13 @@ def run_ours(args, wl, rank, world, local):
             step(dev_in)
             torch.cuda.synchronize()
             for fid, fname in PROF_FAMILIES.items():
-                cm, cf, cb, cn = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
-                _lib.check(lib.miso_prof_collect(fid, ctypes.byref(cm), ctypes.byref(cf), ctypes.byref(cb), ctypes.byref(cn)))
+                cm, cf, cb, ce, cn = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_uint64()
+                _lib.check(lib.miso_prof_collect2(fid, ctypes.byref(cm), ctypes.byref(cf), ctypes.byref(cb), ctypes.byref(ce), ctypes.byref(cn)))
                 f = fams[fname]
                 f["ms"] += cm.value
                 f["flops"] += cf.value
                 f["bytes"] += cb.value
+                f["exec"] += ce.value
                 f["launches"] += int(cn.value)
         e1.record()
         torch.cuda.synchronize()
@@ -284,11 +285,19 @@ def run_ours(args, wl, rank, world, local):
     conv_ms, conv_flops, conv_launches = fams[dom]["ms"], fams[dom]["flops"], fams[dom]["launches"]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_c_ncu_traffic_conv_rs_bf16x3.json")
-    if args.workload == "miso1_paper" and args.conv_mode == "bf16x3" and args.batch == 0 and dom.startswith("conv_rs") and os.path.isfile(tp):
+    tp = next((os.path.join(ROOT, "profiles", f) for f in ("r2_ncu_traffic_conv_rs_bf16x3.json", "r1_c_ncu_traffic_conv_rs_bf16x3.json")
+               if os.path.isfile(os.path.join(ROOT, "profiles", f))), None)
+    if args.workload == "miso1_paper" and args.conv_mode == "bf16x3" and args.batch == 0 and dom.startswith("conv_rs") and tp:
         try:
-            traffic = float(json.load(open(tp))["family_dram_bytes_per_launch"])
-            traffic_src = "profiles/r1_c_ncu_traffic_conv_rs_bf16x3.json (dram__bytes_read.sum + dram__bytes_write.sum of this workload's conv_rs + prep launches, per conv launch)"
+            import hashlib
+            tj = json.load(open(tp))
+            traffic = float(tj["family_dram_bytes_per_launch"])
+            cur = hashlib.sha1(open(os.path.join(ROOT, "misonet_b200", "csrc", "conv_rs.cu"), "rb").read()).hexdigest()
+            stamp = tj.get("kernel_source_sha1")
+            fresh = "capture taken from this very conv_rs.cu" if stamp == cur else (
+                "STALE: conv_rs.cu changed since the capture" if stamp else "capture predates the source stamp (round 1)")
+            traffic_src = (f"profiles/{os.path.basename(tp)} (ncu dram__bytes_read.sum + dram__bytes_write.sum of this workload's conv_rs + prep "
+                           f"launches, per conv launch; ncu cannot run inside the timed bench; {fresh})")
         except Exception:
             pass
     tc = [v for k, v in fams.items() if k.split()[0] in ("conv_tc_kernel", "conv_rs_kernel", "tcn_pw_kernel")]
@@ -298,6 +307,7 @@ def run_ours(args, wl, rank, world, local):
     fam_report = {k: {"ms_per_step": v["ms"] / args.steps, "share_of_step": v["ms"] / ms if ms > 0 else None,
                       "launches_per_step": v["launches"] // max(args.steps, 1),
                       "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0,
+                      "executed_tflops": v["exec"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0,
                       "algorithmic_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0}
                   for k, v in fams.items() if v["launches"]}
     line = {
@@ -319,7 +329,9 @@ def run_ours(args, wl, rank, world, local):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom,
                      "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                     "frac": achieved / pk["bf16_tflops"],
+                     "executed_frac": (fams[dom]["exec"] / (conv_ms * 1e-3) / 1e12 / pk["bf16_tflops"]) if conv_ms > 0 else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": fams[dom]["bytes"] / max(conv_launches, 1), "peak_source": pk["source"],
                      "launches": int(conv_launches), "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms if ms > 0 else None,
@@ -330,7 +342,9 @@ def run_ours(args, wl, rank, world, local):
                              "graph, a second pass of the same steps right after the timed one; the per-sample operand preparation launches are their "
                              "own entry under families).  bf16x3 spends 3 MMAs per "
                              "algorithmic product and an SS-mode MMA is shared-memory-operand bound at (4096 + 32 N) / 128 cycles, "
-                             "so the kernel's own ceiling is 0.29 of the bf16 peak at N = 3 cout = 96 (0.86 in bf16 mode); "
+                             "so the kernel's own ceiling is 0.29 of the bf16 peak at N = 3 cout = 96 (0.86 in bf16 mode); executed_frac counts "
+                             "the MMAs actually issued (3 per product, N padded to 3 x 32 for the cout-24 layers, M = 128 rows for 127 bins, "
+                             "K padded to 16 channels) against the same peak: how busy the tensor pipe is; "
                              "all_tensor_core_kernels aggregates every tcgen05 kernel of the step"},
     }
     mv = fams.get(PROF_FAMILIES[3])

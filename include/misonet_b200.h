@@ -64,6 +64,11 @@ uint64_t miso_launch_count(void);
 int miso_prof_enable(int on);
 /* collects (and clears) the records of one family, or of all with MISO_PROF_ALL */
 int miso_prof_collect(int family, double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches);
+/* the same plus the tensor-pipe work the family's kernels actually ISSUED (bf16x3: three MMAs per product; N, M and K
+ * padding of the MMA tiles included): executed / peak is how busy the tensor pipe is, algorithmic / peak is the roofline
+ * fraction */
+int miso_prof_collect2(int family, double *total_ms, double *total_flops, double *total_bytes, double *total_exec_flops,
+                       uint64_t *launches);
 /* per-launch view of the queued records, in launch order: fills up to `capacity` entries of each
  * non-NULL array and returns the count; the records stay queued for miso_prof_collect. */
 int miso_prof_dump(double *ms, double *flops, int *family, int capacity);

@@ -22,6 +22,8 @@ SIGNATURES = {
     "miso_prof_enable": (c_int, [c_int]),
     "miso_prof_collect": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
                                   POINTER(c_uint64)]),
+    "miso_prof_collect2": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+                                   POINTER(ctypes.c_double), POINTER(c_uint64)]),
     "miso_prof_dump": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int), c_int]),
     "miso_stft_num_frames": (c_int, [c_int, c_int, c_int]),
     "miso_stft_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

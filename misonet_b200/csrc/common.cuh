@@ -46,6 +46,7 @@ inline int cuda_fail(cudaError_t e, const char *what) {
 struct ProfRec {
     cudaEvent_t a, b;
     double flops, bytes;
+    double exec_flops;  // tensor-pipe work actually issued (3 MMAs per product in bf16x3, N / M / K padding included)
     int family;
     bool persistent;
 };
@@ -53,7 +54,7 @@ bool prof_enabled();
 void prof_capture(std::vector<ProfRec> *sink);
 void prof_replayed(const std::vector<ProfRec> &recs);
 void prof_begin(cudaStream_t st);
-void prof_end(cudaStream_t st, double flops, double bytes, int family);
+void prof_end(cudaStream_t st, double flops, double bytes, int family, double exec_flops = 0.0);
 
 // Programmatic dependent launch: a kernel launched through launch_pdl may start while its predecessor in the stream is
 // still running; it must execute pdl_wait() before touching anything the predecessor reads or writes (everything before

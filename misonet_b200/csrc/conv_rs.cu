@@ -1148,7 +1148,10 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
         const double pix = (double)a.B * a.T * a.Fout;
         const double flops = 2.0 * pix * a.cin * a.cout * 9;
         const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
-        prof_end(stream, flops, bytes, MISO_PROF_CONV_RS);
+        // issued: every input row (incl. the two halo rows of a strip: ignored here) is one M = 128 tile per column region,
+        // nunit K units x 3 bin taps x (3 products in bf16x3) MMAs of width N3
+        const double exec = (double)rs_rows(a, g) * g.nunit * 3.0 * (split == 3 ? 3.0 : 1.0) * 2.0 * 128.0 * g.N3 * 16.0;
+        prof_end(stream, flops, bytes, MISO_PROF_CONV_RS, exec);
     }
     MISO_LAUNCHED("conv_rs_kernel");
     return MISO_OK;

@@ -1076,7 +1076,9 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
         const double pix = (double)a.B * a.T * (a.transposed ? a.Fin : a.Fout);
         const double flops = 2.0 * pix * a.cin * a.cout * a.KT * a.KF;
         const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
-        prof_end(stream, flops, bytes, MISO_PROF_CONV_TC);
+        // issued: per tile, nunit K units x ntap taps x G M tiles x (one MMA of width 2N + one of width N in bf16x3)
+        const double exec = (double)g.ntiles * g.nunit * g.ntap * g.G * 2.0 * 128.0 * 16.0 * (split == 3 ? 3.0 * g.N : 1.0 * g.N);
+        prof_end(stream, flops, bytes, MISO_PROF_CONV_TC, exec);
     }
     MISO_LAUNCHED("conv_tc_kernel");
     return MISO_OK;

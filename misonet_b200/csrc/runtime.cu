@@ -72,7 +72,7 @@ void prof_begin(cudaStream_t st) {
     else
         cudaEventRecord(g_open, st);
 }
-void prof_end(cudaStream_t st, double flops, double bytes, int family) {
+void prof_end(cudaStream_t st, double flops, double bytes, int family, double exec_flops) {
     if (!g_open) return;
     ProfRec r;
     r.a = g_open;
@@ -80,6 +80,7 @@ void prof_end(cudaStream_t st, double flops, double bytes, int family) {
     r.b = get_event();
     r.flops = flops;
     r.bytes = bytes;
+    r.exec_flops = exec_flops;
     r.family = family;
     r.persistent = false;
     if (g_sink) {
@@ -101,7 +102,14 @@ int miso_prof_enable(int on) {
     return MISO_OK;
 }
 
+static int prof_collect_impl(int family, double *total_ms, double *total_flops, double *total_bytes, double *total_exec, uint64_t *launches);
 int miso_prof_collect(int family, double *total_ms, double *total_flops, double *total_bytes, uint64_t *launches) {
+    return prof_collect_impl(family, total_ms, total_flops, total_bytes, nullptr, launches);
+}
+int miso_prof_collect2(int family, double *total_ms, double *total_flops, double *total_bytes, double *total_exec_flops, uint64_t *launches) {
+    return prof_collect_impl(family, total_ms, total_flops, total_bytes, total_exec_flops, launches);
+}
+static int prof_collect_impl(int family, double *total_ms, double *total_flops, double *total_bytes, double *total_exec, uint64_t *launches) {
     std::vector<miso::ProfRec> recs;
     {
         std::lock_guard<std::mutex> lk(miso::g_prof_mu);
@@ -109,7 +117,7 @@ int miso_prof_collect(int family, double *total_ms, double *total_flops, double 
         for (auto &r : miso::g_prof) (family < 0 || r.family == family ? recs : keep).push_back(r);
         miso::g_prof.swap(keep);
     }
-    double ms = 0.0, fl = 0.0, by = 0.0;
+    double ms = 0.0, fl = 0.0, by = 0.0, ex = 0.0;
     for (auto &r : recs) {
         cudaError_t e = cudaEventSynchronize(r.b);
         if (e != cudaSuccess) return miso::cuda_fail(e, "cudaEventSynchronize");
@@ -119,6 +127,7 @@ int miso_prof_collect(int family, double *total_ms, double *total_flops, double 
         ms += t;
         fl += r.flops;
         by += r.bytes;
+        ex += r.exec_flops;
     }
     {
         std::lock_guard<std::mutex> lk(miso::g_prof_mu);
@@ -131,6 +140,7 @@ int miso_prof_collect(int family, double *total_ms, double *total_flops, double 
     if (total_ms) *total_ms = ms;
     if (total_flops) *total_flops = fl;
     if (total_bytes) *total_bytes = by;
+    if (total_exec) *total_exec = ex;
     if (launches) *launches = recs.size();
     return MISO_OK;
 }

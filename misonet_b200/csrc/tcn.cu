@@ -398,7 +398,7 @@ int launch_tcn_pw(const TcnPwArgs &p, int split, cudaStream_t stream) {
     else
         MISO_CUDA(launch_pdl(tcn_pw_kernel<1>, grid, dim3(kPwThreads), (size_t)g.smem_total, stream, tm[0], tm[1], k));
     prof_end(stream, 2.0 * p.B * p.T * (double)p.C * p.C, (double)p.B * p.T * p.C * ((split == 3 ? 4.0 : 2.0) + 4.0 + (p.resid ? 4.0 : 0.0)),
-             MISO_PROF_TCN);
+             MISO_PROF_TCN, (double)p.B * k.t_tiles * g.NH * g.nunit * (split == 3 ? 3.0 : 1.0) * 2.0 * 128.0 * g.Nt * 16.0);
     MISO_LAUNCHED("tcn_pw_kernel");
     return MISO_OK;
 }

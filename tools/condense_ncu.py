@@ -65,5 +65,8 @@ else:
     main = max((k for k in agg if "prep" not in k), key=lambda k: agg[k]["duration_us"])
     tot = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in agg.values())
     out["family_dram_bytes_per_launch"] = tot / max(agg[main]["launches"], 1)
+    import hashlib, os
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "misonet_b200", "csrc", "conv_rs.cu")
+    out["kernel_source_sha1"] = hashlib.sha1(open(src, "rb").read()).hexdigest()   # bench.py reports a stale capture
     json.dump(out, open(sys.argv[3], "w"), indent=1)
     print(json.dumps(out)[:600])

@@ -8,7 +8,13 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_uniform.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
         "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__cycles_elapsed.max", "sm__cycles_elapsed.max.per_second",
-        "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        # the tensor pipe per sub-partition: one elected thread of ONE warp issues every tcgen05.mma, so only one of the four
+        # SMSPs of an SM ever shows tensor-pipe instructions; the *.avg over SMSPs is therefore a quarter of the busy SMSP's
+        "smsp__inst_executed_pipe_tensor.sum", "smsp__inst_executed_pipe_tensor.max", "smsp__inst_executed_pipe_tensor.avg",
+        "sm__inst_executed_pipe_tensor.sum", "smsp__pipe_tensor_cycles_active.max", "smsp__pipe_tensor_cycles_active.avg",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__cycles_active.avg", "sm__cycles_active.avg"]
 print("metric,unit," + ",".join(f"launch{i}" for i in range(len(rows) - 2)))
 for w in want:
     for i, h in enumerate(hdr):

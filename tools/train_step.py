@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--conv-mode", default="bf16x3")
+    ap.add_argument("--one-step", action="store_true", help="profiling target: warm-up steps, then ONE step and exit (no e2e / baseline legs)")
     ap.add_argument("--cpu-baseline", action="store_true",
                     help="also time the reference algorithm's training step (oracle network + torch autograd, fp32, all host "
                          "cores) on ONE utterance of the same shape")
@@ -75,6 +76,10 @@ def main():
                 phases[k] += ev[k].elapsed_time(ev[k + 1])
             total_ms += ev[0].elapsed_time(ev[4])
     launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
+    if args.one_step:
+        if rank == 0:
+            print(json.dumps({"ms_per_step": total_ms / args.steps, "launches": int(launches)}))
+        return
     # the same steps without the gradient all-reduce: the difference is the collective's EXPOSED time (what the overlap
     # with the backward does not hide)
     nodp_ms = None
