@@ -57,6 +57,16 @@ struct RsGeom {
     int S, TS, DS, Wr;  // packed mode (F + 1 <= 64): an M tile holds the same row of S frame strips; strip s covers the TS frames
                         // from s * DS, DS = T / S, TS = DS + T % S (the strips overlap by T % S frames so that they tile any T
                         // at a uniform stride; the duplicated frames count for the last strip only)
+    // Layer variant (round 2).  The kernel computes, for grid bin j of an M tile and the three frame taps kt,
+    //     out[t][ostride * j + ooff] = sum_kt sum_{i < nkf} in[t + kt - 1][j + tboff[i]] * W[kt][twk[i]]
+    // with the bin taps read as pixel shifts of the staged rows (pixel 0 of a region = bin 128 m + f_org):
+    //   DenseBlock conv (stride 1, pad 1)   nkf 3, tboff -1 0 1, f_org -1, out bin = j
+    //   first conv (stride 1, pad 0)        nkf 3, tboff  0 1 2, f_org  0, Fout = Fin - 2
+    //   transposed stride (1,2), even bins  nkf 2, tboff 0 -1 with W[.][0], W[.][2], out bin = 2 j      (frame taps flipped by the prep kernel)
+    //   transposed stride (1,2), odd bins   nkf 1, tboff 0 with W[.][1],             out bin = 2 j + 1
+    //   transposed stride 1, pad 0 (last)   nkf 3, tboff 0 -1 -2, f_org -2, Fout = Fin + 2
+    int nkf, tshift[3], twk[3], tboff[3];
+    int f_org, Wg, Fin, Fout, ostride, ooff;
 };
 
 // In-kernel operand preparation ("fused" mode, the forward DenseBlock convs).  The input channels of conv k of a block
@@ -114,7 +124,8 @@ struct RsArgs {
     int out_ctot, out_coff, cout;
     size_t out_lo_off;
     int use_lo, elu;
-    int out_cl;  // 1: the output is fp32 channels-last [B][T*F][out_ctot] and the result is ADDED to it (data gradients)
+    int out_cl;  // fp32 channels-last output [B][T*Fout][out_ctot]: 1 = the result is ADDED to it (data gradients), 2 = stored (the
+                 // network output, model.py:418-423)
     long long *trace;  // debug: clock64 event log of CTA 0 (tools/tc_trace.py), or null
     RsFuse fuse;
 };
@@ -138,6 +149,7 @@ struct RsPrepArgs {
     __nv_bfloat16 *wimg;
     float *btab;
     int B, Nc, nunit, nsp, nsplit;
+    int flip_t;  // transposed convs read input frame t + 1 - kt: the image / bias slots of frame tap kt take W[2 - kt]
 };
 
 // the strips of one CTA: its share [rho, rho_end) of the flattened (sample, column region, frame) row space, cut
@@ -406,7 +418,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 const int slot = w.b - b_first;
                 const __nv_bfloat16 *wlate =
                     a.fuse.on ? a.fuse.priv + ((size_t)blockIdx.x * a.fuse.nslot + slot) * a.fuse.nlate * (size_t)(g.w_unit / 2) : nullptr;
-                const int f0 = 128 * w.m - 1;
+                const int f0 = 128 * w.m + g.f_org;
                 RsTiles tl;
                 tl.init(a, w);
                 while (tl.next()) {
@@ -425,7 +437,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                             const CUtensorMap *tm = sp == 0 ? &tm_hi : &tm_lo;
                             const uint32_t dst = sa + (uint32_t)(sp * g.GS);
                             if (g.S > 1)  // {bins, strip, frame in strip, plane, sample}
-                                tma_load_5d(dst, tm, full, -2, tl.kind == 1 ? -1 : (tl.kind == 2 ? 1 : 0),
+                                tma_load_5d(dst, tm, full, 2 * g.f_org, tl.kind == 1 ? -1 : (tl.kind == 2 ? 1 : 0),
                                             tl.kind == 1 ? g.DS - 1 : (tl.kind == 2 ? g.TS - g.DS : tin), pl, w.b);
                             else if (g.map5d)
                                 tma_load_5d(dst, tm, full, 0, f0, tin, pl, w.b);
@@ -474,6 +486,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             const uint32_t a_kstep = (uint32_t)(2 * g.PL) >> 4, b_kstep = (uint32_t)g.w_unit >> 4;
             const uint32_t b_kfstep = (uint32_t)(g.nsp * 2 * g.N3), b_spstep = (uint32_t)(2 * g.N3);
             const uint32_t row_step = (uint32_t)g.pitch;
+            const int nkf = g.nkf;
+            uint32_t tap_a[3], tap_b[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                tap_a[i] = (uint32_t)g.tshift[i];
+                tap_b[i] = (uint32_t)g.twk[i] * b_kfstep;
+            }
             int s = 0, ph = 0, k = 0, Pcur = 0, ntr = 0;  // Pcur: ring position of the slot two rows above the tile's first input row
             RsWalk w = rs_walk(a);
             while (w.next()) {
@@ -515,11 +534,13 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                     const uint32_t b_i = b_ks + rb[i];
 #pragma unroll
                                     for (int kf = 0; kf < 3; ++kf) {
+                                        if (kf < nkf) {  // bin tap kf: a pixel shift of the staged row, its own slice of the weight image
 #pragma unroll
-                                        for (int pr = 0; pr < NPROD; ++pr) {  // a_hi w_hi, a_hi w_lo, a_lo w_hi
-                                            const uint32_t alo = a_i + (uint32_t)kf + (pr == 2 ? lo_split : 0u);
-                                            const uint32_t blo = b_i + (uint32_t)kf * b_kfstep + (pr == 1 ? b_spstep : 0u);
-                                            umma_bf16(rd[i], ((uint64_t)kDescHi << 32) | (uint64_t)alo, ((uint64_t)kDescHi << 32) | (uint64_t)blo, rid[i], 1u);
+                                            for (int pr = 0; pr < NPROD; ++pr) {  // a_hi w_hi, a_hi w_lo, a_lo w_hi
+                                                const uint32_t alo = a_i + tap_a[kf] + (pr == 2 ? lo_split : 0u);
+                                                const uint32_t blo = b_i + tap_b[kf] + (pr == 1 ? b_spstep : 0u);
+                                                umma_bf16(rd[i], ((uint64_t)kDescHi << 32) | (uint64_t)alo, ((uint64_t)kDescHi << 32) | (uint64_t)blo, rid[i], 1u);
+                                            }
                                         }
                                     }
                                 }
@@ -542,7 +563,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         // ---------------------------------------------------------------- epilogue (warps 2..9)
         const int quad = warp & 3, half = (warp - kRsEpi0) >> 2;
         const int et = tid - kRsEpi0 * 32;
-        const int npix = a.T * a.F;
+        const int npix = a.T * g.Fout;
         float *myred = red + (warp - kRsEpi0) * 2 * Nc;
         int prev_b = -1, k = 0, xo = 2 % L, ntr = 0;  // xo: ring position of the next output row to drain
         const bool tracer = warp == kRsEpi0 && lane == 0;
@@ -648,11 +669,15 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 prev_b = b;
             }
             const int seg = g.S > 1 ? (quad * 32 + lane) / g.Wr : 0;  // packed mode: which strip this lane belongs to
-            const int f = g.S > 1 ? (quad * 32 + lane) - seg * g.Wr : 128 * w.m + quad * 32 + lane;
+            const int jg = g.S > 1 ? (quad * 32 + lane) - seg * g.Wr : 128 * w.m + quad * 32 + lane;  // grid bin of this lane
+            const int f = g.ostride * jg + g.ooff;                                                     // its output bin
             const int tseg = seg * g.DS;
-            const bool fvalid = f < a.F;
+            const bool fvalid = jg < g.Wg && f < g.Fout;
             const bool last_seg = seg == g.S - 1;
-            const int fmask = 7 & ~(f == 0 ? 1 : 0) & ~(f == a.F - 1 ? 4 : 0);
+            int fmask = 0;  // bit kf of the ORIGINAL weight: that bin tap reads inside the input tensor
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (i < g.nkf && jg + g.tboff[i] >= 0 && jg + g.tboff[i] < g.Fin) fmask |= 1 << g.twk[i];
             __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
             RsTiles tl;
             tl.init(a, w);
@@ -706,14 +731,14 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                 ssum[q] += y[q];
                                 ssq[q] = fmaf(y[q], y[q], ssq[q]);
                             }
-                            const int pix = t * a.F + f;
+                            const int pix = t * g.Fout + f;
                             if (a.out_cl) {
                                 // data gradient: accumulate into the fp32 channels-last gradient of the conv's input
                                 float *o = reinterpret_cast<float *>(a.out) + ((size_t)b * npix + pix) * a.out_ctot + a.out_coff + cb;
 #pragma unroll
                                 for (int q = 0; q < 16; q += 4) {
                                     if (cb + q < a.cout) {
-                                        float4 old = *reinterpret_cast<float4 *>(o + q);
+                                        float4 old = a.out_cl == 1 ? *reinterpret_cast<float4 *>(o + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                                         old.x += y[q];
                                         old.y += y[q + 1];
                                         old.z += y[q + 2];
@@ -826,7 +851,7 @@ __global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
             const int r = i / N3;
             const int kg = r & 1, kf = r >> 1;
             const int ktg = n / p.Nc, co = n - ktg * p.Nc;
-            const int kt = 2 - ktg;
+            const int kt = p.flip_t ? ktg : 2 - ktg;  // weight frame tap of image block ktg
             float h[8], l[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -865,8 +890,9 @@ __global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) acc[k] = fmaf(__ldg(p.w + ((size_t)k * p.cin + ci0 + ci) * p.cout_pad + n), sv, acc[k]);
             }
+            // slot k' = (kt', kf) of the kernel's table is the conv-equivalent tap: W[2 - kt'] for a transposed conv
 #pragma unroll
-            for (int k = 0; k < 9; ++k) wb[(part * 9 + k) * p.Nc + n] = acc[k];
+            for (int k = 0; k < 9; ++k) wb[(part * 9 + (p.flip_t ? (2 - k / 3) * 3 + k % 3 : k)) * p.Nc + n] = acc[k];
         }
         __syncthreads();
         float *dst = p.btab + ((size_t)b * p.nsplit + split) * 9 * p.Nc;
@@ -943,40 +969,143 @@ RsEncodeFn rs_get_encode() {
 
 int rs_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-bool rs_shape_ok(const ConvArgs &a) {
-    if (a.transposed || a.KT != 3 || a.KF != 3 || a.stride_f != 1 || a.pad_t != 1 || a.pad_f != 1) return false;
-    if (a.Fin != a.Fout || (a.Fin != 127 && a.Fin != 255 && a.Fin != 63 && a.Fin != 31 && a.Fin != 15 && a.Fin != 7)) return false;
-    if (a.Fin < 127) {  // packed strips: 128 / (F + 1) strips of at least 4 frames
-        static const int packed_min = getenv("MISO_RS_PACKED_MINF") ? atoi(getenv("MISO_RS_PACKED_MINF")) : 7;
-        const int S = 128 / (a.Fin + 1);
-        if (a.Fin < packed_min || a.T / S < 4) return false;
+// Layer variants of the row-streaming kernel (RsGeom): a transposed stride-(1,2) conv is two launches (even / odd output
+// bins) over the same weight image.
+enum RsKind { RS_DENSE = 0, RS_FIRST, RS_DECONV2_EVEN, RS_DECONV2_ODD, RS_DECONV1 };
+
+int rs_kinds(const ConvArgs &a, int kinds[2]) {
+    static const bool variants = !(getenv("MISO_RS_VARIANTS") && atoi(getenv("MISO_RS_VARIANTS")) == 0);
+    if (a.KT != 3 || a.KF != 3 || a.pad_t != 1) return 0;
+    if (!a.transposed && a.stride_f == 1 && a.pad_f == 1 && a.Fin == a.Fout) {
+        kinds[0] = RS_DENSE;
+        return 1;
     }
+    if (!variants) return 0;
+    if (!a.transposed && a.stride_f == 1 && a.pad_f == 0 && a.Fout == a.Fin - 2) {
+        kinds[0] = RS_FIRST;
+        return 1;
+    }
+    // Two launches (even / odd output bins) re-read the input and write every other 16-byte pixel: measured on B200
+    // (profiles/r2_conv_rs_variants.json) 238 us against 245 for the general kernel at 127 -> 255 bins and SLOWER below
+    // (157 vs 137 us at 63 -> 127, 91 vs 79, 62 vs 51), so the pair is opt-in.
+    static const bool deconv2 = getenv("MISO_RS_DECONV2") && atoi(getenv("MISO_RS_DECONV2")) != 0;
+    if (deconv2 && a.transposed && a.stride_f == 2 && a.pad_f == 0 && a.Fout == 2 * a.Fin + 1) {
+        kinds[0] = RS_DECONV2_EVEN;
+        kinds[1] = RS_DECONV2_ODD;
+        return 2;
+    }
+    if (a.transposed && a.stride_f == 1 && a.pad_f == 0 && a.Fout == a.Fin + 2) {
+        kinds[0] = RS_DECONV1;
+        return 1;
+    }
+    return 0;
+}
+
+bool rs_shape_ok(const ConvArgs &a, int kind) {
     if (a.in_layout != LAYOUT_PLANES) return false;
-    if (a.in_ctot % 8 || a.in_coff % 8 || a.cout % 8) return false;
+    if (a.in_ctot % 8 || a.in_coff % 8) return false;
     if (a.out_layout == LAYOUT_PLANES) {
-        if (a.out_ctot % 8 || a.out_coff % 8 || a.resid) return false;
-    } else {
-        // fp32 channels-last output: only as an in-place accumulation (resid == out), no ELU / statistics
+        if (a.out_ctot % 8 || a.out_coff % 8 || a.cout % 8 || a.resid) return false;
+    } else if (a.resid) {
+        // fp32 channels-last output as an in-place accumulation (resid == out, the data gradients): no ELU / statistics
+        if (kind != RS_DENSE || a.cout % 8) return false;
         if (a.resid != reinterpret_cast<const float *>(a.out) || a.resid_ctot != a.out_ctot || a.resid_coff != a.out_coff) return false;
         if (a.out_ctot % 4 || a.out_coff % 4 || a.elu || a.out_sums) return false;
+    } else {
+        // fp32 channels-last output, stored (the network output)
+        if (a.cout % 4 || a.out_ctot % 4 || a.out_coff % 4 || a.out_sums) return false;
     }
     if (a.norm_mode == NORM_GLN) return false;
     if (a.T < 2) return false;
     return true;
 }
 
-bool make_rs_geom(const ConvArgs &a, int split, RsGeom &g) {
+// reads past the Wr pixels of a row (strip) land on the first pixels of the next one: fine iff those reads are padding
+// reads AND the aliased pixels are zero fill (the shared-pad raster)
+bool rs_alias_ok(const RsGeom &g, int Wr) {
+    for (int j = 0; j < g.Wg; ++j)
+        for (int i = 0; i < g.nkf; ++i) {
+            const int px = j + g.tshift[i];
+            if (px < Wr) continue;
+            const int src = j + g.tboff[i], alias = g.f_org + px - Wr;
+            if (src >= 0 && src < g.Fin) return false;
+            if (alias >= 0 && alias < g.Fin) return false;
+        }
+    return g.Fin - g.f_org <= Wr;  // every input bin lies inside the loaded pixels
+}
+
+bool make_rs_geom(const ConvArgs &a, int split, int kind, RsGeom &g) {
     g = RsGeom{};
-    if (!rs_shape_ok(a)) return false;
+    if (!rs_shape_ok(a, kind)) return false;
     g.nsp = split == 3 ? 2 : 1;
     g.Nc = rs_round_up(a.cout, 16);
     static const int max_nc = getenv("MISO_RS_MAXNC") ? atoi(getenv("MISO_RS_MAXNC")) : 64;
     if (g.Nc > max_nc) return false;
     g.N3 = 3 * g.Nc;
-    g.Mr = std::max(1, (a.Fin + 1) / 128);
-    g.map5d = g.Mr == 2;
-    g.pitch = g.map5d ? 130 : 128;
-    g.Wr = std::min(128, a.Fin + 1);
+    g.Fin = a.Fin;
+    g.Fout = a.Fout;
+    g.ostride = 1;
+    g.ooff = 0;
+    g.nkf = 3;
+    for (int i = 0; i < 3; ++i) g.twk[i] = i;
+    switch (kind) {
+        case RS_DENSE:
+            g.tboff[0] = -1, g.tboff[1] = 0, g.tboff[2] = 1;
+            g.f_org = -1;
+            g.Wg = a.Fin;
+            break;
+        case RS_FIRST:
+            g.tboff[0] = 0, g.tboff[1] = 1, g.tboff[2] = 2;
+            g.f_org = 0;
+            g.Wg = a.Fout;
+            break;
+        case RS_DECONV2_EVEN:  // out[2 j] = in[j] W[.][0] + in[j - 1] W[.][2]
+            g.nkf = 2;
+            g.tboff[0] = 0, g.tboff[1] = -1;
+            g.twk[0] = 0, g.twk[1] = 2;
+            g.f_org = -1;
+            g.Wg = a.Fin + 1;
+            g.ostride = 2;
+            break;
+        case RS_DECONV2_ODD:  // out[2 j + 1] = in[j] W[.][1]
+            g.nkf = 1;
+            g.tboff[0] = 0;
+            g.twk[0] = 1;
+            g.f_org = -1;
+            g.Wg = a.Fin;
+            g.ostride = 2;
+            g.ooff = 1;
+            break;
+        case RS_DECONV1:  // out[j] = sum_kf in[j - kf] W[.][kf]
+            g.tboff[0] = 0, g.tboff[1] = -1, g.tboff[2] = -2;
+            g.f_org = -2;
+            g.Wg = a.Fin + 2;
+            break;
+        default:
+            return false;
+    }
+    int max_shift = 0;
+    for (int i = 0; i < g.nkf; ++i) {
+        g.tshift[i] = g.tboff[i] - g.f_org;
+        max_shift = std::max(max_shift, g.tshift[i]);
+    }
+    // M tiling of the Wg grid bins of a frame row: packed strips (Wr <= 64 pixels, S strips of one sample per M tile), one
+    // region on the shared-pad raster (pitch 128), or Mr regions of 128 bins at a pitch of 128 + max_shift (5-D tensor map)
+    int wr = 8;
+    while (wr < std::max(g.Wg, g.Fin - g.f_org)) wr <<= 1;
+    if (wr <= 64) {
+        static const int packed_min = getenv("MISO_RS_PACKED_MINF") ? atoi(getenv("MISO_RS_PACKED_MINF")) : 7;
+        if (!rs_alias_ok(g, wr) || a.Fin < packed_min || a.T / (128 / wr) < 4) return false;
+        g.Wr = wr;
+        g.Mr = 1;
+        g.map5d = 0;
+        g.pitch = 128;
+    } else {
+        g.Wr = 128;
+        g.Mr = (g.Wg + 127) / 128;
+        g.map5d = (g.Mr >= 2 || !rs_alias_ok(g, 128)) ? 1 : 0;
+        g.pitch = g.map5d ? 128 + max_shift : 128;
+    }
     g.S = 128 / g.Wr;
     g.DS = a.T / g.S;
     g.TS = g.DS + a.T % g.S;
@@ -1013,6 +1142,15 @@ bool make_rs_geom(const ConvArgs &a, int split, RsGeom &g) {
     while (cols < (g.L + 2) * g.Nc) cols <<= 1;
     g.tmem_cols = cols;
     return cols <= 512;
+}
+// the geometry of the first launch of a layer (the phases of a transposed stride-2 conv share everything the callers size)
+bool make_rs_geom(const ConvArgs &a, int split, RsGeom &g) {
+    int kinds[2];
+    const int n = rs_kinds(a, kinds);
+    if (n == 0) return false;
+    for (int i = n - 1; i >= 0; --i)
+        if (!make_rs_geom(a, split, kinds[i], g)) return false;
+    return true;
 }
 
 int rs_encode_maps(const ConvArgs &a, const RsGeom &g, CUtensorMap *hi, CUtensorMap *lo) {
@@ -1135,7 +1273,7 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
     k.out_lo_off = a.out_lo_off;
     k.use_lo = a.use_lo;
     k.elu = a.elu;
-    k.out_cl = a.out_layout == LAYOUT_CL_F32 ? 1 : 0;
+    k.out_cl = a.out_layout == LAYOUT_CL_F32 ? (a.resid ? 1 : 2) : 0;
     k.trace = (g_rs_trace && a.cin == g_rs_trace_cin && a.Fin == g_rs_trace_fin) ? g_rs_trace : nullptr;
     k.fuse = fuse;
     dim3 grid(rs_grid(a, g), 1, 1);
@@ -1145,12 +1283,13 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
     else
         MISO_CUDA(launch_pdl(conv_rs_kernel<1>, grid, dim3(kRsThreads), (size_t)g.smem_total, stream, tm_hi, tm_lo, k));
     {
-        const double pix = (double)a.B * a.T * a.Fout;
-        const double flops = 2.0 * pix * a.cin * a.cout * 9;
-        const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout);
+        // a launch's share of the layer: nkf of the three bin taps (a transposed conv's MACs are counted per INPUT pixel)
+        const double pix = (double)a.B * a.T * (a.transposed ? a.Fin : a.Fout);
+        const double flops = 2.0 * pix * a.cin * a.cout * 3 * g.nkf;
+        const double bytes = (a.use_lo ? 4.0 : 2.0) * a.B * a.T * ((double)a.Fin * a.cin + (double)a.Fout * a.cout) * g.nkf / 3.0;
         // issued: every input row (incl. the two halo rows of a strip: ignored here) is one M = 128 tile per column region,
         // nunit K units x 3 bin taps x (3 products in bf16x3) MMAs of width N3
-        const double exec = (double)rs_rows(a, g) * g.nunit * 3.0 * (split == 3 ? 3.0 : 1.0) * 2.0 * 128.0 * g.N3 * 16.0;
+        const double exec = (double)rs_rows(a, g) * g.nunit * g.nkf * (split == 3 ? 3.0 : 1.0) * 2.0 * 128.0 * g.N3 * 16.0;
         prof_end(stream, flops, bytes, MISO_PROF_CONV_RS, exec);
     }
     MISO_LAUNCHED("conv_rs_kernel");
@@ -1159,8 +1298,11 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
 }  // namespace
 
 int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream) {
+    int kinds[2];
+    const int nkind = rs_kinds(a, kinds);
     RsGeom g;
-    MISO_REQUIRE(make_rs_geom(a, split, g), "conv_rs: layer does not fit the row-streaming path (cin=%d cout=%d F=%d)", a.cin, a.cout, a.Fin);
+    MISO_REQUIRE(nkind > 0 && make_rs_geom(a, split, g), "conv_rs: layer does not fit the row-streaming path (cin=%d cout=%d F=%d)", a.cin, a.cout,
+                 a.Fin);
     const int nsplit = (a.cin + kRsBiasCi - 1) / kRsBiasCi;
     const size_t need_w = (size_t)a.B * g.nunit * g.w_unit, need_b = (size_t)a.B * nsplit * 9 * g.Nc * sizeof(float);
     if (need_w > scratch.wimg_bytes || need_b > scratch.btab_bytes) {
@@ -1168,10 +1310,6 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
                   need_b);
         return MISO_E_WORKSPACE;
     }
-    static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
-    if (debug)
-        fprintf(stderr, "conv_rs: cin=%d cout=%d F=%d | S=%d Nc=%d L=%d G=%d Mr=%d pitch=%d kper=%d nchunk=%d nstage=%d stage=%dB tmem=%d smem=%d\n", a.cin,
-                a.cout, a.Fin, g.S, g.Nc, g.L, g.G, g.Mr, g.pitch, g.kper, g.nchunk, g.nstage, g.stage, g.tmem_cols, g.smem_total);
     int rc = conv_rs_init();
     if (rc) return rc;
 
@@ -1193,13 +1331,24 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.nunit = g.nunit;
     p.nsp = g.nsp;
     p.nsplit = nsplit;
+    p.flip_t = a.transposed ? 1 : 0;
     const size_t prep_smem = (size_t)(kRsBiasCi + 8 * 9 * g.Nc) * sizeof(float);
     prof_begin(stream);
     MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_rs_prep_kernel, dim3(a.B * g.nunit + a.B * nsplit), dim3(256), prep_smem, stream, p));
     prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_rs_prep_kernel");
     RsFuse none{};
-    return rs_launch(a, split, g, p.wimg, p.btab, nsplit, none, stream);
+    static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
+    for (int i = 0; i < nkind; ++i) {  // one launch per phase, all over the same weight image / bias sums
+        MISO_REQUIRE(make_rs_geom(a, split, kinds[i], g), "conv_rs: geometry of variant %d", kinds[i]);
+        if (debug)
+            fprintf(stderr, "conv_rs: kind %d cin=%d cout=%d Fin=%d Fout=%d | Wg=%d S=%d Wr=%d Nc=%d L=%d G=%d Mr=%d pitch=%d map5d=%d kper=%d nchunk=%d nstage=%d stage=%dB tmem=%d smem=%d\n",
+                    kinds[i], a.cin, a.cout, a.Fin, a.Fout, g.Wg, g.S, g.Wr, g.Nc, g.L, g.G, g.Mr, g.pitch, g.map5d, g.kper, g.nchunk, g.nstage, g.stage,
+                    g.tmem_cols, g.smem_total);
+        rc = rs_launch(a, split, g, p.wimg, p.btab, nsplit, none, stream);
+        if (rc) return rc;
+    }
+    return MISO_OK;
 }
 
 // ---- fused mode (forward DenseBlock convs): sizes of the per-layer persistent buffers and the launch
@@ -1209,7 +1358,8 @@ bool conv_rs_dense_need(const ConvArgs &a, int split, int c0, RsDenseNeed *need)
     // and run once-per-launch code at instruction-cache-miss speed: 11.3-11.7 ms per bench step against 10.9-11.1.
     static const bool on = getenv("MISO_RS_FUSE") && atoi(getenv("MISO_RS_FUSE")) != 0;
     RsGeom g;
-    if (!on || !conv_rs_eligible(a, split) || !make_rs_geom(a, split, g)) return false;
+    int kinds[2];
+    if (!on || rs_kinds(a, kinds) != 1 || kinds[0] != RS_DENSE || !conv_rs_eligible(a, split) || !make_rs_geom(a, split, g)) return false;
     if (a.norm_mode != NORM_IN || c0 % 8 || c0 < 0 || c0 >= a.cin) return false;
     const int u0 = c0 / 16, nlate = g.nunit - u0;
     if (nlate * 16 > kRsAffCh || a.cin - c0 > kRsAffCh) return false;
