@@ -274,7 +274,7 @@ def test_training_step_upit_end_to_end():
 
 
 @pytest.mark.parametrize("kind", ["miso1", "miso3"])
-def test_training_step_against_reference_fixture(kind):
+def test_training_step_against_reference_fixture_unit_prelu_slopes_loose_bounds(kind):
     """The CUDA training step against the REAL reference's model(mix) -> loss -> loss.backward() (tests/golden/train_ref.npz,
     generated by oracle/make_golden.py:golden_training from model.py + criterion.py; PReLU slopes 1).  The L1 losses'
     sign() makes a single estimate/reference crossing worth ~1e-2 of the gradient at this size (12 k output values), so the
@@ -367,3 +367,43 @@ def test_training_full_size_properties():
             p.add_(g, alpha=eps / gnorm)
     fd = (lp - lm) / (2 * eps)
     assert abs(fd - gnorm) < 2e-2 * gnorm, (fd, gnorm)
+
+
+def test_training_graph_replay_and_gradient_buckets():
+    """Round-2 training plumbing.  (1) From the third step with the same buffers the forward and the backward are replayed as
+    CUDA graphs: the gradient of a replayed step equals the eager one (the tcgen05 weight gradient reduces its per-CTA
+    partial sums in a fixed order; the remaining fp32 atomics of the small kernels move it at rounding level only).
+    (2) miso_net_grad_buckets: five contiguous ranges in completion order that tile the flat gradient buffer exactly, and
+    miso_net_wait_grad_bucket accepts every one of them after a backward."""
+    import ctypes
+    from misonet_b200 import _lib, synth
+    m, cfg, sd = _model(0, "REF", "bf16x3", 1.0)
+    mix = torch.from_numpy(synth.random_spec(3, (2, 6, 24, 129))).cuda()
+    up = torch.from_numpy(synth.random_spec(4, (2, 2, 24, 129))).cuda()
+    grads = []
+    for it in range(4):          # eager, capture, replay, replay
+        m.zero_grad(set_to_none=True)
+        est = m(mix)
+        (est.real * up.real + est.imag * up.imag).sum().backward()
+        grads.append(torch.cat([p.grad.flatten() for p in m.parameters()]).clone())
+    scale = float(grads[0].norm())
+    for g in grads[1:]:
+        assert float((g - grads[0]).norm()) <= 2e-6 * scale
+    assert torch.equal(grads[2], grads[3]) or float((grads[2] - grads[3]).norm()) <= 1e-6 * scale
+    lib = _lib.load()
+    b0, b1 = (ctypes.c_int64 * 8)(), (ctypes.c_int64 * 8)()
+    nb = lib.miso_net_grad_buckets(m._handle, b0, b1, 8)
+    assert nb == 5
+    ranges = sorted((int(b0[k]), int(b1[k])) for k in range(nb))
+    assert ranges[0][0] == 0 and ranges[-1][1] == lib.miso_net_grad_numel(m._handle)
+    assert all(ranges[i][1] == ranges[i + 1][0] for i in range(nb - 1))          # contiguous, no overlap
+    # completion order: the upper decoders' bucket comes first and lies between the encoders and the TCN in key order
+    keys = [k for k, _ in m.named_parameters()]
+    offs = np.cumsum([0] + [p.numel() for p in m.parameters()])
+    first_dec = int(offs[keys.index("decoders.0.0.net.0.weight")])
+    first_tcn = int(offs[[k.startswith("TCN.") for k in keys].index(True)])
+    assert first_dec <= int(b0[0]) < int(b1[0]) == first_tcn
+    st = torch.cuda.Stream()
+    for k in range(nb):
+        _lib.check(lib.miso_net_wait_grad_bucket(m._handle, k, ctypes.c_void_p(st.cuda_stream)), "miso_net_wait_grad_bucket")
+    st.synchronize()
