@@ -109,9 +109,15 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x);
 // occasionally flips the bf16 rounding of an activation downstream).  The buffers are declared double*
 // for historical reasons and only touched through stat_add / stat_get / stat_set.  A negative
 // sum-of-squares marks a channel that is consumed raw (no normalisation in the reference at that point).
+// Range: |sum| < 2^43 ~ 8.8e12, i.e. a channel RMS up to ~8e3 over a 500 x 257 plane -- unit-scale spectra (the
+// reference divides the STFT by the window sum, dataloader/data.py:77) sit nine orders of magnitude below.  A partial
+// sum beyond that is clamped instead of wrapping, so an out-of-range input gives a saturated (finite, wrong-scale)
+// normalisation rather than garbage with a flipped sign.
 constexpr double kStatScale = 1048576.0;
+constexpr double kStatClamp = 4.0e18;  // < 2^62: one clamped addend cannot wrap the accumulator
 __device__ __forceinline__ void stat_add(double *p, double v) {
-    atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)__double2ll_rn(v * kStatScale));
+    const double s = fmin(fmax(v * kStatScale, -kStatClamp), kStatClamp);
+    atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)__double2ll_rn(s));
 }
 __device__ __forceinline__ double stat_get(const double *p) {
     return (double)(*reinterpret_cast<const long long *>(p)) * (1.0 / kStatScale);
