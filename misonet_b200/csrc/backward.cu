@@ -753,6 +753,9 @@ __device__ __forceinline__ GlnStat gln_stat(const double *s, double inv_n, float
 }
 
 constexpr int kTcnBwFrames = 16;
+// ELU / its derivative through ex2.approx (absolute error ~1e-7): the recomputed activations feed bf16 hi/lo GEMM operands
+// and gradients held to 1e-3, and expm1f / expf cost ~10x the instructions
+__device__ __forceinline__ float elu_fast_bw(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
 // y = dwconv(ELU(IN1d(u))) (pre-PReLU) and q = gLN(PReLU(y)) (the pointwise conv's input), both fp32 [B][T][C]
 __global__ void __launch_bounds__(256) tcn_recompute_kernel(const TcnBwdArgs a, float *__restrict__ Y, float *__restrict__ Q) {
@@ -782,7 +785,7 @@ __global__ void __launch_bounds__(256) tcn_recompute_kernel(const TcnBwdArgs a, 
         if (t >= T) break;
         auto act = [&](int tq) {
             if (tq < 0 || tq >= T) return 0.f;
-            return elu1(fmaf(ub[(size_t)tq * C + c], sc[c], sf[c]));
+            return elu_fast_bw(fmaf(ub[(size_t)tq * C + c], sc[c], sf[c]));
         };
         const float y = fmaf(wt[c], act(t - a.dil), fmaf(wt[C + c], act(t), wt[2 * C + c] * act(t + a.dil)));
         const float p = y > 0.f ? y : al * y;
@@ -882,10 +885,13 @@ __global__ void __launch_bounds__(128) gln_bwd_apply_kernel(const TcnBwdArgs a, 
 
 // depthwise conv + ELU backward: DN = dL/dn (n = IN1d(u)), its per-(b,c) sums for the InstanceNorm1d backward, and
 // the depthwise weight gradient
+// 32 frames per CTA: every CTA ends with five atomics per channel onto [b][c] / [c] accumulators, and with 8 frames the 504
+// CTAs of a B = 8, T = 500 step serialised on them (56 us per launch; the arithmetic is ~10 us)
+constexpr int kTcnRowsDw = 32;
 __global__ void __launch_bounds__(128) dw_bwd_kernel(const TcnBwdArgs a, const float *__restrict__ DY, float *__restrict__ DN,
                                                      double *__restrict__ ired, float *__restrict__ dwdw) {
     const int C = a.C, T = a.T, b = blockIdx.y, d = a.dil;
-    const int t0 = blockIdx.x * kTcnRows, t1 = min(T, t0 + kTcnRows);
+    const int t0 = blockIdx.x * kTcnRowsDw, t1 = min(T, t0 + kTcnRowsDw);
     const float *ub = a.u + (size_t)b * T * C;
     const float *dyb = DY + (size_t)b * T * C;
     for (int c = threadIdx.x; c < C; c += 128) {
@@ -895,18 +901,19 @@ __global__ void __launch_bounds__(128) dw_bwd_kernel(const TcnBwdArgs a, const f
         float s1 = 0.f, s2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
         auto nrm = [&](int tq) { return fmaf(ub[(size_t)tq * C + c], af.x, af.y); };
         auto dyat = [&](int tq) { return (tq >= 0 && tq < T) ? dyb[(size_t)tq * C + c] : 0.f; };
-        auto vat = [&](int tq) { return (tq >= 0 && tq < T) ? elu1(nrm(tq)) : 0.f; };
+        auto vat = [&](int tq) { return (tq >= 0 && tq < T) ? elu_fast_bw(nrm(tq)) : 0.f; };
         for (int t = t0; t < t1; ++t) {
             // forward: y[t] = w0 v[t-d] + w1 v[t] + w2 v[t+d]
             const float dy = dyat(t);
             const float dv = fmaf(w0, dyat(t + d), fmaf(w1, dy, w2 * dyat(t - d)));
             const float n = nrm(t);
-            const float dn = n > 0.f ? dv : dv * expf(n);
+            const float en = __expf(n);
+            const float dn = n > 0.f ? dv : dv * en;
             DN[((size_t)b * T + t) * C + c] = dn;
             s1 += dn;
             s2 = fmaf(dn, n, s2);
             g0 = fmaf(dy, vat(t - d), g0);
-            g1 = fmaf(dy, n > 0.f ? n : expm1f(n), g1);
+            g1 = fmaf(dy, n > 0.f ? n : en - 1.f, g1);
             g2 = fmaf(dy, vat(t + d), g2);
         }
         atomicAdd(ired + ((size_t)b * C + c) * 2, (double)s1);
@@ -1127,7 +1134,7 @@ int launch_dw_bwd(const TcnBwdArgs &a, const float *DY, float *DN, double *ired,
                   cudaStream_t st) {
     MISO_CUDA(cudaMemsetAsync(ired, 0, (size_t)a.B * a.C * 2 * sizeof(double), st));
     dim3 grid(ceil_div(a.T, kTcnRows), a.B);
-    dw_bwd_kernel<<<grid, 128, 0, st>>>(a, DY, DN, ired, dwdw);
+    dw_bwd_kernel<<<dim3(ceil_div(a.T, kTcnRowsDw), a.B), 128, 0, st>>>(a, DY, DN, ired, dwdw);
     MISO_LAUNCHED("dw_bwd_kernel");
     in1d_bwd_apply_kernel<<<grid, 128, 0, st>>>(a, DN, ired, out, accumulate);
     MISO_LAUNCHED("in1d_bwd_apply_kernel");
