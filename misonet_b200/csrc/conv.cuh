@@ -74,34 +74,6 @@ bool conv_rs_eligible(const ConvArgs &a, int split);
 void conv_rs_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size_t *btab_bytes);
 int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaStream_t stream);
 
-// Fused operand preparation of the forward DenseBlock convs (conv_rs.cu, RsFuse): conv k of a block builds, inside the
-// kernel, the weight-image units / border-bias sums of its LAST input group (channels [c0, cin), produced by the kernel
-// right before it) for itself, and the same group's slices for the later convs of the block ("jobs") into their
-// persistent per-layer buffers -- no preparation launch between two convs of a block.
-constexpr int kRsMaxJobs = 4;
-struct RsDenseJob {
-    const float *w;   // the consumer's packed fp32 weights [9][cin][cout_pad]
-    void *wimg;       // the consumer's persistent weight image
-    float *btab;      // the consumer's border-bias partial sums [B][ngroup][9][Nc]
-    int cin, cout, cout_pad, ngroup, gidx;
-};
-struct RsDense {
-    int c0;            // first channel of the late group (multiple of 8)
-    void *wimg;        // this layer's persistent image: the units below c0 / 16 were written by the earlier convs' jobs
-    float *btab;       // [B][ngroup_early][9][Nc]
-    int ngroup_early;  // groups in btab (0 for the first conv of a block)
-    void *priv;        // per-CTA private scratch (RsDenseNeed::priv bytes)
-    int njob;
-    RsDenseJob job[kRsMaxJobs];
-};
-struct RsDenseNeed {
-    size_t wimg, btab_per_group, priv;
-};
-bool conv_rs_dense_need(const ConvArgs &a, int split, int c0, RsDenseNeed *need);  // false: not eligible for the fused path
-int launch_conv_rs_dense(const ConvArgs &a, int split, const RsDense &d, cudaStream_t stream);
-bool conv_rs_jobs_in_kernel();  // default: the later convs' slices are built inside the conv kernel
-int launch_rs_group_prep(const ConvArgs &a, int split, const RsDense &d, cudaStream_t stream);  // ... or by a launch of their own
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&v);

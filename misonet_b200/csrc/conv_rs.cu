@@ -38,21 +38,23 @@
 namespace miso {
 namespace {
 
-constexpr int kRsThreads = 10 * 32;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int kRsThreads = 10 * 32;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue (two per tensor-memory lane quarter)
 constexpr int kRsEpi0 = 2;
 constexpr int kRsEpiThreads = 256;
+constexpr int kRsEpiWarps = kRsEpiThreads / 32;
+constexpr int kRsEpiW = kRsEpiWarps / 4;  // epilogue warps per lane quarter
 constexpr int kRsMaxG = 8;
 constexpr int kRsMaxStages = 4;
 constexpr int kRsSmemLimit = 227 * 1024;
 constexpr int kRsFixed = 1024;
 constexpr int kRsBiasCi = 64;
-constexpr int kRsAffCh = 144;  // channels of the late units in fused mode: a group of <= 128 channels + 8 + padding to a unit
 
 struct RsGeom {
     int Nc, N3, L, G, Mr, pitch, PL, GS, nsp;
     int nplanes, nunit, kper, nchunk;
     int w_unit, w_off, stage, nstage, box_bytes;
-    int off_btab, off_red, off_aff, off_stage, smem_total, tmem_cols;
+    int off_btab, off_red, off_stage, smem_total, tmem_cols;
+    int red_stride;  // floats per epilogue warp in the statistics reduction buffer
     int map5d;
     int S, TS, DS, Wr;  // packed mode (F + 1 <= 64): an M tile holds the same row of S frame strips; strip s covers the TS frames
                         // from s * DS, DS = T / S, TS = DS + T % S (the strips overlap by T % S frames so that they tile any T
@@ -69,47 +71,6 @@ struct RsGeom {
     int f_org, Wg, Fin, Fout, ostride, ooff;
 };
 
-// In-kernel operand preparation ("fused" mode, the forward DenseBlock convs).  The input channels of conv k of a block
-// are [x | y0 | ... | y_{k-2}]; only the statistics of the LAST group (produced by the kernel right before this one) are
-// new, so the slices of the weight image / border-bias sums of the older groups were written by the earlier convs of
-// the block (their "jobs"), and this kernel's idle epilogue warps build, at kernel start,
-//   (i)  privately (per CTA, for the samples of its own row range): the image of the units that hold the late group
-//        and the late group's border-bias partial sums -- the producer warp streams those units from the private copy;
-//   (ii) shared: the same group's slices for the LATER convs of the block (distributed over the CTAs; needed one conv later).
-// The packed fp32 weights are cold in L2 behind the previous conv's activation stream, so every line this CTA will read is
-// prefetched first; the producer is released as soon as the private units are in place, the border-bias sums and (ii)
-// follow while the first tiles' MMAs run.  No preparation launch sits between two convs of a block any more.
-constexpr int kRsMaxSlots = 8;   // samples a CTA's row range may touch in fused mode
-struct RsJob {
-    const float *w;        // consumer's packed fp32 weights [9][cin][cout_pad]
-    __nv_bfloat16 *wimg;   // consumer's image [B][nunit][w_unit / 2]
-    float *btab;           // consumer's border-bias partial sums [B][ngroup][9][Nc]
-    int cin, cout, cout_pad, Nc, nunit, ngroup, gidx;
-};
-struct RsFuse {
-    int on;
-    int c0, u0, nlate;     // late group = channels [c0, cin); units [u0, nunit) are built in the kernel
-    int nslot;             // sample slots per CTA of the private scratch
-    __nv_bfloat16 *priv;   // [grid][nslot][nlate][w_unit / 2]
-    float *priv_bias;      // [grid][nslot][9][Nc]
-    const float *w;        // this layer's packed fp32 weights [9][cin][cout_pad]
-    const double *in_sums; // statistics of the input buffer [B][in_ctot][2]
-    int in_ctot, cin, cout_pad;
-    double inv_n;
-    float eps;
-    int njob;              // (ii) in the kernel: slices of the late group for the later convs of the block
-    RsJob job[kRsMaxJobs];
-};
-// the same slices as a separate launch (rs_group_prep_kernel; A/B switch MISO_RS_GROUPKERNEL=1)
-struct RsGroupPrep {
-    const double *in_sums;
-    int in_ctot, c0, nch, B, nsp;
-    double inv_n;
-    float eps;
-    int njob;
-    RsJob job[kRsMaxJobs];
-};
-
 struct RsArgs {
     RsGeom g;
     const __nv_bfloat16 *wimg;  // [B][nunit][kf][hi|lo][kg][N3][8]
@@ -124,10 +85,14 @@ struct RsArgs {
     int out_ctot, out_coff, cout;
     size_t out_lo_off;
     int use_lo, elu;
+    // output-channel chunks (cout > 64: the data gradients of the DenseBlock convs, cout = the forward's cin): the kernel walks
+    // (chunk, sample, region, frame) rows; chunk c covers output channels [c * Nc, c * Nc + Nc) with its own weight image and
+    // border-bias sums.  a.cout is the TOTAL output channel count.
+    int nch;
+    size_t wimg_cstride, btab_cstride;  // elements between the weight images / bias partial sums of consecutive chunks
     int out_cl;  // fp32 channels-last output [B][T*Fout][out_ctot]: 1 = the result is ADDED to it (data gradients), 2 = stored (the
                  // network output, model.py:418-423)
     long long *trace;  // debug: clock64 event log of CTA 0 (tools/tc_trace.py), or null
-    RsFuse fuse;
 };
 
 // trace regions: [0,4096) producer, [4096,8192) MMA issuer, [8192,12288) first epilogue warp; entries are (tag, clock)
@@ -150,20 +115,24 @@ struct RsPrepArgs {
     float *btab;
     int B, Nc, nunit, nsp, nsplit;
     int flip_t;  // transposed convs read input frame t + 1 - kt: the image / bias slots of frame tap kt take W[2 - kt]
+    // output-channel chunks (blockIdx.y): chunk c builds the image / bias sums of output channels [c * Nc, c * Nc + Nc)
+    size_t wimg_cstride, btab_cstride;
 };
 
 // the strips of one CTA: its share [rho, rho_end) of the flattened (sample, column region, frame) row space, cut
 // at (sample, region) boundaries
 struct RsWalk {
-    int rho, rho_end, T, Mr;  // T: rows per unit (frames; packed mode: frames per strip)
-    int b, m, t0, TS, nin;
+    int rho, rho_end, T, Mr, B;  // T: rows per unit (frames; packed mode: frames per strip)
+    int b, m, ch, t0, TS, nin;
     __device__ __forceinline__ bool next() {
         if (rho >= rho_end) return false;
         const int unit = rho / T;
         t0 = rho - unit * T;
         TS = min(T - t0, rho_end - rho);
-        b = unit / Mr;
-        m = unit - b * Mr;
+        const int bb = unit / Mr;  // (chunk, sample)
+        m = unit - bb * Mr;
+        ch = bb / B;
+        b = bb - ch * B;
         nin = TS + 2;  // input rows j = 0 .. TS+1 <-> frames t0-1 .. t0+TS
         rho += TS;
         return true;
@@ -172,11 +141,12 @@ struct RsWalk {
 __device__ __forceinline__ RsWalk rs_walk(const RsArgs &a) {
     RsWalk w;
     const int TU = a.g.S > 1 ? a.g.TS : a.T;
-    const long long R = (long long)a.B * a.g.Mr * TU;
+    const long long R = (long long)a.nch * a.B * a.g.Mr * TU;
     w.rho = (int)(R * blockIdx.x / gridDim.x);
     w.rho_end = (int)(R * (blockIdx.x + 1) / gridDim.x);
     w.T = TU;
     w.Mr = a.g.Mr;
+    w.B = a.B;
     return w;
 }
 
@@ -213,138 +183,27 @@ struct RsTiles {
     }
 };
 
-// ---- fused-mode operand preparation (executed by the 256 epilogue threads; et = thread index among them) ----
-// nhalf consecutive 8-channel halves (kg) of 16-channel K units of a weight image, starting at channel ch0 (multiple of 8):
-// rows [kf][hi|lo][kg][n = (2 - kt) * Nc + co][8 ci] = bf16 split of W[kt][kf][ci][co] * scale[ci - ch0]  (the layout
-// conv_rs_prep_kernel writes).  dst_unit0: image of the unit that holds ch0.  This runs on the critical path of the
-// kernel's start with only a few warps to hide latency, so every thread first issues the loads of kRsBatch outputs
-// (8 weights each) and only then converts and stores them: one L2 round trip per batch instead of one per output.
-constexpr int kRsBatch = 4;
-__device__ __forceinline__ void rs_build_halves(const float *__restrict__ w, int cin, int cout, int cout_pad, int Nc, int nsp, int ch0,
-                                                int nhalf, const float *scale, __nv_bfloat16 *dst_unit0, int tidx, int nthreads) {
-    const int N3 = 3 * Nc, per = 3 * N3;
-    const size_t unit_elems = (size_t)3 * nsp * 2 * N3 * 8;
-    const int total = nhalf * per;
-    for (int i0 = tidx; i0 < total; i0 += kRsBatch * nthreads) {
-        float v[kRsBatch][8];
-        int hh[kRsBatch];
-        size_t doff[kRsBatch];
-#pragma unroll
-        for (int q = 0; q < kRsBatch; ++q) {
-            const int i = i0 + q * nthreads;
-            hh[q] = -1;
-            if (i < total) {
-                const int h = i / per;
-                const int r = i - h * per;
-                const int kf = r / N3, n = r - kf * N3;
-                const int ktg = n / Nc, co = n - ktg * Nc;
-                const int kt = 2 - ktg;
-                const int ch = ch0 + 8 * h, kg = (ch >> 3) & 1;
-                hh[q] = h;
-                doff[q] = (size_t)((ch >> 4) - (ch0 >> 4)) * unit_elems + ((size_t)((kf * nsp) * 2 + kg) * N3 + n) * 8;
-                const float *wp = w + ((size_t)(kt * 3 + kf) * cin + ch) * cout_pad + co;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[q][e] = (ch + e < cin && co < cout) ? __ldg(wp + (size_t)e * cout_pad) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < kRsBatch; ++q) {
-            if (hh[q] < 0) continue;
-            float hv[8], lv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float x = v[q][e] * scale[8 * hh[q] + e];
-                hv[e] = bf16_round(x);
-                lv[e] = x - hv[e];
-            }
-            __nv_bfloat16 *dst = dst_unit0 + doff[q];
-            *reinterpret_cast<uint4 *>(dst) =
-                make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]), pack_bf16x2(hv[6], hv[7]));
-            if (nsp == 2)
-                *reinterpret_cast<uint4 *>(dst + (size_t)2 * N3 * 8) =
-                    make_uint4(pack_bf16x2(lv[0], lv[1]), pack_bf16x2(lv[2], lv[3]), pack_bf16x2(lv[4], lv[5]), pack_bf16x2(lv[6], lv[7]));
-        }
-    }
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2): the epilogue is instruction-issue bound
+__device__ __forceinline__ void add2(float &d0, float &d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 x, y, z;\n\tmov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %5};\n\tadd.rn.f32x2 z, x, y;\n\tmov.b64 {%0, %1}, z;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
-// one tap of a group's border-bias partial sums by ONE warp: dst[n] = sum_{ci < nch} W[k][ch0 + ci][n] * shift(ci), where
-// lane l holds shift of channels l, l + 32, ... in sh[] (fixed summation order)
-__device__ __forceinline__ void rs_warp_bias_tap(const float *__restrict__ w, int cin, int cout, int cout_pad, int Nc, int ch0, int nch, int k,
-                                                 const float (&sh)[5], float *dst, int lane) {
-    for (int n0 = 0; n0 < Nc; n0 += 32) {
-        const int n = n0 + lane;
-        const float *wp = w + ((size_t)k * cin + ch0) * cout_pad + n;
-        float acc = 0.f;
-        for (int c8 = 0; c8 < nch; c8 += 8) {
-            float wv[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) wv[e] = (c8 + e < nch && n < cout) ? __ldg(wp + (size_t)(c8 + e) * cout_pad) : 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int ci = c8 + e;
-                float sv = 0.f;
-#pragma unroll
-                for (int r = 0; r < 5; ++r)
-                    if ((ci >> 5) == r) sv = __shfl_sync(0xffffffffu, sh[r], ci & 31);
-                acc = fmaf(wv[e], sv, acc);
-            }
-        }
-        if (n < Nc) dst[n] = acc;
-    }
+__device__ __forceinline__ void mul2(float &d0, float &d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 x, y, z;\n\tmov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %5};\n\tmul.rn.f32x2 z, x, y;\n\tmov.b64 {%0, %1}, z;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
-// Border-bias partial sums of one channel group: dst[kt * 3 + kf][n] = sum_{ci < nch} W[k][ch0 + ci][n] * shift[ci]
-// (fixed summation order: nparts channel parts, then the parts).  scratch: shared memory, cap floats.
-__device__ __forceinline__ void rs_build_bias(const float *__restrict__ w, int cin, int cout, int cout_pad, int Nc, int ch0, int nch,
-                                              const float *shift, float *scratch, int cap, float *dst, int et) {
-    const int nparts = min(min(7, kRsEpiThreads / Nc), cap / (9 * Nc));
-    const int n = et % Nc, part = et / Nc;
-    if (part < nparts) {
-        float acc[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-        if (n < cout) {
-#pragma unroll 2
-            for (int ci = part; ci < nch; ci += nparts) {
-                const float sv = shift[ci];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) acc[k] = fmaf(__ldg(w + ((size_t)k * cin + ch0 + ci) * cout_pad + n), sv, acc[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) scratch[(part * 9 + k) * Nc + n] = acc[k];
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-    for (int i = et; i < 9 * Nc; i += kRsEpiThreads) {
-        float v = 0.f;
-        for (int q = 0; q < nparts; ++q) v += scratch[q * 9 * Nc + i];
-        dst[i] = v;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
+__device__ __forceinline__ void fma2(float &d0, float &d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 x, y, z, w;\n\tmov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %5};\n\tmov.b64 w, {%6, %7};\n\tfma.rn.f32x2 z, x, y, w;\n\tmov.b64 {%0, %1}, z;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
 }
-// L2 prefetch of the packed weights of channels [ch0, ch0 + nch) of all nine taps ([9][cin][cout_pad] fp32)
-__device__ __forceinline__ void rs_prefetch_w(const float *w, int cin, int cout_pad, int ch0, int nch, int tidx, int nthreads) {
-    const int per_tap = (nch * cout_pad * 4 + 127) >> 7;  // 128-byte lines per tap (a tap's channel range is contiguous)
-    for (int l = tidx; l < 9 * per_tap; l += nthreads) {
-        const int k = l / per_tap, q = l - k * per_tap;
-        const char *p = reinterpret_cast<const char *>(w + ((size_t)k * cin + ch0) * cout_pad) + (size_t)q * 128;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-// consumer-side InstanceNorm affine of channel ci of the input view (in_coff = 0 inside a DenseBlock)
-__device__ __forceinline__ float2 rs_fuse_affine(const RsFuse &fz, int b, int ci) {
-    const double *sp = fz.in_sums + ((size_t)b * fz.in_ctot + ci) * 2;
-    // the statistics were accumulated with atomics by the previous kernel: plain loads through L2
-    return affine_from_sums(stat_get(sp), stat_get(sp + 1), fz.inv_n, (double)fz.eps);
-}
-// first / last sample of this CTA's row range
-__device__ __forceinline__ void rs_sample_range(const RsArgs &a, int &b_first, int &b_last) {
-    const int TU = a.g.S > 1 ? a.g.TS : a.T;
-    const long long R = (long long)a.B * a.g.Mr * TU;
-    const int rho = (int)(R * blockIdx.x / gridDim.x), rho_end = (int)(R * (blockIdx.x + 1) / gridDim.x);
-    b_first = (rho / TU) / a.g.Mr;
-    b_last = rho_end > rho ? ((rho_end - 1) / TU) / a.g.Mr : b_first - 1;
-}
-
-__device__ __forceinline__ float rs_elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
 template <int SPLIT>
 __global__ void __launch_bounds__(kRsThreads, 1)
@@ -358,7 +217,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
     const uint32_t bar_full = smem_u32(smem), bar_empty = smem_u32(smem + 64);
     const uint32_t bar_tfull = smem_u32(smem + 128), bar_tempty = smem_u32(smem + 144);
-    const uint32_t bar_late = smem_u32(smem + 192);  // fused mode: the private late units of sample slot i are in place
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 160);
     float *btab_s = reinterpret_cast<float *>(smem + g.off_btab);
     float *red = reinterpret_cast<float *>(smem + g.off_red);
@@ -373,7 +231,6 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, kRsEpiThreads / 32);
         }
-        for (int i = 0; i < kRsMaxSlots; ++i) mbar_init(bar_late + 8 * i, kRsEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -382,7 +239,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {
-        for (int i = tid; i < 8 * 2 * Nc; i += kRsThreads) red[i] = 0.f;
+        for (int i = tid; i < kRsEpiWarps * g.red_stride; i += kRsThreads) red[i] = 0.f;
         // zero guard behind the A planes of every stage (shared-pad raster: the pixel after the last row)
         for (int i = tid; i < g.nstage * 32; i += kRsThreads)
             reinterpret_cast<uint32_t *>(smem + g.off_stage + (i >> 5) * g.stage + g.w_off - 128)[i & 31] = 0u;
@@ -393,8 +250,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     if (warp >= kRsEpi0) {  // all accumulator slots start cleared
-        const int quad = warp & 3, half = (warp - kRsEpi0) >> 2;
-        for (int col = half * 16; col < g.tmem_cols; col += 32) tmem_zero16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col);
+        const int quad = warp & 3, sub = (warp - kRsEpi0) >> 2;
+        for (int col = sub * 16; col < g.tmem_cols; col += 16 * kRsEpiW) tmem_zero16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -410,14 +267,8 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             int s = 0, ph = 0, ntr = 0;  // stage index and the parity of the release of its previous use
             bool primed = false;         // every stage has been filled once
             RsWalk w = rs_walk(a);
-            int b_first = 0, b_last = 0;
-            if (a.fuse.on) rs_sample_range(a, b_first, b_last);
-            int late_seen = -1;  // last sample slot whose late-unit barrier has been passed
             while (w.next()) {
-                const __nv_bfloat16 *wsrc = a.wimg + (size_t)w.b * a.wimg_bstride;
-                const int slot = w.b - b_first;
-                const __nv_bfloat16 *wlate =
-                    a.fuse.on ? a.fuse.priv + ((size_t)blockIdx.x * a.fuse.nslot + slot) * a.fuse.nlate * (size_t)(g.w_unit / 2) : nullptr;
+                const __nv_bfloat16 *wsrc = a.wimg + (size_t)w.ch * a.wimg_cstride + (size_t)w.b * a.wimg_bstride;
                 const int f0 = 128 * w.m + g.f_org;
                 RsTiles tl;
                 tl.init(a, w);
@@ -444,24 +295,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                             else
                                 tma_load_4d(dst, tm, full, 2 * f0, tin, pl, w.b);
                         }
-                        if (!a.fuse.on) {
-                            bulk_load(sa + (uint32_t)g.w_off, wsrc + (size_t)c * g.kper * (g.w_unit / 2), (uint32_t)(nu * g.w_unit), full);
-                        } else {
-                            for (int q = 0; q < nu; ++q) {  // units below u0 from the layer's image, the late ones from the private copy
-                                const int u = g.kper * c + q;
-                                const __nv_bfloat16 *src;
-                                if (u < a.fuse.u0) {
-                                    src = wsrc + (size_t)u * (g.w_unit / 2);
-                                } else {
-                                    if (late_seen != slot) {
-                                        mbar_wait(bar_late + 8 * slot, 0u);
-                                        late_seen = slot;
-                                    }
-                                    src = wlate + (size_t)(u - a.fuse.u0) * (g.w_unit / 2);
-                                }
-                                bulk_load(sa + (uint32_t)(g.w_off + q * g.w_unit), src, (uint32_t)g.w_unit, full);
-                            }
-                        }
+                        bulk_load(sa + (uint32_t)g.w_off, wsrc + (size_t)c * g.kper * (g.w_unit / 2), (uint32_t)(nu * g.w_unit), full);
                         if (++s == g.nstage) {
                             s = 0;
                             if (primed) ph ^= 1;
@@ -561,112 +395,48 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         }
     } else {
         // ---------------------------------------------------------------- epilogue (warps 2..9)
-        const int quad = warp & 3, half = (warp - kRsEpi0) >> 2;
+        const int quad = warp & 3, sub = (warp - kRsEpi0) >> 2;
         const int et = tid - kRsEpi0 * 32;
         const int npix = a.T * g.Fout;
-        float *myred = red + (warp - kRsEpi0) * 2 * Nc;
+        float *myred = red + (warp - kRsEpi0) * g.red_stride;
+        // Work split between the kRsEpiW warps of a tensor-memory lane quarter over the (row, 16-column chunk) items of a tile:
+        // if the chunks of an accumulator slot divide evenly they split the CHUNKS (each warp takes every row), else the rows.
+        // A warp that owns ONE chunk (Nc = 32, most layers) keeps its statistics in registers for the whole strip; otherwise
+        // the partial sums are flushed per tile and chunk.
+        const int nck = Nc >> 4;
+        const bool by_chunk = nck % kRsEpiW == 0;
+        const bool persist = by_chunk ? nck == kRsEpiW : nck == 1;
+        const int cb0 = by_chunk ? 16 * sub : 0, cbstep = by_chunk ? 16 * kRsEpiW : 16;
+        const int r0 = by_chunk ? 0 : sub, rstep = by_chunk ? 1 : kRsEpiW;
         int prev_b = -1, k = 0, xo = 2 % L, ntr = 0;  // xo: ring position of the next output row to drain
         const bool tracer = warp == kRsEpi0 && lane == 0;
-        int b_first = 0, b_last = -1;
-        if (a.fuse.on) {
-            // ------------------------------------------------ fused operand preparation (see RsFuse)
-            const RsFuse &fz = a.fuse;
-            float *aff = reinterpret_cast<float *>(smem + g.off_aff);  // scale[kRsAffCh], shift[kRsAffCh]
-            rs_sample_range(a, b_first, b_last);
-            const int chA = fz.u0 * 16, nA = fz.nlate * 16;  // channels of the private units (the last ones may lie past cin: zero)
-            const int scratch_cap = 64 * Nc;
-            if (tracer) rs_trace(a.trace, 2, ntr, 50);
-            rs_prefetch_w(fz.w, fz.cin, fz.cout_pad, chA, fz.cin - chA, et, kRsEpiThreads);
-            const int nchl = fz.cin - fz.c0;  // channels of the late group
-            for (int j = 0; j < fz.njob; ++j) rs_prefetch_w(fz.job[j].w, fz.job[j].cin, fz.job[j].cout_pad, fz.c0, nchl, et, kRsEpiThreads);
-            for (int bb = b_first; bb <= b_last; ++bb) {
-                const int slot = bb - b_first;
-                for (int i = et; i < nA; i += kRsEpiThreads) {
-                    float2 af = make_float2(0.f, 0.f);
-                    if (chA + i < fz.cin) af = rs_fuse_affine(fz, bb, chA + i);
-                    aff[i] = af.x;
-                    aff[kRsAffCh + i] = af.y;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-                if (tracer) rs_trace(a.trace, 2, ntr, 60);
-                __nv_bfloat16 *dstp = fz.priv + ((size_t)blockIdx.x * fz.nslot + slot) * fz.nlate * (size_t)(g.w_unit / 2);
-                rs_build_halves(fz.w, fz.cin, a.cout, fz.cout_pad, Nc, g.nsp, chA, 2 * fz.nlate, aff, dstp, et, kRsEpiThreads);
-                if (tracer) rs_trace(a.trace, 2, ntr, 61);
-                // the producer's bulk copies (async proxy) read what these generic-proxy stores wrote
-                asm volatile("fence.proxy.async;" ::: "memory");
-                mbar_arrive(bar_late + 8 * slot);
-                if (tracer) rs_trace(a.trace, 2, ntr, 63);
-                // the MMAs of this sample can start; its border-bias sums are needed by the first epilogue only
-                rs_build_bias(fz.w, fz.cin, a.cout, fz.cout_pad, Nc, fz.c0, nchl, aff + kRsAffCh + (fz.c0 - chA), btab_s, scratch_cap,
-                              fz.priv_bias + ((size_t)blockIdx.x * fz.nslot + slot) * 9 * Nc, et);
-                if (tracer) rs_trace(a.trace, 2, ntr, 62);
-            }
-            if (tracer) rs_trace(a.trace, 2, ntr, 51);
-            // (ii) the late group's slices for the later convs of the block: one item per WARP (no CTA barriers): an
-            // 8-channel half of a consumer's image, or one tap of its border-bias partial sums
-            {
-                const int nh = (nchl + 7) >> 3, pieces = nh + 9;
-                const int total = fz.njob * a.B * pieces;
-                const int ew = warp - kRsEpi0;
-                for (int it = blockIdx.x * 8 + ew; it < total; it += gridDim.x * 8) {
-                    const int piece = it % pieces;
-                    const int r = it / pieces;
-                    const int bb = r % a.B;
-                    const RsJob &J = fz.job[r / a.B];
-                    if (piece < nh) {
-                        const int ch0 = fz.c0 + 8 * piece;
-                        float mine = 0.f;
-                        if (lane < 8 && ch0 + lane < fz.cin) mine = rs_fuse_affine(fz, bb, ch0 + lane).x;
-                        float sc8[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) sc8[e] = __shfl_sync(0xffffffffu, mine, e);
-                        const size_t junit = (size_t)3 * g.nsp * 2 * 3 * J.Nc * 8;  // elements of one unit of the consumer's image
-                        rs_build_halves(J.w, J.cin, J.cout, J.cout_pad, J.Nc, g.nsp, ch0, 1, sc8, J.wimg + ((size_t)bb * J.nunit + (ch0 >> 4)) * junit, lane,
-                                        32);
-                    } else {
-                        float sh[5];
-#pragma unroll
-                        for (int q = 0; q < 5; ++q) {
-                            const int ci = q * 32 + lane;
-                            sh[q] = ci < nchl ? rs_fuse_affine(fz, bb, fz.c0 + ci).y : 0.f;
-                        }
-                        const int k = piece - nh;
-                        rs_warp_bias_tap(J.w, J.cin, J.cout, J.cout_pad, J.Nc, fz.c0, nchl, k, sh,
-                                         J.btab + (((size_t)bb * J.ngroup + J.gidx) * 9 + k) * J.Nc, lane);
-                    }
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-            }
-            if (tracer) rs_trace(a.trace, 2, ntr, 52);
-        }
         RsWalk w = rs_walk(a);
         while (w.next()) {
             const int b = w.b;
-            if (b != prev_b) {
+            const int cbase = w.ch * Nc;  // first output channel of this chunk
+            if (w.ch * a.B + b != prev_b) {
                 // border-bias table of this sample: add the channel splits of the prep kernel's partial sums, then
                 // expand to the 64 (frame-mask, bin-mask) classes
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-                float *wb = red + 16 * Nc;  // [9][Nc]
-                const float *src = a.btab + (size_t)b * a.nsplit * 9 * Nc;
-                const float *late = a.fuse.on ? a.fuse.priv_bias + ((size_t)blockIdx.x * a.fuse.nslot + (b - b_first)) * 9 * Nc : nullptr;
+                float *wb = red + kRsEpiWarps * g.red_stride;  // [9][Nc]
+                const float *src = a.btab + (size_t)w.ch * a.btab_cstride + (size_t)b * a.nsplit * 9 * Nc;
                 for (int i = et; i < 9 * Nc; i += kRsEpiThreads) {
                     float v = 0.f;
                     for (int sp = 0; sp < a.nsplit; ++sp) v += __ldg(src + (size_t)sp * 9 * Nc + i);
-                    if (late) v += late[i];  // written by this CTA a moment ago: plain load
                     wb[i] = v;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
                 for (int i = et; i < 64 * Nc; i += kRsEpiThreads) {
                     const int mk = i / Nc, n = i - mk * Nc;
                     const int tm = mk >> 3, fm = mk & 7;
-                    float v = (a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.f;
+                    float v = (a.bias && cbase + n < a.cout) ? __ldg(a.bias + cbase + n) : 0.f;
                     for (int kt = 0; kt < 3; ++kt)
                         for (int kf = 0; kf < 3; ++kf)
                             if (((tm >> kt) & 1) && ((fm >> kf) & 1)) v += wb[(kt * 3 + kf) * Nc + n];
                     btab_s[i] = v;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-                prev_b = b;
+                prev_b = w.ch * a.B + b;
             }
             const int seg = g.S > 1 ? (quad * 32 + lane) / g.Wr : 0;  // packed mode: which strip this lane belongs to
             const int jg = g.S > 1 ? (quad * 32 + lane) - seg * g.Wr : 128 * w.m + quad * 32 + lane;  // grid bin of this lane
@@ -679,6 +449,22 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             for (int i = 0; i < 3; ++i)
                 if (i < g.nkf && jg + g.tboff[i] >= 0 && jg + g.tboff[i] < g.Fin) fmask |= 1 << g.twk[i];
             __nv_bfloat16 *out_pl = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * npix;
+            const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+            float ssum[16], ssq[16];  // statistics of the chunk in flight
+#pragma unroll
+            for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
+            // this warp's partial sums of one chunk -> its slot of the strip's reduction buffer (fixed order, no atomics)
+            auto flush = [&](int cb) {
+                const float s = warp_reduce16(ssum, lane);
+                const float q2 = warp_reduce16(ssq, lane);
+                const int slot = (persist ? 0 : cb) + (lane >> 1);  // a persistent warp's buffer holds its own chunk only
+                if ((lane & 1) == 0) {
+                    myred[slot * 2] += s;
+                    myred[slot * 2 + 1] += q2;
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
+            };
             RsTiles tl;
             tl.init(a, w);
             for (; tl.next(); ++k) {
@@ -688,70 +474,80 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 mbar_wait(bar_tfull + 8 * (k & 1), (k >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tracer) rs_trace(a.trace, 2, ntr, 2);
-                for (int cb = 0; cb < Nc; cb += 16) {
-                    float ssum[16], ssq[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) ssum[q] = ssq[q] = 0.f;
-                    for (int o = o_lo + half; o < o_hi; o += 2) {
-                        const int t = tseg + w.t0 + o;
-                        const bool valid = fvalid && (last_seg || w.t0 + o < g.DS);  // frames a strip shares with the next one belong to that one
-                        const int tmask = 7 & ~(t == 0 ? 1 : 0) & ~(t == a.T - 1 ? 4 : 0);
+                for (int cb = cb0; cb < Nc; cb += cbstep) {
+                    auto slot_addr = [&](int o) {
                         int x = xo + o - o_lo;
                         if (x >= L) x -= L;
-                        const float *bt = btab_s + (tmask * 8 + fmask) * Nc + cb;
-                        uint32_t v[16], v2[16];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(x * Nc + cb);
-                        tmem_ld16(taddr, v);
-                        if (x < 2) tmem_ld16(taddr + (uint32_t)(L * Nc), v2);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        tmem_zero16(taddr);  // hand the slot back cleared: every MMA accumulates
-                        if (x < 2) tmem_zero16(taddr + (uint32_t)(L * Nc));
+                        return tlane + (uint32_t)(x * Nc + cb);
+                    };
+                    // one row of the chunk: v = the 16 accumulator columns of this lane's bin, already loaded
+                    auto item = [&](uint32_t (&v)[16], int o) {
+                        const int t = tseg + w.t0 + o;
+                        const bool valid = fvalid && (last_seg || w.t0 + o < g.DS);  // frames a strip shares with the next one belong to that one
+                        int x = xo + o - o_lo;
+                        if (x >= L) x -= L;
+                        const uint32_t taddr = tlane + (uint32_t)(x * Nc + cb);
                         float y[16];
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int q = 0; q < 16; ++q) y[q] = __uint_as_float(v[q]);
-                        if (x < 2) {
+                        if (x < 2) {  // the ring's extension slots hold the rest of rows 0 and 1
+                            uint32_t v2[16];
+                            tmem_ld16(taddr + (uint32_t)(L * Nc), v2);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            tmem_zero16(taddr + (uint32_t)(L * Nc));
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) y[q] += __uint_as_float(v2[q]);
+                            for (int q = 0; q < 16; q += 2) add2(y[q], y[q + 1], y[q], y[q + 1], __uint_as_float(v2[q]), __uint_as_float(v2[q + 1]));
                         }
+                        tmem_zero16(taddr);  // hand the slot back cleared: every MMA accumulates
+                        {   // border bias of this (frame, bin) class: the taps that read outside the tensor drop out
+                            const int tmask = 7 & ~(t == 0 ? 1 : 0) & ~(t == a.T - 1 ? 4 : 0);
+                            const float *bt = btab_s + (tmask * 8 + fmask) * Nc + cb;
 #pragma unroll
-                        for (int q = 0; q < 16; q += 4) {
-                            const float4 bb = *reinterpret_cast<const float4 *>(bt + q);
-                            y[q] += bb.x;
-                            y[q + 1] += bb.y;
-                            y[q + 2] += bb.z;
-                            y[q + 3] += bb.w;
+                            for (int q = 0; q < 16; q += 4) {
+                                const float4 bb = *reinterpret_cast<const float4 *>(bt + q);
+                                add2(y[q], y[q + 1], y[q], y[q + 1], bb.x, bb.y);
+                                add2(y[q + 2], y[q + 3], y[q + 2], y[q + 3], bb.z, bb.w);
+                            }
                         }
-                        if (a.elu) {
+                        if (o + rstep < o_hi) tmem_ld16(slot_addr(o + rstep), v);
+                        if (a.elu) {  // ELU(y) = max(y, exp(min(y, 0)) - 1), branch-free
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) y[q] = rs_elu(y[q]);
+                            for (int q = 0; q < 16; q += 2) {
+                                float e0, e1;
+                                mul2(e0, e1, fminf(y[q], 0.f), fminf(y[q + 1], 0.f), 1.4426950408889634f, 1.4426950408889634f);
+                                add2(e0, e1, ex2_ftz(e0), ex2_ftz(e1), -1.f, -1.f);
+                                y[q] = fmaxf(y[q], e0);
+                                y[q + 1] = fmaxf(y[q + 1], e1);
+                            }
                         }
                         if (valid) {
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) {
-                                ssum[q] += y[q];
-                                ssq[q] = fmaf(y[q], y[q], ssq[q]);
+                            for (int q = 0; q < 16; q += 2) {
+                                add2(ssum[q], ssum[q + 1], ssum[q], ssum[q + 1], y[q], y[q + 1]);
+                                fma2(ssq[q], ssq[q + 1], y[q], y[q + 1], y[q], y[q + 1], ssq[q], ssq[q + 1]);
                             }
                             const int pix = t * g.Fout + f;
                             if (a.out_cl) {
                                 // data gradient: accumulate into the fp32 channels-last gradient of the conv's input
-                                float *o = reinterpret_cast<float *>(a.out) + ((size_t)b * npix + pix) * a.out_ctot + a.out_coff + cb;
+                                float *o4 = reinterpret_cast<float *>(a.out) + ((size_t)b * npix + pix) * a.out_ctot + a.out_coff + cbase + cb;
 #pragma unroll
                                 for (int q = 0; q < 16; q += 4) {
-                                    if (cb + q < a.cout) {
-                                        float4 old = a.out_cl == 1 ? *reinterpret_cast<float4 *>(o + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (cbase + cb + q < a.cout) {
+                                        float4 old = a.out_cl == 1 ? *reinterpret_cast<float4 *>(o4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                                         old.x += y[q];
                                         old.y += y[q + 1];
                                         old.z += y[q + 2];
                                         old.w += y[q + 3];
-                                        *reinterpret_cast<float4 *>(o + q) = old;
+                                        *reinterpret_cast<float4 *>(o4 + q) = old;
                                     }
                                 }
                             } else
 #pragma unroll
                             for (int g8 = 0; g8 < 16; g8 += 8) {
                                 const int co = cb + g8;
-                                if (co < a.cout) {
-                                    const int ca = a.out_coff + co;
+                                if (cbase + co < a.cout) {
+                                    const int ca = a.out_coff + cbase + co;
                                     __nv_bfloat16 *p = out_pl + ((size_t)(ca >> 3) * npix + pix) * 8;
                                     uint32_t hp[4];
 #pragma unroll
@@ -760,23 +556,25 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                     if (a.use_lo) {
                                         uint32_t lp[4];
 #pragma unroll
-                                        for (int q = 0; q < 4; ++q)
-                                            lp[q] = pack_bf16x2(y[g8 + 2 * q] - bf16_lo(hp[q]), y[g8 + 2 * q + 1] - bf16_hi(hp[q]));
+                                        for (int q = 0; q < 4; ++q) {
+                                            float l0, l1;
+                                            fma2(l0, l1, bf16_lo(hp[q]), bf16_hi(hp[q]), -1.f, -1.f, y[g8 + 2 * q], y[g8 + 2 * q + 1]);
+                                            lp[q] = pack_bf16x2(l0, l1);
+                                        }
                                         *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(p) + a.out_lo_off) =
                                             make_uint4(lp[0], lp[1], lp[2], lp[3]);
                                     }
                                 }
                             }
                         }
-                    }
-                    if (a.out_sums) {  // this warp's own slot, accumulated over the strip: no atomics, fixed order
-                        const float s = warp_reduce16(ssum, lane);
-                        const float q2 = warp_reduce16(ssq, lane);
-                        if ((lane & 1) == 0) {
-                            myred[(cb + (lane >> 1)) * 2] += s;
-                            myred[(cb + (lane >> 1)) * 2 + 1] += q2;
-                        }
-                    }
+                    };
+                    // rows of the tile: the accumulator load of the next row is issued as soon as this row's values have left
+                    // the load registers, and is in flight while this row is processed
+                    uint32_t v[16];
+                    int o = o_lo + r0;
+                    if (o < o_hi) tmem_ld16(slot_addr(o), v);
+                    for (; o < o_hi; o += rstep) item(v, o);
+                    if (!persist && a.out_sums) flush(cb);
                 }
                 // this warp is done with the tile's slots: hand them back to the MMA issuer
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -787,21 +585,25 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 xo += max(0, o_hi - o_lo);
                 if (xo >= L) xo -= L;
             }
+            if (persist && a.out_sums) flush(cb0);
             if (a.out_sums) {  // strip statistics -> global fixed-point accumulators
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-                if (et < Nc && et < a.cout) {
-                    double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + et) * 2;
+                if (et < Nc && cbase + et < a.cout) {
+                    double *dst = a.out_sums + ((size_t)b * a.out_ctot + a.out_coff + cbase + et) * 2;
                     double s8 = 0.0, q8 = 0.0;
-#pragma unroll
-                    for (int w8 = 0; w8 < 8; ++w8) {
-                        s8 += (double)red[w8 * 2 * Nc + et * 2];
-                        q8 += (double)red[w8 * 2 * Nc + et * 2 + 1];
+                    const int myck = et >> 4, slot = persist ? (et & 15) : et;
+                    for (int w8 = 0; w8 < kRsEpiWarps; ++w8) {  // the warps that own this channel's chunk, in a fixed order
+                        const bool owns = !by_chunk || (w8 >> 2) == myck % kRsEpiW;
+                        if (owns) {
+                            s8 += (double)red[w8 * g.red_stride + slot * 2];
+                            q8 += (double)red[w8 * g.red_stride + slot * 2 + 1];
+                        }
                     }
                     stat_add(dst, s8);
                     stat_add(dst + 1, q8);
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
-                for (int i = et; i < 8 * 2 * Nc; i += kRsEpiThreads) red[i] = 0.f;
+                for (int i = et; i < kRsEpiWarps * g.red_stride; i += kRsEpiThreads) red[i] = 0.f;
             }
             xo += 2;  // the two slots between strips stay unused
             if (xo >= L) xo -= L;
@@ -829,10 +631,18 @@ __device__ __forceinline__ float2 rs_affine(const RsPrepArgs &p, int b, int ci) 
     return make_float2(1.f, 0.f);
 }
 
-__global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
+__global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs pa) {
     extern __shared__ float sh[];
     pdl_trigger();
     pdl_wait();  // the statistics come from the previous conv, which also still reads the scratch this kernel rewrites
+    RsPrepArgs p = pa;
+    {   // this block's output-channel chunk: a column window of the packed weights
+        const int c0 = blockIdx.y * p.Nc;
+        p.w += c0;
+        p.cout = min(p.Nc, p.cout - c0);
+        p.wimg += (size_t)blockIdx.y * p.wimg_cstride;
+        p.btab += (size_t)blockIdx.y * p.btab_cstride;
+    }
     const int nimg = p.B * p.nunit;
     const int N3 = 3 * p.Nc;
     if ((int)blockIdx.x < nimg) {
@@ -904,51 +714,6 @@ __global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs p) {
     }
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// Slices of one channel group (channels [c0, c0 + nch) of the block buffer, just produced) for the later convs of the
-// DenseBlock.  Block = (job, sample, piece): piece < nh builds one 8-channel half of the consumer's weight image, piece ==
-// nh the group's border-bias partial sums (one output per thread, fixed order).  Tiny shared-memory footprint and 256
-// threads so that the blocks fit on the SMs next to the resident conv_rs CTA.
-__global__ void __launch_bounds__(256) rs_group_prep_kernel(const RsGroupPrep p) {
-    __shared__ float sc[kRsAffCh];
-    const int nh = (p.nch + 7) >> 3, pieces = nh + 1;
-    const int piece = blockIdx.x % pieces;
-    const int r = blockIdx.x / pieces;
-    const int b = r % p.B;
-    const RsJob &J = p.job[r / p.B];
-    if (piece < nh) {
-        const int ch0 = p.c0 + 8 * piece;
-        if (threadIdx.x < 8) {
-            float v = 0.f;
-            if (8 * piece + (int)threadIdx.x < p.nch) {
-                const double *sp = p.in_sums + ((size_t)b * p.in_ctot + ch0 + threadIdx.x) * 2;
-                v = affine_from_sums(stat_get(sp), stat_get(sp + 1), p.inv_n, (double)p.eps).x;
-            }
-            sc[threadIdx.x] = v;
-        }
-        __syncthreads();
-        const size_t junit = (size_t)3 * p.nsp * 2 * 3 * J.Nc * 8;
-        rs_build_halves(J.w, J.cin, J.cout, J.cout_pad, J.Nc, p.nsp, ch0, 1, sc, J.wimg + ((size_t)b * J.nunit + (ch0 >> 4)) * junit, threadIdx.x, 256);
-    } else {
-        for (int i = threadIdx.x; i < p.nch; i += 256) {
-            const double *sp = p.in_sums + ((size_t)b * p.in_ctot + p.c0 + i) * 2;
-            sc[i] = affine_from_sums(stat_get(sp), stat_get(sp + 1), p.inv_n, (double)p.eps).y;
-        }
-        __syncthreads();
-        float *dst = J.btab + ((size_t)b * J.ngroup + J.gidx) * 9 * J.Nc;
-        for (int o = threadIdx.x; o < 9 * J.Nc; o += 256) {
-            const int k = o / J.Nc, n = o - k * J.Nc;
-            float acc = 0.f;
-            if (n < J.cout) {
-                const float *wp = J.w + ((size_t)k * J.cin + p.c0) * J.cout_pad + n;
-#pragma unroll 8
-                for (int ci = 0; ci < p.nch; ++ci) acc = fmaf(__ldg(wp + (size_t)ci * J.cout_pad), sc[ci], acc);
-            }
-            dst[o] = acc;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*RsEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -1038,9 +803,15 @@ bool make_rs_geom(const ConvArgs &a, int split, int kind, RsGeom &g) {
     g = RsGeom{};
     if (!rs_shape_ok(a, kind)) return false;
     g.nsp = split == 3 ? 2 : 1;
-    g.Nc = rs_round_up(a.cout, 16);
     static const int max_nc = getenv("MISO_RS_MAXNC") ? atoi(getenv("MISO_RS_MAXNC")) : 64;
+    g.Nc = rs_round_up(std::min(a.cout, max_nc), 16);
     if (g.Nc > max_nc) return false;
+    if (a.cout > g.Nc) {
+        // more output channels than one accumulator slot holds: chunks of Nc channels walked by ONE launch (plane outputs of
+        // the plain DenseBlock variant only)
+        static const bool chunks_ok = getenv("MISO_RS_CHUNKS") && atoi(getenv("MISO_RS_CHUNKS")) != 0;  // host side not wired yet
+        if (!chunks_ok || kind != RS_DENSE || a.out_layout != LAYOUT_PLANES || g.Nc % 8) return false;
+    }
     g.N3 = 3 * g.Nc;
     g.Fin = a.Fin;
     g.Fout = a.Fout;
@@ -1115,8 +886,12 @@ bool make_rs_geom(const ConvArgs &a, int split, int kind, RsGeom &g) {
     g.L = std::min(512 / g.Nc - 2, 30);
     g.off_btab = kRsFixed;
     g.off_red = g.off_btab + 64 * g.Nc * 4;
-    g.off_aff = g.off_red + (16 + 9) * g.Nc * 4;                     // fused mode: (scale, shift) of up to kRsAffCh channels
-    g.off_stage = rs_round_up(g.off_aff + 2 * kRsAffCh * 4, 1024);
+    {
+        const int nck = g.Nc / 16;
+        const bool persist = nck % kRsEpiW == 0 ? nck == kRsEpiW : nck == 1;
+        g.red_stride = persist ? 32 : 2 * g.Nc;
+    }
+    g.off_stage = rs_round_up(g.off_red + (kRsEpiWarps * g.red_stride + 9 * g.Nc) * 4, 1024);
     static const int g_env = getenv("MISO_RS_G") ? atoi(getenv("MISO_RS_G")) : 0;
     for (int G = std::min({(g.L - 2) / 2, kRsMaxG, g_env > 0 ? g_env : kRsMaxG}); G >= 1; --G) {
         for (int kper : {2, 1}) {
@@ -1240,15 +1015,7 @@ void conv_rs_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size
 namespace {
 long long rs_rows(const ConvArgs &a, const RsGeom &g) { return (long long)a.B * g.Mr * (g.S > 1 ? g.TS : a.T); }
 unsigned rs_grid(const ConvArgs &a, const RsGeom &g) { return (unsigned)std::min<long long>(148, std::max<long long>(1, rs_rows(a, g) / 2)); }
-// samples the row range of one CTA can touch
-int rs_slots(const ConvArgs &a, const RsGeom &g) {
-    const long long R = rs_rows(a, g), per = g.Mr * (long long)(g.S > 1 ? g.TS : a.T);
-    const long long len = (R + rs_grid(a, g) - 1) / rs_grid(a, g);
-    return (int)((len + per - 2) / per + 1);
-}
-
-int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16 *wimg, const float *btab, int nsplit, const RsFuse &fuse,
-              cudaStream_t stream) {
+int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16 *wimg, const float *btab, int nsplit, cudaStream_t stream) {
     CUtensorMap tm_hi, tm_lo;
     int rc = rs_encode_maps(a, g, &tm_hi, &tm_lo);
     if (rc) return rc;
@@ -1270,12 +1037,12 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
     k.out_ctot = a.out_ctot;
     k.out_coff = a.out_coff;
     k.cout = a.cout;
+    k.nch = (a.cout + g.Nc - 1) / g.Nc;
     k.out_lo_off = a.out_lo_off;
     k.use_lo = a.use_lo;
     k.elu = a.elu;
     k.out_cl = a.out_layout == LAYOUT_CL_F32 ? (a.resid ? 1 : 2) : 0;
     k.trace = (g_rs_trace && a.cin == g_rs_trace_cin && a.Fin == g_rs_trace_fin) ? g_rs_trace : nullptr;
-    k.fuse = fuse;
     dim3 grid(rs_grid(a, g), 1, 1);
     prof_begin(stream);
     if (split == 3)
@@ -1337,7 +1104,6 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_rs_prep_kernel, dim3(a.B * g.nunit + a.B * nsplit), dim3(256), prep_smem, stream, p));
     prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_rs_prep_kernel");
-    RsFuse none{};
     static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
     for (int i = 0; i < nkind; ++i) {  // one launch per phase, all over the same weight image / bias sums
         MISO_REQUIRE(make_rs_geom(a, split, kinds[i], g), "conv_rs: geometry of variant %d", kinds[i]);
@@ -1345,118 +1111,9 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
             fprintf(stderr, "conv_rs: kind %d cin=%d cout=%d Fin=%d Fout=%d | Wg=%d S=%d Wr=%d Nc=%d L=%d G=%d Mr=%d pitch=%d map5d=%d kper=%d nchunk=%d nstage=%d stage=%dB tmem=%d smem=%d\n",
                     kinds[i], a.cin, a.cout, a.Fin, a.Fout, g.Wg, g.S, g.Wr, g.Nc, g.L, g.G, g.Mr, g.pitch, g.map5d, g.kper, g.nchunk, g.nstage, g.stage,
                     g.tmem_cols, g.smem_total);
-        rc = rs_launch(a, split, g, p.wimg, p.btab, nsplit, none, stream);
+        rc = rs_launch(a, split, g, p.wimg, p.btab, nsplit, stream);
         if (rc) return rc;
     }
-    return MISO_OK;
-}
-
-// ---- fused mode (forward DenseBlock convs): sizes of the per-layer persistent buffers and the launch
-bool conv_rs_dense_need(const ConvArgs &a, int split, int c0, RsDenseNeed *need) {
-    // Off by default: measured on B200 (profiles/r2_fused_prep_*.log) the in-kernel preparation costs more than the
-    // launch it removes -- 148 CTAs re-read the same cold weight lines (9x the L2 traffic of the per-sample prep kernel)
-    // and run once-per-launch code at instruction-cache-miss speed: 11.3-11.7 ms per bench step against 10.9-11.1.
-    static const bool on = getenv("MISO_RS_FUSE") && atoi(getenv("MISO_RS_FUSE")) != 0;
-    RsGeom g;
-    int kinds[2];
-    if (!on || rs_kinds(a, kinds) != 1 || kinds[0] != RS_DENSE || !conv_rs_eligible(a, split) || !make_rs_geom(a, split, g)) return false;
-    if (a.norm_mode != NORM_IN || c0 % 8 || c0 < 0 || c0 >= a.cin) return false;
-    const int u0 = c0 / 16, nlate = g.nunit - u0;
-    if (nlate * 16 > kRsAffCh || a.cin - c0 > kRsAffCh) return false;
-    const int nslot = rs_slots(a, g);
-    if (nslot > kRsMaxSlots) return false;
-    if (need) {
-        need->wimg = align_up((size_t)a.B * g.nunit * g.w_unit, 256);
-        need->btab_per_group = (size_t)a.B * 9 * g.Nc * sizeof(float);
-        need->priv = align_up((size_t)rs_grid(a, g) * nslot * nlate * g.w_unit, 256) + align_up((size_t)rs_grid(a, g) * nslot * 9 * g.Nc * sizeof(float), 256);
-    }
-    return true;
-}
-
-int launch_conv_rs_dense(const ConvArgs &a, int split, const RsDense &d, cudaStream_t stream) {
-    RsGeom g;
-    RsDenseNeed need;
-    MISO_REQUIRE(make_rs_geom(a, split, g) && conv_rs_dense_need(a, split, d.c0, &need), "conv_rs: layer does not fit the fused row-streaming path (cin=%d cout=%d F=%d c0=%d)",
-                 a.cin, a.cout, a.Fin, d.c0);
-    RsFuse f{};
-    f.on = 1;
-    f.c0 = d.c0;
-    f.u0 = d.c0 / 16;
-    f.nlate = g.nunit - f.u0;
-    f.nslot = rs_slots(a, g);
-    const unsigned grid = rs_grid(a, g);
-    f.priv = reinterpret_cast<__nv_bfloat16 *>(d.priv);
-    f.priv_bias = reinterpret_cast<float *>(reinterpret_cast<char *>(d.priv) + align_up((size_t)grid * f.nslot * f.nlate * g.w_unit, 256));
-    f.w = a.w;
-    f.in_sums = a.in_sums + (size_t)a.in_coff * 2;
-    f.in_ctot = a.in_ctot;
-    f.cin = a.cin;
-    f.cout_pad = a.cout_pad;
-    f.inv_n = a.norm_inv_n;
-    f.eps = a.norm_eps;
-    MISO_REQUIRE(d.njob <= kRsMaxJobs, "conv_rs: too many jobs");
-    f.njob = conv_rs_jobs_in_kernel() ? d.njob : 0;
-    for (int j = 0; j < f.njob; ++j) {
-        const RsDenseJob &sj = d.job[j];
-        RsJob &t = f.job[j];
-        t.w = sj.w;
-        t.wimg = reinterpret_cast<__nv_bfloat16 *>(sj.wimg);
-        t.btab = sj.btab;
-        t.cin = sj.cin;
-        t.cout = sj.cout;
-        t.cout_pad = sj.cout_pad;
-        t.Nc = rs_round_up(sj.cout, 16);
-        t.nunit = ((sj.cin + 7) / 8 + 1) / 2;
-        t.ngroup = sj.ngroup;
-        t.gidx = sj.gidx;
-    }
-    static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;
-    if (debug)
-        fprintf(stderr, "conv_rs fused: cin=%d cout=%d F=%d c0=%d | u0=%d nlate=%d nslot=%d njob=%d early groups=%d G=%d nstage=%d smem=%d\n", a.cin, a.cout,
-                a.Fin, d.c0, f.u0, f.nlate, f.nslot, d.njob, d.ngroup_early, g.G, g.nstage, g.smem_total);
-    return rs_launch(a, split, g, reinterpret_cast<const __nv_bfloat16 *>(d.wimg), d.btab, d.ngroup_early, f, stream);
-}
-
-bool conv_rs_jobs_in_kernel() {
-    static const bool sep = getenv("MISO_RS_GROUPKERNEL") && atoi(getenv("MISO_RS_GROUPKERNEL")) != 0;
-    return !sep;
-}
-
-// the late group's slices for the later convs of the block (d.job) as a launch of their own (MISO_RS_GROUPKERNEL=1)
-int launch_rs_group_prep(const ConvArgs &a, int split, const RsDense &d, cudaStream_t stream) {
-    if (d.njob == 0 || conv_rs_jobs_in_kernel()) return MISO_OK;
-    MISO_REQUIRE(d.njob <= kRsMaxJobs, "conv_rs: too many jobs");
-    RsGroupPrep p{};
-    p.in_sums = a.in_sums + (size_t)a.in_coff * 2;
-    p.in_ctot = a.in_ctot;
-    p.c0 = d.c0;
-    p.nch = a.cin - d.c0;
-    MISO_REQUIRE(p.nch > 0 && p.nch <= kRsAffCh, "conv_rs: group of %d channels", p.nch);
-    p.B = a.B;
-    p.nsp = split == 3 ? 2 : 1;
-    p.inv_n = a.norm_inv_n;
-    p.eps = a.norm_eps;
-    p.njob = d.njob;
-    double bytes = 0.0;
-    for (int j = 0; j < d.njob; ++j) {
-        const RsDenseJob &s = d.job[j];
-        RsJob &t = p.job[j];
-        t.w = s.w;
-        t.wimg = reinterpret_cast<__nv_bfloat16 *>(s.wimg);
-        t.btab = s.btab;
-        t.cin = s.cin;
-        t.cout = s.cout;
-        t.cout_pad = s.cout_pad;
-        t.Nc = rs_round_up(s.cout, 16);
-        t.nunit = ((s.cin + 7) / 8 + 1) / 2;
-        t.ngroup = s.ngroup;
-        t.gidx = s.gidx;
-        bytes += (double)a.B * ((double)p.nch * 9 * 3 * t.Nc * 2 * p.nsp + 9.0 * t.Nc * 4);
-    }
-    const int pieces = (p.nch + 7) / 8 + 1;
-    rs_group_prep_kernel<<<d.njob * a.B * pieces, 256, 0, stream>>>(p);
-    (void)bytes;
-    MISO_LAUNCHED("rs_group_prep_kernel");
     return MISO_OK;
 }
 

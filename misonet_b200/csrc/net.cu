@@ -366,9 +366,6 @@ struct miso_net {
     std::vector<TrainGraph> tgraphs;
     cudaStream_t cap_stream = nullptr;
     int use_graph = 1;
-    // forked branch of the forward: the DenseBlock group-preparation launches run next to the conv kernels (Walker::dense)
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // gradient buckets of the backward pass, in the order in which they complete (decoders top-down, TCN, encoders): an
     // event per bucket lets the caller start that bucket's all-reduce while the rest of the backward is still running
     cudaEvent_t bucket_ev[8] = {};
@@ -481,8 +478,6 @@ struct Plan {
     double *stats_base = nullptr;
     size_t stats_bytes = 0;
     TcScratch scratch{};
-    char *dense = nullptr;  // fused DenseBlock convs: per-layer persistent weight images / border-bias sums, then the private scratch
-    size_t dense_bytes = 0, dense_priv = 0;
     size_t total = 0;
 };
 
@@ -634,7 +629,7 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
 }
 
 // tensor-core scratch (per-sample weight images, border-bias tables) goes after the activations
-void plan_scratch(Plan &pl, char *base, size_t need_w, size_t need_b, size_t need_d, size_t need_p) {
+void plan_scratch(Plan &pl, char *base, size_t need_w, size_t need_b) {
     size_t off = pl.total;
     pl.scratch.wimg = base ? base + off : nullptr;
     pl.scratch.wimg_bytes = need_w;
@@ -642,10 +637,6 @@ void plan_scratch(Plan &pl, char *base, size_t need_w, size_t need_b, size_t nee
     pl.scratch.btab = base ? reinterpret_cast<float *>(base + off) : nullptr;
     pl.scratch.btab_bytes = need_b;
     off += align_up(need_b, 256);
-    pl.dense = base ? base + off : nullptr;
-    pl.dense_bytes = align_up(need_d, 256);
-    pl.dense_priv = align_up(need_p, 256);
-    off += pl.dense_bytes + pl.dense_priv;
     pl.total = off;
 }
 
@@ -680,9 +671,6 @@ struct Walker {
     size_t need_w = 0, need_b = 0;
     std::vector<ConvRec> *record = nullptr;  // non-null: list the layers instead of launching them
 
-    size_t need_d = 0, need_p = 0, dense_off = 0;  // fused DenseBlock convs: persistent bytes (running offset) and private scratch (max)
-    cudaStream_t side = nullptr;                    // forked stream for the group-preparation launches (null: run them in line)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     ConvArgs make_args(const ConvDesc &cd, bool transposed, const BufDesc *inb, const void *in_raw, int in_ctot, int in_coff, int Fin,
                        const double *in_sums, const BufDesc *outb, float *out_raw, int out_ctot, int out_coff, int Fout, double *out_sums,
@@ -753,8 +741,6 @@ struct Walker {
 
     // The five convs of a DenseBlock (model.py:437-482) over the block buffer [x | y0 | y1 | y2 | y3]: conv k reads the first
     // c + (k - 1) g1 channels and writes g1 channels behind them; conv 5 writes its g2 channels to out5 at out5_coff.
-    // Tensor-core modes run them with the operand preparation fused into the kernels (conv_rs.cu, RsFuse) when the first
-    // four convs fit the row-streaming path: conv k then owns a persistent weight image / border-bias buffer in pl.dense.
     int dense(const std::vector<ConvDesc> &cds, const BufDesc &buf, int c, int g1, const BufDesc &out5, int out5_coff) {
         ConvArgs a[5];
         for (int k = 1; k <= 5; ++k) {
@@ -768,78 +754,8 @@ struct Walker {
         // block buffers are always consumed through their producer's InstanceNorm; a plan built without a base address
         // (size queries) has null statistics pointers and must still take the same decisions
         for (int k = 0; k < 5; ++k) a[k].norm_mode = NORM_IN;
-        const int split = n->mode == 2 ? 1 : 3;
-        bool fused[5];
-        RsDenseNeed need[5];
-        int c0[5];
-        bool all4 = !record;
         for (int k = 1; k <= 5; ++k) {
-            c0[k - 1] = k == 1 ? 0 : c + (k - 2) * g1;
-            // sized for the bf16x3 images (the plan does not depend on the mode); the launch re-checks the actual split
-            fused[k - 1] = !record && conv_rs_dense_need(a[k - 1], 3, c0[k - 1], &need[k - 1]) &&
-                           (split == 3 || conv_rs_dense_need(a[k - 1], split, c0[k - 1], nullptr));
-            if (k < 5 && !fused[k - 1]) all4 = false;
-        }
-        if (!all4)
-            for (int k = 0; k < 5; ++k) fused[k] = false;
-        char *wimg[5] = {};
-        float *btab[5] = {};
-        for (int k = 1; k <= 5; ++k) {
-            if (!fused[k - 1]) continue;
-            const size_t bt = align_up(need[k - 1].btab_per_group * (size_t)(k - 1), 256);
-            if (!dry) {
-                wimg[k - 1] = pl.dense + dense_off;
-                btab[k - 1] = reinterpret_cast<float *>(pl.dense + dense_off + need[k - 1].wimg);
-            }
-            dense_off += need[k - 1].wimg + bt;
-            need_d = std::max(need_d, dense_off);
-            need_p = std::max(need_p, need[k - 1].priv);
-        }
-        for (int k = 1; k <= 5; ++k) {
-            const BufDesc *outb = k < 5 ? &buf : &out5;
-            int rc;
-            if (fused[k - 1] && !dry && n->mode != 0) {
-                if (dense_off > pl.dense_bytes || need[k - 1].priv > pl.dense_priv) {
-                    set_error("dense block: fused-preparation buffers exceed the plan (%zu > %zu)", dense_off, pl.dense_bytes);
-                    return MISO_E_WORKSPACE;
-                }
-                RsDense d{};
-                d.c0 = c0[k - 1];
-                d.wimg = wimg[k - 1];
-                d.btab = btab[k - 1];
-                d.ngroup_early = k - 1;
-                d.priv = pl.dense + pl.dense_bytes;
-                d.njob = 0;
-                for (int j = k + 1; j <= 5; ++j) {
-                    if (!fused[j - 1]) continue;
-                    RsDenseJob &jb = d.job[d.njob++];
-                    jb.w = a[j - 1].w;
-                    jb.wimg = wimg[j - 1];
-                    jb.btab = btab[j - 1];
-                    jb.cin = a[j - 1].cin;
-                    jb.cout = a[j - 1].cout;
-                    jb.cout_pad = a[j - 1].cout_pad;
-                    jb.ngroup = j - 1;
-                    jb.gidx = k - 1;
-                }
-                // the group's slices for the later convs are needed one conv later: fork them off the conv's predecessor so
-                // that they run next to this conv, and join before the next one
-                const bool fork = d.njob > 0 && side != nullptr && !conv_rs_jobs_in_kernel();
-                if (fork) {
-                    MISO_CUDA(cudaEventRecord(ev_fork, st));
-                    MISO_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-                    rc = launch_rs_group_prep(a[k - 1], split, d, side);
-                    if (rc) return rc;
-                    MISO_CUDA(cudaEventRecord(ev_join, side));
-                } else if (d.njob > 0) {
-                    rc = launch_rs_group_prep(a[k - 1], split, d, st);
-                    if (rc) return rc;
-                }
-                rc = launch_conv_rs_dense(a[k - 1], split, d, st);
-                if (fork) MISO_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-            } else {
-                rc = dispatch(a[k - 1], cds[k - 1], &buf, outb);
-            }
+            const int rc = dispatch(a[k - 1], cds[k - 1], &buf, k < 5 ? &buf : &out5);
             if (rc) return rc;
         }
         return MISO_OK;
@@ -1047,13 +963,6 @@ bool capturing(cudaStream_t st) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
 }
-int ensure_side(miso_net *net) {
-    if (net->side_stream) return MISO_OK;
-    MISO_CUDA(cudaStreamCreateWithFlags(&net->side_stream, cudaStreamNonBlocking));
-    MISO_CUDA(cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
-    MISO_CUDA(cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming));
-    return MISO_OK;
-}
 
 // Data gradient of a recorded layer as a forward conv over dL/dy (bf16 hi/lo planes in pl.dyP) with the transposed
 // weights in pl.wT, accumulated into the input buffer's gradient (resid == out).  Every case maps onto a configuration
@@ -1200,7 +1109,7 @@ bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
             }
         }
     }
-    plan_scratch(pl, base, w.need_w, w.need_b, w.need_d, w.need_p);
+    plan_scratch(pl, base, w.need_w, w.need_b);
     return true;
 }
 
@@ -1302,9 +1211,6 @@ int miso_net_destroy(miso_net_t *net) {
     for (auto &g : net->tgraphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (net->cap_stream) cudaStreamDestroy(net->cap_stream);
-    if (net->side_stream) cudaStreamDestroy(net->side_stream);
-    if (net->ev_fork) cudaEventDestroy(net->ev_fork);
-    if (net->ev_join) cudaEventDestroy(net->ev_join);
     for (auto &e : net->bucket_ev)
         if (e) cudaEventDestroy(e);
     if (net->arena) cudaFree(net->arena);
@@ -1416,8 +1322,6 @@ int miso_net_forward(miso_net_t *net, const void *d_x, float *d_y, int B, int T,
         return MISO_E_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
-    rc = ensure_side(net);
-    if (rc) return rc;
     // Replay a captured graph when nothing baked into the kernel arguments changed.  With per-launch
     // profiling on (miso_prof_enable) the graph additionally carries event-record nodes around every conv.
     if (net->use_graph) {
@@ -1495,12 +1399,6 @@ int enqueue_forward(miso_net *net, const Plan &pl, const void *d_x, float *d_y, 
         MISO_LAUNCHED("sentinel_kernel");
     }
     Walker w{net, pl, B, T, F, st, false};
-    static const bool no_fork = getenv("MISO_RS_FORK") && atoi(getenv("MISO_RS_FORK")) == 0;
-    if (!no_fork && net->side_stream) {  // created by ensure_side() outside any stream capture
-        w.side = net->side_stream;
-        w.ev_fork = net->ev_fork;
-        w.ev_join = net->ev_join;
-    }
     return w.run(d_x, d_y);
 }
 }  // namespace
@@ -1601,6 +1499,43 @@ int param_grad_offsets(const miso_net *n, std::vector<int64_t> &off) {
     for (size_t i = 0; i < n->params.size(); ++i) off[i + 1] = off[i] + n->params[i].numel;
     return MISO_OK;
 }
+
+// MISO_BWD_PROF=1: CUDA-event timing of the backward's phases (eager launches; printed to stderr after every backward)
+struct BwdProf {
+    bool on = getenv("MISO_BWD_PROF") && atoi(getenv("MISO_BWD_PROF")) != 0;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> recs;
+    cudaEvent_t open = nullptr;
+    void begin(cudaStream_t st) {
+        if (!on) return;
+        cudaEventCreate(&open);
+        cudaEventRecord(open, st);
+    }
+    void end(cudaStream_t st, int phase) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        recs.push_back({phase, {open, e}});
+    }
+    void report() {
+        if (!on) return;
+        static const char *names[] = {"in_bwd (IN/ELU backward)", "wgrad", "dgrad", "tcn", "other"};
+        double tot[5] = {0, 0, 0, 0, 0};
+        for (auto &r : recs) {
+            cudaEventSynchronize(r.second.second);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.second.first, r.second.second);
+            tot[r.first] += ms;
+            cudaEventDestroy(r.second.first);
+            cudaEventDestroy(r.second.second);
+        }
+        recs.clear();
+        fprintf(stderr, "backward phases (ms):");
+        for (int i = 0; i < 5; ++i) fprintf(stderr, " %s %.2f |", names[i], tot[i]);
+        fprintf(stderr, "\n");
+    }
+};
+BwdProf g_bwd_prof;
 
 struct Backward {
     const miso_net *n;
@@ -1714,7 +1649,9 @@ struct Backward {
             set_error("backward: normalised layer without statistics");
             return MISO_E_STATE;
         }
+        g_bwd_prof.begin(st);
         rc = launch_in_bwd(ib, st);
+        g_bwd_prof.end(st, 0);
         if (rc) return rc;
         WgradArgs w{};
         w.x = f.in;
@@ -1748,9 +1685,13 @@ struct Backward {
             w.partial_bytes = pl.wgP_bytes;
             w.ones = pl.wg_ones;
         }
+        g_bwd_prof.begin(st);
         rc = launch_wgrad(w, st);
+        g_bwd_prof.end(st, 1);
         if (rc) return rc;
+        g_bwd_prof.begin(st);
         if (r.in_grad) rc = dgrad(f, n->params[r.cd->w].d, r.cd->cout_pad, og, r.in_grad, tc);
+        g_bwd_prof.end(st, 2);
         return rc;
     }
 
@@ -1991,8 +1932,6 @@ int miso_net_forward_train(miso_net_t *net, const void *d_x, float *d_y, int B, 
     }
     rc = conv_tc_init();
     if (rc) return rc;
-    rc = ensure_side(net);
-    if (rc) return rc;
     return train_graphed(net, 1, d_x, d_x, d_y, d_ws, B, T, F, as_stream(stream),
                          [&](cudaStream_t s) { return enqueue_forward(net, pl, d_x, d_y, B, T, F, s); });
 }
@@ -2025,13 +1964,16 @@ int miso_net_backward(miso_net_t *net, const void *d_x, float *d_gy, int B, int 
     if (rc) return rc;
     auto bucket_of = [&](const ConvRec &r) { return r.kind == 1 ? 2 : bucket_of_param(bt, r.cd->w); };
     for (int i = (int)recs.size() - 1; i >= 0; --i) {
+        if (recs[i].kind == 1) g_bwd_prof.begin(st);
         rc = recs[i].kind == 1 ? bw.tcn() : bw.conv_layer(recs[i], d_gy);
+        if (recs[i].kind == 1) g_bwd_prof.end(st, 3);
         if (rc) return rc;
         // the last layer of a completion group: every gradient of the bucket has been written
         // (an EXTERNAL record: inside a captured graph it becomes an event-record node that fires on every replay)
         if (i == 0 || bucket_of(recs[i - 1]) != bucket_of(recs[i]))
             MISO_CUDA(cudaEventRecordWithFlags(net->bucket_ev[bucket_of(recs[i])], st, capturing(st) ? cudaEventRecordExternal : cudaEventRecordDefault));
     }
+    g_bwd_prof.report();
     return MISO_OK;
     });
 }

@@ -259,41 +259,61 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const WtcReduceArg
         aff[i] = af;
     }
     __syncthreads();
+    // 64 outputs per block (consecutive input channels: coalesced partial reads) x 4 threads per output, each summing a
+    // contiguous quarter of the CTAs with eight loads in flight; the quarters are added in a fixed order
+    __shared__ float part[4][64];
     const int total = 9 * a.co_n * a.ci_n;
     const float *P = a.partial + (size_t)a.slice * a.ncta * 3 * 128 * a.N;
     const size_t cstride = (size_t)3 * 128 * a.N;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < total; o += gridDim.x * blockDim.x) {
-        const int ci = o % a.ci_n;  // consecutive threads = consecutive input channels: coalesced partial reads
-        int r = o / a.ci_n;
-        const int co = r % a.co_n;
-        r /= a.co_n;
-        const int kf = r % 3, kt = r / 3;
-        if (a.co0 + co >= a.cout_real || a.ci0 + ci >= a.cin) continue;
-        const int row = (a.rev ? kt : 2 - kt) * a.co_n + co;
-        const float *p0 = P + ((size_t)kf * 128 + row) * a.N;
+    const int lane64 = threadIdx.x & 63, q4 = threadIdx.x >> 6;
+    const int per = (a.ncta + 3) / 4;
+    const int c_lo = q4 * per, c_hi = min(a.ncta, c_lo + per);
+    for (int o0 = blockIdx.x * 64; o0 < total; o0 += gridDim.x * 64) {
+        const int o = o0 + lane64;
         float acc = 0.f;
-        int c = 0;
-        for (; c + 8 <= a.ncta; c += 8) {  // eight CTAs' loads in flight; the additions keep the CTA order
-            float g[8], s1[8];
+        int ci = 0, co = 0, kf = 0, kt = 0;
+        bool live = o < total;
+        if (live) {
+            ci = o % a.ci_n;
+            int r = o / a.ci_n;
+            co = r % a.co_n;
+            r /= a.co_n;
+            kf = r % 3;
+            kt = r / 3;
+            live = a.co0 + co < a.cout_real && a.ci0 + ci < a.cin;
+        }
+        if (live) {
+            const int row = (a.rev ? kt : 2 - kt) * a.co_n + co;
+            const float *p0 = P + ((size_t)kf * 128 + row) * a.N;
+            int c = c_lo;
+            for (; c + 8 <= c_hi; c += 8) {
+                float g[8], s1[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float *p = p0 + (size_t)(c + u) * cstride;
-                g[u] = p[ci];
-                s1[u] = p[a.ci_n];
+                for (int u = 0; u < 8; ++u) {
+                    const float *p = p0 + (size_t)(c + u) * cstride;
+                    g[u] = p[ci];
+                    s1[u] = p[a.ci_n];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float2 af = aff[((c + u) / a.nper) * a.ci_n + ci];
+                    acc = fmaf(af.x, g[u], fmaf(af.y, s1[u], acc));
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float2 af = aff[((c + u) / a.nper) * a.ci_n + ci];
-                acc = fmaf(af.x, g[u], fmaf(af.y, s1[u], acc));
+            for (; c < c_hi; ++c) {
+                const float *p = p0 + (size_t)c * cstride;
+                const float2 af = aff[(c / a.nper) * a.ci_n + ci];
+                acc = fmaf(af.x, p[ci], fmaf(af.y, p[a.ci_n], acc));
             }
         }
-        for (; c < a.ncta; ++c) {
-            const float *p = p0 + (size_t)c * cstride;
-            const float2 af = aff[(c / a.nper) * a.ci_n + ci];
-            acc = fmaf(af.x, p[ci], fmaf(af.y, p[a.ci_n], acc));
+        part[q4][lane64] = acc;
+        __syncthreads();
+        if (q4 == 0 && live) {
+            const float v = ((part[0][lane64] + part[1][lane64]) + part[2][lane64]) + part[3][lane64];
+            const size_t idx = a.transposed ? ((size_t)(a.ci0 + ci) * a.cout_real + a.co0 + co) : ((size_t)(a.co0 + co) * a.cin + a.ci0 + ci);
+            a.dw[(idx * 3 + kt) * 3 + kf] += v;
         }
-        const size_t idx = a.transposed ? ((size_t)(a.ci0 + ci) * a.cout_real + a.co0 + co) : ((size_t)(a.co0 + co) * a.cin + a.ci0 + ci);
-        a.dw[(idx * 3 + kt) * 3 + kf] += acc;
+        __syncthreads();
     }
 }
 
@@ -547,7 +567,7 @@ int launch_wgrad_tc(const WgradArgs &a, cudaStream_t st) {
             r.rev = (kase == WTC_CONVT_S1 || kase == WTC_CONVT_S2) ? 1 : 0;
             r.transposed = a.transposed;
             const int total = 9 * con_c * r.ci_n;
-            wgrad_tc_reduce_kernel<<<std::min(2 * 148, (total + 255) / 256), 256, (size_t)a.B * r.ci_n * sizeof(float2), st>>>(r);
+            wgrad_tc_reduce_kernel<<<std::min(8 * 148, (total + 63) / 64), 256, (size_t)a.B * r.ci_n * sizeof(float2), st>>>(r);
             MISO_LAUNCHED("wgrad_tc_reduce_kernel");
         }
     return MISO_OK;

@@ -671,32 +671,3 @@ def test_native_library_is_what_ran():
     assert _lib.launch_count() > 0
     with open("/proc/self/maps") as f:
         assert "libmisonet_b200.so" in f.read()
-
-
-def test_fused_operand_preparation_switch():
-    """MISO_RS_FUSE=1 (conv_rs.cu, RsFuse: the DenseBlock convs build their late input group's operands inside the kernel;
-    off by default, measured slower -- profiles/r2_fused_prep_ab.json) must give the default path's result.  The switch is
-    read once per process, hence the subprocess."""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = r'''
-import sys, numpy as np, torch
-sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
-from test_gpu_parity import _model
-from conftest import rel_err
-from misonet_b200 import synth
-from oracle import miso_net_torch as mnt
-m, cfg, sd = _model("miso1", 5, layout="PAPER")
-mix = synth.random_spec(7, (3, 6, 40, 257))
-ref = mnt.miso1_forward(sd, cfg, torch.from_numpy(mix)).numpy()
-with torch.no_grad():
-    y = m(torch.from_numpy(mix).cuda()).cpu().numpy()
-e = rel_err(y, ref)
-print("FUSED_REL_ERR", e)
-assert e < 2e-4
-''' % (root, root)
-    env = dict(os.environ, MISO_RS_FUSE="1")
-    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout + res.stderr
-    assert "FUSED_REL_ERR" in res.stdout

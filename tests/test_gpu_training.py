@@ -129,7 +129,9 @@ def test_backward_matches_autograd_ref_layout(mode, B, T, seed):
     m(mix.cuda()).backward(up.cuda())
     scale = max(float(g.norm()) for g in first.values())
     for k, p in m.named_parameters():
-        assert float((p.grad - first[k]).norm()) < 1e-4 * float(first[k].norm()) + 1e-8 * scale, k
+        # (a PReLU slope's gradient is ONE scalar summed over every TCN activation, with heavy cancellation: looser)
+        rel = 1e-3 if p.numel() == 1 else 1e-4
+        assert float((p.grad - first[k]).norm()) < rel * float(first[k].norm()) + 1e-8 * scale, k
 
 
 def test_backward_matches_autograd_paper_layout():
