@@ -830,7 +830,52 @@ int Walker::run(const void *d_x, float *d_y) {
             rc = launch_tcn_wprep(tab, 2 * nblk, C, cpad, n->mode == 1 ? 3 : 1, pl.tcn_wimg, pl.tcn_wvec, st);
             if (rc) return rc;
         }
-        for (int k = 0; k < nblk; ++k) {
+        // tensor-core modes: the whole TCN as one cluster-per-sample launch (tcn.cu, tcn_fused_kernel)
+        const bool fused = !dry && use_pw && tcn_fused_eligible(C, T, 2 * nblk);
+        if (fused) {
+            TcnFusedArgs fa{};
+            fa.nhalf = 2 * nblk;
+            fa.B = B;
+            fa.T = T;
+            fa.C = C;
+            fa.wimg = pl.tcn_wimg;
+            fa.wvec = pl.tcn_wvec;
+            fa.in_inv_n = inv_T;
+            fa.gln_inv_n = 1.0 / ((double)C * T);
+            fa.in_eps = kInEps;
+            fa.gln_eps = kGlnEps;
+            fa.out_ctot = d0.ctot;
+            fa.use_lo = use_lo;
+            fa.out_lo_off = d0.lo_off;
+            for (int k = 0; k < nblk; ++k)
+                for (int half = 0; half < 2; ++half) {
+                    const TcnHalf &h = n->tcn[k * 2 + half];
+                    TcnFusedHalf &fh = fa.h[k * 2 + half];
+                    fh.u = half == 0 ? pl.Sk[k] : pl.Uk[k];
+                    fh.u_sums = half == 0 ? pl.sS[k] : pl.sU[k];
+                    fh.g_sums = half == 0 ? pl.g1[k] : pl.g2[k];
+                    fh.dw = n->params[h.dw].d;
+                    fh.alpha = n->params[h.alpha].d;
+                    fh.dil = 1 << (k % n->X);
+                    if (half == 0) {
+                        fh.out = pl.Uk[k];
+                        fh.out_sums = pl.sU[k];
+                        fh.resid = nullptr;
+                    } else if (k + 1 < nblk) {
+                        fh.out = pl.Sk[k + 1];
+                        fh.out_sums = pl.sS[k + 1];
+                        fh.resid = pl.Sk[k];
+                    } else {
+                        fh.out = d0.p;  // TCN output = first half of decoder 0's input, consumed raw
+                        fh.out_planes = 1;
+                        fh.out_sums = nullptr;
+                        fh.resid = pl.Sk[k];
+                    }
+                }
+            rc = launch_tcn_fused(fa, n->mode == 1 ? 3 : 1, st);
+            if (rc) return rc;
+        }
+        for (int k = 0; k < nblk && !fused; ++k) {
             const int dil = 1 << (k % n->X);
             for (int half = 0; half < 2; ++half) {
                 const TcnHalf &h = n->tcn[k * 2 + half];
@@ -1371,6 +1416,7 @@ int miso_debug_tc_trace(long long *d_buf, int cin, int fin) {
     // and a DenseBlock conv can share (cin, Fin), and the later launch would overwrite the earlier one's log)
     const char *which = getenv("MISO_TRACE_KERNEL");
     const bool tc = !which || which[0] == 't', rs = !which || which[0] == 'r';
+    tcn_fused_set_trace(cin == -7 ? d_buf : nullptr);  // (cin = -7: the fused TCN launch, [half][16] stamps)
     conv_tc_set_trace(tc ? d_buf : nullptr, cin, fin);
     conv_rs_set_trace(rs ? d_buf : nullptr, cin, fin);
     return MISO_OK;

@@ -671,3 +671,33 @@ def test_native_library_is_what_ran():
     assert _lib.launch_count() > 0
     with open("/proc/self/maps") as f:
         assert "libmisonet_b200.so" in f.read()
+
+
+def test_fused_tcn_switch():
+    """MISO_TCN_FUSED=1 (tcn.cu, tcn_fused_kernel: the whole TCN as one launch, a thread-block cluster per sample; opt-in,
+    measured no faster -- profiles/r2_tcn_fused_*) must give the default path's result at one and at several frame tiles per
+    sample, both layouts.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+from test_gpu_parity import _model
+from conftest import rel_err
+from misonet_b200 import synth, _lib
+from oracle import miso_net_torch as mnt
+for layout, F, B, T in (("REF", 129, 1, 200), ("PAPER", 257, 2, 300), ("PAPER", 257, 1, 40)):
+    m, cfg, sd = _model("miso1", 5, layout=layout)
+    mix = synth.random_spec(7, (B, 6, T, F))
+    ref = mnt.miso1_forward(sd, cfg, torch.from_numpy(mix)).numpy()
+    with torch.no_grad():
+        y = m(torch.from_numpy(mix).cuda()).cpu().numpy()
+    e = rel_err(y, ref)
+    print("FUSED_TCN_REL_ERR", layout, T, e)
+    assert e < 2e-4
+''' % (root, root)
+    env = dict(os.environ, MISO_TCN_FUSED="1", MISO_TC_DEBUG="1")
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("FUSED_TCN_REL_ERR") == 3
