@@ -53,7 +53,7 @@ struct RsGeom {
     int Nc, N3, L, G, Mr, pitch, PL, GS, nsp;
     int nplanes, nunit, kper, nchunk;
     int w_unit, w_off, stage, nstage, box_bytes;
-    int off_btab, off_red, off_stage, smem_total, tmem_cols;
+    int off_btab, off_red, off_stg, off_stage, smem_total, tmem_cols;
     int red_stride;  // floats per epilogue warp in the statistics reduction buffer
     int map5d;
     int S, TS, DS, Wr;  // packed mode (F + 1 <= 64): an M tile holds the same row of S frame strips; strip s covers the TS frames
@@ -399,6 +399,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         const int et = tid - kRsEpi0 * 32;
         const int npix = a.T * g.Fout;
         float *myred = red + (warp - kRsEpi0) * g.red_stride;
+        float *stg = reinterpret_cast<float *>(smem + g.off_stg);  // channels-last outputs: per-warp transposition tiles
         // Work split between the kRsEpiW warps of a tensor-memory lane quarter over the (row, 16-column chunk) items of a tile:
         // if the chunks of an accumulator slot divide evenly they split the CHUNKS (each warp takes every row), else the rows.
         // A warp that owns ONE chunk (Nc = 32, most layers) keeps its statistics in registers for the whole strip; otherwise
@@ -528,21 +529,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                 fma2(ssq[q], ssq[q + 1], y[q], y[q + 1], y[q], y[q + 1], ssq[q], ssq[q + 1]);
                             }
                             const int pix = t * g.Fout + f;
-                            if (a.out_cl) {
-                                // data gradient: accumulate into the fp32 channels-last gradient of the conv's input
-                                float *o4 = reinterpret_cast<float *>(a.out) + ((size_t)b * npix + pix) * a.out_ctot + a.out_coff + cbase + cb;
-#pragma unroll
-                                for (int q = 0; q < 16; q += 4) {
-                                    if (cbase + cb + q < a.cout) {
-                                        float4 old = a.out_cl == 1 ? *reinterpret_cast<float4 *>(o4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                        old.x += y[q];
-                                        old.y += y[q + 1];
-                                        old.z += y[q + 2];
-                                        old.w += y[q + 3];
-                                        *reinterpret_cast<float4 *>(o4 + q) = old;
-                                    }
-                                }
-                            } else
+                            if (!a.out_cl)
 #pragma unroll
                             for (int g8 = 0; g8 < 16; g8 += 8) {
                                 const int co = cb + g8;
@@ -566,6 +553,35 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                                     }
                                 }
                             }
+                        }
+                        if (a.out_cl) {
+                            // fp32 channels-last output (1: added to the gradient buffer, 2: stored).  One bin per lane would make
+                            // every 16-byte access of the warp touch 32 different lines of the buffer; the [32 bins x 16 channels]
+                            // tile is turned through shared memory so that four lanes cover the 64 contiguous bytes of a bin.
+                            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                            const int pix = t * g.Fout + f;
+                            float *stw = stg + (warp - kRsEpi0) * (32 * 20);
+                            __syncwarp();  // the previous item's readers are done with the tile
+#pragma unroll
+                            for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4 *>(stw + lane * 20 + q) = make_float4(y[q], y[q + 1], y[q + 2], y[q + 3]);
+                            __syncwarp();
+                            const int ch = cbase + cb + 4 * (lane & 3);
+                            float *optr[4];
+                            float4 vv[4], old[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int p = (lane >> 2) + 8 * i;
+                                const int pixp = __shfl_sync(0xffffffffu, pix, p);
+                                const bool ok = ((vmask >> p) & 1u) && ch < a.cout;
+                                optr[i] = ok ? reinterpret_cast<float *>(a.out) + ((size_t)b * npix + pixp) * a.out_ctot + a.out_coff + ch : nullptr;
+                                vv[i] = *reinterpret_cast<const float4 *>(stw + p * 20 + 4 * (lane & 3));
+                                old[i] = (optr[i] && a.out_cl == 1) ? *reinterpret_cast<const float4 *>(optr[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (optr[i])
+                                    *reinterpret_cast<float4 *>(optr[i]) =
+                                        make_float4(vv[i].x + old[i].x, vv[i].y + old[i].y, vv[i].z + old[i].z, vv[i].w + old[i].w);
                         }
                     };
                     // rows of the tile: the accumulator load of the next row is issued as soon as this row's values have left
@@ -891,7 +907,8 @@ bool make_rs_geom(const ConvArgs &a, int split, int kind, RsGeom &g) {
         const bool persist = nck % kRsEpiW == 0 ? nck == kRsEpiW : nck == 1;
         g.red_stride = persist ? 32 : 2 * g.Nc;
     }
-    g.off_stage = rs_round_up(g.off_red + (kRsEpiWarps * g.red_stride + 9 * g.Nc) * 4, 1024);
+    g.off_stg = g.off_red + (kRsEpiWarps * g.red_stride + 9 * g.Nc) * 4;
+    g.off_stage = rs_round_up(g.off_stg + (a.out_layout == LAYOUT_CL_F32 ? kRsEpiWarps * 32 * 20 * 4 : 0), 1024);
     static const int g_env = getenv("MISO_RS_G") ? atoi(getenv("MISO_RS_G")) : 0;
     for (int G = std::min({(g.L - 2) / 2, kRsMaxG, g_env > 0 ? g_env : kRsMaxG}); G >= 1; --G) {
         for (int kper : {2, 1}) {

@@ -1083,12 +1083,13 @@ bool dgrad_tc_ok(const ConvArgs &f, const ConvArgs &d, const Plan &pl, int B, in
 // configuration if it writes planes, so it runs on conv_rs in chunks of <= 64 output channels into pl.dgP (the kernel's
 // N limit; the small dL/dy is re-read per chunk) and planes_accumulate_kernel adds the result into the fp32 gradient.
 constexpr int kRsChunk = 64;
-// DenseBlock data gradients on the row-streaming kernel in chunks of <= 64 output channels (its N limit) into a planes
-// scratch that planes_accumulate_kernel adds to the fp32 gradient.  MISO_DGRAD_RS_CL=1: the kernel's epilogue adds into
-// the fp32 gradient buffer itself (no scratch, no second kernel) -- measured SLOWER on B200 (52.1 against 50.1 ms per
-// training step, 8 utterances PAPER): the read-modify-write stalls the epilogue warps that drain tensor memory.
+// DenseBlock data gradients on the row-streaming kernel in chunks of <= 64 output channels (its N limit); the kernel's
+// epilogue adds into the fp32 channels-last gradient buffer itself.  With one bin per lane that read-modify-write was slower
+// than a planes scratch plus planes_accumulate_kernel (52.1 against 50.1 ms per training step, 8 utterances PAPER: every
+// 16-byte access of a warp touched 32 lines); turned through shared memory so that four lanes cover a bin's 64 bytes it is
+// faster (43.05 against 44.07 ms).  MISO_DGRAD_RS_CL=0 selects the scratch path.
 bool dgrad_rs_cl() {
-    static const bool on = getenv("MISO_DGRAD_RS_CL") && atoi(getenv("MISO_DGRAD_RS_CL")) != 0;
+    static const bool on = !(getenv("MISO_DGRAD_RS_CL") && atoi(getenv("MISO_DGRAD_RS_CL")) == 0);
     return on;
 }
 ConvArgs dgrad_rs_chunk(const ConvArgs &d, const Plan &pl, int T, int c0) {

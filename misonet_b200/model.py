@@ -130,14 +130,27 @@ class _NetFunction(torch.autograd.Function):
                 import torch.distributed as dist
                 if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                     m._allreduce_buckets(flat, numel, B, dev)
-            # autograd may alias what it is handed as .grad (and accumulate into it): give it a copy, not the buffer the
-            # next backward overwrites
+            # the step's gradients live in a copy, not in the buffer the next backward overwrites
             flat = flat.clone()
+        # The 268 parameter gradients are handed over as views of that ONE buffer, set as ``p.grad`` directly: returned through
+        # autograd, every view is cloned by its AccumulateGrad node (268 small kernels after the backward graph, ~1.5 ms of
+        # a 43 ms step).  A parameter that already holds a gradient (no ``zero_grad(set_to_none=True)``) accumulates.
+        params = list(m._param_list)
+        direct = len(params) == len(ctx.param_shapes) and all(p.requires_grad for p in params)
         grads, off = [], 0
-        for shp in ctx.param_shapes:
+        for i, shp in enumerate(ctx.param_shapes):
             n = int(torch.Size(shp).numel())
-            grads.append(flat[off:off + n].view(shp))
+            g_i = flat[off:off + n].view(shp)
             off += n
+            if direct:
+                p = params[i]
+                if p.grad is None:
+                    p.grad = g_i
+                else:
+                    p.grad.add_(g_i)
+                grads.append(None)
+            else:
+                grads.append(g_i)
         return (None, None, None, None, None, *grads)
 
 
