@@ -820,13 +820,14 @@ bool make_rs_geom(const ConvArgs &a, int split, int kind, RsGeom &g) {
     if (!rs_shape_ok(a, kind)) return false;
     g.nsp = split == 3 ? 2 : 1;
     static const int max_nc = getenv("MISO_RS_MAXNC") ? atoi(getenv("MISO_RS_MAXNC")) : 64;
-    g.Nc = rs_round_up(std::min(a.cout, max_nc), 16);
-    if (g.Nc > max_nc) return false;
-    if (a.cout > g.Nc) {
-        // more output channels than one accumulator slot holds: chunks of Nc channels walked by ONE launch (plane outputs of
-        // the plain DenseBlock variant only)
-        static const bool chunks_ok = getenv("MISO_RS_CHUNKS") && atoi(getenv("MISO_RS_CHUNKS")) != 0;  // host side not wired yet
-        if (!chunks_ok || kind != RS_DENSE || a.out_layout != LAYOUT_PLANES || g.Nc % 8) return false;
+    {
+        // more output channels than one accumulator slot holds (the data gradients of the DenseBlock convs: cout = the
+        // forward's cin): nch chunks of Nc channels, evenly sized, walked by ONE launch
+        const int nch = (a.cout + max_nc - 1) / max_nc;
+        g.Nc = rs_round_up((a.cout + nch - 1) / nch, 16);
+        if (g.Nc > max_nc) return false;
+        static const bool chunks_ok = !(getenv("MISO_RS_CHUNKS") && atoi(getenv("MISO_RS_CHUNKS")) == 0);
+        if (nch > 1 && (!chunks_ok || kind != RS_DENSE || a.out_sums)) return false;
     }
     g.N3 = 3 * g.Nc;
     g.Fin = a.Fin;
@@ -1010,6 +1011,13 @@ int conv_rs_init() {
     e = cudaFuncSetAttribute(conv_rs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_rs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemLimit);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rs_kernel)");
+    // the preparation kernel runs between two conv kernels that take (almost) all shared memory: ask for the same carve-out so
+    // that the SMs do not reconfigure their L1 / shared split twice per layer (MISO_CARVEOUT=0: the driver's default)
+    static const bool carve = !(getenv("MISO_CARVEOUT") && atoi(getenv("MISO_CARVEOUT")) == 0);
+    if (carve) {
+        e = cudaFuncSetAttribute(conv_rs_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_rs_prep_kernel, carveout)");
+    }
     done = true;
     return MISO_OK;
 }
@@ -1025,8 +1033,9 @@ void conv_rs_scratch_need(const ConvArgs &a, int split, size_t *wimg_bytes, size
     RsGeom g;
     *wimg_bytes = *btab_bytes = 0;
     if (!make_rs_geom(a, split, g)) return;
-    *wimg_bytes = (size_t)a.B * g.nunit * g.w_unit;
-    *btab_bytes = (size_t)a.B * ((a.cin + kRsBiasCi - 1) / kRsBiasCi) * 9 * g.Nc * sizeof(float);
+    const int nch = (a.cout + g.Nc - 1) / g.Nc;
+    *wimg_bytes = (size_t)nch * a.B * g.nunit * g.w_unit;
+    *btab_bytes = (size_t)nch * a.B * ((a.cin + kRsBiasCi - 1) / kRsBiasCi) * 9 * g.Nc * sizeof(float);
 }
 
 namespace {
@@ -1055,6 +1064,8 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
     k.out_coff = a.out_coff;
     k.cout = a.cout;
     k.nch = (a.cout + g.Nc - 1) / g.Nc;
+    k.wimg_cstride = (size_t)a.B * k.wimg_bstride;
+    k.btab_cstride = (size_t)a.B * nsplit * 9 * g.Nc;
     k.out_lo_off = a.out_lo_off;
     k.use_lo = a.use_lo;
     k.elu = a.elu;
@@ -1088,7 +1099,8 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     MISO_REQUIRE(nkind > 0 && make_rs_geom(a, split, g), "conv_rs: layer does not fit the row-streaming path (cin=%d cout=%d F=%d)", a.cin, a.cout,
                  a.Fin);
     const int nsplit = (a.cin + kRsBiasCi - 1) / kRsBiasCi;
-    const size_t need_w = (size_t)a.B * g.nunit * g.w_unit, need_b = (size_t)a.B * nsplit * 9 * g.Nc * sizeof(float);
+    const int nch = (a.cout + g.Nc - 1) / g.Nc;
+    const size_t need_w = (size_t)nch * a.B * g.nunit * g.w_unit, need_b = (size_t)nch * a.B * nsplit * 9 * g.Nc * sizeof(float);
     if (need_w > scratch.wimg_bytes || need_b > scratch.btab_bytes) {
         set_error("conv_rs: scratch too small (%zu/%zu weight bytes, %zu/%zu bias bytes)", scratch.wimg_bytes, need_w, scratch.btab_bytes,
                   need_b);
@@ -1116,9 +1128,11 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.nsp = g.nsp;
     p.nsplit = nsplit;
     p.flip_t = a.transposed ? 1 : 0;
+    p.wimg_cstride = (size_t)a.B * g.nunit * (g.w_unit / 2);
+    p.btab_cstride = (size_t)a.B * nsplit * 9 * g.Nc;
     const size_t prep_smem = (size_t)(kRsBiasCi + 8 * 9 * g.Nc) * sizeof(float);
     prof_begin(stream);
-    MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_rs_prep_kernel, dim3(a.B * g.nunit + a.B * nsplit), dim3(256), prep_smem, stream, p));
+    MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_rs_prep_kernel, dim3(a.B * g.nunit + a.B * nsplit, nch), dim3(256), prep_smem, stream, p));
     prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_rs_prep_kernel");
     static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;

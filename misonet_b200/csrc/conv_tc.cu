@@ -928,6 +928,11 @@ int conv_tc_init() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_kernel)");
+    static const bool carve = !(getenv("MISO_CARVEOUT") && atoi(getenv("MISO_CARVEOUT")) == 0);  // see conv_rs_init
+    if (carve) {
+        e = cudaFuncSetAttribute(conv_tc_prep_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(conv_tc_prep_kernel, carveout)");
+    }
     if (!get_encode()) {
         set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver");
         return MISO_E_CUDA;

@@ -1092,9 +1092,9 @@ bool dgrad_rs_cl() {
     static const bool on = !(getenv("MISO_DGRAD_RS_CL") && atoi(getenv("MISO_DGRAD_RS_CL")) == 0);
     return on;
 }
-ConvArgs dgrad_rs_chunk(const ConvArgs &d, const Plan &pl, int T, int c0) {
+ConvArgs dgrad_rs_chunk(const ConvArgs &d, const Plan &pl, int T, int c0, int width) {
     ConvArgs a = d;
-    a.cout = std::min(kRsChunk, d.cout - c0);
+    a.cout = std::min(width, d.cout - c0);
     a.w = d.w ? d.w + c0 : nullptr;
     if (dgrad_rs_cl()) {
         a.out_coff = d.out_coff + c0;
@@ -1112,9 +1112,10 @@ ConvArgs dgrad_rs_chunk(const ConvArgs &d, const Plan &pl, int T, int c0) {
 }
 bool dgrad_rs_ok(const ConvArgs &d, int flip, const Plan &pl, int B, int T) {
     if (!flip || d.cout % 8) return false;
-    if (!dgrad_rs_cl() && (size_t)B * ((d.cout + 7) & ~7) * T * d.Fout * 4 > pl.dgP_bytes) return false;
+    if (dgrad_rs_cl()) return conv_rs_eligible(dgrad_rs_chunk(d, pl, T, 0, d.cout), 3);
+    if ((size_t)B * ((d.cout + 7) & ~7) * T * d.Fout * 4 > pl.dgP_bytes) return false;
     for (int c0 = 0; c0 < d.cout; c0 += kRsChunk)
-        if (!conv_rs_eligible(dgrad_rs_chunk(d, pl, T, c0), 3)) return false;
+        if (!conv_rs_eligible(dgrad_rs_chunk(d, pl, T, c0, kRsChunk), 3)) return false;
     return true;
 }
 
@@ -1138,7 +1139,7 @@ bool full_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
             w.need_b = std::max(w.need_b, bb);
             if (dgrad_rs_ok(d, flip, pl, B, T))
                 for (int c0 = 0; c0 < d.cout; c0 += kRsChunk) {
-                    conv_tc_scratch_need(dgrad_rs_chunk(d, pl, T, c0), 3, &ww, &bb);
+                    conv_tc_scratch_need(dgrad_rs_chunk(d, pl, T, dgrad_rs_cl() ? 0 : c0, dgrad_rs_cl() ? d.cout : kRsChunk), 3, &ww, &bb);
                     w.need_w = std::max(w.need_w, ww);
                     w.need_b = std::max(w.need_b, bb);
                 }
@@ -1613,11 +1614,11 @@ struct Backward {
             if (rc) return rc;
             static const bool no_rs = getenv("MISO_DGRAD_RS") && atoi(getenv("MISO_DGRAD_RS")) == 0;  // debugging: general kernel only
             if (!no_rs && dgrad_rs_ok(d, flip, pl, B, T)) {
+                if (dgrad_rs_cl()) return launch_conv_tc(dgrad_rs_chunk(d, pl, T, 0, d.cout), 3, pl.scratch, st);  // all chunks in one launch
                 for (int c0 = 0; c0 < d.cout; c0 += kRsChunk) {
-                    rc = launch_conv_tc(dgrad_rs_chunk(d, pl, T, c0), 3, pl.scratch, st);
+                    rc = launch_conv_tc(dgrad_rs_chunk(d, pl, T, c0, kRsChunk), 3, pl.scratch, st);
                     if (rc) return rc;
                 }
-                if (dgrad_rs_cl()) return MISO_OK;
                 return launch_planes_accumulate(reinterpret_cast<const __nv_bfloat16 *>(pl.dgP), (d.cout + 7) & ~7, din, d.out_ctot,
                                                 d.out_coff, d.cout, B, T * d.Fout, st);
             }
