@@ -74,7 +74,8 @@ struct RsGeom {
 struct RsArgs {
     RsGeom g;
     const __nv_bfloat16 *wimg;  // [B][nunit][kf][hi|lo][kg][N3][8]
-    size_t wimg_bstride;        // elements per sample
+    size_t wimg_bstride;        // elements per sample (0: one image for all samples -- no per-sample normalisation)
+    size_t btab_bstride;        // floats per sample of the border-bias partial sums (0: shared)
     const float *btab;          // border-bias partial sums [B][nsplit][9][Nc]
     const float *bias;
     int nsplit;
@@ -114,6 +115,7 @@ struct RsPrepArgs {
     __nv_bfloat16 *wimg;
     float *btab;
     int B, Nc, nunit, nsp, nsplit;
+    int nb;  // sample images / bias tables built: B, or 1 without a per-sample normalisation (data gradients, the first conv)
     int flip_t;  // transposed convs read input frame t + 1 - kt: the image / bias slots of frame tap kt take W[2 - kt]
     // output-channel chunks (blockIdx.y): chunk c builds the image / bias sums of output channels [c * Nc, c * Nc + Nc)
     size_t wimg_cstride, btab_cstride;
@@ -420,7 +422,7 @@ conv_rs_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 // expand to the 64 (frame-mask, bin-mask) classes
                 asm volatile("bar.sync 1, %0;" ::"n"(kRsEpiThreads));
                 float *wb = red + kRsEpiWarps * g.red_stride;  // [9][Nc]
-                const float *src = a.btab + (size_t)w.ch * a.btab_cstride + (size_t)b * a.nsplit * 9 * Nc;
+                const float *src = a.btab + (size_t)w.ch * a.btab_cstride + (size_t)b * a.btab_bstride;
                 for (int i = et; i < 9 * Nc; i += kRsEpiThreads) {
                     float v = 0.f;
                     for (int sp = 0; sp < a.nsplit; ++sp) v += __ldg(src + (size_t)sp * 9 * Nc + i);
@@ -659,7 +661,7 @@ __global__ void __launch_bounds__(256) conv_rs_prep_kernel(const RsPrepArgs pa) 
         p.wimg += (size_t)blockIdx.y * p.wimg_cstride;
         p.btab += (size_t)blockIdx.y * p.btab_cstride;
     }
-    const int nimg = p.B * p.nunit;
+    const int nimg = p.nb * p.nunit;
     const int N3 = 3 * p.Nc;
     if ((int)blockIdx.x < nimg) {
         const int b = blockIdx.x / p.nunit, unit = blockIdx.x - b * p.nunit;
@@ -1050,7 +1052,9 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
     RsArgs k{};
     k.g = g;
     k.wimg = wimg;
-    k.wimg_bstride = (size_t)g.nunit * (g.w_unit / 2);
+    const int nb = a.norm_mode == NORM_IN ? a.B : 1;
+    k.wimg_bstride = nb > 1 ? (size_t)g.nunit * (g.w_unit / 2) : 0;
+    k.btab_bstride = nb > 1 ? (size_t)nsplit * 9 * g.Nc : 0;
     k.btab = btab;
     k.bias = a.bias;
     k.nsplit = nsplit;
@@ -1064,8 +1068,8 @@ int rs_launch(const ConvArgs &a, int split, const RsGeom &g, const __nv_bfloat16
     k.out_coff = a.out_coff;
     k.cout = a.cout;
     k.nch = (a.cout + g.Nc - 1) / g.Nc;
-    k.wimg_cstride = (size_t)a.B * k.wimg_bstride;
-    k.btab_cstride = (size_t)a.B * nsplit * 9 * g.Nc;
+    k.wimg_cstride = (size_t)nb * g.nunit * (g.w_unit / 2);
+    k.btab_cstride = (size_t)nb * nsplit * 9 * g.Nc;
     k.out_lo_off = a.out_lo_off;
     k.use_lo = a.use_lo;
     k.elu = a.elu;
@@ -1128,11 +1132,12 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.nsp = g.nsp;
     p.nsplit = nsplit;
     p.flip_t = a.transposed ? 1 : 0;
-    p.wimg_cstride = (size_t)a.B * g.nunit * (g.w_unit / 2);
-    p.btab_cstride = (size_t)a.B * nsplit * 9 * g.Nc;
+    p.nb = a.norm_mode == NORM_IN ? a.B : 1;
+    p.wimg_cstride = (size_t)p.nb * g.nunit * (g.w_unit / 2);
+    p.btab_cstride = (size_t)p.nb * nsplit * 9 * g.Nc;
     const size_t prep_smem = (size_t)(kRsBiasCi + 8 * 9 * g.Nc) * sizeof(float);
     prof_begin(stream);
-    MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_rs_prep_kernel, dim3(a.B * g.nunit + a.B * nsplit, nch), dim3(256), prep_smem, stream, p));
+    MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_rs_prep_kernel, dim3(p.nb * g.nunit + p.nb * nsplit, nch), dim3(256), prep_smem, stream, p));
     prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_rs_prep_kernel");
     static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;

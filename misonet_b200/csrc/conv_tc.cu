@@ -75,6 +75,7 @@ struct TcArgs {
     TcGeom g;
     const __nv_bfloat16 *wimg;  // [B][nNt][nchunk][ntap][2][nsp*N][8]
     const float *btab;          // border-bias partial sums [B][nNt][nsplit][9][N] (conv_tc_prep_kernel)
+    int bias_shared;            // no per-sample normalisation: one table (all zero) for every sample
     const float *bias;          // [cout_pad] or null
     int nsplit;
     void *out;
@@ -116,7 +117,9 @@ struct PrepArgs {
     __nv_bfloat16 *wimg;
     float *btab;
     int B, N, nNt, nunit, nsp, ntap, KT, KF;
-    int shared_w;  // gLN: one weight image for all samples (scaled by gamma only; rstd is applied in the epilogue)
+    int shared_w;  // gLN: one weight image for all samples (scaled by gamma only; rstd is applied in the epilogue); also
+                   // without any normalisation (data gradients, the network's first conv), where the bias tables are shared too
+    int nb_bias;   // samples with a border-bias table of their own: B, or 1
     int nsplit;    // channel splits of the border-bias partial sums
     int tapk[kMaxTaps];
 };
@@ -360,7 +363,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
                 float *wb = red + 16 * N;  // [9][N] scratch behind the statistics
                 const int ntaps = a.KT * a.KF;
-                const float *src = a.btab + ((size_t)b * g.nNt + tr.nt) * a.nsplit * 9 * N;
+                const float *src = a.btab + ((size_t)(a.bias_shared ? 0 : b) * g.nNt + tr.nt) * a.nsplit * 9 * N;
                 for (int i = et; i < ntaps * N; i += kEpiThreads) {
                     float v = 0.f;
                     for (int sp = 0; sp < a.nsplit; ++sp) v += __ldg(src + (size_t)sp * 9 * N + i);
@@ -633,7 +636,7 @@ __global__ void __launch_bounds__(256) conv_tc_prep_kernel(const PrepArgs p) {
         int idx = blockIdx.x - nimg;
         const int split = idx % p.nsplit;
         idx /= p.nsplit;
-        const int b = idx / p.nNt, nt = idx - b * p.nNt;
+        const int b = idx / p.nNt, nt = idx - b * p.nNt;  // (b < nb_bias by the grid size)
         float *shift = sh;                 // [kBiasCi]
         float *wb = sh + kBiasCi;          // [nparts <= 8][ntaps][N]: one slot per channel part, summed in a fixed order
         const int ci0 = split * kBiasCi, nci = min(kBiasCi, p.cin - ci0);
@@ -975,7 +978,8 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     if (conv_rs_eligible(a, split)) return launch_conv_rs(a, split, scratch, stream);
     TcGeom g;
     MISO_REQUIRE(make_geom(a, split, g), "conv_tc: layer does not fit the tcgen05 path (cin=%d cout=%d Fin=%d)", a.cin, a.cout, a.Fin);
-    const bool shared_w = a.norm_mode == NORM_GLN;
+    const bool shared_w = a.norm_mode != NORM_IN;
+    const int nb_bias = a.norm_mode == NORM_NONE ? 1 : a.B;
     const size_t need_w = (size_t)(shared_w ? 1 : a.B) * g.nNt * g.nunit * g.w_unit, need_b = (size_t)a.B * g.nNt * ((a.cin + kBiasCi - 1) / kBiasCi) * 9 * g.N * sizeof(float);
     if (need_w > scratch.wimg_bytes || need_b > scratch.btab_bytes) {
         set_error("conv_tc: scratch too small (%zu/%zu weight bytes, %zu/%zu bias bytes)", scratch.wimg_bytes, need_w,
@@ -1014,6 +1018,7 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.nNt = g.nNt;
     p.nunit = g.nunit;
     p.shared_w = shared_w ? 1 : 0;
+    p.nb_bias = nb_bias;
     p.nsplit = (a.cin + kBiasCi - 1) / kBiasCi;
     p.nsp = g.nsp;
     p.ntap = g.ntap;
@@ -1022,7 +1027,7 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     for (int i = 0; i < g.ntap; ++i) p.tapk[i] = g.tapk[i];
     const size_t prep_smem = (size_t)(kBiasCi + 8 * 9 * g.N) * sizeof(float);
     prof_begin(stream);
-    MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_tc_prep_kernel, dim3((shared_w ? 1 : a.B) * g.nunit + a.B * g.nNt * p.nsplit), dim3(256), prep_smem, stream, p));
+    MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_tc_prep_kernel, dim3((shared_w ? 1 : a.B) * g.nunit + nb_bias * g.nNt * p.nsplit), dim3(256), prep_smem, stream, p));
     prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_tc_prep_kernel");
     prof_begin(stream);
@@ -1054,7 +1059,8 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     k.transposed = a.transposed;
     k.elu = a.elu;
     k.wimg_bstride = shared_w ? 0 : (size_t)g.nNt * g.nunit * (g.w_unit / 2);
-    k.gln_sums = shared_w ? a.in_sums : nullptr;
+    k.gln_sums = a.norm_mode == NORM_GLN ? a.in_sums : nullptr;
+    k.bias_shared = nb_bias == 1 && a.B > 1 ? 1 : 0;
     k.gln_inv_n = a.norm_inv_n;
     k.gln_eps = a.norm_eps;
     k.resid = a.resid;
