@@ -779,13 +779,15 @@ __global__ void __launch_bounds__(256) tcn_recompute_kernel(const TcnBwdArgs a, 
     const float al = a.alpha[0];
     const float *ub = a.u + (size_t)b * T * C;
     const int t0 = blockIdx.x * kTcnBwFrames;
+    const float *__restrict__ ubr = ub;
+#pragma unroll 4
     for (int i = threadIdx.x; i < kTcnBwFrames * C; i += blockDim.x) {
         const int tt = i / C, c = i - tt * C;
         const int t = t0 + tt;
         if (t >= T) break;
         auto act = [&](int tq) {
             if (tq < 0 || tq >= T) return 0.f;
-            return elu_fast_bw(fmaf(ub[(size_t)tq * C + c], sc[c], sf[c]));
+            return elu_fast_bw(fmaf(__ldg(ubr + (size_t)tq * C + c), sc[c], sf[c]));
         };
         const float y = fmaf(wt[c], act(t - a.dil), fmaf(wt[C + c], act(t), wt[2 * C + c] * act(t + a.dil)));
         const float p = y > 0.f ? y : al * y;
@@ -886,35 +888,56 @@ __global__ void __launch_bounds__(128) gln_bwd_apply_kernel(const TcnBwdArgs a, 
 // depthwise conv + ELU backward: DN = dL/dn (n = IN1d(u)), its per-(b,c) sums for the InstanceNorm1d backward, and
 // the depthwise weight gradient
 // 32 frames per CTA: every CTA ends with five atomics per channel onto [b][c] / [c] accumulators, and with 8 frames the 504
-// CTAs of a B = 8, T = 500 step serialised on them (56 us per launch; the arithmetic is ~10 us)
+// CTAs of a B = 8, T = 500 step serialised on them (56 us per launch; the arithmetic is ~10 us).  With 128 threads walking
+// three channels each, one frame at a time, the 32-frame version was a chain of ~100 dependent L2 round trips (103 us under
+// ncu): one channel per thread and the loads of four frames in flight.
 constexpr int kTcnRowsDw = 32;
-__global__ void __launch_bounds__(128) dw_bwd_kernel(const TcnBwdArgs a, const float *__restrict__ DY, float *__restrict__ DN,
-                                                     double *__restrict__ ired, float *__restrict__ dwdw) {
+constexpr int kDwBwdThreads = 384;  // one channel per thread at the PAPER width: the frame loop is a chain of L2 round trips,
+                                    // so the parallelism has to come from the channels and from four frames' loads in flight
+__global__ void __launch_bounds__(kDwBwdThreads) dw_bwd_kernel(const TcnBwdArgs a, const float *__restrict__ DY, float *__restrict__ DN,
+                                                               double *__restrict__ ired, float *__restrict__ dwdw) {
     const int C = a.C, T = a.T, b = blockIdx.y, d = a.dil;
     const int t0 = blockIdx.x * kTcnRowsDw, t1 = min(T, t0 + kTcnRowsDw);
-    const float *ub = a.u + (size_t)b * T * C;
-    const float *dyb = DY + (size_t)b * T * C;
-    for (int c = threadIdx.x; c < C; c += 128) {
+    const float *__restrict__ ub = a.u + (size_t)b * T * C;
+    const float *__restrict__ dyb = DY + (size_t)b * T * C;
+    for (int c = threadIdx.x; c < C; c += kDwBwdThreads) {
         const double *us = a.u_sums + ((size_t)b * C + c) * 2;
         const float2 af = affine_from_sums(stat_get(us), stat_get(us + 1), a.inv_T, (double)a.in_eps);
         const float w0 = a.wdw[c * 3], w1 = a.wdw[c * 3 + 1], w2 = a.wdw[c * 3 + 2];
         float s1 = 0.f, s2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        auto nrm = [&](int tq) { return fmaf(ub[(size_t)tq * C + c], af.x, af.y); };
-        auto dyat = [&](int tq) { return (tq >= 0 && tq < T) ? dyb[(size_t)tq * C + c] : 0.f; };
-        auto vat = [&](int tq) { return (tq >= 0 && tq < T) ? elu_fast_bw(nrm(tq)) : 0.f; };
-        for (int t = t0; t < t1; ++t) {
-            // forward: y[t] = w0 v[t-d] + w1 v[t] + w2 v[t+d]
-            const float dy = dyat(t);
-            const float dv = fmaf(w0, dyat(t + d), fmaf(w1, dy, w2 * dyat(t - d)));
-            const float n = nrm(t);
-            const float en = __expf(n);
-            const float dn = n > 0.f ? dv : dv * en;
-            DN[((size_t)b * T + t) * C + c] = dn;
-            s1 += dn;
-            s2 = fmaf(dn, n, s2);
-            g0 = fmaf(dy, vat(t - d), g0);
-            g1 = fmaf(dy, n > 0.f ? n : en - 1.f, g1);
-            g2 = fmaf(dy, vat(t + d), g2);
+        auto uat = [&](int tq) { return (tq >= 0 && tq < T) ? __ldg(ub + (size_t)tq * C + c) : 0.f; };
+        auto dyat = [&](int tq) { return (tq >= 0 && tq < T) ? __ldg(dyb + (size_t)tq * C + c) : 0.f; };
+        for (int tb = t0; tb < t1; tb += 4) {
+            // forward: y[t] = w0 v[t-d] + w1 v[t] + w2 v[t+d]; four frames at a time: all 24 loads first
+            float dy0[4], dym[4], dyp[4], u0[4], um[4], up[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = tb + i;
+                const bool in = t < t1;
+                dy0[i] = in ? dyat(t) : 0.f;
+                dym[i] = in ? dyat(t - d) : 0.f;
+                dyp[i] = in ? dyat(t + d) : 0.f;
+                u0[i] = in ? uat(t) : 0.f;
+                um[i] = in ? uat(t - d) : 0.f;
+                up[i] = in ? uat(t + d) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int t = tb + i;
+                if (t >= t1) break;
+                const float dv = fmaf(w0, dyp[i], fmaf(w1, dy0[i], w2 * dym[i]));
+                const float n = fmaf(u0[i], af.x, af.y);
+                const float en = __expf(n);
+                const float dn = n > 0.f ? dv : dv * en;
+                DN[((size_t)b * T + t) * C + c] = dn;
+                s1 += dn;
+                s2 = fmaf(dn, n, s2);
+                const float vm = (t - d >= 0) ? elu_fast_bw(fmaf(um[i], af.x, af.y)) : 0.f;
+                const float vp = (t + d < T) ? elu_fast_bw(fmaf(up[i], af.x, af.y)) : 0.f;
+                g0 = fmaf(dy0[i], vm, g0);
+                g1 = fmaf(dy0[i], n > 0.f ? n : en - 1.f, g1);
+                g2 = fmaf(dy0[i], vp, g2);
+            }
         }
         atomicAdd(ired + ((size_t)b * C + c) * 2, (double)s1);
         atomicAdd(ired + ((size_t)b * C + c) * 2 + 1, (double)s2);
@@ -1134,7 +1157,7 @@ int launch_dw_bwd(const TcnBwdArgs &a, const float *DY, float *DN, double *ired,
                   cudaStream_t st) {
     MISO_CUDA(cudaMemsetAsync(ired, 0, (size_t)a.B * a.C * 2 * sizeof(double), st));
     dim3 grid(ceil_div(a.T, kTcnRows), a.B);
-    dw_bwd_kernel<<<dim3(ceil_div(a.T, kTcnRowsDw), a.B), 128, 0, st>>>(a, DY, DN, ired, dwdw);
+    dw_bwd_kernel<<<dim3(ceil_div(a.T, kTcnRowsDw), a.B), kDwBwdThreads, 0, st>>>(a, DY, DN, ired, dwdw);
     MISO_LAUNCHED("dw_bwd_kernel");
     in1d_bwd_apply_kernel<<<grid, 128, 0, st>>>(a, DN, ired, out, accumulate);
     MISO_LAUNCHED("in1d_bwd_apply_kernel");
