@@ -817,13 +817,16 @@ __global__ void __launch_bounds__(128) gln_bwd_reduce_kernel(const TcnBwdArgs a,
         gam[k] = c < C ? a.gamma[c] : 0.f;
     }
     float a1 = 0.f, a2 = 0.f;
-    for (int t = t0; t < t1; ++t) {
+#pragma unroll
+    for (int ti = 0; ti < kTcnRows; ++ti) {  // constant trip count: the loads of all frames are issued up front
+        const int t = t0 + ti;
+        if (t >= t1) break;
         const size_t row = ((size_t)b * T + t) * C;
 #pragma unroll
         for (int k = 0; k < kTcnCh; ++k) {
             const int c = threadIdx.x + k * 128;
             if (c < C) {
-                const float dq = DQ[row + c], y = Y[row + c];
+                const float dq = __ldg(DQ + row + c), y = __ldg(Y + row + c);
                 const float p = y > 0.f ? y : al * y;
                 const float ph = (p - gs.mean) * gs.rstd;
                 const float g = gam[k] * dq;
@@ -864,10 +867,23 @@ __global__ void __launch_bounds__(128) gln_bwd_apply_kernel(const TcnBwdArgs a, 
     const float m1 = (float)(gred[(size_t)b * 2] * a.gln_inv_n), m2 = (float)(gred[(size_t)b * 2 + 1] * a.gln_inv_n);
     const int t0 = blockIdx.x * kTcnRows, t1 = min(T, t0 + kTcnRows);
     float da = 0.f;
-    for (int t = t0; t < t1; ++t) {
-        const size_t row = ((size_t)b * T + t) * C;
-        for (int c = threadIdx.x; c < C; c += 128) {
-            const float dq = DQ[row + c], y = Y[row + c];
+    for (int c = threadIdx.x; c < C; c += 128) {
+        // all frames of this channel: loads first (DQ is rewritten in place, which would otherwise order every load behind the
+        // previous frame's store)
+        float dqv[kTcnRows], yv[kTcnRows];
+#pragma unroll
+        for (int ti = 0; ti < kTcnRows; ++ti) {
+            const int t = t0 + ti;
+            const size_t row = ((size_t)b * T + min(t, T - 1)) * C;
+            dqv[ti] = DQ[row + c];
+            yv[ti] = __ldg(Y + row + c);
+        }
+#pragma unroll
+        for (int ti = 0; ti < kTcnRows; ++ti) {
+            const int t = t0 + ti;
+            if (t >= t1) break;
+            const size_t row = ((size_t)b * T + t) * C;
+            const float dq = dqv[ti], y = yv[ti];
             const float p = y > 0.f ? y : al * y;
             const float ph = (p - gs.mean) * gs.rstd;
             const float dp = gs.rstd * (a.gamma[c] * dq - m1 - ph * m2);
@@ -957,11 +973,21 @@ __global__ void __launch_bounds__(128) in1d_bwd_apply_kernel(const TcnBwdArgs a,
         const double *us = a.u_sums + ((size_t)b * C + c) * 2;
         const float2 af = affine_from_sums(stat_get(us), stat_get(us + 1), a.inv_T, (double)a.in_eps);
         const float m1 = (float)(ired[((size_t)b * C + c) * 2] * a.inv_T), m2 = (float)(ired[((size_t)b * C + c) * 2 + 1] * a.inv_T);
-        for (int t = t0; t < t1; ++t) {
+        float uv[kTcnRows], dnv[kTcnRows], ov[kTcnRows];  // loads of all frames first: the stores to `out` order the rest
+#pragma unroll
+        for (int ti = 0; ti < kTcnRows; ++ti) {
+            const size_t o = ((size_t)b * T + min(t0 + ti, T - 1)) * C + c;
+            uv[ti] = __ldg(a.u + o);
+            dnv[ti] = __ldg(DN + o);
+            ov[ti] = accumulate ? out[o] : 0.f;
+        }
+#pragma unroll
+        for (int ti = 0; ti < kTcnRows; ++ti) {
+            const int t = t0 + ti;
+            if (t >= t1) break;
             const size_t o = ((size_t)b * T + t) * C + c;
-            const float n = fmaf(a.u[o], af.x, af.y);
-            const float du = af.x * (DN[o] - m1 - n * m2);
-            out[o] = accumulate ? out[o] + du : du;
+            const float n = fmaf(uv[ti], af.x, af.y);
+            out[o] = ov[ti] + af.x * (dnv[ti] - m1 - n * m2);
         }
     }
 }

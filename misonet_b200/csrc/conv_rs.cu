@@ -20,6 +20,14 @@
 // input rows: the epilogue of tile k (output rows that became complete) overlaps the MMAs of tile k + 1;
 // 2G + 2 <= L.
 //
+// Epilogue (8 warps, two per tensor-memory lane quarter).  An item = one output row x 16 accumulator columns of a warp's 32
+// bins.  With cin <= 64 the kernel is bound by the epilogue, not by the MMAs (profiles/r2_conv_rs_epilogue_study.log), so:
+// the two warps of a quarter split the 16-column CHUNKS (each takes every row; with Nc = 32 a warp owns one chunk and keeps
+// its InstanceNorm statistics in registers for a whole strip), the tensor-memory load of the next row is issued as soon as
+// this row's values have left the load registers, the arithmetic is packed fp32x2 (FADD2 / FMUL2 / FFMA2) with a branch-free
+// ELU, and fp32 channels-last outputs (the data gradients, the network output) go through a per-warp transposition tile so
+// that four lanes cover the 64 contiguous bytes of a bin instead of one lane per bin (32 lines per access).
+//
 // Layout in shared memory per stage (kper 16-channel K units): A planes [hi|lo][unit][kg][row][pitch px][8 ch]
 // by one TMA box per plane set, then the per-sample weight image of the units (conv_rs_prep_kernel):
 // [unit][kf][hi|lo][kg][3 Nc rows][8 ch].  F + 1 = 128: rows are stored at a pitch of 128 pixels starting at
