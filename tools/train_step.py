@@ -173,7 +173,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s per GPU, algorithmic (3 x forward 2*MAC) / step time",
                          "peak": peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops"), "note": "whole step, not one kernel: "
-                         "the backward GEMMs run bf16 hi/lo split (3 MMAs per product) on mma.sync and the tcgen05 conv kernel"},
+                         "forward, data gradients and the 3x3 weight gradients run bf16 hi/lo split (3 MMAs per product) on tcgen05 kernels; the TCN pointwise / sub-15-bin weight gradients on mma.sync"},
             "cpu_baseline": cpu,
             "loss": float(loss.detach()), "train_workspace_gb": model._ws_train.numel() / 2 ** 30,
             "data": "synthetic (seeded random spectrograms, default PyTorch initialisation)"}))
