@@ -952,8 +952,12 @@ int Walker::run(const void *d_x, float *d_y) {
                     }
                     continue;
                 }
-                if (use_pw && a.out_layout == LAYOUT_CL_F32) {
+                if (use_pw && (a.out_layout == LAYOUT_CL_F32 || (a.out_layout == LAYOUT_PLANES && a.out_coff == 0 && !a.out_sums))) {
                     TcnPwArgs p{};
+                    p.out_planes = a.out_layout == LAYOUT_PLANES ? 1 : 0;
+                    p.out_ctot = a.out_ctot;
+                    p.use_lo = use_lo;
+                    p.out_lo_off = a.out_lo_off;
                     p.planes = pl.P;
                     p.lo_off = a.in_lo_off;
                     p.wimg = pl.tcn_wimg;

@@ -43,6 +43,8 @@ struct PwArgs {
     const float *resid;  // same layout, or null
     double *out_sums;    // [B][C][2] or null
     int B, T, C, t_tiles;
+    int out_planes, out_ctot, use_lo;  // bf16 hi/lo plane output [B][hi|lo][out_ctot/8][T][8]
+    size_t out_lo_off;
 };
 
 template <int SPLIT>
@@ -191,7 +193,17 @@ tcn_pw_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                 y.z = fmaf(ac.z, rstd, b4.z) + rr[i].z;
                 y.w = fmaf(ac.w, rstd, b4.w) + rr[i].w;
                 if (tt < a.T) {
-                    *reinterpret_cast<float4 *>(a.out + ((size_t)b * a.T + tt) * a.C + co0 + cb + 4 * cq) = y;
+                    if (!a.out_planes) {
+                        *reinterpret_cast<float4 *>(a.out + ((size_t)b * a.T + tt) * a.C + co0 + cb + 4 * cq) = y;
+                    } else {  // four channels of a frame = 8 bytes of the frame's 16 in an 8-channel plane group
+                        const int c = co0 + cb + 4 * cq;
+                        __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(a.out) + (size_t)b * 2 * a.out_ctot * a.T + ((size_t)(c >> 3) * a.T + tt) * 8 + (c & 7);
+                        const uint32_t h0 = pack_bf16x2(y.x, y.y), h1 = pack_bf16x2(y.z, y.w);
+                        *reinterpret_cast<uint2 *>(p) = make_uint2(h0, h1);
+                        if (a.use_lo)
+                            *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(p) + a.out_lo_off) =
+                                make_uint2(pack_bf16x2(y.x - bf16_lo(h0), y.y - bf16_hi(h0)), pack_bf16x2(y.z - bf16_lo(h1), y.w - bf16_hi(h1)));
+                    }
                     ps[0] += y.x, ps[1] += y.y, ps[2] += y.z, ps[3] += y.w;
                     pq[0] = fmaf(y.x, y.x, pq[0]), pq[1] = fmaf(y.y, y.y, pq[1]), pq[2] = fmaf(y.z, y.z, pq[2]), pq[3] = fmaf(y.w, y.w, pq[3]);
                 }
@@ -858,6 +870,10 @@ int launch_tcn_pw(const TcnPwArgs &p, int split, cudaStream_t stream) {
     k.out = p.out;
     k.resid = p.resid;
     k.out_sums = p.out_sums;
+    k.out_planes = p.out_planes;
+    k.out_ctot = p.out_ctot;
+    k.use_lo = p.use_lo;
+    k.out_lo_off = p.out_lo_off;
     k.B = p.B;
     k.T = p.T;
     k.C = p.C;

@@ -25,6 +25,9 @@ struct TcnPwArgs {
     const float *resid;
     double *out_sums;
     int B, T, C;
+    // out_planes: `out` is a bf16 hi/lo plane buffer [B][hi|lo][out_ctot/8][T][8] (the TCN's last half writes the decoder's input)
+    int out_planes, out_ctot, use_lo;
+    size_t out_lo_off;
 };
 
 // The whole TCN as ONE launch (tcn_fused_kernel, tcn.cu): a thread-block cluster per sample (one CTA per 128 frames) walks the
