@@ -115,6 +115,10 @@ int64_t miso_net_param_numel(const miso_net_t *net, int i);
 /* (re)pack one parameter from a DEVICE fp32 tensor in the reference's layout
  * (Conv2d [Cout,Cin,3,3], ConvTranspose2d [Cin,Cout,3,3], Conv1d [C,1,3]/[C,C,1], ...). */
 int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, int64_t numel, void *stream);
+/* the same for ALL parameters in one or two launches: d_data[i] = device fp32 tensor of parameter i (key order of
+ * miso_net_param_key), or NULL to leave that parameter untouched; n = miso_net_num_params().  A training step changes
+ * every parameter (trainer.py:212 optimizer.step()): one call instead of 268. */
+int miso_net_set_params(miso_net_t *net, const float *const *d_data, int n, void *stream);
 /* compute path of the 3x3 (de)convs: 0 = fp32 FMA kernels everywhere; 1 = tcgen05 bf16x3 split
  * (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32 accumulate: parity-grade, 3 MMAs per product); 2 = tcgen05
  * bf16 operands and hi-only activation planes (throughput mode, ~1e-2 relative error).

@@ -38,6 +38,7 @@ SIGNATURES = {
     "miso_net_param_key": (c_char_p, [c_void_p, c_int]),
     "miso_net_param_numel": (c_int64, [c_void_p, c_int]),
     "miso_net_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+    "miso_net_set_params": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "miso_net_set_mode": (c_int, [c_void_p, c_int]),
     "miso_net_set_graph": (c_int, [c_void_p, c_int]),
     "miso_debug_tc_trace": (c_int, [c_void_p, c_int, c_int]),

@@ -48,6 +48,42 @@ __global__ void pad_copy_kernel(const float *__restrict__ src, float *__restrict
     if (i < n_pad) dst[i] = i < n ? src[i] : 0.f;
 }
 
+// All parameters of a network in one launch (miso_net_set_params: a training step changes every one of the 268 parameters, and
+// 268 separate launches from Python cost ~2 ms of host time per step).  blockIdx.y = parameter (of this launch's batch),
+// blockIdx.x strides over its packed elements.
+struct PackDesc {
+    float *dst;
+    int kind, cout, cin, taps, cout_pad;  // kind: 0 conv weight, 1 transposed conv weight, 2 bias (zero padded), 3 plain copy
+    long long numel, packed_elems;
+};
+constexpr int kPackBatch = 128;
+struct PackSrcs {
+    const float *src[kPackBatch];
+};
+__global__ void __launch_bounds__(256) pack_params_kernel(const PackDesc *__restrict__ tab, const PackSrcs srcs, int first, int count) {
+    const int j = blockIdx.y;
+    if (j >= count) return;
+    const PackDesc d = tab[first + j];
+    const float *__restrict__ w = srcs.src[j];
+    if (!w) return;
+    const long long total = d.kind <= 1 ? (long long)d.taps * d.cin * d.cout_pad : (d.kind == 2 ? (long long)d.cout_pad : d.numel);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float v;
+        if (d.kind <= 1) {
+            const int co = (int)(i % d.cout_pad);
+            const long long r = i / d.cout_pad;
+            const int ci = (int)(r % d.cin), tap = (int)(r / d.cin);
+            v = 0.f;
+            if (co < d.cout) v = d.kind == 1 ? w[((long long)ci * d.cout + co) * d.taps + tap] : w[((long long)co * d.cin + ci) * d.taps + tap];
+        } else if (d.kind == 2) {
+            v = i < d.cout ? w[i] : 0.f;
+        } else {
+            v = w[i];
+        }
+        d.dst[i] = v;
+    }
+}
+
 __global__ void sentinel_kernel(double *sums, int B, int ctot, int coff, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * n) {
@@ -337,6 +373,7 @@ struct miso_net {
     std::vector<ConvDesc> dec_deconv;               // [nb]
     std::vector<TcnHalf> tcn;                       // [R*X*2]
     float *arena = nullptr;
+    PackDesc *d_pack = nullptr;  // device table of the parameters' packing descriptors (pack_params_kernel)
     int mode = 0;
     int n_loaded = 0;
     // CUDA-graph cache of the forward launch sequence (about 200 launches, 140 tensor-map encodes):
@@ -1265,6 +1302,7 @@ int miso_net_destroy(miso_net_t *net) {
     for (auto &e : net->bucket_ev)
         if (e) cudaEventDestroy(e);
     if (net->arena) cudaFree(net->arena);
+    if (net->d_pack) cudaFree(net->d_pack);
     delete net;
     return MISO_OK;
 }
@@ -1309,6 +1347,42 @@ int miso_net_set_param(miso_net_t *net, const char *key, const float *d_data, in
         p.loaded = true;
         net->n_loaded++;
     }
+    return MISO_OK;
+}
+
+int miso_net_set_params(miso_net_t *net, const float *const *d_data, int n, void *stream) {
+    MISO_REQUIRE(net && d_data, "miso_net_set_params: null argument");
+    MISO_REQUIRE(n == (int)net->params.size(), "miso_net_set_params: %d pointers for %d parameters", n, (int)net->params.size());
+    cudaStream_t st = as_stream(stream);
+    if (!net->d_pack) {
+        std::vector<PackDesc> tab(net->params.size());
+        for (size_t i = 0; i < net->params.size(); ++i) {
+            const Param &p = net->params[i];
+            PackDesc &d = tab[i];
+            d.dst = p.d;
+            d.kind = p.kind == P_DECONV_W ? 1 : ((p.kind == P_CONV_W || p.kind == P_PW_W) ? 0 : (p.kind == P_BIAS ? 2 : 3));
+            d.cout = p.cout;
+            d.cin = p.cin;
+            d.taps = p.taps;
+            d.cout_pad = p.cout_pad;
+            d.numel = p.numel;
+            d.packed_elems = (long long)p.packed_elems;
+        }
+        MISO_CUDA(cudaMalloc(&net->d_pack, tab.size() * sizeof(PackDesc)));
+        MISO_CUDA(cudaMemcpy(net->d_pack, tab.data(), tab.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
+    }
+    for (int first = 0; first < n; first += kPackBatch) {
+        const int count = std::min(kPackBatch, n - first);
+        PackSrcs srcs{};
+        for (int j = 0; j < count; ++j) srcs.src[j] = d_data[first + j];  // null: leave that parameter as it is
+        pack_params_kernel<<<dim3(32, count), 256, 0, st>>>(net->d_pack, srcs, first, count);
+        MISO_LAUNCHED("pack_params_kernel");
+    }
+    for (int i = 0; i < n; ++i)
+        if (d_data[i] && !net->params[i].loaded) {
+            net->params[i].loaded = true;
+            net->n_loaded++;
+        }
     return MISO_OK;
 }
 
