@@ -60,9 +60,7 @@ void prof_end(cudaStream_t st, double flops, double bytes, int family, double ex
 // still running; it must execute pdl_wait() before touching anything the predecessor reads or writes (everything before
 // that point -- barrier / tensor-memory set-up -- overlaps the predecessor's tail).  pdl_trigger() lets the successor's
 // launch begin.  Off by default (it measured 2.6 % slower on the bench workload: the early-resident dependents compete with
-// the predecessor's tail); MISO_PDL=1 turns the attribute on for every kernel of the chain, 2 for the operand-preparation kernels
-// only, 3 for the conv / TCN kernels only (2 and 3 measured ~0.6 % faster, inside the run-to-run noise; without the attribute the
-// device-side instructions are no-ops).
+// the predecessor's tail); MISO_PDL=1 turns the attribute on (without it the device-side instructions are no-ops).
 bool pdl_enabled();
 int pdl_level();
 template <typename... KArgs, typename... Args>
@@ -81,7 +79,7 @@ inline cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, d
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
-    return launch_pdl_if(pdl_level() == 1 || pdl_level() == 3, kernel, grid, block, smem, st, static_cast<Args &&>(args)...);
+    return launch_pdl_if(pdl_level() == 1, kernel, grid, block, smem, st, static_cast<Args &&>(args)...);
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -1145,7 +1145,7 @@ int launch_conv_rs(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     p.btab_cstride = (size_t)p.nb * nsplit * 9 * g.Nc;
     const size_t prep_smem = (size_t)(kRsBiasCi + 8 * 9 * g.Nc) * sizeof(float);
     prof_begin(stream);
-    MISO_CUDA(launch_pdl_if(pdl_level() == 1 || pdl_level() == 2, conv_rs_prep_kernel, dim3(p.nb * g.nunit + p.nb * nsplit, nch), dim3(256), prep_smem, stream, p));
+    MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_rs_prep_kernel, dim3(p.nb * g.nunit + p.nb * nsplit, nch), dim3(256), prep_smem, stream, p));
     prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_rs_prep_kernel");
     static const bool debug = getenv("MISO_TC_DEBUG") != nullptr;

@@ -1027,7 +1027,7 @@ int launch_conv_tc(const ConvArgs &a, int split, const TcScratch &scratch, cudaS
     for (int i = 0; i < g.ntap; ++i) p.tapk[i] = g.tapk[i];
     const size_t prep_smem = (size_t)(kBiasCi + 8 * 9 * g.N) * sizeof(float);
     prof_begin(stream);
-    MISO_CUDA(launch_pdl_if(pdl_level() == 1 || pdl_level() == 2, conv_tc_prep_kernel, dim3((shared_w ? 1 : a.B) * g.nunit + nb_bias * g.nNt * p.nsplit), dim3(256), prep_smem, stream, p));
+    MISO_CUDA(launch_pdl_if(pdl_level() >= 1, conv_tc_prep_kernel, dim3((shared_w ? 1 : a.B) * g.nunit + nb_bias * g.nNt * p.nsplit), dim3(256), prep_smem, stream, p));
     prof_end(stream, 0.0, (double)need_w + (double)need_b, MISO_PROF_PREP);
     MISO_LAUNCHED("conv_tc_prep_kernel");
     prof_begin(stream);

@@ -9,7 +9,7 @@
 namespace miso {
 
 int pdl_level() {
-    static const int lvl = getenv("MISO_PDL") ? atoi(getenv("MISO_PDL")) : 0;  // 1: whole chain, 2: operand-preparation kernels only, 3: conv / TCN kernels only
+    static const int lvl = getenv("MISO_PDL") ? atoi(getenv("MISO_PDL")) : 0;  // 1: whole chain, 2: operand-preparation kernels only
     return lvl;
 }
 
