@@ -133,8 +133,8 @@ class _NetFunction(torch.autograd.Function):
             # the step's gradients live in a copy, not in the buffer the next backward overwrites
             flat = flat.clone()
         # The 268 parameter gradients are handed over as views of that ONE buffer, set as ``p.grad`` directly: returned through
-        # autograd, every view is cloned by its AccumulateGrad node (268 small kernels after the backward graph, ~1.5 ms of
-        # a 43 ms step).  A parameter that already holds a gradient (no ``zero_grad(set_to_none=True)``) accumulates.
+        # autograd they pass 268 AccumulateGrad nodes one by one (~0.5 ms of host time per step, measured 43.05 -> 42.54 ms).
+        # A parameter that already holds a gradient (no ``zero_grad(set_to_none=True)``) accumulates.
         params = list(m._param_list)
         direct = len(params) == len(ctx.param_shapes) and all(p.requires_grad for p in params)
         grads, off = [], 0
