@@ -509,6 +509,7 @@ struct Plan {
     size_t wgP_bytes = 0;
     __nv_bfloat16 *wg_ones = nullptr;  // ... and its constant-one pixels [T * max F][8]
     size_t wg_ones_pix = 0;
+    void *tcn_wimgT = nullptr; // ... and their transposes for the backward (training plans)
     void *tcn_wimg = nullptr;  // tensor-core pointwise convs: weight images and W beta / W gamma vectors (tcn.cu)
     float *tcn_wvec = nullptr;
     std::vector<double *> sS, sU, g1, g2;
@@ -650,6 +651,7 @@ bool make_plan(const miso_net *n, int B, int T, int F, char *base, Plan &pl, boo
         tcn_pw_scratch_need(n->C, 2 * nblk, &wi, &wv);
         pl.tcn_wimg = take(wi);
         pl.tcn_wvec = reinterpret_cast<float *>(take(wv));
+        if (train) pl.tcn_wimgT = take(wi);  // transposed images: the pointwise convs' data gradients as tcn_pw GEMMs
     }
     pl.sS.resize(nblk);
     pl.sU.resize(nblk);
@@ -1875,23 +1877,58 @@ struct Backward {
         w.transposed = 0;
         rc = launch_wgrad(w, st);
         if (rc) return rc;
-        MISO_CUDA(cudaMemsetAsync(pl.tDQ, 0, (size_t)B * T * C * sizeof(float), st));
         const bool tc = use_tc(f);
         if (tc) {
             rc = launch_cl_to_planes(dout, reinterpret_cast<__nv_bfloat16 *>(pl.dyP), B, T, C, st);
             if (rc) return rc;
         }
-        rc = dgrad(f, n->params[h.pw].d, n->params[h.pw].cout_pad, dout, pl.tDQ, tc);
+        if (tc && pw_dgrad_gemm) {
+            // dq = dy W^T as the forward's pointwise GEMM kernel over the transposed weight image (built once per backward)
+            TcnPwArgs p{};
+            p.planes = pl.dyP;
+            p.lo_off = (size_t)C * T * 2;
+            p.wimg = pl.tcn_wimgT;
+            p.wvec = pl.tcn_wvec;
+            p.index = k * 2 + half;
+            p.plain = 1;
+            p.out = pl.tDQ;
+            p.B = B;
+            p.T = T;
+            p.C = C;
+            rc = launch_tcn_pw(p, 3, st);
+        } else {
+            MISO_CUDA(cudaMemsetAsync(pl.tDQ, 0, (size_t)B * T * C * sizeof(float), st));
+            rc = dgrad(f, n->params[h.pw].d, n->params[h.pw].cout_pad, dout, pl.tDQ, tc);
+        }
         if (rc) return rc;
         rc = launch_gln_bwd(a, pl.tDQ, pl.tY, pl.bred, g(h.gamma), g(h.beta), g(h.alpha), st);
         if (rc) return rc;
         return launch_dw_bwd(a, pl.tDQ, pl.tDN, pl.bred, g(h.dw), din, accumulate, st);
     }
 
+    bool pw_dgrad_gemm = false;  // the pointwise convs' data gradients run on tcn_pw_kernel (transposed images in pl.tcn_wimgT)
+
     int tcn() {
         const int C = n->C;
         const BufDesc &d0 = pl.D[0];
         const int64_t rows = (int64_t)B * T;
+        {
+            static const bool off = getenv("MISO_TCN_DGRAD_PW") && atoi(getenv("MISO_TCN_DGRAD_PW")) == 0;
+            const int nblk = n->R * n->X;
+            pw_dgrad_gemm = !off && n->mode == 1 && pl.tcn_wimgT && tcn_pw_eligible(C) && 2 * nblk <= kTcnMaxPw;
+            if (pw_dgrad_gemm) {
+                const int bn = conv_fp32_tile_n(C);
+                const int cpad = (C + bn - 1) / bn * bn;
+                TcnPwTable tab{};
+                for (int i = 0; i < 2 * nblk; ++i) {
+                    tab.w[i] = n->params[n->tcn[i].pw].d;
+                    tab.gamma[i] = n->params[n->tcn[i].gamma].d;
+                    tab.beta[i] = n->params[n->tcn[i].beta].d;
+                }
+                int rc0 = launch_tcn_wprep(tab, 2 * nblk, C, cpad, 3, pl.tcn_wimgT, nullptr, st, 1);
+                if (rc0) return rc0;
+            }
+        }
         // upstream: the TCN output is consumed raw as channels [0, C) of decoder 0's buffer (model.py:97-99)
         int rc = launch_copy_channels(d0.grad, d0.ctot, 0, pl.gS, C, 0, C, rows, 0, st);
         if (rc) return rc;

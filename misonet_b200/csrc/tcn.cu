@@ -45,6 +45,7 @@ struct PwArgs {
     int B, T, C, t_tiles;
     int out_planes, out_ctot, use_lo;  // bf16 hi/lo plane output [B][hi|lo][out_ctot/8][T][8]
     size_t out_lo_off;
+    int plain;  // no gLN epilogue (rstd 1, no bias): the data gradient GEMMs
 };
 
 template <int SPLIT>
@@ -144,14 +145,17 @@ tcn_pw_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
         const int quad = warp & 3, half = (warp - kPwEpi0) >> 2;
         const int et = tid - kPwEpi0 * 32;
         // gLN statistics of this sample (model.py:628-631)
-        const double mean = stat_get(a.gln_sums + (size_t)b * 2) * a.gln_inv_n;
-        double var = stat_get(a.gln_sums + (size_t)b * 2 + 1) * a.gln_inv_n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const double rstd_d = rsqrt(var + (double)a.gln_eps);
-        const float rstd = (float)rstd_d;
-        const float mr = (float)(mean * rstd_d);
+        float rstd = 1.f, mr = 0.f;
+        if (!a.plain) {
+            const double mean = stat_get(a.gln_sums + (size_t)b * 2) * a.gln_inv_n;
+            double var = stat_get(a.gln_sums + (size_t)b * 2 + 1) * a.gln_inv_n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double rstd_d = rsqrt(var + (double)a.gln_eps);
+            rstd = (float)rstd_d;
+            mr = (float)(mean * rstd_d);
+        }
         const int co0 = nh * Nt;
-        for (int i = et; i < Nt; i += kPwEpiThreads) vec[i] = __ldg(a.wbeta + co0 + i) - mr * __ldg(a.wgamma + co0 + i);
+        for (int i = et; i < Nt; i += kPwEpiThreads) vec[i] = a.plain ? 0.f : __ldg(a.wbeta + co0 + i) - mr * __ldg(a.wgamma + co0 + i);
         asm volatile("bar.sync 1, %0;" ::"n"(kPwEpiThreads));
         mbar_wait(bar_done, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -249,8 +253,9 @@ tcn_pw_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
 }
 
 // weight images and bias vectors of all pointwise convs of the TCN: block (unit or vector part, half)
+// transposed: the images of the DATA GRADIENT GEMMs dq = dy W^T (K = the forward's output channels, no gLN factors, no vectors)
 __global__ void __launch_bounds__(256) tcn_wprep_kernel(const TcnPwTable tab, __nv_bfloat16 *wimg, float *wvec, int C, int cpad, int Nt,
-                                                        int nsp) {
+                                                        int nsp, int transposed) {
     const int h = blockIdx.y;
     const float *W = tab.w[h], *gamma = tab.gamma[h], *beta = tab.beta[h];
     const int nunit = C / 16, NH = C / Nt;
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(256) tcn_wprep_kernel(const TcnPwTable tab, __
     if ((int)blockIdx.x < nunit) {
         const int unit = blockIdx.x;
         __shared__ float gm[16];
-        if (threadIdx.x < 16) gm[threadIdx.x] = gamma[unit * 16 + threadIdx.x];
+        if (threadIdx.x < 16) gm[threadIdx.x] = transposed ? 1.f : gamma[unit * 16 + threadIdx.x];
         __syncthreads();
         for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
             const int co = i % C, kg = i / C;
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(256) tcn_wprep_kernel(const TcnPwTable tab, __
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int ci = unit * 16 + kg * 8 + e;
-                const float v = W[(size_t)ci * cpad + co] * gm[kg * 8 + e];
+                const float v = (transposed ? W[(size_t)co * cpad + ci] : W[(size_t)ci * cpad + co]) * gm[kg * 8 + e];
                 hv[e] = bf16_round(v);
                 lv[e] = v - hv[e];
             }
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(256) tcn_wprep_kernel(const TcnPwTable tab, __
     } else {
         // W beta and W gamma: one thread per output channel, fixed summation order
         const int co = (blockIdx.x - nunit) * blockDim.x + threadIdx.x;
-        if (co < C) {
+        if (co < C && !transposed) {
             float sb = 0.f, sg = 0.f;
             for (int ci = 0; ci < C; ++ci) {
                 const float w = W[(size_t)ci * cpad + co];
@@ -824,12 +829,12 @@ int tcn_pw_init() {
     return MISO_OK;
 }
 
-int launch_tcn_wprep(const TcnPwTable &tab, int nconv, int C, int cpad, int split, void *wimg, float *wvec, cudaStream_t stream) {
+int launch_tcn_wprep(const TcnPwTable &tab, int nconv, int C, int cpad, int split, void *wimg, float *wvec, cudaStream_t stream, int transposed) {
     PwGeom g;
     MISO_REQUIRE(make_pw_geom(C, split, g), "tcn_pw: unsupported channel count %d", C);
     MISO_REQUIRE(nconv <= kTcnMaxPw, "tcn_pw: too many pointwise convs (%d)", nconv);
     dim3 grid(g.nunit + (C + 255) / 256, nconv);
-    tcn_wprep_kernel<<<grid, 256, 0, stream>>>(tab, reinterpret_cast<__nv_bfloat16 *>(wimg), wvec, C, cpad, g.Nt, g.nsp);
+    tcn_wprep_kernel<<<grid, 256, 0, stream>>>(tab, reinterpret_cast<__nv_bfloat16 *>(wimg), wvec, C, cpad, g.Nt, g.nsp, transposed);
     MISO_LAUNCHED("tcn_wprep_kernel");
     return MISO_OK;
 }
@@ -874,6 +879,7 @@ int launch_tcn_pw(const TcnPwArgs &p, int split, cudaStream_t stream) {
     k.out_ctot = p.out_ctot;
     k.use_lo = p.use_lo;
     k.out_lo_off = p.out_lo_off;
+    k.plain = p.plain;
     k.B = p.B;
     k.T = p.T;
     k.C = p.C;

@@ -28,6 +28,7 @@ struct TcnPwArgs {
     // out_planes: `out` is a bf16 hi/lo plane buffer [B][hi|lo][out_ctot/8][T][8] (the TCN's last half writes the decoder's input)
     int out_planes, out_ctot, use_lo;
     size_t out_lo_off;
+    int plain;  // no gLN epilogue (rstd 1, no bias, wvec unused): the data gradient dq = dy W^T over transposed images
 };
 
 // The whole TCN as ONE launch (tcn_fused_kernel, tcn.cu): a thread-block cluster per sample (one CTA per 128 frames) walks the
@@ -62,7 +63,8 @@ void tcn_fused_set_trace(long long *d_buf);
 bool tcn_pw_eligible(int C);
 void tcn_pw_scratch_need(int C, int nconv, size_t *wimg_bytes, size_t *wvec_bytes);
 int tcn_pw_init();
-int launch_tcn_wprep(const TcnPwTable &tab, int nconv, int C, int cpad, int split, void *wimg, float *wvec, cudaStream_t stream);
+int launch_tcn_wprep(const TcnPwTable &tab, int nconv, int C, int cpad, int split, void *wimg, float *wvec, cudaStream_t stream,
+                     int transposed = 0);
 int launch_tcn_pw(const TcnPwArgs &p, int split, cudaStream_t stream);
 
 }  // namespace miso
