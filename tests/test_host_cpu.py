@@ -258,3 +258,24 @@ def test_model_defaults_and_invalidate():
     m.eval()
     m.autograd_in_eval = True
     assert m._training_pass()
+
+
+def test_documented_switches_exist_in_the_sources():
+    """Every MISO_* environment switch that INTEGRATION.md / DESIGN.md name is read somewhere in the sources (stale docs
+    after an experiment is removed are the failure this guards against)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = ""
+    for d, _, files in os.walk(os.path.join(root, "misonet_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".py")):
+                src += open(os.path.join(d, f), errors="ignore").read()
+    read = set(re.findall(r'getenv\("(MISO_[A-Z0-9_]+)"\)', src)) | set(re.findall(r'environ[^\n]*"(MISO_[A-Z0-9_]+)"', src))
+    removed = {"MISO_RS_FUSE", "MISO_RS_GROUPKERNEL", "MISO_RS_FORK", "MISO_RS_DBG"}   # named in DESIGN.md as removed experiments
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        text = open(os.path.join(root, doc)).read()
+        for name in set(re.findall(r"`(MISO_[A-Z0-9_]+)(?:=[^`]*)?`", text)):
+            if (name.startswith("MISO_E_") or name.startswith("MISO_PROF") or name in removed or name == "MISO_OK"
+                    or re.fullmatch(r"MISO_\d", name)):     # MISO_1 / MISO_3 are classes of the reference
+                continue
+            assert name in read, f"{doc} names {name}, which no source file reads"
